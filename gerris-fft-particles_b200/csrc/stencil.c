@@ -1,0 +1,473 @@
+/* stencil.c -- corner-interpolator stencils on the flat tree, deduplicated
+ * into a per-vertex table.
+ *
+ * gfs_interpolate (src/fluid.c:2697-2710) rebuilds, for every call, the
+ * inverse-distance stencil of each of the 2^dim corners of the containing
+ * cell (gfs_cell_corner_interpolator, src/fluid.c:3015-3069).  Those stencils
+ * depend on the tree topology only -- not on the particle, not on the field --
+ * so here they are built once per adapt, on the host, by the same
+ * depth-first walk over the cells sharing the vertex (including T-junction
+ * averaging and the domain-corner rule), and stored as (cell, weight) lists.
+ * Leaves sharing a vertex share one list when the lists agree as sets, which
+ * shrinks the table 2^dim-fold on regular regions; the device then only
+ * evaluates sum(w_i * v_i) once per vertex per field update.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include "gfsb200_internal.h"
+
+typedef struct {
+  int n;
+  int32_t c[GFSB200_MAX_STENCIL];
+  double w[GFSB200_MAX_STENCIL];
+} interp_t;
+
+/* corner k -> its dim face directions, in the order of the reference's
+ * corner[] table (src/fluid.c:2588-2606): x, y, z */
+static const int corner_dir[2][8][3] = {
+  { {1,3,0}, {0,3,0}, {0,2,0}, {1,2,0} },
+  { {1,3,4}, {0,3,4}, {0,2,4}, {1,2,4}, {1,3,5}, {0,3,5}, {0,2,5}, {1,2,5} }
+};
+
+/* Depth-first order in which the 2^dim cells around a vertex are visited
+ * (do_path, src/fluid.c:2925-2981).  Slot s holds the cell reached from slot 0
+ * by crossing the faces whose bits are set in s; from slot s, try j crosses
+ * face walk[s][j][0] first and passes the remaining positions in the listed
+ * order.  Entries are positions in the corner's direction array, and the sign
+ * of each direction follows from the slot (set bit = already crossed = go
+ * back), so only the permutations are tabulated. */
+static const unsigned char walk3[8][3][3] = {
+  { {0,1,2}, {1,0,2}, {2,0,1} },
+  { {1,2,0}, {2,1,0}, {0,1,2} },
+  { {0,1,2}, {2,1,0}, {1,2,0} },
+  { {2,0,1}, {1,0,2}, {0,1,2} },
+  { {1,0,2}, {0,1,2}, {2,0,1} },
+  { {1,0,2}, {0,1,2}, {2,1,0} },
+  { {0,1,2}, {1,0,2}, {2,0,1} },
+  { {0,1,2}, {1,0,2}, {2,0,1} }
+};
+static const unsigned char walk2[4][2][2] = {
+  { {0,1}, {1,0} },
+  { {1,0}, {0,1} },
+  { {0,1}, {1,0} },
+  { {0,1}, {1,0} }
+};
+
+static inline int child_positive (int n, int axis)
+{
+  return axis == 0 ? (n & 1) : !((n >> axis) & 1);
+}
+
+/* ftt_cell_child_corner, src/ftt.h:366-422 */
+static int32_t child_corner (const gfsb200_tree * t, int32_t cell, const int * d)
+{
+  int n = 0;
+  for (int l = 0; l < t->dim; l++) {
+    int axis = d[l] >> 1, positive = !(d[l] & 1);
+    if (axis == 0) n |= positive ? 1 : 0;
+    else n |= positive ? 0 : (1 << axis);
+  }
+  int32_t c = t->child0[cell] + n;
+  return (t->flags[c] & GFSB200_CELL_DESTROYED) ? -1 : c;
+}
+
+/* ftt_cell_neighbor_is_brother, src/ftt.h:620-638 */
+static int neighbor_is_brother (const gfsb200_tree * t, int32_t cell, int d)
+{
+  int32_t p = t->parent[cell];
+  if (p < 0) return 0;
+  int n = cell - t->child0[p];
+  return child_positive (n, d >> 1) != !(d & 1);
+}
+
+/* cell_corner_neighbor, src/fluid.c:2813-2846 (max_level = -1) */
+static int32_t corner_neighbor (const gfsb200_tree * t, int32_t cell, const int * d, int * t_junction)
+{
+  int32_t nb = t->neighbor[(int64_t) cell*t->ndir + d[0]];
+  if (nb < 0)
+    return -1;
+  if (t->level[nb] < t->level[cell]) {
+    /* shallower neighbour */
+    if (child_corner (t, t->parent[cell], d) != cell)
+      *t_junction = 1;
+    return nb;
+  }
+  if (t->child0[nb] < 0)
+    return nb;
+  /* deeper: the neighbour's child touching the vertex */
+  int d1[3];
+  d1[0] = d[0] ^ 1;
+  for (int l = 1; l < t->dim; l++) d1[l] = d[l];
+  int32_t n = child_corner (t, nb, d1);
+  return n >= 0 ? n : nb;
+}
+
+/* interpolator_merge / interpolator_scale, src/fluid.c:2848-2877 */
+static void merge (interp_t * a, const interp_t * b)
+{
+  for (int i = 0; i < b->n; i++) {
+    int j;
+    for (j = 0; j < a->n && b->c[i] != a->c[j]; j++)
+      ;
+    if (j < a->n)
+      a->w[j] += b->w[i];
+    else if (j < GFSB200_MAX_STENCIL) {
+      a->c[j] = b->c[i];
+      a->w[j] = b->w[i];
+      a->n++;
+    }
+  }
+}
+
+static void scale (interp_t * a, double b)
+{
+  for (int i = 0; i < a->n; i++)
+    a->w[i] *= b;
+}
+
+static void corner_interp (const gfsb200_tree * t, int32_t cell, const int * d, interp_t * inter);
+
+/* t_junction_interpolator, src/fluid.c:2879-2923 */
+static void t_junction (const gfsb200_tree * t, int32_t cell, const int * d, int32_t n,
+			interp_t * inter)
+{
+  int d1[3];
+  interp_t a;
+  d1[0] = d[0] ^ 1;
+  if (t->dim == 2) {
+    d1[1] = d[1];
+    corner_interp (t, n, d1, inter);
+    d1[1] = d[1] ^ 1;
+    corner_interp (t, n, d1, &a);
+    merge (inter, &a);
+    scale (inter, 0.5);
+    return;
+  }
+  d1[1] = d[1]; d1[2] = d[2];
+  corner_interp (t, n, d1, inter);
+  if (neighbor_is_brother (t, cell, d[1])) {
+    d1[1] = d[1] ^ 1;
+    corner_interp (t, n, d1, &a);
+    merge (inter, &a);
+    if (neighbor_is_brother (t, cell, d[2])) {
+      d1[2] = d[2] ^ 1;
+      corner_interp (t, n, d1, &a);
+      merge (inter, &a);
+      d1[1] = d[1];
+      corner_interp (t, n, d1, &a);
+      merge (inter, &a);
+      scale (inter, 0.25);
+    }
+    else
+      scale (inter, 0.5);
+  }
+  else {
+    d1[2] = d[2] ^ 1;
+    corner_interp (t, n, d1, &a);
+    merge (inter, &a);
+    scale (inter, 0.5);
+  }
+}
+
+/* do_path, src/fluid.c:2925-2981 */
+static int do_path (const gfsb200_tree * t, int32_t cell, int slot, int32_t * n, const int * d,
+		    interp_t * inter)
+{
+  for (int j = 0; j < t->dim; j++) {
+    const unsigned char * w = t->dim == 3 ? walk3[slot][j] : walk2[slot][j];
+    int k = slot ^ (1 << w[0]);
+    if (n[k] < 0) {
+      int tj = 0, d1[3];
+      for (int l = 0; l < t->dim; l++)
+	d1[l] = (slot >> w[l]) & 1 ? d[w[l]] ^ 1 : d[w[l]];
+      n[k] = corner_neighbor (t, cell, d1, &tj);
+      if (tj) {
+	t_junction (t, cell, d1, n[k], inter);
+	return 1;
+      }
+      if (n[k] >= 0 && do_path (t, n[k], k, n, d, inter))
+	return 1;
+    }
+  }
+  return 0;
+}
+
+/* gfs_cell_corner_interpolator, src/fluid.c:3015-3069, for non-centred
+ * variables on a tree without solid (mixed) cells */
+static void corner_interp (const gfsb200_tree * t, int32_t cell, const int * d, interp_t * inter)
+{
+  int32_t n[8], c;
+  int ncells = t->nchild;
+  while (t->child0[cell] >= 0 && (c = child_corner (t, cell, d)) >= 0)
+    cell = c;
+  n[0] = cell;
+  for (int i = 1; i < ncells; i++)
+    n[i] = -1;
+  if (do_path (t, cell, 0, n, d, inter))
+    return;
+
+  double w = 0.;
+  int boundaries = 0;
+  const double diag = t->dim == 3 ? 0.866025403785 : 0.707106781185;  /* distance(), :2983-2992 */
+  inter->n = 0;
+  for (int i = 0; i < ncells; i++)
+    if (n[i] >= 0) {
+      double size = ldexp (1., -t->level[n[i]]);
+      double a = 1./(size*diag + 1e-12);
+      inter->c[inter->n] = n[i];
+      inter->w[inter->n++] = a;
+      w += a;
+      if (t->flags[n[i]] & GFSB200_CELL_BOUNDARY)
+	boundaries++;
+    }
+  /* corners of the domain: drop the central cell (:3056-3065) */
+  if (inter->n == t->dim + 1 && boundaries == t->dim) {
+    w -= inter->w[0];
+    for (int i = 0; i < inter->n - 1; i++) {
+      inter->c[i] = inter->c[i + 1];
+      inter->w[i] = inter->w[i + 1];
+    }
+    inter->n--;
+  }
+  scale (inter, 1./w);
+}
+
+int gfsb200_tree_corner_interpolator (const gfsb200_tree * t, int cell, int k,
+				      int32_t * cells, double * w)
+{
+  if (!t || !t->finalized)
+    return gfsb200_fail (GFSB200_ERR_STATE, "corner_interpolator: tree not finalized");
+  if (cell < 0 || cell >= t->n_cells || k < 0 || k >= t->nchild ||
+      (t->flags[cell] & GFSB200_CELL_DESTROYED))
+    return gfsb200_fail (GFSB200_ERR_ARG, "corner_interpolator: bad cell/corner");
+  interp_t inter;
+  corner_interp (t, cell, corner_dir[t->dim - 2][k], &inter);
+  for (int i = 0; i < inter.n; i++) {
+    cells[i] = inter.c[i];
+    w[i] = inter.w[i];
+  }
+  return inter.n;
+}
+
+/* ------------------------------------------------------------------ */
+/* vertex deduplication                                                 */
+
+static inline uint64_t mix64 (uint64_t x)
+{
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
+  x ^= x >> 27; x *= 0x94d049bb133111ebULL;
+  x ^= x >> 31;
+  return x;
+}
+
+/* order-independent signature of a stencil: hash of the (cell, weight) pairs
+ * sorted by cell */
+static void signature (const interp_t * in, uint64_t * h1, uint64_t * h2)
+{
+  int idx[GFSB200_MAX_STENCIL];
+  for (int i = 0; i < in->n; i++) {
+    int j = i;
+    while (j > 0 && in->c[idx[j - 1]] > in->c[i]) {
+      idx[j] = idx[j - 1];
+      j--;
+    }
+    idx[j] = i;
+  }
+  uint64_t a = 0x9e3779b97f4a7c15ULL + (uint64_t) in->n, b = 0xc2b2ae3d27d4eb4fULL;
+  for (int i = 0; i < in->n; i++) {
+    uint64_t wb;
+    memcpy (&wb, &in->w[idx[i]], 8);
+    a = mix64 (a ^ (uint64_t) (uint32_t) in->c[idx[i]]);
+    a = mix64 (a ^ wb);
+    b = mix64 (b + wb*0x2545f4914f6cdd1dULL + (uint64_t) (uint32_t) in->c[idx[i]]);
+  }
+  *h1 = a; *h2 = b;
+}
+
+typedef struct {
+  int64_t k[3];
+  uint64_t h1, h2;
+  int32_t vid;       /* -1 = empty */
+  int32_t rep;       /* canonical cell*nchild + corner */
+} vslot_t;
+
+typedef struct {
+  vslot_t * s;
+  uint64_t mask;
+  int64_t used;
+} vtable_t;
+
+static int vtable_init (vtable_t * v, uint64_t cap)
+{
+  uint64_t c = 1024;
+  while (c < cap) c <<= 1;
+  v->s = malloc (c*sizeof (vslot_t));
+  if (!v->s) return -1;
+  for (uint64_t i = 0; i < c; i++) v->s[i].vid = -1;
+  v->mask = c - 1;
+  v->used = 0;
+  return 0;
+}
+
+static inline uint64_t vhash (const int64_t k[3], uint64_t h1)
+{
+  return mix64 ((uint64_t) k[0]*0x9e3779b97f4a7c15ULL ^ mix64 ((uint64_t) k[1] + 0x632be59bd9b4e019ULL) ^
+		mix64 ((uint64_t) k[2]*0xd6e8feb86659fd93ULL + 7) ^ h1);
+}
+
+static vslot_t * vtable_find (vtable_t * v, const int64_t k[3], uint64_t h1, uint64_t h2)
+{
+  uint64_t i = vhash (k, h1) & v->mask;
+  for (;;) {
+    vslot_t * s = &v->s[i];
+    if (s->vid < 0 ||
+	(s->k[0] == k[0] && s->k[1] == k[1] && s->k[2] == k[2] && s->h1 == h1 && s->h2 == h2))
+      return s;
+    i = (i + 1) & v->mask;
+  }
+}
+
+static int vtable_grow (vtable_t * v)
+{
+  vtable_t n;
+  if (vtable_init (&n, (v->mask + 1)*2))
+    return -1;
+  for (uint64_t i = 0; i <= v->mask; i++)
+    if (v->s[i].vid >= 0) {
+      vslot_t * s = vtable_find (&n, v->s[i].k, v->s[i].h1, v->s[i].h2);
+      *s = v->s[i];
+    }
+  n.used = v->used;
+  free (v->s);
+  *v = n;
+  return 0;
+}
+
+int gfsb200_tree_build_stencils (gfsb200_tree * t)
+{
+  if (!t || !t->finalized)
+    return gfsb200_fail (GFSB200_ERR_STATE, "build_stencils: tree not finalized");
+  free (t->vtx_off); free (t->vtx_cell); free (t->vtx_w); free (t->leaf_vtx);
+  t->vtx_off = NULL; t->vtx_cell = NULL; t->vtx_w = NULL; t->leaf_vtx = NULL;
+  t->n_vertices = 0;
+
+  const int nc = t->nchild;
+  const int32_t n = t->n_cells;
+  const int (* cd)[3] = corner_dir[t->dim - 2];
+  uint64_t * sig = malloc ((size_t) n*nc*2*sizeof (uint64_t));
+  t->leaf_vtx = malloc ((size_t) n*nc*sizeof (int32_t));
+  if (!sig || !t->leaf_vtx) {
+    free (sig);
+    return gfsb200_fail (GFSB200_ERR_NOMEM, "build_stencils: out of memory");
+  }
+
+  /* pass A: signature of every (box leaf, corner) stencil */
+#pragma omp parallel for schedule(dynamic, 4096)
+  for (int32_t i = 0; i < n; i++) {
+    int box_leaf = (t->flags[i] & (GFSB200_CELL_LEAF | GFSB200_CELL_BOUNDARY)) == GFSB200_CELL_LEAF;
+    for (int k = 0; k < nc; k++) {
+      t->leaf_vtx[(int64_t) i*nc + k] = -1;
+      if (box_leaf) {
+	interp_t inter;
+	corner_interp (t, i, cd[k], &inter);
+	signature (&inter, &sig[((int64_t) i*nc + k)*2], &sig[((int64_t) i*nc + k)*2 + 1]);
+      }
+    }
+  }
+
+  /* pass B: group by (vertex position, signature); ids in first-seen order */
+  vtable_t vt;
+  if (vtable_init (&vt, (uint64_t) (t->n_leaves*2 + 1024))) {
+    free (sig);
+    return gfsb200_fail (GFSB200_ERR_NOMEM, "build_stencils: out of memory");
+  }
+  const double lattice = ldexp (1., GFSB200_MAX_LEVEL + 2);
+  int32_t nv = 0;
+  int32_t * rep = NULL;
+  int64_t rep_cap = 0;
+  for (int32_t i = 0; i < n; i++) {
+    if ((t->flags[i] & (GFSB200_CELL_LEAF | GFSB200_CELL_BOUNDARY)) != GFSB200_CELL_LEAF)
+      continue;
+    double half = ldexp (1., -t->level[i])/2.;
+    for (int k = 0; k < nc; k++) {
+      int64_t key[3] = { 0, 0, 0 };
+      for (int l = 0; l < t->dim; l++) {
+	int d = cd[k][l];
+	double p = t->pos[3*i + (d >> 1)] + (d & 1 ? -half : half);
+	key[d >> 1] = (int64_t) llround (p*lattice);
+      }
+      int64_t e = (int64_t) i*nc + k;
+      if ((vt.used + 1)*10 > (int64_t) (vt.mask + 1)*6 && vtable_grow (&vt)) {
+	free (sig); free (vt.s); free (rep);
+	return gfsb200_fail (GFSB200_ERR_NOMEM, "build_stencils: out of memory");
+      }
+      vslot_t * s = vtable_find (&vt, key, sig[2*e], sig[2*e + 1]);
+      if (s->vid < 0) {
+	s->k[0] = key[0]; s->k[1] = key[1]; s->k[2] = key[2];
+	s->h1 = sig[2*e]; s->h2 = sig[2*e + 1];
+	s->vid = nv;
+	s->rep = (int32_t) 0;
+	if (nv >= rep_cap) {
+	  rep_cap = rep_cap ? rep_cap*2 : 1 << 16;
+	  int32_t * r2 = realloc (rep, (size_t) rep_cap*2*sizeof (int32_t));
+	  if (!r2) {
+	    free (sig); free (vt.s); free (rep);
+	    return gfsb200_fail (GFSB200_ERR_NOMEM, "build_stencils: out of memory");
+	  }
+	  rep = r2;
+	}
+	rep[2*nv] = i; rep[2*nv + 1] = k;
+	vt.used++;
+	nv++;
+      }
+      t->leaf_vtx[e] = s->vid;
+    }
+  }
+  free (sig);
+  free (vt.s);
+
+  /* pass C: CSR of the canonical stencils */
+  t->vtx_off = malloc ((size_t) (nv + 1)*sizeof (int32_t));
+  if (!t->vtx_off) {
+    free (rep);
+    return gfsb200_fail (GFSB200_ERR_NOMEM, "build_stencils: out of memory");
+  }
+  t->vtx_off[0] = 0;
+#pragma omp parallel for schedule(dynamic, 4096)
+  for (int32_t v = 0; v < nv; v++) {
+    interp_t inter;
+    corner_interp (t, rep[2*v], cd[rep[2*v + 1]], &inter);
+    t->vtx_off[v + 1] = inter.n;
+  }
+  int64_t total = 0;
+  for (int32_t v = 0; v < nv; v++) {
+    int32_t c = t->vtx_off[v + 1];
+    t->vtx_off[v] = (int32_t) total;
+    total += c;
+    if (total > INT32_MAX) {
+      free (rep);
+      return gfsb200_fail (GFSB200_ERR_UNSUPPORTED, "build_stencils: stencil table too large");
+    }
+  }
+  t->vtx_off[nv] = (int32_t) total;
+  t->vtx_cell = malloc ((size_t) (total ? total : 1)*sizeof (int32_t));
+  t->vtx_w = malloc ((size_t) (total ? total : 1)*sizeof (double));
+  if (!t->vtx_cell || !t->vtx_w) {
+    free (rep);
+    return gfsb200_fail (GFSB200_ERR_NOMEM, "build_stencils: out of memory");
+  }
+#pragma omp parallel for schedule(dynamic, 4096)
+  for (int32_t v = 0; v < nv; v++) {
+    interp_t inter;
+    corner_interp (t, rep[2*v], cd[rep[2*v + 1]], &inter);
+    int32_t o = t->vtx_off[v];
+    for (int i = 0; i < inter.n; i++) {
+      t->vtx_cell[o + i] = inter.c[i];
+      t->vtx_w[o + i] = inter.w[i];
+    }
+  }
+  free (rep);
+  t->n_vertices = nv;
+  return GFSB200_OK;
+}

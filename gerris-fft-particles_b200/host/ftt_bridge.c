@@ -1,0 +1,157 @@
+/* ftt_bridge.c -- the FTT flattening pass: mirrors a live Gerris FttCell
+ * pointer tree (src/ftt.h:134-159) into a gfsb200 flat tree, and gathers /
+ * scatters cell variables between the two.
+ *
+ * Compiled once per dimension (-DFTT_2D=1 or not) against the Gerris headers,
+ * exactly like the reference builds libparticulates2D/3D
+ * (modules/Makefile.am:154-164).  Only struct members and inline helpers of
+ * ftt.h are used, so the object has no unresolved libgfs symbols and can sit
+ * inside the drop-in module or be loaded on its own.
+ *
+ * Called after every mesh adaptation (gfs_simulation_adapt, src/adaptive.c:1445)
+ * and never on the per-step path; the per-step work is the value gather only.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include "ftt.h"
+#include "gfsb200.h"
+#include "gfsb200_ftt.h"
+
+/* GFS_FLAG_BOUNDARY (src/fluid.h:63): ghost cells of a GfsBoundary tree */
+#define BRIDGE_FLAG_BOUNDARY (1u << (FTT_FLAG_USER + 1))
+
+struct gfsb200_ftt_map {
+  int32_t n_cells;
+  FttCell ** cell;            /* flat index -> FttCell */
+};
+
+static const char * bridge_error = "";
+const char * gfsb200_ftt_last_error (void) { return bridge_error; }
+
+void gfsb200_ftt_map_free (gfsb200_ftt_map * m)
+{
+  if (!m) return;
+  free (m->cell);
+  free (m);
+}
+
+int32_t gfsb200_ftt_map_size (const gfsb200_ftt_map * m) { return m->n_cells; }
+void * gfsb200_ftt_map_cell (const gfsb200_ftt_map * m, int32_t i) { return m->cell[i]; }
+void * const * gfsb200_ftt_map_cells (const gfsb200_ftt_map * m) { return (void * const *) m->cell; }
+
+int gfsb200_ftt_flatten (int n_roots, void * const * roots_, const int * is_box,
+			 gfsb200_tree ** tree_out, gfsb200_ftt_map ** map_out)
+{
+  FttCell * const * roots = (FttCell * const *) roots_;
+  if (n_roots <= 0 || !roots || !is_box || !tree_out || !map_out) {
+    bridge_error = "flatten: bad argument";
+    return GFSB200_ERR_ARG;
+  }
+  gfsb200_tree * t = gfsb200_tree_new (FTT_DIMENSION);
+  if (!t) { bridge_error = gfsb200_last_error (); return GFSB200_ERR_NOMEM; }
+
+  /* roots: GfsBox roots first (caller's order within each class is kept) */
+  int * order = malloc (sizeof (int)*n_roots);
+  int no = 0;
+  for (int pass = 1; pass >= 0; pass--)
+    for (int r = 0; r < n_roots; r++)
+      if ((is_box[r] != 0) == pass)
+	order[no++] = r;
+
+  size_t cap = 1024, n = 0;
+  FttCell ** cells = malloc (cap*sizeof (FttCell *));
+  int rc = GFSB200_OK;
+  for (int j = 0; j < n_roots && rc >= 0; j++) {
+    FttCell * root = roots[order[j]];
+    if (!root || !FTT_CELL_IS_ROOT (root)) {
+      bridge_error = "flatten: not a root cell";
+      rc = GFSB200_ERR_ARG;
+      break;
+    }
+    double pos[3] = { FTT_ROOT_CELL (root)->pos.x, FTT_ROOT_CELL (root)->pos.y,
+		      FTT_ROOT_CELL (root)->pos.z };
+    rc = gfsb200_tree_add_root (t, pos, FTT_ROOT_CELL (root)->level, is_box[order[j]]);
+    cells[n++] = root;
+  }
+  /* root adjacency (FttRootCell.neighbors, src/ftt.h:142-149) */
+  for (int j = 0; j < n_roots && rc >= 0; j++)
+    for (int d = 0; d < FTT_NEIGHBORS; d++) {
+      FttCell * nb = FTT_ROOT_CELL (cells[j])->neighbors.c[d];
+      if (nb)
+	for (int k = 0; k < n_roots; k++)
+	  if (cells[k] == nb)
+	    rc = gfsb200_tree_link_roots (t, j, d, k);
+    }
+  /* breadth-first mirror: cells[] doubles as the queue; a split appends the
+     2^dim children in FTT child order, destroyed ones included, so growth
+     order == flat order and the map needs no permutation */
+  for (size_t head = 0; head < n && rc >= 0; head++) {
+    FttCell * c = cells[head];
+    if (FTT_CELL_IS_DESTROYED (c) || FTT_CELL_IS_LEAF (c))
+      continue;
+    struct _FttOct * oct = c->children;
+    unsigned destroyed = 0, flags = 0;
+    for (int k = 0; k < FTT_CELLS; k++) {
+      if (FTT_CELL_IS_DESTROYED (&oct->cell[k]))
+	destroyed |= 1u << k;
+      if (oct->cell[k].flags & BRIDGE_FLAG_BOUNDARY)
+	flags |= GFSB200_CELL_BOUNDARY;
+    }
+    int c0 = gfsb200_tree_split (t, (int) head, destroyed, flags);
+    if (c0 < 0) { rc = c0; break; }
+    if ((size_t) c0 != n) { bridge_error = "flatten: internal order error"; rc = GFSB200_ERR_STATE; break; }
+    if (n + FTT_CELLS > cap) {
+      cap *= 2;
+      cells = realloc (cells, cap*sizeof (FttCell *));
+    }
+    for (int k = 0; k < FTT_CELLS; k++)
+      cells[n++] = &oct->cell[k];
+  }
+  free (order);
+  if (rc >= 0) {
+    int32_t * perm = malloc (n*sizeof (int32_t));
+    rc = gfsb200_tree_finalize (t, perm);
+    if (rc >= 0)
+      for (size_t i = 0; i < n; i++)
+	if ((size_t) perm[i] != i) { bridge_error = "flatten: finalize permuted cells"; rc = GFSB200_ERR_STATE; break; }
+    free (perm);
+  }
+  if (rc < 0) {
+    if (!*bridge_error) bridge_error = gfsb200_last_error ();
+    gfsb200_tree_free (t);
+    free (cells);
+    return rc;
+  }
+  gfsb200_ftt_map * m = malloc (sizeof *m);
+  m->n_cells = (int32_t) n;
+  m->cell = cells;
+  *tree_out = t;
+  *map_out = m;
+  return GFSB200_OK;
+}
+
+/* GFS_VALUEI (cell, i) = (&GFS_STATE (cell)->place_holder)[i]  (src/fluid.h:71-72).
+ * `offset` is the byte offset of place_holder inside the cell's data block
+ * (offsetof (GfsStateVector, place_holder)), passed in so that this file does
+ * not need fluid.h/gts.h. */
+int gfsb200_ftt_gather (const gfsb200_ftt_map * m, size_t offset, int var, double nodata, double * out)
+{
+  for (int32_t i = 0; i < m->n_cells; i++) {
+    FttCell * c = m->cell[i];
+    out[i] = (FTT_CELL_IS_DESTROYED (c) || !c->data) ? nodata :
+      ((const double *) ((const char *) c->data + offset))[var];
+  }
+  return GFSB200_OK;
+}
+
+int gfsb200_ftt_scatter (const gfsb200_ftt_map * m, size_t offset, int var, int leaves_only,
+			 const double * in)
+{
+  for (int32_t i = 0; i < m->n_cells; i++) {
+    FttCell * c = m->cell[i];
+    if (FTT_CELL_IS_DESTROYED (c) || !c->data || (leaves_only && !FTT_CELL_IS_LEAF (c)))
+      continue;
+    ((double *) ((char *) c->data + offset))[var] = in[i];
+  }
+  return GFSB200_OK;
+}

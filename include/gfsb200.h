@@ -1,0 +1,252 @@
+/* gfsb200.h -- C-ABI of the B200-native Gerris particulate hot path.
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, int status
+ * codes, no GLib/GTS and no torch types.  A replacement
+ * libparticulates{2D,3D}.so (see INTEGRATION.md and
+ * gerris-fft-particles_b200/host/particulates_b200.c) keeps the reference's
+ * GtsObject classes and .gfs syntax and calls down into these entry points
+ * from the same places the reference does its per-particle CPU work.
+ *
+ * Reference interfaces replaced (paths relative to the reference tree):
+ *   tree flattening      FttCell/FttOct pointer tree        src/ftt.h:134-159
+ *   point location       gfs_domain_locate                  src/domain.c:2623-2638
+ *                        ftt_cell_locate                    src/ftt.c:1535-1574
+ *                        GfsLocateArray                     src/domain.c:43-145
+ *   interpolation        gfs_interpolate                    src/fluid.c:2697-2710
+ *                        gfs_cell_corner_interpolator       src/fluid.c:3015-3069
+ *   vorticity            vorticity_vector                   modules/particulatecommon.c:142-164
+ *                        gfs_center_gradient                src/fluid.c:434-475
+ *   forces               compute_{drag,lift,buoyancy}_force modules/particulatecommon.c:423-655
+ *   integrator           gfs_particulate_event              modules/particulatecommon.c:768-842
+ *   list driver          gfs_particle_list_event            modules/particulatecommon.c:980-1015
+ *   deposition           particulate_field_event            modules/particulatecommon.c:1934-1957
+ *                        source_particulate_event (NGP)     modules/particulatecommon.c:2177-2228
+ *   tracer advection     gfs_domain_advect_point            src/domain.c:2764-2788
+ *
+ * All functions returning int return GFSB200_OK (0) or a negative error code;
+ * gfsb200_last_error() gives the message of the last failure on the calling
+ * thread.  There is no CPU fallback: every compute entry point fails with
+ * GFSB200_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef GFSB200_H
+#define GFSB200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GFSB200_OK             0
+#define GFSB200_ERR_ARG       -1
+#define GFSB200_ERR_STATE     -2
+#define GFSB200_ERR_NOMEM     -3
+#define GFSB200_ERR_CUDA      -4
+#define GFSB200_ERR_UNSUPPORTED -5
+
+/* cell flags (flat tree) */
+#define GFSB200_CELL_DESTROYED 1u   /* FTT_FLAG_DESTROYED   src/ftt.h:113-118 */
+#define GFSB200_CELL_BOUNDARY  2u   /* GFS_FLAG_BOUNDARY    src/fluid.h:63   */
+#define GFSB200_CELL_LEAF      4u   /* FTT_CELL_IS_LEAF and not destroyed   */
+
+/* force kinds, in GfsParticleList force-list order */
+#define GFSB200_FORCE_DRAG 1        /* GfsForceDrag */
+#define GFSB200_FORCE_LIFT 2        /* GfsForceLift */
+#define GFSB200_FORCE_BUOY 3        /* GfsForceBuoy */
+#define GFSB200_MAX_FORCES 8
+
+const char * gfsb200_last_error (void);
+const char * gfsb200_version (void);
+
+/* ------------------------------------------------------------------------
+ * Flat tree (host side).  A level-ordered array of cells: all root cells
+ * first (GfsBox roots before GfsBoundary roots), then every deeper level in
+ * turn; the 2^dim children of a cell are contiguous, in FTT child order
+ * (src/ftt.c:301-316), and sibling groups follow their parents' order, so
+ * within a level cells are keyed by the Morton path from their root.
+ * ------------------------------------------------------------------------ */
+typedef struct gfsb200_tree gfsb200_tree;
+
+gfsb200_tree * gfsb200_tree_new (int dim);
+void gfsb200_tree_free (gfsb200_tree * t);
+
+/* Roots must all be added before any split.  pos = centre of the root cell,
+ * level = its FTT level (GfsDomain.rootlevel), is_box = 1 for a GfsBox root,
+ * 0 for a GfsBoundary (ghost) root.  Returns the root index (= cell index). */
+int gfsb200_tree_add_root (gfsb200_tree * t, const double pos[3], int level, int is_box);
+/* root r0's neighbour in direction d is root r1 (and vice versa) */
+int gfsb200_tree_link_roots (gfsb200_tree * t, int r0, int d, int r1);
+
+/* Raw split: gives `cell` 2^dim children; bit n of destroyed_mask marks child
+ * n destroyed, `child_flags` is OR-ed into every child.  No 2:1 balancing
+ * (used when mirroring an existing FTT tree).  Returns index of child 0. */
+int gfsb200_tree_split (gfsb200_tree * t, int cell, unsigned destroyed_mask, unsigned child_flags);
+/* Split with the face 2:1 rule of oct_new(check_neighbors), src/ftt.c:45-84 */
+int gfsb200_tree_refine_cell (gfsb200_tree * t, int cell);
+
+/* Native world builders (single unit GfsBox at the origin unless roots were
+ * added by hand); semantics of ftt_cell_refine, src/ftt.c:169-192. */
+typedef int (* gfsb200_refine_func) (const double pos[3], int level, double h, void * data);
+int gfsb200_tree_refine (gfsb200_tree * t, gfsb200_refine_func f, void * data);
+int gfsb200_tree_refine_uniform (gfsb200_tree * t, int level);
+/* refine while level < minlevel, or level < maxlevel and the distance from the
+ * cell centre to the circle of radius R (plane z = 0) is < factor*h */
+int gfsb200_tree_refine_ring (gfsb200_tree * t, int minlevel, int maxlevel, double R, double factor);
+/* the corner-balance sweep of gfs_simulation_refine, src/simulation.c:1226-1231 */
+int gfsb200_tree_corner_sweep (gfsb200_tree * t);
+/* ghost-cell tree on side `side` of box root `box_root`, mirroring
+ * boundary_match, src/boundary.c:652-685; call after all refinement */
+int gfsb200_tree_add_boundary (gfsb200_tree * t, int box_root, int side);
+
+/* Reorders to level order, builds neighbour tables, centres, locate array.
+ * perm (may be NULL, else n_cells ints) receives old index -> new index. */
+int gfsb200_tree_finalize (gfsb200_tree * t, int32_t * perm);
+/* Corner-interpolator stencils for every (leaf, corner), deduplicated into a
+ * vertex table (requires finalize). */
+int gfsb200_tree_build_stencils (gfsb200_tree * t);
+
+/* read-only views of a finalized tree (pointers owned by the tree) */
+typedef struct {
+  int32_t dim, n_cells, n_roots, n_box_roots;
+  int32_t min_level, max_level;       /* absolute FTT levels present */
+  int32_t complete_level;             /* deepest absolute level to which every GfsBox tree is
+					 fully refined (>= min_level) */
+  int64_t n_leaves;                   /* non-ghost leaves */
+  const int32_t * level_start;        /* [max_level - min_level + 2] */
+  const int32_t * parent;             /* [n_cells], -1 for roots */
+  const int32_t * child0;             /* [n_cells], -1 for leaves */
+  const int32_t * neighbor;           /* [n_cells][2*dim], ftt_cell_neighbor semantics, -1 = NULL */
+  const uint8_t * level;              /* [n_cells] absolute level */
+  const uint8_t * flags;              /* [n_cells] GFSB200_CELL_* */
+  const double  * pos;                /* [n_cells][3] exact centres */
+  /* GfsLocateArray */
+  double la_min[3], la_h;
+  int32_t la_n[3];
+  const int32_t * la_slot;            /* [la_n product] GfsBox root cell or -1 */
+  /* stencils (NULL / 0 until build_stencils) */
+  int32_t n_vertices;
+  const int32_t * vtx_off;            /* [n_vertices + 1] CSR offsets */
+  const int32_t * vtx_cell;           /* stencil cells, reference slot order of the canonical corner */
+  const double  * vtx_w;              /* normalised weights */
+  const int32_t * leaf_vtx;           /* [n_cells][2^dim] vertex id per corner (reference corner
+					 order, src/fluid.c:2588-2606), -1 for non-leaves */
+} gfsb200_tree_view;
+
+int gfsb200_tree_get_view (const gfsb200_tree * t, gfsb200_tree_view * v);
+/* the (cell, weight) list of gfs_cell_corner_interpolator (cell, corner k),
+ * in reference order; cells/w need 29 entries.  Returns count or <0. */
+int gfsb200_tree_corner_interpolator (const gfsb200_tree * t, int cell, int k,
+				      int32_t * cells, double * w);
+
+/* ------------------------------------------------------------------------
+ * Device context.  One per GPU / per process rank.
+ * ------------------------------------------------------------------------ */
+typedef struct gfsb200_ctx gfsb200_ctx;
+
+int gfsb200_ctx_create (int device, gfsb200_ctx ** out);
+void gfsb200_ctx_destroy (gfsb200_ctx * c);
+/* the CUDA stream all of this context's work is issued on (cudaStream_t) */
+void * gfsb200_ctx_stream (gfsb200_ctx * c);
+int gfsb200_ctx_synchronize (gfsb200_ctx * c);
+
+/* Upload the flattened tree + stencil tables; call again after each adapt. */
+int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t);
+
+/* Mirror the cell variables (host arrays of n_cells doubles, flat-tree order;
+ * w = NULL in 2D; alpha/mu = NULL for constants) and rebuild the per-vertex
+ * velocity table and the per-leaf vorticity table on the device. */
+int gfsb200_upload_field (gfsb200_ctx * c, const double * u, const double * v, const double * w,
+			  const double * alpha, const double * mu);
+/* same, from device pointers */
+int gfsb200_set_field_device (gfsb200_ctx * c, const double * u, const double * v, const double * w,
+			      const double * alpha, const double * mu);
+/* recompute vertex + vorticity tables from the resident field (the per-step
+ * cell pass) */
+int gfsb200_refresh_field (gfsb200_ctx * c);
+/* device -> host copies of derived tables, for parity tests */
+int gfsb200_download_corner_values (gfsb200_ctx * c, int comp, int64_t n, const int32_t * cells,
+				    double * out /* [n][2^dim] */);
+int gfsb200_download_vorticity (gfsb200_ctx * c, int64_t n, const int32_t * cells,
+				double * out /* [n][3] */);
+
+/* ---- particles: SoA fp64 on the device -------------------------------- */
+/* host arrays of n; z/vz = NULL in 2D; id may be NULL (ids 1..n assigned) */
+int gfsb200_particles_upload (gfsb200_ctx * c, int64_t n,
+			      const double * x, const double * y, const double * z,
+			      const double * vx, const double * vy, const double * vz,
+			      const double * mass, const double * volume, const uint32_t * id);
+/* any output pointer may be NULL */
+int gfsb200_particles_download (gfsb200_ctx * c,
+				double * x, double * y, double * z,
+				double * vx, double * vy, double * vz,
+				double * fx, double * fy, double * fz,
+				double * mass, double * volume, uint32_t * id, int32_t * cell);
+int64_t gfsb200_particles_count (gfsb200_ctx * c);
+/* reserve device storage for n particles without a host copy, and expose the
+ * SoA device pointers (x,y,z,vx,vy,vz,mass,volume) so a harness can fill them
+ * on the device */
+int gfsb200_particles_resize (gfsb200_ctx * c, int64_t n);
+int gfsb200_particles_device_ptrs (gfsb200_ctx * c, double * ptrs[8]);
+
+typedef struct {
+  double dt;                       /* sim->advection_params.dt */
+  int32_t n_forces;
+  int32_t force[GFSB200_MAX_FORCES]; /* GFSB200_FORCE_* in list order; n_forces = 0 => passive
+				        tracer (gfs_domain_advect_point) */
+  double rho;                      /* 1/alpha when no alpha array is resident (alpha unset => 1) */
+  double mu;                       /* GfsSourceDiffusion constant; 0 => drag returns 0 */
+  double g[3];                     /* sum of GfsSource intensities on U,V,W */
+  double cd_const;                 /* constant GfsForceDrag coefficient function; NaN = built-in */
+  double cl_const;                 /* constant GfsForceLift coefficient function; NaN = 0.5 */
+  int32_t record_cells;            /* 1: also store each particle's containing cell index */
+  int32_t record_forces;           /* 1: also store the accumulated force (particulate->force) */
+} gfsb200_step_params;
+
+void gfsb200_step_params_default (gfsb200_step_params * p);
+
+/* One fused locate + interpolate + forces + integrate pass over all resident
+ * particles (gfs_particulate_event for every list member).  Particles whose
+ * gfs_domain_locate is NULL are left untouched (cell = -1). */
+int gfsb200_step (gfsb200_ctx * c, const gfsb200_step_params * p);
+
+/* gfs_particle_list_event: cull particles outside the domain
+ * (remove_particles_not_in_domain), then step.  *n_removed may be NULL. */
+int gfsb200_particle_list_event (gfsb200_ctx * c, const gfsb200_step_params * p,
+				 int64_t * n_removed);
+int gfsb200_particles_cull (gfsb200_ctx * c, int64_t * n_removed);
+/* re-sort resident particles by containing cell (Morton-ordered flat index)
+ * so that neighbouring threads gather neighbouring cells */
+int gfsb200_particles_sort (gfsb200_ctx * c);
+
+/* Batched gfs_domain_locate: host points -> flat cell index or -1. */
+int gfsb200_locate (gfsb200_ctx * c, int64_t n, const double * x, const double * y,
+		    const double * z, int32_t * cell);
+/* Batched locate + gfs_interpolate of U,V,W at host points; out[comp] may be NULL */
+int gfsb200_interpolate (gfsb200_ctx * c, int64_t n, const double * x, const double * y,
+			 const double * z, double * u, double * v, double * w);
+
+/* ---- two-way coupling -------------------------------------------------- */
+/* GfsParticulateField: field[cell] = sum V_p / V_cell over resident particles
+ * (nearest cell).  The device field is zeroed first. */
+int gfsb200_deposit_volume (gfsb200_ctx * c);
+/* GfsSourceParticulate in the single-cell limit: forces recomputed without
+ * GfsForceBuoy, field_c[cell] -= F_c / rho / V_cell. */
+int gfsb200_deposit_force (gfsb200_ctx * c, const gfsb200_step_params * p);
+/* device pointer / element count of the deposition buffer
+ * ([1 + dim][n_cells]: void fraction, Fx, Fy(, Fz)); for the multi-GPU
+ * all-reduce (NCCL) issued by the caller on gfsb200_ctx_stream() */
+int gfsb200_deposit_buffer (gfsb200_ctx * c, double ** dev, int64_t * count);
+int gfsb200_download_deposit (gfsb200_ctx * c, int comp, double * out /* [n_cells] */);
+
+/* ---- timing ------------------------------------------------------------ */
+/* average device time (ms) of the fused step kernel over the launches since
+ * the last reset, measured with CUDA events on the context's stream */
+int gfsb200_timer_reset (gfsb200_ctx * c);
+int gfsb200_timer_read (gfsb200_ctx * c, double * step_kernel_ms, int64_t * launches);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* GFSB200_H */

@@ -1,0 +1,50 @@
+/* gfsb200_ftt.h -- bridge between a live Gerris FttCell tree and the flat
+ * tree of gfsb200.h.  Built per dimension as libgfsb200_ftt2D.so /
+ * libgfsb200_ftt3D.so (the same -DFTT_2D=1 switch the reference uses,
+ * modules/Makefile.am:154-164).
+ *
+ * Replaces nothing in the reference by itself: it is the pass that lets
+ * gfs_particle_list_event (modules/particulatecommon.c:980-1015) hand the mesh
+ * of src/ftt.h:134-159 and the GFS_VALUE cell data of src/fluid.h:44-72 to the
+ * device path.  Pointers are passed as void* so that callers need no Gerris
+ * headers.
+ */
+#ifndef GFSB200_FTT_H
+#define GFSB200_FTT_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "gfsb200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gfsb200_ftt_map gfsb200_ftt_map;
+
+const char * gfsb200_ftt_last_error (void);
+
+/* roots[r]: FttCell* root of a GfsBox (is_box[r] = 1, box->root) or of a
+ * GfsBoundary (is_box[r] = 0, boundary->root).  On success *tree is a
+ * FINALIZED flat tree (stencils not yet built) and *map gives, for every flat
+ * cell index, the FttCell it mirrors. */
+int gfsb200_ftt_flatten (int n_roots, void * const * roots, const int * is_box,
+			 gfsb200_tree ** tree, gfsb200_ftt_map ** map);
+void gfsb200_ftt_map_free (gfsb200_ftt_map * m);
+int32_t gfsb200_ftt_map_size (const gfsb200_ftt_map * m);
+void * gfsb200_ftt_map_cell (const gfsb200_ftt_map * m, int32_t i);
+void * const * gfsb200_ftt_map_cells (const gfsb200_ftt_map * m);
+
+/* out[i] = GFS_VALUEI (cell_i, var) for every flat cell (nodata for destroyed
+ * cells); offset = offsetof (GfsStateVector, place_holder). */
+int gfsb200_ftt_gather (const gfsb200_ftt_map * m, size_t offset, int var, double nodata,
+			double * out);
+/* GFS_VALUEI (cell_i, var) = in[i] */
+int gfsb200_ftt_scatter (const gfsb200_ftt_map * m, size_t offset, int var, int leaves_only,
+			 const double * in);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -247,43 +247,60 @@ static void match (FttCell * cell, OraBoundary * boundary)
     boundary->depth = level;
 }
 
-/* d: the side of the box the boundary sits on (box->neighbor[d]) */
+/* gfs_boundary_new + the root == NULL branch of boundary_match
+ * (src/boundary.c:652-668, 840-858).  side: the side of the box the boundary
+ * sits on (box->neighbor[side]).  Gerris creates its boundaries while reading
+ * the .gfs file, i.e. BEFORE refinement; call ora_match_boundaries() after
+ * refinement, as gfs_simulation_refine does (src/simulation.c:1233). */
 void ora_add_boundary (OraSim * sim, int side)
 {
   static FttVector rpos[6] = {
     {1.,0.,0.}, {-1.,0.,0.}, {0.,1.,0.}, {0.,-1.,0.}, {0.,0.,1.}, {0.,0.,-1.}
   };
-  OraBoundary b;
+  FttCell * root;
   FttVector pos;
   gdouble size;
-  FttDirection od;
-  guint l;
+  FttDirection d, od;
 
   g_assert (side >= 0 && side < FTT_NEIGHBORS && sim->broot[side] == NULL);
-  b.sim = sim;
-  b.d = FTT_OPPOSITE_DIRECTION (side);
-  b.root = ftt_cell_new ((FttCellInitFunc) cell_init, sim);
-  ftt_cell_set_level (b.root, ftt_cell_level (sim->root));
-  ftt_cell_set_neighbor_match (b.root, sim->root, b.d, (FttCellInitFunc) cell_init, sim);
+  d = FTT_OPPOSITE_DIRECTION (side);
+  root = ftt_cell_new ((FttCellInitFunc) cell_init, sim);
+  root->flags |= GFS_FLAG_BOUNDARY;
+  ftt_cell_set_level (root, ftt_cell_level (sim->root));
+  ftt_cell_set_neighbor_match (root, sim->root, d, (FttCellInitFunc) cell_init, sim);
   ftt_cell_pos (sim->root, &pos);
   size = ftt_cell_size (sim->root);
-  od = FTT_OPPOSITE_DIRECTION (b.d);
+  od = FTT_OPPOSITE_DIRECTION (d);
   pos.x += rpos[od].x*size;
   pos.y += rpos[od].y*size;
   pos.z += rpos[od].z*size;
-  ftt_cell_set_pos (b.root, &pos);
+  ftt_cell_set_pos (root, &pos);
+  sim->broot[side] = root;
+}
 
-  l = ftt_cell_level (b.root);
-  b.changed = FALSE;
-  b.depth = l;
-  while (b.root && l <= b.depth) {
-    ftt_cell_traverse_boundary (b.root, b.d, FTT_PRE_ORDER, FTT_TRAVERSE_LEVEL, l,
-				(FttCellTraverseFunc) match, &b);
-    l++;
-  }
-  if (b.root && b.changed)
-    ftt_cell_flatten (b.root, b.d, cell_cleanup, NULL);
-  sim->broot[side] = b.root;
+/* gfs_domain_match -> boundary_match for every boundary (src/boundary.c:670-685) */
+void ora_match_boundaries (OraSim * sim)
+{
+  int side;
+  for (side = 0; side < FTT_NEIGHBORS; side++)
+    if (sim->broot[side]) {
+      OraBoundary b;
+      guint l;
+      b.sim = sim;
+      b.d = FTT_OPPOSITE_DIRECTION (side);
+      b.root = sim->broot[side];
+      l = ftt_cell_level (b.root);
+      b.changed = FALSE;
+      b.depth = l;
+      while (b.root && l <= b.depth) {
+	ftt_cell_traverse_boundary (b.root, b.d, FTT_PRE_ORDER, FTT_TRAVERSE_LEVEL, l,
+				    (FttCellTraverseFunc) match, &b);
+	l++;
+      }
+      if (b.root && b.changed)
+	ftt_cell_flatten (b.root, b.d, cell_cleanup, NULL);
+      sim->broot[side] = b.root;
+    }
 }
 
 /* ------------------------------------------------------------------ */

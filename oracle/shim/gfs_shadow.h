@@ -67,6 +67,9 @@ gdouble gfs_domain_face_fraction (const GfsDomain * domain, const FttCellFace * 
 gdouble gfs_domain_face_fraction_right (const GfsDomain * domain, const FttCellFace * face);
 gdouble gfs_domain_solid_metric (const GfsDomain * domain, const FttCell * cell, FttVector * m);
 
+/* --- simulation.h:158 -- the oracle's domains are never axisymmetric --- */
+#define GFS_IS_AXI(obj) (FALSE)
+
 /* --- poisson.h bits (linear problem / stencils, untouched by the hot path) --- */
 struct _GfsLinearProblem {
   GPtrArray * LP;
