@@ -1,0 +1,765 @@
+/* capi.cu -- device context and the C-ABI entry points of include/gfsb200.h.
+ *
+ * HBM layout per context (one context per GPU / rank):
+ *   tree      child0 (int32, -1 leaf / -2 destroyed), neighbor [n][2*dim] int32,
+ *             level + info (uint8), leaf_vtx [n][2^dim] int32, vertex CSR
+ *             (vtx_off int32, vtx_cell int32, vtx_w fp64)      -- re-uploaded per adapt
+ *   field     U,V,W (+alpha, mu) fp64 SoA in flat-tree order    -- mirrored per step
+ *   derived   vtx_val [n_vertices][4] fp64, vort [n_cells][4] fp64 -- rebuilt per field update
+ *   particles x,y,z,vx,vy,vz,mass,volume fp64 SoA (+ alternate buffers for the
+ *             sort/cull permutation), id uint32, optional fx,fy,fz, cell
+ *   deposit   [1 + dim][n_cells] fp64 (void fraction, force components)
+ *
+ * All work is issued on the context's own non-blocking stream.  There is no
+ * CPU fallback anywhere in this file: without a usable sm_100 device
+ * gfsb200_ctx_create fails with GFSB200_ERR_CUDA.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+#include "gfsb200_internal.h"
+#include "device_types.cuh"
+
+extern "C" {
+void gfsb200_launch_cell_pass (const DevTree *, const DevField *, int, cudaStream_t);
+void gfsb200_launch_step (const DevTree *, const DevField *, const DevParticles *, const DevStep *,
+			  int, int, cudaStream_t);
+void gfsb200_launch_advect (const DevTree *, const DevField *, const DevParticles *, double, int,
+			    cudaStream_t);
+void gfsb200_launch_locate (const DevTree *, int64_t, const double *, const double *,
+			    const double *, int32_t *, cudaStream_t);
+void gfsb200_launch_interpolate (const DevTree *, const DevField *, int64_t, const double *,
+				 const double *, const double *, double *, double *, double *,
+				 cudaStream_t);
+void gfsb200_launch_corner_values (const DevTree *, const DevField *, int, int64_t, const int32_t *,
+				   double *, cudaStream_t);
+void gfsb200_launch_deposit_volume (const DevTree *, const DevParticles *, double *, cudaStream_t);
+void gfsb200_launch_deposit_force (const DevTree *, const DevField *, const DevParticles *,
+				   const DevStep *, double *, double *, double *, cudaStream_t);
+void gfsb200_launch_gather (int64_t, const int32_t *, int, const double * const *, double * const *,
+			    const uint32_t *, uint32_t *, cudaStream_t);
+void gfsb200_launch_iota (int64_t, int32_t *, cudaStream_t);
+void gfsb200_launch_iota_u32 (int64_t, uint32_t *, uint32_t, cudaStream_t);
+void gfsb200_launch_sort_keys (int64_t, const int32_t *, uint32_t *, uint32_t, cudaStream_t);
+void gfsb200_launch_inside_flags (int64_t, const int32_t *, uint8_t *, cudaStream_t);
+cudaError_t gfsb200_cub_sort_pairs (void *, size_t *, const uint32_t *, uint32_t *, const int32_t *,
+				    int32_t *, int64_t, int, cudaStream_t);
+cudaError_t gfsb200_cub_select_flagged (void *, size_t *, const int32_t *, const uint8_t *,
+					int32_t *, int32_t *, int64_t, cudaStream_t);
+}
+
+#define NCOL 8     /* x y z vx vy vz mass volume */
+
+struct gfsb200_ctx {
+  int device, n_sm;
+  cudaStream_t stream;
+  /* tree */
+  bool have_tree;
+  DevTree T;
+  int32_t * d_child0, * d_neighbor, * d_la_slot, * d_vtx_off, * d_vtx_cell, * d_leaf_vtx;
+  uint8_t * d_level, * d_info;
+  double * d_vtx_w;
+  /* field */
+  bool have_field, own_field;
+  DevField F;
+  double * d_field[5];         /* owned copies: u v w alpha mu */
+  /* particles */
+  int64_t n, cap;
+  double * col[2][NCOL];       /* double-buffered SoA */
+  uint32_t * id[2];
+  int cur;
+  double * force[3];
+  int32_t * cell;
+  int64_t aux_cap;             /* capacity of force/cell/perm/key buffers */
+  int32_t * perm, * perm2;
+  uint32_t * key, * key2;
+  uint8_t * flag;
+  int32_t * d_count;
+  void * cub_tmp;
+  size_t cub_tmp_bytes;
+  double ** d_ptr_table;       /* [2][NCOL] device copy of col pointers */
+  /* deposit */
+  double * deposit;
+  int64_t deposit_count;
+  /* timing */
+  std::vector<cudaEvent_t> ev;
+  size_t ev_used;
+  bool timing;
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+  return gfsb200_fail (GFSB200_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString (e_), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename Tp>
+static int dev_alloc_copy (Tp ** dst, const Tp * src, size_t n, cudaStream_t st)
+{
+  *dst = NULL;
+  CK (cudaMalloc ((void **) dst, (n ? n : 1)*sizeof (Tp)));
+  if (n && src)
+    CK (cudaMemcpyAsync (*dst, src, n*sizeof (Tp), cudaMemcpyHostToDevice, st));
+  return GFSB200_OK;
+}
+
+static void free_tree (gfsb200_ctx * c)
+{
+  cudaFree (c->d_child0); cudaFree (c->d_neighbor); cudaFree (c->d_la_slot);
+  cudaFree (c->d_vtx_off); cudaFree (c->d_vtx_cell); cudaFree (c->d_leaf_vtx);
+  cudaFree (c->d_level); cudaFree (c->d_info); cudaFree (c->d_vtx_w);
+  c->d_child0 = c->d_neighbor = c->d_la_slot = c->d_vtx_off = c->d_vtx_cell = c->d_leaf_vtx = NULL;
+  c->d_level = c->d_info = NULL; c->d_vtx_w = NULL;
+  cudaFree (c->F.vtx_val); cudaFree (c->F.vort);
+  c->F.vtx_val = c->F.vort = NULL;
+  for (int i = 0; i < 5; i++) { cudaFree (c->d_field[i]); c->d_field[i] = NULL; }
+  cudaFree (c->deposit); c->deposit = NULL; c->deposit_count = 0;
+  c->have_tree = c->have_field = false;
+}
+
+static void free_particles (gfsb200_ctx * c)
+{
+  for (int b = 0; b < 2; b++) {
+    for (int k = 0; k < NCOL; k++) { cudaFree (c->col[b][k]); c->col[b][k] = NULL; }
+    cudaFree (c->id[b]); c->id[b] = NULL;
+  }
+  for (int k = 0; k < 3; k++) { cudaFree (c->force[k]); c->force[k] = NULL; }
+  cudaFree (c->cell); cudaFree (c->perm); cudaFree (c->perm2); cudaFree (c->key); cudaFree (c->key2);
+  cudaFree (c->flag); cudaFree (c->cub_tmp);
+  c->cell = c->perm = c->perm2 = NULL; c->key = c->key2 = NULL; c->flag = NULL; c->cub_tmp = NULL;
+  c->cub_tmp_bytes = 0;
+  c->n = c->cap = c->aux_cap = 0;
+}
+
+extern "C" int gfsb200_ctx_create (int device, gfsb200_ctx ** out)
+{
+  if (!out)
+    return gfsb200_fail (GFSB200_ERR_ARG, "ctx_create: null output");
+  *out = NULL;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount (&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return gfsb200_fail (GFSB200_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path",
+			 cudaGetErrorString (e));
+  if (device < 0 || device >= ndev)
+    return gfsb200_fail (GFSB200_ERR_ARG, "ctx_create: device %d out of range (%d devices)", device, ndev);
+  CK (cudaSetDevice (device));
+  cudaDeviceProp prop;
+  CK (cudaGetDeviceProperties (&prop, device));
+  if (prop.major != 10)
+    return gfsb200_fail (GFSB200_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only",
+			 device, prop.major, prop.minor);
+  gfsb200_ctx * c = new gfsb200_ctx ();
+  memset (&c->T, 0, sizeof c->T);
+  memset (&c->F, 0, sizeof c->F);
+  c->device = device;
+  c->n_sm = prop.multiProcessorCount;
+  c->have_tree = c->have_field = c->own_field = false;
+  c->d_child0 = c->d_neighbor = c->d_la_slot = c->d_vtx_off = c->d_vtx_cell = c->d_leaf_vtx = NULL;
+  c->d_level = c->d_info = NULL; c->d_vtx_w = NULL;
+  for (int i = 0; i < 5; i++) c->d_field[i] = NULL;
+  c->n = c->cap = c->aux_cap = 0; c->cur = 0;
+  for (int b = 0; b < 2; b++) { for (int k = 0; k < NCOL; k++) c->col[b][k] = NULL; c->id[b] = NULL; }
+  for (int k = 0; k < 3; k++) c->force[k] = NULL;
+  c->cell = c->perm = c->perm2 = NULL; c->key = c->key2 = NULL; c->flag = NULL;
+  c->d_count = NULL; c->cub_tmp = NULL; c->cub_tmp_bytes = 0; c->d_ptr_table = NULL;
+  c->deposit = NULL; c->deposit_count = 0;
+  c->ev_used = 0; c->timing = true;
+  if (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc ((void **) &c->d_count, sizeof (int32_t)) != cudaSuccess ||
+      cudaMalloc ((void **) &c->d_ptr_table, 2*NCOL*sizeof (double *)) != cudaSuccess) {
+    delete c;
+    return gfsb200_fail (GFSB200_ERR_CUDA, "ctx_create: %s", cudaGetErrorString (cudaGetLastError ()));
+  }
+  *out = c;
+  return GFSB200_OK;
+}
+
+extern "C" void gfsb200_ctx_destroy (gfsb200_ctx * c)
+{
+  if (!c) return;
+  cudaSetDevice (c->device);
+  cudaStreamSynchronize (c->stream);
+  free_tree (c);
+  free_particles (c);
+  cudaFree (c->d_count); cudaFree (c->d_ptr_table);
+  for (size_t i = 0; i < c->ev.size (); i++) cudaEventDestroy (c->ev[i]);
+  cudaStreamDestroy (c->stream);
+  delete c;
+}
+
+extern "C" void * gfsb200_ctx_stream (gfsb200_ctx * c) { return c ? (void *) c->stream : NULL; }
+
+extern "C" int gfsb200_ctx_synchronize (gfsb200_ctx * c)
+{
+  if (!c) return gfsb200_fail (GFSB200_ERR_ARG, "null context");
+  CK (cudaSetDevice (c->device));
+  CK (cudaStreamSynchronize (c->stream));
+  return GFSB200_OK;
+}
+
+/* ------------------------------------------------------------------ */
+
+extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
+{
+  if (!c || !t) return gfsb200_fail (GFSB200_ERR_ARG, "upload_tree: null argument");
+  if (!t->finalized || !t->leaf_vtx)
+    return gfsb200_fail (GFSB200_ERR_STATE, "upload_tree: tree needs finalize + build_stencils");
+  if (t->n_roots > GFSB200_MAX_DEV_ROOTS)
+    return gfsb200_fail (GFSB200_ERR_UNSUPPORTED, "upload_tree: more than %d root cells", GFSB200_MAX_DEV_ROOTS);
+  CK (cudaSetDevice (c->device));
+  CK (cudaStreamSynchronize (c->stream));
+  free_tree (c);
+
+  const int32_t n = t->n_cells;
+  const int nc = t->nchild;
+  std::vector<int32_t> child0 (n);
+  std::vector<uint8_t> info (n);
+  for (int32_t i = 0; i < n; i++) {
+    child0[i] = (t->flags[i] & GFSB200_CELL_DESTROYED) ? CHILD_DESTROYED :
+      (t->child0[i] < 0 ? CHILD_LEAF : t->child0[i]);
+    int k = t->parent[i] < 0 ? 0 : i - t->child0[t->parent[i]];
+    info[i] = (uint8_t) ((t->flags[i] & 7) | (k << 4));
+  }
+  int r;
+  if ((r = dev_alloc_copy (&c->d_child0, child0.data (), n, c->stream))) return r;
+  if ((r = dev_alloc_copy (&c->d_info, info.data (), n, c->stream))) return r;
+  if ((r = dev_alloc_copy (&c->d_level, (const uint8_t *) t->level, n, c->stream))) return r;
+  if ((r = dev_alloc_copy (&c->d_neighbor, (const int32_t *) t->neighbor, (size_t) n*t->ndir, c->stream))) return r;
+  if ((r = dev_alloc_copy (&c->d_la_slot, (const int32_t *) t->la_slot, t->la_size, c->stream))) return r;
+  if ((r = dev_alloc_copy (&c->d_vtx_off, (const int32_t *) t->vtx_off, (size_t) t->n_vertices + 1, c->stream))) return r;
+  const size_t ne = t->vtx_off[t->n_vertices];
+  if ((r = dev_alloc_copy (&c->d_vtx_cell, (const int32_t *) t->vtx_cell, ne, c->stream))) return r;
+  if ((r = dev_alloc_copy (&c->d_vtx_w, (const double *) t->vtx_w, ne, c->stream))) return r;
+  if ((r = dev_alloc_copy (&c->d_leaf_vtx, (const int32_t *) t->leaf_vtx, (size_t) n*nc, c->stream))) return r;
+  CK (cudaStreamSynchronize (c->stream));   /* host staging vectors go out of scope */
+
+  DevTree & T = c->T;
+  memset (&T, 0, sizeof T);
+  T.dim = t->dim; T.n_cells = n; T.n_roots = t->n_roots; T.n_box_roots = t->n_box_roots;
+  T.root_level = t->root_level;
+  T.top_levels = t->complete_level - t->root_level;
+  /* Morton keys of the arithmetic top are built from 10 (3D) / 16 (2D) bits per axis */
+  if (T.top_levels > (t->dim == 3 ? 10 : 15)) T.top_levels = t->dim == 3 ? 10 : 15;
+  T.top_start = t->level_start[T.top_levels];
+  T.root_size = ldexp (1., -t->root_level);
+  for (int rr = 0; rr < t->n_roots; rr++)
+    for (int a = 0; a < 3; a++)
+      T.root_pos[rr][a] = t->pos[3*rr + a];
+  for (int a = 0; a < 3; a++) { T.la_min[a] = t->la_min[a]; T.la_n[a] = t->la_n[a]; }
+  T.la_h = t->la_h;
+  T.single_box = t->la_size == 1 && t->la_slot[0] == 0;
+  T.la_slot = c->d_la_slot;
+  T.child0 = c->d_child0; T.neighbor = c->d_neighbor; T.level = c->d_level; T.info = c->d_info;
+  T.n_vertices = t->n_vertices;
+  T.vtx_off = c->d_vtx_off; T.vtx_cell = c->d_vtx_cell; T.vtx_w = c->d_vtx_w; T.leaf_vtx = c->d_leaf_vtx;
+
+  memset (&c->F, 0, sizeof c->F);
+  const int vs = t->dim == 3 ? 4 : 2, ws = t->dim == 3 ? 4 : 1;
+  CK (cudaMalloc ((void **) &c->F.vtx_val, (size_t) (t->n_vertices ? t->n_vertices : 1)*vs*sizeof (double)));
+  CK (cudaMalloc ((void **) &c->F.vort, (size_t) n*ws*sizeof (double)));
+  c->deposit_count = (int64_t) (1 + t->dim)*n;
+  CK (cudaMalloc ((void **) &c->deposit, (size_t) c->deposit_count*sizeof (double)));
+  CK (cudaMemsetAsync (c->deposit, 0, (size_t) c->deposit_count*sizeof (double), c->stream));
+  c->have_tree = true;
+  c->have_field = false;
+  return GFSB200_OK;
+}
+
+extern "C" int gfsb200_refresh_field (gfsb200_ctx * c)
+{
+  if (!c || !c->have_tree || !c->F.u[0])
+    return gfsb200_fail (GFSB200_ERR_STATE, "refresh_field: no tree/field resident");
+  CK (cudaSetDevice (c->device));
+  gfsb200_launch_cell_pass (&c->T, &c->F, c->n_sm, c->stream);
+  CK (cudaGetLastError ());
+  c->have_field = true;
+  return GFSB200_OK;
+}
+
+extern "C" int gfsb200_upload_field (gfsb200_ctx * c, const double * u, const double * v,
+				     const double * w, const double * alpha, const double * mu)
+{
+  if (!c || !c->have_tree) return gfsb200_fail (GFSB200_ERR_STATE, "upload_field: upload a tree first");
+  if (!u || !v || (c->T.dim == 3 && !w))
+    return gfsb200_fail (GFSB200_ERR_ARG, "upload_field: missing velocity component");
+  CK (cudaSetDevice (c->device));
+  const double * src[5] = { u, v, c->T.dim == 3 ? w : NULL, alpha, mu };
+  const size_t bytes = (size_t) c->T.n_cells*sizeof (double);
+  for (int i = 0; i < 5; i++) {
+    if (src[i]) {
+      if (!c->d_field[i]) CK (cudaMalloc ((void **) &c->d_field[i], bytes));
+      CK (cudaMemcpyAsync (c->d_field[i], src[i], bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    else if (c->d_field[i]) {
+      CK (cudaStreamSynchronize (c->stream));
+      cudaFree (c->d_field[i]);
+      c->d_field[i] = NULL;
+    }
+  }
+  c->F.u[0] = c->d_field[0]; c->F.u[1] = c->d_field[1]; c->F.u[2] = c->d_field[2];
+  c->F.alpha = c->d_field[3]; c->F.mu = c->d_field[4];
+  return gfsb200_refresh_field (c);
+}
+
+extern "C" int gfsb200_set_field_device (gfsb200_ctx * c, const double * u, const double * v,
+					 const double * w, const double * alpha, const double * mu)
+{
+  if (!c || !c->have_tree) return gfsb200_fail (GFSB200_ERR_STATE, "set_field_device: upload a tree first");
+  if (!u || !v || (c->T.dim == 3 && !w))
+    return gfsb200_fail (GFSB200_ERR_ARG, "set_field_device: missing velocity component");
+  c->F.u[0] = u; c->F.u[1] = v; c->F.u[2] = c->T.dim == 3 ? w : NULL;
+  c->F.alpha = alpha; c->F.mu = mu;
+  return gfsb200_refresh_field (c);
+}
+
+extern "C" int gfsb200_download_corner_values (gfsb200_ctx * c, int comp, int64_t n,
+					       const int32_t * cells, double * out)
+{
+  if (!c || !c->have_field) return gfsb200_fail (GFSB200_ERR_STATE, "download_corner_values: no field");
+  if (comp < 0 || comp >= c->T.dim || n < 0 || !cells || !out)
+    return gfsb200_fail (GFSB200_ERR_ARG, "download_corner_values: bad argument");
+  CK (cudaSetDevice (c->device));
+  const int nc = 1 << c->T.dim;
+  int32_t * d_cells; double * d_out;
+  CK (cudaMalloc ((void **) &d_cells, (n ? n : 1)*sizeof (int32_t)));
+  CK (cudaMalloc ((void **) &d_out, (n ? n : 1)*nc*sizeof (double)));
+  CK (cudaMemcpyAsync (d_cells, cells, n*sizeof (int32_t), cudaMemcpyHostToDevice, c->stream));
+  gfsb200_launch_corner_values (&c->T, &c->F, comp, n, d_cells, d_out, c->stream);
+  CK (cudaGetLastError ());
+  CK (cudaMemcpyAsync (out, d_out, n*nc*sizeof (double), cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  cudaFree (d_cells); cudaFree (d_out);
+  return GFSB200_OK;
+}
+
+extern "C" int gfsb200_download_vorticity (gfsb200_ctx * c, int64_t n, const int32_t * cells,
+					   double * out)
+{
+  if (!c || !c->have_field) return gfsb200_fail (GFSB200_ERR_STATE, "download_vorticity: no field");
+  if (n < 0 || !cells || !out) return gfsb200_fail (GFSB200_ERR_ARG, "download_vorticity: bad argument");
+  CK (cudaSetDevice (c->device));
+  const int ws = c->T.dim == 3 ? 4 : 1;
+  std::vector<double> all ((size_t) c->T.n_cells*ws);
+  CK (cudaMemcpyAsync (all.data (), c->F.vort, all.size ()*sizeof (double), cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  for (int64_t j = 0; j < n; j++) {
+    if (cells[j] < 0 || cells[j] >= c->T.n_cells)
+      return gfsb200_fail (GFSB200_ERR_ARG, "download_vorticity: cell %d out of range", cells[j]);
+    if (c->T.dim == 3) {
+      out[3*j] = all[(size_t) cells[j]*4]; out[3*j + 1] = all[(size_t) cells[j]*4 + 1];
+      out[3*j + 2] = all[(size_t) cells[j]*4 + 2];
+    }
+    else {
+      out[3*j] = 0.; out[3*j + 1] = 0.; out[3*j + 2] = all[cells[j]];
+    }
+  }
+  return GFSB200_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* particles                                                            */
+
+static int ensure_aux (gfsb200_ctx * c, int64_t n)
+{
+  if (n <= c->aux_cap) return GFSB200_OK;
+  for (int k = 0; k < 3; k++) { cudaFree (c->force[k]); c->force[k] = NULL; }
+  cudaFree (c->cell); cudaFree (c->perm); cudaFree (c->perm2); cudaFree (c->key); cudaFree (c->key2);
+  cudaFree (c->flag);
+  c->aux_cap = 0;
+  for (int k = 0; k < 3; k++) CK (cudaMalloc ((void **) &c->force[k], n*sizeof (double)));
+  CK (cudaMalloc ((void **) &c->cell, n*sizeof (int32_t)));
+  CK (cudaMalloc ((void **) &c->perm, n*sizeof (int32_t)));
+  CK (cudaMalloc ((void **) &c->perm2, n*sizeof (int32_t)));
+  CK (cudaMalloc ((void **) &c->key, n*sizeof (uint32_t)));
+  CK (cudaMalloc ((void **) &c->key2, n*sizeof (uint32_t)));
+  CK (cudaMalloc ((void **) &c->flag, n));
+  c->aux_cap = n;
+  return GFSB200_OK;
+}
+
+extern "C" int gfsb200_particles_resize (gfsb200_ctx * c, int64_t n)
+{
+  if (!c || n < 0 || n > INT32_MAX)
+    return gfsb200_fail (GFSB200_ERR_ARG, "particles_resize: bad count");
+  CK (cudaSetDevice (c->device));
+  if (n > c->cap) {
+    CK (cudaStreamSynchronize (c->stream));
+    int64_t keep = c->n;
+    double * ncol[2][NCOL]; uint32_t * nid[2];
+    for (int b = 0; b < 2; b++) {
+      for (int k = 0; k < NCOL; k++) CK (cudaMalloc ((void **) &ncol[b][k], n*sizeof (double)));
+      CK (cudaMalloc ((void **) &nid[b], n*sizeof (uint32_t)));
+    }
+    if (keep) {
+      for (int k = 0; k < NCOL; k++)
+	CK (cudaMemcpyAsync (ncol[0][k], c->col[c->cur][k], keep*sizeof (double), cudaMemcpyDeviceToDevice, c->stream));
+      CK (cudaMemcpyAsync (nid[0], c->id[c->cur], keep*sizeof (uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+      CK (cudaStreamSynchronize (c->stream));
+    }
+    for (int b = 0; b < 2; b++) {
+      for (int k = 0; k < NCOL; k++) { cudaFree (c->col[b][k]); c->col[b][k] = ncol[b][k]; }
+      cudaFree (c->id[b]); c->id[b] = nid[b];
+    }
+    c->cur = 0;
+    c->cap = n;
+    double * table[2*NCOL];
+    for (int b = 0; b < 2; b++) for (int k = 0; k < NCOL; k++) table[b*NCOL + k] = c->col[b][k];
+    CK (cudaMemcpyAsync (c->d_ptr_table, table, sizeof table, cudaMemcpyHostToDevice, c->stream));
+    CK (cudaStreamSynchronize (c->stream));
+  }
+  int r = ensure_aux (c, n > 0 ? n : 1);
+  if (r) return r;
+  if (n > c->n)    /* new slots get ids continuing the sequence */
+    gfsb200_launch_iota_u32 (n - c->n, c->id[c->cur] + c->n, (uint32_t) c->n + 1, c->stream);
+  c->n = n;
+  return GFSB200_OK;
+}
+
+extern "C" int gfsb200_particles_device_ptrs (gfsb200_ctx * c, double * ptrs[8])
+{
+  if (!c || !ptrs) return gfsb200_fail (GFSB200_ERR_ARG, "particles_device_ptrs: null argument");
+  for (int k = 0; k < NCOL; k++) ptrs[k] = c->col[c->cur][k];
+  return GFSB200_OK;
+}
+
+extern "C" int64_t gfsb200_particles_count (gfsb200_ctx * c) { return c ? c->n : -1; }
+
+extern "C" int gfsb200_particles_upload (gfsb200_ctx * c, int64_t n,
+					 const double * x, const double * y, const double * z,
+					 const double * vx, const double * vy, const double * vz,
+					 const double * mass, const double * volume, const uint32_t * id)
+{
+  if (!c || n < 0 || (n && (!x || !y || !vx || !vy || !mass || !volume)))
+    return gfsb200_fail (GFSB200_ERR_ARG, "particles_upload: bad argument");
+  c->n = 0;
+  int r = gfsb200_particles_resize (c, n);
+  if (r) return r;
+  const double * src[NCOL] = { x, y, z, vx, vy, vz, mass, volume };
+  for (int k = 0; k < NCOL; k++) {
+    if (src[k])
+      CK (cudaMemcpyAsync (c->col[c->cur][k], src[k], n*sizeof (double), cudaMemcpyHostToDevice, c->stream));
+    else
+      CK (cudaMemsetAsync (c->col[c->cur][k], 0, n*sizeof (double), c->stream));
+  }
+  if (id)
+    CK (cudaMemcpyAsync (c->id[c->cur], id, n*sizeof (uint32_t), cudaMemcpyHostToDevice, c->stream));
+  CK (cudaMemsetAsync (c->cell, 0xff, (n ? n : 1)*sizeof (int32_t), c->stream));
+  for (int k = 0; k < 3; k++) CK (cudaMemsetAsync (c->force[k], 0, (n ? n : 1)*sizeof (double), c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  return GFSB200_OK;
+}
+
+extern "C" int gfsb200_particles_download (gfsb200_ctx * c,
+					   double * x, double * y, double * z,
+					   double * vx, double * vy, double * vz,
+					   double * fx, double * fy, double * fz,
+					   double * mass, double * volume, uint32_t * id, int32_t * cell)
+{
+  if (!c) return gfsb200_fail (GFSB200_ERR_ARG, "particles_download: null context");
+  CK (cudaSetDevice (c->device));
+  const int64_t n = c->n;
+  double * dst[NCOL] = { x, y, z, vx, vy, vz, mass, volume };
+  for (int k = 0; k < NCOL; k++)
+    if (dst[k] && n)
+      CK (cudaMemcpyAsync (dst[k], c->col[c->cur][k], n*sizeof (double), cudaMemcpyDeviceToHost, c->stream));
+  double * fd[3] = { fx, fy, fz };
+  for (int k = 0; k < 3; k++)
+    if (fd[k] && n)
+      CK (cudaMemcpyAsync (fd[k], c->force[k], n*sizeof (double), cudaMemcpyDeviceToHost, c->stream));
+  if (id && n) CK (cudaMemcpyAsync (id, c->id[c->cur], n*sizeof (uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (cell && n) CK (cudaMemcpyAsync (cell, c->cell, n*sizeof (int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  return GFSB200_OK;
+}
+
+static DevParticles particles_view (gfsb200_ctx * c)
+{
+  DevParticles P;
+  P.n = c->n;
+  double ** col = c->col[c->cur];
+  P.x = col[0]; P.y = col[1]; P.z = col[2]; P.vx = col[3]; P.vy = col[4]; P.vz = col[5];
+  P.mass = col[6]; P.volume = col[7];
+  P.fx = c->force[0]; P.fy = c->force[1]; P.fz = c->force[2];
+  P.cell = c->cell;
+  P.id = c->id[c->cur];
+  return P;
+}
+
+extern "C" void gfsb200_step_params_default (gfsb200_step_params * p)
+{
+  if (!p) return;
+  memset (p, 0, sizeof *p);
+  p->rho = 1.;
+  p->cd_const = NAN;
+  p->cl_const = NAN;
+}
+
+static int make_step (const gfsb200_step_params * p, DevStep * S)
+{
+  if (!p) return gfsb200_fail (GFSB200_ERR_ARG, "null step parameters");
+  if (p->n_forces < 0 || p->n_forces > GFSB200_MAX_FORCES)
+    return gfsb200_fail (GFSB200_ERR_ARG, "n_forces = %d out of range", p->n_forces);
+  memset (S, 0, sizeof *S);
+  S->dt = p->dt;
+  S->n_forces = p->n_forces;
+  for (int k = 0; k < p->n_forces; k++) {
+    if (p->force[k] < GFSB200_FORCE_DRAG || p->force[k] > GFSB200_FORCE_BUOY)
+      return gfsb200_fail (GFSB200_ERR_UNSUPPORTED, "force kind %d is not supported on the device", p->force[k]);
+    S->forces |= (unsigned) p->force[k] << (4*k);
+    if (p->force[k] != GFSB200_FORCE_BUOY) S->need_velocity = 1;
+  }
+  S->rho = p->rho; S->mu = p->mu;
+  for (int a = 0; a < 3; a++) S->g[a] = p->g[a];
+  S->cd_const = p->cd_const; S->cl_const = p->cl_const;
+  return GFSB200_OK;
+}
+
+#define MAX_TIMED_EVENTS 16384
+
+static int timed_begin (gfsb200_ctx * c)
+{
+  c->timing = c->ev_used + 2 <= MAX_TIMED_EVENTS;   /* stop recording until the next timer_reset */
+  if (!c->timing) return GFSB200_OK;
+  if (c->ev_used + 2 > c->ev.size ()) {
+    cudaEvent_t a, b;
+    CK (cudaEventCreate (&a));
+    CK (cudaEventCreate (&b));
+    c->ev.push_back (a); c->ev.push_back (b);
+  }
+  CK (cudaEventRecord (c->ev[c->ev_used], c->stream));
+  return GFSB200_OK;
+}
+
+static int timed_end (gfsb200_ctx * c)
+{
+  if (!c->timing) return GFSB200_OK;
+  CK (cudaEventRecord (c->ev[c->ev_used + 1], c->stream));
+  c->ev_used += 2;
+  return GFSB200_OK;
+}
+
+extern "C" int gfsb200_step (gfsb200_ctx * c, const gfsb200_step_params * p)
+{
+  if (!c || !c->have_field)
+    return gfsb200_fail (GFSB200_ERR_STATE, "step: tree and field must be resident");
+  DevStep S;
+  int r = make_step (p, &S);
+  if (r) return r;
+  CK (cudaSetDevice (c->device));
+  DevParticles P = particles_view (c);
+  if ((r = timed_begin (c))) return r;
+  if (S.n_forces == 0)
+    gfsb200_launch_advect (&c->T, &c->F, &P, S.dt, p->record_cells, c->stream);
+  else
+    gfsb200_launch_step (&c->T, &c->F, &P, &S, p->record_cells, p->record_forces, c->stream);
+  if ((r = timed_end (c))) return r;
+  CK (cudaGetLastError ());
+  return GFSB200_OK;
+}
+
+static int ensure_cub_tmp (gfsb200_ctx * c, size_t bytes)
+{
+  if (bytes <= c->cub_tmp_bytes) return GFSB200_OK;
+  cudaFree (c->cub_tmp);
+  c->cub_tmp = NULL; c->cub_tmp_bytes = 0;
+  CK (cudaMalloc (&c->cub_tmp, bytes));
+  c->cub_tmp_bytes = bytes;
+  return GFSB200_OK;
+}
+
+/* apply c->perm2 (new position -> old position) to the SoA, n_new entries */
+static int apply_permutation (gfsb200_ctx * c, int64_t n_new)
+{
+  const int nb = 1 - c->cur;
+  gfsb200_launch_gather (n_new, c->perm2, NCOL, (const double * const *) (c->d_ptr_table + c->cur*NCOL),
+			 c->d_ptr_table + nb*NCOL, c->id[c->cur], c->id[nb], c->stream);
+  CK (cudaGetLastError ());
+  c->cur = nb;
+  c->n = n_new;
+  return GFSB200_OK;
+}
+
+extern "C" int gfsb200_particles_sort (gfsb200_ctx * c)
+{
+  if (!c || !c->have_tree) return gfsb200_fail (GFSB200_ERR_STATE, "particles_sort: no tree");
+  if (c->n <= 1) return GFSB200_OK;
+  CK (cudaSetDevice (c->device));
+  DevParticles P = particles_view (c);
+  gfsb200_launch_locate (&c->T, P.n, P.x, P.y, P.z, c->cell, c->stream);
+  gfsb200_launch_sort_keys (P.n, c->cell, c->key, (uint32_t) c->T.n_cells, c->stream);
+  gfsb200_launch_iota (P.n, c->perm, c->stream);
+  CK (cudaGetLastError ());
+  int end_bit = 1;
+  while (end_bit < 32 && (1u << end_bit) <= (uint32_t) c->T.n_cells) end_bit++;
+  size_t bytes = 0;
+  CK (gfsb200_cub_sort_pairs (NULL, &bytes, c->key, c->key2, c->perm, c->perm2, P.n, end_bit, c->stream));
+  int r = ensure_cub_tmp (c, bytes);
+  if (r) return r;
+  CK (gfsb200_cub_sort_pairs (c->cub_tmp, &bytes, c->key, c->key2, c->perm, c->perm2, P.n, end_bit, c->stream));
+  return apply_permutation (c, P.n);
+}
+
+extern "C" int gfsb200_particles_cull (gfsb200_ctx * c, int64_t * n_removed)
+{
+  if (!c || !c->have_tree) return gfsb200_fail (GFSB200_ERR_STATE, "particles_cull: no tree");
+  if (n_removed) *n_removed = 0;
+  if (c->n == 0) return GFSB200_OK;
+  CK (cudaSetDevice (c->device));
+  DevParticles P = particles_view (c);
+  gfsb200_launch_locate (&c->T, P.n, P.x, P.y, P.z, c->cell, c->stream);
+  gfsb200_launch_inside_flags (P.n, c->cell, c->flag, c->stream);
+  gfsb200_launch_iota (P.n, c->perm, c->stream);
+  CK (cudaGetLastError ());
+  size_t bytes = 0;
+  CK (gfsb200_cub_select_flagged (NULL, &bytes, c->perm, c->flag, c->perm2, c->d_count, P.n, c->stream));
+  int r = ensure_cub_tmp (c, bytes);
+  if (r) return r;
+  CK (gfsb200_cub_select_flagged (c->cub_tmp, &bytes, c->perm, c->flag, c->perm2, c->d_count, P.n, c->stream));
+  int32_t kept = 0;
+  CK (cudaMemcpyAsync (&kept, c->d_count, sizeof kept, cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  if (kept == P.n) return GFSB200_OK;
+  if (n_removed) *n_removed = P.n - kept;
+  return apply_permutation (c, kept);
+}
+
+extern "C" int gfsb200_particle_list_event (gfsb200_ctx * c, const gfsb200_step_params * p,
+					    int64_t * n_removed)
+{
+  int r = gfsb200_particles_cull (c, n_removed);
+  if (r) return r;
+  return gfsb200_step (c, p);
+}
+
+/* ------------------------------------------------------------------ */
+/* batched point queries                                                */
+
+extern "C" int gfsb200_locate (gfsb200_ctx * c, int64_t n, const double * x, const double * y,
+			       const double * z, int32_t * cell)
+{
+  if (!c || !c->have_tree) return gfsb200_fail (GFSB200_ERR_STATE, "locate: no tree resident");
+  if (n < 0 || (n && (!x || !y || !cell || (c->T.dim == 3 && !z))))
+    return gfsb200_fail (GFSB200_ERR_ARG, "locate: bad argument");
+  if (n == 0) return GFSB200_OK;
+  CK (cudaSetDevice (c->device));
+  double * d[3] = { NULL, NULL, NULL }; int32_t * dc = NULL;
+  const double * src[3] = { x, y, z };
+  for (int a = 0; a < c->T.dim; a++) {
+    CK (cudaMalloc ((void **) &d[a], n*sizeof (double)));
+    CK (cudaMemcpyAsync (d[a], src[a], n*sizeof (double), cudaMemcpyHostToDevice, c->stream));
+  }
+  CK (cudaMalloc ((void **) &dc, n*sizeof (int32_t)));
+  gfsb200_launch_locate (&c->T, n, d[0], d[1], d[2], dc, c->stream);
+  CK (cudaGetLastError ());
+  CK (cudaMemcpyAsync (cell, dc, n*sizeof (int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  for (int a = 0; a < 3; a++) cudaFree (d[a]);
+  cudaFree (dc);
+  return GFSB200_OK;
+}
+
+extern "C" int gfsb200_interpolate (gfsb200_ctx * c, int64_t n, const double * x, const double * y,
+				    const double * z, double * u, double * v, double * w)
+{
+  if (!c || !c->have_field) return gfsb200_fail (GFSB200_ERR_STATE, "interpolate: no field resident");
+  if (n < 0 || (n && (!x || !y || (c->T.dim == 3 && !z))))
+    return gfsb200_fail (GFSB200_ERR_ARG, "interpolate: bad argument");
+  if (n == 0) return GFSB200_OK;
+  CK (cudaSetDevice (c->device));
+  double * d[3] = { NULL, NULL, NULL }, * o[3] = { NULL, NULL, NULL };
+  const double * src[3] = { x, y, z };
+  double * dst[3] = { u, v, c->T.dim == 3 ? w : NULL };
+  for (int a = 0; a < c->T.dim; a++) {
+    CK (cudaMalloc ((void **) &d[a], n*sizeof (double)));
+    CK (cudaMemcpyAsync (d[a], src[a], n*sizeof (double), cudaMemcpyHostToDevice, c->stream));
+    if (dst[a]) CK (cudaMalloc ((void **) &o[a], n*sizeof (double)));
+  }
+  gfsb200_launch_interpolate (&c->T, &c->F, n, d[0], d[1], d[2], o[0], o[1], o[2], c->stream);
+  CK (cudaGetLastError ());
+  for (int a = 0; a < c->T.dim; a++)
+    if (dst[a])
+      CK (cudaMemcpyAsync (dst[a], o[a], n*sizeof (double), cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  for (int a = 0; a < 3; a++) { cudaFree (d[a]); cudaFree (o[a]); }
+  return GFSB200_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* two-way coupling                                                     */
+
+extern "C" int gfsb200_deposit_volume (gfsb200_ctx * c)
+{
+  if (!c || !c->have_tree) return gfsb200_fail (GFSB200_ERR_STATE, "deposit_volume: no tree resident");
+  CK (cudaSetDevice (c->device));
+  /* gfs_cell_reset on the leaves, then scatter */
+  CK (cudaMemsetAsync (c->deposit, 0, (size_t) c->T.n_cells*sizeof (double), c->stream));
+  DevParticles P = particles_view (c);
+  gfsb200_launch_deposit_volume (&c->T, &P, c->deposit, c->stream);
+  CK (cudaGetLastError ());
+  return GFSB200_OK;
+}
+
+extern "C" int gfsb200_deposit_force (gfsb200_ctx * c, const gfsb200_step_params * p)
+{
+  if (!c || !c->have_field) return gfsb200_fail (GFSB200_ERR_STATE, "deposit_force: no field resident");
+  DevStep S;
+  int r = make_step (p, &S);
+  if (r) return r;
+  CK (cudaSetDevice (c->device));
+  const size_t n = c->T.n_cells;
+  CK (cudaMemsetAsync (c->deposit + n, 0, (size_t) c->T.dim*n*sizeof (double), c->stream));
+  DevParticles P = particles_view (c);
+  gfsb200_launch_deposit_force (&c->T, &c->F, &P, &S, c->deposit + n, c->deposit + 2*n,
+				c->T.dim == 3 ? c->deposit + 3*n : NULL, c->stream);
+  CK (cudaGetLastError ());
+  return GFSB200_OK;
+}
+
+extern "C" int gfsb200_deposit_buffer (gfsb200_ctx * c, double ** dev, int64_t * count)
+{
+  if (!c || !c->have_tree) return gfsb200_fail (GFSB200_ERR_STATE, "deposit_buffer: no tree resident");
+  if (dev) *dev = c->deposit;
+  if (count) *count = c->deposit_count;
+  return GFSB200_OK;
+}
+
+extern "C" int gfsb200_download_deposit (gfsb200_ctx * c, int comp, double * out)
+{
+  if (!c || !c->have_tree) return gfsb200_fail (GFSB200_ERR_STATE, "download_deposit: no tree resident");
+  if (comp < 0 || comp > c->T.dim || !out) return gfsb200_fail (GFSB200_ERR_ARG, "download_deposit: bad argument");
+  CK (cudaSetDevice (c->device));
+  const size_t n = c->T.n_cells;
+  CK (cudaMemcpyAsync (out, c->deposit + comp*n, n*sizeof (double), cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  return GFSB200_OK;
+}
+
+/* ------------------------------------------------------------------ */
+
+extern "C" int gfsb200_timer_reset (gfsb200_ctx * c)
+{
+  if (!c) return gfsb200_fail (GFSB200_ERR_ARG, "null context");
+  CK (cudaSetDevice (c->device));
+  CK (cudaStreamSynchronize (c->stream));
+  c->ev_used = 0;
+  return GFSB200_OK;
+}
+
+extern "C" int gfsb200_timer_read (gfsb200_ctx * c, double * step_kernel_ms, int64_t * launches)
+{
+  if (!c) return gfsb200_fail (GFSB200_ERR_ARG, "null context");
+  CK (cudaSetDevice (c->device));
+  CK (cudaStreamSynchronize (c->stream));
+  double total = 0.;
+  for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
+    float ms = 0.f;
+    CK (cudaEventElapsedTime (&ms, c->ev[i], c->ev[i + 1]));
+    total += ms;
+  }
+  const int64_t n = (int64_t) (c->ev_used/2);
+  if (step_kernel_ms) *step_kernel_ms = n ? total/n : 0.;
+  if (launches) *launches = n;
+  return GFSB200_OK;
+}

@@ -1,0 +1,239 @@
+/* cell_kernels.cu -- the per-field-update cell pass (sm_100a).
+ *
+ *   vertex_values_kernel   one thread per deduplicated vertex: sum(w_i * v_i)
+ *                          over its corner stencil for U,V(,W)
+ *                          = gfs_cell_corner_value, src/fluid.c:3081-3101
+ *   vorticity_kernel       one thread per cell: the cell-constant vorticity
+ *                          vector of vorticity_vector,
+ *                          modules/particulatecommon.c:142-164, built from
+ *                          gfs_center_gradient, src/fluid.c:434-475
+ *
+ * The reference recomputes both per particle per force (72 stencil
+ * constructions and 6 gradients per particle-step); they depend on the cell
+ * only, so here they are evaluated once per cell per field update and the
+ * particle kernel gathers the results.
+ *
+ * This translation unit is compiled with --fmad=false and keeps the
+ * reference's operation order, so its results are bit-identical to the
+ * reference's non-FMA x86-64 arithmetic.  Both kernels are HBM/L2-bound
+ * streaming passes over the cell arrays (roofline: DESIGN.md section 4).
+ */
+#include "device_types.cuh"
+
+namespace {
+
+__device__ __forceinline__ bool is_leaf (const DevTree & T, int c) { return T.child0[c] == CHILD_LEAF; }
+__device__ __forceinline__ int child_id (const DevTree & T, int c) { return T.info[c] >> 4; }
+__device__ __forceinline__ bool child_positive (int n, int axis)
+{
+  return axis == 0 ? (n & 1) : !((n >> axis) & 1);
+}
+
+/* average_neighbor_value, src/fluid.c:64-93 (no solid fractions) */
+template <int DIM>
+__device__ double average_neighbor_value (const DevTree & T, const double * __restrict__ F,
+					  int cell, int nb, int d, double * x)
+{
+  if (is_leaf (T, nb))
+    return F[nb];
+  double av = 0., a = 0.;
+  const int od = d ^ 1, axis = d >> 1;
+  const bool od_pos = !(od & 1);
+  const int c0 = T.child0[nb];
+  for (int k = 0; k < (1 << DIM); k++) {
+    if (child_positive (k, axis) != od_pos)
+      continue;
+    int c = c0 + k;
+    if (T.child0[c] != CHILD_DESTROYED && F[c] != GFSB200_NODATA) {
+      a += 1.;
+      av += 1.*F[c];
+    }
+  }
+  if (a > 0.) {
+    *x = 3./4.;
+    return av/a;
+  }
+  return F[cell];
+}
+
+struct Grad2 { double a, b; };
+
+/* interpolate_2D1 (3D), src/fluid.c:214-245; interpolate_1D1 (2D), :171-191 */
+template <int DIM>
+__device__ Grad2 interpolate_perp (const DevTree & T, const double * __restrict__ F,
+				   int cell, int d1, int d2, double x, double y)
+{
+  Grad2 p = { 1., 0. };
+  const int nd = 2*DIM;
+  if (DIM == 3) {
+    int f1 = T.neighbor[(int64_t) cell*nd + d1];
+    if (f1 >= 0) {
+      double y1 = 1.;
+      double p1 = average_neighbor_value<DIM> (T, F, cell, f1, d1, &y1);
+      if (p1 != GFSB200_NODATA) {
+	double a1 = y/y1;
+	p.b += a1*p1;
+	p.a -= a1;
+      }
+    }
+  }
+  int f2 = T.neighbor[(int64_t) cell*nd + d2];
+  if (f2 >= 0) {
+    double x2 = 1.;
+    double p2 = average_neighbor_value<DIM> (T, F, cell, f2, d2, &x2);
+    if (p2 != GFSB200_NODATA) {
+      double a2 = x/x2;
+      p.b += a2*p2;
+      p.a -= a2;
+    }
+  }
+  return p;
+}
+
+/* gfs_neighbor_value, src/fluid.c:364-396 */
+template <int DIM>
+__device__ double neighbor_value (const DevTree & T, const double * __restrict__ F,
+				  int cell, int nb, int d, double * x)
+{
+  if (T.level[nb] == T.level[cell])
+    return average_neighbor_value<DIM> (T, F, cell, nb, d, x);
+  if (F[nb] == GFSB200_NODATA)
+    return GFSB200_NODATA;
+  /* coarser neighbour: perpendicular[d][child id], src/fluid.c:264-278 --
+     the directions in which `cell` sits inside its parent along the other
+     axes, in cyclic axis order */
+  const int n = child_id (T, cell), axis = d >> 1;
+  Grad2 vc;
+  if (DIM == 3) {
+    int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
+    int d1 = 2*a1 + (child_positive (n, a1) ? 0 : 1);
+    int d2 = 2*a2 + (child_positive (n, a2) ? 0 : 1);
+    vc = interpolate_perp<DIM> (T, F, nb, d1, d2, 1./4., 1./4.);
+  }
+  else {
+    int a1 = 1 - axis;
+    int dp = 2*a1 + (child_positive (n, a1) ? 0 : 1);
+    vc = interpolate_perp<DIM> (T, F, nb, 0, dp, 1./4., 0.);
+  }
+  *x = 3./2.;
+  return vc.a*F[nb] + vc.b;
+}
+
+/* gfs_center_gradient, src/fluid.c:434-475 */
+template <int DIM>
+__device__ double center_gradient (const DevTree & T, const double * __restrict__ F, int cell, int c)
+{
+  const int nd = 2*DIM, d = 2*c;
+  const int f1 = T.neighbor[(int64_t) cell*nd + (d ^ 1)];
+  const int f2 = T.neighbor[(int64_t) cell*nd + d];
+  const double v0 = F[cell];
+  if (f1 >= 0) {
+    double x1 = 1., v1;
+    v1 = neighbor_value<DIM> (T, F, cell, f1, d ^ 1, &x1);
+    if (f2 >= 0) {
+      double x2 = 1., v2;
+      v2 = neighbor_value<DIM> (T, F, cell, f2, d, &x2);
+      return (x1*x1*(v2 - v0) + x2*x2*(v0 - v1))/(x1*x2*(x2 + x1));
+    }
+    return (v0 - v1)/x1;
+  }
+  if (f2 >= 0) {
+    double x2 = 1.;
+    return (neighbor_value<DIM> (T, F, cell, f2, d, &x2) - v0)/x2;
+  }
+  return 0.;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256)
+vorticity_kernel (DevTree T, DevField fld)
+{
+  const int stride = gridDim.x*blockDim.x;
+  for (int cell = blockIdx.x*blockDim.x + threadIdx.x; cell < T.n_cells; cell += stride) {
+    const unsigned info = T.info[cell];
+    const bool box_leaf = (info & (GFSB200_CELL_LEAF | GFSB200_CELL_BOUNDARY)) == GFSB200_CELL_LEAF;
+    double wx = 0., wy = 0., wz = 0.;
+    if (box_leaf) {
+      /* ftt_cell_size: 2^-level, exact */
+      const double size = __longlong_as_double ((long long) (1023 - T.level[cell]) << 52);
+      if (DIM == 2)
+	wz = (center_gradient<DIM> (T, fld.u[1], cell, 0) -
+	      center_gradient<DIM> (T, fld.u[0], cell, 1))/size;
+      else {
+	wx = (center_gradient<DIM> (T, fld.u[2], cell, 1) -
+	      center_gradient<DIM> (T, fld.u[1], cell, 2))/size;
+	wy = (center_gradient<DIM> (T, fld.u[0], cell, 2) -
+	      center_gradient<DIM> (T, fld.u[2], cell, 0))/size;
+	wz = (center_gradient<DIM> (T, fld.u[1], cell, 0) -
+	      center_gradient<DIM> (T, fld.u[0], cell, 1))/size;
+      }
+    }
+    if (DIM == 2)
+      fld.vort[cell] = wz;
+    else {
+      double2 * o = reinterpret_cast<double2 *> (fld.vort + (int64_t) cell*4);
+      o[0] = make_double2 (wx, wy);
+      o[1] = make_double2 (wz, 0.);
+    }
+  }
+}
+
+/* gfs_cell_corner_value, src/fluid.c:3081-3101: val = sum w_i v_i in stencil
+ * order.  (The GFS_NODATA early-out returns the *calling* leaf's own value,
+ * which a shared vertex cannot represent: a vertex whose stencil touches
+ * NODATA is stored as NODATA and resolved by the particle kernel.) */
+template <int DIM>
+__global__ void __launch_bounds__(256)
+vertex_values_kernel (DevTree T, DevField fld)
+{
+  const int stride = gridDim.x*blockDim.x;
+  for (int v = blockIdx.x*blockDim.x + threadIdx.x; v < T.n_vertices; v += stride) {
+    const int b = T.vtx_off[v], e = T.vtx_off[v + 1];
+    double s0 = 0., s1 = 0., s2 = 0.;
+    bool nodata = false;
+    for (int i = b; i < e; i++) {
+      const int c = T.vtx_cell[i];
+      const double w = T.vtx_w[i];
+      const double v0 = fld.u[0][c], v1 = fld.u[1][c];
+      nodata |= (v0 == GFSB200_NODATA) | (v1 == GFSB200_NODATA);
+      s0 += w*v0;
+      s1 += w*v1;
+      if (DIM == 3) {
+	const double v2 = fld.u[2][c];
+	nodata |= (v2 == GFSB200_NODATA);
+	s2 += w*v2;
+      }
+    }
+    if (nodata)
+      s0 = s1 = s2 = GFSB200_NODATA;
+    if (DIM == 2)
+      reinterpret_cast<double2 *> (fld.vtx_val)[v] = make_double2 (s0, s1);
+    else {
+      double2 * o = reinterpret_cast<double2 *> (fld.vtx_val + (int64_t) v*4);
+      o[0] = make_double2 (s0, s1);
+      o[1] = make_double2 (s2, 0.);
+    }
+  }
+}
+
+} // namespace
+
+extern "C" void gfsb200_launch_cell_pass (const DevTree * T, const DevField * fld, int n_sm,
+					  cudaStream_t stream)
+{
+  const int threads = 256;
+  int gv = (T->n_vertices + threads - 1)/threads, gc = (T->n_cells + threads - 1)/threads;
+  const int cap = n_sm*8;             /* grid-stride: at most 8 CTAs of 256 threads per SM */
+  if (gv > cap) gv = cap;
+  if (gc > cap) gc = cap;
+  if (gv < 1) gv = 1;
+  if (gc < 1) gc = 1;
+  if (T->dim == 2) {
+    vertex_values_kernel<2><<<gv, threads, 0, stream>>> (*T, *fld);
+    vorticity_kernel<2><<<gc, threads, 0, stream>>> (*T, *fld);
+  }
+  else {
+    vertex_values_kernel<3><<<gv, threads, 0, stream>>> (*T, *fld);
+    vorticity_kernel<3><<<gc, threads, 0, stream>>> (*T, *fld);
+  }
+}

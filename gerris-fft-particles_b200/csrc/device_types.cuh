@@ -1,0 +1,69 @@
+/* device_types.cuh -- plain structs passed by value to the kernels */
+#ifndef GFSB200_DEVICE_TYPES_CUH
+#define GFSB200_DEVICE_TYPES_CUH
+
+#include <stdint.h>
+#include "gfsb200.h"
+
+#define GFSB200_NODATA 1.7976931348623157e308   /* GFS_NODATA = G_MAXDOUBLE, src/utils.h:80 */
+#define GFSB200_MAX_DEV_ROOTS 27
+
+/* child0 encoding on the device: >= 0 first child, -1 leaf, -2 destroyed cell
+ * (so that the descent sees FTT_CELL_IS_DESTROYED without a second load) */
+#define CHILD_LEAF      (-1)
+#define CHILD_DESTROYED (-2)
+
+struct DevTree {
+  int dim, n_cells, n_roots, n_box_roots;
+  int root_level;
+  int top_levels;              /* complete_level - root_level: levels resolved arithmetically */
+  int top_start;               /* level_start of the complete level */
+  int single_box;              /* locate array has exactly one slot holding box root 0 */
+  double root_size;            /* ftt_level_size (root_level) */
+  double root_pos[GFSB200_MAX_DEV_ROOTS][3];
+  /* GfsLocateArray */
+  double la_min[3], la_h;
+  int la_n[3];
+  const int32_t * la_slot;
+  /* topology */
+  const int32_t * child0;      /* encoded as above */
+  const int32_t * neighbor;    /* [n_cells][2*dim] */
+  const uint8_t * level;       /* absolute level */
+  const uint8_t * info;        /* flags (low 3 bits) | child id << 4 */
+  /* stencils */
+  int n_vertices;
+  const int32_t * vtx_off;
+  const int32_t * vtx_cell;
+  const double  * vtx_w;
+  const int32_t * leaf_vtx;    /* [n_cells][2^dim] */
+};
+
+struct DevField {
+  const double * u[3];         /* cell-centred U,V,W in flat-tree order */
+  const double * alpha;        /* optional per-cell 1/rho */
+  const double * mu;           /* optional per-cell viscosity */
+  /* derived per field update */
+  double * vtx_val;            /* 3D: [n_vertices][4] (u,v,w,pad); 2D: [n_vertices][2] */
+  double * vort;               /* 3D: [n_cells][4] (wx,wy,wz,pad); 2D: [n_cells] (wz) */
+};
+
+struct DevParticles {
+  int64_t n;
+  double * x, * y, * z, * vx, * vy, * vz, * mass, * volume;
+  double * fx, * fy, * fz;     /* optional (record_forces) */
+  int32_t * cell;              /* optional (record_cells) */
+  uint32_t * id;
+};
+
+struct DevStep {
+  double dt;
+  int n_forces;
+  unsigned forces;             /* force kinds in list order, 4 bits each (no indexed array: keeps
+				  the by-value struct in the constant bank) */
+  int need_velocity;           /* any drag/lift in the list */
+  double rho, mu;
+  double g[3];
+  double cd_const, cl_const;   /* NaN = built-in law */
+};
+
+#endif

@@ -1,0 +1,693 @@
+/* particle_kernels.cu -- the per-particle kernels (sm_100a).
+ *
+ *   step_kernel        fused locate + interpolate + forces + integrate
+ *                      = gfs_particulate_event, modules/particulatecommon.c:768-842,
+ *                        over every member of the GfsParticleList
+ *   locate_kernel      batched gfs_domain_locate (src/domain.c:2623-2638)
+ *   interpolate_kernel batched locate + gfs_interpolate (src/fluid.c:2697-2710)
+ *   deposit kernels    GfsParticulateField / GfsSourceParticulate (single-cell limit)
+ *   gather kernels     SoA permutation for the cell sort and the cull
+ *
+ * Data flow of step_kernel per particle: 8 coalesced fp64 loads
+ * (x,y,z,vx,vy,vz,m,V), point location (arithmetic over the complete top
+ * levels of the tree, then a child-index descent through L2-resident child0),
+ * 2^dim vertex ids + 2^dim (u,v,w) vertex gathers + 1 vorticity gather (all
+ * L1/L2 hits when particles are kept sorted by cell), ~250 fp64 instructions,
+ * 6 coalesced fp64 stores.  Algorithmic HBM traffic: 112 B/particle-step in
+ * 3D, 80 B in 2D.  No tensor cores: nothing here is a
+ * contraction.
+ */
+#include <cub/cub.cuh>
+#include "device_types.cuh"
+
+namespace {
+
+/* ------------------------------------------------------------------ */
+/* point location                                                       */
+
+struct Located {
+  int cell;            /* flat index, -1 = outside the domain */
+  double cx, cy, cz;   /* exact centre of the leaf */
+  double half;         /* half its size */
+};
+
+/* spread the low 10 bits of v to every third bit */
+__device__ __forceinline__ unsigned spread3 (unsigned v)
+{
+  v &= 0x3ff;
+  v = (v | (v << 16)) & 0x030000ff;
+  v = (v | (v << 8))  & 0x0300f00f;
+  v = (v | (v << 4))  & 0x030c30c3;
+  v = (v | (v << 2))  & 0x09249249;
+  return v;
+}
+
+/* spread the low 16 bits of v to every second bit */
+__device__ __forceinline__ unsigned spread2 (unsigned v)
+{
+  v &= 0xffff;
+  v = (v | (v << 8)) & 0x00ff00ff;
+  v = (v | (v << 4)) & 0x0f0f0f0f;
+  v = (v | (v << 2)) & 0x33333333;
+  v = (v | (v << 1)) & 0x55555555;
+  return v;
+}
+
+/* Number of level thresholds  lo + k*h (k = 1..n-1)  that are strictly below
+ * p, i.e. the column the reference's strict-'>' descent (src/ftt.c:1556-1570)
+ * ends in after log2(n) levels.  The quotient gives a candidate that can be
+ * off by one when p - lo rounds; the two exact comparisons repair it, so the
+ * result is bit-identical to the descent (thresholds are exact dyadics). */
+__device__ __forceinline__ int column (double p, double lo, double h, double inv_h, int n)
+{
+  int k = (int) floor ((p - lo)*inv_h);
+  k = max (0, min (n - 1, k));
+  if (k < n - 1 && p > lo + (k + 1)*h)
+    k++;
+  else if (k > 0 && !(p > lo + k*h))
+    k--;
+  return k;
+}
+
+template <int DIM>
+__device__ __forceinline__ Located locate (const DevTree & T, double x, double y, double z)
+{
+  Located L;
+  L.cell = -1;
+  L.cx = L.cy = L.cz = 0.; L.half = 0.;
+  if (!(x == x && y == y && z == z))      /* NaN: floor() -> INT_MIN -> outside in the reference */
+    return L;
+
+  /* GfsLocateArray, src/domain.c:43-80: i_c = floor ((p_c - min_c)/h) */
+  int root;
+  if (T.single_box) {
+    int ix = (int) floor ((x - T.la_min[0])/T.la_h);
+    int iy = (int) floor ((y - T.la_min[1])/T.la_h);
+    int iz = DIM == 3 ? (int) floor ((z - T.la_min[2])/T.la_h) : 0;
+    if ((ix | iy | iz) != 0)
+      return L;
+    root = 0;
+  }
+  else {
+    int ix = (int) floor ((x - T.la_min[0])/T.la_h);
+    int iy = (int) floor ((y - T.la_min[1])/T.la_h);
+    if (ix < 0 || ix >= T.la_n[0] || iy < 0 || iy >= T.la_n[1])
+      return L;
+    int index = ix*T.la_n[1] + iy;
+    if (DIM == 3) {
+      int iz = (int) floor ((z - T.la_min[2])/T.la_h);
+      if (iz < 0 || iz >= T.la_n[2])
+	return L;
+      index = index*T.la_n[2] + iz;
+    }
+    root = T.la_slot[index];
+    if (root < 0)
+      return L;
+  }
+
+  /* ftt_cell_locate, src/ftt.c:1535-1574: inclusive root test ... */
+  double cx = T.root_pos[root][0], cy = T.root_pos[root][1], cz = DIM == 3 ? T.root_pos[root][2] : 0.;
+  double half = T.root_size/2.;
+  if (x > cx + half || x < cx - half || y > cy + half || y < cy - half ||
+      (DIM == 3 && (z > cz + half || z < cz - half)))
+    return L;
+
+  int cell = root;
+  if (T.top_levels > 0) {
+    /* ... the first top_levels levels of the descent, resolved arithmetically
+       because every GfsBox tree is complete down to that level */
+    const int n = 1 << T.top_levels;
+    const double h = T.root_size/n, inv_h = n/T.root_size;
+    const int kx = column (x, cx - half, h, inv_h, n);
+    const int ky = column (y, cy - half, h, inv_h, n);
+    /* child digit per level: bit0 = (x > c), bit1 = !(y > c), bit2 = !(z > c) */
+    unsigned key;
+    if (DIM == 3) {
+      const int kz = column (z, cz - half, h, inv_h, n);
+      key = spread3 (kx) | (spread3 (~ky & (n - 1)) << 1) | (spread3 (~kz & (n - 1)) << 2);
+      cz = (cz - half) + (kz + 0.5)*h;
+    }
+    else
+      key = spread2 (kx) | (spread2 (~ky & (n - 1)) << 1);
+    cx = (cx - half) + (kx + 0.5)*h;
+    cy = (cy - half) + (ky + 0.5)*h;
+    half = h/2.;
+    cell = T.top_start + (root << (DIM*T.top_levels)) + (int) key;
+  }
+
+  /* ... then strict-'>' descent with exactly tracked dyadic centres */
+  int c0;
+  while ((c0 = __ldg (T.child0 + cell)) >= 0) {
+    half *= 0.5;
+    const bool px = x > cx, py = y > cy;
+    int n = (px ? 1 : 0) | (py ? 0 : 2);
+    cx += px ? half : -half;
+    cy += py ? half : -half;
+    if (DIM == 3) {
+      const bool pz = z > cz;
+      n |= pz ? 0 : 4;
+      cz += pz ? half : -half;
+    }
+    cell = c0 + n;
+  }
+  if (c0 == CHILD_DESTROYED)
+    return L;
+  L.cell = cell;
+  L.cx = cx; L.cy = cy; L.cz = cz; L.half = half;
+  return L;
+}
+
+/* ------------------------------------------------------------------ */
+/* interpolation                                                        */
+
+__device__ __forceinline__ double lerp (double a, double b, double t)
+{
+  return fma (t, b - a, a);
+}
+
+/* Per-leaf NODATA fallback of gfs_cell_corner_value (src/fluid.c:3094-3097) */
+__device__ __forceinline__ double resolve (double v, const double * __restrict__ F, int cell)
+{
+  return __double2hiint (v) == 0x7fefffff && __double2loint (v) == (int) 0xffffffff ? F[cell] : v;
+}
+
+/* gfs_interpolate (src/fluid.c:2697-2710) of U,V,W at p inside leaf L.
+ * 3D: trilinear in the 8 corner values (gfs_interpolate_from_corners,
+ * :2666-2681, written as nested linear interpolations);
+ * 2D: centre value + the two diagonal triangles (:2655-2664). */
+template <int DIM>
+__device__ __forceinline__ void interpolate (const DevTree & T, const DevField & fld,
+					     const Located & L, double x, double y, double z,
+					     double & u, double & v, double & w)
+{
+  const double inv = 1./L.half;     /* half is a power of two: exact */
+  if (DIM == 3) {
+    const int4 * vi = reinterpret_cast<const int4 *> (T.leaf_vtx + (int64_t) L.cell*8);
+    const int4 i0 = __ldg (vi), i1 = __ldg (vi + 1);
+    const int id[8] = { i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w };
+    double fu[8], fv[8], fw[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const double2 * p = reinterpret_cast<const double2 *> (fld.vtx_val + (int64_t) id[k]*4);
+      const double2 a = __ldg (p), b = __ldg (p + 1);
+      fu[k] = a.x; fv[k] = a.y; fw[k] = b.x;
+    }
+    if (__double2hiint (fu[0]) == 0x7fefffff || __double2hiint (fu[1]) == 0x7fefffff ||
+	__double2hiint (fu[2]) == 0x7fefffff || __double2hiint (fu[3]) == 0x7fefffff ||
+	__double2hiint (fu[4]) == 0x7fefffff || __double2hiint (fu[5]) == 0x7fefffff ||
+	__double2hiint (fu[6]) == 0x7fefffff || __double2hiint (fu[7]) == 0x7fefffff) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+	fu[k] = resolve (fu[k], fld.u[0], L.cell);
+	fv[k] = resolve (fv[k], fld.u[1], L.cell);
+	fw[k] = resolve (fw[k], fld.u[2], L.cell);
+      }
+    }
+    /* t in [0,1] along each axis: (1 + (p - o)/(h/2))/2 */
+    const double tx = fma (x - L.cx, 0.5*inv, 0.5);
+    const double ty = fma (y - L.cy, 0.5*inv, 0.5);
+    const double tz = fma (z - L.cz, 0.5*inv, 0.5);
+    /* corners: 0(-,-,+) 1(+,-,+) 2(+,+,+) 3(-,+,+) 4(-,-,-) 5(+,-,-) 6(+,+,-) 7(-,+,-) */
+    u = lerp (lerp (lerp (fu[4], fu[5], tx), lerp (fu[7], fu[6], tx), ty),
+	      lerp (lerp (fu[0], fu[1], tx), lerp (fu[3], fu[2], tx), ty), tz);
+    v = lerp (lerp (lerp (fv[4], fv[5], tx), lerp (fv[7], fv[6], tx), ty),
+	      lerp (lerp (fv[0], fv[1], tx), lerp (fv[3], fv[2], tx), ty), tz);
+    w = lerp (lerp (lerp (fw[4], fw[5], tx), lerp (fw[7], fw[6], tx), ty),
+	      lerp (lerp (fw[0], fw[1], tx), lerp (fw[3], fw[2], tx), ty), tz);
+  }
+  else {
+    const int4 id = __ldg (reinterpret_cast<const int4 *> (T.leaf_vtx + (int64_t) L.cell*4));
+    const double2 * vv = reinterpret_cast<const double2 *> (fld.vtx_val);
+    double2 f0 = __ldg (vv + id.x), f1 = __ldg (vv + id.y), f2 = __ldg (vv + id.z), f3 = __ldg (vv + id.w);
+    const double c0 = fld.u[0][L.cell], c1 = fld.u[1][L.cell];
+    f0.x = resolve (f0.x, fld.u[0], L.cell); f0.y = resolve (f0.y, fld.u[1], L.cell);
+    f1.x = resolve (f1.x, fld.u[0], L.cell); f1.y = resolve (f1.y, fld.u[1], L.cell);
+    f2.x = resolve (f2.x, fld.u[0], L.cell); f2.y = resolve (f2.y, fld.u[1], L.cell);
+    f3.x = resolve (f3.x, fld.u[0], L.cell); f3.y = resolve (f3.y, fld.u[1], L.cell);
+    const double px = (x - L.cx)*inv, py = (y - L.cy)*inv;
+    const double a = (px + py)/2., b = (py - px)/2.;
+    double uu = c0, vv2 = c1;
+    if (a > 0.) { uu += a*(f2.x - c0); vv2 += a*(f2.y - c1); }
+    else        { uu -= a*(f0.x - c0); vv2 -= a*(f0.y - c1); }
+    if (b > 0.) { uu += b*(f3.x - c0); vv2 += b*(f3.y - c1); }
+    else        { uu -= b*(f1.x - c0); vv2 -= b*(f1.y - c1); }
+    u = uu; v = vv2; w = 0.;
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/* forces: modules/particulatecommon.c:423-490 (lift), 519-588 (drag),
+ * 617-655 (buoyancy), accumulated as in compute_forces (:737-751)      */
+
+template <int DIM, bool ONFLUID>
+__device__ __forceinline__ void total_force (const DevTree & T, const DevField & fld,
+					     const DevStep & S, const Located & L,
+					     double x, double y, double z,
+					     double vx, double vy, double vz,
+					     double mass, double volume,
+					     double & Fx, double & Fy, double & Fz, double & rho_out)
+{
+  Fx = Fy = Fz = 0.;
+  const double rho = fld.alpha ? 1./fld.alpha[L.cell] : S.rho;
+  rho_out = rho;
+  double rx = 0., ry = 0., rz = 0.;
+  if (S.need_velocity) {
+    double u, v, w;
+    interpolate<DIM> (T, fld, L, x, y, z, u, v, w);
+    rx = u - vx; ry = v - vy; rz = DIM == 3 ? w - vz : 0.;
+  }
+  for (int k = 0; k < S.n_forces; k++) {
+    const int kind = (S.forces >> (4*k)) & 15;
+    double fx = 0., fy = 0., fz = 0.;
+    if (kind == GFSB200_FORCE_DRAG) {
+      const double mu = fld.mu ? fld.mu[L.cell] : S.mu;
+      if (mu != 0.) {
+	const double dia = 2.*cbrt (3.0*volume/4.0/M_PI);
+	const double nrm = sqrt (DIM == 3 ? rx*rx + ry*ry + rz*rz : rx*rx + ry*ry);
+	const double Re = nrm*dia*rho/mu;
+	double cd;
+	bool zero = false;
+	if (S.cd_const == S.cd_const)
+	  cd = S.cd_const;
+	else {
+	  zero = Re < 1e-8;
+	  const double s = sqrt (Re);
+	  cd = Re < 50.0 ? 16.*(1. + 0.15*s)/Re : 48.*(1. - 2.21/s)/Re;
+	}
+	if (!zero) {
+	  const double k3 = 3./(4.*dia)*cd*nrm;
+	  fx = k3*rx*rho; fy = k3*ry*rho;
+	  if (DIM == 3) fz = k3*rz*rho;
+	}
+      }
+    }
+    else if (kind == GFSB200_FORCE_LIFT) {
+      const double cl = S.cl_const == S.cl_const ? S.cl_const : 0.5;
+      if (DIM == 3) {
+	const double2 * p = reinterpret_cast<const double2 *> (fld.vort + (int64_t) L.cell*4);
+	const double2 a = __ldg (p), b = __ldg (p + 1);
+	const double wx = a.x, wy = a.y, wz = b.x;
+	fx = rho*cl*(ry*wz - rz*wy);
+	fy = rho*cl*(rz*wx - rx*wz);
+	fz = rho*cl*(rx*wy - ry*wx);
+      }
+      else {
+	const double wz = __ldg (fld.vort + L.cell);
+	fx = rho*cl*ry*wz;
+	fy = -rho*cl*rx*wz;
+      }
+    }
+    else if (kind == GFSB200_FORCE_BUOY) {
+      if (!ONFLUID) {                   /* compute_forces_onfluid skips GfsForceBuoy, :753-765 */
+	const double drho = mass/volume - rho;
+	fx = drho*S.g[0]; fy = drho*S.g[1];
+	if (DIM == 3) fz = drho*S.g[2];
+      }
+    }
+    Fx = fx*volume + Fx;
+    Fy = fy*volume + Fy;
+    if (DIM == 3) Fz = fz*volume + Fz;
+  }
+}
+
+/* ------------------------------------------------------------------ */
+
+template <int DIM, bool REC_CELL, bool REC_FORCE>
+__global__ void __launch_bounds__(256)
+step_kernel (DevTree T, DevField fld, DevParticles P, DevStep S)
+{
+  const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= P.n)
+    return;
+  double x = P.x[i], y = P.y[i], z = DIM == 3 ? P.z[i] : 0.;
+  double vx = P.vx[i], vy = P.vy[i], vz = DIM == 3 ? P.vz[i] : 0.;
+  const double mass = P.mass[i], volume = P.volume[i];
+
+  const Located L = locate<DIM> (T, x, y, z);
+  if (REC_CELL)
+    P.cell[i] = L.cell;
+  if (L.cell < 0)     /* outside: gfs_particle_list_event removes it first (:987) */
+    return;
+
+  double Fx, Fy, Fz, rho;
+  total_force<DIM, false> (T, fld, S, L, x, y, z, vx, vy, vz, mass, volume, Fx, Fy, Fz, rho);
+  if (REC_FORCE) {
+    P.fx[i] = Fx; P.fy[i] = Fy; P.fz[i] = Fz;
+  }
+
+  /* x += v dt/2 ; v += F dt/m ; x += v dt/2   (:828-839) */
+  const double dt = S.dt;
+  x += vx*dt/2.; vx += Fx*dt/mass; x += vx*dt/2.;
+  y += vy*dt/2.; vy += Fy*dt/mass; y += vy*dt/2.;
+  P.x[i] = x; P.y[i] = y; P.vx[i] = vx; P.vy[i] = vy;
+  if (DIM == 3) {
+    z += vz*dt/2.; vz += Fz*dt/mass; z += vz*dt/2.;
+    P.z[i] = z; P.vz[i] = vz;
+  }
+}
+
+/* passive tracers: gfs_domain_advect_point, src/domain.c:2764-2788 (RK2) */
+template <int DIM, bool REC_CELL>
+__global__ void __launch_bounds__(256)
+advect_kernel (DevTree T, DevField fld, DevParticles P, double dt)
+{
+  const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= P.n)
+    return;
+  const double x = P.x[i], y = P.y[i], z = DIM == 3 ? P.z[i] : 0.;
+  Located L = locate<DIM> (T, x, y, z);
+  if (REC_CELL)
+    P.cell[i] = L.cell;
+  if (L.cell < 0)
+    return;
+  double u, v, w;
+  interpolate<DIM> (T, fld, L, x, y, z, u, v, w);
+  const double x1 = x + dt*u/2., y1 = y + dt*v/2., z1 = DIM == 3 ? z + dt*w/2. : 0.;
+  L = locate<DIM> (T, x1, y1, z1);
+  if (L.cell < 0)
+    return;
+  interpolate<DIM> (T, fld, L, x1, y1, z1, u, v, w);
+  P.x[i] = x + dt*u;
+  P.y[i] = y + dt*v;
+  if (DIM == 3) P.z[i] = z + dt*w;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256)
+locate_kernel (DevTree T, int64_t n, const double * __restrict__ x, const double * __restrict__ y,
+	       const double * __restrict__ z, int32_t * __restrict__ cell)
+{
+  const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  cell[i] = locate<DIM> (T, x[i], y[i], DIM == 3 ? z[i] : 0.).cell;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256)
+interpolate_kernel (DevTree T, DevField fld, int64_t n, const double * __restrict__ x,
+		    const double * __restrict__ y, const double * __restrict__ z,
+		    double * __restrict__ u, double * __restrict__ v, double * __restrict__ w)
+{
+  const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const double px = x[i], py = y[i], pz = DIM == 3 ? z[i] : 0.;
+  const Located L = locate<DIM> (T, px, py, pz);
+  double a = GFSB200_NODATA, b = GFSB200_NODATA, c = GFSB200_NODATA;
+  if (L.cell >= 0) {
+    interpolate<DIM> (T, fld, L, px, py, pz, a, b, c);
+    /* gfs_interpolate returns NODATA when the cell's own value is (:2704-2705) */
+    if (fld.u[0][L.cell] == GFSB200_NODATA) a = GFSB200_NODATA;
+    if (fld.u[1][L.cell] == GFSB200_NODATA) b = GFSB200_NODATA;
+    if (DIM == 3 && fld.u[2][L.cell] == GFSB200_NODATA) c = GFSB200_NODATA;
+  }
+  if (u) u[i] = a;
+  if (v) v[i] = b;
+  if (w && DIM == 3) w[i] = c;
+}
+
+/* corner values of a list of leaves, for the parity tests:
+ * out[j][k] = vtx_val[leaf_vtx[cells[j]][k]].comp (NODATA resolved per leaf) */
+template <int DIM>
+__global__ void corner_values_kernel (DevTree T, DevField fld, int comp, int64_t n,
+				      const int32_t * __restrict__ cells, double * __restrict__ out)
+{
+  const int64_t j = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
+  const int nc = 1 << DIM;
+  if (j >= n*nc)
+    return;
+  const int cell = cells[j/nc], k = (int) (j % nc);
+  const int v = T.leaf_vtx[(int64_t) cell*nc + k];
+  double val = GFSB200_NODATA;
+  if (v >= 0) {
+    val = fld.vtx_val[(int64_t) v*(DIM == 3 ? 4 : 2) + comp];
+    val = resolve (val, fld.u[comp], cell);
+  }
+  out[j] = val;
+}
+
+/* ------------------------------------------------------------------ */
+/* deposition: one atomic per run of equal cells inside a warp          */
+
+/* Adds val to dst[cell] with one atomic per run of consecutive lanes that
+ * share the same cell (particles are kept sorted by cell, so runs are long).
+ * Lanes with cell < 0 contribute nothing. */
+__device__ __forceinline__ void run_atomic_add (double * __restrict__ dst, int cell, double val)
+{
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  /* run head = lowest lane of my run */
+  const int prev = __shfl_up_sync (full, cell, 1);
+  const bool head = lane == 0 || prev != cell;
+  const unsigned heads = __ballot_sync (full, head);
+  /* my run spans [my_head, next_head) */
+  const unsigned below = heads & (0xffffffffu >> (31 - lane));
+  const int my_head = 31 - __clz (below);
+  const unsigned above = lane == 31 ? 0u : heads & (0xffffffffu << (lane + 1));
+  const int run_end = above ? __ffs (above) - 1 : 32;
+  /* tree-sum inside the run: lane accumulates lane + o while inside run */
+  double s = val;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_down_sync (full, s, o);
+    if (lane + o < run_end)
+      s += t;
+  }
+  if (lane == my_head && cell >= 0)
+    atomicAdd (dst + cell, s);
+}
+
+/* GfsParticulateField with voidfraction_from_particles,
+ * modules/particulatecommon.c:1929-1957: v[cell] += V_p / V_cell */
+template <int DIM>
+__global__ void __launch_bounds__(256)
+deposit_volume_kernel (DevTree T, DevParticles P, double * __restrict__ field)
+{
+  const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
+  int cell = -1;
+  double val = 0.;
+  if (i < P.n) {
+    const Located L = locate<DIM> (T, P.x[i], P.y[i], DIM == 3 ? P.z[i] : 0.);
+    cell = L.cell;
+    if (cell >= 0) {
+      const double h = 2.*L.half;
+      val = P.volume[i]/(DIM == 3 ? h*h*h : h*h);    /* ftt_cell_volume */
+    }
+  }
+  run_atomic_add (field, cell, val);
+}
+
+/* GfsSourceParticulate in the single-cell limit,
+ * modules/particulatecommon.c:2158-2228: forces without buoyancy, then
+ * u_c[cell] -= F_c / rho / V_cell */
+template <int DIM>
+__global__ void __launch_bounds__(256)
+deposit_force_kernel (DevTree T, DevField fld, DevParticles P, DevStep S,
+		      double * __restrict__ f0, double * __restrict__ f1, double * __restrict__ f2)
+{
+  const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
+  int cell = -1;
+  double ax = 0., ay = 0., az = 0.;
+  if (i < P.n) {
+    const double x = P.x[i], y = P.y[i], z = DIM == 3 ? P.z[i] : 0.;
+    const Located L = locate<DIM> (T, x, y, z);
+    cell = L.cell;
+    if (cell >= 0) {
+      double Fx, Fy, Fz, rho;
+      total_force<DIM, true> (T, fld, S, L, x, y, z, P.vx[i], P.vy[i], DIM == 3 ? P.vz[i] : 0.,
+			      P.mass[i], P.volume[i], Fx, Fy, Fz, rho);
+      const double h = 2.*L.half;
+      const double cellvol = DIM == 3 ? h*h*h : h*h;
+      ax = -(Fx/rho/cellvol);
+      ay = -(Fy/rho/cellvol);
+      az = -(Fz/rho/cellvol);
+    }
+  }
+  run_atomic_add (f0, cell, ax);
+  run_atomic_add (f1, cell, ay);
+  if (DIM == 3)
+    run_atomic_add (f2, cell, az);
+}
+
+/* ------------------------------------------------------------------ */
+/* permutation gathers (sort by cell, cull)                             */
+
+__global__ void __launch_bounds__(256)
+gather_kernel (int64_t n, const int32_t * __restrict__ perm, int ncols,
+	       const double * const * __restrict__ src, double * const * __restrict__ dst,
+	       const uint32_t * __restrict__ id_src, uint32_t * __restrict__ id_dst)
+{
+  const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const int32_t j = perm[i];
+  for (int c = 0; c < ncols; c++)
+    dst[c][i] = src[c][j];
+  id_dst[i] = id_src[j];
+}
+
+__global__ void iota_kernel (int64_t n, int32_t * __restrict__ a)
+{
+  const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n) a[i] = (int32_t) i;
+}
+
+__global__ void iota_u32_kernel (int64_t n, uint32_t * __restrict__ a, uint32_t base)
+{
+  const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n) a[i] = base + (uint32_t) i;
+}
+
+__global__ void sort_keys_kernel (int64_t n, const int32_t * __restrict__ cell,
+				  uint32_t * __restrict__ key, uint32_t outside_key)
+{
+  const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n) key[i] = cell[i] < 0 ? outside_key : (uint32_t) cell[i];
+}
+
+__global__ void inside_flag_kernel (int64_t n, const int32_t * __restrict__ cell,
+				    uint8_t * __restrict__ flag)
+{
+  const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = cell[i] >= 0;
+}
+
+inline unsigned grid_for (int64_t n, int threads) { return (unsigned) ((n + threads - 1)/threads); }
+
+} // namespace
+
+/* ------------------------------------------------------------------ */
+/* launchers (C linkage, called from capi.cu)                           */
+
+extern "C" {
+
+void gfsb200_launch_step (const DevTree * T, const DevField * F, const DevParticles * P,
+			  const DevStep * S, int rec_cell, int rec_force, cudaStream_t st)
+{
+  if (P->n <= 0) return;
+  const int th = 256;
+  const unsigned g = grid_for (P->n, th);
+#define LAUNCH(D, RC, RF) step_kernel<D, RC, RF><<<g, th, 0, st>>> (*T, *F, *P, *S)
+  if (T->dim == 3) {
+    if (rec_cell) { if (rec_force) LAUNCH (3, true, true); else LAUNCH (3, true, false); }
+    else          { if (rec_force) LAUNCH (3, false, true); else LAUNCH (3, false, false); }
+  }
+  else {
+    if (rec_cell) { if (rec_force) LAUNCH (2, true, true); else LAUNCH (2, true, false); }
+    else          { if (rec_force) LAUNCH (2, false, true); else LAUNCH (2, false, false); }
+  }
+#undef LAUNCH
+}
+
+void gfsb200_launch_advect (const DevTree * T, const DevField * F, const DevParticles * P,
+			    double dt, int rec_cell, cudaStream_t st)
+{
+  if (P->n <= 0) return;
+  const int th = 256;
+  const unsigned g = grid_for (P->n, th);
+  if (T->dim == 3) {
+    if (rec_cell) advect_kernel<3, true><<<g, th, 0, st>>> (*T, *F, *P, dt);
+    else advect_kernel<3, false><<<g, th, 0, st>>> (*T, *F, *P, dt);
+  }
+  else {
+    if (rec_cell) advect_kernel<2, true><<<g, th, 0, st>>> (*T, *F, *P, dt);
+    else advect_kernel<2, false><<<g, th, 0, st>>> (*T, *F, *P, dt);
+  }
+}
+
+void gfsb200_launch_locate (const DevTree * T, int64_t n, const double * x, const double * y,
+			    const double * z, int32_t * cell, cudaStream_t st)
+{
+  if (n <= 0) return;
+  if (T->dim == 3) locate_kernel<3><<<grid_for (n, 256), 256, 0, st>>> (*T, n, x, y, z, cell);
+  else locate_kernel<2><<<grid_for (n, 256), 256, 0, st>>> (*T, n, x, y, z, cell);
+}
+
+void gfsb200_launch_interpolate (const DevTree * T, const DevField * F, int64_t n,
+				 const double * x, const double * y, const double * z,
+				 double * u, double * v, double * w, cudaStream_t st)
+{
+  if (n <= 0) return;
+  if (T->dim == 3)
+    interpolate_kernel<3><<<grid_for (n, 256), 256, 0, st>>> (*T, *F, n, x, y, z, u, v, w);
+  else
+    interpolate_kernel<2><<<grid_for (n, 256), 256, 0, st>>> (*T, *F, n, x, y, z, u, v, w);
+}
+
+void gfsb200_launch_corner_values (const DevTree * T, const DevField * F, int comp, int64_t n,
+				   const int32_t * cells, double * out, cudaStream_t st)
+{
+  if (n <= 0) return;
+  const int nc = 1 << T->dim;
+  if (T->dim == 3)
+    corner_values_kernel<3><<<grid_for (n*nc, 256), 256, 0, st>>> (*T, *F, comp, n, cells, out);
+  else
+    corner_values_kernel<2><<<grid_for (n*nc, 256), 256, 0, st>>> (*T, *F, comp, n, cells, out);
+}
+
+void gfsb200_launch_deposit_volume (const DevTree * T, const DevParticles * P, double * field,
+				    cudaStream_t st)
+{
+  if (P->n <= 0) return;
+  if (T->dim == 3) deposit_volume_kernel<3><<<grid_for (P->n, 256), 256, 0, st>>> (*T, *P, field);
+  else deposit_volume_kernel<2><<<grid_for (P->n, 256), 256, 0, st>>> (*T, *P, field);
+}
+
+void gfsb200_launch_deposit_force (const DevTree * T, const DevField * F, const DevParticles * P,
+				   const DevStep * S, double * f0, double * f1, double * f2,
+				   cudaStream_t st)
+{
+  if (P->n <= 0) return;
+  if (T->dim == 3)
+    deposit_force_kernel<3><<<grid_for (P->n, 256), 256, 0, st>>> (*T, *F, *P, *S, f0, f1, f2);
+  else
+    deposit_force_kernel<2><<<grid_for (P->n, 256), 256, 0, st>>> (*T, *F, *P, *S, f0, f1, f2);
+}
+
+void gfsb200_launch_gather (int64_t n, const int32_t * perm, int ncols, const double * const * src,
+			    double * const * dst, const uint32_t * id_src, uint32_t * id_dst,
+			    cudaStream_t st)
+{
+  if (n <= 0) return;
+  gather_kernel<<<grid_for (n, 256), 256, 0, st>>> (n, perm, ncols, src, dst, id_src, id_dst);
+}
+
+void gfsb200_launch_iota (int64_t n, int32_t * a, cudaStream_t st)
+{
+  if (n > 0) iota_kernel<<<grid_for (n, 256), 256, 0, st>>> (n, a);
+}
+
+void gfsb200_launch_iota_u32 (int64_t n, uint32_t * a, uint32_t base, cudaStream_t st)
+{
+  if (n > 0) iota_u32_kernel<<<grid_for (n, 256), 256, 0, st>>> (n, a, base);
+}
+
+void gfsb200_launch_sort_keys (int64_t n, const int32_t * cell, uint32_t * key,
+			       uint32_t outside_key, cudaStream_t st)
+{
+  if (n > 0) sort_keys_kernel<<<grid_for (n, 256), 256, 0, st>>> (n, cell, key, outside_key);
+}
+
+void gfsb200_launch_inside_flags (int64_t n, const int32_t * cell, uint8_t * flag, cudaStream_t st)
+{
+  if (n > 0) inside_flag_kernel<<<grid_for (n, 256), 256, 0, st>>> (n, cell, flag);
+}
+
+/* cub wrappers: pass tmp = NULL to query *tmp_bytes */
+cudaError_t gfsb200_cub_sort_pairs (void * tmp, size_t * tmp_bytes, const uint32_t * keys_in,
+				    uint32_t * keys_out, const int32_t * vals_in, int32_t * vals_out,
+				    int64_t n, int end_bit, cudaStream_t st)
+{
+  return cub::DeviceRadixSort::SortPairs (tmp, *tmp_bytes, keys_in, keys_out, vals_in, vals_out,
+					  (int) n, 0, end_bit, st);
+}
+
+cudaError_t gfsb200_cub_select_flagged (void * tmp, size_t * tmp_bytes, const int32_t * in,
+					const uint8_t * flags, int32_t * out, int32_t * n_selected,
+					int64_t n, cudaStream_t st)
+{
+  return cub::DeviceSelect::Flagged (tmp, *tmp_bytes, in, flags, out, n_selected, (int) n, st);
+}
+
+} // extern "C"

@@ -1,0 +1,237 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes wrapper of oracle/_ref/libgfsoracle{2D,3D}.so.
+
+The oracle is the reference's own src/ftt.c + src/fluid.c object code plus the
+restated particulate layer of oracle/particulate_port.c (see its header for the
+file:line map and the "parity unpinned" note).  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product path never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+FORCE_DRAG, FORCE_LIFT, FORCE_BUOY = 1, 2, 3
+
+
+class StepParams(C.Structure):
+    _fields_ = [
+        ("dt", C.c_double), ("n_forces", C.c_int), ("force", C.c_int * 8),
+        ("rho", C.c_double), ("ivar_alpha", C.c_int), ("mu", C.c_double), ("ivar_mu", C.c_int),
+        ("g", C.c_double * 3), ("cd_const", C.c_double), ("cl_const", C.c_double),
+        ("pattern", C.c_int),
+    ]
+
+
+def step_params(dt, forces, rho=1.0, mu=0.0, g=(0.0, 0.0, 0.0), cd_const=float("nan"),
+                cl_const=float("nan"), pattern=0, ivar_alpha=-1, ivar_mu=-1) -> StepParams:
+    p = StepParams()
+    p.dt = dt
+    p.n_forces = len(forces)
+    for k, f in enumerate(forces):
+        p.force[k] = int(f)
+    p.rho, p.mu, p.ivar_alpha, p.ivar_mu = rho, mu, ivar_alpha, ivar_mu
+    for a in range(3):
+        p.g[a] = float(g[a])
+    p.cd_const, p.cl_const, p.pattern = cd_const, cl_const, pattern
+    return p
+
+
+_libs = {}
+
+
+def available(dim: int) -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", f"libgfsoracle{dim}D.so"))
+
+
+def load(dim: int) -> C.CDLL:
+    if dim in _libs:
+        return _libs[dim]
+    path = os.path.join(_HERE, "_ref", f"libgfsoracle{dim}D.so")
+    L = C.CDLL(path)
+    vp, u64, dbl, lng, i32 = C.c_void_p, C.c_uint64, C.c_double, C.c_long, C.c_int
+    sig = {
+        "ora_sim_new": (vp, [i32]), "ora_sim_destroy": (None, [vp]),
+        "ora_root": (u64, [vp]), "ora_boundary_root": (u64, [vp, i32]), "ora_dimension": (i32, []),
+        "ora_refine_uniform": (None, [vp, i32]), "ora_refine_ring": (None, [vp, i32, i32, dbl, dbl]),
+        "ora_refine_points": (i32, [vp, i32, vp, vp, vp, vp]),
+        "ora_corner_sweep": (None, [vp]), "ora_add_boundary": (None, [vp, i32]),
+        "ora_match_boundaries": (None, [vp]), "ora_finalize": (None, [vp]),
+        "ora_locate_array": (None, [vp, vp, vp, vp]),
+        "ora_locate": (None, [vp, lng, vp, vp, vp, vp]),
+        "ora_cell_info": (None, [u64, vp, vp, vp, vp]),
+        "ora_set_values": (None, [vp, i32, lng, vp, vp]), "ora_get_values": (None, [vp, i32, lng, vp, vp]),
+        "ora_neighbor": (u64, [u64, i32]), "ora_count": (lng, [vp, i32]),
+        "ora_interpolate": (None, [vp, i32, lng, vp, vp, vp, vp]),
+        "ora_corner_interpolator": (i32, [vp, u64, i32, vp, vp]),
+        "ora_corner_values": (None, [vp, i32, lng, vp, vp]),
+        "ora_center_gradient": (None, [vp, i32, i32, lng, vp, vp]),
+        "ora_vorticity": (None, [vp, lng, vp, vp]),
+        "ora_list_new": (vp, [lng] + [vp] * 8), "ora_list_destroy": (None, [vp]),
+        "ora_list_size": (lng, [vp]), "ora_list_get": (None, [vp] + [vp] * 10),
+        "ora_list_cull": (lng, [vp, vp]),
+        "ora_list_step": (None, [vp, vp, C.POINTER(StepParams), i32]),
+        "ora_deposit_volume": (None, [vp, vp, i32]),
+        "ora_deposit_force": (None, [vp, vp, C.POINTER(StepParams), i32]),
+        "ora_advect_points": (None, [vp, lng, vp, vp, vp, dbl]),
+        "ora_max_threads": (i32, []),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+    _libs[dim] = L
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Sim:
+    """One single-box reference domain (OraSim) with nvar cell variables;
+    variables 0,1,2 are U,V,W (U,V in 2D)."""
+
+    def __init__(self, dim: int, nvar: int = 8):
+        self.dim, self.L = dim, load(dim)
+        self.h = C.c_void_p(self.L.ora_sim_new(nvar))
+        self.nvar = nvar
+        self.sides = []
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.ora_sim_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # construction, in Gerris' order: boundaries, refinement, corner sweep, match
+    def add_boundary(self, side):
+        self.L.ora_add_boundary(self.h, side)
+        self.sides.append(side)
+
+    def refine_uniform(self, level):
+        self.L.ora_refine_uniform(self.h, level)
+
+    def refine_ring(self, minlevel, maxlevel, R=0.25, factor=1.5):
+        self.L.ora_refine_ring(self.h, minlevel, maxlevel, R, factor)
+
+    def corner_sweep(self):
+        self.L.ora_corner_sweep(self.h)
+
+    def finalize(self):
+        self.L.ora_match_boundaries(self.h)
+        self.L.ora_finalize(self.h)
+
+    def roots(self):
+        """(FttCell* list, is_box list) in flat-tree root order"""
+        r = [self.L.ora_root(self.h)] + [self.L.ora_boundary_root(self.h, s) for s in self.sides]
+        return r, [1] + [0] * len(self.sides)
+
+    def count(self, leaves_only=False):
+        return self.L.ora_count(self.h, int(leaves_only))
+
+    # queries
+    def locate(self, x, y, z=None):
+        x, y, z = _f64(x), _f64(y), _f64(z)
+        out = np.zeros(len(x), dtype=np.uint64)
+        self.L.ora_locate(self.h, len(x), _p(x), _p(y), _p(z), _p(out))
+        return out
+
+    def set_values(self, ivar, cells, vals):
+        cells = np.ascontiguousarray(cells, dtype=np.uint64)
+        vals = _f64(vals)
+        self.L.ora_set_values(self.h, ivar, len(cells), _p(cells), _p(vals))
+
+    def get_values(self, ivar, cells):
+        cells = np.ascontiguousarray(cells, dtype=np.uint64)
+        out = np.empty(len(cells))
+        self.L.ora_get_values(self.h, ivar, len(cells), _p(cells), _p(out))
+        return out
+
+    def interpolate(self, ivar, x, y, z=None):
+        x, y, z = _f64(x), _f64(y), _f64(z)
+        out = np.empty(len(x))
+        self.L.ora_interpolate(self.h, ivar, len(x), _p(x), _p(y), _p(z), _p(out))
+        return out
+
+    def corner_interpolator(self, cell, k):
+        cells = (C.c_uint64 * 29)()
+        w = (C.c_double * 29)()
+        n = self.L.ora_corner_interpolator(self.h, int(cell), k, cells, w)
+        return list(cells[:n]), list(w[:n])
+
+    def corner_values(self, ivar, cells):
+        cells = np.ascontiguousarray(cells, dtype=np.uint64)
+        out = np.empty((len(cells), 2 ** self.dim))
+        self.L.ora_corner_values(self.h, ivar, len(cells), _p(cells), _p(out))
+        return out
+
+    def center_gradient(self, comp, ivar, cells):
+        cells = np.ascontiguousarray(cells, dtype=np.uint64)
+        out = np.empty(len(cells))
+        self.L.ora_center_gradient(self.h, comp, ivar, len(cells), _p(cells), _p(out))
+        return out
+
+    def vorticity(self, cells):
+        cells = np.ascontiguousarray(cells, dtype=np.uint64)
+        out = np.empty((len(cells), 3))
+        self.L.ora_vorticity(self.h, len(cells), _p(cells), _p(out))
+        return out
+
+    def advect_points(self, x, y, z, dt):
+        x, y, z = _f64(x).copy(), _f64(y).copy(), None if z is None else _f64(z).copy()
+        self.L.ora_advect_points(self.h, len(x), _p(x), _p(y), _p(z), dt)
+        return x, y, z
+
+
+class ParticleList:
+    """GfsParticleList stand-in: one heap object per particle."""
+
+    def __init__(self, sim: Sim, x, y, z, vx, vy, vz, mass, volume):
+        self.sim = sim
+        a = [_f64(v) for v in (x, y, z, vx, vy, vz, mass, volume)]
+        self.h = C.c_void_p(sim.L.ora_list_new(len(a[0]), *[_p(v) for v in a]))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.sim.L.ora_list_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def __len__(self):
+        return self.sim.L.ora_list_size(self.h)
+
+    def cull(self):
+        return self.sim.L.ora_list_cull(self.sim.h, self.h)
+
+    def step(self, params: StepParams, nthreads=1):
+        self.sim.L.ora_list_step(self.sim.h, self.h, C.byref(params), nthreads)
+
+    def get(self):
+        n = len(self)
+        d3 = self.sim.dim == 3
+        out = {k: np.empty(n) for k in ("x", "y", "vx", "vy", "fx", "fy", "fz")}
+        out["z"] = np.empty(n) if d3 else None
+        out["vz"] = np.empty(n) if d3 else None
+        ids = np.empty(n, dtype=np.uint32)
+        self.sim.L.ora_list_get(self.h, _p(out["x"]), _p(out["y"]), _p(out["z"]), _p(out["vx"]),
+                                _p(out["vy"]), _p(out["vz"]), _p(out["fx"]), _p(out["fy"]),
+                                _p(out["fz"]), _p(ids))
+        out["id"] = ids
+        return out
+
+    def deposit_volume(self, ivar):
+        self.sim.L.ora_deposit_volume(self.sim.h, self.h, ivar)
+
+    def deposit_force(self, params: StepParams, ivar0):
+        self.sim.L.ora_deposit_force(self.sim.h, self.h, C.byref(params), ivar0)
