@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the fused Gerris particulate hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2|C3|C5] [--particles n]
+                  [--two-way] [--impl b200|reference]
+
+A "step" is one gfs_particle_list_event-equivalent pass over the resident
+particle batch: the per-field-update cell pass (vertex velocity table +
+vorticity table; the fluid field changes every step in a coupled run, so it
+is redone every step here even though the synthetic field is frozen), the
+fused locate+interpolate+force+integrate kernel, a re-sort by cell every
+--resort steps, and with --two-way the void-fraction/force deposition plus an
+NCCL all-reduce of the deposited field.  At N=1 the workload is BASELINE
+config C2 (128^3 uniform octree, frozen Taylor-Green field, 10 M particles,
+drag+lift+buoyancy).  For N>1 particles are sharded (weak scaling: every rank
+holds the full per-GPU batch), tree and field are replicated.
+
+Prints ONE JSON line (rank 0).  `value` is whole-job particle-steps/s with
+inputs resident in HBM; `e2e` is the same metric through the host-buffer
+C-ABI call (H2D of the particle arrays and the field, D2H of the new state
+inside the timed region); `roofline` describes the fused step kernel;
+`cpu_baseline` is the oracle timed on this box's host cores.
+
+--impl reference times the reference's CPU implementation of the path
+(oracle/_ref: the reference's own ftt.c/fluid.c object code + the restated
+force/integrator layer, reference call pattern) with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+BYTES_PER_PARTICLE_STEP = {3: 112, 2: 80}
+COLS = ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_world(worlds, name, n_particles):
+    if name == "C2":
+        return worlds.make_c2(n_particles=n_particles or 10_000_000)
+    if name == "C3":
+        return worlds.make_c3(n_particles=n_particles or 10_000_000)
+    if name == "C4":
+        return worlds.make_c4(n_particles=n_particles or 50_000_000)
+    if name == "C5":
+        return worlds.make_c5(n_particles=n_particles or 200_000_000)
+    if name == "C1":
+        return worlds.make_c1(n_particles=n_particles or 1000)
+    raise SystemExit(f"unknown config {name}")
+
+
+# --------------------------------------------------------------------------
+# reference arm: the reference's CPU path (oracle/_ref), all host threads
+
+def oracle_world(ora, worlds, name):
+    """Reference-built tree + analytic field for the config, oracle only."""
+    sp = worlds.spec(name)
+    sim = ora.Sim(sp.dim, nvar=4)
+    m = sp.meta
+    if m["field"] == "lid":
+        for s in range(4):
+            sim.add_boundary(s)
+        sim.refine_uniform(m["level"])
+    elif m["field"] == "tg":
+        sim.refine_uniform(m["level"])
+    else:
+        sim.refine_ring(m["levels"][0], m["levels"][1], 0.25, 1.5)
+        sim.corner_sweep()
+    sim.finalize()
+    ptr, pos, level, leaf = sim.export_cells()
+    f = worlds.field_of(sp, pos)
+    for i in range(sp.dim):
+        sim.set_values(i, ptr, f[i])
+    return sp, sim
+
+
+def time_oracle(ora, worlds, helpers_params, sp, sim, n_sample, steps, warmup, threads, pattern=0):
+    parts = worlds.make_particles(sp, n_sample)
+    plist = ora.ParticleList(sim, *[parts[k] for k in COLS])
+    par = helpers_params(sp, pattern)
+    for _ in range(warmup):
+        plist.step(par, threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        plist.step(par, threads)
+    dt = time.perf_counter() - t0
+    return n_sample * steps / dt, dt
+
+
+def oracle_params_factory(ora):
+    fmap = {1: ora.FORCE_DRAG, 2: ora.FORCE_LIFT, 3: ora.FORCE_BUOY}
+
+    def make(sp, pattern):
+        return ora.step_params(sp.dt, [fmap[f] for f in sp.forces], rho=sp.rho, mu=sp.mu, g=sp.g, pattern=pattern)
+    return make
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pkg = entry.load_package()          # worlds.spec / analytic fields only: no product compute
+    ora = entry.load_oracle()
+    worlds = pkg.worlds
+    threads = ora.load(3).ora_max_threads()
+    sp, sim = oracle_world(ora, worlds, args.config)
+    mk = oracle_params_factory(ora)
+    # size the per-step sample so that one step takes about a second
+    rate, _ = time_oracle(ora, worlds, mk, sp, sim, 20_000, 1, 1, threads)
+    n_sample = int(min(sp.n_particles, max(20_000, rate * 1.0)))
+    value, dt = time_oracle(ora, worlds, mk, sp, sim, n_sample, args.steps, args.warmup, threads)
+    line = {
+        "impl": "reference", "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.config), "sample_particles_per_step": n_sample},
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": threads, "kind": "reference",
+                         "sample": f"{n_sample} particles/step of the {args.config} cloud x {args.steps} steps; "
+                                   "reference ftt.c+fluid.c object code + restated forces/integrator, "
+                                   "reference call pattern (6 locates, 9 interpolations, 6 gradients per "
+                                   "particle-step), OpenMP over particles"},
+        "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(cfg):
+    return {
+        "C1": "C1: 2D lid-style level-6 quadtree, 1k particles, drag",
+        "C2": "C2: 3D uniform level-7 octree (128^3), frozen Taylor-Green field, 10M one-way particles, drag+lift+buoyancy",
+        "C3": "C3: 3D adaptive octree levels 5-9 around a vortex ring, 10M particles, drag+lift+buoyancy",
+        "C4": "C4: two-way, adaptive octree levels 6-10, 50M particles, deposit + all-reduce",
+        "C5": "C5: 3D adaptive octree levels 6-10, 200M particles, drag+lift+buoyancy",
+    }[cfg]
+
+
+# --------------------------------------------------------------------------
+# B200 arm
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    pkg = entry.load_package()
+    capi, worlds = pkg.capi, pkg.worlds
+    world = build_world(worlds, args.config, args.particles)
+    n_local = world.n_particles                       # weak scaling: fixed per-GPU batch
+    ctx = capi.Context(local_rank)
+    ctx.upload_tree(world.tree)
+    ctx.upload_field(world.u, world.v, world.w)
+    parts = worlds.make_particles(world, n_local * world_size, rank, world_size)
+    n_local = len(parts["x"])
+    ctx.particles_upload(**parts)
+    ctx.sort()
+    ctx.synchronize()
+
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    par = world.step_params()
+    dep_tensor = None
+    if args.two_way and world_size > 1:
+        ptr, count = ctx.deposit_buffer()
+        # alias the C-ABI's deposit buffer as a tensor for the NCCL all-reduce
+        class _Alias:
+            __cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+        dep_tensor = torch.as_tensor(_Alias(), device=f"cuda:{local_rank}")
+
+    launches_per_step = 3 + (2 if args.two_way else 0)        # vertex + vorticity + step (+ 2 deposit)
+
+    def one_step(i):
+        ctx.refresh_field()
+        ctx.step(par)
+        if args.two_way:
+            ctx.deposit_volume()
+            ctx.deposit_force(par)
+            if dep_tensor is not None:
+                with torch.cuda.stream(stream):
+                    dist.all_reduce(dep_tensor)
+        if args.resort and (i + 1) % args.resort == 0:
+            ctx.sort()
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.timer_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        one_step(i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    kernel_ms, kernel_launches = ctx.timer_read()
+    clocks = sampler.stop() if rank == 0 else None
+    n_sorts = (args.steps // args.resort) if args.resort else 0
+
+    if world_size > 1:
+        t = torch.tensor([ms], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    total_particles = n_local * world_size
+    value = total_particles * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host buffers in, host buffers out, through the C-ABI -----------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    host = {k: torch.from_numpy(np.ascontiguousarray(parts[k])).pin_memory().numpy() for k in COLS if parts[k] is not None}
+    fields = [torch.from_numpy(np.ascontiguousarray(f)).pin_memory().numpy()
+              for f in (world.u, world.v, world.w) if f is not None]
+    h2d = sum(a.nbytes for a in host.values()) + sum(a.nbytes for a in fields)
+    d2h = n_local * 8 * 2 * world.dim
+
+    def e2e_step():
+        ctx.upload_field(*fields)                     # mirror U,V,W + cell pass
+        ctx.particles_upload(**{k: host.get(k) for k in COLS})
+        ctx.step(par)
+        out = ctx.particles_download()                # x,y,z,vx,vy,vz (+m,V) back on the host
+        return out
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world_size > 1:
+        t = torch.tensor([e2e_s], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = total_particles * e2e_steps / e2e_s
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        bps = BYTES_PER_PARTICLE_STEP[world.dim]
+        achieved = n_local * bps / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+        line = {
+            "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s",
+            "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.config), "particles_per_gpu": n_local,
+                       "cells": int(world.arrays.n_cells), "leaves": int(world.arrays.n_leaves),
+                       "vertices": int(world.arrays.n_vertices), "two_way": bool(args.two_way),
+                       "resort_every": args.resort, "sorts_in_timed_region": n_sorts,
+                       "cell_pass_every_step": True,
+                       "l2": "per-step particle stream (%.0f MB) exceeds the 126 MB L2" % (n_local * bps / 1e6)},
+            "roofline": {"bound": "hbm", "kernel": "step_kernel<3,false,false>" if world.dim == 3 else "step_kernel<2,false,false>",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_particle_step": bps,
+                         "kernel_ms": kernel_ms, "kernel_launches": kernel_launches},
+            "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                    "what": "gfsb200_upload_field + gfsb200_particles_upload (pinned host) + gfsb200_step + "
+                            "gfsb200_particles_download per step"},
+            "gpu_launches": args.steps * launches_per_step + n_sorts * 8,
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world_size == 1:
+            line["cpu_baseline"] = cpu_baseline(args, worlds)
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, worlds):
+    """The oracle on one host core, reference call pattern, bounded sample."""
+    ora = entry.load_oracle()
+    sp, sim = oracle_world(ora, worlds, args.config)
+    mk = oracle_params_factory(ora)
+    rate, _ = time_oracle(ora, worlds, mk, sp, sim, 20_000, 1, 0, 1)
+    n = int(min(sp.n_particles, max(20_000, rate * 5.0)))          # ~5 s per step
+    value, dt = time_oracle(ora, worlds, mk, sp, sim, n, 3, 0, 1)
+    threads = ora.load(3).ora_max_threads()
+    value_mt, _ = time_oracle(ora, worlds, mk, sp, sim, n, 3, 1, threads)
+    value_fused, _ = time_oracle(ora, worlds, mk, sp, sim, n, 3, 0, 1, pattern=1)
+    return {"value": value, "unit": "particle-steps/s", "cores": 1, "kind": "reference",
+            "sample": f"{n} particles x 3 steps of the {args.config} cloud on the full tree; reference "
+                      "ftt.c+fluid.c object code + restated forces/integrator, reference call pattern, "
+                      "serial as the reference is per MPI rank",
+            "all_cores": {"value": value_mt, "cores": threads, "note": "same code, OpenMP over particles"},
+            "fused_1core": {"value": value_fused, "note": "one locate + one interpolation set per particle"},
+            "host_cpus": os.cpu_count()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--particles", type=int, default=0, help="particles per GPU (default: the config's)")
+    ap.add_argument("--two-way", action="store_true")
+    ap.add_argument("--resort", type=int, default=25, help="re-sort particles by cell every R steps (0: never)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

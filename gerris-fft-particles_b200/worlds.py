@@ -27,10 +27,10 @@ LEAF, BOUNDARY = capi.CELL_LEAF, capi.CELL_BOUNDARY
 class World:
     name: str
     dim: int
-    tree: capi.Tree
-    arrays: capi.TreeArrays
-    u: np.ndarray
-    v: np.ndarray
+    tree: Optional[capi.Tree]          # None for a bare spec (no product tree built)
+    arrays: Optional[capi.TreeArrays]
+    u: Optional[np.ndarray]
+    v: Optional[np.ndarray]
     w: Optional[np.ndarray]
     forces: Tuple[int, ...]
     dt: float
@@ -130,6 +130,45 @@ def particle_props(rng, n, d_lo, d_hi, rho_p):
 # ---------------------------------------------------------------------------
 # the configs
 
+ALL3 = (capi.FORCE_DRAG, capi.FORCE_LIFT, capi.FORCE_BUOY)
+
+
+def spec(name: str, n_particles: Optional[int] = None) -> World:
+    """The config's parameters without building any tree (tree/arrays/fields = None):
+    what the reference arm of bench.py needs to draw the same particle cloud."""
+    ring = dict(d_p=(1e-4, 1e-3), rho_p=2.5, v0="fluid", field="ring",
+                cloud="half uniform, half gaussian(0.08) around the core")
+    table = {
+        "C1": dict(dim=2, forces=(capi.FORCE_DRAG,), dt=1e-2, seed=1001, n=1000,
+                   meta=dict(d_p=(1e-3, 1e-3), rho_p=1000.0, v0="zero", field="lid", level=6)),
+        "C2": dict(dim=3, forces=ALL3, dt=1e-3, g=(0.0, -1.0, 0.0), seed=2002, n=10_000_000,
+                   meta=dict(d_p=(1e-4, 1e-3), rho_p=2.5, v0="fluid", field="tg", level=7)),
+        "C3": dict(dim=3, forces=ALL3, dt=1e-3, g=(0.0, -1.0, 0.0), seed=3003, n=10_000_000,
+                   meta=dict(ring, levels=(5, 9))),
+        "C4": dict(dim=3, forces=ALL3, dt=1e-3, g=(0.0, -1.0, 0.0), seed=4004, n=50_000_000,
+                   meta=dict(ring, levels=(6, 10))),
+        "C5": dict(dim=3, forces=ALL3, dt=1e-3, g=(0.0, -1.0, 0.0), seed=5005, n=200_000_000,
+                   meta=dict(ring, levels=(6, 10))),
+    }
+    t = table[name]
+    return World(name, t["dim"], None, None, None, None, None, t["forces"], t["dt"], mu=1e-3,
+                 g=t.get("g", (0.0, 0.0, 0.0)), seed=t["seed"],
+                 n_particles=t["n"] if n_particles is None else n_particles, meta=dict(t["meta"]))
+
+
+def field_of(world: World, pos: np.ndarray):
+    """analytic (u, v, w) of the world's config at positions pos[n,3]"""
+    kind = world.meta.get("field")
+    if kind == "tg":
+        return taylor_green(pos)
+    if kind == "ring":
+        return vortex_ring(pos)
+    if kind == "lid":
+        u, v = lid_style(pos)
+        return u, v, None
+    raise KeyError(kind)
+
+
 def _finish(tree: capi.Tree) -> capi.TreeArrays:
     tree.finalize()
     tree.build_stencils()
@@ -149,7 +188,7 @@ def make_c1(level: int = 6, n_particles: int = 1000) -> World:
     apply_dirichlet_ghosts(a, v, {})
     return World("C1", 2, t, a, u, v, None, (capi.FORCE_DRAG,), dt=1e-2, mu=1e-3,
                  seed=1001, n_particles=n_particles,
-                 meta=dict(d_p=(1e-3, 1e-3), rho_p=1000.0, v0="zero", level=level))
+                 meta=dict(d_p=(1e-3, 1e-3), rho_p=1000.0, v0="zero", field="lid", level=level))
 
 
 def make_c2(level: int = 7, n_particles: int = 10_000_000) -> World:
@@ -159,7 +198,7 @@ def make_c2(level: int = 7, n_particles: int = 10_000_000) -> World:
     u, v, w = taylor_green(a.pos)
     return World("C2", 3, t, a, u, v, w, (capi.FORCE_DRAG, capi.FORCE_LIFT, capi.FORCE_BUOY),
                  dt=1e-3, mu=1e-3, g=(0.0, -1.0, 0.0), seed=2002, n_particles=n_particles,
-                 meta=dict(d_p=(1e-4, 1e-3), rho_p=2.5, v0="fluid", level=level))
+                 meta=dict(d_p=(1e-4, 1e-3), rho_p=2.5, v0="fluid", field="tg", level=level))
 
 
 def make_ring(name: str, minlevel: int, maxlevel: int, n_particles: int, seed: int) -> World:
@@ -170,7 +209,8 @@ def make_ring(name: str, minlevel: int, maxlevel: int, n_particles: int, seed: i
     u, v, w = vortex_ring(a.pos)
     return World(name, 3, t, a, u, v, w, (capi.FORCE_DRAG, capi.FORCE_LIFT, capi.FORCE_BUOY),
                  dt=1e-3, mu=1e-3, g=(0.0, -1.0, 0.0), seed=seed, n_particles=n_particles,
-                 meta=dict(d_p=(1e-4, 1e-3), rho_p=2.5, v0="fluid", levels=(minlevel, maxlevel),
+                 meta=dict(d_p=(1e-4, 1e-3), rho_p=2.5, v0="fluid", field="ring",
+                           levels=(minlevel, maxlevel),
                            cloud="half uniform, half gaussian(0.08) around the core"))
 
 
@@ -214,7 +254,7 @@ def make_particles(world: World, n: Optional[int] = None, rank: int = 0, n_ranks
         vel = [np.zeros(n_local) for _ in range(dim)]
     else:
         P = np.stack(pos + ([np.zeros(n_local)] if dim == 2 else []), axis=1)
-        vel = list((taylor_green if world.name == "C2" else vortex_ring)(P))[:dim]
+        vel = list(field_of(world, P))[:dim]
     if dim == 2:
         return dict(x=pos[0], y=pos[1], z=None, vx=vel[0], vy=vel[1], vz=None, mass=mass, volume=vol)
     return dict(x=pos[0], y=pos[1], z=pos[2], vx=vel[0], vy=vel[1], vz=vel[2], mass=mass, volume=vol)

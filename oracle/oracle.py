@@ -65,6 +65,7 @@ def load(dim: int) -> C.CDLL:
         "ora_cell_info": (None, [u64, vp, vp, vp, vp]),
         "ora_set_values": (None, [vp, i32, lng, vp, vp]), "ora_get_values": (None, [vp, i32, lng, vp, vp]),
         "ora_neighbor": (u64, [u64, i32]), "ora_count": (lng, [vp, i32]),
+        "ora_export_cells": (lng, [vp, vp, vp, vp, vp]),
         "ora_interpolate": (None, [vp, i32, lng, vp, vp, vp, vp]),
         "ora_corner_interpolator": (i32, [vp, u64, i32, vp, vp]),
         "ora_corner_values": (None, [vp, i32, lng, vp, vp]),
@@ -137,6 +138,17 @@ class Sim:
 
     def count(self, leaves_only=False):
         return self.L.ora_count(self.h, int(leaves_only))
+
+    def export_cells(self):
+        """(ptr, pos[n,3], level, is_leaf) of every GfsBox cell, pre-order"""
+        n = self.count()
+        ptr = np.zeros(n, dtype=np.uint64)
+        pos = np.zeros((n, 3))
+        level = np.zeros(n, dtype=np.int32)
+        leaf = np.zeros(n, dtype=np.int32)
+        m = self.L.ora_export_cells(self.h, _p(ptr), _p(pos), _p(level), _p(leaf))
+        assert m == n
+        return ptr, pos, level, leaf.astype(bool)
 
     # queries
     def locate(self, x, y, z=None):

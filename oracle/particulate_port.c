@@ -438,6 +438,29 @@ uint64_t ora_neighbor (uint64_t cellp, int d)
   return (uint64_t) (uintptr_t) ftt_cell_neighbor ((FttCell *) (uintptr_t) cellp, d);
 }
 
+typedef struct { long n; uint64_t * cell; double * pos; int * level; int * leaf; } OraExport;
+
+static void export_cell (FttCell * cell, OraExport * e)
+{
+  FttVector p;
+  ftt_cell_pos (cell, &p);
+  e->cell[e->n] = (uint64_t) (uintptr_t) cell;
+  e->pos[3*e->n] = p.x; e->pos[3*e->n + 1] = p.y; e->pos[3*e->n + 2] = p.z;
+  e->level[e->n] = ftt_cell_level (cell);
+  e->leaf[e->n] = FTT_CELL_IS_LEAF (cell);
+  e->n++;
+}
+
+/* every cell of the GfsBox tree (pre-order): pointer, centre, level, leaf flag;
+ * arrays must hold ora_count (sim, 0) entries */
+long ora_export_cells (OraSim * sim, uint64_t * cell, double * pos, int * level, int * leaf)
+{
+  OraExport e = { 0, cell, pos, level, leaf };
+  ftt_cell_traverse (sim->root, FTT_PRE_ORDER, FTT_TRAVERSE_ALL, -1,
+		     (FttCellTraverseFunc) export_cell, &e);
+  return e.n;
+}
+
 static void count_cell (FttCell * cell, long * n) { (*n)++; }
 
 long ora_count (OraSim * sim, int leaves_only)

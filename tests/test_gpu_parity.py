@@ -1,0 +1,388 @@
+"""GPU parity tests: every call goes through the C-ABI (lib/libgfsb200.so) and
+is compared with the oracle (reference ftt.c/fluid.c object code + restated
+particulate layer) on the same seeded inputs.
+
+Bars (BASELINE.json north_star):
+  * cell indices from point location: bit-exact
+  * vorticity table: bit-exact (cell pass is compiled --fmad=false)
+  * corner values: bit-exact for the canonical leaf of each vertex, <= 4 ulp of
+    max|field| for the other leaves sharing it (summation order)
+  * particle positions / velocities after one step: relative error <= 1e-12
+"""
+import numpy as np
+import pytest
+
+import helpers
+from helpers import capi, worlds, ora
+
+pytestmark = pytest.mark.gpu
+
+STATE = ("x", "y", "z", "vx", "vy", "vz")
+RTOL_STEP = 1e-12          # north_star: <= 1e-12 relative after one step
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _world(kind):
+    if kind == "c1":
+        return worlds.make_c1(level=5, n_particles=1000)
+    if kind == "uniform3":
+        return worlds.make_c2(level=4, n_particles=20000)
+    if kind == "ring3":
+        return worlds.make_ring("ring3", 3, 6, 30000, 3003)
+    if kind == "ring2":
+        t = capi.Tree(2)
+        t.refine_ring(3, 7, 0.25, 1.5)
+        t.corner_sweep()
+        for s in range(4):
+            t.add_boundary(s)
+        t.finalize(); t.build_stencils()
+        a = t.view()
+        u, v = worlds.lid_style(a.pos)
+        worlds.apply_dirichlet_ghosts(a, u, {2: 1.0})
+        worlds.apply_dirichlet_ghosts(a, v, {})
+        return worlds.World("ring2", 2, t, a, u, v, None, (capi.FORCE_DRAG, capi.FORCE_LIFT, capi.FORCE_BUOY),
+                            dt=1e-2, mu=1e-3, g=(0.3, -1.0, 0.0), seed=11, n_particles=5000,
+                            meta=dict(d_p=(1e-4, 1e-3), rho_p=2.5, v0="zero", field="lid"))
+    if kind == "ring3b":
+        t = capi.Tree(3)
+        t.refine_ring(2, 5, 0.3, 1.5)
+        t.corner_sweep()
+        for s in range(6):
+            t.add_boundary(s)
+        t.finalize(); t.build_stencils()
+        a = t.view()
+        u, v, w = worlds.vortex_ring(a.pos)
+        return worlds.World("ring3b", 3, t, a, u, v, w, (capi.FORCE_LIFT, capi.FORCE_DRAG),
+                            dt=2e-3, mu=2e-3, rho=1.3, seed=12, n_particles=8000,
+                            meta=dict(d_p=(1e-4, 1e-3), rho_p=2.5, v0="fluid", field="ring",
+                                      cloud="half uniform, half gaussian"))
+    raise KeyError(kind)
+
+
+_cache = {}
+
+
+def setup(kind, ctx):
+    if kind not in _cache:
+        w = _world(kind)
+        sim, ptrs = helpers.matched_oracle(w)
+        _cache[kind] = (w, sim, ptrs, helpers.PtrIndex(ptrs))
+    w, sim, ptrs, idx = _cache[kind]
+    ctx.upload_tree(w.tree)
+    ctx.upload_field(w.u, w.v, w.w)
+    return w, sim, ptrs, idx
+
+
+KINDS = ["c1", "uniform3", "ring3", "ring2", "ring3b"]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_locate_bit_exact(kind, ctx):
+    w, sim, ptrs, idx = setup(kind, ctx)
+    rng = np.random.default_rng(5)
+    n = 200_000
+    cols = [rng.uniform(-0.6, 0.6, n) for _ in range(w.dim)] + ([None] if w.dim == 2 else [])
+    adv = worlds.adversarial_points(w.arrays, rng, 20000)
+    for x, y, z in (cols, adv):
+        got = ctx.locate(x, y, z)
+        want = idx(sim.locate(x, y, z))
+        assert np.array_equal(got, want), f"{(got != want).sum()} of {len(got)} cell indices differ"
+        assert (got < 0).any() and (got >= 0).any()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_vorticity_bit_exact(kind, ctx):
+    w, sim, ptrs, idx = setup(kind, ctx)
+    leaves = w.arrays.box_leaves
+    got = ctx.vorticity(leaves)
+    want = sim.vorticity(ptrs[leaves])
+    assert np.array_equal(got, want), f"max diff {np.abs(got - want).max():.3e}"
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_corner_values(kind, ctx):
+    w, sim, ptrs, idx = setup(kind, ctx)
+    leaves = w.arrays.box_leaves
+    fields = [w.u, w.v] + ([w.w] if w.dim == 3 else [])
+    for comp, f in enumerate(fields):
+        got = ctx.corner_values(comp, leaves)
+        want = sim.corner_values(comp, ptrs[leaves])
+        tol = 4 * np.finfo(np.float64).eps * max(np.abs(f).max(), 1e-300)
+        assert np.abs(got - want).max() <= tol
+        # the canonical (first-seen) leaf of every vertex is bit-exact
+        lv = w.arrays.leaf_vtx[leaves]
+        first = np.zeros(lv.shape, dtype=bool)
+        _, pos = np.unique(lv.ravel(), return_index=True)
+        first.ravel()[pos] = True
+        assert np.array_equal(got[first], want[first])
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_interpolate(kind, ctx):
+    w, sim, ptrs, idx = setup(kind, ctx)
+    rng = np.random.default_rng(9)
+    n = 50_000
+    cols = [rng.uniform(-0.5, 0.5, n) for _ in range(w.dim)] + ([None] if w.dim == 2 else [])
+    got = ctx.interpolate(*cols)
+    fields = [w.u, w.v] + ([w.w] if w.dim == 3 else [])
+    for comp, f in enumerate(fields):
+        want = sim.interpolate(comp, *cols)
+        inside = want != capi.NODATA
+        assert np.array_equal(got[comp] == capi.NODATA, ~inside)
+        scale = np.abs(f).max()
+        assert np.abs(got[comp][inside] - want[inside]).max() <= 1e-14 * scale
+
+
+def _run_step(ctx, w, parts, **kw):
+    ctx.particles_upload(**parts)
+    ctx.step(w.step_params(record_cells=True, record_forces=True, **kw))
+    return ctx.particles_download(forces=True, cells=True)
+
+
+def _check_state(got, want, dim, rtol=RTOL_STEP):
+    for k in STATE:
+        if dim == 2 and k in ("z", "vz"):
+            continue
+        err = helpers.rel_err(got[k], want[k])
+        assert err <= rtol, f"{k}: relative error {err:.3e} > {rtol:g}"
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_step_one(kind, ctx):
+    """cells bit-exact; x, v within 1e-12 relative; forces within 1e-11 of the
+    force scale (they are differences of O(1) velocities)"""
+    w, sim, ptrs, idx = setup(kind, ctx)
+    parts = worlds.make_particles(w)
+    got = _run_step(ctx, w, parts)
+    cells, want = helpers.oracle_step(sim, ptrs, w, parts)
+    assert np.array_equal(got["cell"], cells)
+    _check_state(got, want, w.dim)
+    for k in ("fx", "fy", "fz"):
+        scale = max(np.abs(want[k]).max(), 1e-300)
+        assert np.abs(got[k] - want[k]).max() <= 1e-11 * scale
+
+
+@pytest.mark.parametrize("forces,kw", [
+    ((capi.FORCE_BUOY,), {}),
+    ((capi.FORCE_BUOY, capi.FORCE_DRAG, capi.FORCE_LIFT), {}),
+    ((capi.FORCE_DRAG,), dict(cd_const=0.44)),
+    ((capi.FORCE_LIFT, capi.FORCE_DRAG), dict(cl_const=0.25)),
+    ((capi.FORCE_DRAG, capi.FORCE_DRAG), {}),
+])
+def test_step_force_lists(forces, kw, ctx):
+    w, sim, ptrs, idx = setup("ring3", ctx)
+    w2 = worlds.World(**{**w.__dict__, "forces": forces})
+    parts = worlds.make_particles(w2, 5000)
+    got = _run_step(ctx, w2, parts, **kw)
+    cells, want = helpers.oracle_step(sim, ptrs, w2, parts, **kw)
+    assert np.array_equal(got["cell"], cells)
+    _check_state(got, want, 3)
+
+
+def test_step_zero_viscosity_and_stokes(ctx):
+    """mu = 0: GfsForceDrag returns 0 (:560-561); tiny relative velocity: Re < 1e-8 => 0"""
+    w, sim, ptrs, idx = setup("uniform3", ctx)
+    w0 = worlds.World(**{**w.__dict__, "mu": 0.0, "forces": (capi.FORCE_DRAG,)})
+    parts = worlds.make_particles(w0, 2000)
+    got = _run_step(ctx, w0, parts)
+    assert np.all(got["fx"] == 0) and np.all(got["fy"] == 0) and np.all(got["fz"] == 0)
+    cells, want = helpers.oracle_step(sim, ptrs, w0, parts)
+    _check_state(got, want, 3)
+
+
+def test_step_per_cell_alpha_mu(ctx):
+    """sim->physical_params.alpha and a per-cell viscosity variable"""
+    w, sim, ptrs, idx = setup("ring3", ctx)
+    rng = np.random.default_rng(3)
+    alpha = rng.uniform(0.5, 2.0, w.arrays.n_cells)
+    mu = rng.uniform(5e-4, 2e-3, w.arrays.n_cells)
+    ctx.upload_field(w.u, w.v, w.w, alpha=alpha, mu=mu)
+    live = (w.arrays.flags & capi.CELL_DESTROYED) == 0
+    sim.set_values(3, ptrs[live], alpha[live])
+    sim.set_values(4, ptrs[live], mu[live])
+    parts = worlds.make_particles(w, 5000)
+    got = _run_step(ctx, w, parts)
+    cells, want = helpers.oracle_step(sim, ptrs, w, parts, ivar_alpha=3, ivar_mu=4)
+    assert np.array_equal(got["cell"], cells)
+    _check_state(got, want, 3)
+    ctx.upload_field(w.u, w.v, w.w)
+
+
+@pytest.mark.parametrize("kind", ["c1", "ring3"])
+def test_drift_after_n_steps(kind, ctx):
+    """Documented drift bound: particles whose cell history matches the
+    reference's stay within 1e-12 * 4^(steps/10) ... in practice ~1e-13 after
+    100 steps; the lift force is cell-constant, so a particle whose cell flips
+    one step early may differ by O(dt * |dF|) -- those are counted, not bounded."""
+    w, sim, ptrs, idx = setup(kind, ctx)
+    parts = worlds.make_particles(w, 2000)
+    ctx.particles_upload(**parts)
+    par = w.step_params(record_cells=True)
+    plist = ora.ParticleList(sim, *[parts[k] for k in ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")])
+    opar = helpers.oracle_params(w)
+    same = np.ones(len(parts["x"]), dtype=bool)
+    for step in range(1, 101):
+        s = plist.get()
+        ocell = idx(sim.locate(s["x"], s["y"], s["z"]))
+        plist.step(opar)
+        ctx.step(par)
+        if step in (1, 10, 100):
+            got = ctx.particles_download(cells=True)
+            same &= got["cell"] == ocell
+            want = plist.get()
+            errs = [helpers.rel_err(got[k][same], want[k][same]) for k in STATE
+                    if not (w.dim == 2 and k in ("z", "vz"))]
+            bound = {1: 1e-12, 10: 1e-11, 100: 1e-9}[step]
+            assert max(errs) <= bound, f"step {step}: drift {max(errs):.3e} > {bound:g}"
+            assert same.mean() > 0.98, f"step {step}: only {same.mean():.3f} of cell histories match"
+
+
+def test_outside_particles_untouched_and_cull(ctx):
+    """gfs_particle_list_event: particles with locate == NULL are removed
+    (remove_particles_not_in_domain) before the children run"""
+    w, sim, ptrs, idx = setup("uniform3", ctx)
+    parts = worlds.make_particles(w, 3000)
+    rng = np.random.default_rng(1)
+    out = rng.random(3000) < 0.2
+    parts["x"] = np.where(out, parts["x"] + 1.0, parts["x"])
+    ctx.particles_upload(**parts)
+    ctx.step(w.step_params(record_cells=True))
+    got = ctx.particles_download(cells=True)
+    assert np.all(got["cell"][out] == -1)
+    for k in STATE:
+        assert np.array_equal(got[k][out], parts[k][out])
+    # the list event: cull, then step
+    ctx.particles_upload(**parts)
+    removed = ctx.particle_list_event(w.step_params(record_cells=True))
+    assert removed == int(out.sum()) and ctx.count == 3000 - removed
+    got = ctx.particles_download(cells=True, ids=True)
+    assert np.array_equal(got["id"], np.nonzero(~out)[0] + 1)      # list order preserved
+    plist = ora.ParticleList(sim, *[parts[k] for k in ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")])
+    assert plist.cull() == removed
+    plist.step(helpers.oracle_params(w))
+    want = plist.get()
+    assert np.array_equal(got["id"], want["id"])
+    _check_state(got, want, 3)
+
+
+def test_sort_is_a_permutation_and_step_invariant(ctx):
+    w, sim, ptrs, idx = setup("ring3", ctx)
+    parts = worlds.make_particles(w, 20000)
+    ref = _run_step(ctx, w, parts)
+    ctx.particles_upload(**parts)
+    ctx.sort()
+    pre = ctx.particles_download(ids=True)
+    perm = pre["id"].astype(np.int64) - 1
+    assert np.array_equal(np.sort(perm), np.arange(20000))
+    for k in STATE:
+        assert np.array_equal(pre[k], parts[k][perm])
+    cells = ctx.locate(pre["x"], pre["y"], pre["z"])
+    assert np.all(np.diff(cells) >= 0), "particles are not sorted by cell"
+    ctx.step(w.step_params(record_cells=True))
+    got = ctx.particles_download(cells=True)
+    for k in STATE:
+        assert np.array_equal(got[k], ref[k][perm])      # bitwise: the step does not depend on order
+    assert np.array_equal(got["cell"], ref["cell"][perm])
+
+
+@pytest.mark.parametrize("kind", ["c1", "ring3"])
+def test_tracer_advection(kind, ctx):
+    """no forces attached: gfs_domain_advect_point (RK2), src/domain.c:2764-2788"""
+    w, sim, ptrs, idx = setup(kind, ctx)
+    parts = worlds.make_particles(w, 5000)
+    ctx.particles_upload(**parts)
+    ctx.step(capi.StepParams(w.dt, ()))
+    got = ctx.particles_download()
+    x, y, z = sim.advect_points(parts["x"], parts["y"], parts["z"], w.dt)
+    assert helpers.rel_err(got["x"], x) <= RTOL_STEP and helpers.rel_err(got["y"], y) <= RTOL_STEP
+    if w.dim == 3:
+        assert helpers.rel_err(got["z"], z) <= RTOL_STEP
+
+
+@pytest.mark.parametrize("kind", ["c1", "ring3"])
+def test_deposit(kind, ctx):
+    """GfsParticulateField (void fraction) and the single-cell force deposit.
+    Summation order differs (atomics): abs tol 1e-12 * max|field|."""
+    w, sim, ptrs, idx = setup(kind, ctx)
+    n = 40000
+    parts = worlds.make_particles(w, n)
+    ctx.particles_upload(**parts)
+    ctx.sort()
+    ctx.deposit_volume()
+    ctx.deposit_force(w.step_params())
+    live = (w.arrays.flags & capi.CELL_DESTROYED) == 0
+    plist = ora.ParticleList(sim, *[parts[k] for k in ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")])
+    zero = np.zeros(int(live.sum()))
+    for iv in range(3, 3 + 1 + w.dim):
+        sim.set_values(iv, ptrs[live], zero)
+    plist.deposit_volume(3)
+    plist.deposit_force(helpers.oracle_params(w), 4)
+    for comp in range(1 + w.dim):
+        got = ctx.download_deposit(comp)[live]
+        want = sim.get_values(3 + comp, ptrs[live])
+        assert np.abs(want).max() > 0
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max(), comp
+    # conservation: sum(field * V_cell) = sum(V_p) over located particles
+    a = w.arrays
+    vol = ctx.download_deposit(0)
+    inside = ctx.locate(parts["x"], parts["y"], parts["z"]) >= 0
+    total = np.sum(vol * a.h ** w.dim)
+    assert abs(total - parts["volume"][inside].sum()) <= 1e-12 * parts["volume"].sum()
+
+
+def test_empty_and_single_particle(ctx):
+    w, sim, ptrs, idx = setup("uniform3", ctx)
+    empty = {k: np.zeros(0) for k in ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")}
+    ctx.particles_upload(**empty)
+    ctx.step(w.step_params())
+    ctx.sort(); ctx.cull(); ctx.deposit_volume()
+    assert ctx.count == 0
+    one = worlds.make_particles(w, 1)
+    got = _run_step(ctx, w, one)
+    cells, want = helpers.oracle_step(sim, ptrs, w, one)
+    assert np.array_equal(got["cell"], cells)
+    _check_state(got, want, 3)
+
+
+def test_full_size_c2_properties(ctx):
+    """BASELINE config C2 at full size (128^3, 10 M particles): properties that
+    need no oracle run -- sortedness, permutation, idempotent locate, volume
+    conservation of the deposit, and a 1e5-particle oracle spot check."""
+    w = worlds.make_c2()
+    assert w.arrays.n_leaves == 128 ** 3 and w.arrays.n_vertices == 129 ** 3
+    ctx.upload_tree(w.tree)
+    ctx.upload_field(w.u, w.v, w.w)
+    parts = worlds.make_particles(w)
+    n = len(parts["x"])
+    assert n == 10_000_000
+    ctx.particles_upload(**parts)
+    ctx.sort()
+    pre = ctx.particles_download(ids=True)
+    cells = ctx.locate(pre["x"], pre["y"], pre["z"])
+    assert np.all(np.diff(cells) >= 0) and cells.min() >= 0
+    assert np.array_equal(np.sort(pre["id"]), np.arange(1, n + 1, dtype=np.uint32))
+    # cell centre of the located leaf is within h/2 of the particle (exact containment)
+    a = w.arrays
+    d = np.abs(np.stack([pre["x"], pre["y"], pre["z"]], 1) - a.pos[cells])
+    assert np.all(d <= a.h[cells][:, None] / 2)
+    ctx.deposit_volume()
+    vol = ctx.download_deposit(0)
+    assert abs(np.sum(vol) * (1 / 128) ** 3 - parts["volume"].sum()) <= 1e-12 * parts["volume"].sum()
+    ctx.step(w.step_params(record_cells=True))
+    got = ctx.particles_download(cells=True, ids=True)
+    assert np.array_equal(got["cell"], cells)
+    # oracle spot check on the first 1e5 ids
+    sim, ptrs = helpers.matched_oracle(w)
+    m = 100_000
+    sub = {k: parts[k][:m] for k in parts}
+    ocells, want = helpers.oracle_step(sim, ptrs, w, sub, nthreads=ora.load(3).ora_max_threads())
+    sel = np.argsort(got["id"])[:m]          # rows holding ids 1..m, in id order
+    assert np.array_equal(got["cell"][sel], ocells)
+    for k in STATE:
+        assert helpers.rel_err(got[k][sel], want[k]) <= RTOL_STEP, k
