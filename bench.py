@@ -55,41 +55,54 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region"""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML (nvidia_ml_py) from a
+    thread while the timed region runs (nvidia-smi's start-up alone is longer
+    than a 100-step region)."""
 
-    def __init__(self, gpu: int):
-        self.gpu, self.rows, self.proc = gpu, [], None
-
-    def start(self):
+    def __init__(self, gpu: int, period_s: float = 0.002):
+        self.gpu, self.period, self.rows = gpu, period_s, []
+        self._stop = threading.Event()
+        self._thread = None
+        self._h = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(gpu)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self._h = None
+            self.max_sm = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+    def _loop(self):
+        nv, h = self._nv, self._h
+        while not self._stop.is_set():
             try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    why = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    why = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(sm), int(why)))
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            time.sleep(self.period)
+
+    def start(self):
+        if self._h is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+                 0x4: "sw_power_cap"}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({n for r in self.rows for bit, n in names.items() if r[1] & bit})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": reasons, "samples": len(sm)}
 
 
 def build_world(worlds, name, n_particles):
@@ -268,6 +281,13 @@ def run_b200(args):
     ms = e0.elapsed_time(e1)
     kernel_ms, kernel_launches = ctx.timer_read()
     clocks = sampler.stop() if rank == 0 else None
+    # validity: the timed kernel early-outs for particles outside the domain, so
+    # prove that (nearly) all of them were still inside when the timed region ended
+    removed = ctx.cull()
+    inside_frac = 1.0 - removed / max(n_local, 1)
+    if inside_frac < 0.999:
+        raise SystemExit(f"bench.py: only {inside_frac:.4f} of the particles are still inside the domain "
+                         "after the timed region -- the workload is invalid")
     n_sorts = (args.steps // args.resort) if args.resort else 0
 
     if world_size > 1:
@@ -318,7 +338,7 @@ def run_b200(args):
                        "cells": int(world.arrays.n_cells), "leaves": int(world.arrays.n_leaves),
                        "vertices": int(world.arrays.n_vertices), "two_way": bool(args.two_way),
                        "resort_every": args.resort, "sorts_in_timed_region": n_sorts,
-                       "cell_pass_every_step": True,
+                       "cell_pass_every_step": True, "particles_inside_at_end": inside_frac,
                        "l2": "per-step particle stream (%.0f MB) exceeds the 126 MB L2" % (n_local * bps / 1e6)},
             "roofline": {"bound": "hbm", "kernel": "step_kernel<3,false,false>" if world.dim == 3 else "step_kernel<2,false,false>",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -22,6 +22,18 @@ from . import capi
 
 LEAF, BOUNDARY = capi.CELL_LEAF, capi.CELL_BOUNDARY
 
+# Particle properties of the 3D configs.  SURVEY.md section 8d proposed
+# d_p in [1e-4, 1e-3], rho_p = 2.5 with mu = 1e-3 and dt = 1e-3; the Stokes
+# response time rho_p d^2/(18 mu) is then 1.4e-6 .. 1.4e-4 s, i.e. dt/tau up to
+# 720, and the reference's explicit update v += F dt/m (particulatecommon.c:835)
+# amplifies the slip velocity ~6-700x per step: every particle leaves the
+# domain within ~10 steps, on the reference CPU path just as on the GPU.  A
+# benchmark on that would time an empty kernel.  These values keep
+# dt/tau <= 0.02 (tau = 0.055 .. 0.89 s), particle Reynolds numbers O(0.1-50),
+# and every particle inside the box for thousands of steps.
+D_P = (1e-3, 4e-3)
+RHO_P = 1000.0
+
 
 @dataclass
 class World:
@@ -136,13 +148,13 @@ ALL3 = (capi.FORCE_DRAG, capi.FORCE_LIFT, capi.FORCE_BUOY)
 def spec(name: str, n_particles: Optional[int] = None) -> World:
     """The config's parameters without building any tree (tree/arrays/fields = None):
     what the reference arm of bench.py needs to draw the same particle cloud."""
-    ring = dict(d_p=(1e-4, 1e-3), rho_p=2.5, v0="fluid", field="ring",
+    ring = dict(d_p=D_P, rho_p=RHO_P, v0="fluid", field="ring",
                 cloud="half uniform, half gaussian(0.08) around the core")
     table = {
         "C1": dict(dim=2, forces=(capi.FORCE_DRAG,), dt=1e-2, seed=1001, n=1000,
                    meta=dict(d_p=(1e-3, 1e-3), rho_p=1000.0, v0="zero", field="lid", level=6)),
         "C2": dict(dim=3, forces=ALL3, dt=1e-3, g=(0.0, -1.0, 0.0), seed=2002, n=10_000_000,
-                   meta=dict(d_p=(1e-4, 1e-3), rho_p=2.5, v0="fluid", field="tg", level=7)),
+                   meta=dict(d_p=D_P, rho_p=RHO_P, v0="fluid", field="tg", level=7)),
         "C3": dict(dim=3, forces=ALL3, dt=1e-3, g=(0.0, -1.0, 0.0), seed=3003, n=10_000_000,
                    meta=dict(ring, levels=(5, 9))),
         "C4": dict(dim=3, forces=ALL3, dt=1e-3, g=(0.0, -1.0, 0.0), seed=4004, n=50_000_000,
@@ -198,7 +210,7 @@ def make_c2(level: int = 7, n_particles: int = 10_000_000) -> World:
     u, v, w = taylor_green(a.pos)
     return World("C2", 3, t, a, u, v, w, (capi.FORCE_DRAG, capi.FORCE_LIFT, capi.FORCE_BUOY),
                  dt=1e-3, mu=1e-3, g=(0.0, -1.0, 0.0), seed=2002, n_particles=n_particles,
-                 meta=dict(d_p=(1e-4, 1e-3), rho_p=2.5, v0="fluid", field="tg", level=level))
+                 meta=dict(d_p=D_P, rho_p=RHO_P, v0="fluid", field="tg", level=level))
 
 
 def make_ring(name: str, minlevel: int, maxlevel: int, n_particles: int, seed: int) -> World:
@@ -209,7 +221,7 @@ def make_ring(name: str, minlevel: int, maxlevel: int, n_particles: int, seed: i
     u, v, w = vortex_ring(a.pos)
     return World(name, 3, t, a, u, v, w, (capi.FORCE_DRAG, capi.FORCE_LIFT, capi.FORCE_BUOY),
                  dt=1e-3, mu=1e-3, g=(0.0, -1.0, 0.0), seed=seed, n_particles=n_particles,
-                 meta=dict(d_p=(1e-4, 1e-3), rho_p=2.5, v0="fluid", field="ring",
+                 meta=dict(d_p=D_P, rho_p=RHO_P, v0="fluid", field="ring",
                            levels=(minlevel, maxlevel),
                            cloud="half uniform, half gaussian(0.08) around the core"))
 

@@ -96,3 +96,16 @@ def oracle_step(sim, ptrs, world, parts, steps=1, pattern=0, nthreads=1, **kw):
 
 def rel_err(got, want, floor=1e-300):
     return float(np.max(np.abs(got - want) / np.maximum(np.abs(want), floor))) if len(want) else 0.0
+
+
+def vec_rel_err(got, want, keys, sel=None):
+    """max over particles of |got_i - want_i|_2 / |want_i|_2 for the vector
+    with components `keys` (position or velocity).  A per-component ratio is
+    meaningless where one component passes through zero."""
+    g = np.stack([got[k] if sel is None else got[k][sel] for k in keys], 1)
+    w = np.stack([want[k] if sel is None else want[k][sel] for k in keys], 1)
+    if not len(w):
+        return 0.0
+    num = np.sqrt(((g - w) ** 2).sum(1))
+    den = np.sqrt((w ** 2).sum(1))
+    return float(np.max(num / np.maximum(den, 1e-300)))

@@ -48,7 +48,7 @@ def _world(kind):
         worlds.apply_dirichlet_ghosts(a, v, {})
         return worlds.World("ring2", 2, t, a, u, v, None, (capi.FORCE_DRAG, capi.FORCE_LIFT, capi.FORCE_BUOY),
                             dt=1e-2, mu=1e-3, g=(0.3, -1.0, 0.0), seed=11, n_particles=5000,
-                            meta=dict(d_p=(1e-4, 1e-3), rho_p=2.5, v0="zero", field="lid"))
+                            meta=dict(d_p=worlds.D_P, rho_p=worlds.RHO_P, v0="zero", field="lid"))
     if kind == "ring3b":
         t = capi.Tree(3)
         t.refine_ring(2, 5, 0.3, 1.5)
@@ -60,7 +60,7 @@ def _world(kind):
         u, v, w = worlds.vortex_ring(a.pos)
         return worlds.World("ring3b", 3, t, a, u, v, w, (capi.FORCE_LIFT, capi.FORCE_DRAG),
                             dt=2e-3, mu=2e-3, rho=1.3, seed=12, n_particles=8000,
-                            meta=dict(d_p=(1e-4, 1e-3), rho_p=2.5, v0="fluid", field="ring",
+                            meta=dict(d_p=worlds.D_P, rho_p=worlds.RHO_P, v0="fluid", field="ring",
                                       cloud="half uniform, half gaussian"))
     raise KeyError(kind)
 
@@ -145,12 +145,15 @@ def _run_step(ctx, w, parts, **kw):
     return ctx.particles_download(forces=True, cells=True)
 
 
-def _check_state(got, want, dim, rtol=RTOL_STEP):
-    for k in STATE:
-        if dim == 2 and k in ("z", "vz"):
-            continue
-        err = helpers.rel_err(got[k], want[k])
-        assert err <= rtol, f"{k}: relative error {err:.3e} > {rtol:g}"
+def _vec_keys(dim):
+    return (("x", "y", "z"), ("vx", "vy", "vz")) if dim == 3 else (("x", "y"), ("vx", "vy"))
+
+
+def _check_state(got, want, dim, rtol=RTOL_STEP, sel=None):
+    """|dx|/|x| and |dv|/|v| per particle (2-norm of the vector) <= rtol"""
+    for keys in _vec_keys(dim):
+        err = helpers.vec_rel_err(got, want, keys, sel)
+        assert err <= rtol, f"{keys}: relative error {err:.3e} > {rtol:g}"
 
 
 @pytest.mark.parametrize("kind", KINDS)
@@ -236,8 +239,7 @@ def test_drift_after_n_steps(kind, ctx):
             got = ctx.particles_download(cells=True)
             same &= got["cell"] == ocell
             want = plist.get()
-            errs = [helpers.rel_err(got[k][same], want[k][same]) for k in STATE
-                    if not (w.dim == 2 and k in ("z", "vz"))]
+            errs = [helpers.vec_rel_err(got, want, keys, same) for keys in _vec_keys(w.dim)]
             bound = {1: 1e-12, 10: 1e-11, 100: 1e-9}[step]
             assert max(errs) <= bound, f"step {step}: drift {max(errs):.3e} > {bound:g}"
             assert same.mean() > 0.98, f"step {step}: only {same.mean():.3f} of cell histories match"
@@ -300,9 +302,8 @@ def test_tracer_advection(kind, ctx):
     ctx.step(capi.StepParams(w.dt, ()))
     got = ctx.particles_download()
     x, y, z = sim.advect_points(parts["x"], parts["y"], parts["z"], w.dt)
-    assert helpers.rel_err(got["x"], x) <= RTOL_STEP and helpers.rel_err(got["y"], y) <= RTOL_STEP
-    if w.dim == 3:
-        assert helpers.rel_err(got["z"], z) <= RTOL_STEP
+    keys = ("x", "y", "z")[:w.dim]
+    assert helpers.vec_rel_err(got, dict(x=x, y=y, z=z), keys) <= RTOL_STEP
 
 
 @pytest.mark.parametrize("kind", ["c1", "ring3"])
@@ -384,5 +385,5 @@ def test_full_size_c2_properties(ctx):
     ocells, want = helpers.oracle_step(sim, ptrs, w, sub, nthreads=ora.load(3).ora_max_threads())
     sel = np.argsort(got["id"])[:m]          # rows holding ids 1..m, in id order
     assert np.array_equal(got["cell"][sel], ocells)
-    for k in STATE:
-        assert helpers.rel_err(got[k][sel], want[k]) <= RTOL_STEP, k
+    sub_got = {k: got[k][sel] for k in STATE}
+    _check_state(sub_got, want, 3)
