@@ -39,6 +39,7 @@ class TreeView(C.Structure):
         ("la_slot", C.POINTER(C.c_int32)),
         ("n_vertices", C.c_int32), ("vtx_off", C.POINTER(C.c_int32)), ("vtx_cell", C.POINTER(C.c_int32)),
         ("vtx_w", C.POINTER(C.c_double)), ("leaf_vtx", C.POINTER(C.c_int32)),
+        ("lattice_level", C.c_int32),
     ]
 
 
@@ -238,6 +239,7 @@ class TreeArrays:
         self.la_n = np.array(list(v.la_n))
         self.la_slot = as_arr(v.la_slot, shape=(int(np.prod(self.la_n)),))
         self.n_vertices = v.n_vertices
+        self.lattice_level = v.lattice_level
         if v.n_vertices and bool(v.vtx_off):
             self.vtx_off = as_arr(v.vtx_off, shape=(v.n_vertices + 1,))
             ne = int(self.vtx_off[-1])

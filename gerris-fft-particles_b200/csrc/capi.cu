@@ -26,7 +26,7 @@
 extern "C" {
 void gfsb200_launch_cell_pass (const DevTree *, const DevField *, int, cudaStream_t);
 void gfsb200_launch_step (const DevTree *, const DevField *, const DevParticles *, const DevStep *,
-			  int, int, cudaStream_t);
+			  int, int, cudaStream_t);   /* (.., record, min blocks/SM, stream) */
 void gfsb200_launch_advect (const DevTree *, const DevField *, const DevParticles *, double, int,
 			    cudaStream_t);
 void gfsb200_launch_locate (const DevTree *, int64_t, const double *, const double *,
@@ -61,7 +61,7 @@ struct gfsb200_ctx {
   DevTree T;
   int32_t * d_child0, * d_neighbor, * d_la_slot, * d_vtx_off, * d_vtx_cell, * d_leaf_vtx;
   uint8_t * d_level, * d_info;
-  double * d_vtx_w;
+  double * d_vtx_w, * d_vtx_wuni;
   /* field */
   bool have_field, own_field;
   DevField F;
@@ -84,6 +84,7 @@ struct gfsb200_ctx {
   /* deposit */
   double * deposit;
   int64_t deposit_count;
+  int step_minb;               /* __launch_bounds__ min blocks/SM variant of the step kernel */
   /* timing */
   std::vector<cudaEvent_t> ev;
   size_t ev_used;
@@ -108,9 +109,9 @@ static void free_tree (gfsb200_ctx * c)
 {
   cudaFree (c->d_child0); cudaFree (c->d_neighbor); cudaFree (c->d_la_slot);
   cudaFree (c->d_vtx_off); cudaFree (c->d_vtx_cell); cudaFree (c->d_leaf_vtx);
-  cudaFree (c->d_level); cudaFree (c->d_info); cudaFree (c->d_vtx_w);
+  cudaFree (c->d_level); cudaFree (c->d_info); cudaFree (c->d_vtx_w); cudaFree (c->d_vtx_wuni);
   c->d_child0 = c->d_neighbor = c->d_la_slot = c->d_vtx_off = c->d_vtx_cell = c->d_leaf_vtx = NULL;
-  c->d_level = c->d_info = NULL; c->d_vtx_w = NULL;
+  c->d_level = c->d_info = NULL; c->d_vtx_w = c->d_vtx_wuni = NULL;
   cudaFree (c->F.vtx_val); cudaFree (c->F.vort);
   c->F.vtx_val = c->F.vort = NULL;
   for (int i = 0; i < 5; i++) { cudaFree (c->d_field[i]); c->d_field[i] = NULL; }
@@ -157,7 +158,7 @@ extern "C" int gfsb200_ctx_create (int device, gfsb200_ctx ** out)
   c->n_sm = prop.multiProcessorCount;
   c->have_tree = c->have_field = c->own_field = false;
   c->d_child0 = c->d_neighbor = c->d_la_slot = c->d_vtx_off = c->d_vtx_cell = c->d_leaf_vtx = NULL;
-  c->d_level = c->d_info = NULL; c->d_vtx_w = NULL;
+  c->d_level = c->d_info = NULL; c->d_vtx_w = c->d_vtx_wuni = NULL;
   for (int i = 0; i < 5; i++) c->d_field[i] = NULL;
   c->n = c->cap = c->aux_cap = 0; c->cur = 0;
   for (int b = 0; b < 2; b++) { for (int k = 0; k < NCOL; k++) c->col[b][k] = NULL; c->id[b] = NULL; }
@@ -166,6 +167,7 @@ extern "C" int gfsb200_ctx_create (int device, gfsb200_ctx ** out)
   c->d_count = NULL; c->cub_tmp = NULL; c->cub_tmp_bytes = 0; c->d_ptr_table = NULL;
   c->deposit = NULL; c->deposit_count = 0;
   c->ev_used = 0; c->timing = true;
+  c->step_minb = getenv ("GFSB200_STEP_MINB") ? atoi (getenv ("GFSB200_STEP_MINB")) : 3;
   if (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc ((void **) &c->d_count, sizeof (int32_t)) != cudaSuccess ||
       cudaMalloc ((void **) &c->d_ptr_table, 2*NCOL*sizeof (double *)) != cudaSuccess) {
@@ -220,7 +222,21 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
     child0[i] = (t->flags[i] & GFSB200_CELL_DESTROYED) ? CHILD_DESTROYED :
       (t->child0[i] < 0 ? CHILD_LEAF : t->child0[i]);
     int k = t->parent[i] < 0 ? 0 : i - t->child0[t->parent[i]];
-    info[i] = (uint8_t) ((t->flags[i] & 7) | (k << 4));
+    unsigned regular = (t->flags[i] & GFSB200_CELL_LEAF) ? CELL_REGULAR : 0;
+    for (int d = 0; d < t->ndir && regular; d++) {
+      int32_t nb = t->neighbor[(int64_t) i*t->ndir + d];
+      if (nb < 0 || t->level[nb] != t->level[i] || !(t->flags[nb] & GFSB200_CELL_LEAF))
+	regular = 0;
+    }
+    info[i] = (uint8_t) ((t->flags[i] & 7) | regular | (k << 4));
+  }
+  std::vector<double> wuni (t->n_vertices ? t->n_vertices : 1);
+  for (int32_t v = 0; v < t->n_vertices; v++) {
+    const int32_t b = t->vtx_off[v], e = t->vtx_off[v + 1];
+    double w = e > b ? t->vtx_w[b] : 0.;
+    for (int32_t j = b + 1; j < e; j++)
+      if (t->vtx_w[j] != w) { w = NAN; break; }
+    wuni[v] = w;
   }
   int r;
   if ((r = dev_alloc_copy (&c->d_child0, child0.data (), n, c->stream))) return r;
@@ -232,6 +248,7 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
   const size_t ne = t->vtx_off[t->n_vertices];
   if ((r = dev_alloc_copy (&c->d_vtx_cell, (const int32_t *) t->vtx_cell, ne, c->stream))) return r;
   if ((r = dev_alloc_copy (&c->d_vtx_w, (const double *) t->vtx_w, ne, c->stream))) return r;
+  if ((r = dev_alloc_copy (&c->d_vtx_wuni, (const double *) wuni.data (), (size_t) t->n_vertices, c->stream))) return r;
   if ((r = dev_alloc_copy (&c->d_leaf_vtx, (const int32_t *) t->leaf_vtx, (size_t) n*nc, c->stream))) return r;
   CK (cudaStreamSynchronize (c->stream));   /* host staging vectors go out of scope */
 
@@ -244,6 +261,9 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
   if (T.top_levels > (t->dim == 3 ? 10 : 15)) T.top_levels = t->dim == 3 ? 10 : 15;
   T.top_start = t->level_start[T.top_levels];
   T.root_size = ldexp (1., -t->root_level);
+  T.top_h = ldexp (1., -(t->root_level + T.top_levels));
+  T.top_inv_h = ldexp (1., t->root_level + T.top_levels);
+  T.la_inv_h = 1./t->la_h;
   for (int rr = 0; rr < t->n_roots; rr++)
     for (int a = 0; a < 3; a++)
       T.root_pos[rr][a] = t->pos[3*rr + a];
@@ -254,6 +274,11 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
   T.child0 = c->d_child0; T.neighbor = c->d_neighbor; T.level = c->d_level; T.info = c->d_info;
   T.n_vertices = t->n_vertices;
   T.vtx_off = c->d_vtx_off; T.vtx_cell = c->d_vtx_cell; T.vtx_w = c->d_vtx_w; T.leaf_vtx = c->d_leaf_vtx;
+  T.vtx_wuni = c->d_vtx_wuni;
+  T.lattice_n1 = 0;
+  if (t->lattice_level >= 0 && t->lattice_level - t->root_level == T.top_levels && T.single_box &&
+      !getenv ("GFSB200_NO_LATTICE"))
+    T.lattice_n1 = (1 << T.top_levels) + 1;
 
   memset (&c->F, 0, sizeof c->F);
   const int vs = t->dim == 3 ? 4 : 2, ws = t->dim == 3 ? 4 : 1;
@@ -511,6 +536,7 @@ static int make_step (const gfsb200_step_params * p, DevStep * S)
     if (p->force[k] != GFSB200_FORCE_BUOY) S->need_velocity = 1;
   }
   S->rho = p->rho; S->mu = p->mu;
+  S->inv_mu = p->mu != 0. ? 1./p->mu : 0.;
   for (int a = 0; a < 3; a++) S->g[a] = p->g[a];
   S->cd_const = p->cd_const; S->cl_const = p->cl_const;
   return GFSB200_OK;
@@ -553,7 +579,8 @@ extern "C" int gfsb200_step (gfsb200_ctx * c, const gfsb200_step_params * p)
   if (S.n_forces == 0)
     gfsb200_launch_advect (&c->T, &c->F, &P, S.dt, p->record_cells, c->stream);
   else
-    gfsb200_launch_step (&c->T, &c->F, &P, &S, p->record_cells, p->record_forces, c->stream);
+    gfsb200_launch_step (&c->T, &c->F, &P, &S, p->record_cells || p->record_forces, c->step_minb,
+			 c->stream);
   if ((r = timed_end (c))) return r;
   CK (cudaGetLastError ());
   return GFSB200_OK;

@@ -153,7 +153,26 @@ vorticity_kernel (DevTree T, DevField fld)
     const unsigned info = T.info[cell];
     const bool box_leaf = (info & (GFSB200_CELL_LEAF | GFSB200_CELL_BOUNDARY)) == GFSB200_CELL_LEAF;
     double wx = 0., wy = 0., wz = 0.;
-    if (box_leaf) {
+    if (box_leaf && (info & CELL_REGULAR)) {
+      /* all 2*dim neighbours are leaves of the cell's own level: every
+	 gfs_neighbor_value is the neighbour's value at x = 1, and
+	 gfs_center_gradient reduces to ((v2 - v0) + (v0 - v1))/2 -- the same
+	 operations the general path performs with x1 = x2 = 1 */
+      const double size = __longlong_as_double ((long long) (1023 - T.level[cell]) << 52);
+      const int * nb = T.neighbor + (int64_t) cell*(2*DIM);
+      const double * __restrict__ U = fld.u[0], * __restrict__ V = fld.u[1];
+#define GRAD(F, c) ((((F)[nb[2*(c)]] - (F)[cell]) + ((F)[cell] - (F)[nb[2*(c) + 1]]))/2.)
+      if (DIM == 2)
+	wz = (GRAD (V, 0) - GRAD (U, 1))/size;
+      else {
+	const double * __restrict__ W = fld.u[2];
+	wx = (GRAD (W, 1) - GRAD (V, 2))/size;
+	wy = (GRAD (U, 2) - GRAD (W, 0))/size;
+	wz = (GRAD (V, 0) - GRAD (U, 1))/size;
+      }
+#undef GRAD
+    }
+    else if (box_leaf) {
       /* ftt_cell_size: 2^-level, exact */
       const double size = __longlong_as_double ((long long) (1023 - T.level[cell]) << 52);
       if (DIM == 2)
@@ -191,9 +210,13 @@ vertex_values_kernel (DevTree T, DevField fld)
     const int b = T.vtx_off[v], e = T.vtx_off[v + 1];
     double s0 = 0., s1 = 0., s2 = 0.;
     bool nodata = false;
+    /* most stencils carry one weight repeated (equal-size cells around the
+       vertex): it is stored once per vertex and the per-entry array is skipped */
+    const double wu = T.vtx_wuni[v];
+    const bool uni = wu == wu;
     for (int i = b; i < e; i++) {
       const int c = T.vtx_cell[i];
-      const double w = T.vtx_w[i];
+      const double w = uni ? wu : T.vtx_w[i];
       const double v0 = fld.u[0][c], v1 = fld.u[1][c];
       nodata |= (v0 == GFSB200_NODATA) | (v1 == GFSB200_NODATA);
       s0 += w*v0;

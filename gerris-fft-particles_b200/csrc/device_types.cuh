@@ -10,6 +10,7 @@
 
 /* child0 encoding on the device: >= 0 first child, -1 leaf, -2 destroyed cell
  * (so that the descent sees FTT_CELL_IS_DESTROYED without a second load) */
+#define CELL_REGULAR    8u   /* info bit: all 2*dim neighbours are same-level leaves */
 #define CHILD_LEAF      (-1)
 #define CHILD_DESTROYED (-2)
 
@@ -20,6 +21,8 @@ struct DevTree {
   int top_start;               /* level_start of the complete level */
   int single_box;              /* locate array has exactly one slot holding box root 0 */
   double root_size;            /* ftt_level_size (root_level) */
+  double top_h, top_inv_h;     /* cell size at the complete level and its (exact) inverse */
+  double la_inv_h;             /* 1/la_h; la_h = 2^-rootlevel, so x*la_inv_h == x/la_h bitwise */
   double root_pos[GFSB200_MAX_DEV_ROOTS][3];
   /* GfsLocateArray */
   double la_min[3], la_h;
@@ -29,13 +32,16 @@ struct DevTree {
   const int32_t * child0;      /* encoded as above */
   const int32_t * neighbor;    /* [n_cells][2*dim] */
   const uint8_t * level;       /* absolute level */
-  const uint8_t * info;        /* flags (low 3 bits) | child id << 4 */
+  const uint8_t * info;        /* flags (low 3 bits) | CELL_REGULAR | child id << 4 */
   /* stencils */
   int n_vertices;
   const int32_t * vtx_off;
   const int32_t * vtx_cell;
   const double  * vtx_w;
+  const double  * vtx_wuni;    /* [n_vertices] the stencil's weight if all its weights are equal, else NaN */
   const int32_t * leaf_vtx;    /* [n_cells][2^dim] */
+  int lattice_n1;              /* > 0: uniform one-box tree, vertex id = (k*n1 + j)*n1 + i with
+				  n1 = 2^levels + 1 (no leaf_vtx / child0 loads needed) */
 };
 
 struct DevField {
@@ -62,6 +68,7 @@ struct DevStep {
 				  the by-value struct in the constant bank) */
   int need_velocity;           /* any drag/lift in the list */
   double rho, mu;
+  double inv_mu;               /* 1/mu for a constant viscosity (0 when mu == 0) */
   double g[3];
   double cd_const, cl_const;   /* NaN = built-in law */
 };

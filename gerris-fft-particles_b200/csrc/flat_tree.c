@@ -92,6 +92,7 @@ static void free_final (gfsb200_tree * t)
   free (t->vtx_w); t->vtx_w = NULL;
   free (t->leaf_vtx); t->leaf_vtx = NULL;
   t->n_vertices = 0;
+  t->lattice_level = -1;
   t->finalized = 0;
 }
 
@@ -656,5 +657,6 @@ int gfsb200_tree_get_view (const gfsb200_tree * t, gfsb200_tree_view * v)
   v->la_slot = t->la_slot;
   v->n_vertices = t->n_vertices;
   v->vtx_off = t->vtx_off; v->vtx_cell = t->vtx_cell; v->vtx_w = t->vtx_w; v->leaf_vtx = t->leaf_vtx;
+  v->lattice_level = t->leaf_vtx ? t->lattice_level : -1;
   return GFSB200_OK;
 }

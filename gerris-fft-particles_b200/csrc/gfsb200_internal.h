@@ -39,6 +39,7 @@ struct gfsb200_tree {
   int32_t * vtx_off, * vtx_cell;
   double * vtx_w;
   int32_t * leaf_vtx;
+  int lattice_level;             /* >= 0: vertices are numbered row-major on the lattice of that level */
 };
 
 int gfsb200_fail (int code, const char * fmt, ...);

@@ -29,6 +29,7 @@ struct Located {
   int cell;            /* flat index, -1 = outside the domain */
   double cx, cy, cz;   /* exact centre of the leaf */
   double half;         /* half its size */
+  int kx, ky, kz;      /* column indices at the complete level (lattice trees: of the leaf) */
 };
 
 /* spread the low 10 bits of v to every third bit */
@@ -69,33 +70,35 @@ __device__ __forceinline__ int column (double p, double lo, double h, double inv
   return k;
 }
 
-template <int DIM>
+template <int DIM, bool LATTICE = false>
 __device__ __forceinline__ Located locate (const DevTree & T, double x, double y, double z)
 {
   Located L;
   L.cell = -1;
   L.cx = L.cy = L.cz = 0.; L.half = 0.;
+  L.kx = L.ky = L.kz = 0;
   if (!(x == x && y == y && z == z))      /* NaN: floor() -> INT_MIN -> outside in the reference */
     return L;
 
-  /* GfsLocateArray, src/domain.c:43-80: i_c = floor ((p_c - min_c)/h) */
+  /* GfsLocateArray, src/domain.c:43-80: i_c = floor ((p_c - min_c)/h); h is a
+     power of two, so the division is a multiplication by its exact inverse */
   int root;
   if (T.single_box) {
-    int ix = (int) floor ((x - T.la_min[0])/T.la_h);
-    int iy = (int) floor ((y - T.la_min[1])/T.la_h);
-    int iz = DIM == 3 ? (int) floor ((z - T.la_min[2])/T.la_h) : 0;
-    if ((ix | iy | iz) != 0)
+    /* one slot: floor (t) == 0  <=>  0 <= t < 1 */
+    const double tx = (x - T.la_min[0])*T.la_inv_h, ty = (y - T.la_min[1])*T.la_inv_h;
+    const double tz = DIM == 3 ? (z - T.la_min[2])*T.la_inv_h : 0.;
+    if (!(tx >= 0. && tx < 1. && ty >= 0. && ty < 1. && tz >= 0. && tz < 1.))
       return L;
     root = 0;
   }
   else {
-    int ix = (int) floor ((x - T.la_min[0])/T.la_h);
-    int iy = (int) floor ((y - T.la_min[1])/T.la_h);
+    int ix = (int) floor ((x - T.la_min[0])*T.la_inv_h);
+    int iy = (int) floor ((y - T.la_min[1])*T.la_inv_h);
     if (ix < 0 || ix >= T.la_n[0] || iy < 0 || iy >= T.la_n[1])
       return L;
     int index = ix*T.la_n[1] + iy;
     if (DIM == 3) {
-      int iz = (int) floor ((z - T.la_min[2])/T.la_h);
+      int iz = (int) floor ((z - T.la_min[2])*T.la_inv_h);
       if (iz < 0 || iz >= T.la_n[2])
 	return L;
       index = index*T.la_n[2] + iz;
@@ -107,7 +110,7 @@ __device__ __forceinline__ Located locate (const DevTree & T, double x, double y
 
   /* ftt_cell_locate, src/ftt.c:1535-1574: inclusive root test ... */
   double cx = T.root_pos[root][0], cy = T.root_pos[root][1], cz = DIM == 3 ? T.root_pos[root][2] : 0.;
-  double half = T.root_size/2.;
+  double half = 0.5*T.root_size;
   if (x > cx + half || x < cx - half || y > cy + half || y < cy - half ||
       (DIM == 3 && (z > cz + half || z < cz - half)))
     return L;
@@ -117,7 +120,7 @@ __device__ __forceinline__ Located locate (const DevTree & T, double x, double y
     /* ... the first top_levels levels of the descent, resolved arithmetically
        because every GfsBox tree is complete down to that level */
     const int n = 1 << T.top_levels;
-    const double h = T.root_size/n, inv_h = n/T.root_size;
+    const double h = T.top_h, inv_h = T.top_inv_h;
     const int kx = column (x, cx - half, h, inv_h, n);
     const int ky = column (y, cy - half, h, inv_h, n);
     /* child digit per level: bit0 = (x > c), bit1 = !(y > c), bit2 = !(z > c) */
@@ -126,13 +129,21 @@ __device__ __forceinline__ Located locate (const DevTree & T, double x, double y
       const int kz = column (z, cz - half, h, inv_h, n);
       key = spread3 (kx) | (spread3 (~ky & (n - 1)) << 1) | (spread3 (~kz & (n - 1)) << 2);
       cz = (cz - half) + (kz + 0.5)*h;
+      L.kz = kz;
     }
     else
       key = spread2 (kx) | (spread2 (~ky & (n - 1)) << 1);
     cx = (cx - half) + (kx + 0.5)*h;
     cy = (cy - half) + (ky + 0.5)*h;
-    half = h/2.;
+    half = 0.5*h;
     cell = T.top_start + (root << (DIM*T.top_levels)) + (int) key;
+    L.kx = kx; L.ky = ky;
+  }
+  if (LATTICE) {
+    /* every leaf sits at the complete level: no descent, no child0 load */
+    L.cell = cell;
+    L.cx = cx; L.cy = cy; L.cz = cz; L.half = half;
+    return L;
   }
 
   /* ... then strict-'>' descent with exactly tracked dyadic centres */
@@ -175,16 +186,28 @@ __device__ __forceinline__ double resolve (double v, const double * __restrict__
  * 3D: trilinear in the 8 corner values (gfs_interpolate_from_corners,
  * :2666-2681, written as nested linear interpolations);
  * 2D: centre value + the two diagonal triangles (:2655-2664). */
-template <int DIM>
+template <int DIM, bool LATTICE = false>
 __device__ __forceinline__ void interpolate (const DevTree & T, const DevField & fld,
 					     const Located & L, double x, double y, double z,
 					     double & u, double & v, double & w)
 {
-  const double inv = 1./L.half;     /* half is a power of two: exact */
+  /* half is a power of two: its inverse is an exponent flip, no division */
+  const double inv = __longlong_as_double ((2046LL << 52) - __double_as_longlong (L.half));
   if (DIM == 3) {
-    const int4 * vi = reinterpret_cast<const int4 *> (T.leaf_vtx + (int64_t) L.cell*8);
-    const int4 i0 = __ldg (vi), i1 = __ldg (vi + 1);
-    const int id[8] = { i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w };
+    int id[8];
+    if (LATTICE) {
+      /* vertex ids straight from the leaf's column indices (row-major lattice) */
+      const int n1 = T.lattice_n1;
+      const int b = (L.kz*n1 + L.ky)*n1 + L.kx, up = n1*n1;
+      id[4] = b;          id[5] = b + 1;          id[7] = b + n1;      id[6] = b + n1 + 1;
+      id[0] = b + up;     id[1] = b + up + 1;     id[3] = b + up + n1; id[2] = b + up + n1 + 1;
+    }
+    else {
+      const int4 * vi = reinterpret_cast<const int4 *> (T.leaf_vtx + (int64_t) L.cell*8);
+      const int4 i0 = __ldg (vi), i1 = __ldg (vi + 1);
+      id[0] = i0.x; id[1] = i0.y; id[2] = i0.z; id[3] = i0.w;
+      id[4] = i1.x; id[5] = i1.y; id[6] = i1.z; id[7] = i1.w;
+    }
     double fu[8], fv[8], fw[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -216,7 +239,14 @@ __device__ __forceinline__ void interpolate (const DevTree & T, const DevField &
 	      lerp (lerp (fw[0], fw[1], tx), lerp (fw[3], fw[2], tx), ty), tz);
   }
   else {
-    const int4 id = __ldg (reinterpret_cast<const int4 *> (T.leaf_vtx + (int64_t) L.cell*4));
+    int4 id;
+    if (LATTICE) {
+      /* corners: 0(-,-) 1(+,-) 2(+,+) 3(-,+) */
+      const int n1 = T.lattice_n1, b = L.ky*n1 + L.kx;
+      id = make_int4 (b, b + 1, b + n1 + 1, b + n1);
+    }
+    else
+      id = __ldg (reinterpret_cast<const int4 *> (T.leaf_vtx + (int64_t) L.cell*4));
     const double2 * vv = reinterpret_cast<const double2 *> (fld.vtx_val);
     double2 f0 = __ldg (vv + id.x), f1 = __ldg (vv + id.y), f2 = __ldg (vv + id.z), f3 = __ldg (vv + id.w);
     const double c0 = fld.u[0][L.cell], c1 = fld.u[1][L.cell];
@@ -239,7 +269,17 @@ __device__ __forceinline__ void interpolate (const DevTree & T, const DevField &
 /* forces: modules/particulatecommon.c:423-490 (lift), 519-588 (drag),
  * 617-655 (buoyancy), accumulated as in compute_forces (:737-751)      */
 
-template <int DIM, bool ONFLUID>
+/* The drag law of compute_drag_force,
+ *   Re = |u_r| d rho/mu,  cd = 16 (1 + 0.15 Re^.5)/Re  (Re < 50)  or  48 (1 - 2.21/Re^.5)/Re,
+ *   f  = 3/(4 d) cd |u_r| u_r rho        (per unit particle volume),
+ * with cd/Re substituted: |u_r| and rho cancel, leaving
+ *   f = 12 mu (1 + 0.15 Re^.5)/d^2 u_r   or   36 mu (1 - 2.21/Re^.5)/d^2 u_r.
+ * Same value up to a few ulp, one square root and no division in the common
+ * branch.  d = 2 (3V/4pi)^(1/3) = K V^(1/3): 1/d^2 comes from one rcbrt. */
+#define DIA_K 1.2407009817988000333       /* 2 (3/(4 pi))^(1/3) */
+#define INV_DIA_K2 0.64962951495345899316  /* 1/DIA_K^2 */
+
+template <int DIM, bool ONFLUID, bool LATTICE = false>
 __device__ __forceinline__ void total_force (const DevTree & T, const DevField & fld,
 					     const DevStep & S, const Located & L,
 					     double x, double y, double z,
@@ -253,96 +293,107 @@ __device__ __forceinline__ void total_force (const DevTree & T, const DevField &
   double rx = 0., ry = 0., rz = 0.;
   if (S.need_velocity) {
     double u, v, w;
-    interpolate<DIM> (T, fld, L, x, y, z, u, v, w);
+    interpolate<DIM, LATTICE> (T, fld, L, x, y, z, u, v, w);
     rx = u - vx; ry = v - vy; rz = DIM == 3 ? w - vz : 0.;
   }
   for (int k = 0; k < S.n_forces; k++) {
     const int kind = (S.forces >> (4*k)) & 15;
+    /* f*V, the particle force contribution of compute_forces (:744) */
     double fx = 0., fy = 0., fz = 0.;
     if (kind == GFSB200_FORCE_DRAG) {
-      const double mu = fld.mu ? fld.mu[L.cell] : S.mu;
+      double mu = S.mu, inv_mu = S.inv_mu;
+      if (fld.mu) {
+	mu = fld.mu[L.cell];
+	inv_mu = mu != 0. ? 1./mu : 0.;
+      }
       if (mu != 0.) {
-	const double dia = 2.*cbrt (3.0*volume/4.0/M_PI);
+	const double r3 = rcbrt (volume);                  /* V^(-1/3) */
+	const double dia = DIA_K*volume*r3*r3;             /* K V^(1/3) */
+	const double inv_d2 = r3*r3*INV_DIA_K2;
 	const double nrm = sqrt (DIM == 3 ? rx*rx + ry*ry + rz*rz : rx*rx + ry*ry);
-	const double Re = nrm*dia*rho/mu;
-	double cd;
-	bool zero = false;
+	double k3;
 	if (S.cd_const == S.cd_const)
-	  cd = S.cd_const;
+	  k3 = 0.75*S.cd_const*nrm*rho/dia;
 	else {
-	  zero = Re < 1e-8;
+	  const double Re = nrm*dia*rho*inv_mu;
 	  const double s = sqrt (Re);
-	  cd = Re < 50.0 ? 16.*(1. + 0.15*s)/Re : 48.*(1. - 2.21/s)/Re;
+	  if (Re < 1e-8)
+	    k3 = 0.;
+	  else if (Re < 50.0)
+	    k3 = 12.*mu*inv_d2*(1. + 0.15*s);
+	  else
+	    k3 = 36.*mu*inv_d2*(1. - 2.21/s);
 	}
-	if (!zero) {
-	  const double k3 = 3./(4.*dia)*cd*nrm;
-	  fx = k3*rx*rho; fy = k3*ry*rho;
-	  if (DIM == 3) fz = k3*rz*rho;
-	}
+	k3 *= volume;
+	fx = k3*rx; fy = k3*ry;
+	if (DIM == 3) fz = k3*rz;
       }
     }
     else if (kind == GFSB200_FORCE_LIFT) {
       const double cl = S.cl_const == S.cl_const ? S.cl_const : 0.5;
+      const double q = rho*cl*volume;
       if (DIM == 3) {
 	const double2 * p = reinterpret_cast<const double2 *> (fld.vort + (int64_t) L.cell*4);
 	const double2 a = __ldg (p), b = __ldg (p + 1);
 	const double wx = a.x, wy = a.y, wz = b.x;
-	fx = rho*cl*(ry*wz - rz*wy);
-	fy = rho*cl*(rz*wx - rx*wz);
-	fz = rho*cl*(rx*wy - ry*wx);
+	fx = q*(ry*wz - rz*wy);
+	fy = q*(rz*wx - rx*wz);
+	fz = q*(rx*wy - ry*wx);
       }
       else {
 	const double wz = __ldg (fld.vort + L.cell);
-	fx = rho*cl*ry*wz;
-	fy = -rho*cl*rx*wz;
+	fx = q*ry*wz;
+	fy = -q*rx*wz;
       }
     }
     else if (kind == GFSB200_FORCE_BUOY) {
       if (!ONFLUID) {                   /* compute_forces_onfluid skips GfsForceBuoy, :753-765 */
-	const double drho = mass/volume - rho;
-	fx = drho*S.g[0]; fy = drho*S.g[1];
-	if (DIM == 3) fz = drho*S.g[2];
+	/* (m/V - rho) g V = (m - rho V) g */
+	const double dm = mass - rho*volume;
+	fx = dm*S.g[0]; fy = dm*S.g[1];
+	if (DIM == 3) fz = dm*S.g[2];
       }
     }
-    Fx = fx*volume + Fx;
-    Fy = fy*volume + Fy;
-    if (DIM == 3) Fz = fz*volume + Fz;
+    Fx += fx; Fy += fy;
+    if (DIM == 3) Fz += fz;
   }
 }
 
 /* ------------------------------------------------------------------ */
 
-template <int DIM, bool REC_CELL, bool REC_FORCE>
-__global__ void __launch_bounds__(256)
+template <int DIM, bool REC, bool LATTICE, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 step_kernel (DevTree T, DevField fld, DevParticles P, DevStep S)
 {
   const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= P.n)
     return;
-  double x = P.x[i], y = P.y[i], z = DIM == 3 ? P.z[i] : 0.;
-  double vx = P.vx[i], vy = P.vy[i], vz = DIM == 3 ? P.vz[i] : 0.;
-  const double mass = P.mass[i], volume = P.volume[i];
+  /* streaming (evict-first) loads: the particle arrays are touched once per
+     step and must not displace the vertex / vorticity tables from L1/L2 */
+  double x = __ldcs (P.x + i), y = __ldcs (P.y + i), z = DIM == 3 ? __ldcs (P.z + i) : 0.;
+  double vx = __ldcs (P.vx + i), vy = __ldcs (P.vy + i), vz = DIM == 3 ? __ldcs (P.vz + i) : 0.;
+  const double mass = __ldcs (P.mass + i), volume = __ldcs (P.volume + i);
 
-  const Located L = locate<DIM> (T, x, y, z);
-  if (REC_CELL)
+  const Located L = locate<DIM, LATTICE> (T, x, y, z);
+  if (REC)
     P.cell[i] = L.cell;
   if (L.cell < 0)     /* outside: gfs_particle_list_event removes it first (:987) */
     return;
 
   double Fx, Fy, Fz, rho;
-  total_force<DIM, false> (T, fld, S, L, x, y, z, vx, vy, vz, mass, volume, Fx, Fy, Fz, rho);
-  if (REC_FORCE) {
+  total_force<DIM, false, LATTICE> (T, fld, S, L, x, y, z, vx, vy, vz, mass, volume, Fx, Fy, Fz, rho);
+  if (REC) {
     P.fx[i] = Fx; P.fy[i] = Fy; P.fz[i] = Fz;
   }
 
   /* x += v dt/2 ; v += F dt/m ; x += v dt/2   (:828-839) */
-  const double dt = S.dt;
-  x += vx*dt/2.; vx += Fx*dt/mass; x += vx*dt/2.;
-  y += vy*dt/2.; vy += Fy*dt/mass; y += vy*dt/2.;
-  P.x[i] = x; P.y[i] = y; P.vx[i] = vx; P.vy[i] = vy;
+  const double hdt = 0.5*S.dt, dtm = S.dt/mass;
+  x = fma (vx, hdt, x); vx = fma (Fx, dtm, vx); x = fma (vx, hdt, x);
+  y = fma (vy, hdt, y); vy = fma (Fy, dtm, vy); y = fma (vy, hdt, y);
+  __stcs (P.x + i, x); __stcs (P.y + i, y); __stcs (P.vx + i, vx); __stcs (P.vy + i, vy);
   if (DIM == 3) {
-    z += vz*dt/2.; vz += Fz*dt/mass; z += vz*dt/2.;
-    P.z[i] = z; P.vz[i] = vz;
+    z = fma (vz, hdt, z); vz = fma (Fz, dtm, vz); z = fma (vz, hdt, z);
+    __stcs (P.z + i, z); __stcs (P.vz + i, vz);
   }
 }
 
@@ -563,20 +614,20 @@ inline unsigned grid_for (int64_t n, int threads) { return (unsigned) ((n + thre
 extern "C" {
 
 void gfsb200_launch_step (const DevTree * T, const DevField * F, const DevParticles * P,
-			  const DevStep * S, int rec_cell, int rec_force, cudaStream_t st)
+			  const DevStep * S, int rec, int minb, cudaStream_t st)
 {
   if (P->n <= 0) return;
   const int th = 256;
   const unsigned g = grid_for (P->n, th);
-#define LAUNCH(D, RC, RF) step_kernel<D, RC, RF><<<g, th, 0, st>>> (*T, *F, *P, *S)
-  if (T->dim == 3) {
-    if (rec_cell) { if (rec_force) LAUNCH (3, true, true); else LAUNCH (3, true, false); }
-    else          { if (rec_force) LAUNCH (3, false, true); else LAUNCH (3, false, false); }
-  }
-  else {
-    if (rec_cell) { if (rec_force) LAUNCH (2, true, true); else LAUNCH (2, true, false); }
-    else          { if (rec_force) LAUNCH (2, false, true); else LAUNCH (2, false, false); }
-  }
+  const bool lat = T->lattice_n1 > 0;
+#define LAUNCH(D, R, LA, MB) step_kernel<D, R, LA, MB><<<g, th, 0, st>>> (*T, *F, *P, *S)
+#define PICK_MB(D, R, LA) do { if (minb <= 2) LAUNCH (D, R, LA, 2); else if (minb == 3) LAUNCH (D, R, LA, 3); \
+			       else LAUNCH (D, R, LA, 4); } while (0)
+#define PICK(D) do { if (rec) { if (lat) PICK_MB (D, true, true); else PICK_MB (D, true, false); } \
+		     else     { if (lat) PICK_MB (D, false, true); else PICK_MB (D, false, false); } } while (0)
+  if (T->dim == 3) PICK (3); else PICK (2);
+#undef PICK
+#undef PICK_MB
 #undef LAUNCH
 }
 

@@ -344,6 +344,71 @@ static int vtable_grow (vtable_t * v)
   return 0;
 }
 
+/* A one-box tree whose leaves all sit at one level L has exactly one vertex per
+ * point of the (2^L + 1)^dim lattice.  Renumber them in row-major lattice order,
+ *   id = (k*(N + 1) + j)*(N + 1) + i,   N = 2^L,
+ * so that the device can compute the ids of a leaf's corners from its column
+ * indices instead of loading leaf_vtx.  Leaves lattice_level = -1 otherwise. */
+static void lattice_renumber (gfsb200_tree * t, const int64_t * vkey)
+{
+  const int dim = t->dim, nc = t->nchild;
+  const int L = t->max_level - t->root_level;
+  if (t->n_box_roots != 1 || t->complete_level != t->max_level || L < 1 || L > (dim == 3 ? 10 : 15))
+    return;
+  const int64_t N1 = ((int64_t) 1 << L) + 1;
+  int64_t want = N1*N1*(dim == 3 ? N1 : 1);
+  if (want != t->n_vertices)
+    return;
+  const int nv = t->n_vertices;
+  const double lattice = ldexp (1., GFSB200_MAX_LEVEL + 2);
+  const double size = ldexp (1., -t->root_level);
+  const int64_t step = (int64_t) llround (ldexp (size, -L)*lattice);
+  int64_t lo[3];
+  for (int a = 0; a < 3; a++)
+    lo[a] = a < dim ? (int64_t) llround ((t->pos[a] - size/2.)*lattice) : 0;
+  int32_t * newid = malloc ((size_t) nv*sizeof (int32_t));
+  char * seen = calloc ((size_t) nv, 1);
+  int ok = newid && seen;
+  for (int v = 0; v < nv && ok; v++) {
+    int64_t id = 0;
+    for (int a = dim - 1; a >= 0; a--) {
+      int64_t d = vkey[3*v + a] - lo[a];
+      if (d < 0 || d % step || d/step >= N1) { ok = 0; break; }
+      id = id*N1 + d/step;
+    }
+    if (ok && seen[id]) ok = 0;
+    if (ok) { seen[id] = 1; newid[v] = (int32_t) id; }
+  }
+  free (seen);
+  if (ok) {
+    int32_t * off = malloc ((size_t) (nv + 1)*sizeof (int32_t));
+    int32_t * cell = malloc ((size_t) (t->vtx_off[nv] ? t->vtx_off[nv] : 1)*sizeof (int32_t));
+    double * w = malloc ((size_t) (t->vtx_off[nv] ? t->vtx_off[nv] : 1)*sizeof (double));
+    if (off && cell && w) {
+      for (int v = 0; v < nv; v++)
+	off[newid[v] + 1] = t->vtx_off[v + 1] - t->vtx_off[v];
+      off[0] = 0;
+      for (int v = 0; v < nv; v++)
+	off[v + 1] += off[v];
+      for (int v = 0; v < nv; v++) {
+	int32_t o = off[newid[v]], b = t->vtx_off[v], n = t->vtx_off[v + 1] - b;
+	memcpy (cell + o, t->vtx_cell + b, (size_t) n*sizeof (int32_t));
+	memcpy (w + o, t->vtx_w + b, (size_t) n*sizeof (double));
+      }
+      for (int64_t e = 0; e < (int64_t) t->n_cells*nc; e++)
+	if (t->leaf_vtx[e] >= 0)
+	  t->leaf_vtx[e] = newid[t->leaf_vtx[e]];
+      free (t->vtx_off); free (t->vtx_cell); free (t->vtx_w);
+      t->vtx_off = off; t->vtx_cell = cell; t->vtx_w = w;
+      t->lattice_level = t->max_level;
+    }
+    else {
+      free (off); free (cell); free (w);
+    }
+  }
+  free (newid);
+}
+
 int gfsb200_tree_build_stencils (gfsb200_tree * t)
 {
   if (!t || !t->finalized)
@@ -385,6 +450,7 @@ int gfsb200_tree_build_stencils (gfsb200_tree * t)
   const double lattice = ldexp (1., GFSB200_MAX_LEVEL + 2);
   int32_t nv = 0;
   int32_t * rep = NULL;
+  int64_t * vkey = NULL;            /* [nv][3] lattice position of each vertex */
   int64_t rep_cap = 0;
   for (int32_t i = 0; i < n; i++) {
     if ((t->flags[i] & (GFSB200_CELL_LEAF | GFSB200_CELL_BOUNDARY)) != GFSB200_CELL_LEAF)
@@ -399,7 +465,7 @@ int gfsb200_tree_build_stencils (gfsb200_tree * t)
       }
       int64_t e = (int64_t) i*nc + k;
       if ((vt.used + 1)*10 > (int64_t) (vt.mask + 1)*6 && vtable_grow (&vt)) {
-	free (sig); free (vt.s); free (rep);
+	free (sig); free (vt.s); free (rep); free (vkey);
 	return gfsb200_fail (GFSB200_ERR_NOMEM, "build_stencils: out of memory");
       }
       vslot_t * s = vtable_find (&vt, key, sig[2*e], sig[2*e + 1]);
@@ -411,13 +477,16 @@ int gfsb200_tree_build_stencils (gfsb200_tree * t)
 	if (nv >= rep_cap) {
 	  rep_cap = rep_cap ? rep_cap*2 : 1 << 16;
 	  int32_t * r2 = realloc (rep, (size_t) rep_cap*2*sizeof (int32_t));
-	  if (!r2) {
-	    free (sig); free (vt.s); free (rep);
+	  int64_t * k2 = realloc (vkey, (size_t) rep_cap*3*sizeof (int64_t));
+	  if (r2) rep = r2;
+	  if (k2) vkey = k2;
+	  if (!r2 || !k2) {
+	    free (sig); free (vt.s); free (rep); free (vkey);
 	    return gfsb200_fail (GFSB200_ERR_NOMEM, "build_stencils: out of memory");
 	  }
-	  rep = r2;
 	}
 	rep[2*nv] = i; rep[2*nv + 1] = k;
+	vkey[3*nv] = key[0]; vkey[3*nv + 1] = key[1]; vkey[3*nv + 2] = key[2];
 	vt.used++;
 	nv++;
       }
@@ -430,7 +499,7 @@ int gfsb200_tree_build_stencils (gfsb200_tree * t)
   /* pass C: CSR of the canonical stencils */
   t->vtx_off = malloc ((size_t) (nv + 1)*sizeof (int32_t));
   if (!t->vtx_off) {
-    free (rep);
+    free (rep); free (vkey);
     return gfsb200_fail (GFSB200_ERR_NOMEM, "build_stencils: out of memory");
   }
   t->vtx_off[0] = 0;
@@ -446,7 +515,7 @@ int gfsb200_tree_build_stencils (gfsb200_tree * t)
     t->vtx_off[v] = (int32_t) total;
     total += c;
     if (total > INT32_MAX) {
-      free (rep);
+      free (rep); free (vkey);
       return gfsb200_fail (GFSB200_ERR_UNSUPPORTED, "build_stencils: stencil table too large");
     }
   }
@@ -454,7 +523,7 @@ int gfsb200_tree_build_stencils (gfsb200_tree * t)
   t->vtx_cell = malloc ((size_t) (total ? total : 1)*sizeof (int32_t));
   t->vtx_w = malloc ((size_t) (total ? total : 1)*sizeof (double));
   if (!t->vtx_cell || !t->vtx_w) {
-    free (rep);
+    free (rep); free (vkey);
     return gfsb200_fail (GFSB200_ERR_NOMEM, "build_stencils: out of memory");
   }
 #pragma omp parallel for schedule(dynamic, 4096)
@@ -469,5 +538,8 @@ int gfsb200_tree_build_stencils (gfsb200_tree * t)
   }
   free (rep);
   t->n_vertices = nv;
+  t->lattice_level = -1;
+  lattice_renumber (t, vkey);
+  free (vkey);
   return GFSB200_OK;
 }

@@ -131,6 +131,8 @@ typedef struct {
   const double  * vtx_w;              /* normalised weights */
   const int32_t * leaf_vtx;           /* [n_cells][2^dim] vertex id per corner (reference corner
 					 order, src/fluid.c:2588-2606), -1 for non-leaves */
+  int32_t lattice_level;              /* >= 0: all leaves at this level and vertex ids are
+					 row-major on its (2^L + 1)^dim lattice; else -1 */
 } gfsb200_tree_view;
 
 int gfsb200_tree_get_view (const gfsb200_tree * t, gfsb200_tree_view * v);
