@@ -105,9 +105,9 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def build_world(worlds, name, n_particles):
+def build_world(worlds, name, n_particles, level=0):
     if name == "C2":
-        return worlds.make_c2(n_particles=n_particles or 10_000_000)
+        return worlds.make_c2(level=level or 7, n_particles=n_particles or 10_000_000)
     if name == "C3":
         return worlds.make_c3(n_particles=n_particles or 10_000_000)
     if name == "C4":
@@ -224,7 +224,7 @@ def run_b200(args):
 
     pkg = entry.load_package()
     capi, worlds = pkg.capi, pkg.worlds
-    world = build_world(worlds, args.config, args.particles)
+    world = build_world(worlds, args.config, args.particles, args.level)
     n_local = world.n_particles                       # weak scaling: fixed per-GPU batch
     ctx = capi.Context(local_rank)
     ctx.upload_tree(world.tree)
@@ -389,6 +389,7 @@ def main():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--particles", type=int, default=0, help="particles per GPU (default: the config's)")
     ap.add_argument("--two-way", action="store_true")
+    ap.add_argument("--level", type=int, default=0, help="experiment: override the C2 tree level")
     ap.add_argument("--resort", type=int, default=25, help="re-sort particles by cell every R steps (0: never)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")

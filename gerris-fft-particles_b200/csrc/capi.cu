@@ -26,7 +26,7 @@
 extern "C" {
 void gfsb200_launch_cell_pass (const DevTree *, const DevField *, int, cudaStream_t);
 void gfsb200_launch_step (const DevTree *, const DevField *, const DevParticles *, const DevStep *,
-			  int, int, cudaStream_t);   /* (.., record, min blocks/SM, stream) */
+			  int, int, int, int, cudaStream_t);   /* (.., record, min blocks/SM, mode, SMs, stream) */
 void gfsb200_launch_advect (const DevTree *, const DevField *, const DevParticles *, double, int,
 			    cudaStream_t);
 void gfsb200_launch_locate (const DevTree *, int64_t, const double *, const double *,
@@ -85,6 +85,7 @@ struct gfsb200_ctx {
   double * deposit;
   int64_t deposit_count;
   int step_minb;               /* __launch_bounds__ min blocks/SM variant of the step kernel */
+  int step_mode;               /* 0: plain kernel; 2/3: TMA-staged persistent kernel, that many stages */
   /* timing */
   std::vector<cudaEvent_t> ev;
   size_t ev_used;
@@ -112,8 +113,8 @@ static void free_tree (gfsb200_ctx * c)
   cudaFree (c->d_level); cudaFree (c->d_info); cudaFree (c->d_vtx_w); cudaFree (c->d_vtx_wuni);
   c->d_child0 = c->d_neighbor = c->d_la_slot = c->d_vtx_off = c->d_vtx_cell = c->d_leaf_vtx = NULL;
   c->d_level = c->d_info = NULL; c->d_vtx_w = c->d_vtx_wuni = NULL;
-  cudaFree (c->F.vtx_val); cudaFree (c->F.vort);
-  c->F.vtx_val = c->F.vort = NULL;
+  cudaFree (c->F.vtx_val); cudaFree (c->F.vort); cudaFree (c->F.nodata_flag);
+  c->F.vtx_val = c->F.vort = NULL; c->F.nodata_flag = NULL;
   for (int i = 0; i < 5; i++) { cudaFree (c->d_field[i]); c->d_field[i] = NULL; }
   cudaFree (c->deposit); c->deposit = NULL; c->deposit_count = 0;
   c->have_tree = c->have_field = false;
@@ -168,6 +169,7 @@ extern "C" int gfsb200_ctx_create (int device, gfsb200_ctx ** out)
   c->deposit = NULL; c->deposit_count = 0;
   c->ev_used = 0; c->timing = true;
   c->step_minb = getenv ("GFSB200_STEP_MINB") ? atoi (getenv ("GFSB200_STEP_MINB")) : 3;
+  c->step_mode = getenv ("GFSB200_STEP_MODE") ? atoi (getenv ("GFSB200_STEP_MODE")) : 2;
   if (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc ((void **) &c->d_count, sizeof (int32_t)) != cudaSuccess ||
       cudaMalloc ((void **) &c->d_ptr_table, 2*NCOL*sizeof (double *)) != cudaSuccess) {
@@ -284,6 +286,8 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
   const int vs = t->dim == 3 ? 4 : 2, ws = t->dim == 3 ? 4 : 1;
   CK (cudaMalloc ((void **) &c->F.vtx_val, (size_t) (t->n_vertices ? t->n_vertices : 1)*vs*sizeof (double)));
   CK (cudaMalloc ((void **) &c->F.vort, (size_t) n*ws*sizeof (double)));
+  CK (cudaMemsetAsync (c->F.vort, 0, (size_t) n*ws*sizeof (double), c->stream));
+  CK (cudaMalloc ((void **) &c->F.nodata_flag, sizeof (int)));
   c->deposit_count = (int64_t) (1 + t->dim)*n;
   CK (cudaMalloc ((void **) &c->deposit, (size_t) c->deposit_count*sizeof (double)));
   CK (cudaMemsetAsync (c->deposit, 0, (size_t) c->deposit_count*sizeof (double), c->stream));
@@ -297,6 +301,7 @@ extern "C" int gfsb200_refresh_field (gfsb200_ctx * c)
   if (!c || !c->have_tree || !c->F.u[0])
     return gfsb200_fail (GFSB200_ERR_STATE, "refresh_field: no tree/field resident");
   CK (cudaSetDevice (c->device));
+  CK (cudaMemsetAsync (c->F.nodata_flag, 0, sizeof (int), c->stream));
   gfsb200_launch_cell_pass (&c->T, &c->F, c->n_sm, c->stream);
   CK (cudaGetLastError ());
   c->have_field = true;
@@ -372,12 +377,18 @@ extern "C" int gfsb200_download_vorticity (gfsb200_ctx * c, int64_t n, const int
   for (int64_t j = 0; j < n; j++) {
     if (cells[j] < 0 || cells[j] >= c->T.n_cells)
       return gfsb200_fail (GFSB200_ERR_ARG, "download_vorticity: cell %d out of range", cells[j]);
+    size_t slot = cells[j];
+    if (c->T.lattice_n1 > 0) {
+      const int per_level = 1 << (c->T.dim*c->T.top_levels);
+      if (cells[j] < c->T.top_start || cells[j] >= c->T.top_start + per_level)
+	return gfsb200_fail (GFSB200_ERR_ARG, "download_vorticity: cell %d is not a leaf", cells[j]);
+      slot = gfsb200_lattice_index (c->T.dim, c->T.top_start, c->T.lattice_n1 - 1, cells[j]);
+    }
     if (c->T.dim == 3) {
-      out[3*j] = all[(size_t) cells[j]*4]; out[3*j + 1] = all[(size_t) cells[j]*4 + 1];
-      out[3*j + 2] = all[(size_t) cells[j]*4 + 2];
+      out[3*j] = all[slot*4]; out[3*j + 1] = all[slot*4 + 1]; out[3*j + 2] = all[slot*4 + 2];
     }
     else {
-      out[3*j] = 0.; out[3*j + 1] = 0.; out[3*j + 2] = all[cells[j]];
+      out[3*j] = 0.; out[3*j + 1] = 0.; out[3*j + 2] = all[slot];
     }
   }
   return GFSB200_OK;
@@ -412,10 +423,16 @@ extern "C" int gfsb200_particles_resize (gfsb200_ctx * c, int64_t n)
   if (n > c->cap) {
     CK (cudaStreamSynchronize (c->stream));
     int64_t keep = c->n;
+    /* columns are padded to a whole number of 256-particle tiles so that the
+       bulk copies of the staged step kernel never run past the allocation */
+    const int64_t alloc_n = (n + 255)/256*256;
     double * ncol[2][NCOL]; uint32_t * nid[2];
     for (int b = 0; b < 2; b++) {
-      for (int k = 0; k < NCOL; k++) CK (cudaMalloc ((void **) &ncol[b][k], n*sizeof (double)));
-      CK (cudaMalloc ((void **) &nid[b], n*sizeof (uint32_t)));
+      for (int k = 0; k < NCOL; k++) {
+	CK (cudaMalloc ((void **) &ncol[b][k], alloc_n*sizeof (double)));
+	CK (cudaMemsetAsync (ncol[b][k], 0, alloc_n*sizeof (double), c->stream));
+      }
+      CK (cudaMalloc ((void **) &nid[b], alloc_n*sizeof (uint32_t)));
     }
     if (keep) {
       for (int k = 0; k < NCOL; k++)
@@ -580,7 +597,7 @@ extern "C" int gfsb200_step (gfsb200_ctx * c, const gfsb200_step_params * p)
     gfsb200_launch_advect (&c->T, &c->F, &P, S.dt, p->record_cells, c->stream);
   else
     gfsb200_launch_step (&c->T, &c->F, &P, &S, p->record_cells || p->record_forces, c->step_minb,
-			 c->stream);
+			 c->step_mode, c->n_sm, c->stream);
   if ((r = timed_end (c))) return r;
   CK (cudaGetLastError ());
   return GFSB200_OK;

@@ -187,10 +187,16 @@ vorticity_kernel (DevTree T, DevField fld)
 	      center_gradient<DIM> (T, fld.u[0], cell, 1))/size;
       }
     }
+    int64_t slot = cell;
+    if (T.lattice_n1 > 0) {
+      if (!box_leaf)
+	continue;
+      slot = gfsb200_lattice_index (DIM, T.top_start, T.lattice_n1 - 1, cell);
+    }
     if (DIM == 2)
-      fld.vort[cell] = wz;
+      fld.vort[slot] = wz;
     else {
-      double2 * o = reinterpret_cast<double2 *> (fld.vort + (int64_t) cell*4);
+      double2 * o = reinterpret_cast<double2 *> (fld.vort + slot*4);
       o[0] = make_double2 (wx, wy);
       o[1] = make_double2 (wz, 0.);
     }
@@ -227,8 +233,10 @@ vertex_values_kernel (DevTree T, DevField fld)
 	s2 += w*v2;
       }
     }
-    if (nodata)
+    if (nodata) {
       s0 = s1 = s2 = GFSB200_NODATA;
+      *fld.nodata_flag = 1;
+    }
     if (DIM == 2)
       reinterpret_cast<double2 *> (fld.vtx_val)[v] = make_double2 (s0, s1);
     else {

@@ -50,7 +50,9 @@ struct DevField {
   const double * mu;           /* optional per-cell viscosity */
   /* derived per field update */
   double * vtx_val;            /* 3D: [n_vertices][4] (u,v,w,pad); 2D: [n_vertices][2] */
-  double * vort;               /* 3D: [n_cells][4] (wx,wy,wz,pad); 2D: [n_cells] (wz) */
+  double * vort;               /* 3D: [..][4] (wx,wy,wz,pad); 2D: [..] (wz).  Indexed by cell, or on
+				  lattice trees by (kz*N + ky)*N + kx with N = lattice_n1 - 1 */
+  int * nodata_flag;           /* set by the cell pass when any vertex stencil touches GFS_NODATA */
 };
 
 struct DevParticles {
@@ -72,5 +74,39 @@ struct DevStep {
   double g[3];
   double cd_const, cl_const;   /* NaN = built-in law */
 };
+
+/* compact every third (second) bit of a Morton key back into an integer */
+__host__ __device__ inline unsigned gfsb200_compact3 (unsigned v)
+{
+  v &= 0x09249249;
+  v = (v | (v >> 2)) & 0x030c30c3;
+  v = (v | (v >> 4)) & 0x0300f00f;
+  v = (v | (v >> 8)) & 0x030000ff;
+  v = (v | (v >> 16)) & 0x3ff;
+  return v;
+}
+
+__host__ __device__ inline unsigned gfsb200_compact2 (unsigned v)
+{
+  v &= 0x55555555;
+  v = (v | (v >> 1)) & 0x33333333;
+  v = (v | (v >> 2)) & 0x0f0f0f0f;
+  v = (v | (v >> 4)) & 0x00ff00ff;
+  v = (v | (v >> 8)) & 0xffff;
+  return v;
+}
+
+/* lattice trees: row-major index of leaf `cell` (child digits: bit0 = +x, bit1 = -y, bit2 = -z) */
+__host__ __device__ inline int gfsb200_lattice_index (int dim, int top_start, int n, int cell)
+{
+  const unsigned key = (unsigned) (cell - top_start);
+  if (dim == 3) {
+    const int kx = gfsb200_compact3 (key), ky = ~gfsb200_compact3 (key >> 1) & (n - 1),
+      kz = ~gfsb200_compact3 (key >> 2) & (n - 1);
+    return (kz*n + ky)*n + kx;
+  }
+  const int kx = gfsb200_compact2 (key), ky = ~gfsb200_compact2 (key >> 1) & (n - 1);
+  return ky*n + kx;
+}
 
 #endif

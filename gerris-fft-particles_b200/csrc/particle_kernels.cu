@@ -56,18 +56,17 @@ __device__ __forceinline__ unsigned spread2 (unsigned v)
 
 /* Number of level thresholds  lo + k*h (k = 1..n-1)  that are strictly below
  * p, i.e. the column the reference's strict-'>' descent (src/ftt.c:1556-1570)
- * ends in after log2(n) levels.  The quotient gives a candidate that can be
- * off by one when p - lo rounds; the two exact comparisons repair it, so the
- * result is bit-identical to the descent (thresholds are exact dyadics). */
+ * ends in after log2(n) levels.  The truncated quotient is a candidate that can
+ * be off by one when p - lo rounds; two exact comparisons against the exactly
+ * representable dyadic thresholds repair it, so the result is bit-identical to
+ * the descent.  Branch-free.  Requires p >= lo (the root test guarantees it). */
 __device__ __forceinline__ int column (double p, double lo, double h, double inv_h, int n)
 {
-  int k = (int) floor ((p - lo)*inv_h);
-  k = max (0, min (n - 1, k));
-  if (k < n - 1 && p > lo + (k + 1)*h)
-    k++;
-  else if (k > 0 && !(p > lo + k*h))
-    k--;
-  return k;
+  int k = min (__double2int_rz ((p - lo)*inv_h), n - 1);
+  const double tk = fma ((double) k, h, lo);           /* lower threshold of column k, exact */
+  const int up = (p > tk + h) & (k < n - 1);
+  const int down = (!(p > tk)) & (k > 0);
+  return k + up - down;
 }
 
 template <int DIM, bool LATTICE = false>
@@ -77,11 +76,11 @@ __device__ __forceinline__ Located locate (const DevTree & T, double x, double y
   L.cell = -1;
   L.cx = L.cy = L.cz = 0.; L.half = 0.;
   L.kx = L.ky = L.kz = 0;
-  if (!(x == x && y == y && z == z))      /* NaN: floor() -> INT_MIN -> outside in the reference */
-    return L;
 
   /* GfsLocateArray, src/domain.c:43-80: i_c = floor ((p_c - min_c)/h); h is a
-     power of two, so the division is a multiplication by its exact inverse */
+     power of two, so the division is a multiplication by its exact inverse.
+     NaN coordinates fail every comparison below and end up outside, as in the
+     reference (floor (NaN) -> INT_MIN -> index -1). */
   int root;
   if (T.single_box) {
     /* one slot: floor (t) == 0  <=>  0 <= t < 1 */
@@ -92,6 +91,8 @@ __device__ __forceinline__ Located locate (const DevTree & T, double x, double y
     root = 0;
   }
   else {
+    if (!(x == x && y == y && z == z))
+      return L;
     int ix = (int) floor ((x - T.la_min[0])*T.la_inv_h);
     int iy = (int) floor ((y - T.la_min[1])*T.la_inv_h);
     if (ix < 0 || ix >= T.la_n[0] || iy < 0 || iy >= T.la_n[1])
@@ -116,34 +117,34 @@ __device__ __forceinline__ Located locate (const DevTree & T, double x, double y
     return L;
 
   int cell = root;
-  if (T.top_levels > 0) {
+  if (LATTICE || T.top_levels > 0) {
     /* ... the first top_levels levels of the descent, resolved arithmetically
        because every GfsBox tree is complete down to that level */
     const int n = 1 << T.top_levels;
     const double h = T.top_h, inv_h = T.top_inv_h;
     const int kx = column (x, cx - half, h, inv_h, n);
     const int ky = column (y, cy - half, h, inv_h, n);
-    /* child digit per level: bit0 = (x > c), bit1 = !(y > c), bit2 = !(z > c) */
-    unsigned key;
-    if (DIM == 3) {
-      const int kz = column (z, cz - half, h, inv_h, n);
-      key = spread3 (kx) | (spread3 (~ky & (n - 1)) << 1) | (spread3 (~kz & (n - 1)) << 2);
-      cz = (cz - half) + (kz + 0.5)*h;
-      L.kz = kz;
-    }
-    else
-      key = spread2 (kx) | (spread2 (~ky & (n - 1)) << 1);
+    const int kz = DIM == 3 ? column (z, cz - half, h, inv_h, n) : 0;
     cx = (cx - half) + (kx + 0.5)*h;
     cy = (cy - half) + (ky + 0.5)*h;
+    if (DIM == 3) cz = (cz - half) + (kz + 0.5)*h;
     half = 0.5*h;
+    L.kx = kx; L.ky = ky; L.kz = kz;
+    if (LATTICE) {
+      /* every leaf sits at the complete level: no descent, no child0 load; the
+	 tables are addressed by (kx,ky,kz), the Morton cell index is only
+	 materialised when asked for (cell_index ()) */
+      L.cell = 0;
+      L.cx = cx; L.cy = cy; L.cz = cz; L.half = half;
+      return L;
+    }
+    /* child digit per level: bit0 = (x > c), bit1 = !(y > c), bit2 = !(z > c) */
+    unsigned key;
+    if (DIM == 3)
+      key = spread3 (kx) | (spread3 (~ky & (n - 1)) << 1) | (spread3 (~kz & (n - 1)) << 2);
+    else
+      key = spread2 (kx) | (spread2 (~ky & (n - 1)) << 1);
     cell = T.top_start + (root << (DIM*T.top_levels)) + (int) key;
-    L.kx = kx; L.ky = ky;
-  }
-  if (LATTICE) {
-    /* every leaf sits at the complete level: no descent, no child0 load */
-    L.cell = cell;
-    L.cx = cx; L.cy = cy; L.cz = cz; L.half = half;
-    return L;
   }
 
   /* ... then strict-'>' descent with exactly tracked dyadic centres */
@@ -166,6 +167,31 @@ __device__ __forceinline__ Located locate (const DevTree & T, double x, double y
   L.cell = cell;
   L.cx = cx; L.cy = cy; L.cz = cz; L.half = half;
   return L;
+}
+
+/* flat cell index of a located leaf (lattice trees: rebuilt from the columns) */
+template <int DIM, bool LATTICE>
+__device__ __forceinline__ int cell_index (const DevTree & T, const Located & L)
+{
+  if (!LATTICE || L.cell < 0)
+    return L.cell;
+  const int n = 1 << T.top_levels;
+  unsigned key;
+  if (DIM == 3)
+    key = spread3 (L.kx) | (spread3 (~L.ky & (n - 1)) << 1) | (spread3 (~L.kz & (n - 1)) << 2);
+  else
+    key = spread2 (L.kx) | (spread2 (~L.ky & (n - 1)) << 1);
+  return T.top_start + (int) key;
+}
+
+/* index of the leaf's entry in the per-leaf tables (vorticity) */
+template <int DIM, bool LATTICE>
+__device__ __forceinline__ int64_t leaf_slot (const DevTree & T, const Located & L)
+{
+  if (!LATTICE)
+    return L.cell;
+  const int n = T.lattice_n1 - 1;
+  return DIM == 3 ? ((int64_t) L.kz*n + L.ky)*n + L.kx : (int64_t) L.ky*n + L.kx;
 }
 
 /* ------------------------------------------------------------------ */
@@ -193,6 +219,8 @@ __device__ __forceinline__ void interpolate (const DevTree & T, const DevField &
 {
   /* half is a power of two: its inverse is an exponent flip, no division */
   const double inv = __longlong_as_double ((2046LL << 52) - __double_as_longlong (L.half));
+  /* one uniform load decides whether any vertex needs the NODATA fallback */
+  const bool any_nodata = __ldg (fld.nodata_flag) != 0;
   if (DIM == 3) {
     int id[8];
     if (LATTICE) {
@@ -212,18 +240,16 @@ __device__ __forceinline__ void interpolate (const DevTree & T, const DevField &
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const double2 * p = reinterpret_cast<const double2 *> (fld.vtx_val + (int64_t) id[k]*4);
-      const double2 a = __ldg (p), b = __ldg (p + 1);
-      fu[k] = a.x; fv[k] = a.y; fw[k] = b.x;
+      const double2 a = __ldg (p);
+      fu[k] = a.x; fv[k] = a.y; fw[k] = __ldg (reinterpret_cast<const double *> (p + 1));
     }
-    if (__double2hiint (fu[0]) == 0x7fefffff || __double2hiint (fu[1]) == 0x7fefffff ||
-	__double2hiint (fu[2]) == 0x7fefffff || __double2hiint (fu[3]) == 0x7fefffff ||
-	__double2hiint (fu[4]) == 0x7fefffff || __double2hiint (fu[5]) == 0x7fefffff ||
-	__double2hiint (fu[6]) == 0x7fefffff || __double2hiint (fu[7]) == 0x7fefffff) {
+    if (any_nodata) {
+      const int cell = cell_index<DIM, LATTICE> (T, L);
 #pragma unroll
       for (int k = 0; k < 8; k++) {
-	fu[k] = resolve (fu[k], fld.u[0], L.cell);
-	fv[k] = resolve (fv[k], fld.u[1], L.cell);
-	fw[k] = resolve (fw[k], fld.u[2], L.cell);
+	fu[k] = resolve (fu[k], fld.u[0], cell);
+	fv[k] = resolve (fv[k], fld.u[1], cell);
+	fw[k] = resolve (fw[k], fld.u[2], cell);
       }
     }
     /* t in [0,1] along each axis: (1 + (p - o)/(h/2))/2 */
@@ -247,13 +273,16 @@ __device__ __forceinline__ void interpolate (const DevTree & T, const DevField &
     }
     else
       id = __ldg (reinterpret_cast<const int4 *> (T.leaf_vtx + (int64_t) L.cell*4));
+    const int cell = cell_index<DIM, LATTICE> (T, L);
     const double2 * vv = reinterpret_cast<const double2 *> (fld.vtx_val);
     double2 f0 = __ldg (vv + id.x), f1 = __ldg (vv + id.y), f2 = __ldg (vv + id.z), f3 = __ldg (vv + id.w);
-    const double c0 = fld.u[0][L.cell], c1 = fld.u[1][L.cell];
-    f0.x = resolve (f0.x, fld.u[0], L.cell); f0.y = resolve (f0.y, fld.u[1], L.cell);
-    f1.x = resolve (f1.x, fld.u[0], L.cell); f1.y = resolve (f1.y, fld.u[1], L.cell);
-    f2.x = resolve (f2.x, fld.u[0], L.cell); f2.y = resolve (f2.y, fld.u[1], L.cell);
-    f3.x = resolve (f3.x, fld.u[0], L.cell); f3.y = resolve (f3.y, fld.u[1], L.cell);
+    const double c0 = fld.u[0][cell], c1 = fld.u[1][cell];
+    if (any_nodata) {
+      f0.x = resolve (f0.x, fld.u[0], cell); f0.y = resolve (f0.y, fld.u[1], cell);
+      f1.x = resolve (f1.x, fld.u[0], cell); f1.y = resolve (f1.y, fld.u[1], cell);
+      f2.x = resolve (f2.x, fld.u[0], cell); f2.y = resolve (f2.y, fld.u[1], cell);
+      f3.x = resolve (f3.x, fld.u[0], cell); f3.y = resolve (f3.y, fld.u[1], cell);
+    }
     const double px = (x - L.cx)*inv, py = (y - L.cy)*inv;
     const double a = (px + py)/2., b = (py - px)/2.;
     double uu = c0, vv2 = c1;
@@ -279,7 +308,14 @@ __device__ __forceinline__ void interpolate (const DevTree & T, const DevField &
 #define DIA_K 1.2407009817988000333       /* 2 (3/(4 pi))^(1/3) */
 #define INV_DIA_K2 0.64962951495345899316  /* 1/DIA_K^2 */
 
-template <int DIM, bool ONFLUID, bool LATTICE = false>
+/* PROG: the force list known at compile time (kinds in list order, 4 bits
+ * each), or 0 to read it from the launch parameters. */
+__host__ __device__ constexpr int prog_len (unsigned prog)
+{
+  return prog == 0 ? 0 : 1 + prog_len (prog >> 4);
+}
+
+template <int DIM, bool ONFLUID, bool LATTICE = false, unsigned PROG = 0>
 __device__ __forceinline__ void total_force (const DevTree & T, const DevField & fld,
 					     const DevStep & S, const Located & L,
 					     double x, double y, double z,
@@ -287,23 +323,51 @@ __device__ __forceinline__ void total_force (const DevTree & T, const DevField &
 					     double mass, double volume,
 					     double & Fx, double & Fy, double & Fz, double & rho_out)
 {
+  const unsigned forces = PROG ? PROG : S.forces;
+  const int n_forces = PROG ? prog_len (PROG) : S.n_forces;
+  bool any_lift = false, need_velocity = PROG ? false : S.need_velocity != 0;
+  if (PROG) {
+#pragma unroll
+    for (int k = 0; k < prog_len (PROG); k++) {
+      any_lift |= ((PROG >> (4*k)) & 15) == GFSB200_FORCE_LIFT;
+      need_velocity |= ((PROG >> (4*k)) & 15) != GFSB200_FORCE_BUOY;
+    }
+  }
+  /* issue the per-leaf vorticity gather before the vertex gathers so that the
+     two latencies overlap */
+  double wx = 0., wy = 0., wz = 0.;
+  if (PROG && any_lift) {
+    const int64_t slot = leaf_slot<DIM, LATTICE> (T, L);
+    if (DIM == 3) {
+      const double2 * p = reinterpret_cast<const double2 *> (fld.vort + slot*4);
+      const double2 a = __ldg (p);
+      wx = a.x; wy = a.y; wz = __ldg (reinterpret_cast<const double *> (p + 1));
+    }
+    else
+      wz = __ldg (fld.vort + slot);
+  }
   Fx = Fy = Fz = 0.;
-  const double rho = fld.alpha ? 1./fld.alpha[L.cell] : S.rho;
+  double rho = S.rho;
+  if (fld.alpha)
+    rho = 1./fld.alpha[cell_index<DIM, LATTICE> (T, L)];
   rho_out = rho;
   double rx = 0., ry = 0., rz = 0.;
-  if (S.need_velocity) {
+  if (need_velocity) {
     double u, v, w;
     interpolate<DIM, LATTICE> (T, fld, L, x, y, z, u, v, w);
     rx = u - vx; ry = v - vy; rz = DIM == 3 ? w - vz : 0.;
   }
-  for (int k = 0; k < S.n_forces; k++) {
-    const int kind = (S.forces >> (4*k)) & 15;
+#pragma unroll
+  for (int k = 0; k < (PROG ? prog_len (PROG) : GFSB200_MAX_FORCES); k++) {
+    if (!PROG && k >= n_forces)
+      break;
+    const int kind = (forces >> (4*k)) & 15;
     /* f*V, the particle force contribution of compute_forces (:744) */
     double fx = 0., fy = 0., fz = 0.;
     if (kind == GFSB200_FORCE_DRAG) {
       double mu = S.mu, inv_mu = S.inv_mu;
       if (fld.mu) {
-	mu = fld.mu[L.cell];
+	mu = fld.mu[cell_index<DIM, LATTICE> (T, L)];
 	inv_mu = mu != 0. ? 1./mu : 0.;
       }
       if (mu != 0.) {
@@ -330,18 +394,24 @@ __device__ __forceinline__ void total_force (const DevTree & T, const DevField &
       }
     }
     else if (kind == GFSB200_FORCE_LIFT) {
+      if (!(PROG && any_lift)) {
+	const int64_t slot = leaf_slot<DIM, LATTICE> (T, L);
+	if (DIM == 3) {
+	  const double2 * p = reinterpret_cast<const double2 *> (fld.vort + slot*4);
+	  const double2 a = __ldg (p);
+	  wx = a.x; wy = a.y; wz = __ldg (reinterpret_cast<const double *> (p + 1));
+	}
+	else
+	  wz = __ldg (fld.vort + slot);
+      }
       const double cl = S.cl_const == S.cl_const ? S.cl_const : 0.5;
       const double q = rho*cl*volume;
       if (DIM == 3) {
-	const double2 * p = reinterpret_cast<const double2 *> (fld.vort + (int64_t) L.cell*4);
-	const double2 a = __ldg (p), b = __ldg (p + 1);
-	const double wx = a.x, wy = a.y, wz = b.x;
 	fx = q*(ry*wz - rz*wy);
 	fy = q*(rz*wx - rx*wz);
 	fz = q*(rx*wy - ry*wx);
       }
       else {
-	const double wz = __ldg (fld.vort + L.cell);
 	fx = q*ry*wz;
 	fy = -q*rx*wz;
       }
@@ -361,7 +431,7 @@ __device__ __forceinline__ void total_force (const DevTree & T, const DevField &
 
 /* ------------------------------------------------------------------ */
 
-template <int DIM, bool REC, bool LATTICE, int MINB>
+template <int DIM, bool REC, bool LATTICE, unsigned PROG, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 step_kernel (DevTree T, DevField fld, DevParticles P, DevStep S)
 {
@@ -376,24 +446,186 @@ step_kernel (DevTree T, DevField fld, DevParticles P, DevStep S)
 
   const Located L = locate<DIM, LATTICE> (T, x, y, z);
   if (REC)
-    P.cell[i] = L.cell;
+    P.cell[i] = cell_index<DIM, LATTICE> (T, L);
   if (L.cell < 0)     /* outside: gfs_particle_list_event removes it first (:987) */
     return;
 
   double Fx, Fy, Fz, rho;
-  total_force<DIM, false, LATTICE> (T, fld, S, L, x, y, z, vx, vy, vz, mass, volume, Fx, Fy, Fz, rho);
+  total_force<DIM, false, LATTICE, PROG> (T, fld, S, L, x, y, z, vx, vy, vz, mass, volume,
+					 Fx, Fy, Fz, rho);
   if (REC) {
     P.fx[i] = Fx; P.fy[i] = Fy; P.fz[i] = Fz;
   }
 
   /* x += v dt/2 ; v += F dt/m ; x += v dt/2   (:828-839) */
-  const double hdt = 0.5*S.dt, dtm = S.dt/mass;
+  const double hdt = 0.5*S.dt, dtm = S.dt*__drcp_rn (mass);
   x = fma (vx, hdt, x); vx = fma (Fx, dtm, vx); x = fma (vx, hdt, x);
   y = fma (vy, hdt, y); vy = fma (Fy, dtm, vy); y = fma (vy, hdt, y);
   __stcs (P.x + i, x); __stcs (P.y + i, y); __stcs (P.vx + i, vx); __stcs (P.vy + i, vy);
   if (DIM == 3) {
     z = fma (vz, hdt, z); vz = fma (Fz, dtm, vz); z = fma (vz, hdt, z);
     __stcs (P.z + i, z); __stcs (P.vz + i, vz);
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/* The same step with the particle stream staged through shared memory by the
+ * TMA engine (cp.async.bulk + mbarrier), as a persistent kernel.
+ *
+ * Profiling the plain kernel above showed it latency-bound, not issue- or
+ * bandwidth-bound: with ~24 resident warps per SM each holding 2 KB of loads
+ * in flight only while in its load phase, about 40 % of the bytes-in-flight
+ * needed to saturate HBM3e were outstanding.  Here every CTA keeps STAGES
+ * tiles (256 particles x 8 fp64 columns = 16 KB each) in flight at all times,
+ * independent of what its warps are computing, at no register cost; the
+ * compute part then starts from 29-cycle LDS instead of ~800-cycle LDG. */
+
+namespace pipe {
+
+__device__ __forceinline__ uint32_t smem_u32 (const void * p)
+{
+  return (uint32_t) __cvta_generic_to_shared (p);
+}
+
+__device__ __forceinline__ void mbar_init (uint64_t * bar, unsigned count)
+{
+  asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32 (bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx (uint64_t * bar, unsigned bytes)
+{
+  asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+		:: "r"(smem_u32 (bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait (uint64_t * bar, unsigned parity)
+{
+  asm volatile ("{\n\t.reg .pred p;\n\t"
+		"WAIT_%=:\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+		"@p bra DONE_%=;\n\t"
+		"bra WAIT_%=;\n\t"
+		"DONE_%=:\n\t}"
+		:: "r"(smem_u32 (bar)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ uint64_t policy_evict_first ()
+{
+  uint64_t pol;
+  asm volatile ("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+/* global -> shared bulk copy, completion signalled on `bar` (SASS: UBLKCP) */
+__device__ __forceinline__ void bulk_g2s (void * dst, const void * src, unsigned bytes,
+					  uint64_t * bar, uint64_t policy)
+{
+  asm volatile ("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+		"[%0], [%1], %2, [%3], %4;"
+		:: "r"(smem_u32 (dst)), "l"(src), "r"(bytes), "r"(smem_u32 (bar)), "l"(policy) : "memory");
+}
+
+__device__ __forceinline__ void fence_async_shared ()
+{
+  asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+} // namespace pipe
+
+#define PIPE_TILE 256
+
+template <int DIM, bool LATTICE, unsigned PROG, int STAGES>
+__global__ void __launch_bounds__(PIPE_TILE, 3)
+step_kernel_pipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_tiles)
+{
+  constexpr int NC = DIM == 3 ? 8 : 6;
+  constexpr unsigned COL_BYTES = PIPE_TILE*sizeof (double);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double (* buf)[NC][PIPE_TILE] = reinterpret_cast<double (*)[NC][PIPE_TILE]> (smem_raw);
+  __shared__ uint64_t full[STAGES];
+  const int tid = threadIdx.x;
+
+  const double * col[NC];
+  if (DIM == 3) {
+    col[0] = P.x; col[1] = P.y; col[2] = P.z; col[3] = P.vx; col[4] = P.vy; col[5] = P.vz;
+    col[6] = P.mass; col[7] = P.volume;
+  }
+  else {
+    col[0] = P.x; col[1] = P.y; col[2] = P.vx; col[3] = P.vy; col[4] = P.mass; col[5] = P.volume;
+  }
+
+  uint64_t policy = 0;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++)
+      pipe::mbar_init (&full[s], 1);
+    pipe::fence_async_shared ();
+    policy = pipe::policy_evict_first ();
+  }
+  __syncthreads ();
+
+  auto issue = [&] (int s, int tile) {
+    pipe::mbar_expect_tx (&full[s], NC*COL_BYTES);
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+      pipe::bulk_g2s (&buf[s][c][0], col[c] + (int64_t) tile*PIPE_TILE, COL_BYTES, &full[s], policy);
+  };
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) {
+      const int tile = blockIdx.x + s*gridDim.x;
+      if (tile < n_tiles)
+	issue (s, tile);
+    }
+  }
+
+  int s = 0;
+  unsigned parity = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    pipe::mbar_wait (&full[s], parity);
+    double x, y, z = 0., vx, vy, vz = 0., mass, volume;
+    if (DIM == 3) {
+      x = buf[s][0][tid]; y = buf[s][1][tid]; z = buf[s][2][tid];
+      vx = buf[s][3][tid]; vy = buf[s][4][tid]; vz = buf[s][5][tid];
+      mass = buf[s][6][tid]; volume = buf[s][7][tid];
+    }
+    else {
+      x = buf[s][0][tid]; y = buf[s][1][tid]; vx = buf[s][2][tid]; vy = buf[s][3][tid];
+      mass = buf[s][4][tid]; volume = buf[s][5][tid];
+    }
+    /* The stage is released as soon as every thread holds its particle in
+       registers, so the warps of a CTA run the long compute part unsynchronised
+       (a barrier at the END of the tile, tried with a one-tile lookahead that
+       located and prefetched the next tile's table lines, was 30 % slower:
+       profiles/README.md). */
+    __syncthreads ();
+    if (tid == 0) {
+      const int next = tile + STAGES*gridDim.x;
+      if (next < n_tiles) {
+	pipe::fence_async_shared ();       /* generic-proxy reads before async-proxy writes */
+	issue (s, next);
+      }
+    }
+    if (++s == STAGES) { s = 0; parity ^= 1; }
+
+    const int64_t i = (int64_t) tile*PIPE_TILE + tid;
+    if (i < P.n) {
+      const Located L = locate<DIM, LATTICE> (T, x, y, z);
+      if (L.cell >= 0) {
+	double Fx, Fy, Fz, rho;
+	total_force<DIM, false, LATTICE, PROG> (T, fld, S, L, x, y, z, vx, vy, vz, mass, volume,
+					       Fx, Fy, Fz, rho);
+	const double hdt = 0.5*S.dt, dtm = S.dt*__drcp_rn (mass);
+	x = fma (vx, hdt, x); vx = fma (Fx, dtm, vx); x = fma (vx, hdt, x);
+	y = fma (vy, hdt, y); vy = fma (Fy, dtm, vy); y = fma (vy, hdt, y);
+	__stcs (P.x + i, x); __stcs (P.y + i, y); __stcs (P.vx + i, vx); __stcs (P.vy + i, vy);
+	if (DIM == 3) {
+	  z = fma (vz, hdt, z); vz = fma (Fz, dtm, vz); z = fma (vz, hdt, z);
+	  __stcs (P.z + i, z); __stcs (P.vz + i, vz);
+	}
+      }
+    }
   }
 }
 
@@ -611,22 +843,64 @@ inline unsigned grid_for (int64_t n, int threads) { return (unsigned) ((n + thre
 /* ------------------------------------------------------------------ */
 /* launchers (C linkage, called from capi.cu)                           */
 
+template <int DIM, bool LA, unsigned PR, int ST>
+static void launch_pipe (const DevTree * T, const DevField * F, const DevParticles * P,
+			 const DevStep * S, int n_sm, cudaStream_t st)
+{
+  const int n_tiles = (int) ((P->n + PIPE_TILE - 1)/PIPE_TILE);
+  const size_t smem = (size_t) ST*(DIM == 3 ? 8 : 6)*PIPE_TILE*sizeof (double);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute (step_kernel_pipe<DIM, LA, PR, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			  (int) smem);
+    configured = true;
+  }
+  int grid = n_sm*3;                    /* persistent: 3 CTAs of 256 threads per SM */
+  if (grid > n_tiles) grid = n_tiles;
+  step_kernel_pipe<DIM, LA, PR, ST><<<grid, PIPE_TILE, smem, st>>> (*T, *F, *P, *S, n_tiles);
+}
+
 extern "C" {
 
+/* mode: 0 plain kernel, 2/3 = TMA-staged persistent kernel with that many stages */
 void gfsb200_launch_step (const DevTree * T, const DevField * F, const DevParticles * P,
-			  const DevStep * S, int rec, int minb, cudaStream_t st)
+			  const DevStep * S, int rec, int minb, int mode, int n_sm, cudaStream_t st)
 {
   if (P->n <= 0) return;
   const int th = 256;
   const unsigned g = grid_for (P->n, th);
   const bool lat = T->lattice_n1 > 0;
-#define LAUNCH(D, R, LA, MB) step_kernel<D, R, LA, MB><<<g, th, 0, st>>> (*T, *F, *P, *S)
-#define PICK_MB(D, R, LA) do { if (minb <= 2) LAUNCH (D, R, LA, 2); else if (minb == 3) LAUNCH (D, R, LA, 3); \
-			       else LAUNCH (D, R, LA, 4); } while (0)
-#define PICK(D) do { if (rec) { if (lat) PICK_MB (D, true, true); else PICK_MB (D, true, false); } \
-		     else     { if (lat) PICK_MB (D, false, true); else PICK_MB (D, false, false); } } while (0)
+  /* force lists with a compile-time specialisation (drag / lift / buoyancy = 1 / 2 / 3) */
+  unsigned prog = 0;
+  switch (S->forces) {
+  case 0x1: case 0x21: case 0x321: case 0x31: case 0x3:
+    prog = S->forces;
+  }
+  if (rec || (S->cd_const == S->cd_const)) prog = 0;
+  if (!rec && mode >= 2 && P->n >= 4*PIPE_TILE) {
+#define PIPE_ST(D, LA, PR) do { if (mode == 2) launch_pipe<D, LA, PR, 2> (T, F, P, S, n_sm, st); \
+				else launch_pipe<D, LA, PR, 3> (T, F, P, S, n_sm, st); } while (0)
+#define PIPE_PR(D, LA) do { switch (prog) { \
+    case 0x1: PIPE_ST (D, LA, 0x1); break; case 0x21: PIPE_ST (D, LA, 0x21); break; \
+    case 0x321: PIPE_ST (D, LA, 0x321); break; case 0x31: PIPE_ST (D, LA, 0x31); break; \
+    case 0x3: PIPE_ST (D, LA, 0x3); break; default: PIPE_ST (D, LA, 0); } } while (0)
+    if (T->dim == 3) { if (lat) PIPE_PR (3, true); else PIPE_PR (3, false); }
+    else             { if (lat) PIPE_PR (2, true); else PIPE_PR (2, false); }
+#undef PIPE_PR
+#undef PIPE_ST
+    return;
+  }
+#define LAUNCH(D, R, LA, PR, MB) step_kernel<D, R, LA, PR, MB><<<g, th, 0, st>>> (*T, *F, *P, *S)
+#define PICK_MB(D, LA, PR) do { if (minb <= 3) LAUNCH (D, false, LA, PR, 3); else LAUNCH (D, false, LA, PR, 4); } while (0)
+#define PICK_PR(D, LA) do { switch (prog) { \
+    case 0x1: PICK_MB (D, LA, 0x1); break; case 0x21: PICK_MB (D, LA, 0x21); break; \
+    case 0x321: PICK_MB (D, LA, 0x321); break; case 0x31: PICK_MB (D, LA, 0x31); break; \
+    case 0x3: PICK_MB (D, LA, 0x3); break; default: PICK_MB (D, LA, 0); } } while (0)
+#define PICK(D) do { if (rec) { if (lat) LAUNCH (D, true, true, 0, 3); else LAUNCH (D, true, false, 0, 3); } \
+		     else     { if (lat) PICK_PR (D, true); else PICK_PR (D, false); } } while (0)
   if (T->dim == 3) PICK (3); else PICK (2);
 #undef PICK
+#undef PICK_PR
 #undef PICK_MB
 #undef LAUNCH
 }

@@ -387,3 +387,27 @@ def test_full_size_c2_properties(ctx):
     assert np.array_equal(got["cell"][sel], ocells)
     sub_got = {k: got[k][sel] for k in STATE}
     _check_state(sub_got, want, 3)
+
+
+@pytest.mark.parametrize("mode", ["0", "2", "3"])
+@pytest.mark.parametrize("kind", ["c1", "uniform3", "ring3", "ring2"])
+def test_step_fast_paths(kind, mode, monkeypatch):
+    """The production launch (no cell/force recording): compile-time force
+    lists, lattice addressing on uniform trees, and the TMA-staged persistent
+    kernel (GFSB200_STEP_MODE 2/3 = stages) must all match the oracle."""
+    monkeypatch.setenv("GFSB200_STEP_MODE", mode)
+    c = capi.Context(0)
+    try:
+        w, sim, ptrs, idx = setup(kind, c)
+        n = 20011                                   # not a multiple of the 256-particle tile
+        parts = worlds.make_particles(w, n)
+        c.particles_upload(**parts)
+        for forces in (w.forces, (capi.FORCE_DRAG, capi.FORCE_BUOY), (capi.FORCE_LIFT,)):
+            w2 = worlds.World(**{**w.__dict__, "forces": forces})
+            c.particles_upload(**parts)
+            c.step(w2.step_params())
+            got = c.particles_download()
+            cells, want = helpers.oracle_step(sim, ptrs, w2, parts)
+            _check_state(got, want, w.dim)
+    finally:
+        c.close()
