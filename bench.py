@@ -239,11 +239,8 @@ def run_b200(args):
     par = world.step_params()
     dep_tensor = None
     if args.two_way and world_size > 1:
-        ptr, count = ctx.deposit_buffer()
-        # alias the C-ABI's deposit buffer as a tensor for the NCCL all-reduce
-        class _Alias:
-            __cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3}
-        dep_tensor = torch.as_tensor(_Alias(), device=f"cuda:{local_rank}")
+        # the C-ABI's deposit buffer, aliased (no copy) as a tensor for the NCCL all-reduce
+        dep_tensor = pkg.multigpu.deposit_tensor(ctx, local_rank)
 
     launches_per_step = 3 + (2 if args.two_way else 0)        # vertex + vorticity + step (+ 2 deposit)
 
@@ -254,8 +251,7 @@ def run_b200(args):
             ctx.deposit_volume()
             ctx.deposit_force(par)
             if dep_tensor is not None:
-                with torch.cuda.stream(stream):
-                    dist.all_reduce(dep_tensor)
+                pkg.multigpu.allreduce_deposit(ctx, dep_tensor)
         if args.resort and (i + 1) % args.resort == 0:
             ctx.sort()
 

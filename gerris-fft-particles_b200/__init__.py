@@ -7,6 +7,7 @@ Python modules here are the ctypes harness used by tests/ and bench.py:
 
   capi    ctypes binding of include/gfsb200.h (no compute, no fallback)
   worlds  synthetic trees / fields / particle clouds of the BASELINE configs
+  multigpu  particle sharding + the two-way all-reduce (torch.distributed plumbing)
 
 The directory name carries hyphens, so import it through
 __graft_entry__.load_package(), which registers it as
@@ -14,5 +15,6 @@ __graft_entry__.load_package(), which registers it as
 """
 from . import capi  # noqa: F401
 from . import worlds  # noqa: F401
+from . import multigpu  # noqa: F401
 
-__all__ = ["capi", "worlds"]
+__all__ = ["capi", "worlds", "multigpu"]

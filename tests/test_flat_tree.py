@@ -1,0 +1,151 @@
+"""CPU tests of the host side of the product: the flat FTT tree (native
+builders, 2:1 and corner balancing, ghost trees, level ordering), the FttCell
+bridge, and the corner-stencil table -- all against the reference's own ftt.c /
+fluid.c object code (the oracle)."""
+import numpy as np
+import pytest
+
+import helpers
+from helpers import capi, worlds, ora
+
+KEYS = ("parent", "child0", "neighbor", "level", "flags", "pos")
+
+
+def build_pair(dim, minl, maxl, sides, R=0.25):
+    t = capi.Tree(dim)
+    t.refine_ring(minl, maxl, R, 1.5)
+    t.corner_sweep()
+    for s in sides:
+        t.add_boundary(s)
+    t.finalize()
+    sim = ora.Sim(dim)
+    for s in sides:
+        sim.add_boundary(s)
+    sim.refine_ring(minl, maxl, R, 1.5)
+    sim.corner_sweep()
+    sim.finalize()
+    return t, sim
+
+
+@pytest.mark.parametrize("dim,minl,maxl,sides", [
+    (2, 3, 7, ()), (2, 2, 6, (0, 1, 2, 3)), (2, 4, 4, (0, 3)),
+    (3, 3, 6, ()), (3, 2, 5, (0, 1, 2, 3, 4, 5)), (3, 4, 4, (4,)),
+])
+def test_native_builder_equals_flattened_reference_tree(dim, minl, maxl, sides):
+    """same refinement criterion through ftt_cell_refine + ftt_refine_corner +
+    boundary_match (reference) and through the native builders: identical
+    arrays, cell for cell"""
+    t, sim = build_pair(dim, minl, maxl, sides)
+    a = t.view()
+    roots, is_box = sim.roots()
+    t2, fmap = capi.flatten_ftt(dim, roots, is_box)
+    b = t2.view()
+    assert a.n_cells == b.n_cells == len(fmap.cells)
+    for k in KEYS:
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert np.array_equal(a.la_min, b.la_min) and np.array_equal(a.la_n, b.la_n)
+    assert np.array_equal(a.la_slot, b.la_slot) and a.complete_level == b.complete_level
+    assert sim.count() == int(((a.flags & capi.CELL_BOUNDARY) == 0).sum())
+
+
+@pytest.mark.parametrize("dim,minl,maxl,sides", [(2, 2, 6, (0, 1, 2, 3)), (3, 2, 5, (0, 2, 5)), (3, 3, 6, ())])
+def test_neighbors_match_ftt_cell_neighbor(dim, minl, maxl, sides):
+    t, sim = build_pair(dim, minl, maxl, sides)
+    roots, is_box = sim.roots()
+    t2, fmap = capi.flatten_ftt(dim, roots, is_box)
+    a = t2.view()
+    idx = helpers.PtrIndex(fmap.cells)
+    L = sim.L
+    live = np.nonzero((a.flags & capi.CELL_DESTROYED) == 0)[0]
+    for d in range(2 * dim):
+        want = idx(np.array([L.ora_neighbor(int(fmap.cells[i]), d) for i in live], dtype=np.uint64))
+        assert np.array_equal(a.neighbor[live, d], want), d
+
+
+@pytest.mark.parametrize("dim,minl,maxl,sides", [(2, 2, 6, (0, 1, 2, 3)), (3, 2, 5, (0, 1, 2, 3, 4, 5)), (3, 3, 6, ())])
+def test_corner_stencils_bit_exact(dim, minl, maxl, sides):
+    """every (leaf, corner) interpolator equals gfs_cell_corner_interpolator:
+    same cells, same order, same weights to the last bit -- including
+    T-junctions and the domain-corner rule"""
+    t, sim = build_pair(dim, minl, maxl, sides)
+    roots, is_box = sim.roots()
+    t2, fmap = capi.flatten_ftt(dim, roots, is_box)
+    t2.build_stencils()
+    a = t2.view()
+    idx = helpers.PtrIndex(fmap.cells)
+    nmax = 0
+    for i in a.box_leaves:
+        for k in range(2 ** dim):
+            cells, w = t2.corner_interpolator(int(i), k)
+            oc, ow = sim.corner_interpolator(fmap.cells[i], k)
+            assert list(idx(np.array(oc, dtype=np.uint64))) == cells and ow == w, (i, k)
+            nmax = max(nmax, len(cells))
+            # the shared vertex entry holds the same stencil as a set
+            v = a.leaf_vtx[i, k]
+            sl = slice(a.vtx_off[v], a.vtx_off[v + 1])
+            assert sorted(zip(a.vtx_cell[sl], a.vtx_w[sl])) == sorted(zip(cells, w))
+    assert nmax > 2 ** dim or not sides == ()      # T-junction stencils were exercised
+
+
+def test_uniform_tree_is_a_lattice():
+    w = worlds.make_c2(level=4, n_particles=0)
+    a = w.arrays
+    assert a.n_vertices == 17 ** 3 and a.lattice_level == 4 and a.complete_level == 4
+    # row-major lattice numbering: vertex of leaf corner 4 (-,-,-) at column (kx,ky,kz)
+    leaves = a.box_leaves
+    k = np.rint((a.pos[leaves] + 0.5) * 16 - 0.5).astype(int)
+    assert np.array_equal(a.leaf_vtx[leaves, 4], (k[:, 2] * 17 + k[:, 1]) * 17 + k[:, 0])
+    assert np.array_equal(a.leaf_vtx[leaves, 2], ((k[:, 2] + 1) * 17 + k[:, 1] + 1) * 17 + k[:, 0] + 1)
+    ring = worlds.make_ring("r", 3, 5, 0, 1)
+    assert ring.arrays.lattice_level == -1 and ring.arrays.complete_level == 3
+
+
+def test_level_order_and_morton_keys():
+    """cells are level-ordered; within a complete level the index is the Morton
+    path (child digits: bit0 = +x, bit1 = -y, bit2 = -z)"""
+    w = worlds.make_c2(level=3, n_particles=0)
+    a = w.arrays
+    assert np.all(np.diff(a.level.astype(int)) >= 0)
+    for l in range(1, 4):
+        s = a.level_start[l]
+        n = 8 ** l
+        pos = a.pos[s:s + n]
+        k = np.rint((pos + 0.5) * 2 ** l - 0.5).astype(int)
+        key = np.zeros(n, dtype=int)
+        for b in range(l):
+            key |= ((k[:, 0] >> b) & 1) << (3 * b)
+            key |= (1 - ((k[:, 1] >> b) & 1)) << (3 * b + 1)
+            key |= (1 - ((k[:, 2] >> b) & 1)) << (3 * b + 2)
+        assert np.array_equal(key, np.arange(n))
+
+
+def test_gather_scatter_through_the_bridge():
+    t, sim = build_pair(3, 2, 4, (0,))
+    roots, is_box = sim.roots()
+    t2, fmap = capi.flatten_ftt(3, roots, is_box)
+    a = t2.view()
+    live = (a.flags & capi.CELL_DESTROYED) == 0
+    vals = np.arange(a.n_cells, dtype=np.float64) * 0.5
+    offset = 6 * 16 + 8            # offsetof (GfsStateVector, place_holder) in 3D
+    fmap.scatter(offset, 2, vals)
+    assert np.array_equal(sim.get_values(2, fmap.cells[live]), vals[live])
+    back = fmap.gather(offset, 2)
+    assert np.array_equal(back[live], vals[live]) and np.all(back[~live] == capi.NODATA)
+
+
+def test_error_paths():
+    t = capi.Tree(3)
+    with pytest.raises(capi.GfsB200Error):
+        t.view()                                   # not finalized
+    t.refine_uniform(1)
+    with pytest.raises(capi.GfsB200Error):
+        t.split(0)                                 # root is not a leaf any more
+    with pytest.raises(capi.GfsB200Error):
+        t.add_root((1, 0, 0))                      # roots after a split
+    t.add_boundary(0)
+    with pytest.raises(capi.GfsB200Error):
+        t.add_boundary(0)                          # side already taken
+    with pytest.raises(capi.GfsB200Error):
+        t.corner_sweep()                           # boundaries must come last
+    with pytest.raises(capi.GfsB200Error):
+        capi.Tree(4)
