@@ -303,10 +303,10 @@ def run_b200(args):
 
     def e2e_step():
         ctx.upload_field(*fields)                     # mirror U,V,W + cell pass
-        ctx.particles_upload(**{k: host.get(k) for k in COLS})
-        ctx.step(par)
-        out = ctx.particles_download()                # x,y,z,vx,vy,vz (+m,V) back on the host
-        return out
+        # host particle arrays in, updated host particle arrays out (in place),
+        # streamed through the device in chunks on three streams
+        ctx.step_host(par, host["x"], host["y"], host.get("z"), host["vx"], host["vy"], host.get("vz"),
+                      host["mass"], host["volume"])
 
     e2e_step()
     barrier()
@@ -343,8 +343,9 @@ def run_b200(args):
                          "kernel_ms": kernel_ms, "kernel_launches": kernel_launches},
             "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                    "what": "gfsb200_upload_field + gfsb200_particles_upload (pinned host) + gfsb200_step + "
-                            "gfsb200_particles_download per step"},
+                    "what": "per step: gfsb200_upload_field (U,V,W from pinned host memory, cell pass) + "
+                            "gfsb200_step_host (8 particle columns H2D, fused step, 6 columns D2H, chunked "
+                            "on three streams); wall clock"},
             "gpu_launches": args.steps * launches_per_step + n_sorts * 8,
             "clocks": clocks,
         }

@@ -103,6 +103,7 @@ def lib() -> C.CDLL:
         "gfsb200_step_params_default": (None, [C.POINTER(StepParamsC)]),
         "gfsb200_step": (i32, [vp, C.POINTER(StepParamsC)]),
         "gfsb200_particle_list_event": (i32, [vp, C.POINTER(StepParamsC), C.POINTER(i64)]),
+        "gfsb200_step_host": (i32, [vp, C.POINTER(StepParamsC), i64] + [vp] * 8 + [i64]),
         "gfsb200_particles_cull": (i32, [vp, C.POINTER(i64)]),
         "gfsb200_particles_sort": (i32, [vp]),
         "gfsb200_locate": (i32, [vp, i64, vp, vp, vp, vp]),
@@ -379,6 +380,16 @@ class Context:
 
     def step(self, params: StepParams):
         _check(self._lib.gfsb200_step(self.handle, C.byref(params.c)), "step")
+
+    def step_host(self, params: StepParams, x, y, z, vx, vy, vz, mass, volume, chunk: int = 0):
+        """in-place step of host-resident float64 arrays (no copies are made here:
+        the arrays must already be contiguous float64)"""
+        arrs = [x, y, z, vx, vy, vz, mass, volume]
+        for a in arrs:
+            if a is not None and (a.dtype != np.float64 or not a.flags.c_contiguous):
+                raise GfsB200Error("step_host needs contiguous float64 arrays")
+        _check(self._lib.gfsb200_step_host(self.handle, C.byref(params.c), len(x),
+                                           *[_ptr(a) for a in arrs], chunk), "step_host")
 
     def particle_list_event(self, params: StepParams) -> int:
         removed = C.c_int64(0)

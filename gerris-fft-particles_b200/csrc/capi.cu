@@ -81,6 +81,11 @@ struct gfsb200_ctx {
   void * cub_tmp;
   size_t cub_tmp_bytes;
   double ** d_ptr_table;       /* [2][NCOL] device copy of col pointers */
+  /* host-list pipeline (gfsb200_step_host) */
+  double * hp_col[3][NCOL];
+  int64_t hp_chunk;
+  cudaStream_t hp_h2d, hp_d2h;
+  cudaEvent_t hp_in[3], hp_done[3], hp_out[3];
   /* deposit */
   double * deposit;
   int64_t deposit_count;
@@ -167,6 +172,8 @@ extern "C" int gfsb200_ctx_create (int device, gfsb200_ctx ** out)
   c->cell = c->perm = c->perm2 = NULL; c->key = c->key2 = NULL; c->flag = NULL;
   c->d_count = NULL; c->cub_tmp = NULL; c->cub_tmp_bytes = 0; c->d_ptr_table = NULL;
   c->deposit = NULL; c->deposit_count = 0;
+  memset (c->hp_col, 0, sizeof c->hp_col);
+  c->hp_chunk = 0; c->hp_h2d = c->hp_d2h = NULL;
   c->ev_used = 0; c->timing = true;
   c->step_minb = getenv ("GFSB200_STEP_MINB") ? atoi (getenv ("GFSB200_STEP_MINB")) : 3;
   c->step_mode = getenv ("GFSB200_STEP_MODE") ? atoi (getenv ("GFSB200_STEP_MODE")) : 2;
@@ -187,6 +194,14 @@ extern "C" void gfsb200_ctx_destroy (gfsb200_ctx * c)
   cudaStreamSynchronize (c->stream);
   free_tree (c);
   free_particles (c);
+  for (int s = 0; s < 3; s++)
+    for (int k = 0; k < NCOL; k++) cudaFree (c->hp_col[s][k]);
+  if (c->hp_h2d) {
+    cudaStreamDestroy (c->hp_h2d); cudaStreamDestroy (c->hp_d2h);
+    for (int s = 0; s < 3; s++) {
+      cudaEventDestroy (c->hp_in[s]); cudaEventDestroy (c->hp_done[s]); cudaEventDestroy (c->hp_out[s]);
+    }
+  }
   cudaFree (c->d_count); cudaFree (c->d_ptr_table);
   for (size_t i = 0; i < c->ev.size (); i++) cudaEventDestroy (c->ev[i]);
   cudaStreamDestroy (c->stream);
@@ -600,6 +615,95 @@ extern "C" int gfsb200_step (gfsb200_ctx * c, const gfsb200_step_params * p)
 			 c->step_mode, c->n_sm, c->stream);
   if ((r = timed_end (c))) return r;
   CK (cudaGetLastError ());
+  return GFSB200_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* host-resident particle lists: chunked, triple-buffered H2D -> step -> D2H */
+
+#define HOST_SLOTS 3
+
+static int ensure_host_pipeline (gfsb200_ctx * c, int64_t chunk)
+{
+  const int64_t alloc = (chunk + 255)/256*256;
+  if (c->hp_chunk >= alloc) return GFSB200_OK;
+  for (int s = 0; s < HOST_SLOTS; s++)
+    for (int k = 0; k < NCOL; k++) {
+      cudaFree (c->hp_col[s][k]);
+      c->hp_col[s][k] = NULL;
+    }
+  c->hp_chunk = 0;
+  for (int s = 0; s < HOST_SLOTS; s++)
+    for (int k = 0; k < NCOL; k++) {
+      CK (cudaMalloc ((void **) &c->hp_col[s][k], alloc*sizeof (double)));
+      CK (cudaMemsetAsync (c->hp_col[s][k], 0, alloc*sizeof (double), c->stream));
+    }
+  if (!c->hp_h2d) {
+    CK (cudaStreamCreateWithFlags (&c->hp_h2d, cudaStreamNonBlocking));
+    CK (cudaStreamCreateWithFlags (&c->hp_d2h, cudaStreamNonBlocking));
+    for (int s = 0; s < HOST_SLOTS; s++) {
+      CK (cudaEventCreateWithFlags (&c->hp_in[s], cudaEventDisableTiming));
+      CK (cudaEventCreateWithFlags (&c->hp_done[s], cudaEventDisableTiming));
+      CK (cudaEventCreateWithFlags (&c->hp_out[s], cudaEventDisableTiming));
+    }
+  }
+  CK (cudaStreamSynchronize (c->stream));
+  c->hp_chunk = alloc;
+  return GFSB200_OK;
+}
+
+extern "C" int gfsb200_step_host (gfsb200_ctx * c, const gfsb200_step_params * p, int64_t n,
+				  double * x, double * y, double * z,
+				  double * vx, double * vy, double * vz,
+				  const double * mass, const double * volume, int64_t chunk)
+{
+  if (!c || !c->have_field)
+    return gfsb200_fail (GFSB200_ERR_STATE, "step_host: tree and field must be resident");
+  if (n < 0 || (n && (!x || !y || !vx || !vy || !mass || !volume || (c->T.dim == 3 && (!z || !vz)))))
+    return gfsb200_fail (GFSB200_ERR_ARG, "step_host: bad argument");
+  DevStep S;
+  int r = make_step (p, &S);
+  if (r) return r;
+  if (S.n_forces == 0)
+    return gfsb200_fail (GFSB200_ERR_UNSUPPORTED, "step_host: tracer lists go through gfsb200_step");
+  if (n == 0) return GFSB200_OK;
+  CK (cudaSetDevice (c->device));
+  if (chunk <= 0) chunk = 1 << 20;
+  if (chunk > n) chunk = n;
+  if ((r = ensure_host_pipeline (c, chunk))) return r;
+
+  const bool d3 = c->T.dim == 3;
+  const double * in[NCOL] = { x, y, z, vx, vy, vz, mass, volume };
+  double * out[6] = { x, y, z, vx, vy, vz };
+  const int64_t n_chunks = (n + chunk - 1)/chunk;
+  for (int64_t k = 0; k < n_chunks; k++) {
+    const int s = (int) (k % HOST_SLOTS);
+    const int64_t lo = k*chunk, m = (lo + chunk <= n ? chunk : n - lo);
+    /* slot s is free once the D2H of chunk k - HOST_SLOTS has drained */
+    if (k >= HOST_SLOTS)
+      CK (cudaStreamWaitEvent (c->hp_h2d, c->hp_out[s], 0));
+    for (int q = 0; q < NCOL; q++)
+      if (in[q] && (d3 || (q != 2 && q != 5)))
+	CK (cudaMemcpyAsync (c->hp_col[s][q], in[q] + lo, m*sizeof (double), cudaMemcpyHostToDevice, c->hp_h2d));
+    CK (cudaEventRecord (c->hp_in[s], c->hp_h2d));
+    CK (cudaStreamWaitEvent (c->stream, c->hp_in[s], 0));
+    DevParticles P;
+    memset (&P, 0, sizeof P);
+    P.n = m;
+    P.x = c->hp_col[s][0]; P.y = c->hp_col[s][1]; P.z = c->hp_col[s][2];
+    P.vx = c->hp_col[s][3]; P.vy = c->hp_col[s][4]; P.vz = c->hp_col[s][5];
+    P.mass = c->hp_col[s][6]; P.volume = c->hp_col[s][7];
+    gfsb200_launch_step (&c->T, &c->F, &P, &S, 0, c->step_minb, c->step_mode, c->n_sm, c->stream);
+    CK (cudaGetLastError ());
+    CK (cudaEventRecord (c->hp_done[s], c->stream));
+    CK (cudaStreamWaitEvent (c->hp_d2h, c->hp_done[s], 0));
+    for (int q = 0; q < 6; q++)
+      if (out[q] && (d3 || (q != 2 && q != 5)))
+	CK (cudaMemcpyAsync (out[q] + lo, c->hp_col[s][q], m*sizeof (double), cudaMemcpyDeviceToHost, c->hp_d2h));
+    CK (cudaEventRecord (c->hp_out[s], c->hp_d2h));
+  }
+  CK (cudaStreamSynchronize (c->hp_d2h));
+  CK (cudaStreamSynchronize (c->stream));
   return GFSB200_OK;
 }
 

@@ -1,0 +1,371 @@
+/* particulates_b200.c -- drop-in `particulates` GModule for gerris2D / gerris3D
+ * whose per-step particle work runs on a B200 through the C-ABI of
+ * include/gfsb200.h.
+ *
+ * Build (on a machine that has Gerris' development files; GLib/GTS are absent
+ * from the image this repository is developed in, so this file is
+ * compile-unverified there -- see INTEGRATION.md):
+ *
+ *   gcc -shared -fPIC [-DFTT_2D=1] `pkg-config --cflags gerris3D` \
+ *       particulates_b200.c $(GERRIS)/modules/particulatecommon.c ftt_bridge.c \
+ *       -L$PREFIX/lib -lgfsb200 `pkg-config --libs gerris3D` \
+ *       -o libparticulates3D.so
+ *
+ * Design: the reference's modules/particulatecommon.c is linked UNCHANGED and
+ * keeps every GtsObject class, the .gfs syntax, read/write methods and the
+ * rare host-side machinery (droplet conversion, feeding, output, particle
+ * BCs).  This file only replaces, in the class vtables, the three event
+ * methods that make up the hot path:
+ *
+ *   GfsParticleList.event     gfs_particle_list_event    modules/particulatecommon.c:980-1015
+ *   GfsParticulateField.event particulate_field_event    modules/particulatecommon.c:1934-1957
+ *
+ * and exports the same module symbols as modules/particulates.c:24-49.
+ * A list that carries a force the device does not implement (GfsForceInertial,
+ * GfsForceAddedMass, non-constant coefficient functions), or a domain with
+ * solid boundaries, is handed back to the reference's own event untouched.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <stddef.h>
+#include <gfs.h>
+#include "particulatecommon.h"
+#include "gfsb200.h"
+#include "gfsb200_ftt.h"
+
+/* ------------------------------------------------------------------ */
+/* per-list device state, hung on the GtsObject through g_object data  */
+
+typedef struct {
+  gfsb200_ctx * ctx;
+  gfsb200_tree * tree;
+  gfsb200_ftt_map * map;
+  guint adapt_created, adapt_removed;   /* mesh-change signature, src/simulation.h:49-51 */
+  gboolean tree_valid;
+  gdouble * field[3];                   /* host staging of U,V,W in flat order */
+  gint32 n_cells;
+  gboolean (* reference_event) (GfsEvent *, GfsSimulation *);
+} B200State;
+
+static GHashTable * b200_states = NULL;   /* GfsParticleList* -> B200State* */
+static gboolean (* reference_list_event) (GfsEvent *, GfsSimulation *) = NULL;
+static gboolean (* reference_field_event) (GfsEvent *, GfsSimulation *) = NULL;
+
+static B200State * state_of (GfsParticleList * plist)
+{
+  B200State * s;
+  if (!b200_states)
+    b200_states = g_hash_table_new (NULL, NULL);
+  s = g_hash_table_lookup (b200_states, plist);
+  if (!s) {
+    int device = 0;
+    const gchar * env = g_getenv ("GFSB200_DEVICE");
+    s = g_malloc0 (sizeof (B200State));
+    if (env) device = atoi (env);
+#ifdef HAVE_MPI
+    else device = GFS_DOMAIN (gfs_object_simulation (plist))->pid;   /* one rank per GPU */
+#endif
+    if (gfsb200_ctx_create (device, &s->ctx) != GFSB200_OK)
+      g_error ("particulates (B200): %s", gfsb200_last_error ());   /* no CPU fallback */
+    g_hash_table_insert (b200_states, plist, s);
+  }
+  return s;
+}
+
+/* ------------------------------------------------------------------ */
+/* mesh: flatten after every adapt                                      */
+
+typedef struct { GPtrArray * roots; GArray * is_box; } RootList;
+
+static void collect_roots (GfsBox * box, RootList * r)
+{
+  FttDirection d;
+  gint one = 1, zero = 0;
+  g_ptr_array_add (r->roots, box->root);
+  g_array_append_val (r->is_box, one);
+  for (d = 0; d < FTT_NEIGHBORS; d++)
+    if (GFS_IS_BOUNDARY (box->neighbor[d]) && GFS_BOUNDARY (box->neighbor[d])->root) {
+      g_ptr_array_add (r->roots, GFS_BOUNDARY (box->neighbor[d])->root);
+      g_array_append_val (r->is_box, zero);
+    }
+}
+
+static void refresh_tree (B200State * s, GfsSimulation * sim)
+{
+  GfsDomain * domain = GFS_DOMAIN (sim);
+  if (s->tree_valid &&
+      s->adapt_created == sim->adapts_stats.created &&
+      s->adapt_removed == sim->adapts_stats.removed)
+    return;
+  RootList r = { g_ptr_array_new (), g_array_new (FALSE, FALSE, sizeof (gint)) };
+  FttComponent c;
+  gts_container_foreach (GTS_CONTAINER (domain), (GtsFunc) collect_roots, &r);
+  if (s->map) gfsb200_ftt_map_free (s->map);
+  if (s->tree) gfsb200_tree_free (s->tree);
+  if (gfsb200_ftt_flatten (r.roots->len, (void * const *) r.roots->pdata, (const int *) r.is_box->data,
+			   &s->tree, &s->map) != GFSB200_OK)
+    g_error ("particulates (B200): %s", gfsb200_ftt_last_error ());
+  g_ptr_array_free (r.roots, TRUE);
+  g_array_free (r.is_box, TRUE);
+  if (gfsb200_tree_build_stencils (s->tree) != GFSB200_OK ||
+      gfsb200_upload_tree (s->ctx, s->tree) != GFSB200_OK)
+    g_error ("particulates (B200): %s", gfsb200_last_error ());
+  s->n_cells = gfsb200_ftt_map_size (s->map);
+  for (c = 0; c < FTT_DIMENSION; c++)
+    s->field[c] = g_realloc (s->field[c], sizeof (gdouble)*s->n_cells);
+  s->adapt_created = sim->adapts_stats.created;
+  s->adapt_removed = sim->adapts_stats.removed;
+  s->tree_valid = TRUE;
+}
+
+/* U,V,W of time t^n, ghost cells included (gfs_domain_bc has been applied by
+ * the solver before events run, src/simulation.c:483) */
+static void mirror_velocity (B200State * s, GfsDomain * domain)
+{
+  GfsVariable ** u = gfs_domain_velocity (domain);
+  FttComponent c;
+  for (c = 0; c < FTT_DIMENSION; c++)
+    gfsb200_ftt_gather (s->map, offsetof (GfsStateVector, place_holder), u[c]->i, GFS_NODATA, s->field[c]);
+  if (gfsb200_upload_field (s->ctx, s->field[0], s->field[1], FTT_DIMENSION > 2 ? s->field[2] : NULL,
+			    NULL, NULL) != GFSB200_OK)
+    g_error ("particulates (B200): %s", gfsb200_last_error ());
+}
+
+/* ------------------------------------------------------------------ */
+/* parameters: which forces, rho, mu, g                                 */
+
+static GfsSourceDiffusion * viscosity_source (GfsVariable * v)
+{
+  GSList * i = v->sources ? GTS_SLIST_CONTAINER (v->sources)->items : NULL;
+  while (i) {
+    if (GFS_IS_SOURCE_DIFFUSION (i->data))
+      return GFS_SOURCE_DIFFUSION (i->data);
+    i = i->next;
+  }
+  return NULL;
+}
+
+/* fills *p; returns FALSE if the list needs something only the reference
+ * CPU path implements */
+static gboolean step_params (GfsParticleList * plist, GfsSimulation * sim, gfsb200_step_params * p)
+{
+  GfsDomain * domain = GFS_DOMAIN (sim);
+  GfsVariable ** u = gfs_domain_velocity (domain);
+  GSList * i = plist->forces ? plist->forces->items : NULL;
+  FttComponent c;
+
+  gfsb200_step_params_default (p);
+  p->dt = sim->advection_params.dt;
+  while (i) {
+    GfsForceCoeff * coeff = GFS_IS_FORCE_COEFF (i->data) ? FORCE_COEFF (i->data) : NULL;
+    gdouble k = coeff && coeff->coefficient ? gfs_function_get_constant_value (coeff->coefficient) : 0.;
+    if (p->n_forces == GFSB200_MAX_FORCES || k == G_MAXDOUBLE)
+      return FALSE;
+    if (GFS_IS_FORCE_DRAG (i->data)) {
+      p->force[p->n_forces++] = GFSB200_FORCE_DRAG;
+      if (coeff->coefficient) p->cd_const = k;
+    }
+    else if (GFS_IS_FORCE_LIFT (i->data)) {
+      p->force[p->n_forces++] = GFSB200_FORCE_LIFT;
+      if (coeff->coefficient) p->cl_const = k;
+    }
+    else if (GFS_IS_FORCE_BUOY (i->data))
+      p->force[p->n_forces++] = GFSB200_FORCE_BUOY;
+    else
+      return FALSE;                       /* GfsForceInertial, GfsForceAddedMass, user forces */
+    i = i->next;
+  }
+  /* fluid density 1/alpha (particulatecommon.c:534-535) */
+  if (sim->physical_params.alpha) {
+    gdouble a = gfs_function_get_constant_value (sim->physical_params.alpha);
+    if (a == G_MAXDOUBLE)
+      return FALSE;                       /* variable density: per-cell alpha array, not wired yet */
+    p->rho = 1./a;
+  }
+  /* viscosity of the GfsSourceDiffusion on U (particulatecommon.c:540-541) */
+  {
+    GfsSourceDiffusion * d = viscosity_source (u[0]);
+    if (d) {
+      gdouble mu = gfs_function_get_constant_value (d->D->val);
+      if (mu == G_MAXDOUBLE)
+	return FALSE;
+      p->mu = mu;
+    }
+  }
+  /* g = sum of the GfsSource intensities on U,V,W (particulatecommon.c:634-649) */
+  for (c = 0; c < FTT_DIMENSION; c++) {
+    GSList * j = u[c]->sources ? GTS_SLIST_CONTAINER (u[c]->sources)->items : NULL;
+    while (j) {
+      if (GFS_IS_SOURCE (j->data)) {
+	gdouble g = gfs_function_get_constant_value (GFS_SOURCE (j->data)->intensity);
+	if (g == G_MAXDOUBLE)
+	  return FALSE;
+	p->g[c] += g;
+      }
+      j = j->next;
+    }
+  }
+  return TRUE;
+}
+
+/* ------------------------------------------------------------------ */
+/* particle objects <-> device SoA                                      */
+
+static gint64 upload_particles (B200State * s, GfsParticleList * plist)
+{
+  GSList * i = GFS_EVENT_LIST (plist)->list->items;
+  gint64 n = g_slist_length (i), k = 0;
+  gdouble * col[8];
+  guint32 * id = g_malloc (sizeof (guint32)*(n ? n : 1));
+  gint c;
+  for (c = 0; c < 8; c++)
+    col[c] = g_malloc (sizeof (gdouble)*(n ? n : 1));
+  for (; i; i = i->next, k++) {
+    GfsParticle * p = GFS_PARTICLE (i->data);
+    GfsParticulate * q = GFS_PARTICULATE (i->data);
+    p->pos_old = p->pos;                                     /* :804-805 */
+    col[0][k] = p->pos.x; col[1][k] = p->pos.y; col[2][k] = p->pos.z;
+    col[3][k] = q->vel.x; col[4][k] = q->vel.y; col[5][k] = q->vel.z;
+    col[6][k] = q->mass;  col[7][k] = q->volume;
+    id[k] = p->id;
+  }
+  if (gfsb200_particles_upload (s->ctx, n, col[0], col[1], FTT_DIMENSION > 2 ? col[2] : NULL,
+				col[3], col[4], FTT_DIMENSION > 2 ? col[5] : NULL,
+				col[6], col[7], id) != GFSB200_OK)
+    g_error ("particulates (B200): %s", gfsb200_last_error ());
+  for (c = 0; c < 8; c++) g_free (col[c]);
+  g_free (id);
+  return n;
+}
+
+/* write the device state back into the GtsObjects; particles the device
+ * culled (outside the domain) are removed from the list as
+ * remove_particles_not_in_domain does (:955-969) */
+static void download_particles (B200State * s, GfsParticleList * plist)
+{
+  gint64 n = gfsb200_particles_count (s->ctx), k = 0;
+  gdouble * col[9];
+  guint32 * id = g_malloc (sizeof (guint32)*(n ? n : 1));
+  gint c;
+  GSList * i = GFS_EVENT_LIST (plist)->list->items;
+  for (c = 0; c < 9; c++)
+    col[c] = g_malloc (sizeof (gdouble)*(n ? n : 1));
+  if (gfsb200_particles_download (s->ctx, col[0], col[1], FTT_DIMENSION > 2 ? col[2] : NULL,
+				  col[3], col[4], FTT_DIMENSION > 2 ? col[5] : NULL,
+				  col[6], col[7], col[8], NULL, NULL, id, NULL) != GFSB200_OK)
+    g_error ("particulates (B200): %s", gfsb200_last_error ());
+  while (i) {
+    GSList * next = i->next;
+    GfsParticle * p = GFS_PARTICLE (i->data);
+    if (k < n && id[k] == p->id) {
+      GfsParticulate * q = GFS_PARTICULATE (i->data);
+      p->pos.x = col[0][k]; p->pos.y = col[1][k];
+      q->vel.x = col[3][k]; q->vel.y = col[4][k];
+      q->force.x = col[6][k]; q->force.y = col[7][k];
+#if !FTT_2D
+      p->pos.z = col[2][k]; q->vel.z = col[5][k]; q->force.z = col[8][k];
+#endif
+      k++;
+    }
+    else {                                 /* culled on the device: list order is preserved */
+      gts_container_remove (GTS_CONTAINER (GFS_EVENT_LIST (plist)->list), GTS_CONTAINEE (p));
+      gts_object_destroy (GTS_OBJECT (p));
+    }
+    i = next;
+  }
+  for (c = 0; c < 9; c++) g_free (col[c]);
+  g_free (id);
+}
+
+/* ------------------------------------------------------------------ */
+/* the replaced event methods                                           */
+
+static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
+{
+  GfsParticleList * plist = GFS_PARTICLE_LIST (event);
+  gfsb200_step_params par;
+  B200State * s;
+  gint64 removed = 0;
+
+  if (!step_params (plist, sim, &par) || sim->solids->items != NULL)
+    return (* reference_list_event) (event, sim);            /* not expressible on the device */
+
+  /* the timing gate of gfs_event_list_event (src/event.c:2430-2439) */
+  if (!(* GFS_EVENT_CLASS (gfs_event_class ())->event) (event, sim))
+    return FALSE;
+
+  s = state_of (plist);
+  refresh_tree (s, sim);
+  mirror_velocity (s, GFS_DOMAIN (sim));
+  /* Host objects are authoritative between steps in this first binding
+     (FeedParticle, DropletToParticle, outputs and BCs all mutate them); a
+     resident mode that skips the two copies when nothing on the host touched
+     the list is the next step ("host object sync"). */
+  upload_particles (s, plist);
+  par.record_forces = 1;
+  if (gfsb200_particle_list_event (s->ctx, &par, &removed) != GFSB200_OK)
+    g_error ("particulates (B200): %s", gfsb200_last_error ());
+  download_particles (s, plist);
+
+  gfs_particle_bc (plist);                                   /* :993, host side as in the reference */
+  return TRUE;
+}
+
+static gboolean b200_particulate_field_event (GfsEvent * event, GfsSimulation * sim)
+{
+  GfsVariable * v = GFS_VARIABLE (event);
+  GfsParticulateField * pfield = GFS_PARTICULATE_FIELD (v);
+  gfsb200_step_params par;
+  B200State * s;
+  gdouble * out;
+
+  if (!step_params (pfield->plist, sim, &par))
+    return (* reference_field_event) (event, sim);
+  if (!(* GFS_EVENT_CLASS (gfs_variable_class ())->event) (event, sim))
+    return FALSE;
+  s = state_of (pfield->plist);
+  refresh_tree (s, sim);
+  upload_particles (s, pfield->plist);
+  if (gfsb200_deposit_volume (s->ctx) != GFSB200_OK)
+    g_error ("particulates (B200): %s", gfsb200_last_error ());
+  out = g_malloc (sizeof (gdouble)*s->n_cells);
+  gfsb200_download_deposit (s->ctx, 0, out);
+  /* gfs_cell_reset on the leaves + the scatter of :1945-1953 */
+  gfsb200_ftt_scatter (s->map, offsetof (GfsStateVector, place_holder), v->i, TRUE, out);
+  g_free (out);
+  return TRUE;
+}
+
+/* ------------------------------------------------------------------ */
+/* module symbols, as modules/particulates.c:24-49                      */
+
+const gchar gfs_module_name[] = "particulates";
+const gchar * g_module_check_init (void);
+
+const gchar * g_module_check_init (void)
+{
+  /* instantiate the reference classes in the reference's order ... */
+  gfs_particulate_class ();
+  gfs_particle_list_class ();
+  gfs_force_inertial_class ();
+  gfs_force_addedmass_class ();
+  gfs_force_lift_class ();
+  gfs_force_drag_class ();
+  gfs_force_buoy_class ();
+  gfs_particle_force_class ();
+  gfs_source_particulate_class ();
+  gfs_source_particulatevol_class ();
+  gfs_source_particulatemass_class ();
+  gfs_droplet_to_particle_class ();
+  gfs_particle_to_droplet_class ();
+  gfs_feed_particle_class ();
+  gfs_output_particle_list_class ();
+  gfs_particulate_field_class ();
+
+  /* ... then route the hot-path events to the device */
+  reference_list_event = GFS_EVENT_CLASS (gfs_particle_list_class ())->event;
+  GFS_EVENT_CLASS (gfs_particle_list_class ())->event = b200_particle_list_event;
+  reference_field_event = GFS_EVENT_CLASS (gfs_particulate_field_class ())->event;
+  GFS_EVENT_CLASS (gfs_particulate_field_class ())->event = b200_particulate_field_event;
+  return NULL;
+}

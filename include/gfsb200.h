@@ -212,6 +212,18 @@ void gfsb200_step_params_default (gfsb200_step_params * p);
  * gfs_domain_locate is NULL are left untouched (cell = -1). */
 int gfsb200_step (gfsb200_ctx * c, const gfsb200_step_params * p);
 
+/* The same step for a particle list that LIVES ON THE HOST (the GtsObject list
+ * of the reference, gathered into SoA arrays): positions and velocities are
+ * updated in place.  The arrays are streamed through the device in chunks on
+ * three streams (H2D / kernel / D2H overlap), so the cost is that of the
+ * slower PCIe direction, not the sum.  Pin the arrays (cudaHostRegister /
+ * cudaMallocHost) for full bandwidth.  Particles outside the domain are left
+ * untouched.  chunk = 0 picks 2^20 particles. */
+int gfsb200_step_host (gfsb200_ctx * c, const gfsb200_step_params * p, int64_t n,
+		       double * x, double * y, double * z,
+		       double * vx, double * vy, double * vz,
+		       const double * mass, const double * volume, int64_t chunk);
+
 /* gfs_particle_list_event: cull particles outside the domain
  * (remove_particles_not_in_domain), then step.  *n_removed may be NULL. */
 int gfsb200_particle_list_event (gfsb200_ctx * c, const gfsb200_step_params * p,

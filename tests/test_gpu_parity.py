@@ -411,3 +411,17 @@ def test_step_fast_paths(kind, mode, monkeypatch):
             _check_state(got, want, w.dim)
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("kind", ["c1", "ring3", "uniform3"])
+def test_step_host_streams_match_oracle(kind, ctx):
+    """gfsb200_step_host: host arrays in, host arrays out (in place), chunked"""
+    w, sim, ptrs, idx = setup(kind, ctx)
+    n = 30011
+    parts = worlds.make_particles(w, n)
+    host = {k: (None if v is None else np.ascontiguousarray(v).copy()) for k, v in parts.items()}
+    ctx.step_host(w.step_params(), host["x"], host["y"], host["z"], host["vx"], host["vy"], host["vz"],
+                  host["mass"], host["volume"], chunk=4096)
+    cells, want = helpers.oracle_step(sim, ptrs, w, parts)
+    _check_state(host, want, w.dim)
+    assert np.array_equal(host["mass"], parts["mass"]) and np.array_equal(host["volume"], parts["volume"])
