@@ -22,6 +22,10 @@
 
 namespace {
 
+__device__ __forceinline__ bool is_nodata (double v)
+{
+  return __double2hiint (v) == 0x7fefffff && __double2loint (v) == (int) 0xffffffff;
+}
 __device__ __forceinline__ bool is_leaf (const DevTree & T, int c) { return T.child0[c] == CHILD_LEAF; }
 __device__ __forceinline__ int child_id (const DevTree & T, int c) { return T.info[c] >> 4; }
 __device__ __forceinline__ bool child_positive (int n, int axis)
@@ -145,7 +149,7 @@ __device__ double center_gradient (const DevTree & T, const double * __restrict_
 }
 
 template <int DIM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)      /* 32 registers: full occupancy hides the nb -> value chain */
 vorticity_kernel (DevTree T, DevField fld)
 {
   const int stride = gridDim.x*blockDim.x;
@@ -159,7 +163,15 @@ vorticity_kernel (DevTree T, DevField fld)
 	 gfs_center_gradient reduces to ((v2 - v0) + (v0 - v1))/2 -- the same
 	 operations the general path performs with x1 = x2 = 1 */
       const double size = __longlong_as_double ((long long) (1023 - T.level[cell]) << 52);
-      const int * nb = T.neighbor + (int64_t) cell*(2*DIM);
+      int nb[2*DIM];
+      {
+	const int2 * np = reinterpret_cast<const int2 *> (T.neighbor + (int64_t) cell*(2*DIM));
+#pragma unroll
+	for (int d = 0; d < DIM; d++) {
+	  const int2 t = __ldg (np + d);
+	  nb[2*d] = t.x; nb[2*d + 1] = t.y;
+	}
+      }
       const double * __restrict__ U = fld.u[0], * __restrict__ V = fld.u[1];
 #define GRAD(F, c) ((((F)[nb[2*(c)]] - (F)[cell]) + ((F)[cell] - (F)[nb[2*(c) + 1]]))/2.)
       if (DIM == 2)
@@ -220,17 +232,32 @@ vertex_values_kernel (DevTree T, DevField fld)
        vertex): it is stored once per vertex and the per-entry array is skipped */
     const double wu = T.vtx_wuni[v];
     const bool uni = wu == wu;
-    for (int i = b; i < e; i++) {
-      const int c = T.vtx_cell[i];
-      const double w = uni ? wu : T.vtx_w[i];
-      const double v0 = fld.u[0][c], v1 = fld.u[1][c];
-      nodata |= (v0 == GFSB200_NODATA) | (v1 == GFSB200_NODATA);
-      s0 += w*v0;
-      s1 += w*v1;
-      if (DIM == 3) {
-	const double v2 = fld.u[2][c];
-	nodata |= (v2 == GFSB200_NODATA);
-	s2 += w*v2;
+    /* batches of 2^DIM entries: all indices first, then all gathers, then the
+       ordered accumulation -- the loads of a batch are in flight together.
+       Padding entries repeat a valid cell with weight 0 (s + 0*v == s). */
+    constexpr int NB = 1 << DIM;
+    for (int i = b; i < e; i += NB) {
+      int c[NB];
+      double w[NB], a0[NB], a1[NB], a2[NB];
+#pragma unroll
+      for (int j = 0; j < NB; j++) {
+	const bool ok = i + j < e;
+	c[j] = T.vtx_cell[ok ? i + j : i];
+	w[j] = ok ? (uni ? wu : T.vtx_w[i + j]) : 0.;
+      }
+#pragma unroll
+      for (int j = 0; j < NB; j++) {
+	a0[j] = fld.u[0][c[j]];
+	a1[j] = fld.u[1][c[j]];
+	a2[j] = DIM == 3 ? fld.u[2][c[j]] : 0.;
+      }
+#pragma unroll
+      for (int j = 0; j < NB; j++) {
+	/* GFS_NODATA = DBL_MAX: compare the high word on the integer pipe */
+	nodata |= is_nodata (a0[j]) | is_nodata (a1[j]) | (DIM == 3 && is_nodata (a2[j]));
+	s0 += w[j]*a0[j];
+	s1 += w[j]*a1[j];
+	if (DIM == 3) s2 += w[j]*a2[j];
       }
     }
     if (nodata) {
@@ -254,7 +281,7 @@ extern "C" void gfsb200_launch_cell_pass (const DevTree * T, const DevField * fl
 {
   const int threads = 256;
   int gv = (T->n_vertices + threads - 1)/threads, gc = (T->n_cells + threads - 1)/threads;
-  const int cap = n_sm*8;             /* grid-stride: at most 8 CTAs of 256 threads per SM */
+  const int cap = n_sm*16;            /* grid-stride */
   if (gv > cap) gv = cap;
   if (gc > cap) gc = cap;
   if (gv < 1) gv = 1;
