@@ -236,33 +236,40 @@ __device__ __forceinline__ void interpolate (const DevTree & T, const DevField &
       id[0] = i0.x; id[1] = i0.y; id[2] = i0.z; id[3] = i0.w;
       id[4] = i1.x; id[5] = i1.y; id[6] = i1.z; id[7] = i1.w;
     }
-    double fu[8], fv[8], fw[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const double2 * p = reinterpret_cast<const double2 *> (fld.vtx_val + (int64_t) id[k]*4);
-      const double2 a = __ldg (p);
-      fu[k] = a.x; fv[k] = a.y; fw[k] = __ldg (reinterpret_cast<const double *> (p + 1));
-    }
-    if (any_nodata) {
-      const int cell = cell_index<DIM, LATTICE> (T, L);
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-	fu[k] = resolve (fu[k], fld.u[0], cell);
-	fv[k] = resolve (fv[k], fld.u[1], cell);
-	fw[k] = resolve (fw[k], fld.u[2], cell);
-      }
-    }
     /* t in [0,1] along each axis: (1 + (p - o)/(h/2))/2 */
     const double tx = fma (x - L.cx, 0.5*inv, 0.5);
     const double ty = fma (y - L.cy, 0.5*inv, 0.5);
     const double tz = fma (z - L.cz, 0.5*inv, 0.5);
-    /* corners: 0(-,-,+) 1(+,-,+) 2(+,+,+) 3(-,+,+) 4(-,-,-) 5(+,-,-) 6(+,+,-) 7(-,+,-) */
-    u = lerp (lerp (lerp (fu[4], fu[5], tx), lerp (fu[7], fu[6], tx), ty),
-	      lerp (lerp (fu[0], fu[1], tx), lerp (fu[3], fu[2], tx), ty), tz);
-    v = lerp (lerp (lerp (fv[4], fv[5], tx), lerp (fv[7], fv[6], tx), ty),
-	      lerp (lerp (fv[0], fv[1], tx), lerp (fv[3], fv[2], tx), ty), tz);
-    w = lerp (lerp (lerp (fw[4], fw[5], tx), lerp (fw[7], fw[6], tx), ty),
-	      lerp (lerp (fw[0], fw[1], tx), lerp (fw[3], fw[2], tx), ty), tz);
+    /* corners: 0(-,-,+) 1(+,-,+) 2(+,+,+) 3(-,+,+) 4(-,-,-) 5(+,-,-) 6(+,+,-) 7(-,+,-).
+       Evaluated one z-plane at a time (back: 4 5 7 6, front: 0 1 3 2) so that
+       only 12 corner values are live at once. */
+    const int cell = any_nodata ? cell_index<DIM, LATTICE> (T, L) : 0;
+    double pu[2], pv[2], pw[2];
+#pragma unroll
+    for (int plane = 0; plane < 2; plane++) {
+      const int q[4] = { plane ? 0 : 4, plane ? 1 : 5, plane ? 3 : 7, plane ? 2 : 6 };
+      double fu[4], fv[4], fw[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+	const double2 * p = reinterpret_cast<const double2 *> (fld.vtx_val + (int64_t) id[q[k]]*4);
+	const double2 a = __ldg (p);
+	fu[k] = a.x; fv[k] = a.y; fw[k] = __ldg (reinterpret_cast<const double *> (p + 1));
+      }
+      if (any_nodata) {
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+	  fu[k] = resolve (fu[k], fld.u[0], cell);
+	  fv[k] = resolve (fv[k], fld.u[1], cell);
+	  fw[k] = resolve (fw[k], fld.u[2], cell);
+	}
+      }
+      pu[plane] = lerp (lerp (fu[0], fu[1], tx), lerp (fu[2], fu[3], tx), ty);
+      pv[plane] = lerp (lerp (fv[0], fv[1], tx), lerp (fv[2], fv[3], tx), ty);
+      pw[plane] = lerp (lerp (fw[0], fw[1], tx), lerp (fw[2], fw[3], tx), ty);
+    }
+    u = lerp (pu[0], pu[1], tz);
+    v = lerp (pv[0], pv[1], tz);
+    w = lerp (pw[0], pw[1], tz);
   }
   else {
     int4 id;
@@ -534,8 +541,8 @@ __device__ __forceinline__ void fence_async_shared ()
 
 #define PIPE_TILE 256
 
-template <int DIM, bool LATTICE, unsigned PROG, int STAGES>
-__global__ void __launch_bounds__(PIPE_TILE, 3)
+template <int DIM, bool LATTICE, unsigned PROG, int STAGES, int MINB>
+__global__ void __launch_bounds__(PIPE_TILE, MINB)
 step_kernel_pipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_tiles)
 {
   constexpr int NC = DIM == 3 ? 8 : 6;
@@ -843,7 +850,7 @@ inline unsigned grid_for (int64_t n, int threads) { return (unsigned) ((n + thre
 /* ------------------------------------------------------------------ */
 /* launchers (C linkage, called from capi.cu)                           */
 
-template <int DIM, bool LA, unsigned PR, int ST>
+template <int DIM, bool LA, unsigned PR, int ST, int MB>
 static void launch_pipe (const DevTree * T, const DevField * F, const DevParticles * P,
 			 const DevStep * S, int n_sm, cudaStream_t st)
 {
@@ -851,18 +858,18 @@ static void launch_pipe (const DevTree * T, const DevField * F, const DevParticl
   const size_t smem = (size_t) ST*(DIM == 3 ? 8 : 6)*PIPE_TILE*sizeof (double);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute (step_kernel_pipe<DIM, LA, PR, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-			  (int) smem);
+    cudaFuncSetAttribute (step_kernel_pipe<DIM, LA, PR, ST, MB>,
+			  cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     configured = true;
   }
-  int grid = n_sm*3;                    /* persistent: 3 CTAs of 256 threads per SM */
+  int grid = n_sm*MB;                   /* persistent: MB CTAs of 256 threads per SM */
   if (grid > n_tiles) grid = n_tiles;
-  step_kernel_pipe<DIM, LA, PR, ST><<<grid, PIPE_TILE, smem, st>>> (*T, *F, *P, *S, n_tiles);
+  step_kernel_pipe<DIM, LA, PR, ST, MB><<<grid, PIPE_TILE, smem, st>>> (*T, *F, *P, *S, n_tiles);
 }
 
 extern "C" {
 
-/* mode: 0 plain kernel, 2/3 = TMA-staged persistent kernel with that many stages */
+/* mode: 0 plain kernel, >= 2: TMA-staged persistent kernel (2 stages, minb CTAs per SM) */
 void gfsb200_launch_step (const DevTree * T, const DevField * F, const DevParticles * P,
 			  const DevStep * S, int rec, int minb, int mode, int n_sm, cudaStream_t st)
 {
@@ -878,8 +885,8 @@ void gfsb200_launch_step (const DevTree * T, const DevField * F, const DevPartic
   }
   if (rec || (S->cd_const == S->cd_const)) prog = 0;
   if (!rec && mode >= 2 && P->n >= 4*PIPE_TILE) {
-#define PIPE_ST(D, LA, PR) do { if (mode == 2) launch_pipe<D, LA, PR, 2> (T, F, P, S, n_sm, st); \
-				else launch_pipe<D, LA, PR, 3> (T, F, P, S, n_sm, st); } while (0)
+#define PIPE_ST(D, LA, PR) do { if (minb >= 4) launch_pipe<D, LA, PR, 2, 4> (T, F, P, S, n_sm, st); \
+				else launch_pipe<D, LA, PR, 2, 3> (T, F, P, S, n_sm, st); } while (0)
 #define PIPE_PR(D, LA) do { switch (prog) { \
     case 0x1: PIPE_ST (D, LA, 0x1); break; case 0x21: PIPE_ST (D, LA, 0x21); break; \
     case 0x321: PIPE_ST (D, LA, 0x321); break; case 0x31: PIPE_ST (D, LA, 0x31); break; \
