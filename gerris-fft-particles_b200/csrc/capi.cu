@@ -24,7 +24,8 @@
 #include "device_types.cuh"
 
 extern "C" {
-void gfsb200_launch_cell_pass (const DevTree *, const DevField *, int, cudaStream_t);
+void gfsb200_launch_cell_pass (const DevTree *, const DevField *, int, cudaStream_t, cudaStream_t,
+			       cudaEvent_t, cudaEvent_t);
 void gfsb200_launch_step (const DevTree *, const DevField *, const DevParticles *, const DevStep *,
 			  int, int, int, int, cudaStream_t);   /* (.., record, min blocks/SM, mode, SMs, stream) */
 void gfsb200_launch_advect (const DevTree *, const DevField *, const DevParticles *, double, int,
@@ -56,6 +57,8 @@ cudaError_t gfsb200_cub_select_flagged (void *, size_t *, const int32_t *, const
 struct gfsb200_ctx {
   int device, n_sm;
   cudaStream_t stream;
+  cudaStream_t aux_stream;     /* second stream of the cell pass */
+  cudaEvent_t ev_fork, ev_join;
   /* tree */
   bool have_tree;
   DevTree T;
@@ -176,8 +179,11 @@ extern "C" int gfsb200_ctx_create (int device, gfsb200_ctx ** out)
   c->hp_chunk = 0; c->hp_h2d = c->hp_d2h = NULL;
   c->ev_used = 0; c->timing = true;
   c->step_minb = getenv ("GFSB200_STEP_MINB") ? atoi (getenv ("GFSB200_STEP_MINB")) : 3;
-  c->step_mode = getenv ("GFSB200_STEP_MODE") ? atoi (getenv ("GFSB200_STEP_MODE")) : 2;
+  c->step_mode = getenv ("GFSB200_STEP_MODE") ? atoi (getenv ("GFSB200_STEP_MODE")) : 3;
   if (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags (&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags (&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags (&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaMalloc ((void **) &c->d_count, sizeof (int32_t)) != cudaSuccess ||
       cudaMalloc ((void **) &c->d_ptr_table, 2*NCOL*sizeof (double *)) != cudaSuccess) {
     delete c;
@@ -204,6 +210,8 @@ extern "C" void gfsb200_ctx_destroy (gfsb200_ctx * c)
   }
   cudaFree (c->d_count); cudaFree (c->d_ptr_table);
   for (size_t i = 0; i < c->ev.size (); i++) cudaEventDestroy (c->ev[i]);
+  cudaEventDestroy (c->ev_fork); cudaEventDestroy (c->ev_join);
+  cudaStreamDestroy (c->aux_stream);
   cudaStreamDestroy (c->stream);
   delete c;
 }
@@ -317,7 +325,7 @@ extern "C" int gfsb200_refresh_field (gfsb200_ctx * c)
     return gfsb200_fail (GFSB200_ERR_STATE, "refresh_field: no tree/field resident");
   CK (cudaSetDevice (c->device));
   CK (cudaMemsetAsync (c->F.nodata_flag, 0, sizeof (int), c->stream));
-  gfsb200_launch_cell_pass (&c->T, &c->F, c->n_sm, c->stream);
+  gfsb200_launch_cell_pass (&c->T, &c->F, c->n_sm, c->stream, c->aux_stream, c->ev_fork, c->ev_join);
   CK (cudaGetLastError ());
   c->have_field = true;
   return GFSB200_OK;

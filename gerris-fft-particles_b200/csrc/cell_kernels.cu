@@ -223,8 +223,27 @@ template <int DIM>
 __global__ void __launch_bounds__(256)
 vertex_values_kernel (DevTree T, DevField fld)
 {
-  const int stride = gridDim.x*blockDim.x;
-  for (int v = blockIdx.x*blockDim.x + threadIdx.x; v < T.n_vertices; v += stride) {
+  /* Lattice trees: vertices are numbered row-major, cells in Morton order.  A
+     CTA then takes an 8x8x4 (3D) / 16x16 (2D) brick of vertices instead of 256
+     consecutive ones, which halves the number of distinct cell sectors it
+     gathers (9x9x5 cells per brick instead of two 129-long rows). */
+  const int n1 = T.lattice_n1;
+  const int bx = DIM == 3 ? 8 : 16, by = DIM == 3 ? 8 : 16, bz = DIM == 3 ? 4 : 1;
+  const int tx = n1 > 0 ? (n1 + bx - 1)/bx : 0, ty = n1 > 0 ? (n1 + by - 1)/by : 0,
+    tz = DIM == 3 && n1 > 0 ? (n1 + bz - 1)/bz : 1;
+  const int64_t n_items = n1 > 0 ? (int64_t) tx*ty*tz*256 : T.n_vertices;
+  const int64_t stride = (int64_t) gridDim.x*blockDim.x;
+  for (int64_t item = (int64_t) blockIdx.x*blockDim.x + threadIdx.x; item < n_items; item += stride) {
+    int v = (int) item;
+    if (n1 > 0) {
+      const int brick = (int) (item >> 8), t = (int) (item & 255);
+      const int i = (brick % tx)*bx + (t % bx);
+      const int j = ((brick/tx) % ty)*by + ((t/bx) % by);
+      const int k = DIM == 3 ? (brick/(tx*ty))*bz + t/(bx*by) : 0;
+      if (i >= n1 || j >= n1 || (DIM == 3 && k >= n1))
+	continue;
+      v = (k*n1 + j)*n1 + i;
+    }
     const int b = T.vtx_off[v], e = T.vtx_off[v + 1];
     double s0 = 0., s1 = 0., s2 = 0.;
     bool nodata = false;
@@ -276,22 +295,35 @@ vertex_values_kernel (DevTree T, DevField fld)
 
 } // namespace
 
+/* The two kernels are independent and each is latency-bound (dependent
+ * index -> value gathers), so they are issued on two streams and overlap:
+ * `aux` forks from `stream` at ev_fork and joins back at ev_join. */
 extern "C" void gfsb200_launch_cell_pass (const DevTree * T, const DevField * fld, int n_sm,
-					  cudaStream_t stream)
+					  cudaStream_t stream, cudaStream_t aux,
+					  cudaEvent_t ev_fork, cudaEvent_t ev_join)
 {
   const int threads = 256;
-  int gv = (T->n_vertices + threads - 1)/threads, gc = (T->n_cells + threads - 1)/threads;
+  int64_t n_items = T->n_vertices;
+  if (T->lattice_n1 > 0) {
+    const int n1 = T->lattice_n1, b = T->dim == 3 ? 8 : 16;
+    n_items = (int64_t) ((n1 + b - 1)/b)*((n1 + b - 1)/b)*(T->dim == 3 ? (n1 + 3)/4 : 1)*256;
+  }
+  int gv = (int) ((n_items + threads - 1)/threads), gc = (T->n_cells + threads - 1)/threads;
   const int cap = n_sm*16;            /* grid-stride */
   if (gv > cap) gv = cap;
   if (gc > cap) gc = cap;
   if (gv < 1) gv = 1;
   if (gc < 1) gc = 1;
+  cudaEventRecord (ev_fork, stream);
+  cudaStreamWaitEvent (aux, ev_fork, 0);
   if (T->dim == 2) {
     vertex_values_kernel<2><<<gv, threads, 0, stream>>> (*T, *fld);
-    vorticity_kernel<2><<<gc, threads, 0, stream>>> (*T, *fld);
+    vorticity_kernel<2><<<gc, threads, 0, aux>>> (*T, *fld);
   }
   else {
     vertex_values_kernel<3><<<gv, threads, 0, stream>>> (*T, *fld);
-    vorticity_kernel<3><<<gc, threads, 0, stream>>> (*T, *fld);
+    vorticity_kernel<3><<<gc, threads, 0, aux>>> (*T, *fld);
   }
+  cudaEventRecord (ev_join, aux);
+  cudaStreamWaitEvent (stream, ev_join, 0);
 }

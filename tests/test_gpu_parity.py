@@ -389,7 +389,7 @@ def test_full_size_c2_properties(ctx):
     _check_state(sub_got, want, 3)
 
 
-@pytest.mark.parametrize("mode", ["0", "2"])
+@pytest.mark.parametrize("mode", ["0", "2", "3"])
 @pytest.mark.parametrize("kind", ["c1", "uniform3", "ring3", "ring2"])
 def test_step_fast_paths(kind, mode, monkeypatch):
     """The production launch (no cell/force recording): compile-time force
