@@ -255,14 +255,13 @@ def run_b200(args):
         # the C-ABI's deposit buffer, aliased (no copy) as a tensor for the NCCL all-reduce
         dep_tensor = pkg.multigpu.deposit_tensor(ctx, local_rank)
 
-    launches_per_step = 3 + (2 if args.two_way else 0)        # vertex + vorticity + step (+ 2 deposit)
+    launches_per_step = 3 + (1 if args.two_way else 0)        # vertex + vorticity + step (+ fused deposit)
 
     def one_step(i):
         ctx.refresh_field()
         ctx.step(par)
         if args.two_way:
-            ctx.deposit_volume()
-            ctx.deposit_force(par)
+            ctx.deposit_all(par)
             if dep_tensor is not None:
                 pkg.multigpu.allreduce_deposit(ctx, dep_tensor)
         if args.resort and (i + 1) % args.resort == 0:

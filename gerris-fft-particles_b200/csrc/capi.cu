@@ -37,9 +37,8 @@ void gfsb200_launch_interpolate (const DevTree *, const DevField *, int64_t, con
 				 cudaStream_t);
 void gfsb200_launch_corner_values (const DevTree *, const DevField *, int, int64_t, const int32_t *,
 				   double *, cudaStream_t);
-void gfsb200_launch_deposit_volume (const DevTree *, const DevParticles *, double *, cudaStream_t);
-void gfsb200_launch_deposit_force (const DevTree *, const DevField *, const DevParticles *,
-				   const DevStep *, double *, double *, double *, cudaStream_t);
+void gfsb200_launch_deposit (const DevTree *, const DevField *, const DevParticles *, const DevStep *,
+			     int, double *, double *, double *, double *, cudaStream_t);
 void gfsb200_launch_gather (int64_t, const int32_t *, int, const double * const *, double * const *,
 			    const uint32_t *, uint32_t *, cudaStream_t);
 void gfsb200_launch_iota (int64_t, int32_t *, cudaStream_t);
@@ -845,32 +844,39 @@ extern "C" int gfsb200_interpolate (gfsb200_ctx * c, int64_t n, const double * x
 /* ------------------------------------------------------------------ */
 /* two-way coupling                                                     */
 
-extern "C" int gfsb200_deposit_volume (gfsb200_ctx * c)
+/* what: bit 0 = void fraction (component 0), bit 1 = force (components 1..dim) */
+static int deposit (gfsb200_ctx * c, const gfsb200_step_params * p, int what)
 {
-  if (!c || !c->have_tree) return gfsb200_fail (GFSB200_ERR_STATE, "deposit_volume: no tree resident");
+  if (!c || !c->have_tree) return gfsb200_fail (GFSB200_ERR_STATE, "deposit: no tree resident");
+  if ((what & 2) && !c->have_field) return gfsb200_fail (GFSB200_ERR_STATE, "deposit: no field resident");
+  DevStep S;
+  memset (&S, 0, sizeof S);
+  if (what & 2) {
+    int r = make_step (p, &S);
+    if (r) return r;
+  }
   CK (cudaSetDevice (c->device));
+  const size_t n = c->T.n_cells;
   /* gfs_cell_reset on the leaves, then scatter */
-  CK (cudaMemsetAsync (c->deposit, 0, (size_t) c->T.n_cells*sizeof (double), c->stream));
+  if (what & 1) CK (cudaMemsetAsync (c->deposit, 0, n*sizeof (double), c->stream));
+  if (what & 2) CK (cudaMemsetAsync (c->deposit + n, 0, (size_t) c->T.dim*n*sizeof (double), c->stream));
   DevParticles P = particles_view (c);
-  gfsb200_launch_deposit_volume (&c->T, &P, c->deposit, c->stream);
+  gfsb200_launch_deposit (&c->T, &c->F, &P, &S, what, c->deposit, c->deposit + n, c->deposit + 2*n,
+			  c->T.dim == 3 ? c->deposit + 3*n : NULL, c->stream);
   CK (cudaGetLastError ());
   return GFSB200_OK;
 }
 
+extern "C" int gfsb200_deposit_volume (gfsb200_ctx * c) { return deposit (c, NULL, 1); }
+
 extern "C" int gfsb200_deposit_force (gfsb200_ctx * c, const gfsb200_step_params * p)
 {
-  if (!c || !c->have_field) return gfsb200_fail (GFSB200_ERR_STATE, "deposit_force: no field resident");
-  DevStep S;
-  int r = make_step (p, &S);
-  if (r) return r;
-  CK (cudaSetDevice (c->device));
-  const size_t n = c->T.n_cells;
-  CK (cudaMemsetAsync (c->deposit + n, 0, (size_t) c->T.dim*n*sizeof (double), c->stream));
-  DevParticles P = particles_view (c);
-  gfsb200_launch_deposit_force (&c->T, &c->F, &P, &S, c->deposit + n, c->deposit + 2*n,
-				c->T.dim == 3 ? c->deposit + 3*n : NULL, c->stream);
-  CK (cudaGetLastError ());
-  return GFSB200_OK;
+  return deposit (c, p, 2);
+}
+
+extern "C" int gfsb200_deposit_all (gfsb200_ctx * c, const gfsb200_step_params * p)
+{
+  return deposit (c, p, 3);
 }
 
 extern "C" int gfsb200_deposit_buffer (gfsb200_ctx * c, double ** dev, int64_t * count)

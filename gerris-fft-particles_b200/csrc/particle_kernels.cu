@@ -748,56 +748,50 @@ __device__ __forceinline__ void run_atomic_add (double * __restrict__ dst, int c
     atomicAdd (dst + cell, s);
 }
 
-/* GfsParticulateField with voidfraction_from_particles,
- * modules/particulatecommon.c:1929-1957: v[cell] += V_p / V_cell */
-template <int DIM>
-__global__ void __launch_bounds__(256)
-deposit_volume_kernel (DevTree T, DevParticles P, double * __restrict__ field)
+/* One pass for both deposits of a two-way step:
+ *   VOL    GfsParticulateField with voidfraction_from_particles,
+ *          modules/particulatecommon.c:1929-1957:  v[cell] += V_p / V_cell
+ *   FORCE  GfsSourceParticulate in the single-cell limit, :2158-2228: forces
+ *          recomputed without GfsForceBuoy (compute_forces_onfluid :753-765),
+ *          then u_c[cell] -= F_c / rho / V_cell
+ * One locate, one interpolation set, same compile-time force programs and
+ * lattice addressing as the step kernel; one atomic per run of equal cells. */
+template <int DIM, bool LATTICE, unsigned PROG, bool VOL, bool FORCE>
+__global__ void __launch_bounds__(256, 3)
+deposit_kernel (DevTree T, DevField fld, DevParticles P, DevStep S, double * __restrict__ vol,
+		double * __restrict__ f0, double * __restrict__ f1, double * __restrict__ f2)
 {
   const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
   int cell = -1;
-  double val = 0.;
+  double av = 0., ax = 0., ay = 0., az = 0.;
   if (i < P.n) {
-    const Located L = locate<DIM> (T, P.x[i], P.y[i], DIM == 3 ? P.z[i] : 0.);
-    cell = L.cell;
+    const double x = __ldcs (P.x + i), y = __ldcs (P.y + i), z = DIM == 3 ? __ldcs (P.z + i) : 0.;
+    const Located L = locate<DIM, LATTICE> (T, x, y, z);
+    cell = cell_index<DIM, LATTICE> (T, L);
     if (cell >= 0) {
+      const double volume = __ldcs (P.volume + i);
       const double h = 2.*L.half;
-      val = P.volume[i]/(DIM == 3 ? h*h*h : h*h);    /* ftt_cell_volume */
+      const double inv_cellvol = 1./(DIM == 3 ? h*h*h : h*h);      /* 1/ftt_cell_volume: power of two, exact */
+      if (VOL)
+	av = volume*inv_cellvol;
+      if (FORCE) {
+	double Fx, Fy, Fz, rho;
+	total_force<DIM, true, LATTICE, PROG> (T, fld, S, L, x, y, z, __ldcs (P.vx + i), __ldcs (P.vy + i),
+					      DIM == 3 ? __ldcs (P.vz + i) : 0., __ldcs (P.mass + i), volume,
+					      Fx, Fy, Fz, rho);
+	const double k = -inv_cellvol/rho;
+	ax = Fx*k; ay = Fy*k; az = Fz*k;
+      }
     }
   }
-  run_atomic_add (field, cell, val);
-}
-
-/* GfsSourceParticulate in the single-cell limit,
- * modules/particulatecommon.c:2158-2228: forces without buoyancy, then
- * u_c[cell] -= F_c / rho / V_cell */
-template <int DIM>
-__global__ void __launch_bounds__(256)
-deposit_force_kernel (DevTree T, DevField fld, DevParticles P, DevStep S,
-		      double * __restrict__ f0, double * __restrict__ f1, double * __restrict__ f2)
-{
-  const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
-  int cell = -1;
-  double ax = 0., ay = 0., az = 0.;
-  if (i < P.n) {
-    const double x = P.x[i], y = P.y[i], z = DIM == 3 ? P.z[i] : 0.;
-    const Located L = locate<DIM> (T, x, y, z);
-    cell = L.cell;
-    if (cell >= 0) {
-      double Fx, Fy, Fz, rho;
-      total_force<DIM, true> (T, fld, S, L, x, y, z, P.vx[i], P.vy[i], DIM == 3 ? P.vz[i] : 0.,
-			      P.mass[i], P.volume[i], Fx, Fy, Fz, rho);
-      const double h = 2.*L.half;
-      const double cellvol = DIM == 3 ? h*h*h : h*h;
-      ax = -(Fx/rho/cellvol);
-      ay = -(Fy/rho/cellvol);
-      az = -(Fz/rho/cellvol);
-    }
+  if (VOL)
+    run_atomic_add (vol, cell, av);
+  if (FORCE) {
+    run_atomic_add (f0, cell, ax);
+    run_atomic_add (f1, cell, ay);
+    if (DIM == 3)
+      run_atomic_add (f2, cell, az);
   }
-  run_atomic_add (f0, cell, ax);
-  run_atomic_add (f1, cell, ay);
-  if (DIM == 3)
-    run_atomic_add (f2, cell, az);
 }
 
 /* ------------------------------------------------------------------ */
@@ -960,23 +954,33 @@ void gfsb200_launch_corner_values (const DevTree * T, const DevField * F, int co
     corner_values_kernel<2><<<grid_for (n*nc, 256), 256, 0, st>>> (*T, *F, comp, n, cells, out);
 }
 
-void gfsb200_launch_deposit_volume (const DevTree * T, const DevParticles * P, double * field,
-				    cudaStream_t st)
+/* what: bit 0 = void fraction, bit 1 = force components */
+void gfsb200_launch_deposit (const DevTree * T, const DevField * F, const DevParticles * P,
+			     const DevStep * S, int what, double * vol, double * f0, double * f1,
+			     double * f2, cudaStream_t st)
 {
-  if (P->n <= 0) return;
-  if (T->dim == 3) deposit_volume_kernel<3><<<grid_for (P->n, 256), 256, 0, st>>> (*T, *P, field);
-  else deposit_volume_kernel<2><<<grid_for (P->n, 256), 256, 0, st>>> (*T, *P, field);
-}
-
-void gfsb200_launch_deposit_force (const DevTree * T, const DevField * F, const DevParticles * P,
-				   const DevStep * S, double * f0, double * f1, double * f2,
-				   cudaStream_t st)
-{
-  if (P->n <= 0) return;
-  if (T->dim == 3)
-    deposit_force_kernel<3><<<grid_for (P->n, 256), 256, 0, st>>> (*T, *F, *P, *S, f0, f1, f2);
-  else
-    deposit_force_kernel<2><<<grid_for (P->n, 256), 256, 0, st>>> (*T, *F, *P, *S, f0, f1, f2);
+  if (P->n <= 0 || !(what & 3)) return;
+  const unsigned g = grid_for (P->n, 256);
+  const bool lat = T->lattice_n1 > 0;
+  unsigned prog = 0;
+  if (what & 2)
+    switch (S->forces) {
+    case 0x1: case 0x21: case 0x321: case 0x31: case 0x3:
+      prog = S->forces;
+    }
+  if (S->cd_const == S->cd_const) prog = 0;
+#define DEP(D, LA, PR, V, FO) deposit_kernel<D, LA, PR, V, FO><<<g, 256, 0, st>>> (*T, *F, *P, *S, vol, f0, f1, f2)
+#define DEP_W(D, LA, PR) do { if (what == 1) DEP (D, LA, 0, true, false); else if (what == 2) DEP (D, LA, PR, false, true); \
+			      else DEP (D, LA, PR, true, true); } while (0)
+#define DEP_PR(D, LA) do { switch (prog) { \
+    case 0x1: DEP_W (D, LA, 0x1); break; case 0x21: DEP_W (D, LA, 0x21); break; \
+    case 0x321: DEP_W (D, LA, 0x321); break; case 0x31: DEP_W (D, LA, 0x31); break; \
+    case 0x3: DEP_W (D, LA, 0x3); break; default: DEP_W (D, LA, 0); } } while (0)
+  if (T->dim == 3) { if (lat) DEP_PR (3, true); else DEP_PR (3, false); }
+  else             { if (lat) DEP_PR (2, true); else DEP_PR (2, false); }
+#undef DEP_PR
+#undef DEP_W
+#undef DEP
 }
 
 void gfsb200_launch_gather (int64_t n, const int32_t * perm, int ncols, const double * const * src,

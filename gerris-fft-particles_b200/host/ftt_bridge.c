@@ -87,7 +87,16 @@ int gfsb200_ftt_flatten (int n_roots, void * const * roots_, const int * is_box,
      order == flat order and the map needs no permutation */
   for (size_t head = 0; head < n && rc >= 0; head++) {
     FttCell * c = cells[head];
-    if (FTT_CELL_IS_DESTROYED (c) || FTT_CELL_IS_LEAF (c))
+    if (FTT_CELL_IS_DESTROYED (c))
+      continue;
+    /* GfsStateVector.solid (src/fluid.h:44-52) sits right after f[FTT_NEIGHBORS]:
+       mixed cells need solid fractions the flat tree does not carry */
+    if (c->data && *(void * const *) ((const char *) c->data + FTT_NEIGHBORS*2*sizeof (double))) {
+      bridge_error = "flatten: mixed (solid) cells are not supported on the device path";
+      rc = GFSB200_ERR_UNSUPPORTED;
+      break;
+    }
+    if (FTT_CELL_IS_LEAF (c))
       continue;
     struct _FttOct * oct = c->children;
     unsigned destroyed = 0, flags = 0;

@@ -247,6 +247,8 @@ int gfsb200_deposit_volume (gfsb200_ctx * c);
 /* GfsSourceParticulate in the single-cell limit: forces recomputed without
  * GfsForceBuoy, field_c[cell] -= F_c / rho / V_cell. */
 int gfsb200_deposit_force (gfsb200_ctx * c, const gfsb200_step_params * p);
+/* both of the above in one pass over the particles (one locate, one kernel) */
+int gfsb200_deposit_all (gfsb200_ctx * c, const gfsb200_step_params * p);
 /* device pointer / element count of the deposition buffer
  * ([1 + dim][n_cells]: void fraction, Fx, Fy(, Fz)); for the multi-GPU
  * all-reduce (NCCL) issued by the caller on gfsb200_ctx_stream() */

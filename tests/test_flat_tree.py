@@ -149,3 +149,20 @@ def test_error_paths():
         t.corner_sweep()                           # boundaries must come last
     with pytest.raises(capi.GfsB200Error):
         capi.Tree(4)
+
+
+def test_flatten_rejects_solid_cells():
+    """a mixed cell (GFS_STATE (cell)->solid != NULL) cannot be represented: the
+    bridge must refuse the tree instead of silently dropping the solid fractions"""
+    import ctypes
+    t, sim = build_pair(3, 2, 3, ())
+    roots, is_box = sim.roots()
+    t2, fmap = capi.flatten_ftt(3, roots, is_box)
+    leaf = int(fmap.cells[t2.view().box_leaves[5]])
+    data = ctypes.c_void_p.from_address(leaf + 8).value            # FttCell.data
+    solid_slot = ctypes.c_void_p.from_address(data + 6 * 16)        # GfsStateVector.solid
+    solid_slot.value = 0xdead0
+    with pytest.raises(capi.GfsB200Error, match="solid"):
+        capi.flatten_ftt(3, roots, is_box)
+    solid_slot.value = None
+    capi.flatten_ftt(3, roots, is_box)

@@ -317,6 +317,11 @@ def test_deposit(kind, ctx):
     ctx.sort()
     ctx.deposit_volume()
     ctx.deposit_force(w.step_params())
+    separate = [ctx.download_deposit(c) for c in range(1 + w.dim)]
+    ctx.deposit_all(w.step_params())              # the fused pass gives the same field
+    for c in range(1 + w.dim):
+        fused = ctx.download_deposit(c)
+        assert np.abs(fused - separate[c]).max() <= 1e-13 * max(np.abs(separate[c]).max(), 1e-300)
     live = (w.arrays.flags & capi.CELL_DESTROYED) == 0
     plist = ora.ParticleList(sim, *[parts[k] for k in ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")])
     zero = np.zeros(int(live.sum()))
