@@ -17,7 +17,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(_HERE, "lib")
 
-FORCE_DRAG, FORCE_LIFT, FORCE_BUOY = 1, 2, 3
+FORCE_DRAG, FORCE_LIFT, FORCE_BUOY, FORCE_INERTIAL, FORCE_ADDEDMASS = 1, 2, 3, 4, 5
 CELL_DESTROYED, CELL_BOUNDARY, CELL_LEAF = 1, 2, 4
 MAX_FORCES = 8
 NODATA = float(np.finfo(np.float64).max)
@@ -48,7 +48,7 @@ class StepParamsC(C.Structure):
         ("dt", C.c_double), ("n_forces", C.c_int32), ("force", C.c_int32 * MAX_FORCES),
         ("rho", C.c_double), ("mu", C.c_double), ("g", C.c_double * 3),
         ("cd_const", C.c_double), ("cl_const", C.c_double),
-        ("record_cells", C.c_int32), ("record_forces", C.c_int32),
+        ("record_cells", C.c_int32), ("record_forces", C.c_int32), ("cm_const", C.c_double),
     ]
 
 
@@ -93,6 +93,7 @@ def lib() -> C.CDLL:
         "gfsb200_upload_field": (i32, [vp, vp, vp, vp, vp, vp]),
         "gfsb200_set_field_device": (i32, [vp, vp, vp, vp, vp, vp]),
         "gfsb200_refresh_field": (i32, [vp]),
+        "gfsb200_upload_field_prev": (i32, [vp, vp, vp, vp]),
         "gfsb200_download_corner_values": (i32, [vp, i32, i64, vp, vp]),
         "gfsb200_download_vorticity": (i32, [vp, i64, vp, vp]),
         "gfsb200_particles_upload": (i32, [vp, i64] + [vp] * 9),
@@ -264,7 +265,8 @@ class TreeArrays:
 class StepParams:
     def __init__(self, dt: float, forces: Sequence[int] = (), rho: float = 1.0, mu: float = 0.0,
                  g: Sequence[float] = (0.0, 0.0, 0.0), cd_const: float = float("nan"),
-                 cl_const: float = float("nan"), record_cells: bool = False, record_forces: bool = False):
+                 cl_const: float = float("nan"), record_cells: bool = False, record_forces: bool = False,
+                 cm_const: float = float("nan")):
         self.c = StepParamsC()
         lib().gfsb200_step_params_default(C.byref(self.c))
         self.c.dt = dt
@@ -274,7 +276,7 @@ class StepParams:
         self.c.rho, self.c.mu = rho, mu
         for a in range(3):
             self.c.g[a] = float(g[a])
-        self.c.cd_const, self.c.cl_const = cd_const, cl_const
+        self.c.cd_const, self.c.cl_const, self.c.cm_const = cd_const, cl_const, cm_const
         self.c.record_cells, self.c.record_forces = int(record_cells), int(record_forces)
 
 
@@ -322,6 +324,10 @@ class Context:
     def set_field_device(self, u: int, v: int, w: int = 0, alpha: int = 0, mu: int = 0):
         _check(self._lib.gfsb200_set_field_device(self.handle, u, v, w or None, alpha or None, mu or None),
                "set_field_device")
+
+    def upload_field_prev(self, un, vn, wn=None):
+        arrs = [_f64(a) for a in (un, vn, wn)]
+        _check(self._lib.gfsb200_upload_field_prev(self.handle, *[_ptr(a) for a in arrs]), "upload_field_prev")
 
     def refresh_field(self):
         _check(self._lib.gfsb200_refresh_field(self.handle), "refresh_field")

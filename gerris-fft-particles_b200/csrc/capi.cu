@@ -26,6 +26,8 @@
 extern "C" {
 void gfsb200_launch_cell_pass (const DevTree *, const DevField *, int, cudaStream_t, cudaStream_t,
 			       cudaEvent_t, cudaEvent_t);
+void gfsb200_launch_vertex_values (const DevTree *, const DevField *, int, cudaStream_t);
+void gfsb200_launch_convective (const DevTree *, const DevField *, int, cudaStream_t);
 void gfsb200_launch_step (const DevTree *, const DevField *, const DevParticles *, const DevStep *,
 			  int, int, int, int, cudaStream_t);   /* (.., record, min blocks/SM, mode, SMs, stream) */
 void gfsb200_launch_advect (const DevTree *, const DevField *, const DevParticles *, double, int,
@@ -68,6 +70,8 @@ struct gfsb200_ctx {
   bool have_field, own_field;
   DevField F;
   double * d_field[5];         /* owned copies: u v w alpha mu */
+  double * d_prev[3];          /* Un Vn Wn (GfsForceInertial / GfsForceAddedMass) */
+  bool have_prev, acc_valid;
   /* particles */
   int64_t n, cap;
   double * col[2][NCOL];       /* double-buffered SoA */
@@ -123,6 +127,10 @@ static void free_tree (gfsb200_ctx * c)
   cudaFree (c->F.vtx_val); cudaFree (c->F.vort); cudaFree (c->F.nodata_flag);
   c->F.vtx_val = c->F.vort = NULL; c->F.nodata_flag = NULL;
   for (int i = 0; i < 5; i++) { cudaFree (c->d_field[i]); c->d_field[i] = NULL; }
+  for (int i = 0; i < 3; i++) { cudaFree (c->d_prev[i]); c->d_prev[i] = NULL; }
+  cudaFree (c->F.vtx_prev); cudaFree (c->F.acc);
+  c->F.vtx_prev = c->F.acc = NULL;
+  c->have_prev = c->acc_valid = false;
   cudaFree (c->deposit); c->deposit = NULL; c->deposit_count = 0;
   c->have_tree = c->have_field = false;
 }
@@ -168,6 +176,8 @@ extern "C" int gfsb200_ctx_create (int device, gfsb200_ctx ** out)
   c->d_child0 = c->d_neighbor = c->d_la_slot = c->d_vtx_off = c->d_vtx_cell = c->d_leaf_vtx = NULL;
   c->d_level = c->d_info = NULL; c->d_vtx_w = c->d_vtx_wuni = NULL;
   for (int i = 0; i < 5; i++) c->d_field[i] = NULL;
+  for (int i = 0; i < 3; i++) c->d_prev[i] = NULL;
+  c->have_prev = c->acc_valid = false;
   c->n = c->cap = c->aux_cap = 0; c->cur = 0;
   for (int b = 0; b < 2; b++) { for (int k = 0; k < NCOL; k++) c->col[b][k] = NULL; c->id[b] = NULL; }
   for (int k = 0; k < 3; k++) c->force[k] = NULL;
@@ -327,6 +337,35 @@ extern "C" int gfsb200_refresh_field (gfsb200_ctx * c)
   gfsb200_launch_cell_pass (&c->T, &c->F, c->n_sm, c->stream, c->aux_stream, c->ev_fork, c->ev_join);
   CK (cudaGetLastError ());
   c->have_field = true;
+  c->acc_valid = false;
+  return GFSB200_OK;
+}
+
+extern "C" int gfsb200_upload_field_prev (gfsb200_ctx * c, const double * un, const double * vn,
+					  const double * wn)
+{
+  if (!c || !c->have_tree) return gfsb200_fail (GFSB200_ERR_STATE, "upload_field_prev: upload a tree first");
+  if (!un || !vn || (c->T.dim == 3 && !wn))
+    return gfsb200_fail (GFSB200_ERR_ARG, "upload_field_prev: missing velocity component");
+  CK (cudaSetDevice (c->device));
+  const double * src[3] = { un, vn, wn };
+  const size_t bytes = (size_t) c->T.n_cells*sizeof (double);
+  for (int i = 0; i < c->T.dim; i++) {
+    if (!c->d_prev[i]) CK (cudaMalloc ((void **) &c->d_prev[i], bytes));
+    CK (cudaMemcpyAsync (c->d_prev[i], src[i], bytes, cudaMemcpyHostToDevice, c->stream));
+  }
+  const int vs = c->T.dim == 3 ? 4 : 2;
+  if (!c->F.vtx_prev)
+    CK (cudaMalloc ((void **) &c->F.vtx_prev, (size_t) (c->T.n_vertices ? c->T.n_vertices : 1)*vs*sizeof (double)));
+  if (!c->F.nodata_flag)
+    return gfsb200_fail (GFSB200_ERR_STATE, "upload_field_prev: upload the current field first");
+  for (int i = 0; i < 3; i++) c->F.uprev[i] = c->d_prev[i];
+  DevField tmp = c->F;
+  for (int i = 0; i < 3; i++) tmp.u[i] = c->d_prev[i];
+  tmp.vtx_val = c->F.vtx_prev;
+  gfsb200_launch_vertex_values (&c->T, &tmp, c->n_sm, c->stream);
+  CK (cudaGetLastError ());
+  c->have_prev = true;
   return GFSB200_OK;
 }
 
@@ -558,6 +597,7 @@ extern "C" void gfsb200_step_params_default (gfsb200_step_params * p)
   p->rho = 1.;
   p->cd_const = NAN;
   p->cl_const = NAN;
+  p->cm_const = NAN;
 }
 
 static int make_step (const gfsb200_step_params * p, DevStep * S)
@@ -569,8 +609,9 @@ static int make_step (const gfsb200_step_params * p, DevStep * S)
   S->dt = p->dt;
   S->n_forces = p->n_forces;
   for (int k = 0; k < p->n_forces; k++) {
-    if (p->force[k] < GFSB200_FORCE_DRAG || p->force[k] > GFSB200_FORCE_BUOY)
+    if (p->force[k] < GFSB200_FORCE_DRAG || p->force[k] > GFSB200_FORCE_ADDEDMASS)
       return gfsb200_fail (GFSB200_ERR_UNSUPPORTED, "force kind %d is not supported on the device", p->force[k]);
+    if (p->force[k] == GFSB200_FORCE_ADDEDMASS) S->mutates_mass = 1;
     S->forces |= (unsigned) p->force[k] << (4*k);
     if (p->force[k] != GFSB200_FORCE_BUOY) S->need_velocity = 1;
   }
@@ -578,10 +619,37 @@ static int make_step (const gfsb200_step_params * p, DevStep * S)
   S->inv_mu = p->mu != 0. ? 1./p->mu : 0.;
   for (int a = 0; a < 3; a++) S->g[a] = p->g[a];
   S->cd_const = p->cd_const; S->cl_const = p->cl_const;
+  S->cm_const = p->cm_const;
   return GFSB200_OK;
 }
 
 #define MAX_TIMED_EVENTS 16384
+
+/* GfsForceInertial / GfsForceAddedMass need the previous-step vertex table
+ * (gfsb200_upload_field_prev) and the per-leaf convective acceleration, which
+ * is rebuilt here once per field update, only when such a force is listed */
+static int prepare_inertial (gfsb200_ctx * c, const DevStep * S)
+{
+  bool need = false;
+  for (int k = 0; k < S->n_forces; k++) {
+    const unsigned kind = (S->forces >> (4*k)) & 15;
+    if (kind == GFSB200_FORCE_INERTIAL || kind == GFSB200_FORCE_ADDEDMASS) need = true;
+  }
+  if (!need) return GFSB200_OK;
+  if (!c->have_prev)
+    return gfsb200_fail (GFSB200_ERR_STATE, "GfsForceInertial/AddedMass: call gfsb200_upload_field_prev first");
+  if (!c->acc_valid) {
+    if (!c->F.acc) {
+      const int ws = c->T.dim == 3 ? 4 : 2;
+      CK (cudaMalloc ((void **) &c->F.acc, (size_t) c->T.n_cells*ws*sizeof (double)));
+      CK (cudaMemsetAsync (c->F.acc, 0, (size_t) c->T.n_cells*ws*sizeof (double), c->stream));
+    }
+    gfsb200_launch_convective (&c->T, &c->F, c->n_sm, c->stream);
+    CK (cudaGetLastError ());
+    c->acc_valid = true;
+  }
+  return GFSB200_OK;
+}
 
 static int timed_begin (gfsb200_ctx * c)
 {
@@ -613,6 +681,7 @@ extern "C" int gfsb200_step (gfsb200_ctx * c, const gfsb200_step_params * p)
   int r = make_step (p, &S);
   if (r) return r;
   CK (cudaSetDevice (c->device));
+  if ((r = prepare_inertial (c, &S))) return r;
   DevParticles P = particles_view (c);
   if ((r = timed_begin (c))) return r;
   if (S.n_forces == 0)
@@ -675,6 +744,9 @@ extern "C" int gfsb200_step_host (gfsb200_ctx * c, const gfsb200_step_params * p
     return gfsb200_fail (GFSB200_ERR_UNSUPPORTED, "step_host: tracer lists go through gfsb200_step");
   if (n == 0) return GFSB200_OK;
   CK (cudaSetDevice (c->device));
+  if (S.mutates_mass)
+    return gfsb200_fail (GFSB200_ERR_UNSUPPORTED, "step_host: GfsForceAddedMass rewrites mass; use the resident path");
+  if ((r = prepare_inertial (c, &S))) return r;
   if (chunk <= 0) chunk = 1 << 20;
   if (chunk > n) chunk = n;
   if ((r = ensure_host_pipeline (c, chunk))) return r;
@@ -856,6 +928,10 @@ static int deposit (gfsb200_ctx * c, const gfsb200_step_params * p, int what)
     if (r) return r;
   }
   CK (cudaSetDevice (c->device));
+  if (what & 2) {
+    int r = prepare_inertial (c, &S);
+    if (r) return r;
+  }
   const size_t n = c->T.n_cells;
   /* gfs_cell_reset on the leaves, then scatter */
   if (what & 1) CK (cudaMemsetAsync (c->deposit, 0, n*sizeof (double), c->stream));

@@ -215,6 +215,41 @@ vorticity_kernel (DevTree T, DevField fld)
   }
 }
 
+/* The cell-constant part of compute_inertial_force
+ * (modules/particulatecommon.c:296-300):
+ *   A_c = sum_c2  gfs_center_gradient (cell, c2, U_c) * U_c2 (cell) / size
+ * per leaf, stored like the vorticity table. */
+template <int DIM>
+__global__ void __launch_bounds__(256)
+convective_kernel (DevTree T, DevField fld)
+{
+  const int stride = gridDim.x*blockDim.x;
+  for (int cell = blockIdx.x*blockDim.x + threadIdx.x; cell < T.n_cells; cell += stride) {
+    const unsigned info = T.info[cell];
+    const bool box_leaf = (info & (GFSB200_CELL_LEAF | GFSB200_CELL_BOUNDARY)) == GFSB200_CELL_LEAF;
+    int64_t slot = cell;
+    if (T.lattice_n1 > 0) {
+      if (!box_leaf)
+	continue;
+      slot = gfsb200_lattice_index (DIM, T.top_start, T.lattice_n1 - 1, cell);
+    }
+    double a[3] = { 0., 0., 0. };
+    if (box_leaf) {
+      const double size = __longlong_as_double ((long long) (1023 - T.level[cell]) << 52);
+      for (int c = 0; c < DIM; c++)
+	for (int c2 = 0; c2 < DIM; c2++)
+	  a[c] += center_gradient<DIM> (T, fld.u[c], cell, c2)*fld.u[c2][cell]/size;
+    }
+    if (DIM == 2)
+      reinterpret_cast<double2 *> (fld.acc)[slot] = make_double2 (a[0], a[1]);
+    else {
+      double2 * o = reinterpret_cast<double2 *> (fld.acc + slot*4);
+      o[0] = make_double2 (a[0], a[1]);
+      o[1] = make_double2 (a[2], 0.);
+    }
+  }
+}
+
 /* gfs_cell_corner_value, src/fluid.c:3081-3101: val = sum w_i v_i in stencil
  * order.  (The GFS_NODATA early-out returns the *calling* leaf's own value,
  * which a shared vertex cannot represent: a vertex whose stencil touches
@@ -294,6 +329,38 @@ vertex_values_kernel (DevTree T, DevField fld)
 }
 
 } // namespace
+
+static int cell_grid (int64_t n, int n_sm)
+{
+  int64_t g = (n + 255)/256;
+  if (g > (int64_t) n_sm*16) g = (int64_t) n_sm*16;
+  return g < 1 ? 1 : (int) g;
+}
+
+static int64_t vertex_items (const DevTree * T)
+{
+  if (T->lattice_n1 <= 0) return T->n_vertices;
+  const int n1 = T->lattice_n1, b = T->dim == 3 ? 8 : 16;
+  return (int64_t) ((n1 + b - 1)/b)*((n1 + b - 1)/b)*(T->dim == 3 ? (n1 + 3)/4 : 1)*256;
+}
+
+/* vertex table of an arbitrary field triple (used for Un,Vn,Wn): fld->u / fld->vtx_val
+ * must already point at the source arrays / destination table */
+extern "C" void gfsb200_launch_vertex_values (const DevTree * T, const DevField * fld, int n_sm,
+					      cudaStream_t stream)
+{
+  const int g = cell_grid (vertex_items (T), n_sm);
+  if (T->dim == 2) vertex_values_kernel<2><<<g, 256, 0, stream>>> (*T, *fld);
+  else vertex_values_kernel<3><<<g, 256, 0, stream>>> (*T, *fld);
+}
+
+extern "C" void gfsb200_launch_convective (const DevTree * T, const DevField * fld, int n_sm,
+					   cudaStream_t stream)
+{
+  const int g = cell_grid (T->n_cells, n_sm);
+  if (T->dim == 2) convective_kernel<2><<<g, 256, 0, stream>>> (*T, *fld);
+  else convective_kernel<3><<<g, 256, 0, stream>>> (*T, *fld);
+}
 
 /* The two kernels are independent and each is latency-bound (dependent
  * index -> value gathers), so they are issued on two streams and overlap:

@@ -53,6 +53,11 @@ struct DevField {
   double * vort;               /* 3D: [..][4] (wx,wy,wz,pad); 2D: [..] (wz).  Indexed by cell, or on
 				  lattice trees by (kz*N + ky)*N + kx with N = lattice_n1 - 1 */
   int * nodata_flag;           /* set by the cell pass when any vertex stencil touches GFS_NODATA */
+  /* GfsForceInertial / GfsForceAddedMass only */
+  const double * uprev[3];     /* Un,Vn,Wn cell values */
+  double * vtx_prev;           /* their vertex table, laid out like vtx_val */
+  double * acc;                /* per leaf (u.grad)u at the cell centre, laid out like vort (3D: [..][4];
+				  2D: [..][2]) */
 };
 
 struct DevParticles {
@@ -73,6 +78,8 @@ struct DevStep {
   double inv_mu;               /* 1/mu for a constant viscosity (0 when mu == 0) */
   double g[3];
   double cd_const, cl_const;   /* NaN = built-in law */
+  double cm_const;             /* GfsForceAddedMass coefficient, NaN = 0.5 */
+  int mutates_mass;            /* a GfsForceAddedMass is in the list: mass is written back */
 };
 
 /* compact every third (second) bit of a Morton key back into an integer */

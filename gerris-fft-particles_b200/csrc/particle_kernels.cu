@@ -327,7 +327,7 @@ __device__ __forceinline__ void total_force (const DevTree & T, const DevField &
 					     const DevStep & S, const Located & L,
 					     double x, double y, double z,
 					     double vx, double vy, double vz,
-					     double mass, double volume,
+					     double & mass, double volume,
 					     double & Fx, double & Fy, double & Fz, double & rho_out)
 {
   const unsigned forces = PROG ? PROG : S.forces;
@@ -359,8 +359,8 @@ __device__ __forceinline__ void total_force (const DevTree & T, const DevField &
     rho = 1./fld.alpha[cell_index<DIM, LATTICE> (T, L)];
   rho_out = rho;
   double rx = 0., ry = 0., rz = 0.;
+  double u = 0., v = 0., w = 0.;
   if (need_velocity) {
-    double u, v, w;
     interpolate<DIM, LATTICE> (T, fld, L, x, y, z, u, v, w);
     rx = u - vx; ry = v - vy; rz = DIM == 3 ? w - vz : 0.;
   }
@@ -423,6 +423,37 @@ __device__ __forceinline__ void total_force (const DevTree & T, const DevField &
 	fy = -q*rx*wz;
       }
     }
+    else if (!PROG && (kind == GFSB200_FORCE_INERTIAL || kind == GFSB200_FORCE_ADDEDMASS)) {
+      /* compute_inertial_force, :255-303: rho ((u - u_old)/dt + (u.grad)u|cell); the
+	 convective part is cell-constant and comes from the acc table */
+      if (S.dt > 0.) {
+	DevField prev = fld;
+	prev.vtx_val = fld.vtx_prev;
+	prev.u[0] = fld.uprev[0]; prev.u[1] = fld.uprev[1]; prev.u[2] = fld.uprev[2];
+	double un, vn, wn;
+	interpolate<DIM, LATTICE> (T, prev, L, x, y, z, un, vn, wn);
+	const int64_t slot = leaf_slot<DIM, LATTICE> (T, L);
+	double ax, ay, az = 0.;
+	if (DIM == 3) {
+	  const double2 * p = reinterpret_cast<const double2 *> (fld.acc + slot*4);
+	  const double2 a = __ldg (p);
+	  ax = a.x; ay = a.y; az = __ldg (reinterpret_cast<const double *> (p + 1));
+	}
+	else {
+	  const double2 a = __ldg (reinterpret_cast<const double2 *> (fld.acc) + slot);
+	  ax = a.x; ay = a.y;
+	}
+	fx = rho*(u - un)/S.dt + rho*ax;
+	fy = rho*(v - vn)/S.dt + rho*ay;
+	if (DIM == 3) fz = rho*(w - wn)/S.dt + rho*az;
+      }
+      if (kind == GFSB200_FORCE_ADDEDMASS) {
+	const double cm = S.cm_const == S.cm_const ? S.cm_const : 0.5;
+	fx *= cm; fy *= cm; fz *= cm;
+	mass += rho*volume*cm;            /* the reference's cumulative update, :391 */
+      }
+      fx *= volume; fy *= volume; fz *= volume;
+    }
     else if (kind == GFSB200_FORCE_BUOY) {
       if (!ONFLUID) {                   /* compute_forces_onfluid skips GfsForceBuoy, :753-765 */
 	/* (m/V - rho) g V = (m - rho V) g */
@@ -449,7 +480,8 @@ step_kernel (DevTree T, DevField fld, DevParticles P, DevStep S)
      step and must not displace the vertex / vorticity tables from L1/L2 */
   double x = __ldcs (P.x + i), y = __ldcs (P.y + i), z = DIM == 3 ? __ldcs (P.z + i) : 0.;
   double vx = __ldcs (P.vx + i), vy = __ldcs (P.vy + i), vz = DIM == 3 ? __ldcs (P.vz + i) : 0.;
-  const double mass = __ldcs (P.mass + i), volume = __ldcs (P.volume + i);
+  double mass = __ldcs (P.mass + i);
+  const double volume = __ldcs (P.volume + i);
 
   const Located L = locate<DIM, LATTICE> (T, x, y, z);
   if (REC)
@@ -463,6 +495,8 @@ step_kernel (DevTree T, DevField fld, DevParticles P, DevStep S)
   if (REC) {
     P.fx[i] = Fx; P.fy[i] = Fy; P.fz[i] = Fz;
   }
+  if (!PROG && S.mutates_mass)
+    P.mass[i] = mass;
 
   /* x += v dt/2 ; v += F dt/m ; x += v dt/2   (:828-839) */
   const double hdt = 0.5*S.dt, dtm = S.dt*__drcp_rn (mass);
@@ -623,6 +657,8 @@ step_kernel_pipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_tile
 	double Fx, Fy, Fz, rho;
 	total_force<DIM, false, LATTICE, PROG> (T, fld, S, L, x, y, z, vx, vy, vz, mass, volume,
 					       Fx, Fy, Fz, rho);
+	if (!PROG && S.mutates_mass)
+	  P.mass[i] = mass;
 	const double hdt = 0.5*S.dt, dtm = S.dt*__drcp_rn (mass);
 	x = fma (vx, hdt, x); vx = fma (Fx, dtm, vx); x = fma (vx, hdt, x);
 	y = fma (vy, hdt, y); vy = fma (Fy, dtm, vy); y = fma (vy, hdt, y);
@@ -776,9 +812,12 @@ deposit_kernel (DevTree T, DevField fld, DevParticles P, DevStep S, double * __r
 	av = volume*inv_cellvol;
       if (FORCE) {
 	double Fx, Fy, Fz, rho;
+	double mass = __ldcs (P.mass + i);
 	total_force<DIM, true, LATTICE, PROG> (T, fld, S, L, x, y, z, __ldcs (P.vx + i), __ldcs (P.vy + i),
-					      DIM == 3 ? __ldcs (P.vz + i) : 0., __ldcs (P.mass + i), volume,
+					      DIM == 3 ? __ldcs (P.vz + i) : 0., mass, volume,
 					      Fx, Fy, Fz, rho);
+	if (!PROG && S.mutates_mass)       /* compute_forces_onfluid runs GfsForceAddedMass too */
+	  P.mass[i] = mass;
 	const double k = -inv_cellvol/rho;
 	ax = Fx*k; ay = Fy*k; az = Fz*k;
       }

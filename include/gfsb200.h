@@ -54,6 +54,8 @@ extern "C" {
 #define GFSB200_FORCE_DRAG 1        /* GfsForceDrag */
 #define GFSB200_FORCE_LIFT 2        /* GfsForceLift */
 #define GFSB200_FORCE_BUOY 3        /* GfsForceBuoy */
+#define GFSB200_FORCE_INERTIAL 4    /* GfsForceInertial   modules/particulatecommon.c:255-303 */
+#define GFSB200_FORCE_ADDEDMASS 5   /* GfsForceAddedMass  modules/particulatecommon.c:331-394 */
 #define GFSB200_MAX_FORCES 8
 
 const char * gfsb200_last_error (void);
@@ -163,6 +165,11 @@ int gfsb200_upload_field (gfsb200_ctx * c, const double * u, const double * v, c
 /* same, from device pointers */
 int gfsb200_set_field_device (gfsb200_ctx * c, const double * u, const double * v, const double * w,
 			      const double * alpha, const double * mu);
+/* Mirror the previous-step velocity Un,Vn(,Wn) kept by GfsForceInertial /
+ * GfsForceAddedMass (GfsForceCoeff.Uold, store_domain_previous_vel,
+ * modules/particulatecommon.c:99-113) and build its vertex table.  Needed only
+ * when one of those forces is in the list. */
+int gfsb200_upload_field_prev (gfsb200_ctx * c, const double * un, const double * vn, const double * wn);
 /* recompute vertex + vorticity tables from the resident field (the per-step
  * cell pass) */
 int gfsb200_refresh_field (gfsb200_ctx * c);
@@ -203,6 +210,7 @@ typedef struct {
   double cl_const;                 /* constant GfsForceLift coefficient function; NaN = 0.5 */
   int32_t record_cells;            /* 1: also store each particle's containing cell index */
   int32_t record_forces;           /* 1: also store the accumulated force (particulate->force) */
+  double cm_const;                 /* constant GfsForceAddedMass coefficient function; NaN = 0.5 */
 } gfsb200_step_params;
 
 void gfsb200_step_params_default (gfsb200_step_params * p);

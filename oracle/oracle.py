@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-FORCE_DRAG, FORCE_LIFT, FORCE_BUOY = 1, 2, 3
+FORCE_DRAG, FORCE_LIFT, FORCE_BUOY, FORCE_INERTIAL, FORCE_ADDEDMASS = 1, 2, 3, 4, 5
 
 
 class StepParams(C.Structure):
@@ -22,12 +22,13 @@ class StepParams(C.Structure):
         ("dt", C.c_double), ("n_forces", C.c_int), ("force", C.c_int * 8),
         ("rho", C.c_double), ("ivar_alpha", C.c_int), ("mu", C.c_double), ("ivar_mu", C.c_int),
         ("g", C.c_double * 3), ("cd_const", C.c_double), ("cl_const", C.c_double),
-        ("pattern", C.c_int),
+        ("pattern", C.c_int), ("ivar_uold", C.c_int), ("cm_const", C.c_double),
     ]
 
 
 def step_params(dt, forces, rho=1.0, mu=0.0, g=(0.0, 0.0, 0.0), cd_const=float("nan"),
-                cl_const=float("nan"), pattern=0, ivar_alpha=-1, ivar_mu=-1) -> StepParams:
+                cl_const=float("nan"), pattern=0, ivar_alpha=-1, ivar_mu=-1, ivar_uold=5,
+                cm_const=float("nan")) -> StepParams:
     p = StepParams()
     p.dt = dt
     p.n_forces = len(forces)
@@ -37,6 +38,7 @@ def step_params(dt, forces, rho=1.0, mu=0.0, g=(0.0, 0.0, 0.0), cd_const=float("
     for a in range(3):
         p.g[a] = float(g[a])
     p.cd_const, p.cl_const, p.pattern = cd_const, cl_const, pattern
+    p.ivar_uold, p.cm_const = ivar_uold, cm_const
     return p
 
 
@@ -73,6 +75,7 @@ def load(dim: int) -> C.CDLL:
         "ora_vorticity": (None, [vp, lng, vp, vp]),
         "ora_list_new": (vp, [lng] + [vp] * 8), "ora_list_destroy": (None, [vp]),
         "ora_list_size": (lng, [vp]), "ora_list_get": (None, [vp] + [vp] * 10),
+        "ora_list_get_mass": (None, [vp, vp]),
         "ora_list_cull": (lng, [vp, vp]),
         "ora_list_step": (None, [vp, vp, C.POINTER(StepParams), i32]),
         "ora_deposit_volume": (None, [vp, vp, i32]),
@@ -240,6 +243,8 @@ class ParticleList:
                                 _p(out["vy"]), _p(out["vz"]), _p(out["fx"]), _p(out["fy"]),
                                 _p(out["fz"]), _p(ids))
         out["id"] = ids
+        out["mass"] = np.empty(n)
+        self.sim.L.ora_list_get_mass(self.h, _p(out["mass"]))
         return out
 
     def deposit_volume(self, ivar):

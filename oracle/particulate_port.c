@@ -578,7 +578,8 @@ void ora_vorticity (OraSim * sim, long n, const uint64_t * cell, double * out)
 /* ------------------------------------------------------------------ */
 /* particles: src/particle.h:34-39, modules/particulatecommon.h:35-41    */
 
-enum { ORA_FORCE_DRAG = 1, ORA_FORCE_LIFT = 2, ORA_FORCE_BUOY = 3 };
+enum { ORA_FORCE_DRAG = 1, ORA_FORCE_LIFT = 2, ORA_FORCE_BUOY = 3,
+       ORA_FORCE_INERTIAL = 4, ORA_FORCE_ADDEDMASS = 5 };
 
 typedef struct {
   double dt;
@@ -593,6 +594,8 @@ typedef struct {
   double cl_const;     /* constant lift coefficient function, NaN = 0.5 */
   int pattern;         /* 0: reference call pattern (one locate + interpolation set per
 			  force, dead vliq evaluation), 1: fused (one locate) */
+  int ivar_uold;       /* first of the FTT_DIMENSION variables Un,Vn(,Wn) of GfsForceCoeff.Uold */
+  double cm_const;     /* constant GfsForceAddedMass coefficient function, NaN = 0.5 */
 } OraStepParams;
 
 typedef struct _OraParticulate OraParticulate;
@@ -759,9 +762,75 @@ static FttVector compute_buoyancy_force (OraCtx * ctx, OraParticulate * p)
   return force;
 }
 
+/* modules/particulatecommon.c:255-303 */
+static FttVector compute_inertial_force (OraCtx * ctx, OraParticulate * p)
+{
+  OraSim * sim = ctx->sim;
+  FttVector force = { 0., 0., 0., 0. };
+  FttComponent c;
+
+  FttCell * cell = domain_locate (sim, p->pos, -1);
+  if (cell == NULL) return force;
+
+  gdouble size = ftt_cell_size(cell);
+
+  gdouble fluid_rho = fluid_rho_at (ctx, cell);
+  GfsVariable * u[3] = { &sim->var[0], &sim->var[1], &sim->var[FTT_DIMENSION > 2 ? 2 : 1] };
+
+  FttVector fluid_vel = { 0., 0., 0., 0. };
+  for (c = 0; c < FTT_DIMENSION; c++)
+    (&fluid_vel.x)[c] = gfs_interpolate (cell, p->pos, u[c]);
+
+  FttVector fluid_veln = { 0., 0., 0., 0. };
+  for (c = 0; c < FTT_DIMENSION; c++)
+    (&fluid_veln.x)[c] = gfs_interpolate (cell, p->pos, &sim->var[ctx->par->ivar_uold + c]);
+
+  if(ctx->par->dt > 0.)
+    for (c = 0; c < FTT_DIMENSION; c++)
+      (&force.x)[c] = fluid_rho*((&fluid_vel.x)[c]-(&fluid_veln.x)[c])/ctx->par->dt;
+  else
+    return force;
+
+  FttComponent c2;
+  for(c = 0; c < FTT_DIMENSION; c++)
+    for(c2 = 0; c2 < FTT_DIMENSION; c2++)
+      (&force.x)[c] += fluid_rho*gfs_center_gradient(cell, c2, u[c]->i)*
+	GFS_VALUE(cell, u[c2])/size;
+
+  return force;
+}
+
+/* modules/particulatecommon.c:331-394, including the cumulative mass update (:391) */
+static FttVector compute_addedmass_force (OraCtx * ctx, OraParticulate * p)
+{
+  OraSim * sim = ctx->sim;
+  FttVector force = { 0., 0., 0., 0. };
+  FttComponent c;
+
+  FttCell * cell = domain_locate (sim, p->pos, -1);
+  if (cell == NULL) return force;
+
+  force = compute_inertial_force (ctx, p);
+
+  gdouble fluid_rho = fluid_rho_at (ctx, cell);
+
+  gdouble cm = 0.5;
+  if (ctx->par->cm_const == ctx->par->cm_const)
+    cm = ctx->par->cm_const;
+
+  for (c = 0; c < FTT_DIMENSION; c++)
+    (&force.x)[c] *= cm;
+
+  p->mass += fluid_rho*p->volume*cm;
+
+  return force;
+}
+
 static OraForceFunc force_func (int kind)
 {
   switch (kind) {
+  case ORA_FORCE_INERTIAL: return compute_inertial_force;
+  case ORA_FORCE_ADDEDMASS: return compute_addedmass_force;
   case ORA_FORCE_DRAG: return compute_drag_force;
   case ORA_FORCE_LIFT: return compute_lift_force;
   case ORA_FORCE_BUOY: return compute_buoyancy_force;
@@ -959,6 +1028,13 @@ void ora_list_destroy (OraList * l)
 }
 
 long ora_list_size (OraList * l) { return l->n; }
+
+void ora_list_get_mass (OraList * l, double * mass)
+{
+  long i;
+  for (i = 0; i < l->n; i++)
+    mass[i] = l->p[i]->mass;
+}
 
 void ora_list_get (OraList * l, double * x, double * y, double * z,
 		   double * vx, double * vy, double * vz,

@@ -11,7 +11,8 @@ pkg = entry.load_package()
 capi, worlds = pkg.capi, pkg.worlds
 ora = entry.load_oracle()
 
-FORCE_MAP = {capi.FORCE_DRAG: ora.FORCE_DRAG, capi.FORCE_LIFT: ora.FORCE_LIFT, capi.FORCE_BUOY: ora.FORCE_BUOY}
+FORCE_MAP = {capi.FORCE_DRAG: ora.FORCE_DRAG, capi.FORCE_LIFT: ora.FORCE_LIFT, capi.FORCE_BUOY: ora.FORCE_BUOY,
+             capi.FORCE_INERTIAL: ora.FORCE_INERTIAL, capi.FORCE_ADDEDMASS: ora.FORCE_ADDEDMASS}
 TREE_KEYS = ("parent", "child0", "neighbor", "level", "flags", "pos")
 
 

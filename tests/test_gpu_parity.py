@@ -463,3 +463,55 @@ def test_c1_full_config(ctx):
             worst = max(worst, max(helpers.vec_rel_err(got, want, k, same) for k in _vec_keys(2)))
     assert same.mean() >= 0.99, same.mean()
     assert worst <= 1e-9, worst          # documented drift bound after 1000 steps (measured ~1e-12)
+
+
+@pytest.mark.parametrize("kind", ["c1", "uniform3", "ring3", "ring3b"])
+@pytest.mark.parametrize("forces,kw", [
+    ((capi.FORCE_INERTIAL,), {}),
+    ((capi.FORCE_ADDEDMASS, capi.FORCE_DRAG, capi.FORCE_BUOY), {}),
+    ((capi.FORCE_DRAG, capi.FORCE_INERTIAL, capi.FORCE_ADDEDMASS, capi.FORCE_LIFT), dict(cm_const=0.3)),
+])
+def test_inertial_and_added_mass(kind, forces, kw, ctx):
+    """GfsForceInertial (:255-303) and GfsForceAddedMass (:331-394): previous-step
+    velocity Un,Vn,Wn through a second vertex table, (u.grad)u per leaf, and the
+    reference's cumulative mass += rho V cm, over three steps"""
+    w, sim, ptrs, idx = setup(kind, ctx)
+    a = w.arrays
+    rng = np.random.default_rng(21)
+    fields = [w.u, w.v] + ([w.w] if w.dim == 3 else [])
+    prev = [0.8 * f + 0.05 * rng.standard_normal(a.n_cells) for f in fields]
+    live = (a.flags & capi.CELL_DESTROYED) == 0
+    for c, f in enumerate(prev):
+        sim.set_values(5 + c, ptrs[live], f[live])
+    ctx.upload_field_prev(*prev)
+    w2 = worlds.World(**{**w.__dict__, "forces": forces, "g": (0.1, -1.0, 0.0)})
+    parts = worlds.make_particles(w2, 4000)
+    ctx.particles_upload(**parts)
+    plist = ora.ParticleList(sim, *[parts[k] for k in ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")])
+    opar = helpers.oracle_params(w2, ivar_uold=5, **kw)
+    par = w2.step_params(record_cells=True, record_forces=True, **kw)
+    for step in range(3):
+        plist.step(opar)
+        ctx.step(par)
+        got = ctx.particles_download(forces=True)
+        want = plist.get()
+        _check_state(got, want, w.dim, rtol=1e-12 if step == 0 else 1e-11)
+        assert np.abs(got["mass"] - want["mass"]).max() <= 1e-14 * np.abs(want["mass"]).max()
+        for k in ("fx", "fy", "fz"):
+            scale = max(np.abs(want[k]).max(), 1e-300)
+            assert np.abs(got[k] - want[k]).max() <= 1e-10 * scale, (step, k)
+    if capi.FORCE_ADDEDMASS in forces:
+        assert np.all(got["mass"] > parts["mass"])
+
+
+def test_inertial_needs_the_previous_field():
+    c = capi.Context(0)
+    try:
+        w = worlds.make_c2(level=3, n_particles=100)
+        c.upload_tree(w.tree)
+        c.upload_field(w.u, w.v, w.w)
+        c.particles_upload(**worlds.make_particles(w))
+        with pytest.raises(capi.GfsB200Error, match="upload_field_prev"):
+            c.step(capi.StepParams(1e-3, (capi.FORCE_INERTIAL,)))
+    finally:
+        c.close()
