@@ -21,9 +21,10 @@
  *   GfsParticulateField.event particulate_field_event    modules/particulatecommon.c:1934-1957
  *
  * and exports the same module symbols as modules/particulates.c:24-49.
- * A list that carries a force the device does not implement (GfsForceInertial,
- * GfsForceAddedMass, non-constant coefficient functions), or a domain with
- * solid boundaries, is handed back to the reference's own event untouched.
+ * A list that carries something the device does not implement (user force
+ * classes, non-constant coefficient / density / viscosity functions), or a
+ * domain with solid boundaries, is handed back to the reference's own event
+ * untouched.
  */
 #include <stdlib.h>
 #include <string.h>
@@ -43,6 +44,7 @@ typedef struct {
   guint adapt_created, adapt_removed;   /* mesh-change signature, src/simulation.h:49-51 */
   gboolean tree_valid;
   gdouble * field[3];                   /* host staging of U,V,W in flat order */
+  GfsVariable ** uold;                  /* GfsForceCoeff.Uold of an inertial / added-mass force, or NULL */
   gint32 n_cells;
   gboolean (* reference_event) (GfsEvent *, GfsSimulation *);
 } B200State;
@@ -129,6 +131,32 @@ static void mirror_velocity (B200State * s, GfsDomain * domain)
   if (gfsb200_upload_field (s->ctx, s->field[0], s->field[1], FTT_DIMENSION > 2 ? s->field[2] : NULL,
 			    NULL, NULL) != GFSB200_OK)
     g_error ("particulates (B200): %s", gfsb200_last_error ());
+  if (s->uold) {                          /* Un,Vn,Wn of GfsForceInertial / GfsForceAddedMass */
+    for (c = 0; c < FTT_DIMENSION; c++)
+      gfsb200_ftt_gather (s->map, offsetof (GfsStateVector, place_holder), s->uold[c]->i, GFS_NODATA,
+			  s->field[c]);
+    if (gfsb200_upload_field_prev (s->ctx, s->field[0], s->field[1],
+				   FTT_DIMENSION > 2 ? s->field[2] : NULL) != GFSB200_OK)
+      g_error ("particulates (B200): %s", gfsb200_last_error ());
+  }
+}
+
+/* store_domain_previous_vel, modules/particulatecommon.c:91-113 (static there) */
+static void copy_cell_variable (FttCell * cell, gpointer * data)
+{
+  GFS_VALUE (cell, (GfsVariable *) data[0]) = GFS_VALUE (cell, (GfsVariable *) data[1]);
+}
+
+static void store_previous_velocity (GfsDomain * domain, GfsVariable ** un)
+{
+  GfsVariable ** u = gfs_domain_velocity (domain);
+  FttComponent c;
+  for (c = 0; c < FTT_DIMENSION; c++) {
+    gpointer data[2] = { un[c], u[c] };
+    gfs_domain_cell_traverse (domain, FTT_PRE_ORDER, FTT_TRAVERSE_LEAFS, -1,
+			      (FttCellTraverseFunc) copy_cell_variable, data);
+    gfs_domain_bc (domain, FTT_TRAVERSE_LEAFS, -1, un[c]);
+  }
 }
 
 /* ------------------------------------------------------------------ */
@@ -165,6 +193,15 @@ static gboolean step_params (GfsParticleList * plist, GfsSimulation * sim, gfsb2
       p->force[p->n_forces++] = GFSB200_FORCE_DRAG;
       if (coeff->coefficient) p->cd_const = k;
     }
+    else if (GFS_IS_FORCE_ADDEDMASS (i->data)) {
+      p->force[p->n_forces++] = GFSB200_FORCE_ADDEDMASS;
+      if (coeff->coefficient) p->cm_const = k;
+      state_of (plist)->uold = coeff->Uold;
+    }
+    else if (GFS_IS_FORCE_INERTIAL (i->data)) {
+      p->force[p->n_forces++] = GFSB200_FORCE_INERTIAL;
+      state_of (plist)->uold = coeff->Uold;
+    }
     else if (GFS_IS_FORCE_LIFT (i->data)) {
       p->force[p->n_forces++] = GFSB200_FORCE_LIFT;
       if (coeff->coefficient) p->cl_const = k;
@@ -172,7 +209,7 @@ static gboolean step_params (GfsParticleList * plist, GfsSimulation * sim, gfsb2
     else if (GFS_IS_FORCE_BUOY (i->data))
       p->force[p->n_forces++] = GFSB200_FORCE_BUOY;
     else
-      return FALSE;                       /* GfsForceInertial, GfsForceAddedMass, user forces */
+      return FALSE;                       /* user-defined force classes */
     i = i->next;
   }
   /* fluid density 1/alpha (particulatecommon.c:534-535) */
@@ -244,15 +281,15 @@ static gint64 upload_particles (B200State * s, GfsParticleList * plist)
 static void download_particles (B200State * s, GfsParticleList * plist)
 {
   gint64 n = gfsb200_particles_count (s->ctx), k = 0;
-  gdouble * col[9];
+  gdouble * col[10];
   guint32 * id = g_malloc (sizeof (guint32)*(n ? n : 1));
   gint c;
   GSList * i = GFS_EVENT_LIST (plist)->list->items;
-  for (c = 0; c < 9; c++)
+  for (c = 0; c < 10; c++)
     col[c] = g_malloc (sizeof (gdouble)*(n ? n : 1));
   if (gfsb200_particles_download (s->ctx, col[0], col[1], FTT_DIMENSION > 2 ? col[2] : NULL,
 				  col[3], col[4], FTT_DIMENSION > 2 ? col[5] : NULL,
-				  col[6], col[7], col[8], NULL, NULL, id, NULL) != GFSB200_OK)
+				  col[6], col[7], col[8], col[9], NULL, id, NULL) != GFSB200_OK)
     g_error ("particulates (B200): %s", gfsb200_last_error ());
   while (i) {
     GSList * next = i->next;
@@ -262,6 +299,7 @@ static void download_particles (B200State * s, GfsParticleList * plist)
       p->pos.x = col[0][k]; p->pos.y = col[1][k];
       q->vel.x = col[3][k]; q->vel.y = col[4][k];
       q->force.x = col[6][k]; q->force.y = col[7][k];
+      q->mass = col[9][k];                 /* GfsForceAddedMass updates it every step (:391) */
 #if !FTT_2D
       p->pos.z = col[2][k]; q->vel.z = col[5][k]; q->force.z = col[8][k];
 #endif
@@ -273,7 +311,7 @@ static void download_particles (B200State * s, GfsParticleList * plist)
     }
     i = next;
   }
-  for (c = 0; c < 9; c++) g_free (col[c]);
+  for (c = 0; c < 10; c++) g_free (col[c]);
   g_free (id);
 }
 
@@ -308,6 +346,8 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
   download_particles (s, plist);
 
   gfs_particle_bc (plist);                                   /* :993, host side as in the reference */
+  if (s->uold)
+    store_previous_velocity (GFS_DOMAIN (sim), s->uold);     /* :1003-1012 */
   return TRUE;
 }
 
