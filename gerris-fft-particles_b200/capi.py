@@ -49,6 +49,7 @@ class StepParamsC(C.Structure):
         ("rho", C.c_double), ("mu", C.c_double), ("g", C.c_double * 3),
         ("cd_const", C.c_double), ("cl_const", C.c_double),
         ("record_cells", C.c_int32), ("record_forces", C.c_int32), ("cm_const", C.c_double),
+        ("track_escapes", C.c_int32),
     ]
 
 
@@ -81,6 +82,7 @@ def lib() -> C.CDLL:
         "gfsb200_tree_refine_ring": (i32, [vp, i32, i32, dbl, dbl]),
         "gfsb200_tree_corner_sweep": (i32, [vp]),
         "gfsb200_tree_add_boundary": (i32, [vp, i32, i32]),
+        "gfsb200_tree_set_periodic": (i32, [vp, i32, i32, i32]),
         "gfsb200_tree_finalize": (i32, [vp, vp]),
         "gfsb200_tree_build_stencils": (i32, [vp]),
         "gfsb200_tree_get_view": (i32, [vp, C.POINTER(TreeView)]),
@@ -106,6 +108,7 @@ def lib() -> C.CDLL:
         "gfsb200_particle_list_event": (i32, [vp, C.POINTER(StepParamsC), C.POINTER(i64)]),
         "gfsb200_step_host": (i32, [vp, C.POINTER(StepParamsC), i64] + [vp] * 8 + [i64]),
         "gfsb200_particles_cull": (i32, [vp, C.POINTER(i64)]),
+        "gfsb200_particle_bc": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
         "gfsb200_particles_sort": (i32, [vp]),
         "gfsb200_locate": (i32, [vp, i64, vp, vp, vp, vp]),
         "gfsb200_interpolate": (i32, [vp, i64, vp, vp, vp, vp, vp, vp]),
@@ -196,6 +199,10 @@ class Tree:
     def add_boundary(self, side: int, box_root: int = 0):
         _check(self._lib.gfsb200_tree_add_boundary(self.handle, box_root, side), "add_boundary")
 
+    def set_periodic(self, side: int, box_root: int = 0, matching_box_root: int = 0):
+        _check(self._lib.gfsb200_tree_set_periodic(self.handle, box_root, side, matching_box_root),
+               "set_periodic")
+
     def finalize(self) -> np.ndarray:
         # n_cells is only known through the view after finalize; over-allocate via a first call
         _check(self._lib.gfsb200_tree_finalize(self.handle, None), "finalize")
@@ -266,7 +273,7 @@ class StepParams:
     def __init__(self, dt: float, forces: Sequence[int] = (), rho: float = 1.0, mu: float = 0.0,
                  g: Sequence[float] = (0.0, 0.0, 0.0), cd_const: float = float("nan"),
                  cl_const: float = float("nan"), record_cells: bool = False, record_forces: bool = False,
-                 cm_const: float = float("nan")):
+                 cm_const: float = float("nan"), track_escapes: bool = False):
         self.c = StepParamsC()
         lib().gfsb200_step_params_default(C.byref(self.c))
         self.c.dt = dt
@@ -278,6 +285,7 @@ class StepParams:
             self.c.g[a] = float(g[a])
         self.c.cd_const, self.c.cl_const, self.c.cm_const = cd_const, cl_const, cm_const
         self.c.record_cells, self.c.record_forces = int(record_cells), int(record_forces)
+        self.c.track_escapes = int(track_escapes)
 
 
 class Context:
@@ -408,6 +416,12 @@ class Context:
         removed = C.c_int64(0)
         _check(self._lib.gfsb200_particles_cull(self.handle, C.byref(removed)), "particles_cull")
         return removed.value
+
+    def particle_bc(self):
+        """(wrapped, dropped) of gfs_particle_bc after a step with track_escapes"""
+        w, d = C.c_int64(0), C.c_int64(0)
+        _check(self._lib.gfsb200_particle_bc(self.handle, C.byref(w), C.byref(d)), "particle_bc")
+        return w.value, d.value
 
     def sort(self):
         _check(self._lib.gfsb200_particles_sort(self.handle), "particles_sort")

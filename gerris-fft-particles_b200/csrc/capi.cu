@@ -43,6 +43,8 @@ void gfsb200_launch_deposit (const DevTree *, const DevField *, const DevParticl
 			     int, double *, double *, double *, double *, cudaStream_t);
 void gfsb200_launch_gather (int64_t, const int32_t *, int, const double * const *, double * const *,
 			    const uint32_t *, uint32_t *, cudaStream_t);
+void gfsb200_launch_particle_bc (const DevTree *, const DevParticles *, int, const int32_t *,
+				 const double *, uint8_t *, int *, cudaStream_t);
 void gfsb200_launch_iota (int64_t, int32_t *, cudaStream_t);
 void gfsb200_launch_iota_u32 (int64_t, uint32_t *, uint32_t, cudaStream_t);
 void gfsb200_launch_sort_keys (int64_t, const int32_t *, uint32_t *, uint32_t, cudaStream_t);
@@ -63,7 +65,7 @@ struct gfsb200_ctx {
   /* tree */
   bool have_tree;
   DevTree T;
-  int32_t * d_child0, * d_neighbor, * d_la_slot, * d_vtx_off, * d_vtx_cell, * d_leaf_vtx;
+  int32_t * d_child0, * d_neighbor, * d_la_slot, * d_vtx_off, * d_vtx_cell, * d_leaf_vtx, * d_parent;
   uint8_t * d_level, * d_info;
   double * d_vtx_w, * d_vtx_wuni;
   /* field */
@@ -87,6 +89,12 @@ struct gfsb200_ctx {
   void * cub_tmp;
   size_t cub_tmp_bytes;
   double ** d_ptr_table;       /* [2][NCOL] device copy of col pointers */
+  /* escape tracking for gfs_particle_bc */
+  int * esc_count;             /* [3]: escaped, wrapped, dropped */
+  int32_t * esc_idx;
+  double * esc_old;
+  int esc_cap;
+  bool esc_armed;              /* the last step tracked escapes */
   /* host-list pipeline (gfsb200_step_host) */
   double * hp_col[3][NCOL];
   int64_t hp_chunk;
@@ -120,7 +128,8 @@ static int dev_alloc_copy (Tp ** dst, const Tp * src, size_t n, cudaStream_t st)
 static void free_tree (gfsb200_ctx * c)
 {
   cudaFree (c->d_child0); cudaFree (c->d_neighbor); cudaFree (c->d_la_slot);
-  cudaFree (c->d_vtx_off); cudaFree (c->d_vtx_cell); cudaFree (c->d_leaf_vtx);
+  cudaFree (c->d_vtx_off); cudaFree (c->d_vtx_cell); cudaFree (c->d_leaf_vtx); cudaFree (c->d_parent);
+  c->d_parent = NULL;
   cudaFree (c->d_level); cudaFree (c->d_info); cudaFree (c->d_vtx_w); cudaFree (c->d_vtx_wuni);
   c->d_child0 = c->d_neighbor = c->d_la_slot = c->d_vtx_off = c->d_vtx_cell = c->d_leaf_vtx = NULL;
   c->d_level = c->d_info = NULL; c->d_vtx_w = c->d_vtx_wuni = NULL;
@@ -147,6 +156,8 @@ static void free_particles (gfsb200_ctx * c)
   c->cell = c->perm = c->perm2 = NULL; c->key = c->key2 = NULL; c->flag = NULL; c->cub_tmp = NULL;
   c->cub_tmp_bytes = 0;
   c->n = c->cap = c->aux_cap = 0;
+  cudaFree (c->esc_count); cudaFree (c->esc_idx); cudaFree (c->esc_old);
+  c->esc_count = NULL; c->esc_idx = NULL; c->esc_old = NULL; c->esc_cap = 0; c->esc_armed = false;
 }
 
 extern "C" int gfsb200_ctx_create (int device, gfsb200_ctx ** out)
@@ -174,7 +185,8 @@ extern "C" int gfsb200_ctx_create (int device, gfsb200_ctx ** out)
   c->n_sm = prop.multiProcessorCount;
   c->have_tree = c->have_field = c->own_field = false;
   c->d_child0 = c->d_neighbor = c->d_la_slot = c->d_vtx_off = c->d_vtx_cell = c->d_leaf_vtx = NULL;
-  c->d_level = c->d_info = NULL; c->d_vtx_w = c->d_vtx_wuni = NULL;
+  c->d_level = c->d_info = NULL; c->d_vtx_w = c->d_vtx_wuni = NULL; c->d_parent = NULL;
+  c->esc_count = NULL; c->esc_idx = NULL; c->esc_old = NULL; c->esc_cap = 0; c->esc_armed = false;
   for (int i = 0; i < 5; i++) c->d_field[i] = NULL;
   for (int i = 0; i < 3; i++) c->d_prev[i] = NULL;
   c->have_prev = c->acc_valid = false;
@@ -284,6 +296,7 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
   if ((r = dev_alloc_copy (&c->d_vtx_w, (const double *) t->vtx_w, ne, c->stream))) return r;
   if ((r = dev_alloc_copy (&c->d_vtx_wuni, (const double *) wuni.data (), (size_t) t->n_vertices, c->stream))) return r;
   if ((r = dev_alloc_copy (&c->d_leaf_vtx, (const int32_t *) t->leaf_vtx, (size_t) n*nc, c->stream))) return r;
+  if ((r = dev_alloc_copy (&c->d_parent, (const int32_t *) t->parent, (size_t) n, c->stream))) return r;
   CK (cudaStreamSynchronize (c->stream));   /* host staging vectors go out of scope */
 
   DevTree & T = c->T;
@@ -309,6 +322,10 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
   T.n_vertices = t->n_vertices;
   T.vtx_off = c->d_vtx_off; T.vtx_cell = c->d_vtx_cell; T.vtx_w = c->d_vtx_w; T.leaf_vtx = c->d_leaf_vtx;
   T.vtx_wuni = c->d_vtx_wuni;
+  T.parent = c->d_parent;
+  for (int rr = 0; rr < GFSB200_MAX_DEV_ROOTS; rr++)
+    for (int d = 0; d < 6; d++)
+      T.periodic[rr][d] = rr < t->n_roots ? (signed char) t->periodic[rr][d] : -1;
   T.lattice_n1 = 0;
   if (t->lattice_level >= 0 && t->lattice_level - t->root_level == T.top_levels && T.single_box &&
       !getenv ("GFSB200_NO_LATTICE"))
@@ -682,6 +699,23 @@ extern "C" int gfsb200_step (gfsb200_ctx * c, const gfsb200_step_params * p)
   if (r) return r;
   CK (cudaSetDevice (c->device));
   if ((r = prepare_inertial (c, &S))) return r;
+  c->esc_armed = false;
+  if (p->track_escapes && S.n_forces > 0) {
+    /* room for 1/16 of the list (+1024) to leave the domain in one step */
+    const int want = (int) (c->n/16 + 1024);
+    if (want > c->esc_cap) {
+      cudaFree (c->esc_idx); cudaFree (c->esc_old);
+      c->esc_idx = NULL; c->esc_old = NULL; c->esc_cap = 0;
+      CK (cudaMalloc ((void **) &c->esc_idx, want*sizeof (int32_t)));
+      CK (cudaMalloc ((void **) &c->esc_old, (size_t) want*3*sizeof (double)));
+      c->esc_cap = want;
+    }
+    if (!c->esc_count) CK (cudaMalloc ((void **) &c->esc_count, 3*sizeof (int)));
+    CK (cudaMemsetAsync (c->esc_count, 0, 3*sizeof (int), c->stream));
+    S.track_escapes = 1;
+    S.esc_cap = c->esc_cap; S.esc_count = c->esc_count; S.esc_idx = c->esc_idx; S.esc_old = c->esc_old;
+    c->esc_armed = true;
+  }
   DevParticles P = particles_view (c);
   if ((r = timed_begin (c))) return r;
   if (S.n_forces == 0)
@@ -852,12 +886,55 @@ extern "C" int gfsb200_particles_cull (gfsb200_ctx * c, int64_t * n_removed)
   return apply_permutation (c, kept);
 }
 
+extern "C" int gfsb200_particle_bc (gfsb200_ctx * c, int64_t * n_wrapped, int64_t * n_dropped)
+{
+  if (n_wrapped) *n_wrapped = 0;
+  if (n_dropped) *n_dropped = 0;
+  if (!c || !c->have_tree) return gfsb200_fail (GFSB200_ERR_STATE, "particle_bc: no tree");
+  if (!c->esc_armed)
+    return gfsb200_fail (GFSB200_ERR_STATE, "particle_bc: the last step did not track escapes");
+  CK (cudaSetDevice (c->device));
+  c->esc_armed = false;
+  int counts[3] = { 0, 0, 0 };
+  CK (cudaMemcpyAsync (counts, c->esc_count, sizeof (int), cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  if (counts[0] == 0) return GFSB200_OK;
+  if (counts[0] > c->esc_cap)
+    return gfsb200_fail (GFSB200_ERR_STATE, "particle_bc: %d particles left the domain in one step, more "
+			 "than the %d tracked (1/16 of the list)", counts[0], c->esc_cap);
+  DevParticles P = particles_view (c);
+  CK (cudaMemsetAsync (c->flag, 1, (size_t) P.n, c->stream));
+  gfsb200_launch_particle_bc (&c->T, &P, counts[0], c->esc_idx, c->esc_old, c->flag, c->esc_count + 1,
+			      c->stream);
+  CK (cudaGetLastError ());
+  CK (cudaMemcpyAsync (counts, c->esc_count, 3*sizeof (int), cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  if (n_wrapped) *n_wrapped = counts[1];
+  if (n_dropped) *n_dropped = counts[2];
+  if (counts[2] == 0) return GFSB200_OK;
+  /* compact the list without the dropped particles (order kept) */
+  gfsb200_launch_iota (P.n, c->perm, c->stream);
+  size_t bytes = 0;
+  CK (gfsb200_cub_select_flagged (NULL, &bytes, c->perm, c->flag, c->perm2, c->d_count, P.n, c->stream));
+  int r = ensure_cub_tmp (c, bytes);
+  if (r) return r;
+  CK (gfsb200_cub_select_flagged (c->cub_tmp, &bytes, c->perm, c->flag, c->perm2, c->d_count, P.n, c->stream));
+  return apply_permutation (c, P.n - counts[2]);
+}
+
 extern "C" int gfsb200_particle_list_event (gfsb200_ctx * c, const gfsb200_step_params * p,
 					    int64_t * n_removed)
 {
-  int r = gfsb200_particles_cull (c, n_removed);
+  if (!p) return gfsb200_fail (GFSB200_ERR_ARG, "null step parameters");
+  int64_t culled = 0, dropped = 0;
+  int r = gfsb200_particles_cull (c, &culled);
   if (r) return r;
-  return gfsb200_step (c, p);
+  gfsb200_step_params q = *p;
+  q.track_escapes = q.n_forces > 0;
+  if ((r = gfsb200_step (c, &q))) return r;
+  if (q.track_escapes && (r = gfsb200_particle_bc (c, NULL, &dropped))) return r;
+  if (n_removed) *n_removed = culled + dropped;
+  return GFSB200_OK;
 }
 
 /* ------------------------------------------------------------------ */

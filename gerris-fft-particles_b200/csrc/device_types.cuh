@@ -33,6 +33,8 @@ struct DevTree {
   const int32_t * neighbor;    /* [n_cells][2*dim] */
   const uint8_t * level;       /* absolute level */
   const uint8_t * info;        /* flags (low 3 bits) | CELL_REGULAR | child id << 4 */
+  const int32_t * parent;      /* [n_cells], -1 for roots */
+  signed char periodic[GFSB200_MAX_DEV_ROOTS][6];   /* box root, side -> matching box root or -1 */
   /* stencils */
   int n_vertices;
   const int32_t * vtx_off;
@@ -80,6 +82,12 @@ struct DevStep {
   double cd_const, cl_const;   /* NaN = built-in law */
   double cm_const;             /* GfsForceAddedMass coefficient, NaN = 0.5 */
   int mutates_mass;            /* a GfsForceAddedMass is in the list: mass is written back */
+  /* escape tracking for gfs_particle_bc */
+  int track_escapes;
+  int esc_cap;
+  int * esc_count;
+  int32_t * esc_idx;           /* [esc_cap] particle index */
+  double * esc_old;            /* [esc_cap][3] position before the step */
 };
 
 /* compact every third (second) bit of a Morton key back into an integer */

@@ -122,8 +122,10 @@ int gfsb200_tree_add_root (gfsb200_tree * t, const double pos[3], int level, int
   t->root_level = level;
   if (is_box) t->n_box_roots++;
   t->root_is_box[r] = is_box != 0;
-  for (int d = 0; d < 6; d++)
+  for (int d = 0; d < 6; d++) {
     t->root_nb[r][d] = -1;
+    t->periodic[r][d] = -1;
+  }
   int32_t i = t->n_cells++;
   t->parent[i] = -1;
   t->child0[i] = -1;
@@ -141,6 +143,18 @@ int gfsb200_tree_link_roots (gfsb200_tree * t, int r0, int d, int r1)
   t->root_nb[r0][d] = r1;
   t->root_nb[r1][d ^ 1] = r0;
   free_final (t);
+  return GFSB200_OK;
+}
+
+int gfsb200_tree_set_periodic (gfsb200_tree * t, int box_root, int side, int matching_box_root)
+{
+  if (!t || box_root < 0 || box_root >= t->n_box_roots || side < 0 || side >= t->ndir ||
+      matching_box_root < 0 || matching_box_root >= t->n_box_roots)
+    return gfsb200_fail (GFSB200_ERR_ARG, "set_periodic: bad argument");
+  if (t->root_nb[box_root][side] < 0 || t->root_is_box[t->root_nb[box_root][side]])
+    return gfsb200_fail (GFSB200_ERR_STATE, "set_periodic: side %d of box %d has no boundary (ghost) tree",
+			 side, box_root);
+  t->periodic[box_root][side] = matching_box_root;
   return GFSB200_OK;
 }
 
@@ -448,8 +462,10 @@ int gfsb200_tree_add_boundary (gfsb200_tree * t, int box_root, int side)
   t->pos[3*nr + (side >> 1)] += (side & 1 ? -1. : 1.)*size;
   t->n_roots = nr + 1;
   t->root_is_box[nr] = 0;
-  for (int d = 0; d < 6; d++)
+  for (int d = 0; d < 6; d++) {
     t->root_nb[nr][d] = -1;
+    t->periodic[nr][d] = -1;
+  }
   t->root_nb[nr][side ^ 1] = box_root;
   t->root_nb[box_root][side] = nr;
   return match_ghost (t, nr, box_root, side ^ 1);

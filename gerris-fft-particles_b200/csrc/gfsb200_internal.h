@@ -26,6 +26,8 @@ struct gfsb200_tree {
   int n_roots, n_box_roots, root_level;
   uint8_t root_is_box[GFSB200_MAX_ROOTS];
   int32_t root_nb[GFSB200_MAX_ROOTS][6];
+  int32_t periodic[GFSB200_MAX_ROOTS][6];   /* box root, side -> matching box root of a
+					       GfsBoundaryPeriodic, or -1 */
   /* finalized */
   int32_t * neighbor;            /* [n][ndir] */
   int32_t * level_start;

@@ -169,6 +169,56 @@ __device__ __forceinline__ Located locate (const DevTree & T, double x, double y
   return L;
 }
 
+/* is p inside some GfsBox root (locate array slot + inclusive root test)?  For
+ * trees without destroyed box cells this is exactly gfs_domain_locate != NULL. */
+template <int DIM>
+__device__ __forceinline__ bool in_domain (const DevTree & T, double x, double y, double z)
+{
+  int root = 0;
+  if (T.single_box) {
+    const double tx = (x - T.la_min[0])*T.la_inv_h, ty = (y - T.la_min[1])*T.la_inv_h;
+    const double tz = DIM == 3 ? (z - T.la_min[2])*T.la_inv_h : 0.;
+    if (!(tx >= 0. && tx < 1. && ty >= 0. && ty < 1. && tz >= 0. && tz < 1.))
+      return false;
+  }
+  else {
+    if (!(x == x && y == y && z == z))
+      return false;
+    int ix = (int) floor ((x - T.la_min[0])*T.la_inv_h);
+    int iy = (int) floor ((y - T.la_min[1])*T.la_inv_h);
+    if (ix < 0 || ix >= T.la_n[0] || iy < 0 || iy >= T.la_n[1])
+      return false;
+    int index = ix*T.la_n[1] + iy;
+    if (DIM == 3) {
+      int iz = (int) floor ((z - T.la_min[2])*T.la_inv_h);
+      if (iz < 0 || iz >= T.la_n[2])
+	return false;
+      index = index*T.la_n[2] + iz;
+    }
+    root = T.la_slot[index];
+    if (root < 0)
+      return false;
+  }
+  const double cx = T.root_pos[root][0], cy = T.root_pos[root][1], cz = DIM == 3 ? T.root_pos[root][2] : 0.;
+  const double half = 0.5*T.root_size;
+  return !(x > cx + half || x < cx - half || y > cy + half || y < cy - half ||
+	   (DIM == 3 && (z > cz + half || z < cz - half)));
+}
+
+/* remember a particle that is about to leave the domain; its position before
+ * the step is still in global memory at this point */
+template <int DIM>
+__device__ __forceinline__ void record_escape (const DevStep & S, const DevParticles & P, int64_t i)
+{
+  const int k = atomicAdd (S.esc_count, 1);
+  if (k < S.esc_cap) {
+    S.esc_idx[k] = (int32_t) i;
+    S.esc_old[3*k] = P.x[i];
+    S.esc_old[3*k + 1] = P.y[i];
+    S.esc_old[3*k + 2] = DIM == 3 ? P.z[i] : 0.;
+  }
+}
+
 /* flat cell index of a located leaf (lattice trees: rebuilt from the columns) */
 template <int DIM, bool LATTICE>
 __device__ __forceinline__ int cell_index (const DevTree & T, const Located & L)
@@ -502,9 +552,13 @@ step_kernel (DevTree T, DevField fld, DevParticles P, DevStep S)
   const double hdt = 0.5*S.dt, dtm = S.dt*__drcp_rn (mass);
   x = fma (vx, hdt, x); vx = fma (Fx, dtm, vx); x = fma (vx, hdt, x);
   y = fma (vy, hdt, y); vy = fma (Fy, dtm, vy); y = fma (vy, hdt, y);
-  __stcs (P.x + i, x); __stcs (P.y + i, y); __stcs (P.vx + i, vx); __stcs (P.vy + i, vy);
   if (DIM == 3) {
     z = fma (vz, hdt, z); vz = fma (Fz, dtm, vz); z = fma (vz, hdt, z);
+  }
+  if (S.track_escapes && !in_domain<DIM> (T, x, y, z))
+    record_escape<DIM> (S, P, i);
+  __stcs (P.x + i, x); __stcs (P.y + i, y); __stcs (P.vx + i, vx); __stcs (P.vy + i, vy);
+  if (DIM == 3) {
     __stcs (P.z + i, z); __stcs (P.vz + i, vz);
   }
 }
@@ -662,9 +716,13 @@ step_kernel_pipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_tile
 	const double hdt = 0.5*S.dt, dtm = S.dt*__drcp_rn (mass);
 	x = fma (vx, hdt, x); vx = fma (Fx, dtm, vx); x = fma (vx, hdt, x);
 	y = fma (vy, hdt, y); vy = fma (Fy, dtm, vy); y = fma (vy, hdt, y);
-	__stcs (P.x + i, x); __stcs (P.y + i, y); __stcs (P.vx + i, vx); __stcs (P.vy + i, vy);
 	if (DIM == 3) {
 	  z = fma (vz, hdt, z); vz = fma (Fz, dtm, vz); z = fma (vz, hdt, z);
+	}
+	if (S.track_escapes && !in_domain<DIM> (T, x, y, z))
+	  record_escape<DIM> (S, P, i);
+	__stcs (P.x + i, x); __stcs (P.y + i, y); __stcs (P.vx + i, vx); __stcs (P.vy + i, vy);
+	if (DIM == 3) {
 	  __stcs (P.z + i, z); __stcs (P.vz + i, vz);
 	}
       }
@@ -830,6 +888,103 @@ deposit_kernel (DevTree T, DevField fld, DevParticles P, DevStep S, double * __r
     run_atomic_add (f1, cell, ay);
     if (DIM == 3)
       run_atomic_add (f2, cell, az);
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/* gfs_particle_bc on the escaped particles                             */
+
+/* check_intersetion, modules/particulatecommon.c:3058-3148: the first face
+ * direction d (in order) through which the segment p0 -> p1 leaves the cell */
+template <int DIM>
+__device__ __forceinline__ int exit_face (const double c[3], double size, const double p0[3],
+					  const double p1[3])
+{
+  for (int d = 0; d < 2*DIM; d++) {
+    const double normal = d & 1 ? -1. : 1.;
+    const int a = d >> 1;
+    const double dp = p1[a] - p0[a];
+    if (dp != 0. && normal*dp > 0.) {
+      const double t = (c[a] + normal*size*0.5 - p0[a])/dp;
+      bool ok = t*(t - 1.) <= 0.;
+      for (int b = 0; b < DIM; b++)
+	if (b != a) {
+	  const double q = p0[b] + t*(p1[b] - p0[b]);
+	  ok = ok && (q - c[b] + size*0.5)*(q - c[b] - size*0.5) <= 0.;
+	}
+      if (ok)
+	return d;
+    }
+  }
+  return -1;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(128)
+particle_bc_kernel (DevTree T, DevParticles P, int n_esc, const int32_t * __restrict__ esc_idx,
+		    const double * __restrict__ esc_old, uint8_t * __restrict__ keep,
+		    int * __restrict__ counters /* [0] wrapped, [1] dropped */)
+{
+  const int k = blockIdx.x*blockDim.x + threadIdx.x;
+  if (k >= n_esc)
+    return;
+  const int64_t i = esc_idx[k];
+  const double p0[3] = { esc_old[3*k], esc_old[3*k + 1], esc_old[3*k + 2] };
+  double p1[3] = { P.x[i], P.y[i], DIM == 3 ? P.z[i] : 0. };
+  /* boundarycell, :3151-3186: walk from the cell of pos_old along the path */
+  const Located L = locate<DIM> (T, p0[0], p0[1], p0[2]);
+  int d = -1;
+  int cell = L.cell;
+  if (cell >= 0) {
+    double c[3] = { L.cx, L.cy, L.cz };
+    double size = 2.*L.half;
+    for (int it = 0; it < 4096; it++) {
+      d = exit_face<DIM> (c, size, p0, p1);
+      if (d < 0)
+	break;
+      const int nb = T.neighbor[(int64_t) cell*(2*DIM) + d];
+      if (nb < 0 || (T.info[nb] & GFSB200_CELL_BOUNDARY))
+	break;
+      /* centre of the neighbour: same level, or one level coarser */
+      const double dir = d & 1 ? -1. : 1.;
+      if (T.level[nb] == T.level[cell])
+	c[d >> 1] += dir*size;
+      else {
+	const int n = T.info[cell] >> 4;            /* child id: where `cell` sits in its parent */
+	c[0] -= (n & 1 ? 1. : -1.)*size*0.5;
+	c[1] -= (n & 2 ? -1. : 1.)*size*0.5;
+	if (DIM == 3) c[2] -= (n & 4 ? -1. : 1.)*size*0.5;
+	size *= 2.;
+	c[d >> 1] += dir*size;
+      }
+      cell = nb;
+    }
+  }
+  int match = -1, root = -1;
+  if (cell >= 0 && d >= 0) {
+    root = cell;
+    while (T.parent[root] >= 0)
+      root = T.parent[root];
+    match = T.periodic[root][d];
+  }
+  if (match >= 0) {
+    /* periodic_bc_particle, :3189-3214 */
+    const int a = d >> 1;
+    const double normal = d & 1 ? -1. : 1.;
+    const double size = T.root_size;
+    const double box_face = T.root_pos[root][a] + normal*size/2.;
+    const double box_face_nbr = T.root_pos[match][a] - normal*size/2.;
+    const double tolerance = size/1.e8;
+    const double distance = (p1[a] - box_face)*normal;
+    p1[a] = box_face_nbr + distance + normal*tolerance;
+    if (a == 0) P.x[i] = p1[0];
+    else if (a == 1) P.y[i] = p1[1];
+    else P.z[i] = p1[2];
+    atomicAdd (counters, 1);
+  }
+  else {
+    keep[i] = 0;
+    atomicAdd (counters + 1, 1);
   }
 }
 
@@ -1020,6 +1175,17 @@ void gfsb200_launch_deposit (const DevTree * T, const DevField * F, const DevPar
 #undef DEP_PR
 #undef DEP_W
 #undef DEP
+}
+
+void gfsb200_launch_particle_bc (const DevTree * T, const DevParticles * P, int n_esc,
+				 const int32_t * esc_idx, const double * esc_old, uint8_t * keep,
+				 int * counters, cudaStream_t st)
+{
+  if (n_esc <= 0) return;
+  if (T->dim == 3)
+    particle_bc_kernel<3><<<(n_esc + 127)/128, 128, 0, st>>> (*T, *P, n_esc, esc_idx, esc_old, keep, counters);
+  else
+    particle_bc_kernel<2><<<(n_esc + 127)/128, 128, 0, st>>> (*T, *P, n_esc, esc_idx, esc_old, keep, counters);
 }
 
 void gfsb200_launch_gather (int64_t n, const int32_t * perm, int ncols, const double * const * src,

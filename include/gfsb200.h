@@ -101,6 +101,11 @@ int gfsb200_tree_corner_sweep (gfsb200_tree * t);
  * boundary_match, src/boundary.c:652-685; call after all refinement */
 int gfsb200_tree_add_boundary (gfsb200_tree * t, int box_root, int side);
 
+/* the GfsBoundary on `side` of box root `box_root` is a GfsBoundaryPeriodic whose
+ * matching box is `matching_box_root` (src/boundary.c:1500-1532); used by
+ * gfsb200_particle_bc.  Call after add_boundary / link_roots. */
+int gfsb200_tree_set_periodic (gfsb200_tree * t, int box_root, int side, int matching_box_root);
+
 /* Reorders to level order, builds neighbour tables, centres, locate array.
  * perm (may be NULL, else n_cells ints) receives old index -> new index. */
 int gfsb200_tree_finalize (gfsb200_tree * t, int32_t * perm);
@@ -211,6 +216,8 @@ typedef struct {
   int32_t record_cells;            /* 1: also store each particle's containing cell index */
   int32_t record_forces;           /* 1: also store the accumulated force (particulate->force) */
   double cm_const;                 /* constant GfsForceAddedMass coefficient function; NaN = 0.5 */
+  int32_t track_escapes;           /* 1: remember which particles left the domain (with their
+				      previous position) for gfsb200_particle_bc */
 } gfsb200_step_params;
 
 void gfsb200_step_params_default (gfsb200_step_params * p);
@@ -233,10 +240,19 @@ int gfsb200_step_host (gfsb200_ctx * c, const gfsb200_step_params * p, int64_t n
 		       const double * mass, const double * volume, int64_t chunk);
 
 /* gfs_particle_list_event: cull particles outside the domain
- * (remove_particles_not_in_domain), then step.  *n_removed may be NULL. */
+ * (remove_particles_not_in_domain), step, then gfs_particle_bc (periodic wrap /
+ * drop).  *n_removed (may be NULL) counts the culled and the dropped. */
 int gfsb200_particle_list_event (gfsb200_ctx * c, const gfsb200_step_params * p,
 				 int64_t * n_removed);
 int gfsb200_particles_cull (gfsb200_ctx * c, int64_t * n_removed);
+/* gfs_particle_bc (modules/particulatecommon.c:3375-3395) for the particles that
+ * left the domain during the LAST gfsb200_step issued with track_escapes = 1
+ * (gfsb200_particle_list_event always tracks): the exit face is found by the
+ * reference's cell-to-cell ray walk (boundarycell / check_intersetion,
+ * :3058-3186); a particle leaving through a periodic side is wrapped
+ * (periodic_bc_particle :3189-3214), any other is dropped from the list.
+ * Unlike the reference, wrapped particles keep their place in the list. */
+int gfsb200_particle_bc (gfsb200_ctx * c, int64_t * n_wrapped, int64_t * n_dropped);
 /* re-sort resident particles by containing cell (Morton-ordered flat index)
  * so that neighbouring threads gather neighbouring cells */
 int gfsb200_particles_sort (gfsb200_ctx * c);

@@ -77,6 +77,7 @@ def load(dim: int) -> C.CDLL:
         "ora_list_size": (lng, [vp]), "ora_list_get": (None, [vp] + [vp] * 10),
         "ora_list_get_mass": (None, [vp, vp]),
         "ora_list_cull": (lng, [vp, vp]),
+        "ora_list_bc": (lng, [vp, vp, C.c_uint]),
         "ora_list_step": (None, [vp, vp, C.POINTER(StepParams), i32]),
         "ora_deposit_volume": (None, [vp, vp, i32]),
         "ora_deposit_force": (None, [vp, vp, C.POINTER(StepParams), i32]),
@@ -228,6 +229,10 @@ class ParticleList:
 
     def cull(self):
         return self.sim.L.ora_list_cull(self.sim.h, self.h)
+
+    def bc(self, periodic_mask=0):
+        """gfs_particle_bc: wrap through periodic sides (bit d of the mask), drop the rest"""
+        return self.sim.L.ora_list_bc(self.sim.h, self.h, periodic_mask)
 
     def step(self, params: StepParams, nthreads=1):
         self.sim.L.ora_list_step(self.sim.h, self.h, C.byref(params), nthreads)

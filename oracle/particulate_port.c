@@ -21,6 +21,7 @@
  *   GfsParticulateField deposit          modules/particulatecommon.c:1929-1957
  *   force deposit (single-cell limit)    modules/particulatecommon.c:753-765, 2158-2228
  *   passive tracer advection             src/particle.c:31-44, src/domain.c:2764-2788
+ *   particle BCs (periodic wrap / drop)  modules/particulatecommon.c:3058-3214, 3318-3395
  *
  * PARITY PIN: the reference ships no test, example or golden vector for the
  * particulates module, so the restated part is "parity
@@ -1090,6 +1091,169 @@ void ora_list_step (OraSim * sim, OraList * l, const OraStepParams * par, int nt
     else
       particulate_event_fused (&ctx, l->p[i]);
   }
+}
+
+/* ------------------------------------------------------------------ */
+/* particle boundary conditions: modules/particulatecommon.c:3049-3397   */
+
+/* :3058-3148 */
+static gboolean check_intersetion(FttVector cellpos, FttVector p0, FttVector p1,
+				  FttDirection *dstore, gdouble size)
+{
+  gdouble t;
+  FttDirection d;
+
+  for(d = 0; d < FTT_NEIGHBORS; d++){
+    gdouble normal = ((gdouble) FTT_OPPOSITE_DIRECTION(d) - (gdouble)d);
+#if FTT_2D
+    switch(d/2){
+    case 0:
+      if((p1.x - p0.x)!=0 && normal*(p1.x-p0.x) > 0){
+	t = (cellpos.x + normal*size*0.5 - p0.x)/(p1.x - p0.x);
+	gdouble py = p0.y + t*(p1.y - p0.y);
+	if((py - cellpos.y + size*0.5)*(py - cellpos.y - size*0.5) <= 0  &&  t*(t-1)<= 0 ){
+	  *dstore = d;
+	  return TRUE;
+	}
+      }
+      break;
+    case 1:
+      if((p1.y - p0.y)!=0 && normal*(p1.y-p0.y) > 0){
+	t = (cellpos.y + normal*size*0.5- p0.y)/(p1.y - p0.y);
+	gdouble px = p0.x + t*(p1.x - p0.x);
+	if((px - cellpos.x + size*0.5)*(px - cellpos.x - size*0.5) <= 0  &&  t*(t-1) <= 0){
+	  *dstore = d;
+	  return TRUE;
+	}
+      }
+      break;
+    }
+#else
+    switch(d/2){
+    case 0:
+      if((p1.x - p0.x)!=0 && normal*(p1.x-p0.x) > 0){
+	t = (cellpos.x + normal*size*0.5 - p0.x)/(p1.x - p0.x);
+	gdouble py = p0.y + t*(p1.y - p0.y);
+	gdouble pz = p0.z + t*(p1.z - p0.z);
+	if((py - cellpos.y + size*0.5)*(py - cellpos.y - size*0.5) <= 0  &&
+	   (pz - cellpos.z + size*0.5)*(pz - cellpos.z - size*0.5) <= 0
+	   &&  t*(t-1)<= 0 )
+	  {
+	  *dstore = d;
+	  return TRUE;
+	}
+      }
+      break;
+    case 1:
+      if((p1.y - p0.y)!=0 && normal*(p1.y-p0.y) > 0){
+	t = (cellpos.y + normal*size*0.5- p0.y)/(p1.y - p0.y);
+	gdouble px = p0.x + t*(p1.x - p0.x);
+	gdouble pz = p0.z + t*(p1.z - p0.z);
+	if((px - cellpos.x + size*0.5)*(px - cellpos.x - size*0.5) <= 0  &&
+	   (pz - cellpos.z + size*0.5)*(pz - cellpos.z - size*0.5) <= 0
+	   &&  t*(t-1)<= 0 )
+	  {
+	  *dstore = d;
+	  return TRUE;
+	}
+      }
+      break;
+    case 2:
+      if((p1.z - p0.z)!=0 && normal*(p1.z-p0.z) > 0){
+	t = (cellpos.z + normal*size*0.5- p0.z)/(p1.z - p0.z);
+	gdouble px = p0.x + t*(p1.x - p0.x);
+	gdouble py = p0.y + t*(p1.y - p0.y);
+	if((px - cellpos.x + size*0.5)*(px - cellpos.x - size*0.5) <= 0  &&
+	   (py - cellpos.y + size*0.5)*(py - cellpos.y - size*0.5) <= 0
+	   &&  t*(t-1)<= 0 )
+	  {
+	  *dstore = d;
+	  return TRUE;
+	}
+      }
+      break;
+    }
+#endif
+  }
+  return FALSE;
+}
+
+/* :3151-3186.  Returns NULL when the intersection search fails (the reference
+ * then reads an uninitialised direction; the oracle reports "no face"). */
+static FttCell * boundarycell (OraSim * sim, OraParticulate * p, FttDirection * dstore)
+{
+  FttCell * cell = domain_locate (sim, p->pos_old, -1);
+  if (cell == NULL) return NULL;
+
+  FttVector cellpos;
+  gdouble size;
+  ftt_cell_pos(cell, &cellpos);
+  size = ftt_cell_size(cell);
+
+  if (!check_intersetion(cellpos, p->pos_old, p->pos, dstore, size))
+    return NULL;
+  FttCellFace face = ftt_cell_face(cell, *dstore);
+
+  if(!face.neighbor)
+    return cell;
+
+  while(!GFS_CELL_IS_BOUNDARY(face.neighbor)) {
+    cell = face.neighbor;
+    ftt_cell_pos(cell, &cellpos);
+    size = ftt_cell_size(cell);
+
+    if (!check_intersetion(cellpos, p->pos_old, p->pos, dstore, size))
+      return NULL;
+    face = ftt_cell_face(cell, *dstore);
+
+    if(!face.neighbor)
+      return cell;
+  };
+  return cell;
+}
+
+/* gfs_particle_bc (:3375-3395) for the one-box domains of the oracle:
+ * particles whose gfs_domain_locate is NULL leave the list; those that left
+ * through a side whose GfsBoundary is periodic (bit `side` of periodic_mask;
+ * the matching box is the box itself) are wrapped by periodic_bc_particle
+ * (:3189-3214) and re-appended at the END of the list, the others are dropped.
+ * Returns the number dropped. */
+long ora_list_bc (OraSim * sim, OraList * l, unsigned periodic_mask)
+{
+  long i, m = 0, nw = 0, dropped = 0;
+  OraParticulate ** wrapped = g_malloc0 (sizeof (OraParticulate *)*(l->n ? l->n : 1));
+  for (i = 0; i < l->n; i++) {
+    OraParticulate * p = l->p[i];
+    if (domain_locate (sim, p->pos, -1) != NULL) {
+      l->p[m++] = p;
+      continue;
+    }
+    FttDirection d = 0;
+    FttCell * cell = boundarycell (sim, p, &d);
+    if (cell && sim->broot[d] && (periodic_mask >> d & 1)) {
+      FttVector box_face, box_face_nbr;
+      ftt_cell_pos(sim->root, &box_face);
+      ftt_cell_pos(sim->root, &box_face_nbr);
+      gdouble size = ftt_cell_size(sim->root);
+      gdouble normal = (gdouble)FTT_OPPOSITE_DIRECTION(d) - (gdouble) d;
+      (&box_face.x)[d/2] += (gdouble)normal * size/2.;
+      (&box_face_nbr.x)[d/2] -= (gdouble)normal * size/2.;
+      gdouble tolerance = size/1.e8;
+      gdouble distance = ((&p->pos.x)[d/2] - (&box_face.x)[d/2])*normal;
+      (&p->pos.x)[d/2] = (&box_face_nbr.x)[d/2] + distance + normal*tolerance;
+      (&p->pos_old.x)[d/2] = (&p->pos.x)[d/2];
+      wrapped[nw++] = p;
+    }
+    else {
+      free (p);
+      dropped++;
+    }
+  }
+  for (i = 0; i < nw; i++)
+    l->p[m++] = wrapped[i];
+  free (wrapped);
+  l->n = m;
+  return dropped;
 }
 
 /* ------------------------------------------------------------------ */

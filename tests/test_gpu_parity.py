@@ -515,3 +515,72 @@ def test_inertial_needs_the_previous_field():
             c.step(capi.StepParams(1e-3, (capi.FORCE_INERTIAL,)))
     finally:
         c.close()
+
+
+def _periodic_world(dim):
+    """uniform (3D) / ring-refined (2D) box with ghost layers on every side;
+    x (and z in 3D) periodic, y sides plain boundaries (particles leaving there are dropped)"""
+    t = capi.Tree(dim)
+    if dim == 3:
+        t.refine_uniform(4)
+    else:
+        t.refine_ring(3, 6, 0.25, 1.5)
+        t.corner_sweep()
+    for s in range(2 * dim):
+        t.add_boundary(s)
+    periodic = [0, 1] + ([4, 5] if dim == 3 else [])
+    for s in periodic:
+        t.set_periodic(s)
+    t.finalize(); t.build_stencils()
+    a = t.view()
+    u, v, wz = worlds.taylor_green(a.pos)            # period 1: ghost values = field at the ghost centres
+    w = worlds.World("periodic%d" % dim, dim, t, a, 3.0 * u, 3.0 * v + 0.7, wz if dim == 3 else None,
+                     (capi.FORCE_DRAG, capi.FORCE_BUOY), dt=4e-3, mu=1e-3, g=(0.0, -1.0, 0.0), seed=5,
+                     n_particles=3000, meta=dict(d_p=worlds.D_P, rho_p=worlds.RHO_P, v0="fluid", field="tg"))
+    mask = sum(1 << s for s in periodic)
+    return w, mask
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_periodic_wrap_and_drop(dim, ctx):
+    """gfs_particle_list_event with gfs_particle_bc: cull, step, then wrap the
+    particles that crossed a periodic side (periodic_bc_particle) and drop the
+    ones that crossed a plain boundary -- 25 steps against the oracle, by id"""
+    w, mask = _periodic_world(dim)
+    sim, ptrs = helpers.matched_oracle(w)
+    ctx.upload_tree(w.tree)
+    ctx.upload_field(w.u, w.v, w.w)
+    rng = np.random.default_rng(9)
+    parts = worlds.make_particles(w)
+    n = len(parts["x"])
+    for k in ("x", "y", "z")[:dim]:
+        parts[k] = rng.uniform(-0.499, 0.499, n)
+    for k, f in zip(("vx", "vy", "vz")[:dim], (3.0, 3.0, 2.0)):
+        parts[k] = f * rng.standard_normal(n)
+    ctx.particles_upload(**parts)
+    plist = ora.ParticleList(sim, *[parts[k] for k in ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")])
+    opar = helpers.oracle_params(w)
+    par = w.step_params()
+    wrapped_total = dropped_total = 0
+    for step in range(25):
+        before = ctx.count
+        removed = ctx.particle_list_event(par)
+        plist.cull()
+        plist.step(opar)
+        n_before_bc = len(plist)
+        odrop = plist.bc(mask)
+        dropped_total += removed
+        assert ctx.count == len(plist) == before - removed
+        got = ctx.particles_download(ids=True)
+        want = plist.get()
+        go, wo = np.argsort(got["id"]), np.argsort(want["id"])
+        assert np.array_equal(got["id"][go], want["id"][wo])
+        g = {k: got[k][go] for k in STATE if got[k] is not None and (dim == 3 or k not in ("z", "vz"))}
+        wv = {k: want[k][wo] for k in g}
+        _check_state(g, wv, dim, rtol=1e-11)
+        # wrapped particles were re-appended at the end of the reference's list
+        wrapped_total += int((np.diff(want["id"].astype(np.int64)) < 0).sum() > 0)
+    assert dropped_total > 20, "the test did not exercise dropping"
+    assert wrapped_total > 5, "the test did not exercise wrapping"
+    inside = ctx.locate(got["x"], got["y"], got["z"] if dim == 3 else None) >= 0
+    assert inside.mean() > 0.95
