@@ -341,7 +341,13 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
      the list is the next step ("host object sync"). */
   upload_particles (s, plist);
   par.record_forces = 1;
-  if (gfsb200_particle_list_event (s->ctx, &par, &removed) != GFSB200_OK)
+  /* cull + step on the device; the BCs stay on the host in this binding because
+     gfs_particle_bc also ships particles to other MPI ranks (:3218-3244).  A
+     single-process periodic run can instead declare its periodic sides with
+     gfsb200_tree_set_periodic and call gfsb200_particle_list_event, which wraps
+     and drops on the device (gfsb200_particle_bc). */
+  if (gfsb200_particles_cull (s->ctx, &removed) != GFSB200_OK ||
+      gfsb200_step (s->ctx, &par) != GFSB200_OK)
     g_error ("particulates (B200): %s", gfsb200_last_error ());
   download_particles (s, plist);
 
