@@ -250,10 +250,11 @@ def run_b200(args):
 
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
     par = world.step_params()
-    dep_tensor = None
+    reducer = None
     if args.two_way and world_size > 1:
-        # the C-ABI's deposit buffer, aliased (no copy) as a tensor for the NCCL all-reduce
-        dep_tensor = pkg.multigpu.deposit_tensor(ctx, local_rank)
+        # the C-ABI's two deposit buffers, aliased (no copy) as tensors; the NCCL all-reduce of
+        # step n runs on a communication stream while step n+1 computes
+        reducer = pkg.multigpu.OverlappedDepositReduce(ctx, local_rank)
 
     launches_per_step = 3 + (1 if args.two_way else 0)        # vertex + vorticity + step (+ fused deposit)
 
@@ -261,13 +262,17 @@ def run_b200(args):
         ctx.refresh_field()
         ctx.step(par)
         if args.two_way:
+            if reducer is not None:
+                reducer.begin_step()
             ctx.deposit_all(par)
-            if dep_tensor is not None:
-                pkg.multigpu.allreduce_deposit(ctx, dep_tensor)
+            if reducer is not None:
+                reducer.end_step()
         if args.resort and (i + 1) % args.resort == 0:
             ctx.sort()
 
     def barrier():
+        if reducer is not None:
+            reducer.drain()
         if world_size > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -284,6 +289,8 @@ def run_b200(args):
     e0.record(stream)
     for i in range(args.steps):
         one_step(i)
+    if reducer is not None:
+        reducer.join()              # the timed region ends when the last all-reduce has landed
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)

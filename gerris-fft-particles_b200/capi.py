@@ -115,6 +115,7 @@ def lib() -> C.CDLL:
         "gfsb200_deposit_volume": (i32, [vp]),
         "gfsb200_deposit_force": (i32, [vp, C.POINTER(StepParamsC)]),
         "gfsb200_deposit_all": (i32, [vp, C.POINTER(StepParamsC)]),
+        "gfsb200_deposit_select": (i32, [vp, i32]),
         "gfsb200_deposit_buffer": (i32, [vp, C.POINTER(vp), C.POINTER(i64)]),
         "gfsb200_download_deposit": (i32, [vp, i32, vp]),
         "gfsb200_timer_reset": (i32, [vp]),
@@ -449,6 +450,9 @@ class Context:
 
     def deposit_all(self, params: StepParams):
         _check(self._lib.gfsb200_deposit_all(self.handle, C.byref(params.c)), "deposit_all")
+
+    def deposit_select(self, which: int):
+        _check(self._lib.gfsb200_deposit_select(self.handle, which), "deposit_select")
 
     def deposit_buffer(self):
         p, n = C.c_void_p(), C.c_int64()

@@ -100,8 +100,9 @@ struct gfsb200_ctx {
   int64_t hp_chunk;
   cudaStream_t hp_h2d, hp_d2h;
   cudaEvent_t hp_in[3], hp_done[3], hp_out[3];
-  /* deposit */
-  double * deposit;
+  /* deposit: two buffers so that the all-reduce of one step can overlap the next step */
+  double * deposit;            /* the selected one */
+  double * deposit_buf[2];
   int64_t deposit_count;
   int step_minb;               /* __launch_bounds__ min blocks/SM variant of the step kernel */
   int step_mode;               /* 0: plain kernel; 2/3: TMA-staged persistent kernel, that many stages */
@@ -140,7 +141,8 @@ static void free_tree (gfsb200_ctx * c)
   cudaFree (c->F.vtx_prev); cudaFree (c->F.acc);
   c->F.vtx_prev = c->F.acc = NULL;
   c->have_prev = c->acc_valid = false;
-  cudaFree (c->deposit); c->deposit = NULL; c->deposit_count = 0;
+  cudaFree (c->deposit_buf[0]); cudaFree (c->deposit_buf[1]);
+  c->deposit = c->deposit_buf[0] = c->deposit_buf[1] = NULL; c->deposit_count = 0;
   c->have_tree = c->have_field = false;
 }
 
@@ -195,7 +197,7 @@ extern "C" int gfsb200_ctx_create (int device, gfsb200_ctx ** out)
   for (int k = 0; k < 3; k++) c->force[k] = NULL;
   c->cell = c->perm = c->perm2 = NULL; c->key = c->key2 = NULL; c->flag = NULL;
   c->d_count = NULL; c->cub_tmp = NULL; c->cub_tmp_bytes = 0; c->d_ptr_table = NULL;
-  c->deposit = NULL; c->deposit_count = 0;
+  c->deposit = c->deposit_buf[0] = c->deposit_buf[1] = NULL; c->deposit_count = 0;
   memset (c->hp_col, 0, sizeof c->hp_col);
   c->hp_chunk = 0; c->hp_h2d = c->hp_d2h = NULL;
   c->ev_used = 0; c->timing = true;
@@ -338,8 +340,9 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
   CK (cudaMemsetAsync (c->F.vort, 0, (size_t) n*ws*sizeof (double), c->stream));
   CK (cudaMalloc ((void **) &c->F.nodata_flag, sizeof (int)));
   c->deposit_count = (int64_t) (1 + t->dim)*n;
-  CK (cudaMalloc ((void **) &c->deposit, (size_t) c->deposit_count*sizeof (double)));
-  CK (cudaMemsetAsync (c->deposit, 0, (size_t) c->deposit_count*sizeof (double), c->stream));
+  CK (cudaMalloc ((void **) &c->deposit_buf[0], (size_t) c->deposit_count*sizeof (double)));
+  CK (cudaMemsetAsync (c->deposit_buf[0], 0, (size_t) c->deposit_count*sizeof (double), c->stream));
+  c->deposit = c->deposit_buf[0];
   c->have_tree = true;
   c->have_field = false;
   return GFSB200_OK;
@@ -1030,6 +1033,19 @@ extern "C" int gfsb200_deposit_force (gfsb200_ctx * c, const gfsb200_step_params
 extern "C" int gfsb200_deposit_all (gfsb200_ctx * c, const gfsb200_step_params * p)
 {
   return deposit (c, p, 3);
+}
+
+extern "C" int gfsb200_deposit_select (gfsb200_ctx * c, int which)
+{
+  if (!c || !c->have_tree) return gfsb200_fail (GFSB200_ERR_STATE, "deposit_select: no tree resident");
+  if (which != 0 && which != 1) return gfsb200_fail (GFSB200_ERR_ARG, "deposit_select: buffer 0 or 1");
+  CK (cudaSetDevice (c->device));
+  if (!c->deposit_buf[which]) {
+    CK (cudaMalloc ((void **) &c->deposit_buf[which], (size_t) c->deposit_count*sizeof (double)));
+    CK (cudaMemsetAsync (c->deposit_buf[which], 0, (size_t) c->deposit_count*sizeof (double), c->stream));
+  }
+  c->deposit = c->deposit_buf[which];
+  return GFSB200_OK;
 }
 
 extern "C" int gfsb200_deposit_buffer (gfsb200_ctx * c, double ** dev, int64_t * count)

@@ -59,3 +59,57 @@ def allreduce_host(array: np.ndarray, group=None) -> np.ndarray:
     t = torch.from_numpy(np.ascontiguousarray(array))
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t.numpy()
+
+
+class OverlappedDepositReduce:
+    """Two-way coupling without a bubble: the deposited field of step n is summed
+    over ranks on a communication stream while step n+1 (cell pass, fused step,
+    deposit into the OTHER buffer) runs on the context's stream.  The reduced
+    field of step n is what the host fluid solver consumes; `wait(which)` orders
+    a consumer (or the next deposit into that buffer) after its all-reduce."""
+
+    def __init__(self, ctx, device_index: int, group=None):
+        import torch
+        self.ctx, self.group, self.torch = ctx, group, torch
+        self.device = torch.device("cuda", device_index)
+        self.compute = torch.cuda.ExternalStream(ctx.stream, device=self.device)
+        self.comm = torch.cuda.Stream(device=self.device)
+        self.tensors, self.done = [], []
+        for which in (0, 1):
+            ctx.deposit_select(which)
+            self.tensors.append(deposit_tensor(ctx, device_index))
+            self.done.append(None)
+        self.which = 0
+        ctx.deposit_select(0)
+
+    def begin_step(self):
+        """call before the deposit of a step: picks the buffer and makes the
+        compute stream wait until that buffer's previous all-reduce has drained"""
+        if self.done[self.which] is not None:
+            self.compute.wait_event(self.done[self.which])
+        self.ctx.deposit_select(self.which)
+
+    def end_step(self):
+        """call after the deposit: launches the all-reduce on the comm stream"""
+        import torch.distributed as dist
+        torch = self.torch
+        ready = torch.cuda.Event()
+        ready.record(self.compute)
+        self.comm.wait_event(ready)
+        with torch.cuda.stream(self.comm):
+            dist.all_reduce(self.tensors[self.which], op=dist.ReduceOp.SUM, group=self.group)
+            ev = torch.cuda.Event()
+            ev.record(self.comm)
+        self.done[self.which] = ev
+        self.which ^= 1
+
+    def join(self):
+        """make the compute stream wait for every outstanding all-reduce"""
+        for ev in self.done:
+            if ev is not None:
+                self.compute.wait_event(ev)
+
+    def drain(self):
+        for ev in self.done:
+            if ev is not None:
+                ev.synchronize()

@@ -273,6 +273,10 @@ int gfsb200_deposit_volume (gfsb200_ctx * c);
 int gfsb200_deposit_force (gfsb200_ctx * c, const gfsb200_step_params * p);
 /* both of the above in one pass over the particles (one locate, one kernel) */
 int gfsb200_deposit_all (gfsb200_ctx * c, const gfsb200_step_params * p);
+/* There are two deposition buffers; select which one the deposit calls, the
+ * buffer query and the download use (default 0).  Alternating them lets the
+ * all-reduce of step n run on another stream while step n+1 deposits. */
+int gfsb200_deposit_select (gfsb200_ctx * c, int which);
 /* device pointer / element count of the deposition buffer
  * ([1 + dim][n_cells]: void fraction, Fx, Fy(, Fz)); for the multi-GPU
  * all-reduce (NCCL) issued by the caller on gfsb200_ctx_stream() */
