@@ -166,3 +166,23 @@ def test_flatten_rejects_solid_cells():
         capi.flatten_ftt(3, roots, is_box)
     solid_slot.value = None
     capi.flatten_ftt(3, roots, is_box)
+
+
+@pytest.mark.parametrize("dim,level,sides", [(3, 4, ()), (3, 3, (0, 1, 2, 3, 4, 5)), (2, 5, (0, 1, 2, 3)), (3, 4, (2, 5))])
+def test_lattice_stencil_fast_path_equals_general_path(dim, level, sides, monkeypatch):
+    """uniform trees build one interpolator per lattice vertex (canonical leaf);
+    the result must be the table the general de-duplicating builder produces"""
+    def build():
+        t = capi.Tree(dim)
+        t.refine_uniform(level)
+        for s in sides:
+            t.add_boundary(s)
+        t.finalize()
+        t.build_stencils()
+        return t, t.view()
+    ta, a = build()
+    monkeypatch.setenv("GFSB200_GENERAL_STENCILS", "1")
+    tb, b = build()
+    assert a.lattice_level == b.lattice_level == level
+    for k in ("vtx_off", "vtx_cell", "vtx_w", "leaf_vtx"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
