@@ -58,6 +58,8 @@ def load(dim: int) -> C.CDLL:
     sig = {
         "ora_sim_new": (vp, [i32]), "ora_sim_destroy": (None, [vp]),
         "ora_root": (u64, [vp]), "ora_boundary_root": (u64, [vp, i32]), "ora_dimension": (i32, []),
+        "ora_add_box": (i32, [vp]), "ora_nbox": (i32, [vp]), "ora_box_root": (u64, [vp, i32]),
+        "ora_box_boundary_root": (u64, [vp, i32, i32]), "ora_add_boundary_box": (None, [vp, i32, i32]),
         "ora_refine_uniform": (None, [vp, i32]), "ora_refine_ring": (None, [vp, i32, i32, dbl, dbl]),
         "ora_refine_points": (i32, [vp, i32, vp, vp, vp, vp]),
         "ora_corner_sweep": (None, [vp]), "ora_add_boundary": (None, [vp, i32]),
@@ -117,10 +119,14 @@ class Sim:
         except Exception:
             pass
 
-    # construction, in Gerris' order: boundaries, refinement, corner sweep, match
-    def add_boundary(self, side):
-        self.L.ora_add_boundary(self.h, side)
-        self.sides.append(side)
+    # construction, in Gerris' order: boxes, boundaries, refinement, corner sweep, match
+    def add_box(self):
+        """append a unit GfsBox to the right (+x) of the last one"""
+        return self.L.ora_add_box(self.h)
+
+    def add_boundary(self, side, box=0):
+        self.L.ora_add_boundary_box(self.h, box, side)
+        self.sides.append((box, side))
 
     def refine_uniform(self, level):
         self.L.ora_refine_uniform(self.h, level)
@@ -137,8 +143,10 @@ class Sim:
 
     def roots(self):
         """(FttCell* list, is_box list) in flat-tree root order"""
-        r = [self.L.ora_root(self.h)] + [self.L.ora_boundary_root(self.h, s) for s in self.sides]
-        return r, [1] + [0] * len(self.sides)
+        nb = self.L.ora_nbox(self.h)
+        r = [self.L.ora_box_root(self.h, b) for b in range(nb)] + \
+            [self.L.ora_box_boundary_root(self.h, b, s) for b, s in self.sides]
+        return r, [1] * nb + [0] * len(self.sides)
 
     def count(self, leaves_only=False):
         return self.L.ora_count(self.h, int(leaves_only))

@@ -42,17 +42,23 @@
 #endif
 
 #define ORA_MAXVAR 16
+#define ORA_MAXBOX 8
 
 typedef struct {
   GfsDomain domain;
   GfsVariable var[ORA_MAXVAR];
   int nvar;
-  FttCell * root;                    /* the GfsBox root cell */
-  FttCell * broot[FTT_NEIGHBORS];    /* GfsBoundary roots, indexed by box side */
+  /* GfsBox root cells: a chain of nbox unit boxes along +x, box k centred at
+     (k,0,0) and linked to box k+1 through their root neighbours (how a
+     multi-box GfsDomain looks to ftt.c); `root` is box 0 */
+  FttCell * root;
+  FttCell * box[ORA_MAXBOX];
+  int nbox;
+  FttCell * broot[ORA_MAXBOX][FTT_NEIGHBORS];    /* GfsBoundary roots, by box and side */
   /* GfsLocateArray (src/domain.h:32-36) */
   double min[3], max[3], h;
   int n[3], size;
-  signed char * slot;                /* 0: empty, 1: GfsBox first, 2: boundaries only */
+  signed char * slot;                /* 0: empty, 1 + b: GfsBox b first, -1: boundaries only */
 } OraSim;
 
 /* ------------------------------------------------------------------ */
@@ -105,16 +111,42 @@ OraSim * ora_sim_new (int nvar)
   }
   sim->domain.rootlevel = 0;
   sim->root = ftt_cell_new ((FttCellInitFunc) cell_init, sim);
+  sim->box[0] = sim->root;
+  sim->nbox = 1;
   return sim;
+}
+
+/* appends a GfsBox to the right of the last one (before any refinement):
+ * what "GfsBox ... GEdge k k+1 right" builds, src/boundary.c gfs_gedge_link_boxes */
+int ora_add_box (OraSim * sim)
+{
+  FttVector pos = { sim->nbox, 0., 0., 0. };
+  FttCell * b;
+  g_assert (sim->nbox < ORA_MAXBOX);
+  b = ftt_cell_new ((FttCellInitFunc) cell_init, sim);
+  ftt_cell_set_pos (b, &pos);
+  ftt_cell_set_neighbor (sim->box[sim->nbox - 1], b, FTT_RIGHT, (FttCellInitFunc) cell_init, sim);
+  sim->box[sim->nbox] = b;
+  return sim->nbox++;
+}
+
+int ora_nbox (OraSim * sim) { return sim->nbox; }
+uint64_t ora_box_root (OraSim * sim, int b) { return (uint64_t) (uintptr_t) sim->box[b]; }
+uint64_t ora_box_boundary_root (OraSim * sim, int b, int d)
+{
+  return (uint64_t) (uintptr_t) sim->broot[b][d];
 }
 
 void ora_sim_destroy (OraSim * sim)
 {
   FttDirection d;
-  for (d = 0; d < FTT_NEIGHBORS; d++)
-    if (sim->broot[d])
-      ftt_cell_destroy (sim->broot[d], cell_cleanup, NULL);
-  ftt_cell_destroy (sim->root, cell_cleanup, NULL);
+  int b;
+  for (b = 0; b < sim->nbox; b++)
+    for (d = 0; d < FTT_NEIGHBORS; d++)
+      if (sim->broot[b][d])
+	ftt_cell_destroy (sim->broot[b][d], cell_cleanup, NULL);
+  for (b = 0; b < sim->nbox; b++)
+    ftt_cell_destroy (sim->box[b], cell_cleanup, NULL);
   free (sim->slot);
   free (sim);
 }
@@ -122,7 +154,7 @@ void ora_sim_destroy (OraSim * sim)
 uint64_t ora_root (OraSim * sim) { return (uint64_t) (uintptr_t) sim->root; }
 uint64_t ora_boundary_root (OraSim * sim, int d)
 {
-  return (uint64_t) (uintptr_t) sim->broot[d];
+  return (uint64_t) (uintptr_t) sim->broot[0][d];
 }
 int ora_dimension (void) { return FTT_DIMENSION; }
 
@@ -142,7 +174,9 @@ static gboolean refine_uniform (FttCell * cell, gpointer data)
 void ora_refine_uniform (OraSim * sim, int level)
 {
   guint l = level;
-  ftt_cell_refine (sim->root, refine_uniform, &l, (FttCellInitFunc) cell_init, sim);
+  int b;
+  for (b = 0; b < sim->nbox; b++)
+    ftt_cell_refine (sim->box[b], refine_uniform, &l, (FttCellInitFunc) cell_init, sim);
 }
 
 /* refine while level < maxlevel and the distance
@@ -170,7 +204,9 @@ static gboolean refine_ring (FttCell * cell, gpointer data)
 void ora_refine_ring (OraSim * sim, int minlevel, int maxlevel, double R, double factor)
 {
   RingRefine r = { minlevel, maxlevel, R, factor };
-  ftt_cell_refine (sim->root, refine_ring, &r, (FttCellInitFunc) cell_init, sim);
+  int b;
+  for (b = 0; b < sim->nbox; b++)
+    ftt_cell_refine (sim->box[b], refine_ring, &r, (FttCellInitFunc) cell_init, sim);
 }
 
 /* Refines, in the order given, the leaf cell of level level[i] containing
@@ -182,7 +218,10 @@ int ora_refine_points (OraSim * sim, int n, const int * level,
   int i, done = 0;
   for (i = 0; i < n; i++) {
     FttVector p = { x[i], y[i], z ? z[i] : 0., 0. };
-    FttCell * cell = ftt_cell_locate (sim->root, p, level[i]);
+    FttCell * cell = NULL;
+    int b;
+    for (b = 0; b < sim->nbox && !cell; b++)
+      cell = ftt_cell_locate (sim->box[b], p, level[i]);
     if (cell && FTT_CELL_IS_LEAF (cell) && (int) ftt_cell_level (cell) == level[i]) {
       ftt_cell_refine_single (cell, (FttCellInitFunc) cell_init, sim);
       done++;
@@ -201,10 +240,14 @@ static void refine_cell_corner (FttCell * cell, OraSim * sim)
 /* src/simulation.c:1226-1231 (gfs_domain_cell_traverse visits GfsBox trees only) */
 void ora_corner_sweep (OraSim * sim)
 {
-  gint l, depth = ftt_cell_depth (sim->root);
+  gint l, depth = 0;
+  int b;
+  for (b = 0; b < sim->nbox; b++)
+    depth = MAX (depth, (gint) ftt_cell_depth (sim->box[b]));      /* gfs_domain_depth */
   for (l = depth - 2; l >= 0; l--)
-    ftt_cell_traverse (sim->root, FTT_PRE_ORDER, FTT_TRAVERSE_LEVEL, l,
-		       (FttCellTraverseFunc) refine_cell_corner, sim);
+    for (b = 0; b < sim->nbox; b++)
+      ftt_cell_traverse (sim->box[b], FTT_PRE_ORDER, FTT_TRAVERSE_LEVEL, l,
+			 (FttCellTraverseFunc) refine_cell_corner, sim);
 }
 
 /* ------------------------------------------------------------------ */
@@ -253,7 +296,11 @@ static void match (FttCell * cell, OraBoundary * boundary)
  * sits on (box->neighbor[side]).  Gerris creates its boundaries while reading
  * the .gfs file, i.e. BEFORE refinement; call ora_match_boundaries() after
  * refinement, as gfs_simulation_refine does (src/simulation.c:1233). */
-void ora_add_boundary (OraSim * sim, int side)
+void ora_add_boundary_box (OraSim * sim, int b, int side);
+
+void ora_add_boundary (OraSim * sim, int side) { ora_add_boundary_box (sim, 0, side); }
+
+void ora_add_boundary_box (OraSim * sim, int b, int side)
 {
   static FttVector rpos[6] = {
     {1.,0.,0.}, {-1.,0.,0.}, {0.,1.,0.}, {0.,-1.,0.}, {0.,0.,1.}, {0.,0.,-1.}
@@ -263,33 +310,34 @@ void ora_add_boundary (OraSim * sim, int side)
   gdouble size;
   FttDirection d, od;
 
-  g_assert (side >= 0 && side < FTT_NEIGHBORS && sim->broot[side] == NULL);
+  g_assert (side >= 0 && side < FTT_NEIGHBORS && b >= 0 && b < sim->nbox && sim->broot[b][side] == NULL);
   d = FTT_OPPOSITE_DIRECTION (side);
   root = ftt_cell_new ((FttCellInitFunc) cell_init, sim);
   root->flags |= GFS_FLAG_BOUNDARY;
-  ftt_cell_set_level (root, ftt_cell_level (sim->root));
-  ftt_cell_set_neighbor_match (root, sim->root, d, (FttCellInitFunc) cell_init, sim);
-  ftt_cell_pos (sim->root, &pos);
-  size = ftt_cell_size (sim->root);
+  ftt_cell_set_level (root, ftt_cell_level (sim->box[b]));
+  ftt_cell_set_neighbor_match (root, sim->box[b], d, (FttCellInitFunc) cell_init, sim);
+  ftt_cell_pos (sim->box[b], &pos);
+  size = ftt_cell_size (sim->box[b]);
   od = FTT_OPPOSITE_DIRECTION (d);
   pos.x += rpos[od].x*size;
   pos.y += rpos[od].y*size;
   pos.z += rpos[od].z*size;
   ftt_cell_set_pos (root, &pos);
-  sim->broot[side] = root;
+  sim->broot[b][side] = root;
 }
 
 /* gfs_domain_match -> boundary_match for every boundary (src/boundary.c:670-685) */
 void ora_match_boundaries (OraSim * sim)
 {
-  int side;
+  int side, box;
+  for (box = 0; box < sim->nbox; box++)
   for (side = 0; side < FTT_NEIGHBORS; side++)
-    if (sim->broot[side]) {
+    if (sim->broot[box][side]) {
       OraBoundary b;
       guint l;
       b.sim = sim;
       b.d = FTT_OPPOSITE_DIRECTION (side);
-      b.root = sim->broot[side];
+      b.root = sim->broot[box][side];
       l = ftt_cell_level (b.root);
       b.changed = FALSE;
       b.depth = l;
@@ -300,7 +348,7 @@ void ora_match_boundaries (OraSim * sim)
       }
       if (b.root && b.changed)
 	ftt_cell_flatten (b.root, b.d, cell_cleanup, NULL);
-      sim->broot[side] = b.root;
+      sim->broot[box][side] = b.root;
     }
 }
 
@@ -349,10 +397,15 @@ void ora_finalize (OraSim * sim)
     sim->min[i] = G_MAXDOUBLE;
     sim->max[i] = - G_MAXDOUBLE;
   }
-  root_bounds (sim->root, sim);
-  for (d = 0; d < FTT_NEIGHBORS; d++)
-    if (sim->broot[d])
-      root_bounds (sim->broot[d], sim);
+  {
+    int bb;
+    for (bb = 0; bb < sim->nbox; bb++) {
+      root_bounds (sim->box[bb], sim);
+      for (d = 0; d < FTT_NEIGHBORS; d++)
+	if (sim->broot[bb][d])
+	  root_bounds (sim->broot[bb][d], sim);
+    }
+  }
   sim->size = 1;
   for (i = 0; i < FTT_DIMENSION; i++) {
     g_assert (sim->max[i] > sim->min[i]);
@@ -361,19 +414,25 @@ void ora_finalize (OraSim * sim)
   }
   free (sim->slot);
   sim->slot = g_malloc0 (sim->size);
-  ftt_cell_pos (sim->root, &p);
-  k = locate_linear_index (&p, sim);
-  g_assert (k >= 0 && !sim->slot[k]);
-  sim->slot[k] = 1;
-  for (d = 0; d < FTT_NEIGHBORS; d++)
-    if (sim->broot[d]) {
-      ftt_cell_pos (sim->broot[d], &p);
+  {
+    int bb;
+    /* box_index(), src/domain.c:82-98: the box first, its boundaries PREPENDED;
+       gfs_domain_locate only accepts a slot whose first entry is a GfsBox */
+    for (bb = 0; bb < sim->nbox; bb++) {
+      ftt_cell_pos (sim->box[bb], &p);
       k = locate_linear_index (&p, sim);
-      g_assert (k >= 0);
-      /* g_slist_prepend: a boundary prepended to a box slot hides the box
-	 (src/domain.c:92, 2632); cannot happen for a one-box domain */
-      sim->slot[k] = 2;
+      g_assert (k >= 0 && !sim->slot[k]);
+      sim->slot[k] = 1 + bb;
     }
+    for (bb = 0; bb < sim->nbox; bb++)
+      for (d = 0; d < FTT_NEIGHBORS; d++)
+	if (sim->broot[bb][d]) {
+	  ftt_cell_pos (sim->broot[bb][d], &p);
+	  k = locate_linear_index (&p, sim);
+	  g_assert (k >= 0);
+	  sim->slot[k] = -1;
+	}
+  }
 }
 
 void ora_locate_array (OraSim * sim, double * min, double * h, int * n)
@@ -390,8 +449,8 @@ void ora_locate_array (OraSim * sim, double * min, double * h, int * n)
 static FttCell * domain_locate (OraSim * sim, FttVector target, gint max_depth)
 {
   gint i = locate_linear_index (&target, sim);
-  if (i >= 0 && sim->slot[i] == 1)
-    return ftt_cell_locate (sim->root, target, max_depth);
+  if (i >= 0 && sim->slot[i] >= 1)
+    return ftt_cell_locate (sim->box[sim->slot[i] - 1], target, max_depth);
   return NULL;
 }
 
@@ -457,8 +516,10 @@ static void export_cell (FttCell * cell, OraExport * e)
 long ora_export_cells (OraSim * sim, uint64_t * cell, double * pos, int * level, int * leaf)
 {
   OraExport e = { 0, cell, pos, level, leaf };
-  ftt_cell_traverse (sim->root, FTT_PRE_ORDER, FTT_TRAVERSE_ALL, -1,
-		     (FttCellTraverseFunc) export_cell, &e);
+  int b;
+  for (b = 0; b < sim->nbox; b++)
+    ftt_cell_traverse (sim->box[b], FTT_PRE_ORDER, FTT_TRAVERSE_ALL, -1,
+		       (FttCellTraverseFunc) export_cell, &e);
   return e.n;
 }
 
@@ -467,9 +528,11 @@ static void count_cell (FttCell * cell, long * n) { (*n)++; }
 long ora_count (OraSim * sim, int leaves_only)
 {
   long n = 0;
-  ftt_cell_traverse (sim->root, FTT_PRE_ORDER,
-		     leaves_only ? FTT_TRAVERSE_LEAFS : FTT_TRAVERSE_ALL, -1,
-		     (FttCellTraverseFunc) count_cell, &n);
+  int b;
+  for (b = 0; b < sim->nbox; b++)
+    ftt_cell_traverse (sim->box[b], FTT_PRE_ORDER,
+		       leaves_only ? FTT_TRAVERSE_LEAFS : FTT_TRAVERSE_ALL, -1,
+		       (FttCellTraverseFunc) count_cell, &n);
   return n;
 }
 
@@ -1230,7 +1293,7 @@ long ora_list_bc (OraSim * sim, OraList * l, unsigned periodic_mask)
     }
     FttDirection d = 0;
     FttCell * cell = boundarycell (sim, p, &d);
-    if (cell && sim->broot[d] && (periodic_mask >> d & 1)) {
+    if (cell && sim->nbox == 1 && sim->broot[0][d] && (periodic_mask >> d & 1)) {
       FttVector box_face, box_face_nbr;
       ftt_cell_pos(sim->root, &box_face);
       ftt_cell_pos(sim->root, &box_face_nbr);

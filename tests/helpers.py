@@ -20,11 +20,17 @@ def oracle_tree_from_flat(arrays) -> "ora.Sim":
     """Reference FTT tree with exactly the cells of the flat tree."""
     a = arrays
     sim = ora.Sim(a.dim, nvar=8)
-    # boundaries first, as Gerris does while reading the .gfs file
+    # boxes: the oracle supports a chain of unit boxes along +x starting at the origin
+    for b in range(1, a.n_box_roots):
+        assert np.array_equal(a.pos[b], [float(b), 0.0, 0.0]), "oracle boxes form a chain along +x"
+        sim.add_box()
+    # boundaries next, as Gerris does while reading the .gfs file
     for r in range(a.n_box_roots, a.n_roots):
-        d = a.pos[r] - a.pos[0]
+        dist = np.abs(a.pos[:a.n_box_roots] - a.pos[r]).sum(1)
+        b = int(np.argmin(dist))                      # the box this ghost root touches
+        d = a.pos[r] - a.pos[b]
         axis = int(np.argmax(np.abs(d)))
-        sim.add_boundary(2 * axis + (0 if d[axis] > 0 else 1))
+        sim.add_boundary(2 * axis + (0 if d[axis] > 0 else 1), b)
     refined = np.nonzero((a.child0 >= 0) & ((a.flags & capi.CELL_BOUNDARY) == 0))[0]   # level order
     if len(refined):
         lv = np.ascontiguousarray(a.level[refined], dtype=np.int32)

@@ -186,3 +186,73 @@ def test_lattice_stencil_fast_path_equals_general_path(dim, level, sides, monkey
     assert a.lattice_level == b.lattice_level == level
     for k in ("vtx_off", "vtx_cell", "vtx_w", "leaf_vtx"):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
+
+
+def build_chain(dim, nbox, minl, maxl, R, ghost=True):
+    """nbox unit boxes in a row along +x (a multi-GfsBox domain), refined around a
+    ring that straddles the box interfaces, with ghost layers on the outer sides"""
+    t = capi.Tree(dim)
+    sim = ora.Sim(dim)
+    t.add_root((0.0, 0.0, 0.0))
+    for b in range(1, nbox):
+        t.add_root((float(b), 0.0, 0.0))
+        t.link_roots(b - 1, 0, b)
+        sim.add_box()
+    sides = []
+    if ghost:
+        sides = [(0, 1), (nbox - 1, 0)] + [(b, s) for b in range(nbox) for s in range(2, 2 * dim)]
+        for b, s in sides:
+            sim.add_boundary(s, b)
+    # centre the ring on the interface between box 0 and box 1
+    crit = lambda pos, level, h: level < minl or (level < maxl and abs(
+        np.hypot(pos[0] - 0.5, pos[1]) - R) < 1.5 * h and (dim == 2 or abs(pos[2]) < 3 * h))
+    t.refine(crit)
+    t.corner_sweep()
+    for b, s in sides:
+        t.add_boundary(s, b)
+    t.finalize()
+    return t, sim, crit
+
+
+@pytest.mark.parametrize("dim,nbox,minl,maxl", [(2, 2, 2, 6), (2, 3, 3, 5), (3, 2, 2, 5)])
+def test_multi_box_domain(dim, nbox, minl, maxl):
+    """several GfsBoxes: the locate array has one slot per box, refinement and
+    2:1 / corner balance cross the box interfaces, stencils straddle them"""
+    t, sim, crit = build_chain(dim, nbox, minl, maxl, 0.3)
+    a = t.view()
+    # the reference tree with exactly these cells, then flatten it
+    sim2 = helpers.oracle_tree_from_flat(a)
+    roots, is_box = sim2.roots()
+    t2, fmap = capi.flatten_ftt(dim, roots, is_box)
+    b = t2.view()
+    assert a.n_box_roots == nbox and a.n_cells == b.n_cells
+    for k in KEYS:
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert np.array_equal(a.la_n, b.la_n) and np.array_equal(a.la_slot, b.la_slot)
+    assert a.la_n[0] == nbox + 2 and sorted(a.la_slot[a.la_slot >= 0]) == list(range(nbox))
+    # stencils against gfs_cell_corner_interpolator, including those across the interface
+    t2.build_stencils()
+    idx = helpers.PtrIndex(fmap.cells)
+    leaves = b.box_leaves
+    near = leaves[np.abs(b.pos[leaves, 0] - 0.5) < 0.2]
+    assert len(near) > 50
+    for i in near[::3]:
+        for k in range(2 ** dim):
+            cells, w = t2.corner_interpolator(int(i), k)
+            oc, ow = sim2.corner_interpolator(fmap.cells[i], k)
+            assert list(idx(np.array(oc, dtype=np.uint64))) == cells and ow == w
+    # point location across the boxes
+    rng = np.random.default_rng(2)
+    x = rng.uniform(-0.7, nbox - 0.3, 4000)
+    y = rng.uniform(-0.7, 0.7, 4000)
+    z = rng.uniform(-0.7, 0.7, 4000) if dim == 3 else None
+    got = idx(sim2.locate(x, y, z))
+    assert (got >= 0).sum() > 1000 and (got < 0).sum() > 100
+    roots_of = got.copy()
+    while True:
+        p = np.where(roots_of >= 0, b.parent[np.maximum(roots_of, 0)], -1)
+        m = p >= 0
+        if not m.any():
+            break
+        roots_of[m] = p[m]
+    assert set(np.unique(roots_of[got >= 0])) == set(range(nbox))

@@ -62,7 +62,38 @@ def _world(kind):
                             dt=2e-3, mu=2e-3, rho=1.3, seed=12, n_particles=8000,
                             meta=dict(d_p=worlds.D_P, rho_p=worlds.RHO_P, v0="fluid", field="ring",
                                       cloud="half uniform, half gaussian"))
+    if kind in ("chain2", "chain3"):
+        # several GfsBoxes in a row along +x, refined around a ring straddling the first interface
+        dim, nbox = (2, 3) if kind == "chain2" else (3, 2)
+        minl, maxl = (3, 6) if dim == 2 else (2, 5)
+        t = capi.Tree(dim)
+        t.add_root((0.0, 0.0, 0.0))
+        for b in range(1, nbox):
+            t.add_root((float(b), 0.0, 0.0))
+            t.link_roots(b - 1, 0, b)
+        t.refine(lambda pos, level, h: level < minl or (level < maxl and abs(
+            np.hypot(pos[0] - 0.5, pos[1]) - 0.3) < 1.5 * h and (dim == 2 or abs(pos[2]) < 3 * h)))
+        t.corner_sweep()
+        for b, sd in [(0, 1), (nbox - 1, 0)] + [(b, sd) for b in range(nbox) for sd in range(2, 2 * dim)]:
+            t.add_boundary(sd, b)
+        t.finalize(); t.build_stencils()
+        a = t.view()
+        u, v, wz = worlds.taylor_green(a.pos * 0.5)
+        forces = (capi.FORCE_DRAG, capi.FORCE_LIFT, capi.FORCE_BUOY)
+        return worlds.World(kind, dim, t, a, u, v, (0.3 * u if dim == 3 else None), forces, dt=2e-3, mu=1e-3,
+                            g=(0.2, -1.0, 0.0), seed=14, n_particles=6000,
+                            meta=dict(d_p=worlds.D_P, rho_p=worlds.RHO_P, v0="zero", field="tg", nbox=nbox))
     raise KeyError(kind)
+
+
+def _particles(w, n=None):
+    """the world's seeded cloud; chains of boxes get it stretched over all boxes"""
+    parts = worlds.make_particles(w, n)
+    nbox = w.meta.get("nbox", 1)
+    if nbox > 1:
+        rng = np.random.default_rng(w.seed + 1)
+        parts["x"] = rng.uniform(-0.47, nbox - 0.53, len(parts["x"]))
+    return parts
 
 
 _cache = {}
@@ -79,7 +110,7 @@ def setup(kind, ctx):
     return w, sim, ptrs, idx
 
 
-KINDS = ["c1", "uniform3", "ring3", "ring2", "ring3b"]
+KINDS = ["c1", "uniform3", "ring3", "ring2", "ring3b", "chain2", "chain3"]
 
 
 @pytest.mark.parametrize("kind", KINDS)
@@ -88,6 +119,7 @@ def test_locate_bit_exact(kind, ctx):
     rng = np.random.default_rng(5)
     n = 200_000
     cols = [rng.uniform(-0.6, 0.6, n) for _ in range(w.dim)] + ([None] if w.dim == 2 else [])
+    cols[0] = rng.uniform(-0.6, w.meta.get("nbox", 1) - 0.4, n)
     adv = worlds.adversarial_points(w.arrays, rng, 20000)
     for x, y, z in (cols, adv):
         got = ctx.locate(x, y, z)
@@ -129,6 +161,7 @@ def test_interpolate(kind, ctx):
     rng = np.random.default_rng(9)
     n = 50_000
     cols = [rng.uniform(-0.5, 0.5, n) for _ in range(w.dim)] + ([None] if w.dim == 2 else [])
+    cols[0] = rng.uniform(-0.5, w.meta.get("nbox", 1) - 0.5, n)
     got = ctx.interpolate(*cols)
     fields = [w.u, w.v] + ([w.w] if w.dim == 3 else [])
     for comp, f in enumerate(fields):
@@ -161,7 +194,7 @@ def test_step_one(kind, ctx):
     """cells bit-exact; x, v within 1e-12 relative; forces within 1e-11 of the
     force scale (they are differences of O(1) velocities)"""
     w, sim, ptrs, idx = setup(kind, ctx)
-    parts = worlds.make_particles(w)
+    parts = _particles(w)
     got = _run_step(ctx, w, parts)
     cells, want = helpers.oracle_step(sim, ptrs, w, parts)
     assert np.array_equal(got["cell"], cells)
@@ -395,7 +428,7 @@ def test_full_size_c2_properties(ctx):
 
 
 @pytest.mark.parametrize("mode", ["0", "2", "3"])
-@pytest.mark.parametrize("kind", ["c1", "uniform3", "ring3", "ring2"])
+@pytest.mark.parametrize("kind", ["c1", "uniform3", "ring3", "ring2", "chain2"])
 def test_step_fast_paths(kind, mode, monkeypatch):
     """The production launch (no cell/force recording): compile-time force
     lists, lattice addressing on uniform trees, and the TMA-staged persistent
@@ -405,7 +438,7 @@ def test_step_fast_paths(kind, mode, monkeypatch):
     try:
         w, sim, ptrs, idx = setup(kind, c)
         n = 20011                                   # not a multiple of the 256-particle tile
-        parts = worlds.make_particles(w, n)
+        parts = _particles(w, n)
         c.particles_upload(**parts)
         for forces in (w.forces, (capi.FORCE_DRAG, capi.FORCE_BUOY), (capi.FORCE_LIFT,)):
             w2 = worlds.World(**{**w.__dict__, "forces": forces})
