@@ -15,6 +15,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#ifdef _OPENMP
+# include <omp.h>
+#endif
 #include "gfsb200_internal.h"
 
 typedef struct {
@@ -534,60 +537,108 @@ int gfsb200_tree_build_stencils (gfsb200_tree * t)
     }
   }
 
-  /* pass B: group by (vertex position, signature); ids in first-seen order */
-  vtable_t vt;
-  if (vtable_init (&vt, (uint64_t) (t->n_leaves*2 + 1024))) {
+  /* pass B: group by (vertex position, signature).  The hash table is sharded
+     by position: every thread scans all (leaf, corner) pairs, in ascending
+     order, but only inserts those whose position hashes to its shard, so the
+     first pair it sees for a group is that group's canonical representative
+     (the lowest e = leaf*nc + corner).  Vertex ids are then handed out in
+     ascending order of the representatives -- the same numbering a serial
+     first-seen scan gives, independent of the thread count. */
+  if ((int64_t) n*nc > INT32_MAX) {
     free (sig);
-    return gfsb200_fail (GFSB200_ERR_NOMEM, "build_stencils: out of memory");
+    return gfsb200_fail (GFSB200_ERR_UNSUPPORTED, "build_stencils: tree too large");
   }
   const double lattice = ldexp (1., GFSB200_MAX_LEVEL + 2);
-  int32_t nv = 0;
-  int32_t * rep = NULL;
-  int64_t * vkey = NULL;            /* [nv][3] lattice position of each vertex */
-  int64_t rep_cap = 0;
-  for (int32_t i = 0; i < n; i++) {
-    if ((t->flags[i] & (GFSB200_CELL_LEAF | GFSB200_CELL_BOUNDARY)) != GFSB200_CELL_LEAF)
-      continue;
-    double half = ldexp (1., -t->level[i])/2.;
-    for (int k = 0; k < nc; k++) {
-      int64_t key[3] = { 0, 0, 0 };
-      for (int l = 0; l < t->dim; l++) {
-	int d = cd[k][l];
-	double p = t->pos[3*i + (d >> 1)] + (d & 1 ? -half : half);
-	key[d >> 1] = (int64_t) llround (p*lattice);
-      }
-      int64_t e = (int64_t) i*nc + k;
-      if ((vt.used + 1)*10 > (int64_t) (vt.mask + 1)*6 && vtable_grow (&vt)) {
-	free (sig); free (vt.s); free (rep); free (vkey);
-	return gfsb200_fail (GFSB200_ERR_NOMEM, "build_stencils: out of memory");
-      }
-      vslot_t * s = vtable_find (&vt, key, sig[2*e], sig[2*e + 1]);
-      if (s->vid < 0) {
-	s->k[0] = key[0]; s->k[1] = key[1]; s->k[2] = key[2];
-	s->h1 = sig[2*e]; s->h2 = sig[2*e + 1];
-	s->vid = nv;
-	s->rep = (int32_t) 0;
-	if (nv >= rep_cap) {
-	  rep_cap = rep_cap ? rep_cap*2 : 1 << 16;
-	  int32_t * r2 = realloc (rep, (size_t) rep_cap*2*sizeof (int32_t));
-	  int64_t * k2 = realloc (vkey, (size_t) rep_cap*3*sizeof (int64_t));
-	  if (r2) rep = r2;
-	  if (k2) vkey = k2;
-	  if (!r2 || !k2) {
-	    free (sig); free (vt.s); free (rep); free (vkey);
-	    return gfsb200_fail (GFSB200_ERR_NOMEM, "build_stencils: out of memory");
+  int n_shards = 1;
+#ifdef _OPENMP
+  n_shards = omp_get_max_threads ();
+#endif
+  int oom = 0;
+#pragma omp parallel num_threads(n_shards)
+  {
+    int tid = 0;
+#ifdef _OPENMP
+    tid = omp_get_thread_num ();
+#endif
+    vtable_t vt;
+    if (vtable_init (&vt, (uint64_t) (t->n_leaves*2/n_shards + 1024))) {
+#pragma omp atomic write
+      oom = 1;
+    }
+    else {
+      for (int32_t i = 0; i < n && !oom; i++) {
+	if ((t->flags[i] & (GFSB200_CELL_LEAF | GFSB200_CELL_BOUNDARY)) != GFSB200_CELL_LEAF)
+	  continue;
+	const double half = ldexp (1., -t->level[i])/2.;
+	for (int k = 0; k < nc; k++) {
+	  int64_t key[3] = { 0, 0, 0 };
+	  for (int l = 0; l < t->dim; l++) {
+	    const int d = cd[k][l];
+	    const double p = t->pos[3*i + (d >> 1)] + (d & 1 ? -half : half);
+	    key[d >> 1] = (int64_t) llround (p*lattice);
 	  }
+	  if ((int) (vhash (key, 0) % (uint64_t) n_shards) != tid)
+	    continue;
+	  const int64_t e = (int64_t) i*nc + k;
+	  if ((vt.used + 1)*10 > (int64_t) (vt.mask + 1)*6 && vtable_grow (&vt)) {
+#pragma omp atomic write
+	    oom = 1;
+	    break;
+	  }
+	  vslot_t * sl = vtable_find (&vt, key, sig[2*e], sig[2*e + 1]);
+	  if (sl->vid < 0) {
+	    sl->k[0] = key[0]; sl->k[1] = key[1]; sl->k[2] = key[2];
+	    sl->h1 = sig[2*e]; sl->h2 = sig[2*e + 1];
+	    sl->vid = 0;
+	    sl->rep = (int32_t) e;
+	    vt.used++;
+	  }
+	  t->leaf_vtx[e] = sl->rep;          /* provisional: the representative pair */
 	}
-	rep[2*nv] = i; rep[2*nv + 1] = k;
-	vkey[3*nv] = key[0]; vkey[3*nv + 1] = key[1]; vkey[3*nv + 2] = key[2];
-	vt.used++;
-	nv++;
       }
-      t->leaf_vtx[e] = s->vid;
+      free (vt.s);
     }
   }
   free (sig);
-  free (vt.s);
+  if (oom)
+    return gfsb200_fail (GFSB200_ERR_NOMEM, "build_stencils: out of memory");
+  /* ids in ascending order of the representatives */
+  int32_t nv = 0;
+  int32_t * idmap = malloc ((size_t) n*nc*sizeof (int32_t));
+  if (!idmap)
+    return gfsb200_fail (GFSB200_ERR_NOMEM, "build_stencils: out of memory");
+  for (int64_t e = 0; e < (int64_t) n*nc; e++)
+    if (t->leaf_vtx[e] == e)
+      idmap[e] = nv++;
+  int32_t * rep = malloc ((size_t) (nv ? nv : 1)*2*sizeof (int32_t));
+  int64_t * vkey = malloc ((size_t) (nv ? nv : 1)*3*sizeof (int64_t));   /* lattice position of each vertex */
+  if (!rep || !vkey) {
+    free (idmap); free (rep); free (vkey);
+    return gfsb200_fail (GFSB200_ERR_NOMEM, "build_stencils: out of memory");
+  }
+#pragma omp parallel for schedule(static)
+  for (int64_t e = 0; e < (int64_t) n*nc; e++) {
+    const int32_t r = t->leaf_vtx[e];
+    if (r < 0)
+      continue;
+    if (r == e) {
+      const int32_t v = idmap[e], i = (int32_t) (e/nc);
+      const int k = (int) (e % nc);
+      const double half = ldexp (1., -t->level[i])/2.;
+      rep[2*v] = i; rep[2*v + 1] = k;
+      vkey[3*v] = vkey[3*v + 1] = vkey[3*v + 2] = 0;
+      for (int l = 0; l < t->dim; l++) {
+	const int d = cd[k][l];
+	const double p = t->pos[3*i + (d >> 1)] + (d & 1 ? -half : half);
+	vkey[3*v + (d >> 1)] = (int64_t) llround (p*lattice);
+      }
+    }
+  }
+#pragma omp parallel for schedule(static)
+  for (int64_t e = 0; e < (int64_t) n*nc; e++)
+    if (t->leaf_vtx[e] >= 0)
+      t->leaf_vtx[e] = idmap[t->leaf_vtx[e]];
+  free (idmap);
 
   /* pass C: CSR of the canonical stencils */
   t->vtx_off = malloc ((size_t) (nv + 1)*sizeof (int32_t));
