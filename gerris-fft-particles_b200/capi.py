@@ -19,6 +19,8 @@ LIB_DIR = os.path.join(_HERE, "lib")
 
 FORCE_DRAG, FORCE_LIFT, FORCE_BUOY, FORCE_INERTIAL, FORCE_ADDEDMASS = 1, 2, 3, 4, 5
 CELL_DESTROYED, CELL_BOUNDARY, CELL_LEAF = 1, 2, 4
+KERNEL_CONSTANT, KERNEL_GAUSSIAN, KERNEL_COMPACT = 0, 1, 2
+KERNEL_FIX_Z = 1
 MAX_FORCES = 8
 NODATA = float(np.finfo(np.float64).max)
 
@@ -51,6 +53,12 @@ class StepParamsC(C.Structure):
         ("record_cells", C.c_int32), ("record_forces", C.c_int32), ("cm_const", C.c_double),
         ("track_escapes", C.c_int32),
     ]
+
+
+class KernelC(C.Structure):
+    """gfsb200_kernel: the closed-form smoothing kernels of GfsSourceParticulate"""
+    _fields_ = [("kind", C.c_int32), ("p", C.c_int32), ("a", C.c_double), ("b", C.c_double),
+                ("flags", C.c_int32), ("record_norm", C.c_int32)]
 
 
 REFINE_FUNC = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.c_int, C.c_double, C.c_void_p)
@@ -115,6 +123,8 @@ def lib() -> C.CDLL:
         "gfsb200_deposit_volume": (i32, [vp]),
         "gfsb200_deposit_force": (i32, [vp, C.POINTER(StepParamsC)]),
         "gfsb200_deposit_all": (i32, [vp, C.POINTER(StepParamsC)]),
+        "gfsb200_deposit_force_smoothed": (i32, [vp, C.POINTER(StepParamsC), dbl, C.POINTER(KernelC)]),
+        "gfsb200_download_kernel_norm": (i32, [vp, vp, vp]),
         "gfsb200_deposit_select": (i32, [vp, i32]),
         "gfsb200_deposit_buffer": (i32, [vp, C.POINTER(vp), C.POINTER(i64)]),
         "gfsb200_download_deposit": (i32, [vp, i32, vp]),
@@ -450,6 +460,18 @@ class Context:
 
     def deposit_all(self, params: StepParams):
         _check(self._lib.gfsb200_deposit_all(self.handle, C.byref(params.c)), "deposit_all")
+
+    def deposit_force_smoothed(self, params: StepParams, rkernel: float, kind=KERNEL_GAUSSIAN, a=1.0, b=1.0,
+                               p=1, flags=0, record_norm=False):
+        """GfsSourceParticulate with its smoothing kernel (fills deposit components 1..dim)"""
+        k = KernelC(kind, p, a, b, flags, int(record_norm))
+        _check(self._lib.gfsb200_deposit_force_smoothed(self.handle, C.byref(params.c), rkernel, C.byref(k)),
+               "deposit_force_smoothed")
+
+    def download_kernel_norm(self):
+        corr, vol = np.empty(self.count), np.empty(self.count)
+        _check(self._lib.gfsb200_download_kernel_norm(self.handle, _ptr(corr), _ptr(vol)), "download_kernel_norm")
+        return corr, vol
 
     def deposit_select(self, which: int):
         _check(self._lib.gfsb200_deposit_select(self.handle, which), "deposit_select")

@@ -41,6 +41,9 @@ void gfsb200_launch_corner_values (const DevTree *, const DevField *, int, int64
 				   double *, cudaStream_t);
 void gfsb200_launch_deposit (const DevTree *, const DevField *, const DevParticles *, const DevStep *,
 			     int, double *, double *, double *, double *, cudaStream_t);
+void gfsb200_launch_deposit_smoothed (const DevTree *, const DevField *, const DevParticles *,
+				      const DevStep *, double, const gfsb200_kernel *, double *, double *,
+				      double *, double *, cudaStream_t);
 void gfsb200_launch_gather (int64_t, const int32_t *, int, const double * const *, double * const *,
 			    const uint32_t *, uint32_t *, cudaStream_t);
 void gfsb200_launch_particle_bc (const DevTree *, const DevParticles *, int, const int32_t *,
@@ -104,6 +107,8 @@ struct gfsb200_ctx {
   double * deposit;            /* the selected one */
   double * deposit_buf[2];
   int64_t deposit_count;
+  double * knorm;              /* [2][knorm_n] correction, volume of the last smoothed deposit */
+  int64_t knorm_cap, knorm_n;
   int step_minb;               /* __launch_bounds__ min blocks/SM variant of the step kernel */
   int step_mode;               /* 0: plain kernel; 2/3: TMA-staged persistent kernel, that many stages */
   /* timing */
@@ -142,6 +147,7 @@ static void free_tree (gfsb200_ctx * c)
   c->F.vtx_prev = c->F.acc = NULL;
   c->have_prev = c->acc_valid = false;
   cudaFree (c->deposit_buf[0]); cudaFree (c->deposit_buf[1]);
+  cudaFree (c->knorm); c->knorm = NULL; c->knorm_cap = c->knorm_n = 0;
   c->deposit = c->deposit_buf[0] = c->deposit_buf[1] = NULL; c->deposit_count = 0;
   c->have_tree = c->have_field = false;
 }
@@ -1033,6 +1039,56 @@ extern "C" int gfsb200_deposit_force (gfsb200_ctx * c, const gfsb200_step_params
 extern "C" int gfsb200_deposit_all (gfsb200_ctx * c, const gfsb200_step_params * p)
 {
   return deposit (c, p, 3);
+}
+
+extern "C" int gfsb200_deposit_force_smoothed (gfsb200_ctx * c, const gfsb200_step_params * p,
+						double rkernel, const gfsb200_kernel * kernel)
+{
+  if (!c || !c->have_tree) return gfsb200_fail (GFSB200_ERR_STATE, "deposit_force_smoothed: no tree resident");
+  if (!c->have_field) return gfsb200_fail (GFSB200_ERR_STATE, "deposit_force_smoothed: no field resident");
+  if (!kernel) return gfsb200_fail (GFSB200_ERR_ARG, "deposit_force_smoothed: null kernel");
+  if (kernel->kind < GFSB200_KERNEL_CONSTANT || kernel->kind > GFSB200_KERNEL_COMPACT)
+    return gfsb200_fail (GFSB200_ERR_UNSUPPORTED,
+			 "deposit_force_smoothed: kernel kind %d cannot be evaluated on the device", kernel->kind);
+  if (kernel->kind == GFSB200_KERNEL_COMPACT && (kernel->p < 0 || kernel->p > 64))
+    return gfsb200_fail (GFSB200_ERR_ARG, "deposit_force_smoothed: exponent %d out of range", kernel->p);
+  if (!(rkernel >= 0.)) return gfsb200_fail (GFSB200_ERR_ARG, "deposit_force_smoothed: rkernel must be >= 0");
+  /* the traversal keeps its path in 64 bits: GFSB200_MAX_LEVEL (20) levels x 3 bits fit */
+  DevStep S;
+  int r = make_step (p, &S);
+  if (r) return r;
+  CK (cudaSetDevice (c->device));
+  if ((r = prepare_inertial (c, &S))) return r;
+  if ((r = ensure_aux (c, c->n))) return r;
+  c->knorm_n = 0;
+  if (kernel->record_norm) {
+    if (c->n > c->knorm_cap) {
+      cudaFree (c->knorm); c->knorm = NULL; c->knorm_cap = 0;
+      CK (cudaMalloc ((void **) &c->knorm, 2*(size_t) c->n*sizeof (double)));
+      c->knorm_cap = c->n;
+    }
+    c->knorm_n = c->n;
+  }
+  const size_t n = c->T.n_cells;
+  CK (cudaMemsetAsync (c->deposit + n, 0, (size_t) c->T.dim*n*sizeof (double), c->stream));
+  DevParticles P = particles_view (c);
+  gfsb200_launch_deposit_smoothed (&c->T, &c->F, &P, &S, rkernel, kernel, c->deposit + n, c->deposit + 2*n,
+				   c->T.dim == 3 ? c->deposit + 3*n : NULL,
+				   kernel->record_norm ? c->knorm : NULL, c->stream);
+  CK (cudaGetLastError ());
+  return GFSB200_OK;
+}
+
+extern "C" int gfsb200_download_kernel_norm (gfsb200_ctx * c, double * correction, double * volume)
+{
+  if (!c || !c->knorm_n) return gfsb200_fail (GFSB200_ERR_STATE, "download_kernel_norm: no recorded normalisation");
+  CK (cudaSetDevice (c->device));
+  if (correction)
+    CK (cudaMemcpyAsync (correction, c->knorm, c->knorm_n*sizeof (double), cudaMemcpyDeviceToHost, c->stream));
+  if (volume)
+    CK (cudaMemcpyAsync (volume, c->knorm + c->knorm_n, c->knorm_n*sizeof (double), cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  return GFSB200_OK;
 }
 
 extern "C" int gfsb200_deposit_select (gfsb200_ctx * c, int which)

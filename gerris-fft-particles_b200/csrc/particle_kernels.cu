@@ -1031,6 +1031,178 @@ __global__ void inside_flag_kernel (int64_t n, const int32_t * __restrict__ cell
   if (i < n) flag[i] = cell[i] >= 0;
 }
 
+/* ------------------------------------------------------------------ */
+/* GfsSourceParticulate with its smoothing kernel                        */
+/* modules/particulatecommon.c:2087-2228                                 */
+
+/* stage 1: particulate->force = sum of the forces acting on the fluid
+ * (compute_forces_onfluid :753-765, every force but GfsForceBuoy); zero for a
+ * particle outside the domain (each force model returns 0 when
+ * gfs_domain_locate is NULL) */
+template <int DIM, bool LATTICE>
+__global__ void __launch_bounds__(256, 3)
+onfluid_force_kernel (DevTree T, DevField fld, DevParticles P, DevStep S)
+{
+  const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= P.n)
+    return;
+  const double x = P.x[i], y = P.y[i], z = DIM == 3 ? P.z[i] : 0.;
+  const Located L = locate<DIM, LATTICE> (T, x, y, z);
+  double Fx = 0., Fy = 0., Fz = 0.;
+  if (L.cell >= 0) {
+    double rho, mass = P.mass[i];
+    total_force<DIM, true, LATTICE, 0> (T, fld, S, L, x, y, z, P.vx[i], P.vy[i], DIM == 3 ? P.vz[i] : 0.,
+				       mass, P.volume[i], Fx, Fy, Fz, rho);
+    if (S.mutates_mass)
+      P.mass[i] = mass;
+  }
+  P.fx[i] = Fx; P.fy[i] = Fy; P.fz[i] = Fz;
+}
+
+/* The kernel GfsFunction evaluated at the normalised offset
+ * (gfs_function_spatial_value of distance_normalization, :2087-2098), in the
+ * reference's operation order: round-to-nearest intrinsics are never
+ * contracted into FMAs. */
+__device__ __forceinline__ double kernel_value (const gfsb200_kernel & K, double x, double y, double z)
+{
+  const double r2 = __dadd_rn (__dadd_rn (__dmul_rn (x, x), __dmul_rn (y, y)), __dmul_rn (z, z));
+  if (K.kind == GFSB200_KERNEL_GAUSSIAN)
+    return __dmul_rn (K.a, exp (__dmul_rn (-K.b, r2)));
+  if (K.kind == GFSB200_KERNEL_COMPACT) {
+    const double t = __dsub_rn (1., __dmul_rn (K.b, r2));
+    if (t <= 0.) return 0.;
+    double v = K.a;
+    for (int i = 0; i < K.p; i++) v = __dmul_rn (v, t);
+    return v;
+  }
+  return K.a;
+}
+
+/* gfs_domain_cell_traverse_condition (FTT_PRE_ORDER, FTT_TRAVERSE_LEAFS, -1)
+ * with cond_kernel (:2126-2156) as the pruning condition, over every GfsBox
+ * tree (src/domain.c:1516-1574, src/ftt.c:948-986): depth first, children in
+ * FTT order, destroyed children skipped without evaluating the condition.
+ * No stack: the child digits of the current path live in a 64-bit word, the
+ * centre is tracked with exact dyadic adds and undone on the way up.
+ * visit (cell, cx, cy, cz, half) is called for every leaf reached. */
+template <int DIM, typename Visit>
+__device__ __forceinline__ void traverse_kernel_support (const DevTree & T, double px, double py, double pz,
+							 double rkernel, Visit visit)
+{
+  constexpr int NCH = 1 << DIM;
+  const double SQ = DIM == 3 ? 1.7320508075688772 : 1.4142135623730951;   /* sqrt(3.), sqrt(2.) */
+  for (int r = 0; r < T.n_box_roots; r++) {
+    int cell = r, depth = 0;
+    unsigned long long path = 0;
+    double cx = T.root_pos[r][0], cy = T.root_pos[r][1], cz = DIM == 3 ? T.root_pos[r][2] : 0.;
+    double size = 0.5*T.root_size;             /* ftt_cell_size (cell)/2. */
+    for (;;) {
+      const int c0 = __ldg (T.child0 + cell);
+      bool descend = false;
+      if (c0 != CHILD_DESTROYED) {
+	const double dx = __dsub_rn (cx, px), dy = __dsub_rn (cy, py);
+	double d2 = __dadd_rn (__dmul_rn (dx, dx), __dmul_rn (dy, dy));
+	if (DIM == 3) {
+	  const double dz = __dsub_rn (cz, pz);
+	  d2 = __dadd_rn (d2, __dmul_rn (dz, dz));
+	}
+	bool ok = __dsub_rn (__dsqrt_rn (d2), __dmul_rn (size, SQ)) <= rkernel;
+	if (!ok)          /* "check also if the bubble is inside the cell" */
+	  ok = !(px > cx + size || px < cx - size || py > cy + size || py < cy - size ||
+		 (DIM == 3 && (pz > cz + size || pz < cz - size)));
+	if (ok) {
+	  if (c0 < 0)
+	    visit (cell, cx, cy, cz, size);
+	  else
+	    descend = true;
+	}
+      }
+      if (descend) {
+	size *= 0.5;
+	cell = c0; depth++; path <<= DIM;
+	cx -= size; cy += size;                /* child 0 sits at (-,+,+) */
+	if (DIM == 3) cz += size;
+	continue;
+      }
+      /* next sibling, or up until there is one */
+      bool done = false;
+      for (;;) {
+	if (depth == 0) { done = true; break; }
+	const int n = (int) (path & (NCH - 1));
+	cx -= (n & 1) ? size : -size;
+	cy -= (n & 2) ? -size : size;
+	if (DIM == 3) cz -= (n & 4) ? -size : size;
+	if (n < NCH - 1) {
+	  const int m = n + 1;
+	  cell++; path++;
+	  cx += (m & 1) ? size : -size;
+	  cy += (m & 2) ? -size : size;
+	  if (DIM == 3) cz += (m & 4) ? -size : size;
+	  break;
+	}
+	cell = __ldg (T.parent + cell);
+	path >>= DIM; size *= 2.; depth--;
+      }
+      if (done) break;
+    }
+  }
+}
+
+/* stage 2 (source_particulate_event :2207-2221), one thread per particle:
+ * pass 1 accumulates kd.volume and kd.correction in the reference's traversal
+ * order (kernel_volume :2108-2119), pass 2 scatters
+ *   u_c[cell] -= F_c/rho/V_cell * K/correction          (diffuse_force :2158-2175)
+ * with fp64 atomics.  Neighbouring (cell-sorted) particles walk nearly the same
+ * cells in lock step. */
+template <int DIM>
+__global__ void __launch_bounds__(128)
+smoothed_deposit_kernel (DevTree T, DevField fld, DevParticles P, double rho_const, double rkernel,
+			 gfsb200_kernel K, double * __restrict__ f0, double * __restrict__ f1,
+			 double * __restrict__ f2, double * __restrict__ norm)
+{
+  const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= P.n)
+    return;
+  const double px = P.x[i], py = P.y[i], pz = DIM == 3 ? P.z[i] : 0.;
+  const double Fx = P.fx[i], Fy = P.fy[i], Fz = DIM == 3 ? P.fz[i] : 0.;
+  /* nothing to deposit (outside the domain, or no force): the reference would
+     subtract zeros */
+  if (!norm && Fx == 0. && Fy == 0. && Fz == 0.)
+    return;
+  const double rb = pow (__ddiv_rn (__dmul_rn (3., P.volume[i]), 4.*M_PI), 1./3.);
+  const bool fixz = (K.flags & GFSB200_KERNEL_FIX_Z) != 0;
+
+  double volume = 0., correction = 0.;
+  traverse_kernel_support<DIM> (T, px, py, pz, rkernel,
+    [&] (int cell, double cx, double cy, double cz, double half) {
+      const double h = 2.*half, cellvol = DIM == 3 ? h*h*h : h*h;     /* powers of two: exact */
+      volume = __dadd_rn (volume, cellvol);
+      const double qx = __ddiv_rn (__dsub_rn (cx, px), rb), qy = __ddiv_rn (__dsub_rn (cy, py), rb);
+      const double qz = DIM == 3 ? __ddiv_rn (__dsub_rn (fixz ? cz : 0., pz), rb) : 0.;
+      correction = __dadd_rn (correction, __dmul_rn (kernel_value (K, qx, qy, qz), cellvol));
+    });
+  correction = __ddiv_rn (correction, volume);
+  if (norm) {
+    norm[i] = correction;
+    norm[P.n + i] = volume;
+  }
+  if (!(correction > 1.e-10))
+    return;
+  traverse_kernel_support<DIM> (T, px, py, pz, rkernel,
+    [&] (int cell, double cx, double cy, double cz, double half) {
+      const double h = 2.*half, cellvol = DIM == 3 ? h*h*h : h*h;
+      const double rho = fld.alpha ? __ddiv_rn (1., fld.alpha[cell]) : rho_const;
+      const double qx = __ddiv_rn (__dsub_rn (cx, px), rb), qy = __ddiv_rn (__dsub_rn (cy, py), rb);
+      const double qz = DIM == 3 ? __ddiv_rn (__dsub_rn (fixz ? cz : 0., pz), rb) : 0.;
+      const double k = kernel_value (K, qx, qy, qz);
+      /* F/rho/V_cell*K/correction, left to right */
+      atomicAdd (f0 + cell, -__ddiv_rn (__dmul_rn (__ddiv_rn (__ddiv_rn (Fx, rho), cellvol), k), correction));
+      atomicAdd (f1 + cell, -__ddiv_rn (__dmul_rn (__ddiv_rn (__ddiv_rn (Fy, rho), cellvol), k), correction));
+      if (DIM == 3)
+	atomicAdd (f2 + cell, -__ddiv_rn (__dmul_rn (__ddiv_rn (__ddiv_rn (Fz, rho), cellvol), k), correction));
+    });
+}
+
 inline unsigned grid_for (int64_t n, int threads) { return (unsigned) ((n + threads - 1)/threads); }
 
 } // namespace
@@ -1175,6 +1347,29 @@ void gfsb200_launch_deposit (const DevTree * T, const DevField * F, const DevPar
 #undef DEP_PR
 #undef DEP_W
 #undef DEP
+}
+
+/* GfsSourceParticulate with a smoothing kernel: on-fluid forces into P.fx/fy/fz,
+ * then the two conditional traversals per particle.  norm (may be NULL):
+ * [2][n] per-particle correction and volume. */
+void gfsb200_launch_deposit_smoothed (const DevTree * T, const DevField * F, const DevParticles * P,
+				      const DevStep * S, double rkernel, const gfsb200_kernel * K,
+				      double * f0, double * f1, double * f2, double * norm,
+				      cudaStream_t st)
+{
+  if (P->n <= 0) return;
+  const bool lat = T->lattice_n1 > 0;
+  const unsigned g = grid_for (P->n, 256);
+  if (T->dim == 3) {
+    if (lat) onfluid_force_kernel<3, true><<<g, 256, 0, st>>> (*T, *F, *P, *S);
+    else     onfluid_force_kernel<3, false><<<g, 256, 0, st>>> (*T, *F, *P, *S);
+    smoothed_deposit_kernel<3><<<grid_for (P->n, 128), 128, 0, st>>> (*T, *F, *P, S->rho, rkernel, *K, f0, f1, f2, norm);
+  }
+  else {
+    if (lat) onfluid_force_kernel<2, true><<<g, 256, 0, st>>> (*T, *F, *P, *S);
+    else     onfluid_force_kernel<2, false><<<g, 256, 0, st>>> (*T, *F, *P, *S);
+    smoothed_deposit_kernel<2><<<grid_for (P->n, 128), 128, 0, st>>> (*T, *F, *P, S->rho, rkernel, *K, f0, f1, f2, norm);
+  }
 }
 
 void gfsb200_launch_particle_bc (const DevTree * T, const DevParticles * P, int n_esc,

@@ -20,7 +20,8 @@
  *   integrator           gfs_particulate_event              modules/particulatecommon.c:768-842
  *   list driver          gfs_particle_list_event            modules/particulatecommon.c:980-1015
  *   deposition           particulate_field_event            modules/particulatecommon.c:1934-1957
- *                        source_particulate_event (NGP)     modules/particulatecommon.c:2177-2228
+ *                        source_particulate_event           modules/particulatecommon.c:2177-2228
+ *                          (nearest cell, and with the smoothing kernel :2087-2175)
  *   tracer advection     gfs_domain_advect_point            src/domain.c:2764-2788
  *
  * All functions returning int return GFSB200_OK (0) or a negative error code;
@@ -273,6 +274,36 @@ int gfsb200_deposit_volume (gfsb200_ctx * c);
 int gfsb200_deposit_force (gfsb200_ctx * c, const gfsb200_step_params * p);
 /* both of the above in one pass over the particles (one locate, one kernel) */
 int gfsb200_deposit_all (gfsb200_ctx * c, const gfsb200_step_params * p);
+/* GfsSourceParticulate WITH its smoothing kernel (source_particulate_event,
+ * modules/particulatecommon.c:2177-2228): the force of every particle on the
+ * fluid is spread over the leaves reached by the reference's conditional
+ * traversal (cond_kernel :2126-2156: cells whose circumscribed sphere comes
+ * within `rkernel' -- an absolute distance, as in the reference -- of the
+ * particle, or that contain it), weighted by kernel(offset/r_b)/correction
+ * with the per-particle normalisation of kernel_volume :2108-2119:
+ *   field_c[cell] -= F_c / rho(cell) / V_cell * K / correction.
+ * The user's `kernel = <GfsFunction>' must be one of the closed forms below
+ * (the offset (x,y,z) is in particle radii r_b = (3V/4pi)^(1/3)); anything else
+ * stays on the host.  NB the reference's distance_normalization (:2087-2098)
+ * zeroes the z offset before using it, so in 3D z = -z_particle/r_b for every
+ * cell; that is reproduced unless GFSB200_KERNEL_FIX_Z is set. */
+#define GFSB200_KERNEL_CONSTANT 0   /* K = a */
+#define GFSB200_KERNEL_GAUSSIAN 1   /* K = a exp(-b (x^2+y^2+z^2)) */
+#define GFSB200_KERNEL_COMPACT  2   /* K = a (1 - b r^2)^p where b r^2 < 1, else 0 */
+#define GFSB200_KERNEL_FIX_Z    1   /* flags: z offset = (z_cell - z_particle)/r_b */
+typedef struct {
+  int32_t kind;                    /* GFSB200_KERNEL_* */
+  int32_t p;                       /* COMPACT: integer exponent >= 0 */
+  double a, b;
+  int32_t flags;
+  int32_t record_norm;             /* 1: keep each particle's (correction, volume) for
+				      gfsb200_download_kernel_norm */
+} gfsb200_kernel;
+/* fills deposit components 1..dim (zeroed first); component 0 is untouched */
+int gfsb200_deposit_force_smoothed (gfsb200_ctx * c, const gfsb200_step_params * p,
+				    double rkernel, const gfsb200_kernel * kernel);
+/* per-particle normalisation of the last smoothed deposit issued with record_norm = 1 */
+int gfsb200_download_kernel_norm (gfsb200_ctx * c, double * correction, double * volume);
 /* There are two deposition buffers; select which one the deposit calls, the
  * buffer query and the download use (default 0).  Alternating them lets the
  * all-reduce of step n run on another stream while step n+1 deposits. */

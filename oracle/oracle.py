@@ -15,6 +15,12 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 FORCE_DRAG, FORCE_LIFT, FORCE_BUOY, FORCE_INERTIAL, FORCE_ADDEDMASS = 1, 2, 3, 4, 5
+KERNEL_CONSTANT, KERNEL_GAUSSIAN, KERNEL_COMPACT = 0, 1, 2
+
+
+class Kernel(C.Structure):
+    """OraKernel: closed-form smoothing kernels of GfsSourceParticulate"""
+    _fields_ = [("kind", C.c_int), ("a", C.c_double), ("b", C.c_double), ("p", C.c_int), ("flags", C.c_int)]
 
 
 class StepParams(C.Structure):
@@ -83,6 +89,7 @@ def load(dim: int) -> C.CDLL:
         "ora_list_step": (None, [vp, vp, C.POINTER(StepParams), i32]),
         "ora_deposit_volume": (None, [vp, vp, i32]),
         "ora_deposit_force": (None, [vp, vp, C.POINTER(StepParams), i32]),
+        "ora_deposit_force_smoothed": (None, [vp, vp, C.POINTER(StepParams), i32, dbl, C.POINTER(Kernel), vp, vp]),
         "ora_advect_points": (None, [vp, lng, vp, vp, vp, dbl]),
         "ora_max_threads": (i32, []),
     }
@@ -265,3 +272,12 @@ class ParticleList:
 
     def deposit_force(self, params: StepParams, ivar0):
         self.sim.L.ora_deposit_force(self.sim.h, self.h, C.byref(params), ivar0)
+
+    def deposit_force_smoothed(self, params: StepParams, ivar0, rkernel, kernel: Kernel):
+        """source_particulate_event with its smoothing kernel; returns the per-particle
+        (correction, volume) normalisation"""
+        n = len(self)
+        corr, vol = np.empty(n), np.empty(n)
+        self.sim.L.ora_deposit_force_smoothed(self.sim.h, self.h, C.byref(params), ivar0, rkernel,
+                                              C.byref(kernel), _p(corr), _p(vol))
+        return corr, vol

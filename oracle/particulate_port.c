@@ -20,6 +20,7 @@
  *   remove_particles_not_in_domain       modules/particulatecommon.c:955-969
  *   GfsParticulateField deposit          modules/particulatecommon.c:1929-1957
  *   force deposit (single-cell limit)    modules/particulatecommon.c:753-765, 2158-2228
+ *   force deposit with smoothing kernel  modules/particulatecommon.c:2087-2228
  *   passive tracer advection             src/particle.c:31-44, src/domain.c:2764-2788
  *   particle BCs (periodic wrap / drop)  modules/particulatecommon.c:3058-3214, 3318-3395
  *
@@ -1360,6 +1361,164 @@ void ora_deposit_force (OraSim * sim, OraList * l, const OraStepParams * par, in
       for (c = 0; c < FTT_DIMENSION; c++)
 	GFS_VALUEI (cell, ivar0 + c) -= (&p->force.x)[c]/liq_rho/cellvol;
     }
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/* GfsSourceParticulate with its smoothing kernel:                       */
+/* modules/particulatecommon.c:2087-2228                                 */
+
+/* The user's `kernel = ...' GfsFunction, restricted to the closed forms the
+ * device evaluates (gfs_function_spatial_value of a spatial function of the
+ * normalised offset, src/utils.c:1476-1494, without coordinate mapping). */
+enum { ORA_KERNEL_CONSTANT = 0, ORA_KERNEL_GAUSSIAN = 1, ORA_KERNEL_COMPACT = 2 };
+
+typedef struct {
+  int kind;
+  double a, b;         /* CONSTANT: a;  GAUSSIAN: a*exp(-b*r2);  COMPACT: a*(1 - b*r2)^p, 0 where b*r2 >= 1 */
+  int p;
+  int flags;           /* bit 0: z offset taken from the cell centre (see distance_normalization below) */
+} OraKernel;
+
+static gdouble kernel_function_value (const OraKernel * k, const FttVector * q)
+{
+  gdouble r2 = q->x*q->x + q->y*q->y + q->z*q->z;
+  switch (k->kind) {
+  case ORA_KERNEL_CONSTANT: return k->a;
+  case ORA_KERNEL_GAUSSIAN: return k->a*exp (- k->b*r2);
+  case ORA_KERNEL_COMPACT: {
+    gdouble t = 1. - k->b*r2, v = k->a;
+    int i;
+    if (t <= 0.) return 0.;
+    for (i = 0; i < k->p; i++) v *= t;
+    return v;
+  }
+  }
+  g_assert_not_reached ();
+  return 0.;
+}
+
+/* modules/particulatecommon.c:2087-2098.  NB the reference zeroes pos1->z
+ * BEFORE using it in 3D, so the z offset is (0 - z_p)/rb whatever the cell;
+ * kept (flags bit 0 selects the evidently intended (z_c - z_p)/rb). */
+static void distance_normalization (FttVector * pos1, OraParticulate * p, int flags)
+{
+  gdouble rb = pow (3.*p->volume/(4.*M_PI), 1./3.);
+  FttVector * pos2 = &p->pos;
+  gdouble zc = pos1->z;
+  pos1->x = (pos1->x - pos2->x)/rb;
+  pos1->y = (pos1->y - pos2->y)/rb;
+  pos1->z = 0.;
+#if !FTT_2D
+  if (flags & 1) pos1->z = zc;
+  pos1->z = (pos1->z - pos2->z)/rb;
+#endif
+}
+
+typedef struct {
+  gdouble correction, volume;
+  OraParticulate * p;
+  const OraKernel * kernel_function;
+  int ivar0;
+  OraCtx * ctx;
+} OraKernelData;
+
+/* :2108-2119 */
+static void kernel_volume (FttCell * cell, OraKernelData * kd)
+{
+  gdouble cellvol = gfs_cell_volume (cell, &kd->ctx->sim->domain);
+  FttVector pos;
+
+  kd->volume += cellvol;
+  ftt_cell_pos (cell, &pos);
+  distance_normalization (&pos, kd->p, kd->kernel_function->flags);
+  kd->correction += kernel_function_value (kd->kernel_function, &pos)*cellvol;
+}
+
+typedef struct {
+  FttVector * pos;
+  gdouble distance;
+} OraCondData;
+
+/* :2126-2156 */
+static gboolean cond_kernel (FttCell * cell, gpointer data)
+{
+  OraCondData * p = data;
+  FttVector pos;
+  gdouble radeq, size;
+
+  ftt_cell_pos (cell, &pos);
+  size = ftt_cell_size (cell)/2.;
+#if FTT_2D
+  radeq = size*sqrt (2.);
+#else
+  radeq = size*sqrt (3.);
+#endif
+  if (ftt_vector_distance (&pos, p->pos) - radeq <= p->distance)
+    return TRUE;
+  if (p->pos->x > pos.x + size || p->pos->x < pos.x - size ||
+      p->pos->y > pos.y + size || p->pos->y < pos.y - size
+#if !FTT_2D
+      || p->pos->z > pos.z + size || p->pos->z < pos.z - size
+#endif
+      )
+    return FALSE;
+  return TRUE;
+}
+
+/* :2158-2175 */
+static void diffuse_force (FttCell * cell, OraKernelData * kd)
+{
+  FttVector pos;
+  FttComponent c;
+  gdouble cellvol, liq_rho;
+
+  ftt_cell_pos (cell, &pos);
+  distance_normalization (&pos, kd->p, kd->kernel_function->flags);
+  cellvol = gfs_cell_volume (cell, &kd->ctx->sim->domain);
+  liq_rho = fluid_rho_at (kd->ctx, cell);
+  if (kd->correction > 1.e-10)
+    for (c = 0; c < FTT_DIMENSION; c++)
+      GFS_VALUEI (cell, kd->ivar0 + c) -= (&kd->p->force.x)[c]/liq_rho/cellvol*
+	kernel_function_value (kd->kernel_function, &pos)/kd->correction;
+}
+
+/* source_particulate_event, :2177-2228: forces recomputed without buoyancy for
+ * every particle, then per particle two conditional traversals of every GfsBox
+ * tree (gfs_domain_cell_traverse_condition, src/domain.c:1516-1574 ->
+ * ftt_cell_traverse_condition, the reference's own object code): the
+ * normalisation, then the deposit.  `rkernel' is used as an absolute distance
+ * (:2211; influencerad :2210 is computed and never used).  The reset of the
+ * target variables is done by the caller.  correction_out/volume_out (may be
+ * NULL) receive the per-particle normalisation for the tests. */
+void ora_deposit_force_smoothed (OraSim * sim, OraList * l, const OraStepParams * par, int ivar0,
+				 double rkernel, const OraKernel * kernel,
+				 double * correction_out, double * volume_out)
+{
+  OraCtx ctx = { sim, par };
+  long i;
+  int k, b;
+  FttComponent c;
+  for (i = 0; i < l->n; i++) {
+    OraParticulate * p = l->p[i];
+    for (c = 0; c < 3; c++)
+      (&p->force.x)[c] = 0.;
+    for (k = 0; k < par->n_forces; k++)
+      compute_forces_onfluid (&ctx, par->force[k], p);
+  }
+  for (i = 0; i < l->n; i++) {
+    OraParticulate * p = l->p[i];
+    OraCondData cd = { &p->pos, rkernel };
+    OraKernelData kd = { 0., 0., p, kernel, ivar0, &ctx };
+    for (b = 0; b < sim->nbox; b++)
+      ftt_cell_traverse_condition (sim->box[b], FTT_PRE_ORDER, FTT_TRAVERSE_LEAFS, -1,
+				   (FttCellTraverseFunc) kernel_volume, &kd, cond_kernel, &cd);
+    kd.correction /= kd.volume;
+    if (correction_out) correction_out[i] = kd.correction;
+    if (volume_out) volume_out[i] = kd.volume;
+    for (b = 0; b < sim->nbox; b++)
+      ftt_cell_traverse_condition (sim->box[b], FTT_PRE_ORDER, FTT_TRAVERSE_LEAFS, -1,
+				   (FttCellTraverseFunc) diffuse_force, &kd, cond_kernel, &cd);
   }
 }
 

@@ -375,6 +375,64 @@ def test_deposit(kind, ctx):
     assert abs(total - parts["volume"][inside].sum()) <= 1e-12 * parts["volume"].sum()
 
 
+@pytest.mark.parametrize("kind,rk,kernel,flags", [
+    ("c1", 0.06, (capi.KERNEL_GAUSSIAN, 1.0, 2e-4, 1), 0),
+    ("ring3", 0.04, (capi.KERNEL_COMPACT, 2.0, 1e-4, 2), 0),
+    ("ring3", 0.03, (capi.KERNEL_GAUSSIAN, 1.0, 1e-4, 1), capi.KERNEL_FIX_Z),
+    ("ring2", 0.05, (capi.KERNEL_CONSTANT, 1.0, 0.0, 1), 0),
+    ("chain2", 0.08, (capi.KERNEL_GAUSSIAN, 0.5, 3e-4, 1), 0),
+    ("uniform3", 0.0, (capi.KERNEL_COMPACT, 1.0, 1e-5, 1), 0),
+])
+def test_deposit_smoothed(kind, rk, kernel, flags, ctx):
+    """GfsSourceParticulate with its smoothing kernel (source_particulate_event,
+    modules/particulatecommon.c:2087-2228).  The set of leaves each particle reaches
+    is bit-exact (its exact volume sum); the correction is summed in the reference's
+    traversal order and agrees to 1e-13 (device pow/exp vs libm); the deposited field sums
+    over particles in a different order (atomics): abs tol 1e-12 * max|field|."""
+    w, sim, ptrs, idx = setup(kind, ctx)
+    parts = _particles(w, 3000)
+    if kind != "chain2":                       # a few particles outside the domain (zero force)
+        parts["x"][:5] = 0.7
+    ctx.particles_upload(**parts)
+    kk, ka, kb, kp = kernel
+    ctx.deposit_force_smoothed(w.step_params(), rk, kk, ka, kb, kp, flags, record_norm=True)
+    corr, vol = ctx.download_kernel_norm()
+    live = (w.arrays.flags & capi.CELL_DESTROYED) == 0
+    plist = ora.ParticleList(sim, *[parts[k] for k in ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")])
+    zero = np.zeros(int(live.sum()))
+    for iv in range(4, 4 + w.dim):
+        sim.set_values(iv, ptrs[live], zero)
+    wcorr, wvol = plist.deposit_force_smoothed(helpers.oracle_params(w), 4, rk, ora.Kernel(kk, ka, kb, kp, flags))
+    assert np.array_equal(vol, wvol)
+    # r_b = pow (3V/4pi, 1/3) and exp differ from libm by <= 1-2 ulp, which moves every kernel value
+    # by a few ulp: the correction agrees to 1e-13, not bitwise (a constant kernel is exact)
+    ok = np.isfinite(wcorr)
+    assert np.array_equal(ok, np.isfinite(corr))           # 0/0 for particles outside the domain
+    if kk == capi.KERNEL_CONSTANT:
+        assert np.array_equal(corr[ok], wcorr[ok])
+    else:
+        assert np.abs(corr[ok] - wcorr[ok]).max() <= 1e-13 * np.abs(wcorr[ok]).max()
+    assert (wcorr > 1e-10).any()
+    for comp in range(w.dim):
+        got = ctx.download_deposit(1 + comp)[live]
+        want = sim.get_values(4 + comp, ptrs[live])
+        assert np.abs(want).max() > 0
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max(), comp
+    # without record_norm the kernel skips force-free particles; same field
+    ctx.deposit_force_smoothed(w.step_params(), rk, kk, ka, kb, kp, flags)
+    for comp in range(w.dim):
+        again = ctx.download_deposit(1 + comp)[live]
+        want = sim.get_values(4 + comp, ptrs[live])
+        assert np.abs(again - want).max() <= 1e-12 * np.abs(want).max(), comp
+
+
+def test_deposit_smoothed_rejects_unknown_kernel(ctx):
+    w, sim, ptrs, idx = setup("c1", ctx)
+    ctx.particles_upload(**_particles(w, 10))
+    with pytest.raises(capi.GfsB200Error):
+        ctx.deposit_force_smoothed(w.step_params(), 0.1, kind=7)
+
+
 def test_empty_and_single_particle(ctx):
     w, sim, ptrs, idx = setup("uniform3", ctx)
     empty = {k: np.zeros(0) for k in ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")}

@@ -146,3 +146,96 @@ def test_reference_call_pattern_equals_fused():
     _, b = helpers.oracle_step(sim, ptrs, w, parts, pattern=1)
     for k in ("x", "y", "z", "vx", "vy", "vz", "fx", "fy", "fz"):
         assert np.array_equal(a[k], b[k])
+
+
+def smoothed_deposit_numpy(a, dim, parts, force, rho, rkernel, kernel, fix_z=False):
+    """Independent numpy restatement of source_particulate_event with its kernel
+    (modules/particulatecommon.c:2087-2228): the visited leaves are those whose
+    whole ancestor chain passes cond_kernel; returns (fields [dim][n_cells],
+    correction, volume)."""
+    n_cells = a.n_cells
+    size = 0.5 ** a.level.astype(float) / 2.0
+    radeq = size * (np.sqrt(3.0) if dim == 3 else np.sqrt(2.0))
+    leaf = (a.child0 < 0) & ((a.flags & capi.CELL_DESTROYED) == 0)
+    cellvol = (2 * size) ** dim
+    out = np.zeros((dim, n_cells))
+    n = len(parts["x"])
+    corr, vol = np.zeros(n), np.zeros(n)
+    order = np.argsort(a.level, kind="stable")
+    for i in range(n):
+        p = np.array([parts["x"][i], parts["y"][i], parts["z"][i] if dim == 3 else 0.0])
+        d = a.pos - p
+        if dim == 3:
+            dist = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2])
+        else:
+            dist = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1])
+        ok = dist - radeq <= rkernel
+        inside = np.ones(n_cells, bool)
+        for c in range(dim):
+            inside &= ~((p[c] > a.pos[:, c] + size) | (p[c] < a.pos[:, c] - size))
+        ok |= inside
+        ok &= (a.flags & capi.CELL_DESTROYED) == 0
+        reach = np.zeros(n_cells, bool)
+        reach[:a.n_box_roots] = ok[:a.n_box_roots]
+        for lv in range(a.min_level + 1, a.max_level + 1):
+            sel = np.nonzero(a.level == lv)[0]
+            reach[sel] = ok[sel] & reach[a.parent[sel]]
+        vis = np.nonzero(reach & leaf)[0]
+        rb = (3.0 * parts["volume"][i] / (4.0 * np.pi)) ** (1.0 / 3.0)
+        q = (a.pos[vis] - p) / rb
+        if dim == 2:
+            q[:, 2] = 0.0
+        elif not fix_z:
+            q[:, 2] = (0.0 - p[2]) / rb
+        r2 = q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1] + q[:, 2] * q[:, 2]
+        kind, ka, kb, kp = kernel
+        if kind == ora.KERNEL_CONSTANT:
+            K = np.full(len(vis), ka)
+        elif kind == ora.KERNEL_GAUSSIAN:
+            K = ka * np.exp(-kb * r2)
+        else:
+            t = 1.0 - kb * r2
+            K = np.where(t > 0, ka * t ** kp, 0.0)
+        vol[i] = cellvol[vis].sum()
+        corr[i] = (K * cellvol[vis]).sum() / vol[i]
+        if corr[i] > 1e-10:
+            for c in range(dim):
+                np.subtract.at(out[c], vis, force[c][i] / rho / cellvol[vis] * K / corr[i])
+    return out, corr, vol
+
+
+@pytest.mark.parametrize("name,rk,kernel", [
+    ("c1_l5", 0.06, (ora.KERNEL_GAUSSIAN, 1.0, 2e-4)),
+    ("ring_3_6", 0.05, (ora.KERNEL_COMPACT, 2.0, 1e-4, 2)),
+    ("ring_3_6", 0.0, (ora.KERNEL_CONSTANT, 1.0, 0.0)),
+])
+def test_smoothed_deposit_matches_numpy_restatement(name, rk, kernel):
+    """the oracle's conditional traversals (the reference's ftt_cell_traverse_condition
+    object code + restated cond_kernel / kernel_volume / diffuse_force) against a
+    brute-force numpy restatement over all cells"""
+    w = _world(name)
+    a = w.arrays
+    sim, ptrs = helpers.matched_oracle(w)
+    parts = worlds.make_particles(w, 60)
+    plist = ora.ParticleList(sim, *[parts[k] for k in COLS])
+    live = (a.flags & capi.CELL_DESTROYED) == 0
+    for iv in range(4, 4 + w.dim):
+        sim.set_values(iv, ptrs[live], np.zeros(int(live.sum())))
+    kind, ka, kb = kernel[:3]
+    kp = kernel[3] if len(kernel) > 3 else 1
+    par = helpers.oracle_params(w)
+    corr, vol = plist.deposit_force_smoothed(par, 4, rk, ora.Kernel(kind, ka, kb, kp, 0))
+    st = plist.get()          # force = on-fluid force (drag[, lift])
+    force = [st["fx"], st["fy"], st["fz"]]
+    want, wcorr, wvol = smoothed_deposit_numpy(a, w.dim, parts, force, w.rho, rk, (kind, ka, kb, kp))
+    assert np.array_equal(vol, wvol)                       # same set of visited leaves (exact sums)
+    assert np.allclose(corr, wcorr, rtol=1e-13, atol=0)
+    assert (corr > 1e-10).any()
+    for c in range(w.dim):
+        got = np.zeros(a.n_cells)
+        got[live] = sim.get_values(4 + c, ptrs[live])
+        assert np.abs(want[c]).max() > 0
+        assert np.abs(got - want[c]).max() <= 1e-12 * np.abs(want[c]).max()
+    if rk == 0.0:
+        # rkernel = 0: only cells whose circumscribed sphere contains the particle
+        assert vol.max() <= (2 ** w.dim + 8) * (0.5 ** a.min_level) ** w.dim
