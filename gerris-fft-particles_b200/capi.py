@@ -61,6 +61,7 @@ class KernelC(C.Structure):
                 ("flags", C.c_int32), ("record_norm", C.c_int32)]
 
 
+KERNEL_FUNC = C.CFUNCTYPE(C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p)
 REFINE_FUNC = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.c_int, C.c_double, C.c_void_p)
 
 _lib = None
@@ -125,6 +126,7 @@ def lib() -> C.CDLL:
         "gfsb200_deposit_all": (i32, [vp, C.POINTER(StepParamsC)]),
         "gfsb200_deposit_force_smoothed": (i32, [vp, C.POINTER(StepParamsC), dbl, C.POINTER(KernelC)]),
         "gfsb200_download_kernel_norm": (i32, [vp, vp, vp]),
+        "gfsb200_kernel_fit": (i32, [KERNEL_FUNC, vp, i32, C.POINTER(KernelC)]),
         "gfsb200_deposit_select": (i32, [vp, i32]),
         "gfsb200_deposit_buffer": (i32, [vp, C.POINTER(vp), C.POINTER(i64)]),
         "gfsb200_download_deposit": (i32, [vp, i32, vp]),
@@ -154,6 +156,14 @@ def _ptr(a: Optional[np.ndarray]):
 
 def _f64(a) -> Optional[np.ndarray]:
     return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def kernel_fit(func, dim: int):
+    """gfsb200_kernel_fit of a Python callable f(x, y, z); returns a KernelC or raises"""
+    k = KernelC()
+    cb = KERNEL_FUNC(lambda x, y, z, _d: float(func(x, y, z)))
+    _check(lib().gfsb200_kernel_fit(cb, None, dim, C.byref(k)), "kernel_fit")
+    return k
 
 
 class Tree:

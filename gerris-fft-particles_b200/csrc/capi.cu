@@ -69,6 +69,7 @@ struct gfsb200_ctx {
   bool have_tree;
   DevTree T;
   int32_t * d_child0, * d_neighbor, * d_la_slot, * d_vtx_off, * d_vtx_cell, * d_leaf_vtx, * d_parent;
+  int32_t * d_hull_vtx, * d_hull_leaf;
   uint8_t * d_level, * d_info;
   double * d_vtx_w, * d_vtx_wuni;
   /* field */
@@ -136,6 +137,7 @@ static void free_tree (gfsb200_ctx * c)
   cudaFree (c->d_child0); cudaFree (c->d_neighbor); cudaFree (c->d_la_slot);
   cudaFree (c->d_vtx_off); cudaFree (c->d_vtx_cell); cudaFree (c->d_leaf_vtx); cudaFree (c->d_parent);
   c->d_parent = NULL;
+  cudaFree (c->d_hull_vtx); cudaFree (c->d_hull_leaf); c->d_hull_vtx = c->d_hull_leaf = NULL;
   cudaFree (c->d_level); cudaFree (c->d_info); cudaFree (c->d_vtx_w); cudaFree (c->d_vtx_wuni);
   c->d_child0 = c->d_neighbor = c->d_la_slot = c->d_vtx_off = c->d_vtx_cell = c->d_leaf_vtx = NULL;
   c->d_level = c->d_info = NULL; c->d_vtx_w = c->d_vtx_wuni = NULL;
@@ -194,6 +196,7 @@ extern "C" int gfsb200_ctx_create (int device, gfsb200_ctx ** out)
   c->have_tree = c->have_field = c->own_field = false;
   c->d_child0 = c->d_neighbor = c->d_la_slot = c->d_vtx_off = c->d_vtx_cell = c->d_leaf_vtx = NULL;
   c->d_level = c->d_info = NULL; c->d_vtx_w = c->d_vtx_wuni = NULL; c->d_parent = NULL;
+  c->d_hull_vtx = c->d_hull_leaf = NULL;
   c->esc_count = NULL; c->esc_idx = NULL; c->esc_old = NULL; c->esc_cap = 0; c->esc_armed = false;
   for (int i = 0; i < 5; i++) c->d_field[i] = NULL;
   for (int i = 0; i < 3; i++) c->d_prev[i] = NULL;
@@ -335,9 +338,84 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
     for (int d = 0; d < 6; d++)
       T.periodic[rr][d] = rr < t->n_roots ? (signed char) t->periodic[rr][d] : -1;
   T.lattice_n1 = 0;
+  /* (a one-slot locate array means one GfsBox and no GfsBoundary root: hull cells have NULL
+     neighbours, so "all neighbours are same-level leaves" == interior on such a tree) */
   if (t->lattice_level >= 0 && t->lattice_level - t->root_level == T.top_levels && T.single_box &&
-      !getenv ("GFSB200_NO_LATTICE"))
+      t->n_roots == 1 && !getenv ("GFSB200_NO_LATTICE"))
     T.lattice_n1 = (1 << T.top_levels) + 1;
+  /* Interior vertices of a lattice tree: check once, on the host, that every one of them
+     carries the same stencil shape (the 2^dim leaves around it, equal weights, one common
+     order), so that the cell pass can address them arithmetically instead of through the
+     CSR tables.  Any deviation keeps the tables. */
+  T.lattice_pattern = -1;
+  if (T.lattice_n1 > 0 && T.top_levels >= 2 && !getenv ("GFSB200_NO_LATTICE_PATTERN")) {
+    const int dim = t->dim, nc = 1 << dim, n1 = T.lattice_n1, nn = n1 - 1;
+    double wexp = NAN;                /* the common weight (2^-dim up to the rounding of the
+					 reference's sequential normalisation) */
+    int pattern = -1;
+    bool ok = true;
+    for (int k = dim == 3 ? 1 : 0; ok && k < (dim == 3 ? nn : 1); k++)
+      for (int j = 1; ok && j < nn; j++)
+	for (int i = 1; ok && i < nn; i++) {
+	  const int v = (k*n1 + j)*n1 + i;
+	  const int b = t->vtx_off[v], e = t->vtx_off[v + 1];
+	  if (pattern < 0) wexp = wuni[v];
+	  if (e - b != nc || !(wuni[v] == wexp)) { ok = false; break; }
+	  int pat = 0;
+	  for (int q = 0; q < nc; q++) {
+	    const int cell = t->vtx_cell[b + q];
+	    if (cell < T.top_start || t->child0[cell] >= 0) { ok = false; break; }
+	    const unsigned key = (unsigned) (cell - T.top_start);
+	    int kx, ky, kz = 0;
+	    if (dim == 3) {
+	      kx = gfsb200_compact3 (key); ky = ~gfsb200_compact3 (key >> 1) & (nn - 1);
+	      kz = ~gfsb200_compact3 (key >> 2) & (nn - 1);
+	    }
+	    else {
+	      kx = gfsb200_compact2 (key); ky = ~gfsb200_compact2 (key >> 1) & (nn - 1);
+	    }
+	    const int bx = kx - (i - 1), by = ky - (j - 1), bz = dim == 3 ? kz - (k - 1) : 0;
+	    if ((bx | by | bz) & ~1) { ok = false; break; }
+	    pat |= (bx | by << 1 | bz << 2) << (dim*q);
+	  }
+	  if (pattern < 0) pattern = pat;
+	  else if (pat != pattern) ok = false;
+	}
+    if (ok && pattern >= 0) {
+      T.lattice_pattern = pattern;
+      T.lattice_w = wexp;
+    }
+    /* 3D: the hull lists that complement lattice_cell_pass_kernel (8^3 bricks) */
+    if (T.lattice_pattern >= 0 && dim == 3 && nn >= 16 && nn % 8 == 0) {
+      std::vector<int32_t> hv, hl;
+      for (int k = 0; k < n1; k++)
+	for (int j = 0; j < n1; j++)
+	  for (int i = 0; i < n1; i++)
+	    if (i == 0 || j == 0 || k == 0 || i == nn || j == nn || k == nn)
+	      hv.push_back ((k*n1 + j)*n1 + i);
+      for (int32_t cell = T.top_start; cell < n && ok; cell++) {
+	const bool box_leaf = (info[cell] & (GFSB200_CELL_LEAF | GFSB200_CELL_BOUNDARY)) == GFSB200_CELL_LEAF;
+	if (!box_leaf) { ok = false; break; }
+	const unsigned key = (unsigned) (cell - T.top_start);
+	const int kx = gfsb200_compact3 (key), ky = ~gfsb200_compact3 (key >> 1) & (nn - 1),
+	  kz = ~gfsb200_compact3 (key >> 2) & (nn - 1);
+	const bool interior = kx >= 1 && kx < nn - 1 && ky >= 1 && ky < nn - 1 && kz >= 1 && kz < nn - 1;
+	/* the brick kernel assumes interior <=> all neighbours are same-level leaves */
+	if (interior != ((info[cell] & CELL_REGULAR) != 0)) { ok = false; break; }
+	if (!interior) hl.push_back (cell);
+      }
+      if (ok && (int64_t) T.top_start + (int64_t) nn*nn*nn == n) {
+	if ((r = dev_alloc_copy (&c->d_hull_vtx, hv.data (), hv.size (), c->stream))) return r;
+	if ((r = dev_alloc_copy (&c->d_hull_leaf, hl.data (), hl.size (), c->stream))) return r;
+	CK (cudaStreamSynchronize (c->stream));
+	T.hull_vtx = c->d_hull_vtx; T.n_hull_vtx = (int) hv.size ();
+	T.hull_leaf = c->d_hull_leaf; T.n_hull_leaf = (int) hl.size ();
+      }
+    }
+    if (getenv ("GFSB200_DEBUG"))
+      fprintf (stderr, "gfsb200: lattice n1 = %d, interior vertex pattern %#x (w = %.17g)\n",
+	       T.lattice_n1, T.lattice_pattern, wexp);
+  }
 
   memset (&c->F, 0, sizeof c->F);
   const int vs = t->dim == 3 ? 4 : 2, ws = t->dim == 3 ? 4 : 1;

@@ -18,6 +18,7 @@
  * reference's non-FMA x86-64 arithmetic.  Both kernels are HBM/L2-bound
  * streaming passes over the cell arrays (roofline: DESIGN.md section 4).
  */
+#include <stdlib.h>
 #include "device_types.cuh"
 
 namespace {
@@ -31,6 +32,37 @@ __device__ __forceinline__ int child_id (const DevTree & T, int c) { return T.in
 __device__ __forceinline__ bool child_positive (int n, int axis)
 {
   return axis == 0 ? (n & 1) : !((n >> axis) & 1);
+}
+
+/* Morton arithmetic on lattice trees: the key of a leaf interleaves kx, ~ky, ~kz
+ * (child digit bit0 = +x, bit1 = -y, bit2 = -z).  Adding or subtracting one along
+ * an axis is a carry through that axis' bits only ("dilated" arithmetic). */
+template <int DIM> struct Dilated {
+  static constexpr unsigned X = DIM == 3 ? 0x09249249u : 0x55555555u;
+  __device__ static __forceinline__ unsigned inc (unsigned key, unsigned m)
+  { return (((key | ~m) + 1u) & m) | (key & ~m); }
+  __device__ static __forceinline__ unsigned dec (unsigned key, unsigned m)
+  { return (((key & m) - 1u) & m) | (key & ~m); }
+};
+
+__device__ __forceinline__ unsigned spread_bits3 (unsigned v)
+{
+  v &= 0x3ff;
+  v = (v | (v << 16)) & 0x030000ff;
+  v = (v | (v << 8))  & 0x0300f00f;
+  v = (v | (v << 4))  & 0x030c30c3;
+  v = (v | (v << 2))  & 0x09249249;
+  return v;
+}
+
+__device__ __forceinline__ unsigned spread_bits2 (unsigned v)
+{
+  v &= 0xffff;
+  v = (v | (v << 8)) & 0x00ff00ff;
+  v = (v | (v << 4)) & 0x0f0f0f0f;
+  v = (v | (v << 2)) & 0x33333333;
+  v = (v | (v << 1)) & 0x55555555;
+  return v;
 }
 
 /* average_neighbor_value, src/fluid.c:64-93 (no solid fractions) */
@@ -150,10 +182,13 @@ __device__ double center_gradient (const DevTree & T, const double * __restrict_
 
 template <int DIM>
 __global__ void __launch_bounds__(256, 8)      /* 32 registers: full occupancy hides the nb -> value chain */
-vorticity_kernel (DevTree T, DevField fld)
+vorticity_kernel (DevTree T, DevField fld, int hull_only)
 {
   const int stride = gridDim.x*blockDim.x;
-  for (int cell = blockIdx.x*blockDim.x + threadIdx.x; cell < T.n_cells; cell += stride) {
+  /* hull_only: just the leaves lattice_cell_pass_kernel left out (DevTree.hull_leaf) */
+  const int n_items = hull_only ? T.n_hull_leaf : T.n_cells;
+  for (int item = blockIdx.x*blockDim.x + threadIdx.x; item < n_items; item += stride) {
+    const int cell = hull_only ? T.hull_leaf[item] : item;
     const unsigned info = T.info[cell];
     const bool box_leaf = (info & (GFSB200_CELL_LEAF | GFSB200_CELL_BOUNDARY)) == GFSB200_CELL_LEAF;
     double wx = 0., wy = 0., wz = 0.;
@@ -164,7 +199,22 @@ vorticity_kernel (DevTree T, DevField fld)
 	 operations the general path performs with x1 = x2 = 1 */
       const double size = __longlong_as_double ((long long) (1023 - T.level[cell]) << 52);
       int nb[2*DIM];
-      {
+      if (T.lattice_n1 > 0) {
+	/* lattice trees: a regular cell's neighbours follow from its Morton key (no
+	   neighbour-row load in front of the value gathers); +y / +z decrement
+	   the key's inverted digits */
+	const unsigned key = (unsigned) (cell - T.top_start);
+	const unsigned X = Dilated<DIM>::X, Y = X << 1, Z = X << 2;
+	nb[0] = T.top_start + (int) Dilated<DIM>::inc (key, X);
+	nb[1] = T.top_start + (int) Dilated<DIM>::dec (key, X);
+	nb[2] = T.top_start + (int) Dilated<DIM>::dec (key, Y);
+	nb[3] = T.top_start + (int) Dilated<DIM>::inc (key, Y);
+	if (DIM == 3) {
+	  nb[2*DIM - 2] = T.top_start + (int) Dilated<DIM>::dec (key, Z);
+	  nb[2*DIM - 1] = T.top_start + (int) Dilated<DIM>::inc (key, Z);
+	}
+      }
+      else {
 	const int2 * np = reinterpret_cast<const int2 *> (T.neighbor + (int64_t) cell*(2*DIM));
 #pragma unroll
 	for (int d = 0; d < DIM; d++) {
@@ -256,7 +306,7 @@ convective_kernel (DevTree T, DevField fld)
  * NODATA is stored as NODATA and resolved by the particle kernel.) */
 template <int DIM>
 __global__ void __launch_bounds__(256)
-vertex_values_kernel (DevTree T, DevField fld)
+vertex_values_kernel (DevTree T, DevField fld, int hull_only)
 {
   /* Lattice trees: vertices are numbered row-major, cells in Morton order.  A
      CTA then takes an 8x8x4 (3D) / 16x16 (2D) brick of vertices instead of 256
@@ -266,11 +316,14 @@ vertex_values_kernel (DevTree T, DevField fld)
   const int bx = DIM == 3 ? 8 : 16, by = DIM == 3 ? 8 : 16, bz = DIM == 3 ? 4 : 1;
   const int tx = n1 > 0 ? (n1 + bx - 1)/bx : 0, ty = n1 > 0 ? (n1 + by - 1)/by : 0,
     tz = DIM == 3 && n1 > 0 ? (n1 + bz - 1)/bz : 1;
-  const int64_t n_items = n1 > 0 ? (int64_t) tx*ty*tz*256 : T.n_vertices;
+  /* hull_only: just the vertices lattice_cell_pass_kernel left out (DevTree.hull_vtx) */
+  const int64_t n_items = hull_only ? T.n_hull_vtx : n1 > 0 ? (int64_t) tx*ty*tz*256 : T.n_vertices;
   const int64_t stride = (int64_t) gridDim.x*blockDim.x;
   for (int64_t item = (int64_t) blockIdx.x*blockDim.x + threadIdx.x; item < n_items; item += stride) {
     int v = (int) item;
-    if (n1 > 0) {
+    if (hull_only)
+      v = T.hull_vtx[item];
+    else if (n1 > 0) {
       const int brick = (int) (item >> 8), t = (int) (item & 255);
       const int i = (brick % tx)*bx + (t % bx);
       const int j = ((brick/tx) % ty)*by + ((t/bx) % by);
@@ -279,9 +332,57 @@ vertex_values_kernel (DevTree T, DevField fld)
 	continue;
       v = (k*n1 + j)*n1 + i;
     }
-    const int b = T.vtx_off[v], e = T.vtx_off[v + 1];
     double s0 = 0., s1 = 0., s2 = 0.;
     bool nodata = false;
+    if (!hull_only && n1 > 0 && T.lattice_pattern >= 0) {
+      const int i = v % n1, j = (v/n1) % n1, k = DIM == 3 ? v/(n1*n1) : 1;
+      const int nn = n1 - 1;
+      if (i >= 1 && i < nn && j >= 1 && j < nn && k >= 1 && (DIM == 2 || k < nn)) {
+	/* interior vertex of a lattice tree: the 2^DIM leaves around it, weight and
+	   order as verified at upload (DevTree.lattice_pattern) -- no table loads */
+	constexpr int NB = 1 << DIM;
+	unsigned sx[2], sy[2], sz[2] = { 0u, 0u };
+	if (DIM == 3) {
+	  sx[0] = spread_bits3 (i - 1); sx[1] = spread_bits3 (i);
+	  sy[0] = spread_bits3 (~(j - 1) & (nn - 1)) << 1; sy[1] = spread_bits3 (~j & (nn - 1)) << 1;
+	  sz[0] = spread_bits3 (~(k - 1) & (nn - 1)) << 2; sz[1] = spread_bits3 (~k & (nn - 1)) << 2;
+	}
+	else {
+	  sx[0] = spread_bits2 (i - 1); sx[1] = spread_bits2 (i);
+	  sy[0] = spread_bits2 (~(j - 1) & (nn - 1)) << 1; sy[1] = spread_bits2 (~j & (nn - 1)) << 1;
+	}
+	const double w = T.lattice_w;
+	double a0[NB], a1[NB], a2[NB];
+#pragma unroll
+	for (int q = 0; q < NB; q++) {
+	  const int bits = (T.lattice_pattern >> (DIM*q)) & (NB - 1);
+	  const int c = T.top_start + (int) (sx[bits & 1] | sy[(bits >> 1) & 1] | sz[(bits >> 2) & 1]);
+	  a0[q] = fld.u[0][c];
+	  a1[q] = fld.u[1][c];
+	  a2[q] = DIM == 3 ? fld.u[2][c] : 0.;
+	}
+#pragma unroll
+	for (int q = 0; q < NB; q++) {
+	  nodata |= is_nodata (a0[q]) | is_nodata (a1[q]) | (DIM == 3 && is_nodata (a2[q]));
+	  s0 += w*a0[q];
+	  s1 += w*a1[q];
+	  if (DIM == 3) s2 += w*a2[q];
+	}
+	if (nodata) {
+	  s0 = s1 = s2 = GFSB200_NODATA;
+	  *fld.nodata_flag = 1;
+	}
+	if (DIM == 2)
+	  reinterpret_cast<double2 *> (fld.vtx_val)[v] = make_double2 (s0, s1);
+	else {
+	  double2 * o = reinterpret_cast<double2 *> (fld.vtx_val + (int64_t) v*4);
+	  o[0] = make_double2 (s0, s1);
+	  o[1] = make_double2 (s2, 0.);
+	}
+	continue;
+      }
+    }
+    const int b = T.vtx_off[v], e = T.vtx_off[v + 1];
     /* most stencils carry one weight repeated (equal-size cells around the
        vertex): it is stored once per vertex and the per-entry array is skipped */
     const double wu = T.vtx_wuni[v];
@@ -328,6 +429,155 @@ vertex_values_kernel (DevTree T, DevField fld)
   }
 }
 
+/* ------------------------------------------------------------------ */
+/* Lattice trees (uniform, one GfsBox, no GfsBoundary -- BASELINE config C2):
+ * the whole cell pass for the INTERIOR vertices and leaves in one kernel.
+ *
+ * One CTA per 8x8x8 brick of leaves.  In the flat tree's Morton order such a
+ * brick is 512 consecutive cells, so the bulk of the 10x10x10 region a brick
+ * needs (its leaves plus one layer around them) arrives as contiguous 4 KB
+ * runs per component; the 488 halo cells are short runs of the neighbouring
+ * bricks.  All loads of a CTA are issued before the first use (12 per
+ * thread), the region sits in shared memory (24 KB -> 8 CTAs per SM), and
+ * both tables are then computed from it:
+ *   vertex (i,j,k), i,j,k in [8b+1, 8b+8]: sum of its 8 leaves in the order and
+ *     with the weight verified at upload (DevTree.lattice_pattern/lattice_w)
+ *     = gfs_cell_corner_value, src/fluid.c:3081-3101
+ *   leaf (kx,ky,kz): vorticity_vector (modules/particulatecommon.c:142-164)
+ *     from centred differences, the x1 = x2 = 1 case of gfs_center_gradient
+ * in the same operation order as the table-driven kernels above (bit-identical
+ * results, tested), with no index-table traffic at all.  Vertices and leaves
+ * on the hull (DevTree.hull_vtx / hull_leaf) are left to those kernels.  HBM traffic per
+ * launch: 24 B per cell read (halo re-reads hit L2) + 32 B per vertex + 32 B
+ * per leaf written. */
+#define BRICK 8
+#define REG (BRICK + 2)
+#define PLANE (REG*REG + 4)      /* plane stride = 8 mod 16 doubles: the (x, z) lanes of a warp hit
+				    distinct bank pairs */
+#define REFERENCE_PATTERN 0x21ab3e   /* the order gfs_cell_corner_interpolator visits the 8 leaves in */
+
+__device__ __forceinline__ void cp_async8 (double * smem_dst, const double * gmem_src)
+{
+  asm volatile ("cp.async.ca.shared.global [%0], [%1], 8;"
+		:: "r"((unsigned) __cvta_generic_to_shared (smem_dst)), "l"(gmem_src) : "memory");
+}
+
+/* issue the asynchronous copies of one brick's region into buffer `buf` */
+__device__ __forceinline__ void stage_brick (const DevTree & T, const DevField & fld, int brick,
+					      double (* buf)[REG*PLANE], unsigned (* key)[REG])
+{
+  const int nn = T.lattice_n1 - 1, nb = nn/BRICK;
+  const int bx = brick % nb, by = (brick/nb) % nb, bz = brick/(nb*nb);
+  /* Morton key of region cell (x,y,z) = key[0][x] | key[1][y] | key[2][z]; 0xffffffff marks a
+     coordinate outside the lattice */
+  if (threadIdx.x < 3*REG) {
+    const int axis = threadIdx.x/REG, l = threadIdx.x % REG;
+    const int g = (axis == 0 ? bx : axis == 1 ? by : bz)*BRICK - 1 + l;
+    unsigned k = 0xffffffffu;
+    if ((unsigned) g < (unsigned) nn)
+      k = axis == 0 ? spread_bits3 (g) : spread_bits3 (~g & (nn - 1)) << axis;
+    key[axis][l] = k;
+  }
+  __syncthreads ();
+  const double * __restrict__ U = fld.u[0], * __restrict__ V = fld.u[1], * __restrict__ W = fld.u[2];
+#pragma unroll
+  for (int it = 0; it < (REG*REG*REG + 255)/256; it++) {
+    const int r = threadIdx.x + 256*it;
+    if (r < REG*REG*REG) {
+      const int lx = r % REG, ly = (r/REG) % REG, lz = r/(REG*REG);
+      const unsigned kx = key[0][lx], ky = key[1][ly], kz = key[2][lz];
+      const int o = lz*PLANE + ly*REG + lx;
+      if (kx != 0xffffffffu && ky != 0xffffffffu && kz != 0xffffffffu) {
+	const int c = T.top_start + (int) (kx | ky | kz);
+	cp_async8 (&buf[0][o], U + c); cp_async8 (&buf[1][o], V + c); cp_async8 (&buf[2][o], W + c);
+      }
+      else        /* only ever read by hull items, which this kernel skips */
+	buf[0][o] = buf[1][o] = buf[2][o] = 0.;
+    }
+  }
+  asm volatile ("cp.async.commit_group;" ::: "memory");
+}
+
+/* One CTA per brick, 4 CTAs per SM (64 registers: the 24 shared loads of a vertex are in flight
+ * together).  A persistent variant with two region buffers (the next brick's copies in flight
+ * during the compute phase) measured 1.6x SLOWER and starved the hull kernels; dropped. */
+template <int PATTERN>
+__global__ void __launch_bounds__(256, 4)
+lattice_cell_pass_kernel (DevTree T, DevField fld)
+{
+  __shared__ double sh[3][REG*PLANE];
+  __shared__ unsigned key[3][REG];
+  const int n1 = T.lattice_n1, nn = n1 - 1, nb = nn/BRICK;
+
+  /* a warp = 8 x by 4 z at one y: with the padded plane stride its 64-bit shared loads are
+     conflict-free, and its 32-byte table rows form four 256-byte runs */
+  const int tx = threadIdx.x & 7, tzq = (threadIdx.x >> 3) & 3, ty = threadIdx.x >> 5;
+  const double wgt = T.lattice_w;
+  const int pattern = PATTERN >= 0 ? PATTERN : T.lattice_pattern;
+
+  const int brick = blockIdx.x;
+  stage_brick (T, fld, brick, sh, key);
+  asm volatile ("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads ();
+  {
+    const double (* reg)[REG*PLANE] = sh;
+    const int bx = brick % nb, by = (brick/nb) % nb, bz = brick/(nb*nb);
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      const int tz = tzq + 4*half;
+      const int r0 = (tz + 1)*PLANE + (ty + 1)*REG + (tx + 1);      /* the leaf (bx*8 + tx, ...) */
+      /* ---- vertex (i,j,k) = the low corner of that leaf's +x+y+z neighbour: its 8 leaves are
+	 region cells r0 + {0,1} + {0,REG} + {0,PLANE} */
+      {
+	const int i = bx*BRICK + 1 + tx, j = by*BRICK + 1 + ty, k = bz*BRICK + 1 + tz;
+	if (i < nn && j < nn && k < nn) {
+	  double s0 = 0., s1 = 0., s2 = 0.;
+#pragma unroll
+	  for (int q = 0; q < 8; q++) {
+	    const int bits = (pattern >> (3*q)) & 7;
+	    const int r = r0 + (bits & 1) + ((bits >> 1) & 1)*REG + ((bits >> 2) & 1)*PLANE;
+	    s0 += wgt*reg[0][r]; s1 += wgt*reg[1][r]; s2 += wgt*reg[2][r];
+	  }
+	  /* GFS_NODATA is DBL_MAX: a stencil that touches one sums to >= w*DBL_MAX (or
+	     overflows); no velocity gets near that, so one magnitude test screens for the
+	     exact check */
+	  if (!(fabs (s0) < 1e300 && fabs (s1) < 1e300 && fabs (s2) < 1e300)) {
+	    bool bad = false;
+	    for (int q = 0; q < 8; q++) {
+	      const int bits = (pattern >> (3*q)) & 7;
+	      const int r = r0 + (bits & 1) + ((bits >> 1) & 1)*REG + ((bits >> 2) & 1)*PLANE;
+	      bad |= is_nodata (reg[0][r]) | is_nodata (reg[1][r]) | is_nodata (reg[2][r]);
+	    }
+	    if (bad) {
+	      s0 = s1 = s2 = GFSB200_NODATA;
+	      *fld.nodata_flag = 1;
+	    }
+	  }
+	  double2 * o = reinterpret_cast<double2 *> (fld.vtx_val + ((int64_t) (k*n1 + j)*n1 + i)*4);
+	  o[0] = make_double2 (s0, s1);
+	  o[1] = make_double2 (s2, 0.);
+	}
+      }
+      /* ---- the leaf itself */
+      {
+	const int kx = bx*BRICK + tx, ky = by*BRICK + ty, kz = bz*BRICK + tz;
+	if (kx >= 1 && kx < nn - 1 && ky >= 1 && ky < nn - 1 && kz >= 1 && kz < nn - 1) {
+	  const double size = T.top_h;
+	  /* neighbour in direction 2c is +axis c, 2c + 1 is -axis c (FttDirection) */
+#define GRADS(F, st) ((((F)[r0 + (st)] - (F)[r0]) + ((F)[r0] - (F)[r0 - (st)]))/2.)
+	  const double wx = (GRADS (reg[2], REG) - GRADS (reg[1], PLANE))/size;
+	  const double wy = (GRADS (reg[0], PLANE) - GRADS (reg[2], 1))/size;
+	  const double wz = (GRADS (reg[1], 1) - GRADS (reg[0], REG))/size;
+#undef GRADS
+	  double2 * o = reinterpret_cast<double2 *> (fld.vort + ((int64_t) (kz*nn + ky)*nn + kx)*4);
+	  o[0] = make_double2 (wx, wy);
+	  o[1] = make_double2 (wz, 0.);
+	}
+      }
+    }
+  }
+}
+
 } // namespace
 
 static int cell_grid (int64_t n, int n_sm)
@@ -350,8 +600,8 @@ extern "C" void gfsb200_launch_vertex_values (const DevTree * T, const DevField 
 					      cudaStream_t stream)
 {
   const int g = cell_grid (vertex_items (T), n_sm);
-  if (T->dim == 2) vertex_values_kernel<2><<<g, 256, 0, stream>>> (*T, *fld);
-  else vertex_values_kernel<3><<<g, 256, 0, stream>>> (*T, *fld);
+  if (T->dim == 2) vertex_values_kernel<2><<<g, 256, 0, stream>>> (*T, *fld, 0);
+  else vertex_values_kernel<3><<<g, 256, 0, stream>>> (*T, *fld, 0);
 }
 
 extern "C" void gfsb200_launch_convective (const DevTree * T, const DevField * fld, int n_sm,
@@ -381,15 +631,32 @@ extern "C" void gfsb200_launch_cell_pass (const DevTree * T, const DevField * fl
   if (gc > cap) gc = cap;
   if (gv < 1) gv = 1;
   if (gc < 1) gc = 1;
+  /* 3D lattice trees: interior vertices and leaves in one brick-tiled kernel, the hull through
+     the table-driven kernels */
+  const int nn = T->lattice_n1 - 1;
+  const bool fused = T->dim == 3 && T->hull_vtx != NULL;
   cudaEventRecord (ev_fork, stream);
   cudaStreamWaitEvent (aux, ev_fork, 0);
   if (T->dim == 2) {
-    vertex_values_kernel<2><<<gv, threads, 0, stream>>> (*T, *fld);
-    vorticity_kernel<2><<<gc, threads, 0, aux>>> (*T, *fld);
+    vertex_values_kernel<2><<<gv, threads, 0, stream>>> (*T, *fld, 0);
+    vorticity_kernel<2><<<gc, threads, 0, aux>>> (*T, *fld, 0);
   }
   else {
-    vertex_values_kernel<3><<<gv, threads, 0, stream>>> (*T, *fld);
-    vorticity_kernel<3><<<gc, threads, 0, aux>>> (*T, *fld);
+    if (fused) {
+      /* the (small, latency-bound) hull kernels go first so that their CTAs are resident
+	 before the brick kernel fills the machine */
+      vertex_values_kernel<3><<<(T->n_hull_vtx + threads - 1)/threads, threads, 0, aux>>> (*T, *fld, 1);
+      vorticity_kernel<3><<<(T->n_hull_leaf + threads - 1)/threads, threads, 0, aux>>> (*T, *fld, 1);
+      const int g = (nn/BRICK)*(nn/BRICK)*(nn/BRICK);
+      if (T->lattice_pattern == REFERENCE_PATTERN)
+	lattice_cell_pass_kernel<REFERENCE_PATTERN><<<g, 256, 0, stream>>> (*T, *fld);
+      else
+	lattice_cell_pass_kernel<-1><<<g, 256, 0, stream>>> (*T, *fld);
+    }
+    else {
+      vertex_values_kernel<3><<<gv, threads, 0, stream>>> (*T, *fld, 0);
+      vorticity_kernel<3><<<gc, threads, 0, aux>>> (*T, *fld, 0);
+    }
   }
   cudaEventRecord (ev_join, aux);
   cudaStreamWaitEvent (stream, ev_join, 0);

@@ -44,6 +44,16 @@ struct DevTree {
   const int32_t * leaf_vtx;    /* [n_cells][2^dim] */
   int lattice_n1;              /* > 0: uniform one-box tree, vertex id = (k*n1 + j)*n1 + i with
 				  n1 = 2^levels + 1 (no leaf_vtx / child0 loads needed) */
+  int lattice_pattern;         /* >= 0 (lattice trees): every interior vertex (i,j,k) has the 2^dim
+				  leaves around it as its stencil, all with one weight, in one
+				  common order: entry e is leaf (i - 1 + bx, j - 1 + by, k - 1 + bz)
+				  with (bx,by,bz) = bits dim*e .. dim*e + dim - 1.  Verified against
+				  the CSR tables at upload; -1 = use the tables */
+  double lattice_w;            /* that common weight */
+  /* 3D lattice trees: what lattice_cell_pass_kernel leaves to the table-driven kernels */
+  const int32_t * hull_vtx;    /* [n_hull_vtx] vertices with a coordinate on the hull */
+  const int32_t * hull_leaf;   /* [n_hull_leaf] leaves with a face on the hull */
+  int n_hull_vtx, n_hull_leaf;
 };
 
 struct DevField {

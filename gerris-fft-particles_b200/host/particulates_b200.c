@@ -19,6 +19,7 @@
  *
  *   GfsParticleList.event     gfs_particle_list_event    modules/particulatecommon.c:980-1015
  *   GfsParticulateField.event particulate_field_event    modules/particulatecommon.c:1934-1957
+ *   GfsSourceParticulate.event source_particulate_event  modules/particulatecommon.c:2177-2228
  *
  * and exports the same module symbols as modules/particulates.c:24-49.
  * A list that carries something the device does not implement (user force
@@ -52,6 +53,7 @@ typedef struct {
 static GHashTable * b200_states = NULL;   /* GfsParticleList* -> B200State* */
 static gboolean (* reference_list_event) (GfsEvent *, GfsSimulation *) = NULL;
 static gboolean (* reference_field_event) (GfsEvent *, GfsSimulation *) = NULL;
+static gboolean (* reference_source_event) (GfsEvent *, GfsSimulation *) = NULL;
 
 static B200State * state_of (GfsParticleList * plist)
 {
@@ -382,6 +384,68 @@ static gboolean b200_particulate_field_event (GfsEvent * event, GfsSimulation * 
   return TRUE;
 }
 
+/* GfsSourceParticulate (source_particulate_event, :2177-2228): the force of the
+ * particles on the fluid, spread by the user's kernel.  The kernel GfsFunction
+ * is a compiled expression; it is recognised by probing (gfsb200_kernel_fit)
+ * and the event stays on the reference path when it is none of the closed
+ * forms the device evaluates. */
+static gdouble kernel_trampoline (gdouble x, gdouble y, gdouble z, gpointer data)
+{
+  FttVector q = { x, y, z };
+  return gfs_function_spatial_value ((GfsFunction *) data, &q);
+}
+
+static gboolean b200_source_particulate_event (GfsEvent * event, GfsSimulation * sim)
+{
+  /* (the GFS_SOURCE_PARTICULATE macro of particulatecommon.h:234-236 names a
+     class getter that does not exist; a plain cast is what it expands to) */
+  GfsSourceParticulate * sp = (GfsSourceParticulate *) event;
+  gfsb200_step_params par;
+  gfsb200_kernel kernel;
+  B200State * s;
+  gdouble * out, * force[3];
+  gint64 n, k = 0;
+  GSList * i;
+  FttComponent c;
+
+  if (!step_params (sp->plist, sim, &par) || sim->solids->items != NULL ||
+      gfsb200_kernel_fit (kernel_trampoline, sp->kernel_function, FTT_DIMENSION, &kernel) != GFSB200_OK)
+    return (* reference_source_event) (event, sim);
+  /* the timing gate of the parent class (:2180-2181) */
+  if (!(* GFS_EVENT_CLASS (GTS_OBJECT_CLASS (gfs_source_particulate_class ())->parent_class)->event)
+      (event, sim))
+    return FALSE;
+
+  s = state_of (sp->plist);
+  refresh_tree (s, sim);
+  mirror_velocity (s, GFS_DOMAIN (sim));
+  n = upload_particles (s, sp->plist);
+  kernel.record_norm = 0;
+  if (gfsb200_deposit_force_smoothed (s->ctx, &par, sp->rkernel, &kernel) != GFSB200_OK)
+    g_error ("particulates (B200): %s", gfsb200_last_error ());
+  /* <plist>_Fx,_Fy,_Fz: gfs_cell_reset on the leaves + the scatter of diffuse_force */
+  out = g_malloc (sizeof (gdouble)*s->n_cells);
+  for (c = 0; c < FTT_DIMENSION; c++) {
+    gfsb200_download_deposit (s->ctx, 1 + c, out);
+    gfsb200_ftt_scatter (s->map, offsetof (GfsStateVector, place_holder), sp->u[c]->i, TRUE, out);
+  }
+  g_free (out);
+  /* the reference leaves the on-fluid force in particulate->force (:2195-2201) */
+  for (c = 0; c < 3; c++)
+    force[c] = g_malloc (sizeof (gdouble)*(n ? n : 1));
+  if (gfsb200_particles_download (s->ctx, NULL, NULL, NULL, NULL, NULL, NULL, force[0], force[1], force[2],
+				  NULL, NULL, NULL, NULL) != GFSB200_OK)
+    g_error ("particulates (B200): %s", gfsb200_last_error ());
+  for (i = GFS_EVENT_LIST (sp->plist)->list->items; i && k < n; i = i->next, k++) {
+    GfsParticulate * q = GFS_PARTICULATE (i->data);
+    q->force.x = force[0][k]; q->force.y = force[1][k];
+    q->force.z = FTT_DIMENSION > 2 ? force[2][k] : 0.;
+  }
+  for (c = 0; c < 3; c++)
+    g_free (force[c]);
+  return TRUE;
+}
+
 /* ------------------------------------------------------------------ */
 /* module symbols, as modules/particulates.c:24-49                      */
 
@@ -413,5 +477,7 @@ const gchar * g_module_check_init (void)
   GFS_EVENT_CLASS (gfs_particle_list_class ())->event = b200_particle_list_event;
   reference_field_event = GFS_EVENT_CLASS (gfs_particulate_field_class ())->event;
   GFS_EVENT_CLASS (gfs_particulate_field_class ())->event = b200_particulate_field_event;
+  reference_source_event = GFS_EVENT_CLASS (gfs_source_particulate_class ())->event;
+  GFS_EVENT_CLASS (gfs_source_particulate_class ())->event = b200_source_particulate_event;
   return NULL;
 }

@@ -299,6 +299,14 @@ typedef struct {
   int32_t record_norm;             /* 1: keep each particle's (correction, volume) for
 				      gfsb200_download_kernel_norm */
 } gfsb200_kernel;
+/* Recognise a user kernel by probing it: f is sampled at ~40 offsets (in
+ * particle radii) and *out receives the closed form that reproduces every
+ * sample to 1e-12 of the kernel's peak; GFSB200_ERR_UNSUPPORTED if none does
+ * (the list then stays on the reference's CPU event).  Host-only, no device
+ * needed.  The drop-in module passes a trampoline to gfs_function_spatial_value
+ * of GfsSourceParticulate.kernel_function (modules/particulatecommon.c:2282-2290). */
+typedef double (* gfsb200_kernel_func) (double x, double y, double z, void * data);
+int gfsb200_kernel_fit (gfsb200_kernel_func f, void * data, int dim, gfsb200_kernel * out);
 /* fills deposit components 1..dim (zeroed first); component 0 is untouched */
 int gfsb200_deposit_force_smoothed (gfsb200_ctx * c, const gfsb200_step_params * p,
 				    double rkernel, const gfsb200_kernel * kernel);

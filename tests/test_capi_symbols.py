@@ -59,3 +59,28 @@ def test_product_does_not_touch_the_oracle():
                         bad.append(os.path.join(d, f))
     # the Makefile may point GTS_INC at the shim to compile-check the bridge; sources may not
     assert not bad, bad
+
+
+def test_kernel_fit_recognises_the_closed_forms():
+    """gfsb200_kernel_fit (host only): a user kernel GfsFunction is recognised by
+    probing; anything that is not one of the device's closed forms is refused so
+    that the module keeps such a list on the reference's CPU event."""
+    import math
+    import pytest
+    from helpers import capi
+    k = capi.kernel_fit(lambda x, y, z: 0.25, 3)
+    assert (k.kind, k.a) == (capi.KERNEL_CONSTANT, 0.25)
+    k = capi.kernel_fit(lambda x, y, z: 3.0 * math.exp(-(x * x + y * y + z * z) / 2.0), 3)
+    assert k.kind == capi.KERNEL_GAUSSIAN and k.a == 3.0 and abs(k.b - 0.5) < 1e-14
+    k = capi.kernel_fit(lambda x, y, z: math.exp(-0.02 * (x * x + y * y)), 2)
+    assert k.kind == capi.KERNEL_GAUSSIAN and abs(k.b - 0.02) < 1e-14
+    for p in (1, 2, 4):
+        k = capi.kernel_fit(lambda x, y, z: 2.0 * max(0.0, 1.0 - (x * x + y * y + z * z) / 9.0) ** p, 3)
+        assert (k.kind, k.p, k.a) == (capi.KERNEL_COMPACT, p, 2.0) and abs(k.b - 1.0 / 9.0) < 1e-12
+    for bad in (lambda x, y, z: math.exp(-abs(x) - abs(y) - abs(z)),        # not radial-quadratic
+                lambda x, y, z: math.exp(-(x * x + 2 * y * y + z * z)),      # anisotropic
+                lambda x, y, z: 1.0 / (1.0 + x * x + y * y + z * z),
+                lambda x, y, z: x * x + y * y,                               # zero at the centre
+                lambda x, y, z: float("nan")):
+        with pytest.raises(capi.GfsB200Error):
+            capi.kernel_fit(bad, 3)
