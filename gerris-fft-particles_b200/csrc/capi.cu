@@ -69,7 +69,6 @@ struct gfsb200_ctx {
   bool have_tree;
   DevTree T;
   int32_t * d_child0, * d_neighbor, * d_la_slot, * d_vtx_off, * d_vtx_cell, * d_leaf_vtx, * d_parent;
-  int32_t * d_hull_vtx, * d_hull_leaf;
   uint8_t * d_level, * d_info;
   double * d_vtx_w, * d_vtx_wuni;
   /* field */
@@ -137,7 +136,6 @@ static void free_tree (gfsb200_ctx * c)
   cudaFree (c->d_child0); cudaFree (c->d_neighbor); cudaFree (c->d_la_slot);
   cudaFree (c->d_vtx_off); cudaFree (c->d_vtx_cell); cudaFree (c->d_leaf_vtx); cudaFree (c->d_parent);
   c->d_parent = NULL;
-  cudaFree (c->d_hull_vtx); cudaFree (c->d_hull_leaf); c->d_hull_vtx = c->d_hull_leaf = NULL;
   cudaFree (c->d_level); cudaFree (c->d_info); cudaFree (c->d_vtx_w); cudaFree (c->d_vtx_wuni);
   c->d_child0 = c->d_neighbor = c->d_la_slot = c->d_vtx_off = c->d_vtx_cell = c->d_leaf_vtx = NULL;
   c->d_level = c->d_info = NULL; c->d_vtx_w = c->d_vtx_wuni = NULL;
@@ -196,7 +194,6 @@ extern "C" int gfsb200_ctx_create (int device, gfsb200_ctx ** out)
   c->have_tree = c->have_field = c->own_field = false;
   c->d_child0 = c->d_neighbor = c->d_la_slot = c->d_vtx_off = c->d_vtx_cell = c->d_leaf_vtx = NULL;
   c->d_level = c->d_info = NULL; c->d_vtx_w = c->d_vtx_wuni = NULL; c->d_parent = NULL;
-  c->d_hull_vtx = c->d_hull_leaf = NULL;
   c->esc_count = NULL; c->esc_idx = NULL; c->esc_old = NULL; c->esc_cap = 0; c->esc_armed = false;
   for (int i = 0; i < 5; i++) c->d_field[i] = NULL;
   for (int i = 0; i < 3; i++) c->d_prev[i] = NULL;
@@ -385,36 +382,27 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
       T.lattice_pattern = pattern;
       T.lattice_w = wexp;
     }
-    /* 3D: the hull lists that complement lattice_cell_pass_kernel (8^3 bricks) */
-    if (T.lattice_pattern >= 0 && dim == 3 && nn >= 16 && nn % 8 == 0) {
-      std::vector<int32_t> hv, hl;
-      for (int k = 0; k < n1; k++)
-	for (int j = 0; j < n1; j++)
-	  for (int i = 0; i < n1; i++)
-	    if (i == 0 || j == 0 || k == 0 || i == nn || j == nn || k == nn)
-	      hv.push_back ((k*n1 + j)*n1 + i);
+    /* 3D: can lattice_cell_pass_kernel tile the tree with 8^3 bricks?  It assumes that the
+       complete level holds exactly the nn^3 box leaves and that a leaf has a NULL neighbour
+       exactly where it touches the hull. */
+    if (T.lattice_pattern >= 0 && dim == 3 && nn >= 16 && nn % 8 == 0 &&
+	(int64_t) T.top_start + (int64_t) nn*nn*nn == n) {
       for (int32_t cell = T.top_start; cell < n && ok; cell++) {
-	const bool box_leaf = (info[cell] & (GFSB200_CELL_LEAF | GFSB200_CELL_BOUNDARY)) == GFSB200_CELL_LEAF;
-	if (!box_leaf) { ok = false; break; }
 	const unsigned key = (unsigned) (cell - T.top_start);
-	const int kx = gfsb200_compact3 (key), ky = ~gfsb200_compact3 (key >> 1) & (nn - 1),
-	  kz = ~gfsb200_compact3 (key >> 2) & (nn - 1);
-	const bool interior = kx >= 1 && kx < nn - 1 && ky >= 1 && ky < nn - 1 && kz >= 1 && kz < nn - 1;
-	/* the brick kernel assumes interior <=> all neighbours are same-level leaves */
-	if (interior != ((info[cell] & CELL_REGULAR) != 0)) { ok = false; break; }
-	if (!interior) hl.push_back (cell);
+	const int k3[3] = { (int) gfsb200_compact3 (key), (int) (~gfsb200_compact3 (key >> 1) & (nn - 1)),
+			    (int) (~gfsb200_compact3 (key >> 2) & (nn - 1)) };
+	if ((info[cell] & (GFSB200_CELL_LEAF | GFSB200_CELL_BOUNDARY)) != GFSB200_CELL_LEAF) ok = false;
+	for (int d = 0; d < 6 && ok; d++) {
+	  const int32_t nbr = t->neighbor[(int64_t) cell*6 + d];
+	  const bool at_hull = (d & 1) ? k3[d >> 1] == 0 : k3[d >> 1] == nn - 1;
+	  if (at_hull ? nbr >= 0 : (nbr < T.top_start || t->child0[nbr] >= 0)) ok = false;
+	}
       }
-      if (ok && (int64_t) T.top_start + (int64_t) nn*nn*nn == n) {
-	if ((r = dev_alloc_copy (&c->d_hull_vtx, hv.data (), hv.size (), c->stream))) return r;
-	if ((r = dev_alloc_copy (&c->d_hull_leaf, hl.data (), hl.size (), c->stream))) return r;
-	CK (cudaStreamSynchronize (c->stream));
-	T.hull_vtx = c->d_hull_vtx; T.n_hull_vtx = (int) hv.size ();
-	T.hull_leaf = c->d_hull_leaf; T.n_hull_leaf = (int) hl.size ();
-      }
+      T.lattice_bricks = ok;
     }
     if (getenv ("GFSB200_DEBUG"))
-      fprintf (stderr, "gfsb200: lattice n1 = %d, interior vertex pattern %#x (w = %.17g)\n",
-	       T.lattice_n1, T.lattice_pattern, wexp);
+      fprintf (stderr, "gfsb200: lattice n1 = %d, interior vertex pattern %#x (w = %.17g), bricks %d\n",
+	       T.lattice_n1, T.lattice_pattern, wexp, T.lattice_bricks);
   }
 
   memset (&c->F, 0, sizeof c->F);

@@ -182,13 +182,10 @@ __device__ double center_gradient (const DevTree & T, const double * __restrict_
 
 template <int DIM>
 __global__ void __launch_bounds__(256, 8)      /* 32 registers: full occupancy hides the nb -> value chain */
-vorticity_kernel (DevTree T, DevField fld, int hull_only)
+vorticity_kernel (DevTree T, DevField fld)
 {
   const int stride = gridDim.x*blockDim.x;
-  /* hull_only: just the leaves lattice_cell_pass_kernel left out (DevTree.hull_leaf) */
-  const int n_items = hull_only ? T.n_hull_leaf : T.n_cells;
-  for (int item = blockIdx.x*blockDim.x + threadIdx.x; item < n_items; item += stride) {
-    const int cell = hull_only ? T.hull_leaf[item] : item;
+  for (int cell = blockIdx.x*blockDim.x + threadIdx.x; cell < T.n_cells; cell += stride) {
     const unsigned info = T.info[cell];
     const bool box_leaf = (info & (GFSB200_CELL_LEAF | GFSB200_CELL_BOUNDARY)) == GFSB200_CELL_LEAF;
     double wx = 0., wy = 0., wz = 0.;
@@ -300,13 +297,87 @@ convective_kernel (DevTree T, DevField fld)
   }
 }
 
+/* sum w_i v_i over the CSR stencil of vertex v, in stencil order */
+template <int DIM>
+__device__ __forceinline__ void vertex_from_tables (const DevTree & T, const DevField & fld, int v,
+						     double & s0, double & s1, double & s2)
+{
+  bool nodata = false;
+  s0 = s1 = s2 = 0.;
+  const int b = T.vtx_off[v], e = T.vtx_off[v + 1];
+  /* most stencils carry one weight repeated (equal-size cells around the
+     vertex): it is stored once per vertex and the per-entry array is skipped */
+  const double wu = T.vtx_wuni[v];
+  const bool uni = wu == wu;
+  /* batches of 2^DIM entries: all indices first, then all gathers, then the
+     ordered accumulation -- the loads of a batch are in flight together.
+     Padding entries repeat a valid cell with weight 0 (s + 0*v == s). */
+  constexpr int NB = 1 << DIM;
+  for (int i = b; i < e; i += NB) {
+    int c[NB];
+    double w[NB], a0[NB], a1[NB], a2[NB];
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+	const bool ok = i + j < e;
+	c[j] = T.vtx_cell[ok ? i + j : i];
+	w[j] = ok ? (uni ? wu : T.vtx_w[i + j]) : 0.;
+    }
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+	a0[j] = fld.u[0][c[j]];
+	a1[j] = fld.u[1][c[j]];
+	a2[j] = DIM == 3 ? fld.u[2][c[j]] : 0.;
+    }
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+	/* GFS_NODATA = DBL_MAX: compare the high word on the integer pipe */
+	nodata |= is_nodata (a0[j]) | is_nodata (a1[j]) | (DIM == 3 && is_nodata (a2[j]));
+	s0 += w[j]*a0[j];
+	s1 += w[j]*a1[j];
+	if (DIM == 3) s2 += w[j]*a2[j];
+    }
+  }
+  if (nodata) {
+    s0 = s1 = s2 = GFSB200_NODATA;
+    *fld.nodata_flag = 1;
+  }
+}
+
+/* the same out of line, for the few hull vertices lattice_cell_pass_kernel meets (plain
+ * pointer arguments: taking the address of the by-value kernel parameters would copy them to
+ * local memory in every thread) */
+__device__ __noinline__ void hull_vertex_3d (const int32_t * __restrict__ vtx_off,
+					     const int32_t * __restrict__ vtx_cell,
+					     const double * __restrict__ vtx_w,
+					     const double * __restrict__ U, const double * __restrict__ V,
+					     const double * __restrict__ W, int * nodata_flag,
+					     double * __restrict__ out, int v)
+{
+  const int b = vtx_off[v], e = vtx_off[v + 1];
+  double s0 = 0., s1 = 0., s2 = 0.;
+  bool nodata = false;
+  for (int i = b; i < e; i++) {
+    const int c = vtx_cell[i];
+    const double w = vtx_w[i], a0 = U[c], a1 = V[c], a2 = W[c];
+    nodata |= is_nodata (a0) | is_nodata (a1) | is_nodata (a2);
+    s0 += w*a0; s1 += w*a1; s2 += w*a2;
+  }
+  if (nodata) {
+    s0 = s1 = s2 = GFSB200_NODATA;
+    *nodata_flag = 1;
+  }
+  double2 * o = reinterpret_cast<double2 *> (out + (int64_t) v*4);
+  o[0] = make_double2 (s0, s1);
+  o[1] = make_double2 (s2, 0.);
+}
+
 /* gfs_cell_corner_value, src/fluid.c:3081-3101: val = sum w_i v_i in stencil
  * order.  (The GFS_NODATA early-out returns the *calling* leaf's own value,
  * which a shared vertex cannot represent: a vertex whose stencil touches
  * NODATA is stored as NODATA and resolved by the particle kernel.) */
 template <int DIM>
 __global__ void __launch_bounds__(256)
-vertex_values_kernel (DevTree T, DevField fld, int hull_only)
+vertex_values_kernel (DevTree T, DevField fld)
 {
   /* Lattice trees: vertices are numbered row-major, cells in Morton order.  A
      CTA then takes an 8x8x4 (3D) / 16x16 (2D) brick of vertices instead of 256
@@ -316,14 +387,11 @@ vertex_values_kernel (DevTree T, DevField fld, int hull_only)
   const int bx = DIM == 3 ? 8 : 16, by = DIM == 3 ? 8 : 16, bz = DIM == 3 ? 4 : 1;
   const int tx = n1 > 0 ? (n1 + bx - 1)/bx : 0, ty = n1 > 0 ? (n1 + by - 1)/by : 0,
     tz = DIM == 3 && n1 > 0 ? (n1 + bz - 1)/bz : 1;
-  /* hull_only: just the vertices lattice_cell_pass_kernel left out (DevTree.hull_vtx) */
-  const int64_t n_items = hull_only ? T.n_hull_vtx : n1 > 0 ? (int64_t) tx*ty*tz*256 : T.n_vertices;
+  const int64_t n_items = n1 > 0 ? (int64_t) tx*ty*tz*256 : T.n_vertices;
   const int64_t stride = (int64_t) gridDim.x*blockDim.x;
   for (int64_t item = (int64_t) blockIdx.x*blockDim.x + threadIdx.x; item < n_items; item += stride) {
     int v = (int) item;
-    if (hull_only)
-      v = T.hull_vtx[item];
-    else if (n1 > 0) {
+    if (n1 > 0) {
       const int brick = (int) (item >> 8), t = (int) (item & 255);
       const int i = (brick % tx)*bx + (t % bx);
       const int j = ((brick/tx) % ty)*by + ((t/bx) % by);
@@ -334,7 +402,7 @@ vertex_values_kernel (DevTree T, DevField fld, int hull_only)
     }
     double s0 = 0., s1 = 0., s2 = 0.;
     bool nodata = false;
-    if (!hull_only && n1 > 0 && T.lattice_pattern >= 0) {
+    if (n1 > 0 && T.lattice_pattern >= 0) {
       const int i = v % n1, j = (v/n1) % n1, k = DIM == 3 ? v/(n1*n1) : 1;
       const int nn = n1 - 1;
       if (i >= 1 && i < nn && j >= 1 && j < nn && k >= 1 && (DIM == 2 || k < nn)) {
@@ -382,43 +450,7 @@ vertex_values_kernel (DevTree T, DevField fld, int hull_only)
 	continue;
       }
     }
-    const int b = T.vtx_off[v], e = T.vtx_off[v + 1];
-    /* most stencils carry one weight repeated (equal-size cells around the
-       vertex): it is stored once per vertex and the per-entry array is skipped */
-    const double wu = T.vtx_wuni[v];
-    const bool uni = wu == wu;
-    /* batches of 2^DIM entries: all indices first, then all gathers, then the
-       ordered accumulation -- the loads of a batch are in flight together.
-       Padding entries repeat a valid cell with weight 0 (s + 0*v == s). */
-    constexpr int NB = 1 << DIM;
-    for (int i = b; i < e; i += NB) {
-      int c[NB];
-      double w[NB], a0[NB], a1[NB], a2[NB];
-#pragma unroll
-      for (int j = 0; j < NB; j++) {
-	const bool ok = i + j < e;
-	c[j] = T.vtx_cell[ok ? i + j : i];
-	w[j] = ok ? (uni ? wu : T.vtx_w[i + j]) : 0.;
-      }
-#pragma unroll
-      for (int j = 0; j < NB; j++) {
-	a0[j] = fld.u[0][c[j]];
-	a1[j] = fld.u[1][c[j]];
-	a2[j] = DIM == 3 ? fld.u[2][c[j]] : 0.;
-      }
-#pragma unroll
-      for (int j = 0; j < NB; j++) {
-	/* GFS_NODATA = DBL_MAX: compare the high word on the integer pipe */
-	nodata |= is_nodata (a0[j]) | is_nodata (a1[j]) | (DIM == 3 && is_nodata (a2[j]));
-	s0 += w[j]*a0[j];
-	s1 += w[j]*a1[j];
-	if (DIM == 3) s2 += w[j]*a2[j];
-      }
-    }
-    if (nodata) {
-      s0 = s1 = s2 = GFSB200_NODATA;
-      *fld.nodata_flag = 1;
-    }
+    vertex_from_tables<DIM> (T, fld, v, s0, s1, s2);
     if (DIM == 2)
       reinterpret_cast<double2 *> (fld.vtx_val)[v] = make_double2 (s0, s1);
     else {
@@ -446,8 +478,9 @@ vertex_values_kernel (DevTree T, DevField fld, int hull_only)
  *   leaf (kx,ky,kz): vorticity_vector (modules/particulatecommon.c:142-164)
  *     from centred differences, the x1 = x2 = 1 case of gfs_center_gradient
  * in the same operation order as the table-driven kernels above (bit-identical
- * results, tested), with no index-table traffic at all.  Vertices and leaves
- * on the hull (DevTree.hull_vtx / hull_leaf) are left to those kernels.  HBM traffic per
+ * results, tested), with no index-table traffic at all.  Leaves on the hull
+ * take one-sided differences from the same region; the vertices on the hull
+ * (3 % of them) go through the stencil tables.  HBM traffic per
  * launch: 24 B per cell read (halo re-reads hit L2) + 32 B per vertex + 32 B
  * per leaf written. */
 #define BRICK 8
@@ -491,7 +524,7 @@ __device__ __forceinline__ void stage_brick (const DevTree & T, const DevField &
 	const int c = T.top_start + (int) (kx | ky | kz);
 	cp_async8 (&buf[0][o], U + c); cp_async8 (&buf[1][o], V + c); cp_async8 (&buf[2][o], W + c);
       }
-      else        /* only ever read by hull items, which this kernel skips */
+      else        /* outside the lattice: never read (the hull leaves test their coordinates) */
 	buf[0][o] = buf[1][o] = buf[2][o] = 0.;
     }
   }
@@ -500,7 +533,7 @@ __device__ __forceinline__ void stage_brick (const DevTree & T, const DevField &
 
 /* One CTA per brick, 4 CTAs per SM (64 registers: the 24 shared loads of a vertex are in flight
  * together).  A persistent variant with two region buffers (the next brick's copies in flight
- * during the compute phase) measured 1.6x SLOWER and starved the hull kernels; dropped. */
+ * during the compute phase) measured 1.6x SLOWER; dropped. */
 template <int PATTERN>
 __global__ void __launch_bounds__(256, 4)
 lattice_cell_pass_kernel (DevTree T, DevField fld)
@@ -558,23 +591,46 @@ lattice_cell_pass_kernel (DevTree T, DevField fld)
 	  o[1] = make_double2 (s2, 0.);
 	}
       }
-      /* ---- the leaf itself */
+      /* ---- the leaf itself.  gfs_center_gradient (src/fluid.c:434-475) with same-level leaf
+	 neighbours: centred where both exist (the x1 = x2 = 1 case), one-sided (v0 - v1)/1 or
+	 (v2 - v0)/1 at the hull where a neighbour is NULL, 0 where both are. */
       {
 	const int kx = bx*BRICK + tx, ky = by*BRICK + ty, kz = bz*BRICK + tz;
-	if (kx >= 1 && kx < nn - 1 && ky >= 1 && ky < nn - 1 && kz >= 1 && kz < nn - 1) {
+	{
 	  const double size = T.top_h;
+	  auto grad = [&] (const double * F, int st, int kc) -> double {
+	    const double v0 = F[r0];
+	    if (kc > 0) {
+	      if (kc < nn - 1)
+		return ((F[r0 + st] - v0) + (v0 - F[r0 - st]))/2.;
+	      return (v0 - F[r0 - st])/1.;
+	    }
+	    return kc < nn - 1 ? (F[r0 + st] - v0)/1. : 0.;
+	  };
 	  /* neighbour in direction 2c is +axis c, 2c + 1 is -axis c (FttDirection) */
-#define GRADS(F, st) ((((F)[r0 + (st)] - (F)[r0]) + ((F)[r0] - (F)[r0 - (st)]))/2.)
-	  const double wx = (GRADS (reg[2], REG) - GRADS (reg[1], PLANE))/size;
-	  const double wy = (GRADS (reg[0], PLANE) - GRADS (reg[2], 1))/size;
-	  const double wz = (GRADS (reg[1], 1) - GRADS (reg[0], REG))/size;
-#undef GRADS
+	  const double wx = (grad (reg[2], REG, ky) - grad (reg[1], PLANE, kz))/size;
+	  const double wy = (grad (reg[0], PLANE, kz) - grad (reg[2], 1, kx))/size;
+	  const double wz = (grad (reg[1], 1, kx) - grad (reg[0], REG, ky))/size;
 	  double2 * o = reinterpret_cast<double2 *> (fld.vort + ((int64_t) (kz*nn + ky)*nn + kx)*4);
 	  o[0] = make_double2 (wx, wy);
 	  o[1] = make_double2 (wz, 0.);
 	}
       }
     }
+    /* ---- vertices on the hull (a coordinate equal to 0 or nn): their stencils are the few
+       leaves that exist around them, in the tables' order; only the bricks that touch the hull
+       have any.  This brick owns i in [8 bx + 1, 8 bx + 8], and i = 0 if bx == 0. */
+    if (bx == 0 || by == 0 || bz == 0 || bx == nb - 1 || by == nb - 1 || bz == nb - 1)
+      for (int idx = threadIdx.x; idx < (BRICK + 1)*(BRICK + 1)*(BRICK + 1); idx += 256) {
+	const int li = idx % (BRICK + 1), lj = (idx/(BRICK + 1)) % (BRICK + 1), lk = idx/((BRICK + 1)*(BRICK + 1));
+	if ((li == 0 && bx) || (lj == 0 && by) || (lk == 0 && bz))
+	  continue;                            /* owned by the neighbouring brick */
+	const int i = bx*BRICK + li, j = by*BRICK + lj, k = bz*BRICK + lk;
+	if (i && j && k && i < nn && j < nn && k < nn)
+	  continue;                            /* interior: done above */
+	hull_vertex_3d (T.vtx_off, T.vtx_cell, T.vtx_w, fld.u[0], fld.u[1], fld.u[2], fld.nodata_flag,
+			fld.vtx_val, (k*n1 + j)*n1 + i);
+      }
   }
 }
 
@@ -600,8 +656,8 @@ extern "C" void gfsb200_launch_vertex_values (const DevTree * T, const DevField 
 					      cudaStream_t stream)
 {
   const int g = cell_grid (vertex_items (T), n_sm);
-  if (T->dim == 2) vertex_values_kernel<2><<<g, 256, 0, stream>>> (*T, *fld, 0);
-  else vertex_values_kernel<3><<<g, 256, 0, stream>>> (*T, *fld, 0);
+  if (T->dim == 2) vertex_values_kernel<2><<<g, 256, 0, stream>>> (*T, *fld);
+  else vertex_values_kernel<3><<<g, 256, 0, stream>>> (*T, *fld);
 }
 
 extern "C" void gfsb200_launch_convective (const DevTree * T, const DevField * fld, int n_sm,
@@ -631,32 +687,24 @@ extern "C" void gfsb200_launch_cell_pass (const DevTree * T, const DevField * fl
   if (gc > cap) gc = cap;
   if (gv < 1) gv = 1;
   if (gc < 1) gc = 1;
-  /* 3D lattice trees: interior vertices and leaves in one brick-tiled kernel, the hull through
-     the table-driven kernels */
-  const int nn = T->lattice_n1 - 1;
-  const bool fused = T->dim == 3 && T->hull_vtx != NULL;
+  /* 3D lattice trees: the whole pass in one brick-tiled kernel */
+  if (T->dim == 3 && T->lattice_bricks) {
+    const int nb = (T->lattice_n1 - 1)/BRICK;
+    if (T->lattice_pattern == REFERENCE_PATTERN)
+      lattice_cell_pass_kernel<REFERENCE_PATTERN><<<nb*nb*nb, 256, 0, stream>>> (*T, *fld);
+    else
+      lattice_cell_pass_kernel<-1><<<nb*nb*nb, 256, 0, stream>>> (*T, *fld);
+    return;
+  }
   cudaEventRecord (ev_fork, stream);
   cudaStreamWaitEvent (aux, ev_fork, 0);
   if (T->dim == 2) {
-    vertex_values_kernel<2><<<gv, threads, 0, stream>>> (*T, *fld, 0);
-    vorticity_kernel<2><<<gc, threads, 0, aux>>> (*T, *fld, 0);
+    vertex_values_kernel<2><<<gv, threads, 0, stream>>> (*T, *fld);
+    vorticity_kernel<2><<<gc, threads, 0, aux>>> (*T, *fld);
   }
   else {
-    if (fused) {
-      /* the (small, latency-bound) hull kernels go first so that their CTAs are resident
-	 before the brick kernel fills the machine */
-      vertex_values_kernel<3><<<(T->n_hull_vtx + threads - 1)/threads, threads, 0, aux>>> (*T, *fld, 1);
-      vorticity_kernel<3><<<(T->n_hull_leaf + threads - 1)/threads, threads, 0, aux>>> (*T, *fld, 1);
-      const int g = (nn/BRICK)*(nn/BRICK)*(nn/BRICK);
-      if (T->lattice_pattern == REFERENCE_PATTERN)
-	lattice_cell_pass_kernel<REFERENCE_PATTERN><<<g, 256, 0, stream>>> (*T, *fld);
-      else
-	lattice_cell_pass_kernel<-1><<<g, 256, 0, stream>>> (*T, *fld);
-    }
-    else {
-      vertex_values_kernel<3><<<gv, threads, 0, stream>>> (*T, *fld, 0);
-      vorticity_kernel<3><<<gc, threads, 0, aux>>> (*T, *fld, 0);
-    }
+    vertex_values_kernel<3><<<gv, threads, 0, stream>>> (*T, *fld);
+    vorticity_kernel<3><<<gc, threads, 0, aux>>> (*T, *fld);
   }
   cudaEventRecord (ev_join, aux);
   cudaStreamWaitEvent (stream, ev_join, 0);

@@ -50,10 +50,7 @@ struct DevTree {
 				  with (bx,by,bz) = bits dim*e .. dim*e + dim - 1.  Verified against
 				  the CSR tables at upload; -1 = use the tables */
   double lattice_w;            /* that common weight */
-  /* 3D lattice trees: what lattice_cell_pass_kernel leaves to the table-driven kernels */
-  const int32_t * hull_vtx;    /* [n_hull_vtx] vertices with a coordinate on the hull */
-  const int32_t * hull_leaf;   /* [n_hull_leaf] leaves with a face on the hull */
-  int n_hull_vtx, n_hull_leaf;
+  int lattice_bricks;          /* 3D lattice tree that lattice_cell_pass_kernel can tile with 8^3 bricks */
 };
 
 struct DevField {
