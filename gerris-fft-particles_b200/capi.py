@@ -132,6 +132,7 @@ def lib() -> C.CDLL:
         "gfsb200_download_deposit": (i32, [vp, i32, vp]),
         "gfsb200_timer_reset": (i32, [vp]),
         "gfsb200_timer_read": (i32, [vp, C.POINTER(dbl), C.POINTER(i64)]),
+        "gfsb200_kernel_launches": (i64, []),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)       # AttributeError if the library lacks a declared symbol
@@ -156,6 +157,11 @@ def _ptr(a: Optional[np.ndarray]):
 
 def _f64(a) -> Optional[np.ndarray]:
     return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def kernel_launches() -> int:
+    """this library's own kernels launched so far by the process"""
+    return int(lib().gfsb200_kernel_launches())
 
 
 def kernel_fit(func, dim: int):

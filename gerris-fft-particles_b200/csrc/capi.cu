@@ -60,6 +60,13 @@ cudaError_t gfsb200_cub_select_flagged (void *, size_t *, const int32_t *, const
 
 #define NCOL 8     /* x y z vx vy vz mass volume */
 
+/* number of this library's own kernels launched so far in the process (CUB's sort / select
+   kernels are not counted) */
+extern "C" {
+long long gfsb200_launch_counter = 0;
+int64_t gfsb200_kernel_launches (void) { return gfsb200_launch_counter; }
+}
+
 struct gfsb200_ctx {
   int device, n_sm;
   cudaStream_t stream;

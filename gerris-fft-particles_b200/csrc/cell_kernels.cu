@@ -21,6 +21,8 @@
 #include <stdlib.h>
 #include "device_types.cuh"
 
+extern "C" long long gfsb200_launch_counter;   /* kernels launched by this library (capi.cu) */
+
 namespace {
 
 __device__ __forceinline__ bool is_nodata (double v)
@@ -619,18 +621,35 @@ lattice_cell_pass_kernel (DevTree T, DevField fld)
     }
     /* ---- vertices on the hull (a coordinate equal to 0 or nn): their stencils are the few
        leaves that exist around them, in the tables' order; only the bricks that touch the hull
-       have any.  This brick owns i in [8 bx + 1, 8 bx + 8], and i = 0 if bx == 0. */
-    if (bx == 0 || by == 0 || bz == 0 || bx == nb - 1 || by == nb - 1 || bz == nb - 1)
-      for (int idx = threadIdx.x; idx < (BRICK + 1)*(BRICK + 1)*(BRICK + 1); idx += 256) {
-	const int li = idx % (BRICK + 1), lj = (idx/(BRICK + 1)) % (BRICK + 1), lk = idx/((BRICK + 1)*(BRICK + 1));
-	if ((li == 0 && bx) || (lj == 0 && by) || (lk == 0 && bz))
+       have any.  This brick owns i in [8 bx + 1, 8 bx + 8], and i = 0 if bx == 0.  They are
+       enumerated face by face (81 candidates each, dense in the warp); a vertex on several
+       hull faces belongs to the first. */
+    const int bc[3] = { bx, by, bz };
+#pragma unroll
+    for (int f = 0; f < 6; f++) {
+      const int axis = f >> 1, side = f & 1;
+      if (bc[axis] != (side ? nb - 1 : 0))
+	continue;
+      const int idx = threadIdx.x;
+      if (idx < (BRICK + 1)*(BRICK + 1)) {
+	const int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
+	const int l1 = idx % (BRICK + 1), l2 = idx/(BRICK + 1);
+	if ((l1 == 0 && bc[a1]) || (l2 == 0 && bc[a2]))
 	  continue;                            /* owned by the neighbouring brick */
-	const int i = bx*BRICK + li, j = by*BRICK + lj, k = bz*BRICK + lk;
-	if (i && j && k && i < nn && j < nn && k < nn)
-	  continue;                            /* interior: done above */
-	hull_vertex_3d (T.vtx_off, T.vtx_cell, T.vtx_w, fld.u[0], fld.u[1], fld.u[2], fld.nodata_flag,
-			fld.vtx_val, (k*n1 + j)*n1 + i);
+	int c[3];
+	c[axis] = side ? nn : 0;
+	c[a1] = bc[a1]*BRICK + l1;
+	c[a2] = bc[a2]*BRICK + l2;
+	bool first = true;                     /* not already on a lower-numbered hull face */
+#pragma unroll
+	for (int g = 0; g < 6; g++)
+	  if (g < f && c[g >> 1] == ((g & 1) ? nn : 0))
+	    first = false;
+	if (first)
+	  hull_vertex_3d (T.vtx_off, T.vtx_cell, T.vtx_w, fld.u[0], fld.u[1], fld.u[2], fld.nodata_flag,
+			  fld.vtx_val, (c[2]*n1 + c[1])*n1 + c[0]);
       }
+    }
   }
 }
 
@@ -655,6 +674,7 @@ static int64_t vertex_items (const DevTree * T)
 extern "C" void gfsb200_launch_vertex_values (const DevTree * T, const DevField * fld, int n_sm,
 					      cudaStream_t stream)
 {
+  gfsb200_launch_counter += 1;
   const int g = cell_grid (vertex_items (T), n_sm);
   if (T->dim == 2) vertex_values_kernel<2><<<g, 256, 0, stream>>> (*T, *fld);
   else vertex_values_kernel<3><<<g, 256, 0, stream>>> (*T, *fld);
@@ -663,6 +683,7 @@ extern "C" void gfsb200_launch_vertex_values (const DevTree * T, const DevField 
 extern "C" void gfsb200_launch_convective (const DevTree * T, const DevField * fld, int n_sm,
 					   cudaStream_t stream)
 {
+  gfsb200_launch_counter += 1;
   const int g = cell_grid (T->n_cells, n_sm);
   if (T->dim == 2) convective_kernel<2><<<g, 256, 0, stream>>> (*T, *fld);
   else convective_kernel<3><<<g, 256, 0, stream>>> (*T, *fld);
@@ -690,12 +711,14 @@ extern "C" void gfsb200_launch_cell_pass (const DevTree * T, const DevField * fl
   /* 3D lattice trees: the whole pass in one brick-tiled kernel */
   if (T->dim == 3 && T->lattice_bricks) {
     const int nb = (T->lattice_n1 - 1)/BRICK;
+    gfsb200_launch_counter += 1;
     if (T->lattice_pattern == REFERENCE_PATTERN)
       lattice_cell_pass_kernel<REFERENCE_PATTERN><<<nb*nb*nb, 256, 0, stream>>> (*T, *fld);
     else
       lattice_cell_pass_kernel<-1><<<nb*nb*nb, 256, 0, stream>>> (*T, *fld);
     return;
   }
+  gfsb200_launch_counter += 2;
   cudaEventRecord (ev_fork, stream);
   cudaStreamWaitEvent (aux, ev_fork, 0);
   if (T->dim == 2) {

@@ -20,6 +20,8 @@
 #include <cub/cub.cuh>
 #include "device_types.cuh"
 
+extern "C" long long gfsb200_launch_counter;   /* kernels launched by this library (capi.cu) */
+
 namespace {
 
 /* ------------------------------------------------------------------ */
@@ -1235,6 +1237,7 @@ extern "C" {
 void gfsb200_launch_step (const DevTree * T, const DevField * F, const DevParticles * P,
 			  const DevStep * S, int rec, int minb, int mode, int n_sm, cudaStream_t st)
 {
+  gfsb200_launch_counter += 1;
   if (P->n <= 0) return;
   const int th = 256;
   const unsigned g = grid_for (P->n, th);
@@ -1277,6 +1280,7 @@ void gfsb200_launch_step (const DevTree * T, const DevField * F, const DevPartic
 void gfsb200_launch_advect (const DevTree * T, const DevField * F, const DevParticles * P,
 			    double dt, int rec_cell, cudaStream_t st)
 {
+  gfsb200_launch_counter += 1;
   if (P->n <= 0) return;
   const int th = 256;
   const unsigned g = grid_for (P->n, th);
@@ -1293,6 +1297,7 @@ void gfsb200_launch_advect (const DevTree * T, const DevField * F, const DevPart
 void gfsb200_launch_locate (const DevTree * T, int64_t n, const double * x, const double * y,
 			    const double * z, int32_t * cell, cudaStream_t st)
 {
+  gfsb200_launch_counter += 1;
   if (n <= 0) return;
   if (T->dim == 3) locate_kernel<3><<<grid_for (n, 256), 256, 0, st>>> (*T, n, x, y, z, cell);
   else locate_kernel<2><<<grid_for (n, 256), 256, 0, st>>> (*T, n, x, y, z, cell);
@@ -1302,6 +1307,7 @@ void gfsb200_launch_interpolate (const DevTree * T, const DevField * F, int64_t 
 				 const double * x, const double * y, const double * z,
 				 double * u, double * v, double * w, cudaStream_t st)
 {
+  gfsb200_launch_counter += 1;
   if (n <= 0) return;
   if (T->dim == 3)
     interpolate_kernel<3><<<grid_for (n, 256), 256, 0, st>>> (*T, *F, n, x, y, z, u, v, w);
@@ -1312,6 +1318,7 @@ void gfsb200_launch_interpolate (const DevTree * T, const DevField * F, int64_t 
 void gfsb200_launch_corner_values (const DevTree * T, const DevField * F, int comp, int64_t n,
 				   const int32_t * cells, double * out, cudaStream_t st)
 {
+  gfsb200_launch_counter += 1;
   if (n <= 0) return;
   const int nc = 1 << T->dim;
   if (T->dim == 3)
@@ -1325,6 +1332,7 @@ void gfsb200_launch_deposit (const DevTree * T, const DevField * F, const DevPar
 			     const DevStep * S, int what, double * vol, double * f0, double * f1,
 			     double * f2, cudaStream_t st)
 {
+  gfsb200_launch_counter += 1;
   if (P->n <= 0 || !(what & 3)) return;
   const unsigned g = grid_for (P->n, 256);
   const bool lat = T->lattice_n1 > 0;
@@ -1357,6 +1365,7 @@ void gfsb200_launch_deposit_smoothed (const DevTree * T, const DevField * F, con
 				      double * f0, double * f1, double * f2, double * norm,
 				      cudaStream_t st)
 {
+  gfsb200_launch_counter += 2;
   if (P->n <= 0) return;
   const bool lat = T->lattice_n1 > 0;
   const unsigned g = grid_for (P->n, 256);
@@ -1376,6 +1385,7 @@ void gfsb200_launch_particle_bc (const DevTree * T, const DevParticles * P, int 
 				 const int32_t * esc_idx, const double * esc_old, uint8_t * keep,
 				 int * counters, cudaStream_t st)
 {
+  gfsb200_launch_counter += 1;
   if (n_esc <= 0) return;
   if (T->dim == 3)
     particle_bc_kernel<3><<<(n_esc + 127)/128, 128, 0, st>>> (*T, *P, n_esc, esc_idx, esc_old, keep, counters);
@@ -1387,28 +1397,33 @@ void gfsb200_launch_gather (int64_t n, const int32_t * perm, int ncols, const do
 			    double * const * dst, const uint32_t * id_src, uint32_t * id_dst,
 			    cudaStream_t st)
 {
+  gfsb200_launch_counter += 1;
   if (n <= 0) return;
   gather_kernel<<<grid_for (n, 256), 256, 0, st>>> (n, perm, ncols, src, dst, id_src, id_dst);
 }
 
 void gfsb200_launch_iota (int64_t n, int32_t * a, cudaStream_t st)
 {
+  gfsb200_launch_counter += 1;
   if (n > 0) iota_kernel<<<grid_for (n, 256), 256, 0, st>>> (n, a);
 }
 
 void gfsb200_launch_iota_u32 (int64_t n, uint32_t * a, uint32_t base, cudaStream_t st)
 {
+  gfsb200_launch_counter += 1;
   if (n > 0) iota_u32_kernel<<<grid_for (n, 256), 256, 0, st>>> (n, a, base);
 }
 
 void gfsb200_launch_sort_keys (int64_t n, const int32_t * cell, uint32_t * key,
 			       uint32_t outside_key, cudaStream_t st)
 {
+  gfsb200_launch_counter += 1;
   if (n > 0) sort_keys_kernel<<<grid_for (n, 256), 256, 0, st>>> (n, cell, key, outside_key);
 }
 
 void gfsb200_launch_inside_flags (int64_t n, const int32_t * cell, uint8_t * flag, cudaStream_t st)
 {
+  gfsb200_launch_counter += 1;
   if (n > 0) inside_flag_kernel<<<grid_for (n, 256), 256, 0, st>>> (n, cell, flag);
 }
 

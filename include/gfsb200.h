@@ -327,6 +327,9 @@ int gfsb200_download_deposit (gfsb200_ctx * c, int comp, double * out /* [n_cell
  * the last reset, measured with CUDA events on the context's stream */
 int gfsb200_timer_reset (gfsb200_ctx * c);
 int gfsb200_timer_read (gfsb200_ctx * c, double * step_kernel_ms, int64_t * launches);
+/* how many of this library's own CUDA kernels have been launched by the process so far (the
+ * library kernels inside cub::DeviceRadixSort / DeviceSelect are not counted) */
+int64_t gfsb200_kernel_launches (void);
 
 #ifdef __cplusplus
 }
