@@ -84,3 +84,22 @@ def test_kernel_fit_recognises_the_closed_forms():
                 lambda x, y, z: float("nan")):
         with pytest.raises(capi.GfsB200Error):
             capi.kernel_fit(bad, 3)
+
+
+def test_dropin_module_type_checks_against_reference_headers():
+    """host/particulates_b200.c (the libparticulates{2D,3D}.so replacement) is type-checked
+    with gcc -fsyntax-only against the reference's own src/*.h and
+    modules/particulatecommon.h, GLib/GTS being stood in for by declaration-only headers
+    (host/check/).  Needs the reference tree; skipped on the GPU box."""
+    import os
+    import subprocess
+    import pytest
+    if not os.path.exists("/root/reference/src/ftt.h"):
+        pytest.skip("reference tree not present")
+    env = dict(os.environ)
+    env.pop("CC", None)
+    pkg_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gerris-fft-particles_b200")
+    r = subprocess.run(["make", "check-host"], cwd=pkg_dir, env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "warning" not in r.stdout, r.stdout[-3000:]
