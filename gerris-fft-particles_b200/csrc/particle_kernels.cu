@@ -1108,7 +1108,16 @@ __device__ __forceinline__ void traverse_kernel_support (const DevTree & T, doub
 	  const double dz = __dsub_rn (cz, pz);
 	  d2 = __dadd_rn (d2, __dmul_rn (dz, dz));
 	}
-	bool ok = __dsub_rn (__dsqrt_rn (d2), __dmul_rn (size, SQ)) <= rkernel;
+	/* ftt_vector_distance (..) - radeq <= distance, decided without the square root unless
+	   d2 is within 1e-12 of (distance + radeq)^2 (then by the reference's exact expression) */
+	const double radeq = __dmul_rn (size, SQ), reach = rkernel + radeq, reach2 = reach*reach;
+	bool ok;
+	if (d2 <= reach2*(1. - 1e-12))
+	  ok = true;
+	else if (d2 >= reach2*(1. + 1e-12))
+	  ok = false;
+	else
+	  ok = __dsub_rn (__dsqrt_rn (d2), radeq) <= rkernel;
 	if (!ok)          /* "check also if the bubble is inside the cell" */
 	  ok = !(px > cx + size || px < cx - size || py > cy + size || py < cy - size ||
 		 (DIM == 3 && (pz > cz + size || pz < cz - size)));
@@ -1172,15 +1181,20 @@ smoothed_deposit_kernel (DevTree T, DevField fld, DevParticles P, double rho_con
   if (!norm && Fx == 0. && Fy == 0. && Fz == 0.)
     return;
   const double rb = pow (__ddiv_rn (__dmul_rn (3., P.volume[i]), 4.*M_PI), 1./3.);
+  /* offsets are scaled by 1/r_b with a multiplication (the reference divides): device pow
+     already differs from libm's by an ulp, so the kernel argument is not bit-reproducible
+     either way; the deposit stays within its 1e-12 bar */
+  const double inv_rb = 1./rb;
   const bool fixz = (K.flags & GFSB200_KERNEL_FIX_Z) != 0;
+  const double qz_const = DIM == 3 ? -pz*inv_rb : 0.;        /* the reference's (0 - z_p)/r_b */
 
   double volume = 0., correction = 0.;
   traverse_kernel_support<DIM> (T, px, py, pz, rkernel,
     [&] (int cell, double cx, double cy, double cz, double half) {
       const double h = 2.*half, cellvol = DIM == 3 ? h*h*h : h*h;     /* powers of two: exact */
       volume = __dadd_rn (volume, cellvol);
-      const double qx = __ddiv_rn (__dsub_rn (cx, px), rb), qy = __ddiv_rn (__dsub_rn (cy, py), rb);
-      const double qz = DIM == 3 ? __ddiv_rn (__dsub_rn (fixz ? cz : 0., pz), rb) : 0.;
+      const double qx = (cx - px)*inv_rb, qy = (cy - py)*inv_rb;
+      const double qz = DIM == 3 ? (fixz ? (cz - pz)*inv_rb : qz_const) : 0.;
       correction = __dadd_rn (correction, __dmul_rn (kernel_value (K, qx, qy, qz), cellvol));
     });
   correction = __ddiv_rn (correction, volume);
@@ -1190,18 +1204,21 @@ smoothed_deposit_kernel (DevTree T, DevField fld, DevParticles P, double rho_con
   }
   if (!(correction > 1.e-10))
     return;
+  /* F/rho/V_cell*K/correction: V_cell is a power of two, 1/correction is hoisted */
+  const double inv_corr = 1./correction;
+  const double inv_rho = fld.alpha ? 0. : 1./rho_const;
   traverse_kernel_support<DIM> (T, px, py, pz, rkernel,
     [&] (int cell, double cx, double cy, double cz, double half) {
-      const double h = 2.*half, cellvol = DIM == 3 ? h*h*h : h*h;
-      const double rho = fld.alpha ? __ddiv_rn (1., fld.alpha[cell]) : rho_const;
-      const double qx = __ddiv_rn (__dsub_rn (cx, px), rb), qy = __ddiv_rn (__dsub_rn (cy, py), rb);
-      const double qz = DIM == 3 ? __ddiv_rn (__dsub_rn (fixz ? cz : 0., pz), rb) : 0.;
-      const double k = kernel_value (K, qx, qy, qz);
-      /* F/rho/V_cell*K/correction, left to right */
-      atomicAdd (f0 + cell, -__ddiv_rn (__dmul_rn (__ddiv_rn (__ddiv_rn (Fx, rho), cellvol), k), correction));
-      atomicAdd (f1 + cell, -__ddiv_rn (__dmul_rn (__ddiv_rn (__ddiv_rn (Fy, rho), cellvol), k), correction));
+      const double inv_h = __longlong_as_double ((2045LL << 52) - __double_as_longlong (half));   /* 1/(2 half) */
+      const double inv_cellvol = DIM == 3 ? inv_h*inv_h*inv_h : inv_h*inv_h;
+      const double ir = fld.alpha ? fld.alpha[cell] : inv_rho;       /* 1/rho = alpha */
+      const double qx = (cx - px)*inv_rb, qy = (cy - py)*inv_rb;
+      const double qz = DIM == 3 ? (fixz ? (cz - pz)*inv_rb : qz_const) : 0.;
+      const double s = -kernel_value (K, qx, qy, qz)*inv_corr*inv_cellvol*ir;
+      atomicAdd (f0 + cell, Fx*s);
+      atomicAdd (f1 + cell, Fy*s);
       if (DIM == 3)
-	atomicAdd (f2 + cell, -__ddiv_rn (__dmul_rn (__ddiv_rn (__ddiv_rn (Fz, rho), cellvol), k), correction));
+	atomicAdd (f2 + cell, Fz*s);
     });
 }
 

@@ -36,3 +36,20 @@ for r in rk_h:
     leaves = vol / hmin ** 3
     print(json.dumps({"config": cfg, "particles": n, "rkernel_over_hmin": r, "ms": dt * 1e3,
                       "particles_per_s": n / dt, "mean_cells_per_particle_volume_units": float(leaves.mean())}))
+
+# the oracle (reference traversal object code + restated callbacks) on a small sample, one core
+if os.environ.get("SMOOTHED_ORACLE", "1") == "1" and cfg == "C2":
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    ora = helpers.ora
+    w2 = worlds.make_c2(level=6, n_particles=2000)          # 64^3: the oracle tree build stays short
+    sim, ptrs = helpers.matched_oracle(w2)
+    p2 = worlds.make_particles(w2)
+    plist = ora.ParticleList(sim, *[p2[k] for k in ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")])
+    h6 = 0.5 ** 6
+    for r in rk_h:
+        t0 = time.perf_counter()
+        plist.deposit_force_smoothed(helpers.oracle_params(w2), 4, r * h6, ora.Kernel(ora.KERNEL_GAUSSIAN, 1.0, 1e-5, 1, 0))
+        dt = time.perf_counter() - t0
+        print(json.dumps({"oracle_cpu_1core": True, "tree": "64^3", "particles": 2000, "rkernel_over_hmin": r,
+                          "particles_per_s": 2000 / dt}))
