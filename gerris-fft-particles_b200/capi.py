@@ -121,6 +121,10 @@ def lib() -> C.CDLL:
         "gfsb200_particles_sort": (i32, [vp]),
         "gfsb200_locate": (i32, [vp, i64, vp, vp, vp, vp]),
         "gfsb200_interpolate": (i32, [vp, i64, vp, vp, vp, vp, vp, vp]),
+        "gfsb200_output_location": (i32, [vp, i32, vp, i32, i64, vp, vp, vp, vp, vp]),
+        "gfsb200_particles_write_gfs": (i32, [vp, C.c_char_p, C.c_char_p, dbl, i32]),
+        "gfsb200_checkpoint_save": (i32, [vp, C.c_char_p]),
+        "gfsb200_checkpoint_load": (i32, [vp, C.c_char_p]),
         "gfsb200_deposit_volume": (i32, [vp]),
         "gfsb200_deposit_force": (i32, [vp, C.POINTER(StepParamsC)]),
         "gfsb200_deposit_all": (i32, [vp, C.POINTER(StepParamsC)]),
@@ -467,6 +471,31 @@ class Context:
         _check(self._lib.gfsb200_interpolate(self.handle, n, _ptr(x), _ptr(y), _ptr(z), _ptr(u), _ptr(v), _ptr(w)),
                "interpolate")
         return u, v, w
+
+    def output_location(self, variables, x, y, z=None, interpolate=True):
+        """GfsOutputLocation for arbitrary cell variables (each an array of n_cells doubles);
+        returns (values [nvar][n], cell [n])"""
+        x, y = np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(y, dtype=np.float64)
+        z = None if z is None else np.ascontiguousarray(z, dtype=np.float64)
+        vs = [np.ascontiguousarray(v, dtype=np.float64) for v in variables]
+        n = len(x)
+        out = np.empty((len(vs), n))
+        cell = np.empty(n, dtype=np.int32)
+        vp = (C.c_void_p * max(len(vs), 1))(*[v.ctypes.data for v in vs])
+        op = (C.c_void_p * max(len(vs), 1))(*[out[k].ctypes.data for k in range(len(vs))])
+        _check(self._lib.gfsb200_output_location(self.handle, len(vs), vp, int(bool(interpolate)), n, _ptr(x),
+                                                 _ptr(y), _ptr(z), op, _ptr(cell)), "output_location")
+        return out, cell
+
+    def write_gfs(self, path, class_name="GfsParticulate", L=1.0, append=False):
+        _check(self._lib.gfsb200_particles_write_gfs(self.handle, str(path).encode(), class_name.encode(), L,
+                                                     int(append)), "particles_write_gfs")
+
+    def checkpoint_save(self, path):
+        _check(self._lib.gfsb200_checkpoint_save(self.handle, str(path).encode()), "checkpoint_save")
+
+    def checkpoint_load(self, path):
+        _check(self._lib.gfsb200_checkpoint_load(self.handle, str(path).encode()), "checkpoint_load")
 
     def deposit_volume(self):
         _check(self._lib.gfsb200_deposit_volume(self.handle), "deposit_volume")

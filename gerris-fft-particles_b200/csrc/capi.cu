@@ -1072,6 +1072,191 @@ extern "C" int gfsb200_interpolate (gfsb200_ctx * c, int64_t n, const double * x
   return GFSB200_OK;
 }
 
+/* GfsOutputLocation for arbitrary cell variables, three per pass (the vertex kernel and
+ * the interpolation kernel work on component triples) */
+extern "C" int gfsb200_output_location (gfsb200_ctx * c, int nvar, const double * const * vars,
+					int interpolate, int64_t n, const double * x, const double * y,
+					const double * z, double * const * out, int32_t * cell)
+{
+  if (!c || !c->have_tree) return gfsb200_fail (GFSB200_ERR_STATE, "output_location: no tree resident");
+  if (nvar < 0 || n < 0 || (nvar && (!vars || !out)) || (n && (!x || !y || (c->T.dim == 3 && !z))))
+    return gfsb200_fail (GFSB200_ERR_ARG, "output_location: bad argument");
+  for (int k = 0; k < nvar; k++)
+    if (!vars[k] || !out[k]) return gfsb200_fail (GFSB200_ERR_ARG, "output_location: null variable %d", k);
+  if (n == 0) return GFSB200_OK;
+  CK (cudaSetDevice (c->device));
+  const int dim = c->T.dim;
+  const size_t nc = c->T.n_cells;
+  double * d[3] = { NULL, NULL, NULL }, * o[3] = { NULL, NULL, NULL }, * f[3] = { NULL, NULL, NULL };
+  double * vtx = NULL;
+  int * flag = NULL;
+  int32_t * dcell = NULL;
+  std::vector<int32_t> hcell (n);
+  int rc = GFSB200_OK;
+#define OL(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    rc = gfsb200_fail (GFSB200_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString (e_), __FILE__, __LINE__); \
+    goto done; } } while (0)
+  {
+    const double * src[3] = { x, y, z };
+    for (int a = 0; a < dim; a++) {
+      OL (cudaMalloc ((void **) &d[a], n*sizeof (double)));
+      OL (cudaMemcpyAsync (d[a], src[a], n*sizeof (double), cudaMemcpyHostToDevice, c->stream));
+    }
+    OL (cudaMalloc ((void **) &dcell, n*sizeof (int32_t)));
+    gfsb200_launch_locate (&c->T, n, d[0], d[1], d[2], dcell, c->stream);
+    OL (cudaGetLastError ());
+    OL (cudaMemcpyAsync (hcell.data (), dcell, n*sizeof (int32_t), cudaMemcpyDeviceToHost, c->stream));
+    OL (cudaStreamSynchronize (c->stream));
+    if (cell) memcpy (cell, hcell.data (), n*sizeof (int32_t));
+    if (!interpolate) {
+      /* GFS_VALUE (cell, v) */
+      for (int k = 0; k < nvar; k++)
+	for (int64_t i = 0; i < n; i++)
+	  out[k][i] = hcell[i] >= 0 ? vars[k][hcell[i]] : GFSB200_NODATA;
+      goto done;
+    }
+    const int vs = dim == 3 ? 4 : 2;
+    for (int a = 0; a < dim; a++) {
+      OL (cudaMalloc ((void **) &f[a], nc*sizeof (double)));
+      OL (cudaMalloc ((void **) &o[a], n*sizeof (double)));
+    }
+    OL (cudaMalloc ((void **) &vtx, (size_t) (c->T.n_vertices ? c->T.n_vertices : 1)*vs*sizeof (double)));
+    OL (cudaMalloc ((void **) &flag, sizeof (int)));
+    for (int k0 = 0; k0 < nvar; k0 += dim) {
+      DevField tmp;
+      memset (&tmp, 0, sizeof tmp);
+      for (int a = 0; a < dim; a++) {
+	const int k = k0 + a < nvar ? k0 + a : k0;      /* pad a short batch with its first variable */
+	OL (cudaMemcpyAsync (f[a], vars[k], nc*sizeof (double), cudaMemcpyHostToDevice, c->stream));
+	tmp.u[a] = f[a];
+      }
+      tmp.vtx_val = vtx;
+      tmp.nodata_flag = flag;
+      OL (cudaMemsetAsync (flag, 0, sizeof (int), c->stream));
+      gfsb200_launch_vertex_values (&c->T, &tmp, c->n_sm, c->stream);
+      OL (cudaGetLastError ());
+      gfsb200_launch_interpolate (&c->T, &tmp, n, d[0], d[1], d[2], o[0], o[1], dim == 3 ? o[2] : NULL, c->stream);
+      OL (cudaGetLastError ());
+      for (int a = 0; a < dim && k0 + a < nvar; a++)
+	OL (cudaMemcpyAsync (out[k0 + a], o[a], n*sizeof (double), cudaMemcpyDeviceToHost, c->stream));
+      OL (cudaStreamSynchronize (c->stream));
+    }
+  }
+done:
+#undef OL
+  for (int a = 0; a < 3; a++) { cudaFree (d[a]); cudaFree (o[a]); cudaFree (f[a]); }
+  cudaFree (vtx); cudaFree (flag); cudaFree (dcell);
+  return rc;
+}
+
+/* ------------------------------------------------------------------ */
+/* particle data formats                                                */
+
+extern "C" int gfsb200_particles_write_gfs (gfsb200_ctx * c, const char * path, const char * class_name,
+					    double L, int append)
+{
+  if (!c || !path || !class_name) return gfsb200_fail (GFSB200_ERR_ARG, "particles_write_gfs: null argument");
+  const int64_t n = c->n;
+  const int dim = c->have_tree ? c->T.dim : 3;
+  std::vector<double> col[11];
+  std::vector<uint32_t> id (n ? n : 1);
+  for (int k = 0; k < 11; k++) col[k].assign (n ? n : 1, 0.);
+  int r = gfsb200_particles_download (c, col[0].data (), col[1].data (), dim == 3 ? col[2].data () : NULL,
+				      col[3].data (), col[4].data (), dim == 3 ? col[5].data () : NULL,
+				      c->force[0] ? col[8].data () : NULL, c->force[1] ? col[9].data () : NULL,
+				      c->force[2] && dim == 3 ? col[10].data () : NULL,
+				      col[6].data (), col[7].data (), id.data (), NULL);
+  if (r) return r;
+  FILE * fp = fopen (path, append ? "a" : "w");
+  if (!fp) return gfsb200_fail (GFSB200_ERR_ARG, "particles_write_gfs: cannot open '%s'", path);
+  const double Ld = pow (L, dim);
+  for (int64_t i = 0; i < n; i++) {
+    /* gfs_event_list_write indent; gfs_particle_write; gfs_particulate_write (two fprintf calls) */
+    fputs ("    ", fp);
+    fprintf (fp, "%s", class_name);
+    fprintf (fp, " %d %g %g %g", (int) id[i], col[0][i], col[1][i], col[2][i]);
+    fprintf (fp, " %g %g %g %g %g", col[6][i], col[7][i]*Ld, col[3][i], col[4][i], col[5][i]);
+    fprintf (fp, " %g %g %g", col[8][i], col[9][i], col[10][i]);
+    fputc ('\n', fp);
+  }
+  if (fclose (fp) != 0) return gfsb200_fail (GFSB200_ERR_ARG, "particles_write_gfs: write to '%s' failed", path);
+  return GFSB200_OK;
+}
+
+struct CheckpointHeader {
+  char magic[8];
+  uint32_t version, dim;
+  int64_t n;
+  uint32_t has_force, reserved;
+};
+
+extern "C" int gfsb200_checkpoint_save (gfsb200_ctx * c, const char * path)
+{
+  if (!c || !path) return gfsb200_fail (GFSB200_ERR_ARG, "checkpoint_save: null argument");
+  const int64_t n = c->n;
+  CheckpointHeader h;
+  memset (&h, 0, sizeof h);
+  memcpy (h.magic, "GFSB200P", 8);
+  h.version = 1; h.dim = c->have_tree ? c->T.dim : 3; h.n = n;
+  h.has_force = c->force[0] != NULL && c->aux_cap >= n;
+  std::vector<double> col[11];
+  std::vector<uint32_t> id (n ? n : 1);
+  for (int k = 0; k < 11; k++) col[k].assign (n ? n : 1, 0.);
+  int r = gfsb200_particles_download (c, col[0].data (), col[1].data (), col[2].data (), col[3].data (),
+				      col[4].data (), col[5].data (),
+				      h.has_force ? col[8].data () : NULL, h.has_force ? col[9].data () : NULL,
+				      h.has_force ? col[10].data () : NULL,
+				      col[6].data (), col[7].data (), id.data (), NULL);
+  if (r) return r;
+  FILE * fp = fopen (path, "wb");
+  if (!fp) return gfsb200_fail (GFSB200_ERR_ARG, "checkpoint_save: cannot open '%s'", path);
+  bool ok = fwrite (&h, sizeof h, 1, fp) == 1;
+  for (int k = 0; k < 11 && ok; k++)
+    ok = n == 0 || fwrite (col[k].data (), sizeof (double), n, fp) == (size_t) n;
+  ok = ok && (n == 0 || fwrite (id.data (), sizeof (uint32_t), n, fp) == (size_t) n);
+  ok = (fclose (fp) == 0) && ok;
+  return ok ? GFSB200_OK : gfsb200_fail (GFSB200_ERR_ARG, "checkpoint_save: write to '%s' failed", path);
+}
+
+extern "C" int gfsb200_checkpoint_load (gfsb200_ctx * c, const char * path)
+{
+  if (!c || !path) return gfsb200_fail (GFSB200_ERR_ARG, "checkpoint_load: null argument");
+  FILE * fp = fopen (path, "rb");
+  if (!fp) return gfsb200_fail (GFSB200_ERR_ARG, "checkpoint_load: cannot open '%s'", path);
+  CheckpointHeader h;
+  if (fread (&h, sizeof h, 1, fp) != 1 || memcmp (h.magic, "GFSB200P", 8) || h.version != 1 || h.n < 0 ||
+      h.n > INT32_MAX) {
+    fclose (fp);
+    return gfsb200_fail (GFSB200_ERR_ARG, "checkpoint_load: '%s' is not a version-1 GFSB200P checkpoint", path);
+  }
+  if (c->have_tree && (int) h.dim != c->T.dim) {
+    fclose (fp);
+    return gfsb200_fail (GFSB200_ERR_ARG, "checkpoint_load: checkpoint is %uD, the resident tree %dD", h.dim, c->T.dim);
+  }
+  const int64_t n = h.n;
+  std::vector<double> col[11];
+  std::vector<uint32_t> id (n ? n : 1);
+  bool ok = true;
+  for (int k = 0; k < 11 && ok; k++) {
+    col[k].assign (n ? n : 1, 0.);
+    ok = n == 0 || fread (col[k].data (), sizeof (double), n, fp) == (size_t) n;
+  }
+  ok = ok && (n == 0 || fread (id.data (), sizeof (uint32_t), n, fp) == (size_t) n);
+  fclose (fp);
+  if (!ok) return gfsb200_fail (GFSB200_ERR_ARG, "checkpoint_load: '%s' is truncated", path);
+  int r = gfsb200_particles_upload (c, n, col[0].data (), col[1].data (), h.dim == 3 ? col[2].data () : NULL,
+				    col[3].data (), col[4].data (), h.dim == 3 ? col[5].data () : NULL,
+				    col[6].data (), col[7].data (), id.data ());
+  if (r) return r;
+  if (h.has_force && n) {
+    if ((r = ensure_aux (c, n))) return r;
+    for (int k = 0; k < 3; k++)
+      CK (cudaMemcpyAsync (c->force[k], col[8 + k].data (), n*sizeof (double), cudaMemcpyHostToDevice, c->stream));
+    CK (cudaStreamSynchronize (c->stream));
+  }
+  return GFSB200_OK;
+}
+
 /* ------------------------------------------------------------------ */
 /* two-way coupling                                                     */
 

@@ -5,7 +5,7 @@
  * Build (on a machine that has Gerris' development files; GLib/GTS are absent
  * from the image this repository is developed in, so the module cannot be
  * LINKED there.  It is TYPE-CHECKED there, in 2D and 3D, against the reference's
- * own src/*.h and modules/particulatecommon.h with declaration-only GLib/GTS
+ * own src headers and modules/particulatecommon.h with declaration-only GLib/GTS
  * stand-ins: `make -C gerris-fft-particles_b200 check-host`, run by
  * __graft_entry__.build() and tests/test_capi_symbols.py -- see INTEGRATION.md):
  *

@@ -23,6 +23,9 @@
  *                        source_particulate_event           modules/particulatecommon.c:2177-2228
  *                          (nearest cell, and with the smoothing kernel :2087-2175)
  *   tracer advection     gfs_domain_advect_point            src/domain.c:2764-2788
+ *   output at points     gfs_output_location_event          src/output.c:1153-1212
+ *   particle text/dump   gfs_particle_write                 src/particle.c:86-98
+ *                        gfs_particulate_write              modules/particulatecommon.c:910-926
  *
  * All functions returning int return GFSB200_OK (0) or a negative error code;
  * gfsb200_last_error() gives the message of the last failure on the calling
@@ -264,6 +267,33 @@ int gfsb200_locate (gfsb200_ctx * c, int64_t n, const double * x, const double *
 /* Batched locate + gfs_interpolate of U,V,W at host points; out[comp] may be NULL */
 int gfsb200_interpolate (gfsb200_ctx * c, int64_t n, const double * x, const double * y,
 			 const double * z, double * u, double * v, double * w);
+
+/* GfsOutputLocation (gfs_output_location_event, src/output.c:1153-1212) for ANY cell
+ * variables, batched: every point is located once, then each of the nvar variables
+ * (vars[k]: host array of n_cells doubles in flat-tree order) is evaluated there by
+ * gfs_interpolate (interpolate != 0: corner stencils + trilinear, src/fluid.c:2697-2710) or
+ * as the containing cell's value (interpolate == 0).  out[k]: n doubles; cell (may be NULL):
+ * flat index or -1 -- the reference prints no line for a point outside the domain, and
+ * out[k][i] is GFS_NODATA there.  The resident U,V,W tables are not disturbed. */
+int gfsb200_output_location (gfsb200_ctx * c, int nvar, const double * const * vars, int interpolate,
+			     int64_t n, const double * x, const double * y, const double * z,
+			     double * const * out, int32_t * cell);
+
+/* ---- particle data formats --------------------------------------------- */
+/* The particle block of a GfsParticleList as the reference writes it into a .gfs / simulation
+ * dump: one line per resident particle,
+ *   "    <class> id x y z mass volume*L^dim vx vy vz fx fy fz\n"
+ * with the "%d"/"%g" conversions of gfs_particle_write (src/particle.c:86-98) and
+ * gfs_particulate_write (modules/particulatecommon.c:910-926), indented as gfs_event_list_write
+ * does (src/event.c:2508-2523).  class_name is "GfsParticulate" for the reference's lists.
+ * append != 0 appends to the file.  (%g keeps 6 digits: use the checkpoint below to restart.) */
+int gfsb200_particles_write_gfs (gfsb200_ctx * c, const char * path, const char * class_name,
+				 double L, int append);
+/* Lossless binary checkpoint of the resident particle state (SoA fp64 columns, ids, last
+ * recorded forces) and its restore; the file starts with "GFSB200P", a format version, dim
+ * and the particle count.  Replaces the lossy text round trip on restart. */
+int gfsb200_checkpoint_save (gfsb200_ctx * c, const char * path);
+int gfsb200_checkpoint_load (gfsb200_ctx * c, const char * path);
 
 /* ---- two-way coupling -------------------------------------------------- */
 /* GfsParticulateField: field[cell] = sum V_p / V_cell over resident particles

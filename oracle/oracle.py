@@ -91,6 +91,7 @@ def load(dim: int) -> C.CDLL:
         "ora_deposit_force": (None, [vp, vp, C.POINTER(StepParams), i32]),
         "ora_deposit_force_smoothed": (None, [vp, vp, C.POINTER(StepParams), i32, dbl, C.POINTER(Kernel), vp, vp]),
         "ora_advect_points": (None, [vp, lng, vp, vp, vp, dbl]),
+        "ora_list_write": (i32, [vp, C.c_char_p, dbl]),
         "ora_max_threads": (i32, []),
     }
     for name, (res, args) in sig.items():
@@ -281,3 +282,7 @@ class ParticleList:
         self.sim.L.ora_deposit_force_smoothed(self.sim.h, self.h, C.byref(params), ivar0, rkernel,
                                               C.byref(kernel), _p(corr), _p(vol))
         return corr, vol
+
+    def write(self, path, L=1.0):
+        """the particle block as the reference writes it into a .gfs / dump file"""
+        assert self.sim.L.ora_list_write(self.h, str(path).encode(), L) == 0

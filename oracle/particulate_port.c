@@ -22,6 +22,7 @@
  *   force deposit (single-cell limit)    modules/particulatecommon.c:753-765, 2158-2228
  *   force deposit with smoothing kernel  modules/particulatecommon.c:2087-2228
  *   passive tracer advection             src/particle.c:31-44, src/domain.c:2764-2788
+ *   particle text format                 src/particle.c:86-98, modules/particulatecommon.c:910-926
  *   particle BCs (periodic wrap / drop)  modules/particulatecommon.c:3058-3214, 3318-3395
  *
  * PARITY PIN: the reference ships no test, example or golden vector for the
@@ -1113,6 +1114,29 @@ void ora_list_get (OraList * l, double * x, double * y, double * z,
     if (fx) { fx[i] = p->force.x; fy[i] = p->force.y; fz[i] = p->force.z; }
     if (id) id[i] = p->id;
   }
+}
+
+/* The particle block of gfs_event_list_write (src/event.c:2508-2523): per list member four
+ * spaces, the object's write method -- gfs_particle_write (src/particle.c:86-98: class name,
+ * " %d %g %g %g" id and position) then gfs_particulate_write
+ * (modules/particulatecommon.c:910-926: " %g %g %g %g %g" mass, volume*L^dim, velocity and
+ * " %g %g %g" force) -- and a newline.  No coordinate mapping (GfsMap list empty). */
+int ora_list_write (OraList * l, const char * path, double L)
+{
+  FILE * fp = fopen (path, "w");
+  long i;
+  if (!fp) return -1;
+  for (i = 0; i < l->n; i++) {
+    OraParticulate * p = l->p[i];
+    fputs ("    ", fp);
+    fprintf (fp, "%s", "GfsParticulate");
+    fprintf (fp, " %d %g %g %g", p->id, p->pos.x, p->pos.y, p->pos.z);
+    fprintf (fp, " %g %g %g %g %g", p->mass, p->volume*pow (L, FTT_DIMENSION),
+	     p->vel.x, p->vel.y, p->vel.z);
+    fprintf (fp, " %g %g %g", p->force.x, p->force.y, p->force.z);
+    fputc ('\n', fp);
+  }
+  return fclose (fp);
 }
 
 /* modules/particulatecommon.c:955-969 + 980-987: drop particles whose

@@ -433,6 +433,80 @@ def test_deposit_smoothed_rejects_unknown_kernel(ctx):
         ctx.deposit_force_smoothed(w.step_params(), 0.1, kind=7)
 
 
+@pytest.mark.parametrize("kind", ["c1", "ring3", "chain2", "uniform3"])
+def test_output_location_any_variable(kind, ctx):
+    """GfsOutputLocation (src/output.c:1153-1212) for arbitrary cell variables: four variables
+    (more than one pass of three), interpolated and as cell values; values within 4 ulp of
+    max|field| of gfs_interpolate (vertex sums shared between leaves), cells bit-exact."""
+    w, sim, ptrs, idx = setup(kind, ctx)
+    a = w.arrays
+    rng = np.random.default_rng(99)
+    live = (a.flags & capi.CELL_DESTROYED) == 0
+    variables = [np.sin(3 * a.pos[:, 0]) + a.pos[:, 1] ** 2, np.cos(2 * a.pos[:, 1]) - a.pos[:, 0],
+                 a.pos[:, 0] * a.pos[:, 1] + 0.3 * a.pos[:, 2], rng.standard_normal(a.n_cells)]
+    for k, v in enumerate(variables):
+        sim.set_values(3 + k, ptrs[live], v[live])
+    parts = _particles(w, 5000)
+    x, y, z = parts["x"], parts["y"], parts["z"]
+    x[:7] = 0.9 if kind != "chain2" else 9.0                 # outside the domain
+    got, cell = ctx.output_location(variables, x, y, z)
+    want_cell = idx(sim.locate(x, y, z))
+    assert np.array_equal(cell, want_cell)
+    inside = want_cell >= 0
+    assert (~inside).sum() >= 7 and (got[:, ~inside] == 1.7976931348623157e308).all()
+    for k, v in enumerate(variables):
+        want = sim.interpolate(3 + k, x, y, z)
+        tol = 4 * np.finfo(np.float64).eps * np.abs(v).max()
+        assert np.abs(got[k][inside] - want[inside]).max() <= tol, k
+    got0, _ = ctx.output_location(variables, x, y, z, interpolate=False)
+    for k, v in enumerate(variables):
+        assert np.array_equal(got0[k][inside], v[want_cell[inside]])
+    # the resident U,V,W tables are untouched
+    u, v_, w_ = ctx.interpolate(x, y, z)
+    assert np.abs(u[inside] - sim.interpolate(0, x, y, z)[inside]).max() <= 4e-16 * max(np.abs(w.u).max(), 1)
+
+
+@pytest.mark.parametrize("kind", ["c1", "ring3"])
+def test_particle_text_format_and_checkpoint(kind, ctx, tmp_path):
+    """The particle block written from the device state is byte-identical to the reference's
+    gfs_particle_write + gfs_particulate_write of the oracle's state after the same steps
+    (where the two states agree to the 6 digits %g keeps), and the binary checkpoint restores
+    every column bit-exactly."""
+    w, sim, ptrs, idx = setup(kind, ctx)
+    parts = _particles(w, 300)
+    ctx.particles_upload(**parts)
+    par = w.step_params(record_forces=True)
+    plist = ora.ParticleList(sim, *[parts[k] for k in ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")])
+    for _ in range(3):
+        ctx.step(par)
+        plist.step(helpers.oracle_params(w))
+    ctx.write_gfs(tmp_path / "dev.txt", L=1.0)
+    plist.write(tmp_path / "ref.txt", L=1.0)
+    dev, ref = (tmp_path / "dev.txt").read_text().splitlines(), (tmp_path / "ref.txt").read_text().splitlines()
+    assert len(dev) == len(ref) == 300
+    assert dev[0].startswith("    GfsParticulate 1 ") and len(dev[0].split()) == 13
+    same = sum(d == r for d, r in zip(dev, ref))
+    assert same >= 290, same          # a 1e-13 difference flips a printed 6th digit only rarely
+    for d, r in zip(dev, ref):
+        assert np.allclose([float(t) for t in d.split()[1:]], [float(t) for t in r.split()[1:]], rtol=2e-5, atol=1e-300)
+    # L scales the printed volume by L^dim
+    ctx.write_gfs(tmp_path / "dev2.txt", L=2.0)
+    v1 = float(dev[5].split()[6]); v2 = float((tmp_path / "dev2.txt").read_text().splitlines()[5].split()[6])
+    assert abs(v2 / v1 - 2.0 ** w.dim) < 1e-5
+    # lossless restart
+    before = ctx.particles_download(forces=True)
+    ctx.checkpoint_save(tmp_path / "ckpt.bin")
+    ctx.particles_upload(**_particles(w, 10))
+    ctx.checkpoint_load(tmp_path / "ckpt.bin")
+    after = ctx.particles_download(forces=True)
+    assert ctx.count == 300
+    for k in before:
+        if before[k] is not None:
+            assert np.array_equal(before[k], after[k]), k
+    with pytest.raises(capi.GfsB200Error):
+        ctx.checkpoint_load(tmp_path / "dev.txt")
+
+
 def test_empty_and_single_particle(ctx):
     w, sim, ptrs, idx = setup("uniform3", ctx)
     empty = {k: np.zeros(0) for k in ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")}
