@@ -182,12 +182,12 @@ __device__ double center_gradient (const DevTree & T, const double * __restrict_
   return 0.;
 }
 
+/* body of vorticity_kernel for block `bid` of `nblk` (also run by cell_pass_small_kernel) */
 template <int DIM>
-__global__ void __launch_bounds__(256, 8)      /* 32 registers: full occupancy hides the nb -> value chain */
-vorticity_kernel (DevTree T, DevField fld)
+__device__ __forceinline__ void vorticity_body (const DevTree & T, const DevField & fld, int bid, int nblk)
 {
-  const int stride = gridDim.x*blockDim.x;
-  for (int cell = blockIdx.x*blockDim.x + threadIdx.x; cell < T.n_cells; cell += stride) {
+  const int stride = nblk*blockDim.x;
+  for (int cell = bid*blockDim.x + threadIdx.x; cell < T.n_cells; cell += stride) {
     const unsigned info = T.info[cell];
     const bool box_leaf = (info & (GFSB200_CELL_LEAF | GFSB200_CELL_BOUNDARY)) == GFSB200_CELL_LEAF;
     double wx = 0., wy = 0., wz = 0.;
@@ -262,6 +262,13 @@ vorticity_kernel (DevTree T, DevField fld)
       o[1] = make_double2 (wz, 0.);
     }
   }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256, 8)      /* 32 registers: full occupancy hides the nb -> value chain */
+vorticity_kernel (DevTree T, DevField fld)
+{
+  vorticity_body<DIM> (T, fld, blockIdx.x, gridDim.x);
 }
 
 /* The cell-constant part of compute_inertial_force
@@ -377,9 +384,9 @@ __device__ __noinline__ void hull_vertex_3d (const int32_t * __restrict__ vtx_of
  * order.  (The GFS_NODATA early-out returns the *calling* leaf's own value,
  * which a shared vertex cannot represent: a vertex whose stencil touches
  * NODATA is stored as NODATA and resolved by the particle kernel.) */
+/* body of vertex_values_kernel for block `bid` of `nblk` */
 template <int DIM>
-__global__ void __launch_bounds__(256)
-vertex_values_kernel (DevTree T, DevField fld)
+__device__ __forceinline__ void vertex_values_body (const DevTree & T, const DevField & fld, int bid, int nblk)
 {
   /* Lattice trees: vertices are numbered row-major, cells in Morton order.  A
      CTA then takes an 8x8x4 (3D) / 16x16 (2D) brick of vertices instead of 256
@@ -390,8 +397,8 @@ vertex_values_kernel (DevTree T, DevField fld)
   const int tx = n1 > 0 ? (n1 + bx - 1)/bx : 0, ty = n1 > 0 ? (n1 + by - 1)/by : 0,
     tz = DIM == 3 && n1 > 0 ? (n1 + bz - 1)/bz : 1;
   const int64_t n_items = n1 > 0 ? (int64_t) tx*ty*tz*256 : T.n_vertices;
-  const int64_t stride = (int64_t) gridDim.x*blockDim.x;
-  for (int64_t item = (int64_t) blockIdx.x*blockDim.x + threadIdx.x; item < n_items; item += stride) {
+  const int64_t stride = (int64_t) nblk*blockDim.x;
+  for (int64_t item = (int64_t) bid*blockDim.x + threadIdx.x; item < n_items; item += stride) {
     int v = (int) item;
     if (n1 > 0) {
       const int brick = (int) (item >> 8), t = (int) (item & 255);
@@ -463,6 +470,26 @@ vertex_values_kernel (DevTree T, DevField fld)
   }
 }
 
+template <int DIM>
+__global__ void __launch_bounds__(256)
+vertex_values_kernel (DevTree T, DevField fld)
+{
+  vertex_values_body<DIM> (T, fld, blockIdx.x, gridDim.x);
+}
+
+/* Small trees (adaptive configs: 1e5 cells): both tables in ONE launch -- the first gv blocks
+ * take the vertices, the others the cells -- instead of two kernels on two streams with a
+ * fork/join pair of events, whose fixed cost dominates at that size. */
+template <int DIM>
+__global__ void __launch_bounds__(256)
+cell_pass_small_kernel (DevTree T, DevField fld, int gv)
+{
+  if ((int) blockIdx.x < gv)
+    vertex_values_body<DIM> (T, fld, blockIdx.x, gv);
+  else
+    vorticity_body<DIM> (T, fld, blockIdx.x - gv, gridDim.x - gv);
+}
+
 /* ------------------------------------------------------------------ */
 /* Lattice trees (uniform, one GfsBox, no GfsBoundary -- BASELINE config C2):
  * the whole cell pass for the INTERIOR vertices and leaves in one kernel.
@@ -485,6 +512,7 @@ vertex_values_kernel (DevTree T, DevField fld)
  * (3 % of them) go through the stencil tables.  HBM traffic per
  * launch: 24 B per cell read (halo re-reads hit L2) + 32 B per vertex + 32 B
  * per leaf written. */
+#define SMALL_TREE_CELLS 400000   /* below this the cell pass is one merged launch */
 #define BRICK 8
 #define REG (BRICK + 2)
 #define PLANE (REG*REG + 4)      /* plane stride = 8 mod 16 doubles: the (x, z) lanes of a warp hit
@@ -716,6 +744,12 @@ extern "C" void gfsb200_launch_cell_pass (const DevTree * T, const DevField * fl
       lattice_cell_pass_kernel<REFERENCE_PATTERN><<<nb*nb*nb, 256, 0, stream>>> (*T, *fld);
     else
       lattice_cell_pass_kernel<-1><<<nb*nb*nb, 256, 0, stream>>> (*T, *fld);
+    return;
+  }
+  if (T->n_cells <= SMALL_TREE_CELLS) {
+    gfsb200_launch_counter += 1;
+    if (T->dim == 2) cell_pass_small_kernel<2><<<gv + gc, threads, 0, stream>>> (*T, *fld, gv);
+    else cell_pass_small_kernel<3><<<gv + gc, threads, 0, stream>>> (*T, *fld, gv);
     return;
   }
   gfsb200_launch_counter += 2;
