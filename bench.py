@@ -388,6 +388,7 @@ def run_b200(args):
                        "l2": "per-step particle stream (%.0f MB) exceeds the 126 MB L2" % (n_local * bps / 1e6)},
             "roofline": {"bound": "hbm", "kernel": "step_kernel_pipe<%d,...> (TMA-staged fused locate+interpolate+force+integrate)" % world.dim,
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "frac_of_8TBs_spec": achieved / 8000.0,
                          "traffic": measured_traffic(args.config, n_local, world.dim), "peak_source": peak_src,
                          "algorithmic_bytes_per_particle_step": bps,
                          "kernel_ms": kernel_ms, "kernel_launches": kernel_launches},
