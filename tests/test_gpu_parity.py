@@ -507,6 +507,39 @@ def test_particle_text_format_and_checkpoint(kind, ctx, tmp_path):
         ctx.checkpoint_load(tmp_path / "dev.txt")
 
 
+@pytest.mark.parametrize("level", [5, 6])
+def test_lattice_cell_pass_equals_table_driven_kernels(level, ctx, monkeypatch):
+    """lattice_cell_pass_kernel (brick-tiled, arithmetic addressing, shared-memory staging) gives
+    bit-identical vertex and vorticity tables to the table-driven kernels on every leaf and
+    corner of a 32^3 / 64^3 tree -- interior and hull -- also with GFS_NODATA cells present."""
+    w = worlds.make_c2(level=level, n_particles=10)
+    a = w.arrays
+    leaves = a.box_leaves
+    rng = np.random.default_rng(level)
+    u, v, wz = w.u.copy(), w.v.copy(), 0.3 * w.u + 0.1 * rng.standard_normal(a.n_cells)
+    for nodata in (False, True):
+        if nodata:                               # a few NODATA cells, inside and on the hull
+            bad = rng.choice(leaves, 40, replace=False)
+            u[bad[:20]] = 1.7976931348623157e308
+            wz[bad[20:]] = 1.7976931348623157e308
+        tables = []
+        for env in ("", "1"):
+            if env:
+                monkeypatch.setenv("GFSB200_NO_LATTICE_PATTERN", env)
+            else:
+                monkeypatch.delenv("GFSB200_NO_LATTICE_PATTERN", raising=False)
+            ctx.upload_tree(w.tree)
+            ctx.upload_field(u, v, wz)
+            tables.append((ctx.vorticity(leaves), [ctx.corner_values(c, leaves) for c in range(3)]))
+        monkeypatch.delenv("GFSB200_NO_LATTICE_PATTERN", raising=False)
+        (vort_f, corner_f), (vort_t, corner_t) = tables
+        if not nodata:                           # (NODATA poisons the differences: compare bit patterns)
+            assert np.array_equal(vort_f, vort_t)
+        assert np.array_equal(vort_f.view(np.uint64), vort_t.view(np.uint64))
+        for c in range(3):
+            assert np.array_equal(corner_f[c].view(np.uint64), corner_t[c].view(np.uint64)), c
+
+
 def test_empty_and_single_particle(ctx):
     w, sim, ptrs, idx = setup("uniform3", ctx)
     empty = {k: np.zeros(0) for k in ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")}
