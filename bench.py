@@ -196,9 +196,11 @@ def run_reference(args):
     threads = ora.load(3).ora_max_threads()
     sp, sim = oracle_world(ora, worlds, args.config)
     mk = oracle_params_factory(ora)
-    # size the per-step sample so that one step takes about a second
+    # size the per-step sample so that one step takes about a second and the whole run
+    # (steps + warmup) about a minute and a half at most
     rate, _ = time_oracle(ora, worlds, mk, sp, sim, 20_000, 1, 1, threads)
-    n_sample = int(min(sp.n_particles, max(20_000, rate * 1.0)))
+    per_step_s = min(1.0, 90.0 / max(args.steps + args.warmup, 1))
+    n_sample = int(min(sp.n_particles, max(20_000, rate * per_step_s)))
     value, dt = time_oracle(ora, worlds, mk, sp, sim, n_sample, args.steps, args.warmup, threads)
     line = {
         "impl": "reference", "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s",
