@@ -72,6 +72,7 @@ def load(dim: int) -> C.CDLL:
         "ora_match_boundaries": (None, [vp]), "ora_finalize": (None, [vp]),
         "ora_locate_array": (None, [vp, vp, vp, vp]),
         "ora_locate": (None, [vp, lng, vp, vp, vp, vp]),
+        "ora_locate_one": (vp, [vp, dbl, dbl, dbl, i32]),
         "ora_cell_info": (None, [u64, vp, vp, vp, vp]),
         "ora_set_values": (None, [vp, i32, lng, vp, vp]), "ora_get_values": (None, [vp, i32, lng, vp, vp]),
         "ora_neighbor": (u64, [u64, i32]), "ora_count": (lng, [vp, i32]),
@@ -286,3 +287,150 @@ class ParticleList:
     def write(self, path, L=1.0):
         """the particle block as the reference writes it into a .gfs / dump file"""
         assert self.sim.L.ora_list_write(self.h, str(path).encode(), L) == 0
+
+
+# ---------------------------------------------------------------------------
+# libgfsrefobj: the reference's particulate layer itself as object code
+# (modules/particulatecommon.c + src/event.c + src/particle.c + src/fluid.c +
+# src/ftt.c compiled unmodified; run-time in oracle/refobj/glue.c).  It runs on
+# the trees of a Sim above, shared by pointer.
+
+_reflibs = {}
+_LOCATE_T = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int)
+
+
+def refobj_available(dim: int) -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", f"libgfsrefobj{dim}D.so"))
+
+
+def load_refobj(dim: int) -> C.CDLL:
+    if dim in _reflibs:
+        return _reflibs[dim]
+    R = C.CDLL(os.path.join(_HERE, "_ref", f"libgfsrefobj{dim}D.so"))
+    vp, dbl, lng, i32 = C.c_void_p, C.c_double, C.c_long, C.c_int
+    sig = {
+        "refobj_dimension": (i32, []),
+        "refobj_sim_new": (vp, [i32, vp, vp, C.c_uint, vp, vp, vp, i32]),
+        "refobj_sim_configure": (None, [vp, C.POINTER(StepParams), i32]),
+        "refobj_sim_destroy": (None, [vp]),
+        "refobj_sim_time": (None, [vp, C.POINTER(dbl), C.POINTER(i32)]),
+        "refobj_list_new": (vp, [vp, lng] + [vp] * 8 + [C.POINTER(StepParams)]),
+        "refobj_list_destroy": (None, [vp]),
+        "refobj_list_size": (lng, [vp]),
+        "refobj_list_get": (None, [vp] * 12),
+        "refobj_list_event": (i32, [vp, vp, i32]),
+        "refobj_list_outside": (lng, [vp, vp]),
+        "refobj_force": (None, [vp, lng, i32, vp]),
+        "refobj_list_bc": (None, [vp]),
+        "refobj_list_write": (i32, [vp, C.c_char_p]),
+        "refobj_field_event": (None, [vp, vp, i32]),
+        "refobj_source_event": (None, [vp, vp, i32, dbl, C.POINTER(Kernel)]),
+        "refobj_warnings": (lng, []),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(R, name)
+        f.restype, f.argtypes = res, args
+    assert R.refobj_dimension() == dim
+    _reflibs[dim] = R
+    return R
+
+
+class RefSim:
+    """A GfsSimulation of the reference's own structs around the GfsBox /
+    GfsBoundary trees of `sim`; gfs_domain_locate goes through sim's
+    GfsLocateArray.  Bit d of periodic_mask: the boundaries on side d are
+    GfsBoundaryPeriodic."""
+
+    def __init__(self, sim: Sim, periodic_mask: int = 0):
+        self.sim, self.dim = sim, sim.dim
+        self.R = load_refobj(sim.dim)
+        nb = sim.L.ora_nbox(sim.h)
+        nn = 2 * sim.dim
+        roots = (C.c_void_p * nb)(*[sim.L.ora_box_root(sim.h, b) for b in range(nb)])
+        broots = (C.c_void_p * (nb * nn))()
+        for b, s in sim.sides:
+            broots[b * nn + s] = sim.L.ora_box_boundary_root(sim.h, b, s)
+        locate = C.cast(sim.L.ora_locate_one, C.c_void_p)
+        self.h = C.c_void_p(self.R.refobj_sim_new(nb, roots, broots, periodic_mask, locate, None,
+                                                  sim.h, sim.nvar))
+        self._lists = []
+
+    def configure(self, params: StepParams, timers=True):
+        """PhysicalParams alpha, SourceViscosity, Source g, dt -- what the .gfs
+        file declares around the list"""
+        self.R.refobj_sim_configure(self.h, C.byref(params), int(timers))
+
+    def time(self):
+        t, i = C.c_double(), C.c_int()
+        self.R.refobj_sim_time(self.h, C.byref(t), C.byref(i))
+        return t.value, i.value
+
+    def close(self):
+        for l in list(self._lists):
+            l.close()
+        if self.h:
+            self.R.refobj_sim_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class RefParticleList:
+    """A GfsParticleList of GfsParticulate objects with its GfsForce* list, as
+    gfs_particle_list_read leaves it; ids are 1..n in list order."""
+
+    def __init__(self, rsim: RefSim, x, y, z, vx, vy, vz, mass, volume, params: StepParams):
+        self.rsim, self.R = rsim, rsim.R
+        a = [_f64(v) for v in (x, y, z, vx, vy, vz, mass, volume)]
+        self.h = C.c_void_p(self.R.refobj_list_new(rsim.h, len(a[0]), *[_p(v) for v in a], C.byref(params)))
+        rsim._lists.append(self)
+
+    def close(self):
+        if self.h:
+            self.R.refobj_list_destroy(self.h)
+            self.h = None
+            self.rsim._lists.remove(self)
+
+    def __len__(self):
+        return self.R.refobj_list_size(self.h)
+
+    def event(self, steps=1):
+        """gfs_event_do on the list `steps` times (cull, GfsParticulate events,
+        gfs_particle_bc, Un snapshot), the time level advancing in between"""
+        return self.R.refobj_list_event(self.rsim.h, self.h, steps)
+
+    def outside(self):
+        return self.R.refobj_list_outside(self.rsim.h, self.h)
+
+    def bc(self):
+        self.R.refobj_list_bc(self.h)
+
+    def force(self, index, k):
+        """force model k of the list on particle `index`, per unit volume"""
+        f = np.zeros(3)
+        self.R.refobj_force(self.h, index, k, _p(f))
+        return f
+
+    def get(self):
+        n = len(self)
+        out = {k: np.empty(n) for k in ("x", "y", "z", "vx", "vy", "vz", "fx", "fy", "fz", "mass")}
+        ids = np.empty(n, dtype=np.uint32)
+        self.R.refobj_list_get(self.h, *[_p(out[k]) for k in ("x", "y", "z", "vx", "vy", "vz", "fx", "fy",
+                                                               "fz", "mass")], _p(ids))
+        out["id"] = ids
+        return out
+
+    def field_event(self, ivar):
+        """GfsParticulateField: reset + V_p/V_cell scatter into variable ivar"""
+        self.R.refobj_field_event(self.rsim.h, self.h, ivar)
+
+    def source_event(self, ivar0, rkernel, kernel: Kernel):
+        """GfsSourceParticulate: kernel-smoothed -F/rho/V_cell into ivar0.."""
+        self.R.refobj_source_event(self.rsim.h, self.h, ivar0, rkernel, C.byref(kernel))
+
+    def write(self, path):
+        assert self.R.refobj_list_write(self.h, str(path).encode()) == 0

@@ -467,6 +467,14 @@ void ora_locate (OraSim * sim, long n, const double * x, const double * y, const
   }
 }
 
+/* single-point entry: the gfs_domain_locate that libgfsrefobj (the reference's
+ * particulate object code, oracle/refobj/glue.c) calls back into */
+FttCell * ora_locate_one (OraSim * sim, double x, double y, double z, int max_depth)
+{
+  FttVector p = { x, y, z, 0. };
+  return domain_locate (sim, p, max_depth);
+}
+
 /* ------------------------------------------------------------------ */
 /* cell access helpers for the tests                                    */
 

@@ -1,0 +1,1318 @@
+/* TEST INFRASTRUCTURE ONLY (oracle) -- never linked into, imported by or
+ * executed from the product path.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load this.
+ *
+ * libgfsrefobj{2D,3D}.so = the REFERENCE'S OWN OBJECT CODE for the whole
+ * particulate layer, not a restatement of it:
+ *
+ *   modules/particulatecommon.c   GfsParticulate, GfsParticleList, GfsForce*,
+ *                                 GfsParticulateField, GfsSourceParticulate,
+ *                                 gfs_particle_bc  (every function of SURVEY 8a)
+ *   src/event.c                   GfsEvent gating, gfs_event_do, GfsEventList
+ *   src/particle.c                GfsParticle (passive tracer event, %g writer)
+ *   src/fluid.c, src/ftt.c        gfs_interpolate, gfs_center_gradient, trees
+ *
+ * are compiled UNMODIFIED from where they lie under /root/reference
+ * (oracle/Makefile), against the reference's own headers and the
+ * declaration-level GLib/GTS stand-in of gerris-fft-particles_b200/host/check.
+ * This file is the run-time those objects need and the reference tree does not
+ * contain: GLib and GTS are third-party dependencies absent from this image
+ * (GTS 0.7.6, GLib 2.x: configure.ac:162-200), so the handful of their
+ * functions the path calls are restated from their published behaviour
+ * (object.c / container.c of GTS 0.7.6, gslist.c of GLib), and the few Gerris
+ * functions that live in files which do not compile here (src/domain.c needs
+ * config.h, src/variable.c and src/source.c need MPI/GtsFifo) are restated with
+ * their file:line.  Everything the path does NOT call resolves to an aborting
+ * stub (mkstubs.sh), so a call that strays off the restated set fails loudly.
+ *
+ * The FttCell trees, their cell data and the GfsLocateArray come from
+ * libgfsoracle (oracle/particulate_port.c: trees built by the reference's
+ * ftt.c object code); they are shared by pointer -- FttCell and GfsStateVector
+ * have the same layout in both libraries because both use the reference's
+ * ftt.h / fluid.h.
+ */
+#include <gts.h>
+#include <sys/times.h>
+#include <unistd.h>
+#include "simulation.h"
+#include "event.h"
+#include "particle.h"
+#include "source.h"
+#include "boundary.h"
+#include "particulatecommon.h"
+
+#define REF_EXPORT __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------ */
+/* GLib (restated: gmem.c, gslist.c, garray.c, gmessages.c)            */
+
+gpointer g_malloc (gsize n)
+{
+  gpointer p;
+  if (n == 0) return NULL;
+  p = malloc (n);
+  if (!p) abort ();
+  return p;
+}
+
+gpointer g_malloc0 (gsize n)
+{
+  gpointer p;
+  if (n == 0) return NULL;
+  p = calloc (1, n);
+  if (!p) abort ();
+  return p;
+}
+
+gpointer g_realloc (gpointer p, gsize n)
+{
+  if (n == 0) { free (p); return NULL; }
+  p = realloc (p, n);
+  if (!p) abort ();
+  return p;
+}
+
+void g_free (gpointer p) { free (p); }
+
+gchar * g_strdup (const gchar * s)
+{
+  gchar * d;
+  if (!s) return NULL;
+  d = g_malloc (strlen (s) + 1);
+  strcpy (d, s);
+  return d;
+}
+
+gchar * g_strconcat (const gchar * s, ...)
+{
+  va_list ap;
+  gsize len;
+  const gchar * t;
+  gchar * d;
+  if (!s) return NULL;
+  len = strlen (s) + 1;
+  va_start (ap, s);
+  while ((t = va_arg (ap, const gchar *))) len += strlen (t);
+  va_end (ap);
+  d = g_malloc (len);
+  strcpy (d, s);
+  va_start (ap, s);
+  while ((t = va_arg (ap, const gchar *))) strcat (d, t);
+  va_end (ap);
+  return d;
+}
+
+gchar * g_strdup_printf (const gchar * format, ...)
+{
+  va_list ap;
+  gchar * d = NULL;
+  va_start (ap, format);
+  if (vasprintf (&d, format, ap) < 0) abort ();
+  va_end (ap);
+  return d;
+}
+
+const gchar * g_getenv (const gchar * variable) { return getenv (variable); }
+
+static long ref_warnings = 0;
+
+void g_log (const gchar * domain, GLogLevelFlags level, const gchar * format, ...)
+{
+  va_list ap;
+  if (level & G_LOG_LEVEL_WARNING) {
+    /* g_warning: log and continue (the added-mass/lift code warns per call) */
+    if (ref_warnings++ > 8) return;
+  }
+  va_start (ap, format);
+  fputs ("refobj: ", stderr);
+  vfprintf (stderr, format, ap);
+  fputc ('\n', stderr);
+  va_end (ap);
+  if (level & G_LOG_LEVEL_ERROR)
+    abort ();
+}
+
+void g_assertion_message_expr (const char * domain, const char * file, int line, const char * func,
+			       const char * expr)
+{
+  fprintf (stderr, "refobj: %s:%d (%s): assertion failed: (%s)\n", file, line, func, expr ? expr : "not reached");
+  abort ();
+}
+
+GSList * g_slist_prepend (GSList * l, gpointer data)
+{
+  GSList * n = g_malloc (sizeof (GSList));
+  n->data = data;
+  n->next = l;
+  return n;
+}
+
+GSList * g_slist_append (GSList * l, gpointer data)
+{
+  GSList * n = g_malloc (sizeof (GSList)), * i = l;
+  n->data = data;
+  n->next = NULL;
+  if (!l) return n;
+  while (i->next) i = i->next;
+  i->next = n;
+  return l;
+}
+
+GSList * g_slist_remove (GSList * l, gconstpointer data)
+{
+  GSList ** pp = &l;
+  while (*pp) {
+    if ((*pp)->data == data) {
+      GSList * dead = *pp;
+      *pp = dead->next;
+      free (dead);
+      break;
+    }
+    pp = &(*pp)->next;
+  }
+  return l;
+}
+
+GSList * g_slist_find (GSList * l, gconstpointer data)
+{
+  while (l && l->data != data) l = l->next;
+  return l;
+}
+
+GSList * g_slist_reverse (GSList * l)
+{
+  GSList * prev = NULL;
+  while (l) {
+    GSList * next = l->next;
+    l->next = prev;
+    prev = l;
+    l = next;
+  }
+  return prev;
+}
+
+void g_slist_free (GSList * l)
+{
+  while (l) {
+    GSList * next = l->next;
+    free (l);
+    l = next;
+  }
+}
+
+guint g_slist_length (GSList * l)
+{
+  guint n = 0;
+  while (l) { n++; l = l->next; }
+  return n;
+}
+
+typedef struct { GArray a; guint elt, alloc; } RealArray;
+
+GArray * g_array_new (gboolean zero_terminated, gboolean clear, guint element_size)
+{
+  RealArray * a = g_malloc0 (sizeof (RealArray));
+  a->elt = element_size;
+  return &a->a;
+}
+
+GArray * g_array_append_vals (GArray * array, gconstpointer data, guint len)
+{
+  RealArray * a = (RealArray *) array;
+  if (array->len + len > a->alloc) {
+    a->alloc = MAX (2*a->alloc, array->len + len + 16);
+    array->data = g_realloc (array->data, (gsize) a->alloc*a->elt);
+  }
+  memcpy (array->data + (gsize) array->len*a->elt, data, (gsize) len*a->elt);
+  array->len += len;
+  return array;
+}
+
+gchar * g_array_free (GArray * array, gboolean free_segment)
+{
+  gchar * d = array->data;
+  if (free_segment) { free (d); d = NULL; }
+  free (array);
+  return d;
+}
+
+typedef struct { GPtrArray a; guint alloc; } RealPtrArray;
+
+GPtrArray * g_ptr_array_new (void) { return g_malloc0 (sizeof (RealPtrArray)); }
+
+void g_ptr_array_add (GPtrArray * array, gpointer p)
+{
+  RealPtrArray * a = (RealPtrArray *) array;
+  if (array->len + 1 > a->alloc) {
+    a->alloc = MAX (2*a->alloc, 16);
+    array->pdata = g_realloc (array->pdata, sizeof (gpointer)*a->alloc);
+  }
+  array->pdata[array->len++] = p;
+}
+
+gpointer * g_ptr_array_free (GPtrArray * array, gboolean free_seg)
+{
+  gpointer * d = array->pdata;
+  if (free_seg) { free (d); d = NULL; }
+  free (array);
+  return d;
+}
+
+/* ------------------------------------------------------------------ */
+/* GTS 0.7.6 object system (restated: src/object.c)                     */
+
+static void object_destroy (GtsObject * object)
+{
+  object->klass = NULL;
+  g_free (object);
+}
+
+static void object_class_init (GtsObjectClass * klass)
+{
+  klass->clone = NULL;
+  klass->destroy = object_destroy;
+  klass->read = NULL;
+  klass->write = NULL;
+  klass->color = NULL;
+  klass->attributes = NULL;
+}
+
+static void object_init (GtsObject * object)
+{
+  object->reserved = NULL;
+  object->flags = 0;
+}
+
+/* ancestors' class_init first, the class's own last (object.c: gts_object_class_init) */
+static void run_class_init (GtsObjectClass * klass, GtsObjectClass * parent_class)
+{
+  if (parent_class) {
+    run_class_init (klass, parent_class->parent_class);
+    if (parent_class->info.class_init_func)
+      (* parent_class->info.class_init_func) (klass);
+  }
+}
+
+gpointer gts_object_class_new (GtsObjectClass * parent_class, GtsObjectClassInfo * info)
+{
+  GtsObjectClass * klass;
+
+  g_assert (info != NULL);
+  g_assert (parent_class == NULL || info->object_size >= parent_class->info.object_size);
+  g_assert (parent_class == NULL || info->class_size >= parent_class->info.class_size);
+  klass = g_malloc0 (info->class_size);
+  klass->info = *info;
+  klass->parent_class = parent_class;
+  run_class_init (klass, klass);
+  return klass;
+}
+
+gpointer gts_object_class (void)
+{
+  static GtsObjectClass * klass = NULL;
+  if (klass == NULL) {
+    GtsObjectClassInfo info = {
+      "GtsObject", sizeof (GtsObject), sizeof (GtsObjectClass),
+      (GtsObjectClassInitFunc) object_class_init, (GtsObjectInitFunc) object_init, NULL, NULL
+    };
+    klass = gts_object_class_new (NULL, &info);
+  }
+  return klass;
+}
+
+static void run_object_init (GtsObject * object, GtsObjectClass * klass)
+{
+  if (klass) {
+    run_object_init (object, klass->parent_class);
+    if (klass->info.object_init_func)
+      (* klass->info.object_init_func) (object);
+  }
+}
+
+GtsObject * gts_object_new (GtsObjectClass * klass)
+{
+  GtsObject * object;
+  g_assert (klass != NULL);
+  object = g_malloc0 (klass->info.object_size);
+  object->klass = klass;
+  run_object_init (object, klass);
+  return object;
+}
+
+void gts_object_destroy (GtsObject * object)
+{
+  g_assert (object != NULL && object->klass->destroy);
+  (* object->klass->destroy) (object);
+}
+
+gpointer gts_object_class_is_from_class (gpointer klass, gpointer from)
+{
+  GtsObjectClass * c = klass;
+  while (c) {
+    if (c == from) return klass;
+    c = c->parent_class;
+  }
+  return NULL;
+}
+
+gpointer gts_object_is_from_class (gpointer object, gpointer klass)
+{
+  if (object == NULL || klass == NULL) return NULL;
+  return gts_object_class_is_from_class (((GtsObject *) object)->klass, klass) ? object : NULL;
+}
+
+/* GTS 0.7.6 containers (restated: src/container.c) */
+
+GtsContaineeClass * gts_containee_class (void)
+{
+  static GtsContaineeClass * klass = NULL;
+  if (klass == NULL) {
+    GtsObjectClassInfo info = {
+      "GtsContainee", sizeof (GtsContainee), sizeof (GtsContaineeClass), NULL, NULL, NULL, NULL
+    };
+    klass = gts_object_class_new (gts_object_class (), &info);
+  }
+  return klass;
+}
+
+static void slist_containee_destroy (GtsObject * object)
+{
+  GtsSListContainee * item = (GtsSListContainee *) object;
+  GSList * i = item->containers;
+  while (i) {
+    GSList * next = i->next;
+    gts_container_remove (i->data, GTS_CONTAINEE (item));
+    i = next;
+  }
+  g_assert (item->containers == NULL);
+  (* GTS_OBJECT_CLASS (gts_slist_containee_class ())->parent_class->destroy) (object);
+}
+
+static void slist_containee_add_container (GtsContainee * i, gpointer c)
+{
+  GtsSListContainee * item = (GtsSListContainee *) i;
+  if (!g_slist_find (item->containers, c))
+    item->containers = g_slist_prepend (item->containers, c);
+}
+
+static void slist_containee_remove_container (GtsContainee * i, gpointer c)
+{
+  GtsSListContainee * item = (GtsSListContainee *) i;
+  item->containers = g_slist_remove (item->containers, c);
+}
+
+static gboolean slist_containee_is_contained (GtsContainee * i, gpointer c)
+{
+  return g_slist_find (((GtsSListContainee *) i)->containers, c) != NULL;
+}
+
+static void slist_containee_class_init (GtsContaineeClass * klass)
+{
+  klass->add_container = slist_containee_add_container;
+  klass->remove_container = slist_containee_remove_container;
+  klass->is_contained = slist_containee_is_contained;
+  GTS_OBJECT_CLASS (klass)->destroy = slist_containee_destroy;
+}
+
+GtsSListContaineeClass * gts_slist_containee_class (void)
+{
+  static GtsSListContaineeClass * klass = NULL;
+  if (klass == NULL) {
+    GtsObjectClassInfo info = {
+      "GtsSListContainee", sizeof (GtsSListContainee), sizeof (GtsSListContaineeClass),
+      (GtsObjectClassInitFunc) slist_containee_class_init, NULL, NULL, NULL
+    };
+    klass = gts_object_class_new (GTS_OBJECT_CLASS (gts_containee_class ()), &info);
+  }
+  return klass;
+}
+
+static void container_add (GtsContainer * c, GtsContainee * item)
+{
+  if (GTS_CONTAINEE_CLASS (GTS_OBJECT (item)->klass)->add_container)
+    (* GTS_CONTAINEE_CLASS (GTS_OBJECT (item)->klass)->add_container) (item, c);
+}
+
+static void container_remove (GtsContainer * c, GtsContainee * item)
+{
+  if (GTS_CONTAINEE_CLASS (GTS_OBJECT (item)->klass)->remove_container)
+    (* GTS_CONTAINEE_CLASS (GTS_OBJECT (item)->klass)->remove_container) (item, c);
+}
+
+static void container_class_init (GtsContainerClass * klass)
+{
+  klass->add = container_add;
+  klass->remove = container_remove;
+  klass->foreach = NULL;
+  klass->size = NULL;
+}
+
+GtsContainerClass * gts_container_class (void)
+{
+  static GtsContainerClass * klass = NULL;
+  if (klass == NULL) {
+    GtsObjectClassInfo info = {
+      "GtsContainer", sizeof (GtsContainer), sizeof (GtsContainerClass),
+      (GtsObjectClassInitFunc) container_class_init, NULL, NULL, NULL
+    };
+    klass = gts_object_class_new (GTS_OBJECT_CLASS (gts_slist_containee_class ()), &info);
+  }
+  return klass;
+}
+
+GtsContainer * gts_container_new (GtsContainerClass * klass)
+{
+  return GTS_CONTAINER (gts_object_new (GTS_OBJECT_CLASS (klass)));
+}
+
+void gts_container_add (GtsContainer * c, GtsContainee * item)
+{
+  g_assert (c != NULL && item != NULL);
+  g_assert (GTS_CONTAINER_CLASS (GTS_OBJECT (c)->klass)->add);
+  (* GTS_CONTAINER_CLASS (GTS_OBJECT (c)->klass)->add) (c, item);
+}
+
+void gts_container_remove (GtsContainer * c, GtsContainee * item)
+{
+  g_assert (c != NULL && item != NULL);
+  g_assert (GTS_CONTAINER_CLASS (GTS_OBJECT (c)->klass)->remove);
+  (* GTS_CONTAINER_CLASS (GTS_OBJECT (c)->klass)->remove) (c, item);
+}
+
+void gts_container_foreach (GtsContainer * c, GtsFunc func, gpointer data)
+{
+  g_assert (c != NULL && func != NULL);
+  if (GTS_CONTAINER_CLASS (GTS_OBJECT (c)->klass)->foreach)
+    (* GTS_CONTAINER_CLASS (GTS_OBJECT (c)->klass)->foreach) (c, func, data);
+}
+
+guint gts_container_size (GtsContainer * c)
+{
+  g_assert (c != NULL);
+  return GTS_CONTAINER_CLASS (GTS_OBJECT (c)->klass)->size ?
+    (* GTS_CONTAINER_CLASS (GTS_OBJECT (c)->klass)->size) (c) : 0;
+}
+
+/* GtsSListContainer: add PREPENDS (container.c: slist_container_add); foreach
+   keeps the next link so that the callback may remove the current item */
+static void slist_container_add (GtsContainer * c, GtsContainee * item)
+{
+  GtsSListContainer * s = GTS_SLIST_CONTAINER (c);
+  g_return_if_fail (s->frozen == FALSE);
+  if (!g_slist_find (s->items, item)) {
+    s->items = g_slist_prepend (s->items, item);
+    (* GTS_CONTAINER_CLASS (GTS_OBJECT_CLASS (gts_slist_container_class ())->parent_class)->add) (c, item);
+  }
+}
+
+static void slist_container_remove (GtsContainer * c, GtsContainee * item)
+{
+  GtsSListContainer * s = GTS_SLIST_CONTAINER (c);
+  g_return_if_fail (s->frozen == FALSE);
+  if (g_slist_find (s->items, item)) {
+    s->items = g_slist_remove (s->items, item);
+    (* GTS_CONTAINER_CLASS (GTS_OBJECT_CLASS (gts_slist_container_class ())->parent_class)->remove) (c, item);
+  }
+}
+
+static void slist_container_foreach (GtsContainer * c, GtsFunc func, gpointer data)
+{
+  GSList * i = GTS_SLIST_CONTAINER (c)->items;
+  while (i) {
+    GSList * next = i->next;
+    (* func) (i->data, data);
+    i = next;
+  }
+}
+
+static guint slist_container_size (GtsContainer * c)
+{
+  return g_slist_length (GTS_SLIST_CONTAINER (c)->items);
+}
+
+static void slist_container_destroy (GtsObject * object)
+{
+  GtsSListContainer * s = (GtsSListContainer *) object;
+  GSList * i = s->items;
+  while (i) {
+    GSList * next = i->next;
+    container_remove (GTS_CONTAINER (s), i->data);
+    i = next;
+  }
+  g_slist_free (s->items);
+  s->items = NULL;
+  (* GTS_OBJECT_CLASS (gts_slist_container_class ())->parent_class->destroy) (object);
+}
+
+static void slist_container_class_init (GtsContainerClass * klass)
+{
+  klass->add = slist_container_add;
+  klass->remove = slist_container_remove;
+  klass->foreach = slist_container_foreach;
+  klass->size = slist_container_size;
+  GTS_OBJECT_CLASS (klass)->destroy = slist_container_destroy;
+}
+
+GtsSListContainerClass * gts_slist_container_class (void)
+{
+  static GtsSListContainerClass * klass = NULL;
+  if (klass == NULL) {
+    GtsObjectClassInfo info = {
+      "GtsSListContainer", sizeof (GtsSListContainer), sizeof (GtsSListContainerClass),
+      (GtsObjectClassInitFunc) slist_container_class_init, NULL, NULL, NULL
+    };
+    klass = gts_object_class_new (GTS_OBJECT_CLASS (gts_container_class ()), &info);
+  }
+  return klass;
+}
+
+/* ------------------------------------------------------------------ */
+/* Gerris classes whose source files do not compile here: only the class
+ * objects (name, sizes, parent) -- the path uses them for GFS_IS_*() tests
+ * and inherited GfsEvent methods                                        */
+
+#define SIMPLE_CLASS(func, ctype, cname, otype, parent)			\
+  ctype * func (void)							\
+  {									\
+    static ctype * klass = NULL;					\
+    if (klass == NULL) {						\
+      GtsObjectClassInfo info = { cname, sizeof (otype), sizeof (ctype), NULL, NULL, NULL, NULL }; \
+      klass = gts_object_class_new (GTS_OBJECT_CLASS (parent), &info);	\
+    }									\
+    return klass;							\
+  }
+
+/* src/utils.c: GfsFunction is opaque to the path; here a constant, a cell
+   variable, or a C function of (x,y,z) -- what a .gfs expression compiles to */
+struct _GfsFunction {
+  GtsObject parent;
+  gdouble val;
+  GfsVariable * v;
+  gdouble (* spatial) (gdouble x, gdouble y, gdouble z, gpointer data);
+  gpointer data;
+};
+
+SIMPLE_CLASS (gfs_function_class, GfsFunctionClass, "GfsFunction", struct _GfsFunction, gts_object_class ())
+SIMPLE_CLASS (gfs_function_spatial_class, GfsFunctionClass, "GfsFunctionSpatial", struct _GfsFunction,
+	      gfs_function_class ())
+
+/* src/utils.c:1231-1259 for the constant and the variable case, L = 1 */
+gdouble gfs_function_value (GfsFunction * f, FttCell * cell)
+{
+  g_return_val_if_fail (f != NULL, 0.);
+  return f->v ? GFS_VALUE (cell, f->v) : f->val;
+}
+
+/* src/utils.c:1476-1494 */
+gdouble gfs_function_spatial_value (GfsFunction * f, const FttVector * p)
+{
+  g_return_val_if_fail (f != NULL, 0.);
+  g_return_val_if_fail (p != NULL, 0.);
+  return f->spatial ? (* f->spatial) (p->x, p->y, p->z, f->data) : f->val;
+}
+
+gdouble gfs_function_get_constant_value (GfsFunction * f)
+{
+  return f->v || f->spatial ? G_MAXDOUBLE : f->val;
+}
+
+GfsFunction * gfs_function_new (GfsFunctionClass * klass, gdouble val)
+{
+  GfsFunction * f = (GfsFunction *) gts_object_new (GTS_OBJECT_CLASS (klass));
+  f->val = val;
+  return f;
+}
+
+/* src/variable.c:104-138 (class), :111-118 (init) */
+static void ref_variable_init (GfsVariable * v)
+{
+  GFS_EVENT (v)->istep = 1;
+  v->centered = FALSE;
+  v->component = FTT_DIMENSION;
+}
+
+GfsVariableClass * gfs_variable_class (void)
+{
+  static GfsVariableClass * klass = NULL;
+  if (klass == NULL) {
+    GtsObjectClassInfo info = {
+      "GfsVariable", sizeof (GfsVariable), sizeof (GfsVariableClass),
+      NULL, (GtsObjectInitFunc) ref_variable_init, NULL, NULL
+    };
+    klass = gts_object_class_new (GTS_OBJECT_CLASS (gfs_event_class ()), &info);
+  }
+  return klass;
+}
+
+/* src/variable.c:183-191 */
+GfsVariable * gfs_variable_from_name (GSList * i, const gchar * name)
+{
+  g_return_val_if_fail (name != NULL, NULL);
+  while (i && (!GFS_VARIABLE (i->data)->name || strcmp (name, GFS_VARIABLE (i->data)->name)))
+    i = i->next;
+  return i ? GFS_VARIABLE (i->data) : NULL;
+}
+
+/* src/source.c: class skeletons */
+SIMPLE_CLASS (gfs_source_generic_class, GfsSourceGenericClass, "GfsSourceGeneric", GfsSourceGeneric,
+	      gfs_event_class ())
+SIMPLE_CLASS (gfs_source_scalar_class, GfsSourceGenericClass, "GfsSourceScalar", GfsSourceScalar,
+	      gfs_source_generic_class ())
+SIMPLE_CLASS (gfs_source_velocity_class, GfsSourceGenericClass, "GfsSourceVelocity", GfsSourceVelocity,
+	      gfs_source_generic_class ())
+SIMPLE_CLASS (gfs_source_class, GfsSourceGenericClass, "GfsSource", GfsSource, gfs_source_scalar_class ())
+SIMPLE_CLASS (gfs_source_diffusion_class, GfsSourceGenericClass, "GfsSourceDiffusion", GfsSourceDiffusion,
+	      gfs_source_scalar_class ())
+SIMPLE_CLASS (gfs_diffusion_class, GfsDiffusionClass, "GfsDiffusion", GfsDiffusion, gfs_event_class ())
+
+/* src/source.c:941-946 (diffusion_cell) and :1002-1005 */
+static gdouble ref_diffusion_cell (GfsDiffusion * d, FttCell * cell)
+{
+  gdouble val;
+  if (d->mu) return GFS_VALUE (cell, d->mu);
+  val = gfs_function_get_constant_value (d->val);
+  return val < G_MAXDOUBLE ? val : 0.;
+}
+
+gdouble gfs_diffusion_cell (GfsDiffusion * d, FttCell * cell)
+{
+  return (* d->cell) (d, cell);
+}
+
+/* src/boundary.c: class skeletons */
+SIMPLE_CLASS (gfs_box_class, GfsBoxClass, "GfsBox", GfsBox, gts_slist_container_class ())
+SIMPLE_CLASS (gfs_boundary_class, GfsBoundaryClass, "GfsBoundary", GfsBoundary, gts_object_class ())
+SIMPLE_CLASS (gfs_boundary_periodic_class, GfsBoundaryClass, "GfsBoundaryPeriodic", GfsBoundaryPeriodic,
+	      gfs_boundary_class ())
+
+/* ------------------------------------------------------------------ */
+/* the simulation: a GfsSimulation whose boxes wrap trees built elsewhere */
+
+typedef FttCell * (* RefLocateFunc) (gpointer handle, gdouble x, gdouble y, gdouble z, gint max_depth);
+typedef void (* RefBcFunc) (gpointer handle, gint ivar);
+
+#define REF_TIMERS 64
+
+typedef struct {
+  GfsSimulation sim;
+  gint nbox;
+  GfsBox ** box;
+  RefLocateFunc locate;
+  RefBcFunc bc;
+  gpointer handle;
+  gint nvar;
+  GfsVariable ** var;
+  GfsDiffusion * D;
+  /* gfs_domain_timer_*: name -> accumulated time (src/domain.c:4137-4180) */
+  struct { const gchar * name; GfsTimer t; } timer[REF_TIMERS];
+  gint ntimers;
+  clock_t clock_start;
+  gboolean timers_on;
+} RefSim;
+
+static void sim_foreach (GtsContainer * c, GtsFunc func, gpointer data)
+{
+  RefSim * s = (RefSim *) c;
+  gint b;
+  for (b = 0; b < s->nbox; b++)
+    (* func) (s->box[b], data);
+}
+
+static void sim_class_init (GtsContainerClass * klass)
+{
+  klass->foreach = sim_foreach;
+}
+
+GfsSimulationClass * gfs_simulation_class (void)
+{
+  static GfsSimulationClass * klass = NULL;
+  if (klass == NULL) {
+    GtsObjectClassInfo info = {
+      "GfsSimulation", sizeof (RefSim), sizeof (GfsSimulationClass),
+      (GtsObjectClassInitFunc) sim_class_init, NULL, NULL, NULL
+    };
+    klass = gts_object_class_new (GTS_OBJECT_CLASS (gts_container_class ()), &info);
+  }
+  return klass;
+}
+
+/* src/domain.c:2623-2638 through the GfsLocateArray that libgfsoracle restates */
+FttCell * gfs_domain_locate (GfsDomain * domain, FttVector target, gint max_depth, GfsBox ** where)
+{
+  RefSim * s = (RefSim *) domain;
+  FttCell * cell = (* s->locate) (s->handle, target.x, target.y, target.z, max_depth);
+  if (cell && where) {
+    FttCell * root = cell;
+    while (!FTT_CELL_IS_ROOT (root)) root = ftt_cell_parent (root);
+    *where = GFS_BOX (FTT_ROOT_CELL (root)->parent);
+  }
+  return cell;
+}
+
+/* src/domain.c:2296-2310 */
+GfsVariable ** gfs_domain_velocity (GfsDomain * domain)
+{
+  FttComponent c;
+  static gchar name[][2] = {"U","V","W"};
+
+  g_return_val_if_fail (domain != NULL, NULL);
+  for (c = 0; c < FTT_DIMENSION; c++) {
+    GfsVariable * v = gfs_variable_from_name (domain->variables, name[c]);
+    if (v == NULL)
+      return NULL;
+    domain->velocity[c] = v;
+  }
+  return domain->velocity;
+}
+
+/* src/domain.c:1463-1497, 1550-1574: every GfsBox tree in container order */
+void gfs_domain_cell_traverse (GfsDomain * domain, FttTraverseType order, FttTraverseFlags flags,
+			       gint max_depth, FttCellTraverseFunc func, gpointer data)
+{
+  RefSim * s = (RefSim *) domain;
+  gint b;
+  for (b = 0; b < s->nbox; b++)
+    ftt_cell_traverse (s->box[b]->root, order, flags, max_depth, func, data);
+}
+
+void gfs_domain_cell_traverse_condition (GfsDomain * domain, FttTraverseType order, FttTraverseFlags flags,
+					 gint max_depth, FttCellTraverseFunc func, gpointer data,
+					 gboolean (* condition) (FttCell *, gpointer), gpointer cdata)
+{
+  RefSim * s = (RefSim *) domain;
+  gint b;
+  for (b = 0; b < s->nbox; b++)
+    ftt_cell_traverse_condition (s->box[b]->root, order, flags, max_depth, func, data, condition, cdata);
+}
+
+/* gfs_domain_bc fills the ghost cells of one variable; the ghost trees belong
+   to libgfsoracle, which restates src/boundary.c for them */
+void gfs_domain_bc (GfsDomain * domain, FttTraverseFlags flags, gint max_depth, GfsVariable * v)
+{
+  RefSim * s = (RefSim *) domain;
+  if (s->bc)
+    (* s->bc) (s->handle, v->i);
+}
+
+/* src/domain.c:2764-2788 */
+void gfs_domain_advect_point (GfsDomain * domain, FttVector * p, gdouble dt)
+{
+  FttCell * cell;
+  FttVector p0, p1;
+  FttComponent c;
+  GfsVariable ** u;
+
+  p0 = p1 = *p;
+  cell = gfs_domain_locate (domain, p0, -1, NULL);
+  if (cell == NULL)
+    return;
+  u = gfs_domain_velocity (domain);
+  for (c = 0; c < FTT_DIMENSION; c++)
+    (&p1.x)[c] += dt*gfs_interpolate (cell, p0, u[c])/2.;
+  cell = gfs_domain_locate (domain, p1, -1, NULL);
+  if (cell == NULL)
+    return;
+  for (c = 0; c < FTT_DIMENSION; c++)
+    (&p->x)[c] += dt*gfs_interpolate (cell, p1, u[c]);
+}
+
+/* src/domain.c:4137-4180 with src/utils.c:1923-1936 (one times() call each):
+   the reference brackets EVERY event, i.e. every particle, with a timer */
+static GfsTimer * timer_lookup (RefSim * s, const gchar * name)
+{
+  gint i;
+  for (i = 0; i < s->ntimers; i++)
+    if (s->timer[i].name == name || !strcmp (s->timer[i].name, name))
+      return &s->timer[i].t;
+  g_assert (s->ntimers < REF_TIMERS);
+  s->timer[s->ntimers].name = name;
+  s->timer[s->ntimers].t.start = -1.;
+  return &s->timer[s->ntimers++].t;
+}
+
+static gdouble clock_elapsed (RefSim * s)
+{
+  struct tms tm;
+  times (&tm);
+  return (tm.tms_utime - s->clock_start)/(gdouble) sysconf (_SC_CLK_TCK);
+}
+
+void gfs_domain_timer_start (GfsDomain * domain, const gchar * name)
+{
+  RefSim * s = (RefSim *) domain;
+  if (s->timers_on)
+    timer_lookup (s, name)->start = clock_elapsed (s);
+}
+
+void gfs_domain_timer_stop (GfsDomain * domain, const gchar * name)
+{
+  RefSim * s = (RefSim *) domain;
+  if (s->timers_on) {
+    gdouble end = clock_elapsed (s);
+    GfsTimer * t = timer_lookup (s, name);
+    t->r.sum += end - t->start;
+    t->r.n++;
+    t->start = -1.;
+  }
+}
+
+/* fluid.c externals that only matter for mixed (solid) cells or statistics */
+void gfs_cell_cm (const FttCell * cell, FttVector * cm) { ftt_cell_pos (cell, cm); }
+void gts_range_init (GtsRange * r) { memset (r, 0, sizeof (GtsRange)); r->min = G_MAXDOUBLE; r->max = - G_MAXDOUBLE; }
+void gts_range_add_value (GtsRange * r, gdouble val)
+{
+  if (val < r->min) r->min = val;
+  if (val > r->max) r->max = val;
+  r->sum += val; r->sum2 += val*val; r->n++;
+}
+void gts_range_update (GtsRange * r)
+{
+  if (r->n > 0) { r->mean = r->sum/r->n; r->stddev = sqrt (fabs (r->sum2/r->n - r->mean*r->mean)); }
+}
+
+/* ------------------------------------------------------------------ */
+/* exported driver                                                      */
+
+enum { REF_FORCE_DRAG = 1, REF_FORCE_LIFT = 2, REF_FORCE_BUOY = 3,
+       REF_FORCE_INERTIAL = 4, REF_FORCE_ADDEDMASS = 5 };
+
+/* same layout as OraStepParams (oracle/particulate_port.c) */
+typedef struct {
+  double dt;
+  int n_forces;
+  int force[8];
+  double rho;
+  int ivar_alpha;
+  double mu;
+  int ivar_mu;
+  double g[3];
+  double cd_const, cl_const;
+  int pattern;
+  int ivar_uold;
+  double cm_const;
+} RefStepParams;
+
+REF_EXPORT int refobj_dimension (void) { return FTT_DIMENSION; }
+
+/* nbox GfsBox roots; broot[b*FTT_NEIGHBORS + d] = root of the GfsBoundary ghost
+ * tree on side d of box b (or NULL); bit d of periodic_mask makes the
+ * boundaries on side d GfsBoundaryPeriodic, matched to the box at the far end
+ * of the chain (the box itself for single-box domains). */
+REF_EXPORT RefSim * refobj_sim_new (int nbox, FttCell ** root, FttCell ** broot, unsigned periodic_mask,
+				    RefLocateFunc locate, RefBcFunc bc, void * handle, int nvar)
+{
+  RefSim * s = (RefSim *) gts_object_new (GTS_OBJECT_CLASS (gfs_simulation_class ()));
+  GfsDomain * domain = GFS_DOMAIN (s);
+  gint b, i;
+  FttDirection d;
+
+  s->locate = locate;
+  s->bc = bc;
+  s->handle = handle;
+  s->nbox = nbox;
+  s->box = g_malloc0 (sizeof (GfsBox *)*nbox);
+  for (b = 0; b < nbox; b++) {
+    GfsBox * box = GFS_BOX (gts_object_new (GTS_OBJECT_CLASS (gfs_box_class ())));
+    gfs_object_simulation_set (box, s);
+    box->root = root[b];
+    box->id = b + 1;
+    FTT_ROOT_CELL (root[b])->parent = box;
+    s->box[b] = box;
+  }
+  for (b = 0; b < nbox; b++)
+    for (d = 0; d < FTT_NEIGHBORS; d++) {
+      FttCell * r = broot ? broot[b*FTT_NEIGHBORS + d] : NULL;
+      if (r) {
+	gboolean periodic = (periodic_mask >> d) & 1;
+	GfsBoundary * bo = GFS_BOUNDARY (gts_object_new (GTS_OBJECT_CLASS (periodic ?
+									   gfs_boundary_periodic_class () :
+									   gfs_boundary_class ())));
+	bo->root = r;
+	bo->box = s->box[b];
+	bo->d = FTT_OPPOSITE_DIRECTION (d);
+	if (periodic) {
+	  /* the chain runs along x: the far end for x sides, the box itself otherwise */
+	  GFS_BOUNDARY_PERIODIC (bo)->matching = d/2 == 0 ? s->box[d == FTT_RIGHT ? 0 : nbox - 1] : s->box[b];
+	  GFS_BOUNDARY_PERIODIC (bo)->d = d;
+	}
+	s->box[b]->neighbor[d] = GTS_OBJECT (bo);
+      }
+      else if (d == FTT_RIGHT && b + 1 < nbox)
+	s->box[b]->neighbor[d] = GTS_OBJECT (s->box[b + 1]);
+      else if (d == FTT_LEFT && b > 0)
+	s->box[b]->neighbor[d] = GTS_OBJECT (s->box[b - 1]);
+    }
+
+  s->nvar = nvar;
+  s->var = g_malloc0 (sizeof (GfsVariable *)*nvar);
+  for (i = 0; i < nvar; i++) {
+    static const gchar * uvw[3] = { "U", "V", "W" };
+    GfsVariable * v = GFS_VARIABLE (gts_object_new (GTS_OBJECT_CLASS (gfs_variable_class ())));
+    gfs_object_simulation_set (v, s);
+    v->i = i;
+    v->domain = domain;
+    v->name = i < FTT_DIMENSION ? g_strdup (uvw[i]) : g_strdup_printf ("A%d", i);
+    if (i < FTT_DIMENSION)
+      v->component = i;
+    s->var[i] = v;
+    domain->variables = g_slist_append (domain->variables, v);
+  }
+  s->sim.physical_params.L = 1.;
+  s->sim.time.end = G_MAXDOUBLE;
+  s->sim.time.iend = G_MAXINT;
+  s->clock_start = 0;
+  return s;
+}
+
+static void clear_sources (RefSim * s)
+{
+  gint c;
+  for (c = 0; c < FTT_DIMENSION; c++)
+    if (s->var[c]->sources) {
+      gts_container_foreach (s->var[c]->sources, (GtsFunc) gts_object_destroy, NULL);
+      gts_object_destroy (GTS_OBJECT (s->var[c]->sources));
+      s->var[c]->sources = NULL;
+    }
+  if (s->D) {
+    gts_object_destroy (GTS_OBJECT (s->D->val));
+    gts_object_destroy (GTS_OBJECT (s->D));
+    s->D = NULL;
+  }
+  if (s->sim.physical_params.alpha) {
+    gts_object_destroy (GTS_OBJECT (s->sim.physical_params.alpha));
+    s->sim.physical_params.alpha = NULL;
+  }
+}
+
+static GtsContainer * sources_of (GfsVariable * v)
+{
+  if (!v->sources)
+    v->sources = gts_container_new (GTS_CONTAINER_CLASS (gts_slist_container_class ()));
+  return v->sources;
+}
+
+/* what the .gfs file of a run declares around the particle list:
+ *   PhysicalParams { alpha = ... }, SourceViscosity mu, Source {} V g ...,
+ *   Time { dtmax = dt } */
+REF_EXPORT void refobj_sim_configure (RefSim * s, const RefStepParams * par, int timers_on)
+{
+  gint c;
+
+  clear_sources (s);
+  s->sim.advection_params.dt = par->dt;
+  s->timers_on = timers_on;
+  if (par->ivar_alpha >= 0) {
+    GfsFunction * f = gfs_function_new (gfs_function_class (), 0.);
+    f->v = s->var[par->ivar_alpha];
+    s->sim.physical_params.alpha = f;
+  }
+  else if (par->rho != 1.)
+    s->sim.physical_params.alpha = gfs_function_new (gfs_function_class (), 1./par->rho);
+  if (par->ivar_mu >= 0 || par->mu != 0.) {
+    GfsSourceDiffusion * sd = (GfsSourceDiffusion *)
+      gts_object_new (GTS_OBJECT_CLASS (gfs_source_diffusion_class ()));
+    s->D = (GfsDiffusion *) gts_object_new (GTS_OBJECT_CLASS (gfs_diffusion_class ()));
+    s->D->val = gfs_function_new (gfs_function_class (), par->mu);
+    s->D->mu = par->ivar_mu >= 0 ? s->var[par->ivar_mu] : NULL;
+    s->D->cell = ref_diffusion_cell;
+    sd->D = s->D;
+    gts_container_add (sources_of (s->var[0]), GTS_CONTAINEE (sd));
+  }
+  for (c = 0; c < FTT_DIMENSION; c++)
+    if (par->g[c] != 0.) {
+      GfsSource * src = (GfsSource *) gts_object_new (GTS_OBJECT_CLASS (gfs_source_class ()));
+      src->intensity = gfs_function_new (gfs_function_class (), par->g[c]);
+      gts_container_add (sources_of (s->var[c]), GTS_CONTAINEE (src));
+    }
+}
+
+REF_EXPORT void refobj_sim_destroy (RefSim * s)
+{
+  gint b, i;
+  FttDirection d;
+  clear_sources (s);
+  for (b = 0; b < s->nbox; b++) {
+    for (d = 0; d < FTT_NEIGHBORS; d++)
+      if (s->box[b]->neighbor[d] && GFS_IS_BOUNDARY (s->box[b]->neighbor[d]))
+	gts_object_destroy (s->box[b]->neighbor[d]);
+    FTT_ROOT_CELL (s->box[b]->root)->parent = NULL;
+    gts_object_destroy (GTS_OBJECT (s->box[b]));
+  }
+  g_free (s->box);
+  for (i = 0; i < s->nvar; i++) {
+    g_free (s->var[i]->name);
+    gts_object_destroy (GTS_OBJECT (s->var[i]));
+  }
+  g_free (s->var);
+  g_slist_free (GFS_DOMAIN (s)->variables);
+  gts_object_destroy (GTS_OBJECT (s));
+}
+
+REF_EXPORT void refobj_sim_time (RefSim * s, double * t, int * i)
+{
+  *t = s->sim.time.t;
+  *i = s->sim.time.i;
+}
+
+/* --- GfsParticleList ------------------------------------------------- */
+
+static GtsObjectClass * force_class (int kind)
+{
+  switch (kind) {
+  case REF_FORCE_DRAG:      return GTS_OBJECT_CLASS (gfs_force_drag_class ());
+  case REF_FORCE_LIFT:      return GTS_OBJECT_CLASS (gfs_force_lift_class ());
+  case REF_FORCE_BUOY:      return GTS_OBJECT_CLASS (gfs_force_buoy_class ());
+  case REF_FORCE_INERTIAL:  return GTS_OBJECT_CLASS (gfs_force_inertial_class ());
+  case REF_FORCE_ADDEDMASS: return GTS_OBJECT_CLASS (gfs_force_addedmass_class ());
+  }
+  g_assert_not_reached ();
+  return NULL;
+}
+
+/* Builds the object graph gfs_particle_list_read (:1022-1094) and
+ * gfs_event_list_read (src/event.c:2446-2506) leave behind for
+ *   GfsParticleList { istep = 1 } GfsParticulate { id x y z mass volume vx vy vz ... }
+ *                   { GfsForce... }
+ * : particles added one by one (the container prepends) then reversed, every
+ * particle given the list's event parameters (copy_event), the force list
+ * reversed and shared by pointer.  n_forces == 0 gives plain GfsParticle
+ * tracers when `tracers' is set (GfsParticulate with forces == NULL behaves
+ * the same, :811-813). */
+REF_EXPORT GfsParticleList * refobj_list_new (RefSim * s, long n, const double * x, const double * y,
+					      const double * z, const double * vx, const double * vy,
+					      const double * vz, const double * mass, const double * volume,
+					      const RefStepParams * par)
+{
+  GfsParticleList * plist = GFS_PARTICLE_LIST (gts_object_new (GTS_OBJECT_CLASS (gfs_particle_list_class ())));
+  GfsEventList * l = GFS_EVENT_LIST (plist);
+  GfsEvent * le = GFS_EVENT (plist);
+  GSList * it;
+  long i;
+  gint k, c;
+
+  gfs_object_simulation_set (plist, s);
+  le->name = g_strdup ("P");
+  gfs_event_set (le, -1., -1., -1., -1, -1, 1);
+  l->klass = GTS_OBJECT_CLASS (gfs_particulate_class ());
+  for (i = 0; i < n; i++) {
+    GtsObject * o = gts_object_new (l->klass);
+    GfsParticle * p = GFS_PARTICLE (o);
+    GfsParticulate * pa = GFS_PARTICULATE (o);
+    gfs_object_simulation_set (o, s);
+    p->id = i + 1;
+    p->pos.x = x[i]; p->pos.y = y[i]; p->pos.z = z ? z[i] : 0.;
+    p->pos_old = p->pos;
+    pa->vel.x = vx[i]; pa->vel.y = vy[i]; pa->vel.z = vz ? vz[i] : 0.;
+    pa->mass = mass[i];
+    pa->volume = volume[i];
+    gts_container_add (GTS_CONTAINER (l->list), GTS_CONTAINEE (o));
+  }
+  l->list->items = g_slist_reverse (l->list->items);
+  for (it = l->list->items; it; it = it->next)
+    gfs_event_set (GFS_EVENT (it->data), le->start, le->end, le->step, le->istart, le->iend, le->istep);
+
+  for (k = 0; k < par->n_forces; k++) {
+    GtsObject * o = gts_object_new (force_class (par->force[k]));
+    GfsForceCoeff * coeff = GFS_IS_FORCE_COEFF (o) ? FORCE_COEFF (o) : NULL;
+    gdouble cst = G_MAXDOUBLE;
+    gfs_object_simulation_set (o, s);
+    if (coeff) {
+      for (c = 0; c < FTT_DIMENSION; c++)
+	coeff->Uold[c] = par->ivar_uold >= 0 ? s->var[par->ivar_uold + c] : NULL;
+      if (par->force[k] == REF_FORCE_DRAG && par->cd_const == par->cd_const) cst = par->cd_const;
+      if (par->force[k] == REF_FORCE_LIFT && par->cl_const == par->cl_const) cst = par->cl_const;
+      if (par->force[k] == REF_FORCE_ADDEDMASS && par->cm_const == par->cm_const) cst = par->cm_const;
+      if (cst < G_MAXDOUBLE) {
+	/* a coefficient function: the reference stores Rep, Urelp ... in cell
+	   variables before evaluating it (:566-575); they need a home */
+	g_assert (s->nvar >= 5);
+	coeff->re_p = s->var[s->nvar - 1];
+	coeff->u_rel = s->var[s->nvar - 2];
+	coeff->v_rel = s->var[s->nvar - 3];
+	coeff->w_rel = s->var[s->nvar - 4];
+	coeff->pdia = s->var[s->nvar - 5];
+	coeff->coefficient = gfs_function_new (gfs_function_class (), cst);
+      }
+    }
+    gts_container_add (GTS_CONTAINER (plist->forces), GTS_CONTAINEE (o));
+  }
+  if (plist->forces->items != NULL) {
+    plist->forces->items = g_slist_reverse (plist->forces->items);
+    gts_container_foreach (GTS_CONTAINER (l->list), (GtsFunc) assign_forces, plist->forces);
+  }
+  plist->idlast = n;
+  plist->first_call = TRUE;
+  return plist;
+}
+
+REF_EXPORT void refobj_list_destroy (GfsParticleList * plist)
+{
+  g_free (GFS_EVENT (plist)->name);
+  GFS_EVENT (plist)->name = NULL;
+  gts_object_destroy (GTS_OBJECT (plist));
+}
+
+REF_EXPORT long refobj_list_size (GfsParticleList * plist)
+{
+  return g_slist_length (GFS_EVENT_LIST (plist)->list->items);
+}
+
+REF_EXPORT void refobj_list_get (GfsParticleList * plist, double * x, double * y, double * z,
+				 double * vx, double * vy, double * vz, double * fx, double * fy, double * fz,
+				 double * mass, unsigned * id)
+{
+  GSList * i = GFS_EVENT_LIST (plist)->list->items;
+  long k = 0;
+  for (; i; i = i->next, k++) {
+    GfsParticle * p = GFS_PARTICLE (i->data);
+    GfsParticulate * pa = GFS_PARTICULATE (i->data);
+    if (x) x[k] = p->pos.x;
+    if (y) y[k] = p->pos.y;
+    if (z) z[k] = p->pos.z;
+    if (vx) vx[k] = pa->vel.x;
+    if (vy) vy[k] = pa->vel.y;
+    if (vz) vz[k] = pa->vel.z;
+    if (fx) fx[k] = pa->force.x;
+    if (fy) fy[k] = pa->force.y;
+    if (fz) fz[k] = pa->force.z;
+    if (mass) mass[k] = pa->mass;
+    if (id) id[k] = p->id;
+  }
+}
+
+/* one pass of simulation_run's event loop over this list (src/simulation.c:
+ * 483: gts_container_foreach (sim->events, gfs_event_do, sim)), then the
+ * time level advances as at the bottom of the loop (:541-543) */
+REF_EXPORT int refobj_list_event (RefSim * s, GfsParticleList * plist, int steps)
+{
+  int k, fired = 0;
+  for (k = 0; k < steps; k++) {
+    gfs_event_do (GFS_EVENT (plist), GFS_SIMULATION (s));
+    fired += GFS_EVENT (plist)->realised;
+    s->sim.time.t += s->sim.advection_params.dt;
+    s->sim.time.i++;
+  }
+  return fired;
+}
+
+/* the list's cull alone (remove_particles_not_in_domain is static: run through
+   the public event with a time step of 0 and no forces would move tracers, so
+   instead expose the same test the cull applies) */
+REF_EXPORT long refobj_list_outside (RefSim * s, GfsParticleList * plist)
+{
+  GSList * i = GFS_EVENT_LIST (plist)->list->items;
+  long n = 0;
+  for (; i; i = i->next)
+    if (gfs_domain_locate (GFS_DOMAIN (s), GFS_PARTICLE (i->data)->pos, -1, NULL) == NULL)
+      n++;
+  return n;
+}
+
+/* a single force model on a single particle, through the vtable the class
+   init installed (GfsParticleForce.force): f per unit volume, :423-655 */
+REF_EXPORT void refobj_force (GfsParticleList * plist, long index, int k, double f[3])
+{
+  GSList * i = GFS_EVENT_LIST (plist)->list->items, * j = plist->forces->items;
+  FttVector v;
+  while (index-- > 0) i = i->next;
+  while (k-- > 0) j = j->next;
+  v = (* GFS_PARTICLE_FORCE (j->data)->force) (GFS_PARTICLE (i->data), GFS_PARTICLE_FORCE (j->data));
+  f[0] = v.x; f[1] = v.y; f[2] = v.z;
+}
+
+/* gfs_particle_bc (:3375-3395) alone */
+REF_EXPORT void refobj_list_bc (GfsParticleList * plist)
+{
+  gfs_particle_bc (plist);
+}
+
+/* the reference's writer of the particle block (gfs_particulate_write :910-926
+   over gfs_particle_write src/particle.c:86-98), one line per particle */
+REF_EXPORT int refobj_list_write (GfsParticleList * plist, const char * path)
+{
+  FILE * fp = fopen (path, "w");
+  GSList * i = GFS_EVENT_LIST (plist)->list->items;
+  if (!fp) return -1;
+  for (; i; i = i->next) {
+    (* GTS_OBJECT (i->data)->klass->write) (i->data, fp);
+    fputc ('\n', fp);
+  }
+  fclose (fp);
+  return 0;
+}
+
+/* --- GfsParticulateField --------------------------------------------- */
+
+/* GfsParticulateField <var ivar> P : one event (reset + scatter, :1934-1957) */
+REF_EXPORT void refobj_field_event (RefSim * s, GfsParticleList * plist, int ivar)
+{
+  GfsVariable * v = GFS_VARIABLE (gts_object_new (GTS_OBJECT_CLASS (gfs_particulate_field_class ())));
+  gfs_object_simulation_set (v, s);
+  v->i = ivar;
+  v->domain = GFS_DOMAIN (s);
+  GFS_PARTICULATE_FIELD (v)->plist = plist;
+  gfs_event_set (GFS_EVENT (v), -1., -1., -1., -1, -1, 1);
+  GFS_EVENT (v)->i = s->sim.time.i;
+  gfs_event_do (GFS_EVENT (v), GFS_SIMULATION (s));
+  g_assert (GFS_EVENT (v)->realised);
+  gts_object_destroy (GTS_OBJECT (v));
+}
+
+/* --- GfsSourceParticulate -------------------------------------------- */
+
+/* the closed forms of OraKernel, as the C a user's `kernel = ...` compiles to */
+typedef struct { int kind; double a, b; int p; int flags; } RefKernel;
+
+static gdouble kernel_spatial (gdouble x, gdouble y, gdouble z, gpointer data)
+{
+  const RefKernel * k = data;
+  gdouble r2 = x*x + y*y + z*z;
+  switch (k->kind) {
+  case 0: return k->a;
+  case 1: return k->a*exp (- k->b*r2);
+  case 2: {
+    gdouble t = 1. - k->b*r2, v = k->a;
+    gint i;
+    if (t <= 0.) return 0.;
+    for (i = 0; i < k->p; i++) v *= t;
+    return v;
+  }
+  }
+  g_assert_not_reached ();
+  return 0.;
+}
+
+/* GfsSourceParticulate {} U V W P { rkernel = r kernel = f } : one event
+ * (:2177-2228) depositing into variables ivar0..ivar0+dim-1 */
+REF_EXPORT void refobj_source_event (RefSim * s, GfsParticleList * plist, int ivar0, double rkernel,
+				     const RefKernel * kernel)
+{
+  GfsSourceParticulate * sp = GFS_SOURCE_PARTICULATE (gts_object_new (GTS_OBJECT_CLASS (gfs_source_particulate_class ())));
+  RefKernel k = *kernel;
+  gint c;
+
+  gfs_object_simulation_set (sp, s);
+  sp->plist = plist;
+  sp->rkernel = rkernel;
+  if (!sp->kernel_function)
+    sp->kernel_function = gfs_function_new (gfs_function_spatial_class (), 0.);
+  gfs_object_simulation_set (sp->kernel_function, s);
+  sp->kernel_function->spatial = kernel_spatial;
+  sp->kernel_function->data = &k;
+  for (c = 0; c < FTT_DIMENSION; c++)
+    sp->u[c] = s->var[ivar0 + c];
+  gfs_event_set (GFS_EVENT (sp), -1., -1., -1., -1, -1, 1);
+  GFS_EVENT (sp)->i = s->sim.time.i;
+  gfs_event_do (GFS_EVENT (sp), GFS_SIMULATION (s));
+  g_assert (GFS_EVENT (sp)->realised);
+  gts_object_destroy (GTS_OBJECT (sp));
+}
+
+REF_EXPORT long refobj_warnings (void) { return ref_warnings; }
+
+/* called by the generated stubs */
+void refobj_unimplemented (const char * name)
+{
+  fprintf (stderr, "refobj: `%s' is not part of the particulate path and has no run-time here\n", name);
+  abort ();
+}
