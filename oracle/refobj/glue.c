@@ -816,6 +816,22 @@ void gfs_domain_advect_point (GfsDomain * domain, FttVector * p, gdouble dt)
     (&p->x)[c] += dt*gfs_interpolate (cell, p1, u[c]);
 }
 
+/* src/simulation.c:1893-1932 for a simulation without GfsMap objects (none of
+   the configurations declares one): the L/lambda scaling only */
+void gfs_simulation_map (GfsSimulation * sim, FttVector * p)
+{
+  FttComponent c;
+  for (c = 0; c < 3; c++)
+    (&p->x)[c] *= (&GFS_DOMAIN (sim)->lambda.x)[c]/sim->physical_params.L;
+}
+
+void gfs_simulation_map_inverse (GfsSimulation * sim, FttVector * p)
+{
+  FttComponent c;
+  for (c = 0; c < 3; c++)
+    (&p->x)[c] *= sim->physical_params.L/(&GFS_DOMAIN (sim)->lambda.x)[c];
+}
+
 /* src/domain.c:4137-4180 with src/utils.c:1923-1936 (one times() call each):
    the reference brackets EVERY event, i.e. every particle, with a timer */
 static GfsTimer * timer_lookup (RefSim * s, const gchar * name)
@@ -958,6 +974,7 @@ REF_EXPORT RefSim * refobj_sim_new (int nbox, FttCell ** root, FttCell ** broot,
     domain->variables = g_slist_append (domain->variables, v);
   }
   s->sim.physical_params.L = 1.;
+  domain->lambda.x = domain->lambda.y = domain->lambda.z = 1.;
   s->sim.time.end = G_MAXDOUBLE;
   s->sim.time.iend = G_MAXINT;
   s->clock_start = 0;
@@ -1031,10 +1048,11 @@ REF_EXPORT void refobj_sim_destroy (RefSim * s)
   gint b, i;
   FttDirection d;
   clear_sources (s);
-  for (b = 0; b < s->nbox; b++) {
+  for (b = 0; b < s->nbox; b++)
     for (d = 0; d < FTT_NEIGHBORS; d++)
       if (s->box[b]->neighbor[d] && GFS_IS_BOUNDARY (s->box[b]->neighbor[d]))
 	gts_object_destroy (s->box[b]->neighbor[d]);
+  for (b = 0; b < s->nbox; b++) {
     FTT_ROOT_CELL (s->box[b]->root)->parent = NULL;
     gts_object_destroy (GTS_OBJECT (s->box[b]));
   }
@@ -1234,6 +1252,7 @@ REF_EXPORT int refobj_list_write (GfsParticleList * plist, const char * path)
   GSList * i = GFS_EVENT_LIST (plist)->list->items;
   if (!fp) return -1;
   for (; i; i = i->next) {
+    fputs ("    ", fp);                 /* as gfs_event_list_write does, src/event.c:2516-2520 */
     (* GTS_OBJECT (i->data)->klass->write) (i->data, fp);
     fputc ('\n', fp);
   }

@@ -28,72 +28,7 @@ def ctx():
     c.close()
 
 
-def _world(kind):
-    if kind == "c1":
-        return worlds.make_c1(level=5, n_particles=1000)
-    if kind == "uniform3":
-        return worlds.make_c2(level=4, n_particles=20000)
-    if kind == "ring3":
-        return worlds.make_ring("ring3", 3, 6, 30000, 3003)
-    if kind == "ring2":
-        t = capi.Tree(2)
-        t.refine_ring(3, 7, 0.25, 1.5)
-        t.corner_sweep()
-        for s in range(4):
-            t.add_boundary(s)
-        t.finalize(); t.build_stencils()
-        a = t.view()
-        u, v = worlds.lid_style(a.pos)
-        worlds.apply_dirichlet_ghosts(a, u, {2: 1.0})
-        worlds.apply_dirichlet_ghosts(a, v, {})
-        return worlds.World("ring2", 2, t, a, u, v, None, (capi.FORCE_DRAG, capi.FORCE_LIFT, capi.FORCE_BUOY),
-                            dt=1e-2, mu=1e-3, g=(0.3, -1.0, 0.0), seed=11, n_particles=5000,
-                            meta=dict(d_p=worlds.D_P, rho_p=worlds.RHO_P, v0="zero", field="lid"))
-    if kind == "ring3b":
-        t = capi.Tree(3)
-        t.refine_ring(2, 5, 0.3, 1.5)
-        t.corner_sweep()
-        for s in range(6):
-            t.add_boundary(s)
-        t.finalize(); t.build_stencils()
-        a = t.view()
-        u, v, w = worlds.vortex_ring(a.pos)
-        return worlds.World("ring3b", 3, t, a, u, v, w, (capi.FORCE_LIFT, capi.FORCE_DRAG),
-                            dt=2e-3, mu=2e-3, rho=1.3, seed=12, n_particles=8000,
-                            meta=dict(d_p=worlds.D_P, rho_p=worlds.RHO_P, v0="fluid", field="ring",
-                                      cloud="half uniform, half gaussian"))
-    if kind in ("chain2", "chain3"):
-        # several GfsBoxes in a row along +x, refined around a ring straddling the first interface
-        dim, nbox = (2, 3) if kind == "chain2" else (3, 2)
-        minl, maxl = (3, 6) if dim == 2 else (2, 5)
-        t = capi.Tree(dim)
-        t.add_root((0.0, 0.0, 0.0))
-        for b in range(1, nbox):
-            t.add_root((float(b), 0.0, 0.0))
-            t.link_roots(b - 1, 0, b)
-        t.refine(lambda pos, level, h: level < minl or (level < maxl and abs(
-            np.hypot(pos[0] - 0.5, pos[1]) - 0.3) < 1.5 * h and (dim == 2 or abs(pos[2]) < 3 * h)))
-        t.corner_sweep()
-        for b, sd in [(0, 1), (nbox - 1, 0)] + [(b, sd) for b in range(nbox) for sd in range(2, 2 * dim)]:
-            t.add_boundary(sd, b)
-        t.finalize(); t.build_stencils()
-        a = t.view()
-        u, v, wz = worlds.taylor_green(a.pos * 0.5)
-        forces = (capi.FORCE_DRAG, capi.FORCE_LIFT, capi.FORCE_BUOY)
-        return worlds.World(kind, dim, t, a, u, v, (0.3 * u if dim == 3 else None), forces, dt=2e-3, mu=1e-3,
-                            g=(0.2, -1.0, 0.0), seed=14, n_particles=6000,
-                            meta=dict(d_p=worlds.D_P, rho_p=worlds.RHO_P, v0="zero", field="tg", nbox=nbox))
-    raise KeyError(kind)
-
-
-def _particles(w, n=None):
-    """the world's seeded cloud; chains of boxes get it stretched over all boxes"""
-    parts = worlds.make_particles(w, n)
-    nbox = w.meta.get("nbox", 1)
-    if nbox > 1:
-        rng = np.random.default_rng(w.seed + 1)
-        parts["x"] = rng.uniform(-0.47, nbox - 0.53, len(parts["x"]))
-    return parts
+_world, _particles = helpers.test_world, helpers.test_particles
 
 
 _cache = {}
@@ -715,28 +650,7 @@ def test_inertial_needs_the_previous_field():
         c.close()
 
 
-def _periodic_world(dim):
-    """uniform (3D) / ring-refined (2D) box with ghost layers on every side;
-    x (and z in 3D) periodic, y sides plain boundaries (particles leaving there are dropped)"""
-    t = capi.Tree(dim)
-    if dim == 3:
-        t.refine_uniform(4)
-    else:
-        t.refine_ring(3, 6, 0.25, 1.5)
-        t.corner_sweep()
-    for s in range(2 * dim):
-        t.add_boundary(s)
-    periodic = [0, 1] + ([4, 5] if dim == 3 else [])
-    for s in periodic:
-        t.set_periodic(s)
-    t.finalize(); t.build_stencils()
-    a = t.view()
-    u, v, wz = worlds.taylor_green(a.pos)            # period 1: ghost values = field at the ghost centres
-    w = worlds.World("periodic%d" % dim, dim, t, a, 3.0 * u, 3.0 * v + 0.7, wz if dim == 3 else None,
-                     (capi.FORCE_DRAG, capi.FORCE_BUOY), dt=4e-3, mu=1e-3, g=(0.0, -1.0, 0.0), seed=5,
-                     n_particles=3000, meta=dict(d_p=worlds.D_P, rho_p=worlds.RHO_P, v0="fluid", field="tg"))
-    mask = sum(1 << s for s in periodic)
-    return w, mask
+_periodic_world = helpers.periodic_world
 
 
 @pytest.mark.parametrize("dim", [2, 3])
