@@ -24,11 +24,14 @@ Prints ONE JSON line (rank 0).  `value` is whole-job particle-steps/s with
 inputs resident in HBM; `e2e` is the same metric through the host-buffer
 C-ABI call (H2D of the particle arrays and the field, D2H of the new state
 inside the timed region); `roofline` describes the fused step kernel;
-`cpu_baseline` is the oracle timed on this box's host cores.
+`cpu_baseline` is the reference's own object code (oracle/_ref/libgfsrefobj:
+modules/particulatecommon.c, src/event.c, src/particle.c, src/fluid.c, src/ftt.c
+compiled unmodified) running gfs_event_do on a GfsParticleList on one host core
+-- the reference is serial per MPI rank.
 
---impl reference times the reference's CPU implementation of the path
-(oracle/_ref: the reference's own ftt.c/fluid.c object code + the restated
-force/integrator layer, reference call pattern) with all host threads.
+--impl reference times the same object code on all host cores the way the
+reference scales, as independent single-threaded ranks (forked processes, each
+with its share of the particles and the whole replicated domain).
 """
 from __future__ import annotations
 
@@ -178,6 +181,57 @@ def time_oracle(ora, worlds, helpers_params, sp, sim, n_sample, steps, warmup, t
     return n_sample * steps / dt, dt
 
 
+def time_refobj(ora, worlds, helpers_params, sp, sim, n_sample, steps, warmup, first=0, timers=True):
+    """particle-steps/s of the reference's own GfsParticleList event (cull, per-particle
+    GfsEvent gating + timers, GfsParticulate events, gfs_particle_bc) on one core"""
+    parts = worlds.make_particles(sp, first + n_sample)
+    par = helpers_params(sp, 0)
+    rs = ora.RefSim(sim)
+    rs.configure(par, timers)
+    rl = ora.RefParticleList(rs, *[parts[k][first:] for k in COLS], par)
+    if warmup:
+        rl.event(warmup)
+    t0 = time.perf_counter()
+    rl.event(steps)
+    dt = time.perf_counter() - t0
+    left = len(rl)
+    rs.close()
+    return n_sample * steps / dt, dt, left
+
+
+def _refobj_rank(ora, worlds, mk, sp, sim, first, n, steps, warmup, barrier, out):
+    parts = worlds.make_particles(sp, first + n)
+    par = mk(sp, 0)
+    rs = ora.RefSim(sim)
+    rs.configure(par, True)
+    rl = ora.RefParticleList(rs, *[parts[k][first:] for k in COLS], par)
+    if warmup:
+        rl.event(warmup)
+    barrier.wait()
+    t0 = time.perf_counter()
+    rl.event(steps)
+    out.put(time.perf_counter() - t0)
+    os._exit(0)
+
+
+def time_refobj_ranks(ora, worlds, mk, sp, sim, n_per_rank, steps, warmup, ranks):
+    """`ranks` forked single-threaded processes, each running the reference's list event
+    on its own n_per_rank particles of the cloud; the domain (built before the fork) is
+    shared copy-on-write.  Returns (aggregate particle-steps/s, slowest rank's seconds)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    barrier, out = ctx.Barrier(ranks), ctx.SimpleQueue()
+    procs = [ctx.Process(target=_refobj_rank, args=(ora, worlds, mk, sp, sim, r * n_per_rank, n_per_rank,
+                                                    steps, warmup, barrier, out)) for r in range(ranks)]
+    for p in procs:
+        p.start()
+    times = [out.get() for _ in procs]
+    for p in procs:
+        p.join()
+    dt = max(times)
+    return ranks * n_per_rank * steps / dt, dt
+
+
 def oracle_params_factory(ora):
     fmap = {1: ora.FORCE_DRAG, 2: ora.FORCE_LIFT, 3: ora.FORCE_BUOY}
 
@@ -193,26 +247,28 @@ def run_reference(args):
     pkg = entry.load_package()          # worlds.spec / analytic fields only: no product compute
     ora = entry.load_oracle()
     worlds = pkg.worlds
-    threads = ora.load(3).ora_max_threads()
+    cores = len(os.sched_getaffinity(0))
     sp, sim = oracle_world(ora, worlds, args.config)
     mk = oracle_params_factory(ora)
     # size the per-step sample so that one step takes about a second and the whole run
     # (steps + warmup) about a minute and a half at most
-    rate, _ = time_oracle(ora, worlds, mk, sp, sim, 20_000, 1, 1, threads)
+    rate1, _, _ = time_refobj(ora, worlds, mk, sp, sim, 10_000, 1, 1)
     per_step_s = min(1.0, 90.0 / max(args.steps + args.warmup, 1))
-    n_sample = int(min(sp.n_particles, max(20_000, rate * per_step_s)))
-    value, dt = time_oracle(ora, worlds, mk, sp, sim, n_sample, args.steps, args.warmup, threads)
+    n_rank = int(min(sp.n_particles // cores, max(2_000, rate1 * per_step_s)))
+    value, dt = time_refobj_ranks(ora, worlds, mk, sp, sim, n_rank, args.steps, args.warmup, cores)
+    n_sample = n_rank * cores
     line = {
         "impl": "reference", "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.config), "sample_particles_per_step": n_sample},
-        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": threads, "kind": "reference",
-                         "sample": f"{n_sample} particles/step of the {args.config} cloud x {args.steps} steps; "
-                                   "reference ftt.c+fluid.c object code + restated forces/integrator, "
-                                   "reference call pattern (6 locates, 9 interpolations, 6 gradients per "
-                                   "particle-step), OpenMP over particles"},
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "reference",
+                         "sample": f"{n_sample} particles/step of the {args.config} cloud x {args.steps} steps "
+                                   f"on the full tree, as {cores} single-threaded ranks of {n_rank} particles; "
+                                   "the reference's own object code (particulatecommon.c, event.c, particle.c, "
+                                   "fluid.c, ftt.c unmodified): gfs_event_do on a GfsParticleList",
+                         "one_rank": rate1},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -451,22 +507,26 @@ def run_b200(args):
 
 
 def cpu_baseline(args, worlds):
-    """The oracle on one host core, reference call pattern, bounded sample."""
+    """The reference's own object code on one host core, bounded sample."""
     ora = entry.load_oracle()
     sp, sim = oracle_world(ora, worlds, args.config)
     mk = oracle_params_factory(ora)
-    rate, _ = time_oracle(ora, worlds, mk, sp, sim, 20_000, 1, 0, 1)
+    rate, _, _ = time_refobj(ora, worlds, mk, sp, sim, 20_000, 1, 0)
     n = int(min(sp.n_particles, max(20_000, rate * 5.0)))          # ~5 s per step
-    value, dt = time_oracle(ora, worlds, mk, sp, sim, n, 3, 0, 1)
+    value, dt, left = time_refobj(ora, worlds, mk, sp, sim, n, 3, 0)
+    value_port, _ = time_oracle(ora, worlds, mk, sp, sim, n, 3, 0, 1)
     threads = ora.load(3).ora_max_threads()
     value_mt, _ = time_oracle(ora, worlds, mk, sp, sim, n, 3, 1, threads)
     value_fused, _ = time_oracle(ora, worlds, mk, sp, sim, n, 3, 0, 1, pattern=1)
     return {"value": value, "unit": "particle-steps/s", "cores": 1, "kind": "reference",
-            "sample": f"{n} particles x 3 steps of the {args.config} cloud on the full tree; reference "
-                      "ftt.c+fluid.c object code + restated forces/integrator, reference call pattern, "
-                      "serial as the reference is per MPI rank",
-            "all_cores": {"value": value_mt, "cores": threads, "note": "same code, OpenMP over particles"},
-            "fused_1core": {"value": value_fused, "note": "one locate + one interpolation set per particle"},
+            "sample": f"{n} particles x 3 steps of the {args.config} cloud on the full tree; the reference's "
+                      "own object code (modules/particulatecommon.c, src/event.c, src/particle.c, src/fluid.c, "
+                      "src/ftt.c compiled unmodified): gfs_event_do on a GfsParticleList, serial as the "
+                      "reference is per MPI rank",
+            "port_1core": {"value": value_port, "note": "restated oracle (bit-identical results), same call "
+                                                        "pattern without the GtsObject/event layer"},
+            "port_all_cores": {"value": value_mt, "cores": threads, "note": "restated oracle, OpenMP over particles"},
+            "port_fused_1core": {"value": value_fused, "note": "one locate + one interpolation set per particle"},
             "host_cpus": os.cpu_count()}
 
 

@@ -139,6 +139,42 @@ def test_step_one(kind, ctx):
         assert np.abs(got[k] - want[k]).max() <= 1e-11 * scale
 
 
+@pytest.mark.parametrize("kind", KINDS)
+def test_step_against_reference_object_code(kind, ctx):
+    """the CUDA step against the reference's OWN object code (libgfsrefobj:
+    particulatecommon.c + event.c + particle.c + fluid.c + ftt.c compiled unmodified)
+    driving a GfsParticleList through gfs_event_do -- no restated layer in between;
+    3 steps, same bars as against the restated oracle"""
+    if not ora.refobj_available(2 if kind in ("c1", "ring2", "chain2") else 3):
+        pytest.skip("oracle/_ref/libgfsrefobj*.so not built")
+    w, sim, ptrs, idx = setup(kind, ctx)
+    parts = _particles(w, 5000)
+    ctx.particles_upload(**parts)
+    opar = helpers.oracle_params(w)
+    rs = ora.RefSim(sim)
+    rs.configure(opar)
+    rl = ora.RefParticleList(rs, *[parts[k] for k in ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")], opar)
+    par = w.step_params(record_cells=True, record_forces=True)
+    for step in range(3):
+        s = rl.get()
+        ocell = idx(sim.locate(s["x"], s["y"], s["z"] if w.dim == 3 else None))
+        assert rl.event() == 1
+        ctx.step(par)
+        got = ctx.particles_download(cells=True, forces=True)
+        want = rl.get()
+        assert len(want["x"]) == len(got["x"])
+        if step == 0:
+            assert np.array_equal(got["cell"], ocell)
+            same = np.ones(len(ocell), dtype=bool)
+        same &= got["cell"] == ocell          # a cell flipping one step early is counted, not bounded
+        assert same.mean() > 0.999
+        _check_state(got, want, w.dim, rtol=RTOL_STEP if step == 0 else 1e-11, sel=same)
+        for k in ("fx", "fy", "fz")[:w.dim]:
+            scale = max(np.abs(want[k]).max(), 1e-300)
+            assert np.abs(got[k] - want[k])[same].max() <= 1e-11 * scale, (step, k)
+    rs.close()
+
+
 @pytest.mark.parametrize("forces,kw", [
     ((capi.FORCE_BUOY,), {}),
     ((capi.FORCE_BUOY, capi.FORCE_DRAG, capi.FORCE_LIFT), {}),

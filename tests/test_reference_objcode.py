@@ -313,3 +313,34 @@ def test_particle_text_block_byte_identical(kind, tmp_path):
     assert ref.count(b"\n") == 300 and ref.startswith(b"    GfsParticulate 1 ")
     assert ref == port
     rs.close()
+
+
+import glob
+import os
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: os.path.basename(p)[:-4])
+def test_reference_object_code_reproduces_golden(path):
+    """the committed fixtures (tests/golden, generated by make_golden.py through the
+    restated port) are what the reference's own particulate object code gives"""
+    g = np.load(path)
+    name = os.path.basename(path)[:-4]
+    w = {"c1_l5": lambda: worlds.make_c1(level=5, n_particles=400),
+         "tg_l4": lambda: worlds.make_c2(level=4, n_particles=400),
+         "ring_3_6": lambda: worlds.make_ring("ring", 3, 6, 400, 3003)}[name]()
+    sim, ptrs = helpers.matched_oracle(w)
+    parts = {k: (g["p_" + k] if len(g["p_" + k]) else None) for k in KEYS}
+    par = helpers.oracle_params(w)
+    rs = ora.RefSim(sim)
+    rs.configure(par)
+    rl = ora.RefParticleList(rs, *[parts[k] for k in KEYS], par)
+    done = 0
+    for steps in (1, 10):
+        rl.event(steps - done)
+        done = steps
+        st = rl.get()
+        for k in ("x", "y", "vx", "vy", "fx", "fy"):
+            assert np.array_equal(st[k], g[f"s{steps}_{k}"]), (steps, k)
+    rs.close()
