@@ -158,7 +158,10 @@ int gfsb200_ftt_scatter (const gfsb200_ftt_map * m, size_t offset, int var, int 
 {
   for (int32_t i = 0; i < m->n_cells; i++) {
     FttCell * c = m->cell[i];
-    if (FTT_CELL_IS_DESTROYED (c) || !c->data || (leaves_only && !FTT_CELL_IS_LEAF (c)))
+    /* leaves_only: the cells gfs_domain_cell_traverse (FTT_TRAVERSE_LEAFS) visits, i.e. the
+       leaves of the GfsBox trees -- ghost cells keep their value until the next gfs_domain_bc */
+    if (FTT_CELL_IS_DESTROYED (c) || !c->data ||
+	(leaves_only && (!FTT_CELL_IS_LEAF (c) || (c->flags & BRIDGE_FLAG_BOUNDARY))))
       continue;
     ((double *) ((char *) c->data + offset))[var] = in[i];
   }

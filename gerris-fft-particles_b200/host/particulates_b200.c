@@ -49,6 +49,7 @@ typedef struct {
   gboolean tree_valid;
   gdouble * field[3];                   /* host staging of U,V,W in flat order */
   GfsVariable ** uold;                  /* GfsForceCoeff.Uold of an inertial / added-mass force, or NULL */
+  gboolean snapshot;                    /* a GfsForceInertial is in the list: Un,Vn,Wn are refreshed after each event */
   gint32 n_cells;
   gboolean (* reference_event) (GfsEvent *, GfsSimulation *);
 } B200State;
@@ -77,6 +78,27 @@ static B200State * state_of (GfsParticleList * plist)
     g_hash_table_insert (b200_states, plist, s);
   }
   return s;
+}
+
+/* the list's destroy method (gfs_particle_list_destroy, :1121-1130) with the
+ * device state released first: a later list allocated at the same address must
+ * not inherit this one's context and flat tree */
+static void (* reference_list_destroy) (GtsObject *) = NULL;
+
+static void b200_particle_list_destroy (GtsObject * o)
+{
+  B200State * s = b200_states ? g_hash_table_lookup (b200_states, o) : NULL;
+  if (s) {
+    FttComponent c;
+    g_hash_table_remove (b200_states, o);
+    if (s->map) gfsb200_ftt_map_free (s->map);
+    if (s->tree) gfsb200_tree_free (s->tree);
+    if (s->ctx) gfsb200_ctx_destroy (s->ctx);
+    for (c = 0; c < 3; c++)
+      g_free (s->field[c]);
+    g_free (s);
+  }
+  (* reference_list_destroy) (o);
 }
 
 /* ------------------------------------------------------------------ */
@@ -206,6 +228,7 @@ static gboolean step_params (GfsParticleList * plist, GfsSimulation * sim, gfsb2
     else if (GFS_IS_FORCE_INERTIAL (i->data)) {
       p->force[p->n_forces++] = GFSB200_FORCE_INERTIAL;
       state_of (plist)->uold = coeff->Uold;
+      state_of (plist)->snapshot = TRUE;
     }
     else if (GFS_IS_FORCE_LIFT (i->data)) {
       p->force[p->n_forces++] = GFSB200_FORCE_LIFT;
@@ -357,8 +380,11 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
   download_particles (s, plist);
 
   gfs_particle_bc (plist);                                   /* :993, host side as in the reference */
-  if (s->uold)
-    store_previous_velocity (GFS_DOMAIN (sim), s->uold);     /* :1003-1012 */
+  /* :1003-1012: the reference refreshes Un,Vn,Wn only when the list holds a
+     GfsForceInertial; a GfsForceAddedMass alone keeps the snapshot its read method
+     took (verified against the reference's object code, tests/test_reference_objcode.py) */
+  if (s->uold && s->snapshot)
+    store_previous_velocity (GFS_DOMAIN (sim), s->uold);
   return TRUE;
 }
 
@@ -478,6 +504,8 @@ const gchar * g_module_check_init (void)
   /* ... then route the hot-path events to the device */
   reference_list_event = GFS_EVENT_CLASS (gfs_particle_list_class ())->event;
   GFS_EVENT_CLASS (gfs_particle_list_class ())->event = b200_particle_list_event;
+  reference_list_destroy = GTS_OBJECT_CLASS (gfs_particle_list_class ())->destroy;
+  GTS_OBJECT_CLASS (gfs_particle_list_class ())->destroy = b200_particle_list_destroy;
   reference_field_event = GFS_EVENT_CLASS (gfs_particulate_field_class ())->event;
   GFS_EVENT_CLASS (gfs_particulate_field_class ())->event = b200_particulate_field_event;
   reference_source_event = GFS_EVENT_CLASS (gfs_source_particulate_class ())->event;

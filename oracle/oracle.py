@@ -299,14 +299,19 @@ _reflibs = {}
 _LOCATE_T = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int)
 
 
-def refobj_available(dim: int) -> bool:
-    return os.path.exists(os.path.join(_HERE, "_ref", f"libgfsrefobj{dim}D.so"))
+def refobj_available(dim: int, module: bool = False) -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", f"libgfsref{'mod' if module else 'obj'}{dim}D.so"))
 
 
-def load_refobj(dim: int) -> C.CDLL:
-    if dim in _reflibs:
-        return _reflibs[dim]
-    R = C.CDLL(os.path.join(_HERE, "_ref", f"libgfsrefobj{dim}D.so"))
+def load_refobj(dim: int, module: bool = False) -> C.CDLL:
+    """module=False: libgfsrefobj, the unmodified reference.  module=True:
+    libgfsrefmod, the same objects and run-time with the drop-in GModule
+    (gerris-fft-particles_b200/host/particulates_b200.c) linked in and its
+    g_module_check_init() run, i.e. the three hot-path events routed to the GPU."""
+    key = (dim, module)
+    if key in _reflibs:
+        return _reflibs[key]
+    R = C.CDLL(os.path.join(_HERE, "_ref", f"libgfsref{'mod' if module else 'obj'}{dim}D.so"))
     vp, dbl, lng, i32 = C.c_void_p, C.c_double, C.c_long, C.c_int
     sig = {
         "refobj_dimension": (i32, []),
@@ -326,12 +331,18 @@ def load_refobj(dim: int) -> C.CDLL:
         "refobj_field_event": (None, [vp, vp, i32]),
         "refobj_source_event": (None, [vp, vp, i32, dbl, C.POINTER(Kernel)]),
         "refobj_warnings": (lng, []),
+        "refobj_module_init": (i32, []),
+        "refobj_module_name": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
         f = getattr(R, name)
         f.restype, f.argtypes = res, args
     assert R.refobj_dimension() == dim
-    _reflibs[dim] = R
+    if module:
+        assert R.refobj_module_init() == 1 and R.refobj_module_name() == b"particulates"
+    else:
+        assert R.refobj_module_init() == 0
+    _reflibs[key] = R
     return R
 
 
@@ -341,9 +352,9 @@ class RefSim:
     GfsLocateArray.  Bit d of periodic_mask: the boundaries on side d are
     GfsBoundaryPeriodic."""
 
-    def __init__(self, sim: Sim, periodic_mask: int = 0):
+    def __init__(self, sim: Sim, periodic_mask: int = 0, module: bool = False):
         self.sim, self.dim = sim, sim.dim
-        self.R = load_refobj(sim.dim)
+        self.R = load_refobj(sim.dim, module)
         nb = sim.L.ora_nbox(sim.h)
         nn = 2 * sim.dim
         roots = (C.c_void_p * nb)(*[sim.L.ora_box_root(sim.h, b) for b in range(nb)])

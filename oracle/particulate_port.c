@@ -26,10 +26,16 @@
  *   particle BCs (periodic wrap / drop)  modules/particulatecommon.c:3058-3214, 3318-3395
  *
  * PARITY PIN: the reference ships no test, example or golden vector for the
- * particulates module, so the restated part is "parity
- * unpinned" by the reference's own tests; it is pinned instead to the
- * reference's object code for everything below the force models and to
- * hand-derived known answers in tests/test_oracle.py.
+ * particulates module.  This restatement is pinned to
+ * OUTPUTS OF THE REFERENCE ITSELF RUN HERE: libgfsrefobj (oracle/refobj/glue.c)
+ * holds modules/particulatecommon.c, src/event.c and src/particle.c compiled
+ * unmodified, and tests/test_reference_objcode.py requires every function
+ * restated below to reproduce them BIT FOR BIT (events, each force model,
+ * inertial/added mass, tracers, cull, particle BCs, both deposits, the text
+ * block).  Not covered by object code, because src/domain.c and
+ * src/boundary.c do not compile here: the GfsLocateArray arithmetic, the
+ * ghost-tree construction and gfs_cell_init (hand-derived known answers in
+ * tests/test_oracle.py).
  *
  * Built with -ffp-contract=off to match the reference's non-FMA x86-64 build.
  */

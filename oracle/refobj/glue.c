@@ -258,6 +258,67 @@ gpointer * g_ptr_array_free (GPtrArray * array, gboolean free_seg)
   return d;
 }
 
+/* GHashTable (ghash.c): chained buckets, direct hash/equality when none is given */
+typedef struct _HNode HNode;
+struct _HNode { gpointer key, value; HNode * next; };
+struct _GHashTable { GHashFunc hash; GEqualFunc equal; guint nb; HNode ** bucket; };
+
+guint g_str_hash (gconstpointer v)
+{
+  const signed char * p = v;
+  guint h = 5381;
+  for (; *p; p++) h = (h << 5) + h + *p;
+  return h;
+}
+
+gboolean g_str_equal (gconstpointer a, gconstpointer b) { return strcmp (a, b) == 0; }
+
+GHashTable * g_hash_table_new (GHashFunc hash, GEqualFunc equal)
+{
+  GHashTable * h = g_malloc0 (sizeof (GHashTable));
+  h->hash = hash; h->equal = equal;
+  h->nb = 257;
+  h->bucket = g_malloc0 (sizeof (HNode *)*h->nb);
+  return h;
+}
+
+static HNode ** hash_find (GHashTable * h, gconstpointer key)
+{
+  guint k = h->hash ? (* h->hash) (key) : (guint) ((gulong) key >> 4);
+  HNode ** n = &h->bucket[k % h->nb];
+  while (*n && !(h->equal ? (* h->equal) ((*n)->key, key) : (*n)->key == key))
+    n = &(*n)->next;
+  return n;
+}
+
+void g_hash_table_insert (GHashTable * h, gpointer key, gpointer value)
+{
+  HNode ** n = hash_find (h, key);
+  if (!*n) {
+    *n = g_malloc0 (sizeof (HNode));
+    (*n)->key = key;
+  }
+  (*n)->value = value;
+}
+
+gpointer g_hash_table_lookup (GHashTable * h, gconstpointer key)
+{
+  HNode ** n = hash_find (h, key);
+  return *n ? (*n)->value : NULL;
+}
+
+gboolean g_hash_table_remove (GHashTable * h, gconstpointer key)
+{
+  HNode ** n = hash_find (h, key);
+  if (*n) {
+    HNode * dead = *n;
+    *n = dead->next;
+    free (dead);
+    return TRUE;
+  }
+  return FALSE;
+}
+
 /* ------------------------------------------------------------------ */
 /* GTS 0.7.6 object system (restated: src/object.c)                     */
 
@@ -679,6 +740,12 @@ gdouble gfs_diffusion_cell (GfsDiffusion * d, FttCell * cell)
   return (* d->cell) (d, cell);
 }
 
+/* src/output.c, src/surface.c: parents of classes the module instantiates at load
+   (GfsOutputParticleList, GfsDropletToParticle ...); never used by the path */
+SIMPLE_CLASS (gfs_output_class, GfsOutputClass, "GfsOutput", GfsOutput, gfs_event_class ())
+SIMPLE_CLASS (gfs_output_particle_class, GfsOutputClass, "GfsOutputParticle", GfsOutput, gfs_output_class ())
+SIMPLE_CLASS (gfs_surface_class, GfsGenericSurfaceClass, "GfsSurface", GfsSurface, gts_object_class ())
+
 /* src/boundary.c: class skeletons */
 SIMPLE_CLASS (gfs_box_class, GfsBoxClass, "GfsBox", GfsBox, gts_slist_container_class ())
 SIMPLE_CLASS (gfs_boundary_class, GfsBoundaryClass, "GfsBoundary", GfsBoundary, gts_object_class ())
@@ -974,6 +1041,10 @@ REF_EXPORT RefSim * refobj_sim_new (int nbox, FttCell ** root, FttCell ** broot,
     domain->variables = g_slist_append (domain->variables, v);
   }
   s->sim.physical_params.L = 1.;
+  s->sim.solids = GTS_SLIST_CONTAINER (gts_container_new (GTS_CONTAINER_CLASS (gts_slist_container_class ())));
+  s->sim.events = GTS_SLIST_CONTAINER (gts_container_new (GTS_CONTAINER_CLASS (gts_slist_container_class ())));
+  s->sim.maps = GTS_SLIST_CONTAINER (gts_container_new (GTS_CONTAINER_CLASS (gts_slist_container_class ())));
+  domain->objects = g_hash_table_new (g_str_hash, g_str_equal);
   domain->lambda.x = domain->lambda.y = domain->lambda.z = 1.;
   s->sim.time.end = G_MAXDOUBLE;
   s->sim.time.iend = G_MAXINT;
@@ -1063,6 +1134,9 @@ REF_EXPORT void refobj_sim_destroy (RefSim * s)
   }
   g_free (s->var);
   g_slist_free (GFS_DOMAIN (s)->variables);
+  gts_object_destroy (GTS_OBJECT (s->sim.solids));
+  gts_object_destroy (GTS_OBJECT (s->sim.events));
+  gts_object_destroy (GTS_OBJECT (s->sim.maps));
   gts_object_destroy (GTS_OBJECT (s));
 }
 
@@ -1110,6 +1184,7 @@ REF_EXPORT GfsParticleList * refobj_list_new (RefSim * s, long n, const double *
 
   gfs_object_simulation_set (plist, s);
   le->name = g_strdup ("P");
+  g_hash_table_insert (GFS_DOMAIN (s)->objects, le->name, plist);     /* src/event.c:199-202 */
   gfs_event_set (le, -1., -1., -1., -1, -1, 1);
   l->klass = GTS_OBJECT_CLASS (gfs_particulate_class ());
   for (i = 0; i < n; i++) {
@@ -1165,8 +1240,6 @@ REF_EXPORT GfsParticleList * refobj_list_new (RefSim * s, long n, const double *
 
 REF_EXPORT void refobj_list_destroy (GfsParticleList * plist)
 {
-  g_free (GFS_EVENT (plist)->name);
-  GFS_EVENT (plist)->name = NULL;
   gts_object_destroy (GTS_OBJECT (plist));
 }
 
@@ -1328,6 +1401,35 @@ REF_EXPORT void refobj_source_event (RefSim * s, GfsParticleList * plist, int iv
 }
 
 REF_EXPORT long refobj_warnings (void) { return ref_warnings; }
+
+/* libgfsrefmod only: the drop-in module (gerris-fft-particles_b200/host/
+ * particulates_b200.c) is linked in; run the entry point GLib calls when
+ * Gerris g_module_open()s it (src/simulation.c:199-225).  Returns 1 when the
+ * module is present and its init reported success, 0 when this is the plain
+ * reference library. */
+const gchar * g_module_check_init (void) __attribute__((weak));
+extern const gchar gfs_module_name[] __attribute__((weak));
+
+REF_EXPORT int refobj_module_init (void)
+{
+  static int done = 0;
+  if (!g_module_check_init)
+    return 0;
+  if (!done) {
+    const gchar * err = g_module_check_init ();
+    if (err) {
+      fprintf (stderr, "refobj: module %s failed to initialise: %s\n", gfs_module_name, err);
+      return -1;
+    }
+    done = 1;
+  }
+  return 1;
+}
+
+REF_EXPORT const char * refobj_module_name (void)
+{
+  return g_module_check_init ? gfs_module_name : NULL;
+}
 
 /* called by the generated stubs */
 void refobj_unimplemented (const char * name)

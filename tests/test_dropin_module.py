@@ -1,0 +1,205 @@
+"""The drop-in boundary, executed: gerris-fft-particles_b200/host/particulates_b200.c
+-- the GModule source a Gerris installation would build -- linked with the
+reference's own object code (modules/particulatecommon.c, src/event.c, ...) and
+the GLib/GTS run-time of oracle/refobj/glue.c into oracle/_ref/libgfsrefmod*.so.
+
+Its g_module_check_init() is run exactly as GLib would on g_module_open
+(src/simulation.c:199-225); real GfsParticleList / GfsParticulateField /
+GfsSourceParticulate objects are then driven through gfs_event_do, once in this
+library (events routed to the B200 through the C-ABI: FttCell bridge -> flat
+tree -> CUDA) and once in libgfsrefobj (the unmodified reference), and the
+GtsObject state left behind is compared.
+"""
+import numpy as np
+import pytest
+
+import helpers
+from helpers import capi, worlds, ora
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not (ora.refobj_available(2, True) and ora.refobj_available(3, True)),
+                                 reason="oracle/_ref/libgfsrefmod*.so not built (make -C oracle)")]
+
+KEYS = ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")
+_cache = {}
+
+
+def setup(kind):
+    if kind not in _cache:
+        w = helpers.test_world(kind)
+        sim, ptrs = helpers.matched_oracle(w)
+        _cache[kind] = (w, sim, ptrs)
+    return _cache[kind]
+
+
+def run_list(sim, parts, par, steps, module, periodic_mask=0, before_step=None):
+    """states after each of `steps` list events, in the reference (module=False)
+    or with the drop-in module loaded (module=True).  One RefSim at a time: the
+    GfsBox objects hang on the shared root cells."""
+    rs = ora.RefSim(sim, periodic_mask, module=module)
+    rs.configure(par)
+    rl = ora.RefParticleList(rs, *[parts[k] for k in KEYS], par)
+    out = []
+    for step in range(steps):
+        if before_step:
+            before_step(step)
+        assert rl.event() == 1
+        out.append(rl.get())
+    rs.close()
+    return out
+
+
+def check(got, want, dim, rtol, what):
+    go, wo = np.argsort(got["id"]), np.argsort(want["id"])
+    assert np.array_equal(got["id"][go], want["id"][wo]), what
+    for keys in (("x", "y", "z")[:dim], ("vx", "vy", "vz")[:dim]):
+        g = {k: got[k][go] for k in keys}
+        w = {k: want[k][wo] for k in keys}
+        err = helpers.vec_rel_err(g, w, keys)
+        assert err <= rtol, (what, keys, err)
+    for k in ("fx", "fy", "fz")[:dim]:
+        scale = max(np.abs(want[k]).max(), 1e-300)
+        assert np.abs(got[k][go] - want[k][wo]).max() <= 1e-10 * scale, (what, k)
+    assert np.abs(got["mass"][go] - want["mass"][wo]).max() <= 1e-14 * np.abs(want["mass"]).max(), what
+
+
+@pytest.mark.parametrize("kind", ["c1", "uniform3", "ring3", "ring2", "ring3b", "chain2", "chain3"])
+def test_module_particle_list_event(kind):
+    """GfsParticleList.event re-pointed by the module: flatten the live FttCell
+    trees, mirror U,V,W, cull + fused step on the device, state written back into the
+    GfsParticulate objects, gfs_particle_bc on the host -- against the reference's own
+    gfs_particle_list_event over 3 steps"""
+    w, sim, ptrs = setup(kind)
+    parts = helpers.test_particles(w, 4000)
+    parts["x"][::97] = 5.0                      # a few particles outside: culled by both
+    par = helpers.oracle_params(w)
+    want = run_list(sim, parts, par, 3, module=False)
+    got = run_list(sim, parts, par, 3, module=True)
+    for step in range(3):
+        assert len(got[step]["x"]) == len(want[step]["x"]) < len(parts["x"])
+        check(got[step], want[step], w.dim, 1e-12 if step == 0 else 1e-11, (kind, step))
+
+
+@pytest.mark.parametrize("kind", ["c1", "ring3"])
+@pytest.mark.parametrize("forces,kw", [
+    ((ora.FORCE_INERTIAL, ora.FORCE_DRAG), {}),
+    ((ora.FORCE_ADDEDMASS, ora.FORCE_DRAG, ora.FORCE_BUOY), dict(cm_const=0.3)),
+    ((ora.FORCE_DRAG, ora.FORCE_LIFT), dict(cd_const=0.44, cl_const=0.25)),
+])
+def test_module_force_lists(kind, forces, kw):
+    """force-list wiring of the module (step_params): inertial / added-mass with the
+    Un,Vn,Wn upload and the reference's snapshot rule, constant coefficient functions"""
+    w, sim, ptrs = setup(kind)
+    a = w.arrays
+    rng = np.random.default_rng(21)
+    fields = [w.u, w.v] + ([w.w] if w.dim == 3 else [])
+    prev = [0.8 * f + 0.05 * rng.standard_normal(a.n_cells) for f in fields]
+    live = (a.flags & capi.CELL_DESTROYED) == 0
+
+    def reset_un(step):
+        if step == 0:
+            for c, f in enumerate(prev):
+                sim.set_values(5 + c, ptrs[live], f[live])
+
+    parts = helpers.test_particles(w, 2000)
+    par = ora.step_params(w.dt, list(forces), rho=w.rho, mu=w.mu, g=(0.1, -1.0, 0.0), ivar_uold=5, **kw)
+    want = run_list(sim, parts, par, 3, module=False, before_step=reset_un)
+    got = run_list(sim, parts, par, 3, module=True, before_step=reset_un)
+    for step in range(3):
+        check(got[step], want[step], w.dim, 1e-12 if step == 0 else 1e-11, (kind, forces, step))
+    if ora.FORCE_ADDEDMASS in forces:
+        assert np.all(got[2]["mass"] > parts["mass"])
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_module_periodic_run(dim):
+    """15 steps in a box with periodic and plain sides: device cull + step, the
+    reference's gfs_particle_bc on the host objects afterwards, by particle id"""
+    w, mask = helpers.periodic_world(dim)
+    sim, ptrs = helpers.matched_oracle(w)
+    rng = np.random.default_rng(9)
+    parts = worlds.make_particles(w)
+    n = len(parts["x"])
+    for k in ("x", "y", "z")[:dim]:
+        parts[k] = rng.uniform(-0.499, 0.499, n)
+    for k, f in zip(("vx", "vy", "vz")[:dim], (3.0, 3.0, 2.0)):
+        parts[k] = f * rng.standard_normal(n)
+    par = helpers.oracle_params(w)
+    want = run_list(sim, parts, par, 15, module=False, periodic_mask=mask)
+    got = run_list(sim, parts, par, 15, module=True, periodic_mask=mask)
+    assert len(want[-1]["x"]) < n
+    for step in range(15):
+        assert len(got[step]["x"]) == len(want[step]["x"]), step
+        check(got[step], want[step], dim, 1e-11, ("periodic", dim, step))
+
+
+@pytest.mark.parametrize("kind", ["c1", "ring3", "chain2"])
+def test_module_particulate_field_event(kind):
+    """GfsParticulateField.event re-pointed: void fraction deposited on the device and
+    scattered back into the cell variable (gfs_cell_reset + :1945-1953)"""
+    w, sim, ptrs = setup(kind)
+    a = w.arrays
+    parts = helpers.test_particles(w, 20000)
+    par = helpers.oracle_params(w)
+    live = (a.flags & capi.CELL_DESTROYED) == 0
+    leaves = live & (a.child0 < 0) & ((a.flags & capi.CELL_BOUNDARY) == 0)
+    res = []
+    for module in (False, True):
+        sim.set_values(3, ptrs[live], np.full(int(live.sum()), 7.0))      # must be reset by the event
+        rs = ora.RefSim(sim, module=module)
+        rs.configure(par)
+        rl = ora.RefParticleList(rs, *[parts[k] for k in KEYS], par)
+        rl.field_event(3)
+        res.append(sim.get_values(3, ptrs[leaves]))
+        # neither the reference nor the module touches ghost or non-leaf cells
+        assert np.all(sim.get_values(3, ptrs[live & ~leaves]) == 7.0)
+        rs.close()
+    want, got = res
+    assert want.max() > 0
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("kind,rk,kernel", [
+    ("c1", 0.06, (ora.KERNEL_GAUSSIAN, 1.0, 2e-4, 1)),
+    ("ring3", 0.04, (ora.KERNEL_COMPACT, 2.0, 1e-4, 2)),
+    ("ring2", 0.05, (ora.KERNEL_CONSTANT, 1.0, 0.0, 1)),
+])
+def test_module_source_particulate_event(kind, rk, kernel):
+    """GfsSourceParticulate.event re-pointed: the user's kernel GfsFunction is recognised
+    by probing (gfsb200_kernel_fit through gfs_function_spatial_value), the smoothed
+    force deposited on the device and scattered into <plist>_Fx,_Fy,_Fz; the on-fluid
+    force is left in particulate->force as the reference does (:2195-2201)"""
+    w, sim, ptrs = setup(kind)
+    a = w.arrays
+    parts = helpers.test_particles(w, 600)
+    par = helpers.oracle_params(w)
+    live = (a.flags & capi.CELL_DESTROYED) == 0
+    leaves = live & (a.child0 < 0) & ((a.flags & capi.CELL_BOUNDARY) == 0)
+    k = ora.Kernel(*kernel, 0)
+    res, forces = [], []
+    for module in (False, True):
+        for iv in range(4, 4 + w.dim):
+            sim.set_values(iv, ptrs[live], np.full(int(live.sum()), 3.0))
+        rs = ora.RefSim(sim, module=module)
+        rs.configure(par)
+        rl = ora.RefParticleList(rs, *[parts[q] for q in KEYS], par)
+        rl.source_event(4, rk, k)
+        res.append([sim.get_values(4 + c, ptrs[leaves]) for c in range(w.dim)])
+        forces.append(rl.get())
+        rs.close()
+    for c in range(w.dim):
+        want, got = res[0][c], res[1][c]
+        assert np.abs(want).max() > 0
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max(), c
+    for q in ("fx", "fy", "fz")[:w.dim]:
+        scale = max(np.abs(forces[0][q]).max(), 1e-300)
+        assert np.abs(forces[1][q] - forces[0][q]).max() <= 1e-10 * scale, q
+
+
+def test_module_counts_device_launches():
+    """the events above really ran on the device: the library's own launch counter moved"""
+    w, sim, ptrs = setup("ring3")
+    before = capi.kernel_launches()
+    parts = helpers.test_particles(w, 500)
+    run_list(sim, parts, helpers.oracle_params(w), 1, module=True)
+    assert capi.kernel_launches() > before

@@ -344,3 +344,34 @@ def test_reference_object_code_reproduces_golden(path):
         for k in ("x", "y", "vx", "vy", "fx", "fy"):
             assert np.array_equal(st[k], g[f"s{steps}_{k}"]), (steps, k)
     rs.close()
+
+
+@pytest.mark.skipif(not ora.refobj_available(3, module=True), reason="libgfsrefmod not built")
+def test_dropin_module_loads_and_hands_back_what_the_device_cannot_do():
+    """libgfsrefmod = the reference objects + the drop-in GModule source
+    (host/particulates_b200.c) linked as a Gerris installation would.  Its
+    g_module_check_init() instantiates the 16 classes and re-points the three
+    hot-path events.  A list whose density is a per-cell function is not
+    expressible on the device: the module must hand the event back to the
+    reference's own method, untouched -- checked here without a GPU against the
+    unmodified library."""
+    w, sim, ptrs = setup("ring3")
+    a = w.arrays
+    live = (a.flags & capi.CELL_DESTROYED) == 0
+    rng = np.random.default_rng(4)
+    sim.set_values(3, ptrs[live], rng.uniform(0.5, 2.0, int(live.sum())))
+    parts = helpers.test_particles(w, 800)
+    par = helpers.oracle_params(w, ivar_alpha=3)
+    states = []
+    for module in (True, False):               # one RefSim at a time: the GfsBox objects hang on the roots
+        rs = ora.RefSim(sim, module=module)
+        assert rs.R.refobj_module_name() == (b"particulates" if module else None)
+        rs.configure(par)
+        rl = ora.RefParticleList(rs, *[parts[k] for k in KEYS], par)
+        states.append([])
+        for step in range(2):
+            assert rl.event() == 1
+            states[-1].append(rl.get())
+        rs.close()
+    for step in range(2):
+        assert_same_state(states[0][step], states[1][step], 3, step)
