@@ -48,6 +48,8 @@ typedef struct {
   guint adapt_created, adapt_removed;   /* mesh-change signature, src/simulation.h:49-51 */
   gboolean tree_valid;
   gdouble * field[3];                   /* host staging of U,V,W in flat order */
+  gdouble * cellvar[2];                 /* host staging of per-cell alpha / viscosity, when they are variables */
+  GfsVariable * alpha_var, * mu_var;    /* PhysicalParams alpha = <variable>; GfsDiffusion.mu (src/source.c:941-946) */
   GfsVariable ** uold;                  /* GfsForceCoeff.Uold of an inertial / added-mass force, or NULL */
   gboolean snapshot;                    /* a GfsForceInertial is in the list: Un,Vn,Wn are refreshed after each event */
   gint32 n_cells;
@@ -96,6 +98,8 @@ static void b200_particle_list_destroy (GtsObject * o)
     if (s->ctx) gfsb200_ctx_destroy (s->ctx);
     for (c = 0; c < 3; c++)
       g_free (s->field[c]);
+    g_free (s->cellvar[0]);
+    g_free (s->cellvar[1]);
     g_free (s);
   }
   (* reference_list_destroy) (o);
@@ -142,6 +146,8 @@ static void refresh_tree (B200State * s, GfsSimulation * sim)
   s->n_cells = gfsb200_ftt_map_size (s->map);
   for (c = 0; c < FTT_DIMENSION; c++)
     s->field[c] = g_realloc (s->field[c], sizeof (gdouble)*s->n_cells);
+  for (c = 0; c < 2; c++)
+    s->cellvar[c] = g_realloc (s->cellvar[c], sizeof (gdouble)*s->n_cells);
   s->adapt_created = sim->adapts_stats.created;
   s->adapt_removed = sim->adapts_stats.removed;
   s->tree_valid = TRUE;
@@ -155,8 +161,13 @@ static void mirror_velocity (B200State * s, GfsDomain * domain)
   FttComponent c;
   for (c = 0; c < FTT_DIMENSION; c++)
     gfsb200_ftt_gather (s->map, offsetof (GfsStateVector, place_holder), u[c]->i, GFS_NODATA, s->field[c]);
+  /* per-cell fluid density 1/alpha (:534-535) and viscosity (gfs_diffusion_cell, :540-541) */
+  if (s->alpha_var)
+    gfsb200_ftt_gather (s->map, offsetof (GfsStateVector, place_holder), s->alpha_var->i, 1., s->cellvar[0]);
+  if (s->mu_var)
+    gfsb200_ftt_gather (s->map, offsetof (GfsStateVector, place_holder), s->mu_var->i, 0., s->cellvar[1]);
   if (gfsb200_upload_field (s->ctx, s->field[0], s->field[1], FTT_DIMENSION > 2 ? s->field[2] : NULL,
-			    NULL, NULL) != GFSB200_OK)
+			    s->alpha_var ? s->cellvar[0] : NULL, s->mu_var ? s->cellvar[1] : NULL) != GFSB200_OK)
     g_error ("particulates (B200): %s", gfsb200_last_error ());
   if (s->uold) {                          /* Un,Vn,Wn of GfsForceInertial / GfsForceAddedMass */
     for (c = 0; c < FTT_DIMENSION; c++)
@@ -202,7 +213,24 @@ static GfsSourceDiffusion * viscosity_source (GfsVariable * v)
 
 /* fills *p; returns FALSE if the list needs something only the reference
  * CPU path implements */
-static gboolean step_params (GfsParticleList * plist, GfsSimulation * sim, gfsb200_step_params * p)
+typedef struct {
+  GfsVariable ** uold;                  /* -> B200State.uold */
+  gboolean snapshot;
+  GfsVariable * alpha_var, * mu_var;
+} ListVars;
+
+static void adopt (B200State * s, const ListVars * lv)
+{
+  s->uold = lv->uold;
+  s->snapshot = lv->snapshot;
+  s->alpha_var = lv->alpha_var;
+  s->mu_var = lv->mu_var;
+}
+
+/* (reads the objects only: no device context is created for a list that ends up
+   on the reference path) */
+static gboolean step_params (GfsParticleList * plist, GfsSimulation * sim, gfsb200_step_params * p,
+			     ListVars * lv)
 {
   GfsDomain * domain = GFS_DOMAIN (sim);
   GfsVariable ** u = gfs_domain_velocity (domain);
@@ -210,6 +238,7 @@ static gboolean step_params (GfsParticleList * plist, GfsSimulation * sim, gfsb2
   FttComponent c;
 
   gfsb200_step_params_default (p);
+  memset (lv, 0, sizeof (ListVars));
   p->dt = sim->advection_params.dt;
   while (i) {
     GfsForceCoeff * coeff = GFS_IS_FORCE_COEFF (i->data) ? FORCE_COEFF (i->data) : NULL;
@@ -223,12 +252,12 @@ static gboolean step_params (GfsParticleList * plist, GfsSimulation * sim, gfsb2
     else if (GFS_IS_FORCE_ADDEDMASS (i->data)) {
       p->force[p->n_forces++] = GFSB200_FORCE_ADDEDMASS;
       if (coeff->coefficient) p->cm_const = k;
-      state_of (plist)->uold = coeff->Uold;
+      lv->uold = coeff->Uold;
     }
     else if (GFS_IS_FORCE_INERTIAL (i->data)) {
       p->force[p->n_forces++] = GFSB200_FORCE_INERTIAL;
-      state_of (plist)->uold = coeff->Uold;
-      state_of (plist)->snapshot = TRUE;
+      lv->uold = coeff->Uold;
+      lv->snapshot = TRUE;
     }
     else if (GFS_IS_FORCE_LIFT (i->data)) {
       p->force[p->n_forces++] = GFSB200_FORCE_LIFT;
@@ -243,18 +272,27 @@ static gboolean step_params (GfsParticleList * plist, GfsSimulation * sim, gfsb2
   /* fluid density 1/alpha (particulatecommon.c:534-535) */
   if (sim->physical_params.alpha) {
     gdouble a = gfs_function_get_constant_value (sim->physical_params.alpha);
-    if (a == G_MAXDOUBLE)
-      return FALSE;                       /* variable density: per-cell alpha array, not wired yet */
-    p->rho = 1./a;
+    if (a == G_MAXDOUBLE) {
+      /* alpha = <a cell variable>: mirrored per cell; any other expression stays on the host */
+      GfsVariable * v = gfs_function_get_variable (sim->physical_params.alpha);
+      if (v == NULL)
+	return FALSE;
+      lv->alpha_var = v;
+    }
+    else
+      p->rho = 1./a;
   }
-  /* viscosity of the GfsSourceDiffusion on U (particulatecommon.c:540-541) */
+  /* viscosity of the GfsSourceDiffusion on U (particulatecommon.c:540-541): the per-cell
+     variable GfsDiffusion keeps when its function is not a constant, else the constant */
   {
     GfsSourceDiffusion * d = viscosity_source (u[0]);
     if (d) {
-      gdouble mu = gfs_function_get_constant_value (d->D->val);
-      if (mu == G_MAXDOUBLE)
-	return FALSE;
-      p->mu = mu;
+      if (d->D->mu)
+	lv->mu_var = d->D->mu;
+      else {
+	gdouble mu = gfs_function_get_constant_value (d->D->val);
+	p->mu = mu < G_MAXDOUBLE ? mu : 0.;                  /* diffusion_cell, src/source.c:941-946 */
+      }
     }
   }
   /* g = sum of the GfsSource intensities on U,V,W (particulatecommon.c:634-649) */
@@ -350,10 +388,11 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
 {
   GfsParticleList * plist = GFS_PARTICLE_LIST (event);
   gfsb200_step_params par;
+  ListVars lv;
   B200State * s;
   gint64 removed = 0;
 
-  if (!step_params (plist, sim, &par) || sim->solids->items != NULL)
+  if (sim->solids->items != NULL || !step_params (plist, sim, &par, &lv))
     return (* reference_list_event) (event, sim);            /* not expressible on the device */
 
   /* the timing gate of gfs_event_list_event (src/event.c:2430-2439) */
@@ -361,6 +400,7 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
     return FALSE;
 
   s = state_of (plist);
+  adopt (s, &lv);
   refresh_tree (s, sim);
   mirror_velocity (s, GFS_DOMAIN (sim));
   /* Host objects are authoritative between steps in this first binding
@@ -393,14 +433,16 @@ static gboolean b200_particulate_field_event (GfsEvent * event, GfsSimulation * 
   GfsVariable * v = GFS_VARIABLE (event);
   GfsParticulateField * pfield = GFS_PARTICULATE_FIELD (v);
   gfsb200_step_params par;
+  ListVars lv;
   B200State * s;
   gdouble * out;
 
-  if (!step_params (pfield->plist, sim, &par))
+  if (sim->solids->items != NULL || !step_params (pfield->plist, sim, &par, &lv))
     return (* reference_field_event) (event, sim);
   if (!(* GFS_EVENT_CLASS (gfs_variable_class ())->event) (event, sim))
     return FALSE;
   s = state_of (pfield->plist);
+  adopt (s, &lv);
   refresh_tree (s, sim);
   upload_particles (s, pfield->plist);
   if (gfsb200_deposit_volume (s->ctx) != GFSB200_OK)
@@ -430,6 +472,7 @@ static gboolean b200_source_particulate_event (GfsEvent * event, GfsSimulation *
      class getter that does not exist; a plain cast is what it expands to) */
   GfsSourceParticulate * sp = (GfsSourceParticulate *) event;
   gfsb200_step_params par;
+  ListVars lv;
   gfsb200_kernel kernel;
   B200State * s;
   gdouble * out, * force[3];
@@ -437,7 +480,7 @@ static gboolean b200_source_particulate_event (GfsEvent * event, GfsSimulation *
   GSList * i;
   FttComponent c;
 
-  if (!step_params (sp->plist, sim, &par) || sim->solids->items != NULL ||
+  if (sim->solids->items != NULL || !step_params (sp->plist, sim, &par, &lv) ||
       gfsb200_kernel_fit (kernel_trampoline, sp->kernel_function, FTT_DIMENSION, &kernel) != GFSB200_OK)
     return (* reference_source_event) (event, sim);
   /* the timing gate of the parent class (:2180-2181) */
@@ -446,6 +489,7 @@ static gboolean b200_source_particulate_event (GfsEvent * event, GfsSimulation *
     return FALSE;
 
   s = state_of (sp->plist);
+  adopt (s, &lv);
   refresh_tree (s, sim);
   mirror_velocity (s, GFS_DOMAIN (sim));
   n = upload_particles (s, sp->plist);

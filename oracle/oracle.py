@@ -319,6 +319,7 @@ def load_refobj(dim: int, module: bool = False) -> C.CDLL:
         "refobj_sim_configure": (None, [vp, C.POINTER(StepParams), i32]),
         "refobj_sim_destroy": (None, [vp]),
         "refobj_sim_time": (None, [vp, C.POINTER(dbl), C.POINTER(i32)]),
+        "refobj_sim_add_solid": (None, [vp]),
         "refobj_list_new": (vp, [vp, lng] + [vp] * 8 + [C.POINTER(StepParams)]),
         "refobj_list_destroy": (None, [vp]),
         "refobj_list_size": (lng, [vp]),
@@ -370,6 +371,10 @@ class RefSim:
         """PhysicalParams alpha, SourceViscosity, Source g, dt -- what the .gfs
         file declares around the list"""
         self.R.refobj_sim_configure(self.h, C.byref(params), int(timers))
+
+    def add_solid(self):
+        """an entry in sim->solids, as a GfsSolid declaration leaves"""
+        self.R.refobj_sim_add_solid(self.h)
 
     def time(self):
         t, i = C.c_double(), C.c_int()

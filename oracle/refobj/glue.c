@@ -672,6 +672,13 @@ gdouble gfs_function_spatial_value (GfsFunction * f, const FttVector * p)
   return f->spatial ? (* f->spatial) (p->x, p->y, p->z, f->data) : f->val;
 }
 
+/* src/utils.c:1394-1399 */
+GfsVariable * gfs_function_get_variable (GfsFunction * f)
+{
+  g_return_val_if_fail (f != NULL, NULL);
+  return f->v;
+}
+
 gdouble gfs_function_get_constant_value (GfsFunction * f)
 {
   return f->v || f->spatial ? G_MAXDOUBLE : f->val;
@@ -1134,10 +1141,19 @@ REF_EXPORT void refobj_sim_destroy (RefSim * s)
   }
   g_free (s->var);
   g_slist_free (GFS_DOMAIN (s)->variables);
+  gts_container_foreach (GTS_CONTAINER (s->sim.solids), (GtsFunc) gts_object_destroy, NULL);
   gts_object_destroy (GTS_OBJECT (s->sim.solids));
   gts_object_destroy (GTS_OBJECT (s->sim.events));
   gts_object_destroy (GTS_OBJECT (s->sim.maps));
   gts_object_destroy (GTS_OBJECT (s));
+}
+
+/* declares a GfsSolid in the simulation (an entry in sim->solids is all the
+   module looks at before handing the events back to the reference) */
+REF_EXPORT void refobj_sim_add_solid (RefSim * s)
+{
+  gts_container_add (GTS_CONTAINER (s->sim.solids),
+		     GTS_CONTAINEE (gts_object_new (GTS_OBJECT_CLASS (gts_slist_containee_class ()))));
 }
 
 REF_EXPORT void refobj_sim_time (RefSim * s, double * t, int * i)

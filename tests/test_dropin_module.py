@@ -111,6 +111,24 @@ def test_module_force_lists(kind, forces, kw):
         assert np.all(got[2]["mass"] > parts["mass"])
 
 
+@pytest.mark.parametrize("kind", ["ring2", "uniform3"])
+def test_module_per_cell_alpha_and_viscosity(kind):
+    """PhysicalParams alpha = <variable> and a variable viscosity (GfsDiffusion.mu) are
+    gathered per cell and mirrored with the velocity"""
+    w, sim, ptrs = setup(kind)
+    a = w.arrays
+    live = (a.flags & capi.CELL_DESTROYED) == 0
+    rng = np.random.default_rng(4)
+    sim.set_values(3, ptrs[live], rng.uniform(0.5, 2.0, int(live.sum())))
+    sim.set_values(4, ptrs[live], rng.uniform(5e-4, 2e-3, int(live.sum())))
+    parts = helpers.test_particles(w, 3000)
+    par = helpers.oracle_params(w, ivar_alpha=3, ivar_mu=4)
+    want = run_list(sim, parts, par, 2, module=False)
+    got = run_list(sim, parts, par, 2, module=True)
+    for step in range(2):
+        check(got[step], want[step], w.dim, 1e-12 if step == 0 else 1e-11, (kind, step))
+
+
 @pytest.mark.parametrize("dim", [2, 3])
 def test_module_periodic_run(dim):
     """15 steps in a box with periodic and plain sides: device cull + step, the

@@ -351,22 +351,19 @@ def test_dropin_module_loads_and_hands_back_what_the_device_cannot_do():
     """libgfsrefmod = the reference objects + the drop-in GModule source
     (host/particulates_b200.c) linked as a Gerris installation would.  Its
     g_module_check_init() instantiates the 16 classes and re-points the three
-    hot-path events.  A list whose density is a per-cell function is not
+    hot-path events.  A simulation that declares solid boundaries is not
     expressible on the device: the module must hand the event back to the
     reference's own method, untouched -- checked here without a GPU against the
     unmodified library."""
     w, sim, ptrs = setup("ring3")
-    a = w.arrays
-    live = (a.flags & capi.CELL_DESTROYED) == 0
-    rng = np.random.default_rng(4)
-    sim.set_values(3, ptrs[live], rng.uniform(0.5, 2.0, int(live.sum())))
     parts = helpers.test_particles(w, 800)
-    par = helpers.oracle_params(w, ivar_alpha=3)
+    par = helpers.oracle_params(w)
     states = []
     for module in (True, False):               # one RefSim at a time: the GfsBox objects hang on the roots
         rs = ora.RefSim(sim, module=module)
         assert rs.R.refobj_module_name() == (b"particulates" if module else None)
         rs.configure(par)
+        rs.add_solid()
         rl = ora.RefParticleList(rs, *[parts[k] for k in KEYS], par)
         states.append([])
         for step in range(2):
