@@ -118,6 +118,7 @@ def lib() -> C.CDLL:
         "gfsb200_step_host": (i32, [vp, C.POINTER(StepParamsC), i64] + [vp] * 8 + [i64]),
         "gfsb200_particles_cull": (i32, [vp, C.POINTER(i64)]),
         "gfsb200_particle_bc": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
+        "gfsb200_escaped_count": (i32, [vp, C.POINTER(i64)]),
         "gfsb200_particles_sort": (i32, [vp]),
         "gfsb200_locate": (i32, [vp, i64, vp, vp, vp, vp]),
         "gfsb200_interpolate": (i32, [vp, i64, vp, vp, vp, vp, vp, vp]),
@@ -447,6 +448,12 @@ class Context:
         removed = C.c_int64(0)
         _check(self._lib.gfsb200_particles_cull(self.handle, C.byref(removed)), "particles_cull")
         return removed.value
+
+    def escaped_count(self):
+        """particles that left the domain during the last step issued with track_escapes"""
+        n = C.c_int64(0)
+        _check(self._lib.gfsb200_escaped_count(self.handle, C.byref(n)), "escaped_count")
+        return int(n.value)
 
     def particle_bc(self):
         """(wrapped, dropped) of gfs_particle_bc after a step with track_escapes"""

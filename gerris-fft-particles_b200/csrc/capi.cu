@@ -1004,6 +1004,20 @@ extern "C" int gfsb200_particle_bc (gfsb200_ctx * c, int64_t * n_wrapped, int64_
   return apply_permutation (c, P.n - counts[2]);
 }
 
+extern "C" int gfsb200_escaped_count (gfsb200_ctx * c, int64_t * n_escaped)
+{
+  if (!c || !n_escaped) return gfsb200_fail (GFSB200_ERR_ARG, "escaped_count: bad argument");
+  *n_escaped = 0;
+  if (!c->esc_armed)
+    return gfsb200_fail (GFSB200_ERR_STATE, "escaped_count: the last step did not track escapes");
+  CK (cudaSetDevice (c->device));
+  int n = 0;
+  CK (cudaMemcpyAsync (&n, c->esc_count, sizeof (int), cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  *n_escaped = n;
+  return GFSB200_OK;
+}
+
 extern "C" int gfsb200_particle_list_event (gfsb200_ctx * c, const gfsb200_step_params * p,
 					    int64_t * n_removed)
 {

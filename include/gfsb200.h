@@ -257,6 +257,12 @@ int gfsb200_particles_cull (gfsb200_ctx * c, int64_t * n_removed);
  * (periodic_bc_particle :3189-3214), any other is dropped from the list.
  * Unlike the reference, wrapped particles keep their place in the list. */
 int gfsb200_particle_bc (gfsb200_ctx * c, int64_t * n_wrapped, int64_t * n_dropped);
+/* How many particles left the domain (gfs_domain_locate == NULL at their new position)
+ * during the last gfsb200_step issued with track_escapes = 1.  A caller that keeps
+ * gfs_particle_bc on the host (modules/particulatecommon.c:3375-3395: one gfs_domain_locate
+ * per particle, every step) can skip it when this is 0 -- the reference function would find
+ * nothing to do.  Does not consume the record: gfsb200_particle_bc may still follow. */
+int gfsb200_escaped_count (gfsb200_ctx * c, int64_t * n_escaped);
 /* re-sort resident particles by containing cell (Morton-ordered flat index)
  * so that neighbouring threads gather neighbouring cells */
 int gfsb200_particles_sort (gfsb200_ctx * c);

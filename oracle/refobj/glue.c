@@ -1214,7 +1214,10 @@ REF_EXPORT GfsParticleList * refobj_list_new (RefSim * s, long n, const double *
     pa->vel.x = vx[i]; pa->vel.y = vy[i]; pa->vel.z = vz ? vz[i] : 0.;
     pa->mass = mass[i];
     pa->volume = volume[i];
-    gts_container_add (GTS_CONTAINER (l->list), GTS_CONTAINEE (o));
+    /* gts_container_add (l->list, o) without its O(n) "already there?" search (the
+       object is new): prepend + the containee's add_container, as slist_container_add does */
+    l->list->items = g_slist_prepend (l->list->items, o);
+    container_add (GTS_CONTAINER (l->list), GTS_CONTAINEE (o));
   }
   l->list->items = g_slist_reverse (l->list->items);
   for (it = l->list->items; it; it = it->next)

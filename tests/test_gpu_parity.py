@@ -689,6 +689,28 @@ def test_inertial_needs_the_previous_field():
 _periodic_world = helpers.periodic_world
 
 
+def test_escaped_count_matches_host_locate(ctx):
+    """gfsb200_escaped_count = number of particles whose new position gfs_domain_locate
+    rejects, which is what gfs_particle_bc would find one locate at a time"""
+    w, sim, ptrs, idx = setup("ring3", ctx)
+    rng = np.random.default_rng(17)
+    parts = worlds.make_particles(w, 6000)
+    n = len(parts["x"])
+    parts["x"] = rng.uniform(-0.499, 0.499, n)
+    for k, f in zip(("vx", "vy", "vz"), (4.0, 4.0, 4.0)):
+        parts[k] = f * rng.standard_normal(n)
+    ctx.particles_upload(**parts)
+    par = worlds.World(**{**w.__dict__, "dt": 2e-2}).step_params(track_escapes=True)
+    ctx.step(par)
+    got = ctx.particles_download()
+    outside = int((sim.locate(got["x"], got["y"], got["z"]) == 0).sum())
+    assert outside > 10
+    assert ctx.escaped_count() == outside
+    ctx.step(w.step_params())
+    with pytest.raises(capi.GfsB200Error):
+        ctx.escaped_count()                    # the last step did not track
+
+
 @pytest.mark.parametrize("dim", [2, 3])
 def test_periodic_wrap_and_drop(dim, ctx):
     """gfs_particle_list_event with gfs_particle_bc: cull, step, then wrap the
