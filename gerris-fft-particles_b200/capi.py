@@ -119,6 +119,8 @@ def lib() -> C.CDLL:
         "gfsb200_particles_cull": (i32, [vp, C.POINTER(i64)]),
         "gfsb200_particle_bc": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
         "gfsb200_escaped_count": (i32, [vp, C.POINTER(i64)]),
+        "gfsb200_host_alloc": (vp, [C.c_size_t]),
+        "gfsb200_host_free": (None, [vp]),
         "gfsb200_particles_sort": (i32, [vp]),
         "gfsb200_locate": (i32, [vp, i64, vp, vp, vp, vp]),
         "gfsb200_interpolate": (i32, [vp, i64, vp, vp, vp, vp, vp, vp]),

@@ -468,6 +468,22 @@ extern "C" int gfsb200_upload_field_prev (gfsb200_ctx * c, const double * un, co
   return GFSB200_OK;
 }
 
+extern "C" void * gfsb200_host_alloc (size_t bytes)
+{
+  void * p = NULL;
+  if (cudaMallocHost (&p, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError ();
+    gfsb200_fail (GFSB200_ERR_NOMEM, "host_alloc: cannot page-lock %zu bytes", bytes);
+    return NULL;
+  }
+  return p;
+}
+
+extern "C" void gfsb200_host_free (void * p)
+{
+  if (p) cudaFreeHost (p);
+}
+
 extern "C" int gfsb200_upload_field (gfsb200_ctx * c, const double * u, const double * v,
 				     const double * w, const double * alpha, const double * mu)
 {

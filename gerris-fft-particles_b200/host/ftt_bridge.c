@@ -145,10 +145,30 @@ int gfsb200_ftt_flatten (int n_roots, void * const * roots_, const int * is_box,
  * not need fluid.h/gts.h. */
 int gfsb200_ftt_gather (const gfsb200_ftt_map * m, size_t offset, int var, double nodata, double * out)
 {
+  return gfsb200_ftt_gather_many (m, offset, 1, &var, &nodata, &out);
+}
+
+/* one pass over the cells for all nvar variables: the cost is the pointer chase
+   cell -> data (one cache miss per cell), paid once instead of once per variable,
+   and spread over the host cores */
+int gfsb200_ftt_gather_many (const gfsb200_ftt_map * m, size_t offset, int nvar, const int * var,
+			     const double * nodata, double * const * out)
+{
+  if (!m || nvar < 0 || (nvar && (!var || !nodata || !out))) {
+    bridge_error = "gather: bad argument";
+    return GFSB200_ERR_ARG;
+  }
+#pragma omp parallel for schedule(static)
   for (int32_t i = 0; i < m->n_cells; i++) {
     FttCell * c = m->cell[i];
-    out[i] = (FTT_CELL_IS_DESTROYED (c) || !c->data) ? nodata :
-      ((const double *) ((const char *) c->data + offset))[var];
+    if (FTT_CELL_IS_DESTROYED (c) || !c->data)
+      for (int k = 0; k < nvar; k++)
+	out[k][i] = nodata[k];
+    else {
+      const double * v = (const double *) ((const char *) c->data + offset);
+      for (int k = 0; k < nvar; k++)
+	out[k][i] = v[var[k]];
+    }
   }
   return GFSB200_OK;
 }

@@ -33,6 +33,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stddef.h>
+#include <stdio.h>
+#include <time.h>
 #include <gfs.h>
 #include "particulatecommon.h"
 #include "gfsb200.h"
@@ -47,14 +49,31 @@ typedef struct {
   gfsb200_ftt_map * map;
   guint adapt_created, adapt_removed;   /* mesh-change signature, src/simulation.h:49-51 */
   gboolean tree_valid;
-  gdouble * field[3];                   /* host staging of U,V,W in flat order */
-  gdouble * cellvar[2];                 /* host staging of per-cell alpha / viscosity, when they are variables */
+  gdouble * field[3];                   /* page-locked staging of U,V,W in flat order */
+  gdouble * cellvar[2];                 /* page-locked staging of per-cell alpha / viscosity, when they are variables */
+  gint32 field_cap;                     /* cells the five buffers above hold */
+  GfsParticulate ** obj;                /* the list's objects in list order (rebuilt every event) */
+  gdouble * col[10];                    /* page-locked staging: x y z vx vy vz mass volume | fx fy fz mass on the way back */
+  guint32 * id;
+  gint64 part_cap;
   GfsVariable * alpha_var, * mu_var;    /* PhysicalParams alpha = <variable>; GfsDiffusion.mu (src/source.c:941-946) */
   GfsVariable ** uold;                  /* GfsForceCoeff.Uold of an inertial / added-mass force, or NULL */
   gboolean snapshot;                    /* a GfsForceInertial is in the list: Un,Vn,Wn are refreshed after each event */
   gint32 n_cells;
   gboolean (* reference_event) (GfsEvent *, GfsSimulation *);
+  /* $GFSB200_MODULE_PROFILE: seconds spent per phase of the list event, printed on destroy */
+  gdouble phase[6];
+  guint n_events;
 } B200State;
+
+enum { PH_TREE, PH_FIELD, PH_UPLOAD, PH_DEVICE, PH_DOWNLOAD, PH_BC };
+
+static gdouble wall (void)
+{
+  struct timespec t;
+  clock_gettime (CLOCK_MONOTONIC, &t);
+  return t.tv_sec + 1e-9*t.tv_nsec;
+}
 
 static GHashTable * b200_states = NULL;   /* GfsParticleList* -> B200State* */
 static gboolean (* reference_list_event) (GfsEvent *, GfsSimulation *) = NULL;
@@ -92,14 +111,25 @@ static void b200_particle_list_destroy (GtsObject * o)
   B200State * s = b200_states ? g_hash_table_lookup (b200_states, o) : NULL;
   if (s) {
     FttComponent c;
+    gint k;
     g_hash_table_remove (b200_states, o);
+    if (g_getenv ("GFSB200_MODULE_PROFILE") && s->n_events)
+      fprintf (stderr, "particulates (B200): %u list events; ms/event: tree %.3f, field gather+upload %.3f, "
+	       "particle upload %.3f, cull+step %.3f, particle download %.3f, gfs_particle_bc %.3f\n",
+	       s->n_events, 1e3*s->phase[PH_TREE]/s->n_events, 1e3*s->phase[PH_FIELD]/s->n_events,
+	       1e3*s->phase[PH_UPLOAD]/s->n_events, 1e3*s->phase[PH_DEVICE]/s->n_events,
+	       1e3*s->phase[PH_DOWNLOAD]/s->n_events, 1e3*s->phase[PH_BC]/s->n_events);
     if (s->map) gfsb200_ftt_map_free (s->map);
     if (s->tree) gfsb200_tree_free (s->tree);
     if (s->ctx) gfsb200_ctx_destroy (s->ctx);
     for (c = 0; c < 3; c++)
-      g_free (s->field[c]);
-    g_free (s->cellvar[0]);
-    g_free (s->cellvar[1]);
+      gfsb200_host_free (s->field[c]);
+    gfsb200_host_free (s->cellvar[0]);
+    gfsb200_host_free (s->cellvar[1]);
+    for (k = 0; k < 10; k++)
+      gfsb200_host_free (s->col[k]);
+    gfsb200_host_free (s->id);
+    g_free (s->obj);
     g_free (s);
   }
   (* reference_list_destroy) (o);
@@ -107,6 +137,14 @@ static void b200_particle_list_destroy (GtsObject * o)
 
 /* ------------------------------------------------------------------ */
 /* mesh: flatten after every adapt                                      */
+
+static gpointer pinned (gsize bytes)
+{
+  gpointer p = gfsb200_host_alloc (bytes);
+  if (!p)
+    g_error ("particulates (B200): %s", gfsb200_last_error ());
+  return p;
+}
 
 typedef struct { GPtrArray * roots; GArray * is_box; } RootList;
 
@@ -144,10 +182,17 @@ static void refresh_tree (B200State * s, GfsSimulation * sim)
       gfsb200_upload_tree (s->ctx, s->tree) != GFSB200_OK)
     g_error ("particulates (B200): %s", gfsb200_last_error ());
   s->n_cells = gfsb200_ftt_map_size (s->map);
-  for (c = 0; c < FTT_DIMENSION; c++)
-    s->field[c] = g_realloc (s->field[c], sizeof (gdouble)*s->n_cells);
-  for (c = 0; c < 2; c++)
-    s->cellvar[c] = g_realloc (s->cellvar[c], sizeof (gdouble)*s->n_cells);
+  if (s->n_cells > s->field_cap) {
+    for (c = 0; c < 3; c++) {
+      gfsb200_host_free (s->field[c]);
+      s->field[c] = pinned (sizeof (gdouble)*s->n_cells);
+    }
+    for (c = 0; c < 2; c++) {
+      gfsb200_host_free (s->cellvar[c]);
+      s->cellvar[c] = pinned (sizeof (gdouble)*s->n_cells);
+    }
+    s->field_cap = s->n_cells;
+  }
   s->adapt_created = sim->adapts_stats.created;
   s->adapt_removed = sim->adapts_stats.removed;
   s->tree_valid = TRUE;
@@ -158,21 +203,34 @@ static void refresh_tree (B200State * s, GfsSimulation * sim)
 static void mirror_velocity (B200State * s, GfsDomain * domain)
 {
   GfsVariable ** u = gfs_domain_velocity (domain);
+  const size_t off = offsetof (GfsStateVector, place_holder);
+  int var[5];
+  double nodata[5], * out[5];
+  int n = 0;
   FttComponent c;
-  for (c = 0; c < FTT_DIMENSION; c++)
-    gfsb200_ftt_gather (s->map, offsetof (GfsStateVector, place_holder), u[c]->i, GFS_NODATA, s->field[c]);
-  /* per-cell fluid density 1/alpha (:534-535) and viscosity (gfs_diffusion_cell, :540-541) */
-  if (s->alpha_var)
-    gfsb200_ftt_gather (s->map, offsetof (GfsStateVector, place_holder), s->alpha_var->i, 1., s->cellvar[0]);
-  if (s->mu_var)
-    gfsb200_ftt_gather (s->map, offsetof (GfsStateVector, place_holder), s->mu_var->i, 0., s->cellvar[1]);
+  /* U,V,W and, when they are variables, the per-cell alpha (fluid density 1/alpha, :534-535)
+     and viscosity (gfs_diffusion_cell, :540-541): ONE parallel pass over the cells */
+  for (c = 0; c < FTT_DIMENSION; c++) {
+    var[n] = u[c]->i; nodata[n] = GFS_NODATA; out[n++] = s->field[c];
+  }
+  if (s->alpha_var) {
+    var[n] = s->alpha_var->i; nodata[n] = 1.; out[n++] = s->cellvar[0];
+  }
+  if (s->mu_var) {
+    var[n] = s->mu_var->i; nodata[n] = 0.; out[n++] = s->cellvar[1];
+  }
+  gfsb200_ftt_gather_many (s->map, off, n, var, nodata, out);
   if (gfsb200_upload_field (s->ctx, s->field[0], s->field[1], FTT_DIMENSION > 2 ? s->field[2] : NULL,
 			    s->alpha_var ? s->cellvar[0] : NULL, s->mu_var ? s->cellvar[1] : NULL) != GFSB200_OK)
     g_error ("particulates (B200): %s", gfsb200_last_error ());
   if (s->uold) {                          /* Un,Vn,Wn of GfsForceInertial / GfsForceAddedMass */
-    for (c = 0; c < FTT_DIMENSION; c++)
-      gfsb200_ftt_gather (s->map, offsetof (GfsStateVector, place_holder), s->uold[c]->i, GFS_NODATA,
-			  s->field[c]);
+    for (c = 0; c < FTT_DIMENSION; c++) {
+      var[c] = s->uold[c]->i; nodata[c] = GFS_NODATA; out[c] = s->field[c];
+    }
+    /* the staging buffers are reused: the first upload must have left them */
+    if (gfsb200_ctx_synchronize (s->ctx) != GFSB200_OK)
+      g_error ("particulates (B200): %s", gfsb200_last_error ());
+    gfsb200_ftt_gather_many (s->map, off, FTT_DIMENSION, var, nodata, out);
     if (gfsb200_upload_field_prev (s->ctx, s->field[0], s->field[1],
 				   FTT_DIMENSION > 2 ? s->field[2] : NULL) != GFSB200_OK)
       g_error ("particulates (B200): %s", gfsb200_last_error ());
@@ -314,71 +372,88 @@ static gboolean step_params (GfsParticleList * plist, GfsSimulation * sim, gfsb2
 /* ------------------------------------------------------------------ */
 /* particle objects <-> device SoA                                      */
 
-static gint64 upload_particles (B200State * s, GfsParticleList * plist)
+/* the list's objects as an array, in list order; grows the page-locked columns */
+static gint64 collect_particles (B200State * s, GfsParticleList * plist)
 {
   GSList * i = GFS_EVENT_LIST (plist)->list->items;
   gint64 n = g_slist_length (i), k = 0;
-  gdouble * col[8];
-  guint32 * id = g_malloc (sizeof (guint32)*(n ? n : 1));
   gint c;
-  for (c = 0; c < 8; c++)
-    col[c] = g_malloc (sizeof (gdouble)*(n ? n : 1));
-  for (; i; i = i->next, k++) {
-    GfsParticle * p = GFS_PARTICLE (i->data);
-    GfsParticulate * q = GFS_PARTICULATE (i->data);
+  if (n > s->part_cap) {
+    gint64 cap = n + n/8 + 1024;
+    for (c = 0; c < 10; c++) {
+      gfsb200_host_free (s->col[c]);
+      s->col[c] = pinned (sizeof (gdouble)*cap);
+    }
+    gfsb200_host_free (s->id);
+    s->id = pinned (sizeof (guint32)*cap);
+    s->obj = g_realloc (s->obj, sizeof (GfsParticulate *)*cap);
+    s->part_cap = cap;
+  }
+  for (; i; i = i->next)
+    s->obj[k++] = i->data;
+  return n;
+}
+
+static gint64 upload_particles (B200State * s, GfsParticleList * plist)
+{
+  gint64 n = collect_particles (s, plist), k;
+  gdouble ** col = s->col;
+  /* the objects are scattered over the heap (one cache miss or two each): the gather is
+     spread over the host cores */
+#pragma omp parallel for schedule(static)
+  for (k = 0; k < n; k++) {
+    GfsParticle * p = GFS_PARTICLE (s->obj[k]);
+    GfsParticulate * q = s->obj[k];
     p->pos_old = p->pos;                                     /* :804-805 */
     col[0][k] = p->pos.x; col[1][k] = p->pos.y; col[2][k] = p->pos.z;
     col[3][k] = q->vel.x; col[4][k] = q->vel.y; col[5][k] = q->vel.z;
     col[6][k] = q->mass;  col[7][k] = q->volume;
-    id[k] = p->id;
+    s->id[k] = p->id;
   }
   if (gfsb200_particles_upload (s->ctx, n, col[0], col[1], FTT_DIMENSION > 2 ? col[2] : NULL,
 				col[3], col[4], FTT_DIMENSION > 2 ? col[5] : NULL,
-				col[6], col[7], id) != GFSB200_OK)
+				col[6], col[7], s->id) != GFSB200_OK)
     g_error ("particulates (B200): %s", gfsb200_last_error ());
-  for (c = 0; c < 8; c++) g_free (col[c]);
-  g_free (id);
   return n;
 }
 
-/* write the device state back into the GtsObjects; particles the device
- * culled (outside the domain) are removed from the list as
- * remove_particles_not_in_domain does (:955-969) */
-static void download_particles (B200State * s, GfsParticleList * plist)
+/* write the device state back into the GtsObjects (s->obj holds them in upload order,
+ * which the device keeps); particles the device culled (outside the domain) are removed
+ * from the list as remove_particles_not_in_domain does (:955-969) */
+static void download_particles (B200State * s, GfsParticleList * plist, gint64 n_up)
 {
-  gint64 n = gfsb200_particles_count (s->ctx), k = 0;
-  gdouble * col[10];
-  guint32 * id = g_malloc (sizeof (guint32)*(n ? n : 1));
-  gint c;
-  GSList * i = GFS_EVENT_LIST (plist)->list->items;
-  for (c = 0; c < 10; c++)
-    col[c] = g_malloc (sizeof (gdouble)*(n ? n : 1));
+  gint64 n = gfsb200_particles_count (s->ctx), k, j;
+  gdouble ** col = s->col;
   if (gfsb200_particles_download (s->ctx, col[0], col[1], FTT_DIMENSION > 2 ? col[2] : NULL,
 				  col[3], col[4], FTT_DIMENSION > 2 ? col[5] : NULL,
-				  col[6], col[7], col[8], col[9], NULL, id, NULL) != GFSB200_OK)
+				  col[6], col[7], col[8], col[9], NULL, s->id, NULL) != GFSB200_OK)
     g_error ("particulates (B200): %s", gfsb200_last_error ());
-  while (i) {
-    GSList * next = i->next;
-    GfsParticle * p = GFS_PARTICLE (i->data);
-    if (k < n && id[k] == p->id) {
-      GfsParticulate * q = GFS_PARTICULATE (i->data);
-      p->pos.x = col[0][k]; p->pos.y = col[1][k];
-      q->vel.x = col[3][k]; q->vel.y = col[4][k];
-      q->force.x = col[6][k]; q->force.y = col[7][k];
-      q->mass = col[9][k];                 /* GfsForceAddedMass updates it every step (:391) */
-#if !FTT_2D
-      p->pos.z = col[2][k]; q->vel.z = col[5][k]; q->force.z = col[8][k];
-#endif
-      k++;
+  if (n != n_up) {
+    /* culled on the device: drop the same objects from the list, order preserved */
+    for (k = 0, j = 0; k < n_up; k++) {
+      GfsParticle * p = GFS_PARTICLE (s->obj[k]);
+      if (j < n && s->id[j] == p->id)
+	s->obj[j++] = s->obj[k];
+      else {
+	gts_container_remove (GTS_CONTAINER (GFS_EVENT_LIST (plist)->list), GTS_CONTAINEE (p));
+	gts_object_destroy (GTS_OBJECT (p));
+      }
     }
-    else {                                 /* culled on the device: list order is preserved */
-      gts_container_remove (GTS_CONTAINER (GFS_EVENT_LIST (plist)->list), GTS_CONTAINEE (p));
-      gts_object_destroy (GTS_OBJECT (p));
-    }
-    i = next;
+    if (j != n)
+      g_error ("particulates (B200): the device list and the GfsParticleList disagree");
   }
-  for (c = 0; c < 10; c++) g_free (col[c]);
-  g_free (id);
+#pragma omp parallel for schedule(static)
+  for (k = 0; k < n; k++) {
+    GfsParticle * p = GFS_PARTICLE (s->obj[k]);
+    GfsParticulate * q = s->obj[k];
+    p->pos.x = col[0][k]; p->pos.y = col[1][k];
+    q->vel.x = col[3][k]; q->vel.y = col[4][k];
+    q->force.x = col[6][k]; q->force.y = col[7][k];
+    q->mass = col[9][k];                   /* GfsForceAddedMass updates it every step (:391) */
+#if !FTT_2D
+    p->pos.z = col[2][k]; q->vel.z = col[5][k]; q->force.z = col[8][k];
+#endif
+  }
 }
 
 /* ------------------------------------------------------------------ */
@@ -390,7 +465,9 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
   gfsb200_step_params par;
   ListVars lv;
   B200State * s;
-  gint64 removed = 0, escaped = 0;
+  gint64 removed = 0, escaped = 0, n_up;
+  gdouble t[7];
+  gint k;
 
   if (sim->solids->items != NULL || !step_params (plist, sim, &par, &lv))
     return (* reference_list_event) (event, sim);            /* not expressible on the device */
@@ -401,13 +478,17 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
 
   s = state_of (plist);
   adopt (s, &lv);
+  t[0] = wall ();
   refresh_tree (s, sim);
+  t[1] = wall ();
   mirror_velocity (s, GFS_DOMAIN (sim));
+  t[2] = wall ();
   /* Host objects are authoritative between steps in this first binding
      (FeedParticle, DropletToParticle, outputs and BCs all mutate them); a
      resident mode that skips the two copies when nothing on the host touched
      the list is the next step ("host object sync"). */
-  upload_particles (s, plist);
+  n_up = upload_particles (s, plist);
+  t[3] = wall ();
   par.record_forces = 1;
   /* cull + step on the device; the BCs stay on the host in this binding because
      gfs_particle_bc also ships particles to other MPI ranks (:3218-3244).  A
@@ -419,13 +500,19 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
       gfsb200_step (s->ctx, &par) != GFSB200_OK ||
       (par.track_escapes && gfsb200_escaped_count (s->ctx, &escaped) != GFSB200_OK))
     g_error ("particulates (B200): %s", gfsb200_last_error ());
-  download_particles (s, plist);
+  t[4] = wall ();
+  download_particles (s, plist, n_up);
+  t[5] = wall ();
 
   /* :993, host side as in the reference.  gfs_particle_bc spends one gfs_domain_locate per
      particle to find those that left the domain; the step kernel has already counted them,
      and when there are none the reference function has nothing to do. */
   if (!par.track_escapes || escaped > 0)
     gfs_particle_bc (plist);
+  t[6] = wall ();
+  for (k = 0; k < 6; k++)
+    s->phase[k] += t[k + 1] - t[k];
+  s->n_events++;
   /* :1003-1012: the reference refreshes Un,Vn,Wn only when the list holds a
      GfsForceInertial; a GfsForceAddedMass alone keeps the snapshot its read method
      took (verified against the reference's object code, tests/test_reference_objcode.py) */

@@ -163,6 +163,11 @@ void gfsb200_ctx_destroy (gfsb200_ctx * c);
 void * gfsb200_ctx_stream (gfsb200_ctx * c);
 int gfsb200_ctx_synchronize (gfsb200_ctx * c);
 
+/* Page-locked host staging buffers for a C host that has no CUDA headers (the GModule):
+ * copies from/to them run at full PCIe rate and asynchronously.  NULL on failure. */
+void * gfsb200_host_alloc (size_t bytes);
+void gfsb200_host_free (void * p);
+
 /* Upload the flattened tree + stencil tables; call again after each adapt. */
 int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t);
 

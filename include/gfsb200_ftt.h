@@ -39,6 +39,10 @@ void * const * gfsb200_ftt_map_cells (const gfsb200_ftt_map * m);
  * cells); offset = offsetof (GfsStateVector, place_holder). */
 int gfsb200_ftt_gather (const gfsb200_ftt_map * m, size_t offset, int var, double nodata,
 			double * out);
+/* the same for nvar variables in ONE pass over the cells, parallel over the host cores:
+ * out[k][i] = GFS_VALUEI (cell_i, var[k]), nodata[k] for destroyed cells */
+int gfsb200_ftt_gather_many (const gfsb200_ftt_map * m, size_t offset, int nvar, const int * var,
+			     const double * nodata, double * const * out);
 /* GFS_VALUEI (cell_i, var) = in[i]; leaves_only: only the leaves of the GfsBox trees, the
  * cells gfs_domain_cell_traverse (FTT_TRAVERSE_LEAFS) visits (ghost cells keep their value) */
 int gfsb200_ftt_scatter (const gfsb200_ftt_map * m, size_t offset, int var, int leaves_only,
