@@ -119,6 +119,7 @@ def lib() -> C.CDLL:
         "gfsb200_particles_cull": (i32, [vp, C.POINTER(i64)]),
         "gfsb200_particle_bc": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
         "gfsb200_escaped_count": (i32, [vp, C.POINTER(i64)]),
+        "gfsb200_escaped_download": (i32, [vp, i64, vp, vp, C.POINTER(i64)]),
         "gfsb200_host_alloc": (vp, [C.c_size_t]),
         "gfsb200_host_free": (None, [vp]),
         "gfsb200_particles_sort": (i32, [vp]),
@@ -450,6 +451,17 @@ class Context:
         removed = C.c_int64(0)
         _check(self._lib.gfsb200_particles_cull(self.handle, C.byref(removed)), "particles_cull")
         return removed.value
+
+    def escaped(self):
+        """(list indices, positions before the step [n,3]) of the particles that left the domain
+        during the last step issued with track_escapes"""
+        n = self.escaped_count()
+        idx = np.empty(max(n, 1), dtype=np.int32)
+        old = np.empty((max(n, 1), 3))
+        m = C.c_int64(0)
+        _check(self._lib.gfsb200_escaped_download(self.handle, n, _ptr(idx), _ptr(old), C.byref(m)),
+               "escaped_download")
+        return idx[:m.value], old[:m.value]
 
     def escaped_count(self):
         """particles that left the domain during the last step issued with track_escapes"""

@@ -1034,6 +1034,27 @@ extern "C" int gfsb200_escaped_count (gfsb200_ctx * c, int64_t * n_escaped)
   return GFSB200_OK;
 }
 
+extern "C" int gfsb200_escaped_download (gfsb200_ctx * c, int64_t cap, int32_t * idx, double * old_xyz,
+					  int64_t * n_out)
+{
+  if (!c || cap < 0 || !n_out || (cap && (!idx || !old_xyz)))
+    return gfsb200_fail (GFSB200_ERR_ARG, "escaped_download: bad argument");
+  int64_t n = 0;
+  int r = gfsb200_escaped_count (c, &n);
+  if (r) return r;
+  if (n > c->esc_cap)
+    return gfsb200_fail (GFSB200_ERR_STATE, "escaped_download: %lld particles left the domain in one step, "
+			 "more than the %d tracked (1/16 of the list)", (long long) n, c->esc_cap);
+  if (n > cap) n = cap;
+  if (n) {
+    CK (cudaMemcpyAsync (idx, c->esc_idx, n*sizeof (int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK (cudaMemcpyAsync (old_xyz, c->esc_old, 3*n*sizeof (double), cudaMemcpyDeviceToHost, c->stream));
+    CK (cudaStreamSynchronize (c->stream));
+  }
+  *n_out = n;
+  return GFSB200_OK;
+}
+
 extern "C" int gfsb200_particle_list_event (gfsb200_ctx * c, const gfsb200_step_params * p,
 					    int64_t * n_removed)
 {

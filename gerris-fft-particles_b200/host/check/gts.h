@@ -117,6 +117,7 @@ GHashTable * g_hash_table_new (GHashFunc hash, GEqualFunc equal);
 void g_hash_table_insert (GHashTable * h, gpointer key, gpointer value);
 gpointer g_hash_table_lookup (GHashTable * h, gconstpointer key);
 gboolean g_hash_table_remove (GHashTable * h, gconstpointer key);
+void g_hash_table_foreach (GHashTable * h, GHFunc func, gpointer data);
 typedef struct _GNode GNode;
 struct _GNode { gpointer data; GNode * next, * prev, * parent, * children; };
 typedef struct _GTimer GTimer;
@@ -219,6 +220,8 @@ typedef struct { GtsContainer c; GHashTable * items; gboolean frozen; } GtsHashC
 typedef struct { GtsContainerClass parent_class; } GtsHashContainerClass;
 typedef struct { GtsContainer c; GSList * items; gboolean frozen; } GtsSListContainer;
 typedef struct { GtsContainerClass parent_class; } GtsSListContainerClass;
+#define GTS_CONTAINEE_CLASS(klass) GTS_OBJECT_CLASS_CAST (klass, GtsContaineeClass, gts_containee_class ())
+#define GTS_CONTAINER_CLASS(klass) GTS_OBJECT_CLASS_CAST (klass, GtsContainerClass, gts_container_class ())
 #define GTS_CONTAINEE(obj) GTS_OBJECT_CAST (obj, GtsContainee, gts_containee_class ())
 #define GTS_CONTAINER(obj) GTS_OBJECT_CAST (obj, GtsContainer, gts_container_class ())
 #define GTS_SLIST_CONTAINER(obj) GTS_OBJECT_CAST (obj, GtsSListContainer, gts_slist_container_class ())

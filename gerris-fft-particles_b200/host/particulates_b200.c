@@ -58,6 +58,12 @@ typedef struct {
   gint64 part_cap, obj_cap;
   gint64 n_obj;                         /* objects in obj[] */
   gboolean list_known;                  /* obj[0..n_obj) IS the GSList: no add/remove since it was walked */
+  /* $GFSB200_RESIDENT=1: the device copy stays authoritative between events; the GtsObjects
+     are refreshed (sync_down) only when something on the host is about to look at them */
+  gboolean resident;
+  gboolean host_stale;                  /* the device holds newer particle state than the objects */
+  gboolean syncing;                     /* inside sync_down (its own removals must not recurse) */
+  GfsParticleList * plist;
   GfsVariable * alpha_var, * mu_var;    /* PhysicalParams alpha = <variable>; GfsDiffusion.mu (src/source.c:941-946) */
   GfsVariable ** uold;                  /* GfsForceCoeff.Uold of an inertial / added-mass force, or NULL */
   gboolean snapshot;                    /* a GfsForceInertial is in the list: Un,Vn,Wn are refreshed after each event */
@@ -99,10 +105,19 @@ static B200State * state_of (GfsParticleList * plist)
 #endif
     if (gfsb200_ctx_create (device, &s->ctx) != GFSB200_OK)
       g_error ("particulates (B200): %s", gfsb200_last_error ());   /* no CPU fallback */
+    s->plist = plist;
+    s->resident = g_getenv ("GFSB200_RESIDENT") && atoi (g_getenv ("GFSB200_RESIDENT")) != 0;
     g_hash_table_insert (b200_states, plist, s);
   }
   return s;
 }
+
+static B200State * peek_state (gpointer plist)
+{
+  return b200_states ? g_hash_table_lookup (b200_states, plist) : NULL;
+}
+
+static void sync_down (B200State * s);
 
 /* ------------------------------------------------------------------ */
 /* Walking the GSList of a large list is a serial pointer chase (25-40 ns per node)
@@ -121,8 +136,12 @@ static GtsSListContainerClass * watched_container_class (void);
 static void watched_changed (GtsContainer * c)
 {
   B200State * s = b200_watched ? g_hash_table_lookup (b200_watched, c) : NULL;
-  if (s)
+  if (s) {
+    /* resident mode: bring the objects up to date while obj[] still describes the list */
+    if (s->host_stale && !s->syncing)
+      sync_down (s);
     s->list_known = FALSE;
+  }
 }
 
 static void watched_add (GtsContainer * c, GtsContainee * item)
@@ -549,6 +568,80 @@ static void download_particles (B200State * s, GfsParticleList * plist, gint64 n
   }
 }
 
+/* resident mode: refresh the GtsObjects from the device (positions, velocities, forces,
+ * mass; pos_old is NOT maintained between syncs -- only gfs_particle_bc reads it, and the
+ * event patches it for the particles concerned) */
+static void sync_down (B200State * s)
+{
+  if (!s->host_stale)
+    return;
+  s->syncing = TRUE;
+  download_particles (s, s->plist, s->n_obj);
+  s->syncing = FALSE;
+  s->host_stale = FALSE;
+}
+
+static void sync_one (gpointer key, gpointer value, gpointer data)
+{
+  sync_down (value);
+}
+
+static void sync_all (void)
+{
+  if (b200_states)
+    g_hash_table_foreach (b200_states, sync_one, NULL);
+}
+
+/* For host code outside this module that reads GfsParticulate objects of a list driven in
+ * resident mode (another GModule, a user event): call this first. */
+void gfsb200_module_sync (GfsParticleList * plist);
+void gfsb200_module_sync (GfsParticleList * plist)
+{
+  B200State * s = peek_state (plist);
+  if (s)
+    sync_down (s);
+}
+
+/* make sure the device holds the list's current state; returns the number of particles */
+static gint64 device_current (B200State * s, GfsParticleList * plist)
+{
+  watch_list (s, plist);
+  if (s->resident && s->host_stale && s->list_known)
+    return s->n_obj;                      /* nothing on the host has changed since the last step */
+  if (s->host_stale)
+    sync_down (s);
+  return upload_particles (s, plist);
+}
+
+/* the reference's own readers and writers of particle objects (every class of
+ * particulatecommon.c that looks at a list it does not own): objects first */
+#define N_READERS 6
+static gboolean (* reader_event[N_READERS]) (GfsEvent *, GfsSimulation *);
+static GfsEventClass * reader_class[N_READERS];
+static void (* reference_list_write) (GtsObject *, FILE *) = NULL;
+
+static gboolean synced_reader_event (GfsEvent * event, GfsSimulation * sim)
+{
+  GtsObjectClass * klass = GTS_OBJECT (event)->klass;
+  gint k;
+  sync_all ();
+  /* the method of the nearest wrapped ancestor */
+  for (; klass; klass = klass->parent_class)
+    for (k = 0; k < N_READERS; k++)
+      if (klass == GTS_OBJECT_CLASS (reader_class[k]))
+	return (* reader_event[k]) (event, sim);
+  g_assert_not_reached ();
+  return FALSE;
+}
+
+static void b200_particle_list_write (GtsObject * o, FILE * fp)
+{
+  B200State * s = peek_state (o);
+  if (s)
+    sync_down (s);
+  (* reference_list_write) (o, fp);
+}
+
 /* ------------------------------------------------------------------ */
 /* the replaced event methods                                           */
 
@@ -562,8 +655,10 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
   gdouble t[7];
   gint k;
 
-  if (sim->solids->items != NULL || !step_params (plist, sim, &par, &lv))
+  if (sim->solids->items != NULL || !step_params (plist, sim, &par, &lv)) {
+    gfsb200_module_sync (plist);
     return (* reference_list_event) (event, sim);            /* not expressible on the device */
+  }
 
   /* the timing gate of gfs_event_list_event (src/event.c:2430-2439) */
   if (!(* GFS_EVENT_CLASS (gfs_event_class ())->event) (event, sim))
@@ -580,7 +675,7 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
      (FeedParticle, DropletToParticle, outputs and BCs all mutate them); a
      resident mode that skips the two copies when nothing on the host touched
      the list is the next step ("host object sync"). */
-  n_up = upload_particles (s, plist);
+  n_up = device_current (s, plist);
   t[3] = wall ();
   par.record_forces = 1;
   /* cull + step on the device; the BCs stay on the host in this binding because
@@ -594,8 +689,31 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
       (par.track_escapes && gfsb200_escaped_count (s->ctx, &escaped) != GFSB200_OK))
     g_error ("particulates (B200): %s", gfsb200_last_error ());
   t[4] = wall ();
-  download_particles (s, plist, n_up);
-  t[5] = wall ();
+  if (s->resident && removed == 0 && escaped == 0 && s->list_known) {
+    /* nothing the host has to act on: the objects are refreshed when somebody asks */
+    s->host_stale = TRUE;
+    t[5] = wall ();
+  }
+  else {
+    s->host_stale = FALSE;
+    download_particles (s, plist, n_up);
+    t[5] = wall ();
+    if (s->resident && escaped > 0) {
+      /* pos_old of the particles gfs_particle_bc will walk back from (:3151-3186) */
+      gint64 cap = escaped, got = 0, e;
+      gint32 * idx = g_malloc (sizeof (gint32)*cap);
+      gdouble * old = g_malloc (sizeof (gdouble)*3*cap);
+      if (gfsb200_escaped_download (s->ctx, cap, idx, old, &got) != GFSB200_OK)
+	g_error ("particulates (B200): %s", gfsb200_last_error ());
+      for (e = 0; e < got; e++)
+	if (idx[e] >= 0 && idx[e] < s->n_obj) {
+	  GfsParticle * p = GFS_PARTICLE (s->obj[idx[e]]);
+	  p->pos_old.x = old[3*e]; p->pos_old.y = old[3*e + 1]; p->pos_old.z = old[3*e + 2];
+	}
+      g_free (idx);
+      g_free (old);
+    }
+  }
 
   /* :993, host side as in the reference.  gfs_particle_bc spends one gfs_domain_locate per
      particle to find those that left the domain; the step kernel has already counted them,
@@ -633,7 +751,7 @@ static gboolean b200_particulate_field_event (GfsEvent * event, GfsSimulation * 
   s = state_of (pfield->plist);
   adopt (s, &lv);
   refresh_tree (s, sim);
-  upload_particles (s, pfield->plist);
+  device_current (s, pfield->plist);
   if (gfsb200_deposit_volume (s->ctx) != GFSB200_OK)
     g_error ("particulates (B200): %s", gfsb200_last_error ());
   out = g_malloc (sizeof (gdouble)*s->n_cells);
@@ -681,7 +799,7 @@ static gboolean b200_source_particulate_event (GfsEvent * event, GfsSimulation *
   adopt (s, &lv);
   refresh_tree (s, sim);
   mirror_velocity (s, GFS_DOMAIN (sim));
-  n = upload_particles (s, sp->plist);
+  n = device_current (s, sp->plist);
   kernel.record_norm = 0;
   if (gfsb200_deposit_force_smoothed (s->ctx, &par, sp->rkernel, &kernel) != GFSB200_OK)
     g_error ("particulates (B200): %s", gfsb200_last_error ());
@@ -692,19 +810,22 @@ static gboolean b200_source_particulate_event (GfsEvent * event, GfsSimulation *
     gfsb200_ftt_scatter (s->map, offsetof (GfsStateVector, place_holder), sp->u[c]->i, TRUE, out);
   }
   g_free (out);
-  /* the reference leaves the on-fluid force in particulate->force (:2195-2201) */
-  for (c = 0; c < 3; c++)
-    force[c] = g_malloc (sizeof (gdouble)*(n ? n : 1));
-  if (gfsb200_particles_download (s->ctx, NULL, NULL, NULL, NULL, NULL, NULL, force[0], force[1], force[2],
-				  NULL, NULL, NULL, NULL) != GFSB200_OK)
-    g_error ("particulates (B200): %s", gfsb200_last_error ());
-  for (i = GFS_EVENT_LIST (sp->plist)->list->items; i && k < n; i = i->next, k++) {
-    GfsParticulate * q = GFS_PARTICULATE (i->data);
-    q->force.x = force[0][k]; q->force.y = force[1][k];
-    q->force.z = FTT_DIMENSION > 2 ? force[2][k] : 0.;
+  /* the reference leaves the on-fluid force in particulate->force (:2195-2201); in resident
+     mode with stale objects the device keeps it and the next sync_down delivers it */
+  if (!state_of (sp->plist)->host_stale) {
+    for (c = 0; c < 3; c++)
+      force[c] = g_malloc (sizeof (gdouble)*(n ? n : 1));
+    if (gfsb200_particles_download (s->ctx, NULL, NULL, NULL, NULL, NULL, NULL, force[0], force[1], force[2],
+  				  NULL, NULL, NULL, NULL) != GFSB200_OK)
+      g_error ("particulates (B200): %s", gfsb200_last_error ());
+    for (i = GFS_EVENT_LIST (sp->plist)->list->items; i && k < n; i = i->next, k++) {
+      GfsParticulate * q = GFS_PARTICULATE (i->data);
+      q->force.x = force[0][k]; q->force.y = force[1][k];
+      q->force.z = FTT_DIMENSION > 2 ? force[2][k] : 0.;
+    }
+    for (c = 0; c < 3; c++)
+      g_free (force[c]);
   }
-  for (c = 0; c < 3; c++)
-    g_free (force[c]);
   return TRUE;
 }
 
@@ -737,6 +858,23 @@ const gchar * g_module_check_init (void)
   /* ... then route the hot-path events to the device */
   reference_list_event = GFS_EVENT_CLASS (gfs_particle_list_class ())->event;
   GFS_EVENT_CLASS (gfs_particle_list_class ())->event = b200_particle_list_event;
+  /* ... and, for resident mode, bring the objects up to date before the reference's own
+     readers / writers of a list look at them */
+  {
+    GfsEventClass * readers[N_READERS] = {
+      GFS_EVENT_CLASS (gfs_droplet_to_particle_class ()), GFS_EVENT_CLASS (gfs_particle_to_droplet_class ()),
+      GFS_EVENT_CLASS (gfs_feed_particle_class ()), GFS_EVENT_CLASS (gfs_output_particle_list_class ()),
+      GFS_EVENT_CLASS (gfs_source_particulatevol_class ()), GFS_EVENT_CLASS (gfs_source_particulatemass_class ())
+    };
+    gint k;
+    for (k = 0; k < N_READERS; k++) {
+      reader_class[k] = readers[k];
+      reader_event[k] = readers[k]->event;
+      readers[k]->event = synced_reader_event;
+    }
+  }
+  reference_list_write = GTS_OBJECT_CLASS (gfs_particle_list_class ())->write;
+  GTS_OBJECT_CLASS (gfs_particle_list_class ())->write = b200_particle_list_write;
   reference_list_destroy = GTS_OBJECT_CLASS (gfs_particle_list_class ())->destroy;
   GTS_OBJECT_CLASS (gfs_particle_list_class ())->destroy = b200_particle_list_destroy;
   reference_field_event = GFS_EVENT_CLASS (gfs_particulate_field_class ())->event;

@@ -268,6 +268,12 @@ int gfsb200_particle_bc (gfsb200_ctx * c, int64_t * n_wrapped, int64_t * n_dropp
  * per particle, every step) can skip it when this is 0 -- the reference function would find
  * nothing to do.  Does not consume the record: gfsb200_particle_bc may still follow. */
 int gfsb200_escaped_count (gfsb200_ctx * c, int64_t * n_escaped);
+/* The same record itself: list positions (idx[k], in the order of the resident list) and
+ * positions BEFORE the step (old_xyz[3k..3k+2]; what the reference keeps in GfsParticle.pos_old
+ * for the ray walk of gfs_particle_bc) of up to `cap` escaped particles; *n_out = how many
+ * were written. */
+int gfsb200_escaped_download (gfsb200_ctx * c, int64_t cap, int32_t * idx, double * old_xyz,
+			      int64_t * n_out);
 /* re-sort resident particles by containing cell (Morton-ordered flat index)
  * so that neighbouring threads gather neighbouring cells */
 int gfsb200_particles_sort (gfsb200_ctx * c);

@@ -332,6 +332,8 @@ def load_refobj(dim: int, module: bool = False) -> C.CDLL:
         "refobj_field_event": (None, [vp, vp, i32]),
         "refobj_source_event": (None, [vp, vp, i32, dbl, C.POINTER(Kernel)]),
         "refobj_warnings": (lng, []),
+        "refobj_list_class_write": (i32, [vp, C.c_char_p]),
+        "refobj_list_sync": (i32, [vp]),
         "refobj_module_init": (i32, []),
         "refobj_module_name": (C.c_char_p, []),
     }
@@ -450,3 +452,12 @@ class RefParticleList:
 
     def write(self, path):
         assert self.R.refobj_list_write(self.h, str(path).encode()) == 0
+
+    def class_write(self, path):
+        """the GfsParticleList's own write method: the list as it appears in a simulation dump"""
+        assert self.R.refobj_list_class_write(self.h, str(path).encode()) == 0
+
+    def sync(self):
+        """module library only: gfsb200_module_sync, what foreign host code calls before it reads
+        the objects of a list driven in resident mode; returns False in the plain reference"""
+        return bool(self.R.refobj_list_sync(self.h))

@@ -14,8 +14,6 @@
 #ifndef G_LIKELY
 # define G_LIKELY(x) (x)
 #endif
-#define GTS_CONTAINER_CLASS(klass) GTS_OBJECT_CLASS_CAST (klass, GtsContainerClass, gts_container_class ())
-#define GTS_CONTAINEE_CLASS(klass) GTS_OBJECT_CLASS_CAST (klass, GtsContaineeClass, gts_containee_class ())
 
 GSList * g_slist_reverse (GSList * l);
 GSList * g_slist_find (GSList * l, gconstpointer data);

@@ -307,6 +307,19 @@ gpointer g_hash_table_lookup (GHashTable * h, gconstpointer key)
   return *n ? (*n)->value : NULL;
 }
 
+void g_hash_table_foreach (GHashTable * h, GHFunc func, gpointer data)
+{
+  guint b;
+  for (b = 0; b < h->nb; b++) {
+    HNode * n = h->bucket[b];
+    while (n) {
+      HNode * next = n->next;
+      (* func) (n->key, n->value, data);
+      n = next;
+    }
+  }
+}
+
 gboolean g_hash_table_remove (GHashTable * h, gconstpointer key)
 {
   HNode ** n = hash_find (h, key);
@@ -1442,6 +1455,30 @@ REF_EXPORT int refobj_module_init (void)
     }
     done = 1;
   }
+  return 1;
+}
+
+/* the GfsParticleList's own write method (gfs_particle_list_write :1096-1113 over
+   gfs_event_list_write src/event.c:2508-2523): the whole list as it appears in a dump */
+REF_EXPORT int refobj_list_class_write (GfsParticleList * plist, const char * path)
+{
+  FILE * fp = fopen (path, "w");
+  if (!fp) return -1;
+  (* GTS_OBJECT (plist)->klass->write) (GTS_OBJECT (plist), fp);
+  fputc ('\n', fp);
+  fclose (fp);
+  return 0;
+}
+
+/* libgfsrefmod: what host code outside the module calls before it reads the objects of a
+   list driven in resident mode */
+void gfsb200_module_sync (GfsParticleList * plist) __attribute__((weak));
+
+REF_EXPORT int refobj_list_sync (GfsParticleList * plist)
+{
+  if (!gfsb200_module_sync)
+    return 0;
+  gfsb200_module_sync (plist);
   return 1;
 }
 

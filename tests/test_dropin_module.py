@@ -221,3 +221,73 @@ def test_module_counts_device_launches():
     parts = helpers.test_particles(w, 500)
     run_list(sim, parts, helpers.oracle_params(w), 1, module=True)
     assert capi.kernel_launches() > before
+
+
+def run_resident(sim, parts, par, steps, record_at, periodic_mask=0):
+    """the module with $GFSB200_RESIDENT=1 (set by the caller): objects are only looked at after
+    an explicit gfsb200_module_sync at the steps in record_at"""
+    rs = ora.RefSim(sim, periodic_mask, module=True)
+    rs.configure(par)
+    rl = ora.RefParticleList(rs, *[parts[k] for k in KEYS], par)
+    out, stale = {}, None
+    for step in range(1, steps + 1):
+        assert rl.event() == 1
+        if step == 1:
+            stale = rl.get()                      # NOT synced: what a careless reader would see
+        if step in record_at:
+            assert rl.sync()
+            out[step] = rl.get()
+    rs.close()
+    return out, stale
+
+
+@pytest.mark.parametrize("kind", ["uniform3", "ring2", "chain3"])
+def test_module_resident_mode(kind, monkeypatch, tmp_path):
+    """$GFSB200_RESIDENT=1: the device copy is authoritative between events (no object gather /
+    scatter per event); gfsb200_module_sync, the list's write method and the reference's own
+    reader classes refresh the objects on demand"""
+    monkeypatch.setenv("GFSB200_RESIDENT", "1")
+    w, sim, ptrs = setup(kind)
+    parts = helpers.test_particles(w, 3000)
+    par = helpers.oracle_params(w)
+    want = run_list(sim, parts, par, 6, module=False)
+    got, stale = run_resident(sim, parts, par, 6, record_at=(3, 6))
+    # after the first event the objects still hold the initial state: nothing was written back
+    assert np.array_equal(stale["x"], parts["x"]) and np.array_equal(stale["vx"], parts["vx"])
+    for step in (3, 6):
+        check(got[step], want[step - 1], w.dim, 1e-11, (kind, step))
+    # the list's own write method syncs first: the dump holds the state after the last event
+    rs = ora.RefSim(sim, module=True)
+    rs.configure(par)
+    rl = ora.RefParticleList(rs, *[parts[k] for k in KEYS], par)
+    rl.event(2)
+    rl.class_write(tmp_path / "list.gfs")
+    after = rl.get()
+    rs.close()
+    text = (tmp_path / "list.gfs").read_text()
+    assert text.startswith("GfsParticleList") and text.count("GfsParticulate ") >= 3000
+    check(after, want[1], w.dim, 1e-11, (kind, "write"))
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_module_resident_mode_with_boundaries(dim, monkeypatch):
+    """resident mode where particles keep leaving: every event with an escape falls back to
+    download + the reference's gfs_particle_bc (pos_old patched from the device's record),
+    events without one stay on the device"""
+    monkeypatch.setenv("GFSB200_RESIDENT", "1")
+    w, mask = helpers.periodic_world(dim)
+    sim, ptrs = helpers.matched_oracle(w)
+    rng = np.random.default_rng(9)
+    parts = worlds.make_particles(w, 600)
+    n = len(parts["x"])
+    for k in ("x", "y", "z")[:dim]:
+        parts[k] = rng.uniform(-0.499, 0.499, n)
+    for k, f in zip(("vx", "vy", "vz")[:dim], (1.0, 1.0, 0.7)):
+        parts[k] = f * rng.standard_normal(n)
+    par = helpers.oracle_params(w)
+    want = run_list(sim, parts, par, 20, module=False, periodic_mask=mask)
+    got, _ = run_resident(sim, parts, par, 20, record_at=(5, 10, 20), periodic_mask=mask)
+    assert len(want[-1]["x"]) < n
+    for step in (5, 10, 20):
+        assert len(got[step]["x"]) == len(want[step - 1]["x"]), step
+        check(got[step], want[step - 1], dim, 1e-10, ("resident periodic", dim, step))

@@ -706,6 +706,11 @@ def test_escaped_count_matches_host_locate(ctx):
     outside = int((sim.locate(got["x"], got["y"], got["z"]) == 0).sum())
     assert outside > 10
     assert ctx.escaped_count() == outside
+    eidx, eold = ctx.escaped()
+    gone = np.nonzero(sim.locate(got["x"], got["y"], got["z"]) == 0)[0]
+    assert np.array_equal(np.sort(eidx), gone)
+    for a, k in enumerate(("x", "y", "z")):                 # the positions before the step
+        assert np.array_equal(eold[:, a], parts[k][eidx])
     ctx.step(w.step_params())
     with pytest.raises(capi.GfsB200Error):
         ctx.escaped_count()                    # the last step did not track
