@@ -689,7 +689,7 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
       (par.track_escapes && gfsb200_escaped_count (s->ctx, &escaped) != GFSB200_OK))
     g_error ("particulates (B200): %s", gfsb200_last_error ());
   t[4] = wall ();
-  if (s->resident && removed == 0 && escaped == 0 && s->list_known) {
+  if (s->resident && par.track_escapes && removed == 0 && escaped == 0 && s->list_known) {
     /* nothing the host has to act on: the objects are refreshed when somebody asks */
     s->host_stale = TRUE;
     t[5] = wall ();

@@ -80,6 +80,29 @@ def test_module_particle_list_event(kind):
         check(got[step], want[step], w.dim, 1e-12 if step == 0 else 1e-11, (kind, step))
 
 
+@pytest.mark.parametrize("resident", ["0", "1"])
+@pytest.mark.parametrize("kind", ["c1", "ring3", "chain2"])
+def test_module_tracer_list(kind, resident, monkeypatch):
+    """a list without forces: the reference falls through to gfs_particle_event /
+    gfs_domain_advect_point (src/particle.c:31-44), the module to the device's RK2 tracer
+    kernel; escapes are not tracked there, so the host BCs run every event in either mode"""
+    monkeypatch.setenv("GFSB200_RESIDENT", resident)
+    w, sim, ptrs = setup(kind)
+    parts = helpers.test_particles(w, 3000)
+    par = ora.step_params(w.dt, [])
+    want = run_list(sim, parts, par, 3, module=False)
+    got = run_list(sim, parts, par, 3, module=True)
+    for step in range(3):
+        go, wo = np.argsort(got[step]["id"]), np.argsort(want[step]["id"])
+        assert np.array_equal(got[step]["id"][go], want[step]["id"][wo])
+        keys = ("x", "y", "z")[:w.dim]
+        g = {k: got[step][k][go] for k in keys}
+        wv = {k: want[step][k][wo] for k in keys}
+        assert helpers.vec_rel_err(g, wv, keys) <= 1e-12, (kind, step)
+        for k in ("vx", "vy", "vz")[:w.dim]:                     # tracers keep their velocity field
+            assert np.array_equal(got[step][k][go], want[step][k][wo])
+
+
 @pytest.mark.parametrize("kind", ["c1", "ring3"])
 @pytest.mark.parametrize("forces,kw", [
     ((ora.FORCE_INERTIAL, ora.FORCE_DRAG), {}),
