@@ -314,3 +314,28 @@ def test_module_resident_mode_with_boundaries(dim, monkeypatch):
     for step in (5, 10, 20):
         assert len(got[step]["x"]) == len(want[step - 1]["x"]), step
         check(got[step], want[step - 1], dim, 1e-10, ("resident periodic", dim, step))
+
+
+def test_module_c1_full_config(monkeypatch):
+    """BASELINE config C1 as the reference would run it -- gerris2D, `GModule particulates`,
+    2D level-6 lid-style cavity with four ghost layers, 1000 GfsParticulate objects,
+    GfsForceDrag, dt = 1e-2 -- for 1000 list events through the drop-in module (resident mode,
+    objects synced every 100 events) against 1000 events of the reference's own object code"""
+    monkeypatch.setenv("GFSB200_RESIDENT", "1")
+    w = worlds.make_c1()
+    assert w.arrays.n_leaves == 64 * 64 and w.arrays.n_roots == 5
+    sim, ptrs = helpers.matched_oracle(w)
+    parts = worlds.make_particles(w)
+    assert len(parts["x"]) == 1000
+    par = helpers.oracle_params(w)
+    marks = tuple(range(100, 1001, 100))
+    want = run_list(sim, parts, par, 1000, module=False)
+    got, _ = run_resident(sim, parts, par, 1000, record_at=marks)
+    worst = 0.0
+    for step in marks:
+        g, wv = got[step], want[step - 1]
+        assert np.array_equal(g["id"], wv["id"])                  # nobody leaves the cavity
+        for keys in (("x", "y"), ("vx", "vy")):
+            worst = max(worst, helpers.vec_rel_err(g, wv, keys))
+    assert worst <= 1e-9, worst        # the documented drift bound after 1000 steps (drag only: no
+                                       # cell-constant force, so no particle is excluded)
