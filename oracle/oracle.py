@@ -318,6 +318,8 @@ def load_refobj(dim: int, module: bool = False) -> C.CDLL:
         "refobj_sim_new": (vp, [i32, vp, vp, C.c_uint, vp, vp, vp, i32]),
         "refobj_sim_configure": (None, [vp, C.POINTER(StepParams), i32]),
         "refobj_sim_destroy": (None, [vp]),
+        "refobj_locate": (None, [vp, lng, vp, vp, vp, vp]),
+        "refobj_locate_array": (None, [vp, vp, vp, vp]),
         "refobj_sim_time": (None, [vp, C.POINTER(dbl), C.POINTER(i32)]),
         "refobj_sim_add_solid": (None, [vp]),
         "refobj_list_new": (vp, [vp, lng] + [vp] * 8 + [C.POINTER(StepParams)]),
@@ -351,8 +353,8 @@ def load_refobj(dim: int, module: bool = False) -> C.CDLL:
 
 class RefSim:
     """A GfsSimulation of the reference's own structs around the GfsBox /
-    GfsBoundary trees of `sim`; gfs_domain_locate goes through sim's
-    GfsLocateArray.  Bit d of periodic_mask: the boundaries on side d are
+    GfsBoundary trees of `sim`; gfs_domain_locate and its GfsLocateArray are the
+    reference's own (src/domain.c compiled unmodified).  Bit d of periodic_mask: the boundaries on side d are
     GfsBoundaryPeriodic."""
 
     def __init__(self, sim: Sim, periodic_mask: int = 0, module: bool = False):
@@ -373,6 +375,19 @@ class RefSim:
         """PhysicalParams alpha, SourceViscosity, Source g, dt -- what the .gfs
         file declares around the list"""
         self.R.refobj_sim_configure(self.h, C.byref(params), int(timers))
+
+    def locate(self, x, y, z=None):
+        """gfs_domain_locate of the reference's own src/domain.c: FttCell* (0 = outside)"""
+        x, y, z = _f64(x), _f64(y), _f64(z)
+        out = np.zeros(len(x), dtype=np.uint64)
+        self.R.refobj_locate(self.h, len(x), _p(x), _p(y), _p(z), _p(out))
+        return out
+
+    def locate_array(self):
+        """(min[dim], h, n[dim]) of the GfsLocateArray the reference built"""
+        mn, h, n = np.zeros(3), C.c_double(), np.zeros(3, dtype=np.int32)
+        self.R.refobj_locate_array(self.h, _p(mn), C.byref(h), _p(n))
+        return mn[:self.dim], h.value, n[:self.dim]
 
     def add_solid(self):
         """an entry in sim->solids, as a GfsSolid declaration leaves"""

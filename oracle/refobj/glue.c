@@ -10,6 +10,8 @@
  *                                 gfs_particle_bc  (every function of SURVEY 8a)
  *   src/event.c                   GfsEvent gating, gfs_event_do, GfsEventList
  *   src/particle.c                GfsParticle (passive tracer event, %g writer)
+ *   src/domain.c                  GfsLocateArray, gfs_domain_locate, traversals,
+ *                                 gfs_domain_advect_point, gfs_domain_timer_*
  *   src/fluid.c, src/ftt.c        gfs_interpolate, gfs_center_gradient, trees
  *
  * are compiled UNMODIFIED from where they lie under /root/reference
@@ -20,12 +22,12 @@
  * (GTS 0.7.6, GLib 2.x: configure.ac:162-200), so the handful of their
  * functions the path calls are restated from their published behaviour
  * (object.c / container.c of GTS 0.7.6, gslist.c of GLib), and the few Gerris
- * functions that live in files which do not compile here (src/domain.c needs
- * config.h, src/variable.c and src/source.c need MPI/GtsFifo) are restated with
- * their file:line.  Everything the path does NOT call resolves to an aborting
+ * functions that live in files which are not linked here (src/utils.c,
+ * src/variable.c, src/source.c, src/boundary.c, src/simulation.c: each drags in
+ * the solver) are restated with their file:line.  Everything the path does NOT call resolves to an aborting
  * stub (mkstubs.sh), so a call that strays off the restated set fails loudly.
  *
- * The FttCell trees, their cell data and the GfsLocateArray come from
+ * The FttCell trees and their cell data come from
  * libgfsoracle (oracle/particulate_port.c: trees built by the reference's
  * ftt.c object code); they are shared by pointer -- FttCell and GfsStateVector
  * have the same layout in both libraries because both use the reference's
@@ -778,8 +780,6 @@ SIMPLE_CLASS (gfs_boundary_periodic_class, GfsBoundaryClass, "GfsBoundaryPeriodi
 typedef FttCell * (* RefLocateFunc) (gpointer handle, gdouble x, gdouble y, gdouble z, gint max_depth);
 typedef void (* RefBcFunc) (gpointer handle, gint ivar);
 
-#define REF_TIMERS 64
-
 typedef struct {
   GfsSimulation sim;
   gint nbox;
@@ -790,11 +790,6 @@ typedef struct {
   gint nvar;
   GfsVariable ** var;
   GfsDiffusion * D;
-  /* gfs_domain_timer_*: name -> accumulated time (src/domain.c:4137-4180) */
-  struct { const gchar * name; GfsTimer t; } timer[REF_TIMERS];
-  gint ntimers;
-  clock_t clock_start;
-  gboolean timers_on;
 } RefSim;
 
 static void sim_foreach (GtsContainer * c, GtsFunc func, gpointer data)
@@ -823,84 +818,15 @@ GfsSimulationClass * gfs_simulation_class (void)
   return klass;
 }
 
-/* src/domain.c:2623-2638 through the GfsLocateArray that libgfsoracle restates */
-FttCell * gfs_domain_locate (GfsDomain * domain, FttVector target, gint max_depth, GfsBox ** where)
-{
-  RefSim * s = (RefSim *) domain;
-  FttCell * cell = (* s->locate) (s->handle, target.x, target.y, target.z, max_depth);
-  if (cell && where) {
-    FttCell * root = cell;
-    while (!FTT_CELL_IS_ROOT (root)) root = ftt_cell_parent (root);
-    *where = GFS_BOX (FTT_ROOT_CELL (root)->parent);
-  }
-  return cell;
-}
-
-/* src/domain.c:2296-2310 */
-GfsVariable ** gfs_domain_velocity (GfsDomain * domain)
-{
-  FttComponent c;
-  static gchar name[][2] = {"U","V","W"};
-
-  g_return_val_if_fail (domain != NULL, NULL);
-  for (c = 0; c < FTT_DIMENSION; c++) {
-    GfsVariable * v = gfs_variable_from_name (domain->variables, name[c]);
-    if (v == NULL)
-      return NULL;
-    domain->velocity[c] = v;
-  }
-  return domain->velocity;
-}
-
-/* src/domain.c:1463-1497, 1550-1574: every GfsBox tree in container order */
-void gfs_domain_cell_traverse (GfsDomain * domain, FttTraverseType order, FttTraverseFlags flags,
-			       gint max_depth, FttCellTraverseFunc func, gpointer data)
-{
-  RefSim * s = (RefSim *) domain;
-  gint b;
-  for (b = 0; b < s->nbox; b++)
-    ftt_cell_traverse (s->box[b]->root, order, flags, max_depth, func, data);
-}
-
-void gfs_domain_cell_traverse_condition (GfsDomain * domain, FttTraverseType order, FttTraverseFlags flags,
-					 gint max_depth, FttCellTraverseFunc func, gpointer data,
-					 gboolean (* condition) (FttCell *, gpointer), gpointer cdata)
-{
-  RefSim * s = (RefSim *) domain;
-  gint b;
-  for (b = 0; b < s->nbox; b++)
-    ftt_cell_traverse_condition (s->box[b]->root, order, flags, max_depth, func, data, condition, cdata);
-}
-
-/* gfs_domain_bc fills the ghost cells of one variable; the ghost trees belong
-   to libgfsoracle, which restates src/boundary.c for them */
+/* gfs_domain_bc fills the ghost cells of one variable.  src/domain.c's own (weakened at link
+   time, oracle/Makefile) walks the GfsBc objects of src/boundary.c, which the ghost trees
+   built by libgfsoracle do not carry; this one calls back into libgfsoracle when it is given a
+   filler (the tests set the ghost values themselves) */
 void gfs_domain_bc (GfsDomain * domain, FttTraverseFlags flags, gint max_depth, GfsVariable * v)
 {
   RefSim * s = (RefSim *) domain;
   if (s->bc)
     (* s->bc) (s->handle, v->i);
-}
-
-/* src/domain.c:2764-2788 */
-void gfs_domain_advect_point (GfsDomain * domain, FttVector * p, gdouble dt)
-{
-  FttCell * cell;
-  FttVector p0, p1;
-  FttComponent c;
-  GfsVariable ** u;
-
-  p0 = p1 = *p;
-  cell = gfs_domain_locate (domain, p0, -1, NULL);
-  if (cell == NULL)
-    return;
-  u = gfs_domain_velocity (domain);
-  for (c = 0; c < FTT_DIMENSION; c++)
-    (&p1.x)[c] += dt*gfs_interpolate (cell, p0, u[c])/2.;
-  cell = gfs_domain_locate (domain, p1, -1, NULL);
-  if (cell == NULL)
-    return;
-  for (c = 0; c < FTT_DIMENSION; c++)
-    (&p->x)[c] += dt*gfs_interpolate (cell, p1, u[c]);
 }
 
 /* src/simulation.c:1893-1932 for a simulation without GfsMap objects (none of
@@ -919,44 +845,54 @@ void gfs_simulation_map_inverse (GfsSimulation * sim, FttVector * p)
     (&p->x)[c] *= sim->physical_params.L/(&GFS_DOMAIN (sim)->lambda.x)[c];
 }
 
-/* src/domain.c:4137-4180 with src/utils.c:1923-1936 (one times() call each):
-   the reference brackets EVERY event, i.e. every particle, with a timer */
-static GfsTimer * timer_lookup (RefSim * s, const gchar * name)
+/* src/utils.c:2282-2300: debug messages are off unless gfs_debug_enabled (TRUE) */
+void gfs_debug (const gchar * format, ...)
 {
-  gint i;
-  for (i = 0; i < s->ntimers; i++)
-    if (s->timer[i].name == name || !strcmp (s->timer[i].name, name))
-      return &s->timer[i].t;
-  g_assert (s->ntimers < REF_TIMERS);
-  s->timer[s->ntimers].name = name;
-  s->timer[s->ntimers].t.start = -1.;
-  return &s->timer[s->ntimers++].t;
 }
 
-static gdouble clock_elapsed (RefSim * s)
+/* src/utils.c:1870-1936: GfsClock, the user-time clock behind gfs_domain_timer_start/stop
+   (src/domain.c:4137-4180, now the reference's own object code): one times() call per reading */
+struct _GfsClock {
+  clock_t start, stop;
+  gboolean started;
+};
+
+GfsClock * gfs_clock_new (void)
+{
+  GfsClock * t = g_malloc (sizeof (GfsClock));
+  t->start = -1;
+  t->started = FALSE;
+  return t;
+}
+
+void gfs_clock_start (GfsClock * t)
 {
   struct tms tm;
-  times (&tm);
-  return (tm.tms_utime - s->clock_start)/(gdouble) sysconf (_SC_CLK_TCK);
+  g_return_if_fail (t != NULL);
+  g_return_if_fail (!t->started);
+  if (times (&tm) == (clock_t) -1)
+    g_warning ("cannot read clock");
+  t->start = tm.tms_utime;
+  t->started = TRUE;
 }
 
-void gfs_domain_timer_start (GfsDomain * domain, const gchar * name)
+gdouble gfs_clock_elapsed (GfsClock * t)
 {
-  RefSim * s = (RefSim *) domain;
-  if (s->timers_on)
-    timer_lookup (s, name)->start = clock_elapsed (s);
-}
-
-void gfs_domain_timer_stop (GfsDomain * domain, const gchar * name)
-{
-  RefSim * s = (RefSim *) domain;
-  if (s->timers_on) {
-    gdouble end = clock_elapsed (s);
-    GfsTimer * t = timer_lookup (s, name);
-    t->r.sum += end - t->start;
-    t->r.n++;
-    t->start = -1.;
+  g_return_val_if_fail (t != NULL, 0.);
+  g_return_val_if_fail (t->start >= 0, 0.);
+  if (t->started == FALSE)
+    return (t->stop - t->start)/(gdouble) sysconf (_SC_CLK_TCK);
+  else {
+    struct tms tm;
+    if (times (&tm) == (clock_t) -1)
+      g_warning ("cannot read clock");
+    return (tm.tms_utime - t->start)/(gdouble) sysconf (_SC_CLK_TCK);
   }
+}
+
+void gfs_clock_destroy (GfsClock * t)
+{
+  g_free (t);
 }
 
 /* fluid.c externals that only matter for mixed (solid) cells or statistics */
@@ -1068,7 +1004,14 @@ REF_EXPORT RefSim * refobj_sim_new (int nbox, FttCell ** root, FttCell ** broot,
   domain->lambda.x = domain->lambda.y = domain->lambda.z = 1.;
   s->sim.time.end = G_MAXDOUBLE;
   s->sim.time.iend = G_MAXINT;
-  s->clock_start = 0;
+  /* what gfs_domain_init / gfs_simulation_init set up (src/domain.c:630-690) and the
+     GfsLocateArray gfs_domain_locate needs (built after the boxes are linked, as
+     gfs_domain_read does, src/domain.c:820-823) */
+  domain->rootlevel = FTT_ROOT_CELL (root[0])->level;
+  domain->timers = g_hash_table_new (g_str_hash, g_str_equal);
+  domain->timer = gfs_clock_new ();
+  gfs_clock_start (domain->timer);
+  domain->array = gfs_locate_array_new (domain);
   return s;
 }
 
@@ -1108,7 +1051,7 @@ REF_EXPORT void refobj_sim_configure (RefSim * s, const RefStepParams * par, int
 
   clear_sources (s);
   s->sim.advection_params.dt = par->dt;
-  s->timers_on = timers_on;
+  /* (timers_on is ignored: gfs_domain_timer_start/stop are the reference's own and always run) */
   if (par->ivar_alpha >= 0) {
     GfsFunction * f = gfs_function_new (gfs_function_class (), 0.);
     f->v = s->var[par->ivar_alpha];
@@ -1154,6 +1097,8 @@ REF_EXPORT void refobj_sim_destroy (RefSim * s)
   }
   g_free (s->var);
   g_slist_free (GFS_DOMAIN (s)->variables);
+  gfs_locate_array_destroy (GFS_DOMAIN (s)->array);
+  gfs_clock_destroy (GFS_DOMAIN (s)->timer);
   gts_container_foreach (GTS_CONTAINER (s->sim.solids), (GtsFunc) gts_object_destroy, NULL);
   gts_object_destroy (GTS_OBJECT (s->sim.solids));
   gts_object_destroy (GTS_OBJECT (s->sim.events));
@@ -1167,6 +1112,29 @@ REF_EXPORT void refobj_sim_add_solid (RefSim * s)
 {
   gts_container_add (GTS_CONTAINER (s->sim.solids),
 		     GTS_CONTAINEE (gts_object_new (GTS_OBJECT_CLASS (gts_slist_containee_class ()))));
+}
+
+/* gfs_domain_locate (src/domain.c:2623-2638 over the GfsLocateArray of :43-145), the
+   reference's own object code, for n points */
+REF_EXPORT void refobj_locate (RefSim * s, long n, const double * x, const double * y, const double * z,
+			       void ** cell)
+{
+  long i;
+  for (i = 0; i < n; i++) {
+    FttVector p = { x[i], y[i], z ? z[i] : 0., 0. };
+    cell[i] = gfs_domain_locate (GFS_DOMAIN (s), p, -1, NULL);
+  }
+}
+
+REF_EXPORT void refobj_locate_array (RefSim * s, double * min, double * h, int * n)
+{
+  GfsLocateArray * a = GFS_DOMAIN (s)->array;
+  gint c;
+  for (c = 0; c < FTT_DIMENSION; c++) {
+    min[c] = a->min[c];
+    n[c] = a->n[c];
+  }
+  *h = a->h;
 }
 
 REF_EXPORT void refobj_sim_time (RefSim * s, double * t, int * i)

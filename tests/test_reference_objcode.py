@@ -13,6 +13,8 @@ gives identical bits; any tolerance here would hide a restatement error).
 
 CPU only; nothing here touches the product path.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -372,3 +374,37 @@ def test_dropin_module_loads_and_hands_back_what_the_device_cannot_do():
         rs.close()
     for step in range(2):
         assert_same_state(states[0][step], states[1][step], 3, step)
+
+
+@pytest.mark.parametrize("kind", ["c1", "uniform3", "ring3", "ring2", "ring3b", "chain2", "chain3", "periodic2",
+                                  "periodic3"])
+def test_locate_array_and_domain_locate_bit_identical(kind):
+    """GfsLocateArray (src/domain.c:43-145) and gfs_domain_locate (:2623-2638), the
+    reference's own object code, against the restatement the GPU locate is held to:
+    same array geometry, same FttCell* for random points, points on cell faces /
+    vertices / +-1 ulp around them, the hull, outside, NaN"""
+    if kind.startswith("periodic"):
+        w, mask = helpers.periodic_world(int(kind[-1]))
+        sim, ptrs = helpers.matched_oracle(w)
+    else:
+        w, sim, ptrs = setup(kind)
+        mask = 0
+    rs = ora.RefSim(sim, mask)
+    mn, h, n = rs.locate_array()
+    pmn, ph, pn = np.zeros(3), C.c_double(), np.zeros(3, dtype=np.int32)
+    sim.L.ora_locate_array(sim.h, pmn.ctypes.data, C.byref(ph), pn.ctypes.data)
+    assert np.array_equal(mn, pmn[:w.dim]) and h == ph.value and np.array_equal(n, pn[:w.dim])
+    rng = np.random.default_rng(3)
+    nbox = w.meta.get("nbox", 1)
+    m = 40000
+    pts = rng.uniform(-0.75, nbox - 0.25, (m, 3))
+    pts[:, 1:] = rng.uniform(-0.75, 0.75, (m, 2))
+    ax, ay, az = worlds.adversarial_points(w.arrays, rng, 4000)
+    adv = np.stack([ax, ay, az if az is not None else np.zeros_like(ax)], 1)
+    pts = np.vstack([pts, adv, [[np.nan, 0, 0], [0, np.inf, 0], [1e300, 0, 0]]])
+    z = pts[:, 2].copy() if w.dim == 3 else None
+    ref = rs.locate(pts[:, 0].copy(), pts[:, 1].copy(), z)
+    port = sim.locate(pts[:, 0].copy(), pts[:, 1].copy(), z)
+    assert (ref != 0).sum() > 1000 and (ref == 0).sum() > 1000
+    assert np.array_equal(ref, port)
+    rs.close()
