@@ -61,6 +61,7 @@ typedef struct {
   /* $GFSB200_RESIDENT=1: the device copy stays authoritative between events; the GtsObjects
      are refreshed (sync_down) only when something on the host is about to look at them */
   gboolean resident;
+  gboolean mpi;                         /* parallel run: gfs_particle_bc every event (it also receives) */
   gboolean host_stale;                  /* the device holds newer particle state than the objects */
   gboolean syncing;                     /* inside sync_down (its own removals must not recurse) */
   GfsParticleList * plist;
@@ -107,6 +108,14 @@ static B200State * state_of (GfsParticleList * plist)
       g_error ("particulates (B200): %s", gfsb200_last_error ());   /* no CPU fallback */
     s->plist = plist;
     s->resident = g_getenv ("GFSB200_RESIDENT") && atoi (g_getenv ("GFSB200_RESIDENT")) != 0;
+#ifdef HAVE_MPI
+    /* a parallel run exchanges particles inside gfs_particle_bc (:3218-3244, 3287-3316), which
+       must then run -- on up-to-date objects -- in every event on every rank */
+    if (GFS_DOMAIN (gfs_object_simulation (plist))->pid >= 0) {
+      s->resident = FALSE;
+      s->mpi = TRUE;
+    }
+#endif
     g_hash_table_insert (b200_states, plist, s);
   }
   return s;
@@ -718,7 +727,7 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
   /* :993, host side as in the reference.  gfs_particle_bc spends one gfs_domain_locate per
      particle to find those that left the domain; the step kernel has already counted them,
      and when there are none the reference function has nothing to do. */
-  if (!par.track_escapes || escaped > 0)
+  if (s->mpi || !par.track_escapes || escaped > 0)
     gfs_particle_bc (plist);
   t[6] = wall ();
   if (s->warm) {                /* the first event pays for the flatten and the page-locked buffers */
