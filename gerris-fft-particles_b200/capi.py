@@ -119,6 +119,7 @@ def lib() -> C.CDLL:
         "gfsb200_particles_cull": (i32, [vp, C.POINTER(i64)]),
         "gfsb200_particle_bc": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
         "gfsb200_escaped_count": (i32, [vp, C.POINTER(i64)]),
+        "gfsb200_step_counts": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
         "gfsb200_escaped_download": (i32, [vp, i64, vp, vp, C.POINTER(i64)]),
         "gfsb200_host_alloc": (vp, [C.c_size_t]),
         "gfsb200_host_free": (None, [vp]),
@@ -462,6 +463,12 @@ class Context:
         _check(self._lib.gfsb200_escaped_download(self.handle, n, _ptr(idx), _ptr(old), C.byref(m)),
                "escaped_download")
         return idx[:m.value], old[:m.value]
+
+    def step_counts(self):
+        """(escaped, outside before the step) of the last step issued with track_escapes"""
+        e, o = C.c_int64(0), C.c_int64(0)
+        _check(self._lib.gfsb200_step_counts(self.handle, C.byref(e), C.byref(o)), "step_counts")
+        return int(e.value), int(o.value)
 
     def escaped_count(self):
         """particles that left the domain during the last step issued with track_escapes"""

@@ -100,7 +100,7 @@ struct gfsb200_ctx {
   size_t cub_tmp_bytes;
   double ** d_ptr_table;       /* [2][NCOL] device copy of col pointers */
   /* escape tracking for gfs_particle_bc */
-  int * esc_count;             /* [3]: escaped, wrapped, dropped */
+  int * esc_count;             /* [4]: escaped, wrapped, dropped, outside the domain before the step */
   int32_t * esc_idx;
   double * esc_old;
   int esc_cap;
@@ -808,8 +808,8 @@ extern "C" int gfsb200_step (gfsb200_ctx * c, const gfsb200_step_params * p)
       CK (cudaMalloc ((void **) &c->esc_old, (size_t) want*3*sizeof (double)));
       c->esc_cap = want;
     }
-    if (!c->esc_count) CK (cudaMalloc ((void **) &c->esc_count, 3*sizeof (int)));
-    CK (cudaMemsetAsync (c->esc_count, 0, 3*sizeof (int), c->stream));
+    if (!c->esc_count) CK (cudaMalloc ((void **) &c->esc_count, 4*sizeof (int)));
+    CK (cudaMemsetAsync (c->esc_count, 0, 4*sizeof (int), c->stream));
     S.track_escapes = 1;
     S.esc_cap = c->esc_cap; S.esc_count = c->esc_count; S.esc_idx = c->esc_idx; S.esc_old = c->esc_old;
     c->esc_armed = true;
@@ -1034,6 +1034,22 @@ extern "C" int gfsb200_escaped_count (gfsb200_ctx * c, int64_t * n_escaped)
   return GFSB200_OK;
 }
 
+extern "C" int gfsb200_step_counts (gfsb200_ctx * c, int64_t * n_escaped, int64_t * n_outside)
+{
+  if (!c) return gfsb200_fail (GFSB200_ERR_ARG, "step_counts: null context");
+  if (n_escaped) *n_escaped = 0;
+  if (n_outside) *n_outside = 0;
+  if (!c->esc_armed)
+    return gfsb200_fail (GFSB200_ERR_STATE, "step_counts: the last step did not track escapes");
+  CK (cudaSetDevice (c->device));
+  int counts[4] = { 0, 0, 0, 0 };
+  CK (cudaMemcpyAsync (counts, c->esc_count, 4*sizeof (int), cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  if (n_escaped) *n_escaped = counts[0];
+  if (n_outside) *n_outside = counts[3];
+  return GFSB200_OK;
+}
+
 extern "C" int gfsb200_escaped_download (gfsb200_ctx * c, int64_t cap, int32_t * idx, double * old_xyz,
 					  int64_t * n_out)
 {
@@ -1060,12 +1076,31 @@ extern "C" int gfsb200_particle_list_event (gfsb200_ctx * c, const gfsb200_step_
 {
   if (!p) return gfsb200_fail (GFSB200_ERR_ARG, "null step parameters");
   int64_t culled = 0, dropped = 0;
-  int r = gfsb200_particles_cull (c, &culled);
-  if (r) return r;
+  int r;
   gfsb200_step_params q = *p;
-  q.track_escapes = q.n_forces > 0;
+  if (q.n_forces == 0) {
+    /* tracers: the RK2 kernel does not track, cull first as the reference does */
+    if ((r = gfsb200_particles_cull (c, &culled))) return r;
+    q.track_escapes = 0;
+    if ((r = gfsb200_step (c, &q))) return r;
+    if (n_removed) *n_removed = culled;
+    return GFSB200_OK;
+  }
+  /* The step kernel leaves a particle that is outside the domain untouched and counts it, and it
+     counts those that leave: cull -> step -> BC and step -> BC -> cull give the same list, and in
+     the second order the cull pass (locate + flag + select, about as long as the step itself) and
+     the BC pass only run when their count is not zero -- one 16-byte read-back decides. */
+  q.track_escapes = 1;
   if ((r = gfsb200_step (c, &q))) return r;
-  if (q.track_escapes && (r = gfsb200_particle_bc (c, NULL, &dropped))) return r;
+  int counts[4] = { 0, 0, 0, 0 };
+  CK (cudaMemcpyAsync (counts, c->esc_count, 4*sizeof (int), cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  if (counts[0] > 0) {
+    if ((r = gfsb200_particle_bc (c, NULL, &dropped))) return r;
+  }
+  else
+    c->esc_armed = false;
+  if (counts[3] > 0 && (r = gfsb200_particles_cull (c, &culled))) return r;
   if (n_removed) *n_removed = culled + dropped;
   return GFSB200_OK;
 }

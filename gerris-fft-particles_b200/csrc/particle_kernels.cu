@@ -538,8 +538,11 @@ step_kernel (DevTree T, DevField fld, DevParticles P, DevStep S)
   const Located L = locate<DIM, LATTICE> (T, x, y, z);
   if (REC)
     P.cell[i] = cell_index<DIM, LATTICE> (T, L);
-  if (L.cell < 0)     /* outside: gfs_particle_list_event removes it first (:987) */
+  if (L.cell < 0) {   /* outside: gfs_particle_list_event removes it first (:987) */
+    if (S.track_escapes)
+      atomicAdd (S.esc_count + 3, 1);         /* lets the list event skip its cull pass when 0 */
     return;
+  }
 
   double Fx, Fy, Fz, rho;
   total_force<DIM, false, LATTICE, PROG> (T, fld, S, L, x, y, z, vx, vy, vz, mass, volume,
@@ -728,6 +731,8 @@ step_kernel_pipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_tile
 	  __stcs (P.z + i, z); __stcs (P.vz + i, vz);
 	}
       }
+      else if (S.track_escapes)
+	atomicAdd (S.esc_count + 3, 1);       /* outside the domain before the step */
     }
   }
 }

@@ -654,6 +654,25 @@ static void b200_particle_list_write (GtsObject * o, FILE * fp)
 /* ------------------------------------------------------------------ */
 /* the replaced event methods                                           */
 
+/* resident mode: pos_old of the particles that just left the domain, from the device's record
+ * (list positions refer to the list as it was stepped, i.e. to obj[] before any compaction);
+ * gfs_particle_bc walks back from there (:3151-3186) */
+static void patch_pos_old (B200State * s, gint64 escaped)
+{
+  gint64 got = 0, e;
+  gint32 * idx = g_malloc (sizeof (gint32)*escaped);
+  gdouble * old = g_malloc (sizeof (gdouble)*3*escaped);
+  if (gfsb200_escaped_download (s->ctx, escaped, idx, old, &got) != GFSB200_OK)
+    g_error ("particulates (B200): %s", gfsb200_last_error ());
+  for (e = 0; e < got; e++)
+    if (idx[e] >= 0 && idx[e] < s->n_obj) {
+      GfsParticle * p = GFS_PARTICLE (s->obj[idx[e]]);
+      p->pos_old.x = old[3*e]; p->pos_old.y = old[3*e + 1]; p->pos_old.z = old[3*e + 2];
+    }
+  g_free (idx);
+  g_free (old);
+}
+
 static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
 {
   GfsParticleList * plist = GFS_PARTICLE_LIST (event);
@@ -693,9 +712,20 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
      gfsb200_tree_set_periodic and call gfsb200_particle_list_event, which wraps
      and drops on the device (gfsb200_particle_bc). */
   par.track_escapes = par.n_forces > 0;
-  if (gfsb200_particles_cull (s->ctx, &removed) != GFSB200_OK ||
-      gfsb200_step (s->ctx, &par) != GFSB200_OK ||
-      (par.track_escapes && gfsb200_escaped_count (s->ctx, &escaped) != GFSB200_OK))
+  if (par.track_escapes) {
+    /* the step kernel leaves a particle that is outside the domain untouched and counts it:
+       the cull pass (remove_particles_not_in_domain :955-969) only runs when there is one */
+    gint64 outside = 0;
+    if (gfsb200_step (s->ctx, &par) != GFSB200_OK ||
+	gfsb200_step_counts (s->ctx, &escaped, &outside) != GFSB200_OK)
+      g_error ("particulates (B200): %s", gfsb200_last_error ());
+    if (s->resident && escaped > 0)
+      patch_pos_old (s, escaped);
+    if (outside > 0 && gfsb200_particles_cull (s->ctx, &removed) != GFSB200_OK)
+      g_error ("particulates (B200): %s", gfsb200_last_error ());
+  }
+  else if (gfsb200_particles_cull (s->ctx, &removed) != GFSB200_OK ||
+	   gfsb200_step (s->ctx, &par) != GFSB200_OK)
     g_error ("particulates (B200): %s", gfsb200_last_error ());
   t[4] = wall ();
   if (s->resident && par.track_escapes && removed == 0 && escaped == 0 && s->list_known) {
@@ -707,21 +737,6 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
     s->host_stale = FALSE;
     download_particles (s, plist, n_up);
     t[5] = wall ();
-    if (s->resident && escaped > 0) {
-      /* pos_old of the particles gfs_particle_bc will walk back from (:3151-3186) */
-      gint64 cap = escaped, got = 0, e;
-      gint32 * idx = g_malloc (sizeof (gint32)*cap);
-      gdouble * old = g_malloc (sizeof (gdouble)*3*cap);
-      if (gfsb200_escaped_download (s->ctx, cap, idx, old, &got) != GFSB200_OK)
-	g_error ("particulates (B200): %s", gfsb200_last_error ());
-      for (e = 0; e < got; e++)
-	if (idx[e] >= 0 && idx[e] < s->n_obj) {
-	  GfsParticle * p = GFS_PARTICLE (s->obj[idx[e]]);
-	  p->pos_old.x = old[3*e]; p->pos_old.y = old[3*e + 1]; p->pos_old.z = old[3*e + 2];
-	}
-      g_free (idx);
-      g_free (old);
-    }
   }
 
   /* :993, host side as in the reference.  gfs_particle_bc spends one gfs_domain_locate per

@@ -250,7 +250,10 @@ int gfsb200_step_host (gfsb200_ctx * c, const gfsb200_step_params * p, int64_t n
 
 /* gfs_particle_list_event: cull particles outside the domain
  * (remove_particles_not_in_domain), step, then gfs_particle_bc (periodic wrap /
- * drop).  *n_removed (may be NULL) counts the culled and the dropped. */
+ * drop).  *n_removed (may be NULL) counts the culled and the dropped.  With forces the
+ * passes run as step -> BC -> cull -- the same list, since the step leaves a particle that
+ * is outside the domain untouched -- and the BC and cull passes are skipped when the step
+ * kernel counted no particle for them. */
 int gfsb200_particle_list_event (gfsb200_ctx * c, const gfsb200_step_params * p,
 				 int64_t * n_removed);
 int gfsb200_particles_cull (gfsb200_ctx * c, int64_t * n_removed);
@@ -268,6 +271,10 @@ int gfsb200_particle_bc (gfsb200_ctx * c, int64_t * n_wrapped, int64_t * n_dropp
  * per particle, every step) can skip it when this is 0 -- the reference function would find
  * nothing to do.  Does not consume the record: gfsb200_particle_bc may still follow. */
 int gfsb200_escaped_count (gfsb200_ctx * c, int64_t * n_escaped);
+/* Both counts of the last tracked step in one read-back: particles that left the domain
+ * during the step, and particles that were already outside before it (the step leaves those
+ * untouched; gfsb200_particles_cull removes them).  Either pointer may be NULL. */
+int gfsb200_step_counts (gfsb200_ctx * c, int64_t * n_escaped, int64_t * n_outside);
 /* The same record itself: list positions (idx[k], in the order of the resident list) and
  * positions BEFORE the step (old_xyz[3k..3k+2]; what the reference keeps in GfsParticle.pos_old
  * for the ray walk of gfs_particle_bc) of up to `cap` escaped particles; *n_out = how many

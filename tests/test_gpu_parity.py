@@ -706,11 +706,14 @@ def test_escaped_count_matches_host_locate(ctx):
     outside = int((sim.locate(got["x"], got["y"], got["z"]) == 0).sum())
     assert outside > 10
     assert ctx.escaped_count() == outside
+    assert ctx.step_counts() == (outside, 0)
     eidx, eold = ctx.escaped()
     gone = np.nonzero(sim.locate(got["x"], got["y"], got["z"]) == 0)[0]
     assert np.array_equal(np.sort(eidx), gone)
     for a, k in enumerate(("x", "y", "z")):                 # the positions before the step
         assert np.array_equal(eold[:, a], parts[k][eidx])
+    ctx.step(par)                              # the escapees are still in the list: outside now
+    assert ctx.step_counts()[1] == outside
     ctx.step(w.step_params())
     with pytest.raises(capi.GfsB200Error):
         ctx.escaped_count()                    # the last step did not track
