@@ -44,6 +44,8 @@ void gfsb200_launch_deposit (const DevTree *, const DevField *, const DevParticl
 void gfsb200_launch_deposit_smoothed (const DevTree *, const DevField *, const DevParticles *,
 				      const DevStep *, double, const gfsb200_kernel *, double *, double *,
 				      double *, double *, cudaStream_t);
+void gfsb200_launch_gather3 (int64_t, const int32_t *, const double *, const double *, const double *,
+			     double *, double *, double *, cudaStream_t);
 void gfsb200_launch_gather (int64_t, const int32_t *, int, const double * const *, double * const *,
 			    const uint32_t *, uint32_t *, cudaStream_t);
 void gfsb200_launch_particle_bc (const DevTree *, const DevParticles *, int, const int32_t *,
@@ -100,6 +102,7 @@ struct gfsb200_ctx {
   size_t cub_tmp_bytes;
   double ** d_ptr_table;       /* [2][NCOL] device copy of col pointers */
   /* escape tracking for gfs_particle_bc */
+  bool forces_recorded;        /* force[] holds what the last step (or on-fluid pass) recorded for the resident list */
   int * esc_count;             /* [4]: escaped, wrapped, dropped, outside the domain before the step */
   int32_t * esc_idx;
   double * esc_old;
@@ -202,6 +205,7 @@ extern "C" int gfsb200_ctx_create (int device, gfsb200_ctx ** out)
   c->d_child0 = c->d_neighbor = c->d_la_slot = c->d_vtx_off = c->d_vtx_cell = c->d_leaf_vtx = NULL;
   c->d_level = c->d_info = NULL; c->d_vtx_w = c->d_vtx_wuni = NULL; c->d_parent = NULL;
   c->esc_count = NULL; c->esc_idx = NULL; c->esc_old = NULL; c->esc_cap = 0; c->esc_armed = false;
+  c->forces_recorded = false;
   for (int i = 0; i < 5; i++) c->d_field[i] = NULL;
   for (int i = 0; i < 3; i++) c->d_prev[i] = NULL;
   c->have_prev = c->acc_valid = false;
@@ -665,6 +669,7 @@ extern "C" int gfsb200_particles_upload (gfsb200_ctx * c, int64_t n,
     CK (cudaMemcpyAsync (c->id[c->cur], id, n*sizeof (uint32_t), cudaMemcpyHostToDevice, c->stream));
   CK (cudaMemsetAsync (c->cell, 0xff, (n ? n : 1)*sizeof (int32_t), c->stream));
   for (int k = 0; k < 3; k++) CK (cudaMemsetAsync (c->force[k], 0, (n ? n : 1)*sizeof (double), c->stream));
+  c->forces_recorded = false;
   CK (cudaStreamSynchronize (c->stream));
   return GFSB200_OK;
 }
@@ -823,6 +828,8 @@ extern "C" int gfsb200_step (gfsb200_ctx * c, const gfsb200_step_params * p)
 			 c->step_mode, c->n_sm, c->stream);
   if ((r = timed_end (c))) return r;
   CK (cudaGetLastError ());
+  if (S.n_forces > 0 && p->record_forces)
+    c->forces_recorded = true;
   return GFSB200_OK;
 }
 
@@ -931,12 +938,22 @@ static int ensure_cub_tmp (gfsb200_ctx * c, size_t bytes)
 /* apply c->perm2 (new position -> old position) to the SoA, n_new entries */
 static int apply_permutation (gfsb200_ctx * c, int64_t n_new)
 {
-  const int nb = 1 - c->cur;
+  const int nb = 1 - c->cur, old = c->cur;
   gfsb200_launch_gather (n_new, c->perm2, NCOL, (const double * const *) (c->d_ptr_table + c->cur*NCOL),
 			 c->d_ptr_table + nb*NCOL, c->id[c->cur], c->id[nb], c->stream);
   CK (cudaGetLastError ());
   c->cur = nb;
   c->n = n_new;
+  if (c->forces_recorded && n_new > 0) {
+    /* the forces recorded by the last step follow their particles; the columns just vacated
+       serve as scratch */
+    gfsb200_launch_gather3 (n_new, c->perm2, c->force[0], c->force[1], c->force[2],
+			    c->col[old][0], c->col[old][1], c->col[old][2], c->stream);
+    CK (cudaGetLastError ());
+    for (int k = 0; k < 3; k++)
+      CK (cudaMemcpyAsync (c->force[k], c->col[old][k], n_new*sizeof (double), cudaMemcpyDeviceToDevice,
+			   c->stream));
+  }
   return GFSB200_OK;
 }
 
@@ -1420,6 +1437,7 @@ extern "C" int gfsb200_deposit_force_smoothed (gfsb200_ctx * c, const gfsb200_st
 				   c->T.dim == 3 ? c->deposit + 3*n : NULL,
 				   kernel->record_norm ? c->knorm : NULL, c->stream);
   CK (cudaGetLastError ());
+  c->forces_recorded = true;           /* the on-fluid forces (compute_forces_onfluid) are left in force[] */
   return GFSB200_OK;
 }
 

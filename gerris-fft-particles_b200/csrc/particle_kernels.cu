@@ -1424,6 +1424,26 @@ void gfsb200_launch_gather (int64_t n, const int32_t * perm, int ncols, const do
   gather_kernel<<<grid_for (n, 256), 256, 0, st>>> (n, perm, ncols, src, dst, id_src, id_dst);
 }
 
+/* dst_k[i] = src_k[perm[i]] for three plain arrays (the recorded forces) */
+__global__ void __launch_bounds__(256)
+gather3_kernel (int64_t n, const int32_t * __restrict__ perm,
+		const double * __restrict__ s0, const double * __restrict__ s1, const double * __restrict__ s2,
+		double * __restrict__ d0, double * __restrict__ d1, double * __restrict__ d2)
+{
+  const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t j = perm[i];
+  d0[i] = s0[j]; d1[i] = s1[j]; d2[i] = s2[j];
+}
+
+void gfsb200_launch_gather3 (int64_t n, const int32_t * perm, const double * s0, const double * s1,
+			     const double * s2, double * d0, double * d1, double * d2, cudaStream_t st)
+{
+  gfsb200_launch_counter += 1;
+  if (n <= 0) return;
+  gather3_kernel<<<grid_for (n, 256), 256, 0, st>>> (n, perm, s0, s1, s2, d0, d1, d2);
+}
+
 void gfsb200_launch_iota (int64_t n, int32_t * a, cudaStream_t st)
 {
   gfsb200_launch_counter += 1;

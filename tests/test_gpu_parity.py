@@ -689,6 +689,35 @@ def test_inertial_needs_the_previous_field():
 _periodic_world = helpers.periodic_world
 
 
+def test_recorded_forces_follow_their_particles(ctx):
+    """the force a step records per particle (particulate->force) stays with the particle
+    when the list is re-sorted or compacted (cull, BC drop) afterwards"""
+    w, sim, ptrs, idx = setup("ring3", ctx)
+    parts = worlds.make_particles(w, 5000)
+    ctx.particles_upload(**parts)
+    ctx.step(w.step_params(record_forces=True))
+    before = ctx.particles_download(forces=True, ids=True)
+    ctx.sort()
+    after = ctx.particles_download(forces=True, ids=True)
+    assert not np.array_equal(before["id"], after["id"])
+    a, b = np.argsort(before["id"]), np.argsort(after["id"])
+    for k in ("fx", "fy", "fz", "x", "vx"):
+        assert np.array_equal(before[k][a], after[k][b]), k
+    # push a third of the particles out, cull: the survivors keep their forces
+    x = after["x"].copy()
+    x[::3] = 5.0
+    moved = dict(after, x=x)
+    ctx.particles_upload(**{k: moved[k] for k in ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")})
+    ctx.step(w.step_params(record_forces=True))
+    full = ctx.particles_download(forces=True, ids=True)
+    removed = ctx.cull()
+    assert removed == len(x[::3])
+    kept = ctx.particles_download(forces=True, ids=True)
+    sel = np.isin(full["id"], kept["id"])
+    for k in ("fx", "fy", "fz"):
+        assert np.array_equal(full[k][sel], kept[k]), k
+
+
 def test_escaped_count_matches_host_locate(ctx):
     """gfsb200_escaped_count = number of particles whose new position gfs_domain_locate
     rejects, which is what gfs_particle_bc would find one locate at a time"""
