@@ -63,6 +63,7 @@ typedef struct {
   gboolean resident;
   gboolean mpi;                         /* parallel run: gfs_particle_bc every event (it also receives) */
   gboolean host_stale;                  /* the device holds newer particle state than the objects */
+  gboolean uploaded;                    /* device_current had to upload the objects */
   gboolean syncing;                     /* inside sync_down (its own removals must not recurse) */
   GfsParticleList * plist;
   GfsVariable * alpha_var, * mu_var;    /* PhysicalParams alpha = <variable>; GfsDiffusion.mu (src/source.c:941-946) */
@@ -615,10 +616,12 @@ void gfsb200_module_sync (GfsParticleList * plist)
 static gint64 device_current (B200State * s, GfsParticleList * plist)
 {
   watch_list (s, plist);
+  s->uploaded = FALSE;
   if (s->resident && s->host_stale && s->list_known)
     return s->n_obj;                      /* nothing on the host has changed since the last step */
   if (s->host_stale)
     sync_down (s);
+  s->uploaded = TRUE;
   return upload_particles (s, plist);
 }
 
@@ -680,6 +683,7 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
   ListVars lv;
   B200State * s;
   gint64 removed = 0, escaped = 0, n_up;
+  gboolean carried;
   gdouble t[7];
   gint k;
 
@@ -703,7 +707,9 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
      (FeedParticle, DropletToParticle, outputs and BCs all mutate them); a
      resident mode that skips the two copies when nothing on the host touched
      the list is the next step ("host object sync"). */
+  carried = s->resident && s->host_stale && s->list_known;   /* what device_current is about to decide */
   n_up = device_current (s, plist);
+  carried = carried && !s->uploaded;
   t[3] = wall ();
   par.record_forces = 1;
   /* cull + step on the device; the BCs stay on the host in this binding because
@@ -712,21 +718,26 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
      gfsb200_tree_set_periodic and call gfsb200_particle_list_event, which wraps
      and drops on the device (gfsb200_particle_bc). */
   par.track_escapes = par.n_forces > 0;
+  /* remove_particles_not_in_domain (:955-969) is a whole pass (locate + flag + select).  It is
+     skipped when no particle can be outside: the device state was carried over from the last
+     event (resident mode), in which the step kernel counted no particle leaving, and nothing on
+     the host has touched the list since.  (It cannot simply run after the step instead: the
+     particles that leave during this step must reach gfs_particle_bc, not the cull.) */
+  if (!(carried && par.track_escapes) &&
+      gfsb200_particles_cull (s->ctx, &removed) != GFSB200_OK)
+    g_error ("particulates (B200): %s", gfsb200_last_error ());
+  if (gfsb200_step (s->ctx, &par) != GFSB200_OK)
+    g_error ("particulates (B200): %s", gfsb200_last_error ());
   if (par.track_escapes) {
-    /* the step kernel leaves a particle that is outside the domain untouched and counts it:
-       the cull pass (remove_particles_not_in_domain :955-969) only runs when there is one */
     gint64 outside = 0;
-    if (gfsb200_step (s->ctx, &par) != GFSB200_OK ||
-	gfsb200_step_counts (s->ctx, &escaped, &outside) != GFSB200_OK)
+    if (gfsb200_step_counts (s->ctx, &escaped, &outside) != GFSB200_OK)
       g_error ("particulates (B200): %s", gfsb200_last_error ());
+    if (outside > 0)
+      g_error ("particulates (B200): %lld particles of a carried-over list are outside the domain",
+	       (long long) outside);
     if (s->resident && escaped > 0)
       patch_pos_old (s, escaped);
-    if (outside > 0 && gfsb200_particles_cull (s->ctx, &removed) != GFSB200_OK)
-      g_error ("particulates (B200): %s", gfsb200_last_error ());
   }
-  else if (gfsb200_particles_cull (s->ctx, &removed) != GFSB200_OK ||
-	   gfsb200_step (s->ctx, &par) != GFSB200_OK)
-    g_error ("particulates (B200): %s", gfsb200_last_error ());
   t[4] = wall ();
   if (s->resident && par.track_escapes && removed == 0 && escaped == 0 && s->list_known) {
     /* nothing the host has to act on: the objects are refreshed when somebody asks */
