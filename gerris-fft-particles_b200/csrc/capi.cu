@@ -102,6 +102,7 @@ struct gfsb200_ctx {
   size_t cub_tmp_bytes;
   double ** d_ptr_table;       /* [2][NCOL] device copy of col pointers */
   /* escape tracking for gfs_particle_bc */
+  bool mark_outside;           /* the next tracked step flags (c->flag) the particles outside before it */
   bool forces_recorded;        /* force[] holds what the last step (or on-fluid pass) recorded for the resident list */
   int * esc_count;             /* [4]: escaped, wrapped, dropped, outside the domain before the step */
   int32_t * esc_idx;
@@ -205,6 +206,7 @@ extern "C" int gfsb200_ctx_create (int device, gfsb200_ctx ** out)
   c->d_child0 = c->d_neighbor = c->d_la_slot = c->d_vtx_off = c->d_vtx_cell = c->d_leaf_vtx = NULL;
   c->d_level = c->d_info = NULL; c->d_vtx_w = c->d_vtx_wuni = NULL; c->d_parent = NULL;
   c->esc_count = NULL; c->esc_idx = NULL; c->esc_old = NULL; c->esc_cap = 0; c->esc_armed = false;
+  c->mark_outside = false;
   c->forces_recorded = false;
   for (int i = 0; i < 5; i++) c->d_field[i] = NULL;
   for (int i = 0; i < 3; i++) c->d_prev[i] = NULL;
@@ -817,6 +819,13 @@ extern "C" int gfsb200_step (gfsb200_ctx * c, const gfsb200_step_params * p)
     CK (cudaMemsetAsync (c->esc_count, 0, 4*sizeof (int), c->stream));
     S.track_escapes = 1;
     S.esc_cap = c->esc_cap; S.esc_count = c->esc_count; S.esc_idx = c->esc_idx; S.esc_old = c->esc_old;
+    S.keep = NULL;
+    if (c->mark_outside) {
+      /* list event: the particles the kernel finds outside before the step are flagged, so that
+	 remove_particles_not_in_domain becomes a compaction after the step, and only if needed */
+      CK (cudaMemsetAsync (c->flag, 1, (size_t) (c->n ? c->n : 1), c->stream));
+      S.keep = c->flag;
+    }
     c->esc_armed = true;
   }
   DevParticles P = particles_view (c);
@@ -1001,7 +1010,10 @@ extern "C" int gfsb200_particles_cull (gfsb200_ctx * c, int64_t * n_removed)
   return apply_permutation (c, kept);
 }
 
-extern "C" int gfsb200_particle_bc (gfsb200_ctx * c, int64_t * n_wrapped, int64_t * n_dropped)
+/* flags_ready: c->flag already holds 1 / 0 (kept / outside before the step, `outside` of them);
+ * the particles dropped here are cleared in the same array and ONE compaction removes both */
+static int particle_bc_impl (gfsb200_ctx * c, bool flags_ready, int outside, int64_t * n_wrapped,
+			     int64_t * n_dropped)
 {
   if (n_wrapped) *n_wrapped = 0;
   if (n_dropped) *n_dropped = 0;
@@ -1013,19 +1025,23 @@ extern "C" int gfsb200_particle_bc (gfsb200_ctx * c, int64_t * n_wrapped, int64_
   int counts[3] = { 0, 0, 0 };
   CK (cudaMemcpyAsync (counts, c->esc_count, sizeof (int), cudaMemcpyDeviceToHost, c->stream));
   CK (cudaStreamSynchronize (c->stream));
-  if (counts[0] == 0) return GFSB200_OK;
+  if (counts[0] == 0 && outside == 0) return GFSB200_OK;
   if (counts[0] > c->esc_cap)
     return gfsb200_fail (GFSB200_ERR_STATE, "particle_bc: %d particles left the domain in one step, more "
 			 "than the %d tracked (1/16 of the list)", counts[0], c->esc_cap);
   DevParticles P = particles_view (c);
-  CK (cudaMemsetAsync (c->flag, 1, (size_t) P.n, c->stream));
-  gfsb200_launch_particle_bc (&c->T, &P, counts[0], c->esc_idx, c->esc_old, c->flag, c->esc_count + 1,
-			      c->stream);
-  CK (cudaGetLastError ());
-  CK (cudaMemcpyAsync (counts, c->esc_count, 3*sizeof (int), cudaMemcpyDeviceToHost, c->stream));
-  CK (cudaStreamSynchronize (c->stream));
+  if (!flags_ready)
+    CK (cudaMemsetAsync (c->flag, 1, (size_t) P.n, c->stream));
+  if (counts[0] > 0) {
+    gfsb200_launch_particle_bc (&c->T, &P, counts[0], c->esc_idx, c->esc_old, c->flag, c->esc_count + 1,
+				c->stream);
+    CK (cudaGetLastError ());
+    CK (cudaMemcpyAsync (counts, c->esc_count, 3*sizeof (int), cudaMemcpyDeviceToHost, c->stream));
+    CK (cudaStreamSynchronize (c->stream));
+  }
   if (n_wrapped) *n_wrapped = counts[1];
   if (n_dropped) *n_dropped = counts[2];
+  counts[2] += outside;
   if (counts[2] == 0) return GFSB200_OK;
   /* compact the list without the dropped particles (order kept) */
   gfsb200_launch_iota (P.n, c->perm, c->stream);
@@ -1035,6 +1051,11 @@ extern "C" int gfsb200_particle_bc (gfsb200_ctx * c, int64_t * n_wrapped, int64_
   if (r) return r;
   CK (gfsb200_cub_select_flagged (c->cub_tmp, &bytes, c->perm, c->flag, c->perm2, c->d_count, P.n, c->stream));
   return apply_permutation (c, P.n - counts[2]);
+}
+
+extern "C" int gfsb200_particle_bc (gfsb200_ctx * c, int64_t * n_wrapped, int64_t * n_dropped)
+{
+  return particle_bc_impl (c, false, 0, n_wrapped, n_dropped);
 }
 
 extern "C" int gfsb200_escaped_count (gfsb200_ctx * c, int64_t * n_escaped)
@@ -1103,21 +1124,25 @@ extern "C" int gfsb200_particle_list_event (gfsb200_ctx * c, const gfsb200_step_
     if (n_removed) *n_removed = culled;
     return GFSB200_OK;
   }
-  /* The step kernel leaves a particle that is outside the domain untouched and counts it, and it
-     counts those that leave: cull -> step -> BC and step -> BC -> cull give the same list, and in
-     the second order the cull pass (locate + flag + select, about as long as the step itself) and
-     the BC pass only run when their count is not zero -- one 16-byte read-back decides. */
+  /* The step kernel leaves a particle that is outside the domain untouched; here it also flags
+     and counts it, and it counts those that leave.  remove_particles_not_in_domain then is a
+     compaction AFTER the step, shared with the particles gfs_particle_bc drops -- the same list
+     as cull -> step -> BC -- and neither the cull pass (locate + flag + select, about as long as
+     the step itself) nor the BC pass runs when its count is zero: one 16-byte read-back decides. */
   q.track_escapes = 1;
-  if ((r = gfsb200_step (c, &q))) return r;
+  c->mark_outside = true;
+  r = gfsb200_step (c, &q);
+  c->mark_outside = false;
+  if (r) return r;
   int counts[4] = { 0, 0, 0, 0 };
   CK (cudaMemcpyAsync (counts, c->esc_count, 4*sizeof (int), cudaMemcpyDeviceToHost, c->stream));
   CK (cudaStreamSynchronize (c->stream));
-  if (counts[0] > 0) {
-    if ((r = gfsb200_particle_bc (c, NULL, &dropped))) return r;
+  culled = counts[3];
+  if (counts[0] > 0 || culled > 0) {
+    if ((r = particle_bc_impl (c, true, (int) culled, NULL, &dropped))) return r;
   }
   else
     c->esc_armed = false;
-  if (counts[3] > 0 && (r = gfsb200_particles_cull (c, &culled))) return r;
   if (n_removed) *n_removed = culled + dropped;
   return GFSB200_OK;
 }

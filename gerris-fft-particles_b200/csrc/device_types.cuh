@@ -95,6 +95,7 @@ struct DevStep {
   int * esc_count;
   int32_t * esc_idx;           /* [esc_cap] particle index */
   double * esc_old;            /* [esc_cap][3] position before the step */
+  unsigned char * keep;        /* [n] or NULL: cleared for a particle that was outside the domain BEFORE the step */
 };
 
 /* compact every third (second) bit of a Morton key back into an integer */

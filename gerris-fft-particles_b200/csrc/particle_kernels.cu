@@ -539,8 +539,10 @@ step_kernel (DevTree T, DevField fld, DevParticles P, DevStep S)
   if (REC)
     P.cell[i] = cell_index<DIM, LATTICE> (T, L);
   if (L.cell < 0) {   /* outside: gfs_particle_list_event removes it first (:987) */
-    if (S.track_escapes)
+    if (S.track_escapes) {
       atomicAdd (S.esc_count + 3, 1);         /* lets the list event skip its cull pass when 0 */
+      if (S.keep) S.keep[i] = 0;
+    }
     return;
   }
 
@@ -731,8 +733,10 @@ step_kernel_pipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_tile
 	  __stcs (P.z + i, z); __stcs (P.vz + i, vz);
 	}
       }
-      else if (S.track_escapes)
+      else if (S.track_escapes) {
 	atomicAdd (S.esc_count + 3, 1);       /* outside the domain before the step */
+	if (S.keep) S.keep[i] = 0;
+      }
     }
   }
 }
