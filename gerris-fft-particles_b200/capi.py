@@ -42,6 +42,8 @@ class TreeView(C.Structure):
         ("n_vertices", C.c_int32), ("vtx_off", C.POINTER(C.c_int32)), ("vtx_cell", C.POINTER(C.c_int32)),
         ("vtx_w", C.POINTER(C.c_double)), ("leaf_vtx", C.POINTER(C.c_int32)),
         ("lattice_level", C.c_int32),
+        ("solid_a", C.POINTER(C.c_double)), ("solid_cm", C.POINTER(C.c_double)),
+        ("solid_s", C.POINTER(C.c_double)),
     ]
 
 
@@ -92,6 +94,7 @@ def lib() -> C.CDLL:
         "gfsb200_tree_corner_sweep": (i32, [vp]),
         "gfsb200_tree_add_boundary": (i32, [vp, i32, i32]),
         "gfsb200_tree_set_periodic": (i32, [vp, i32, i32, i32]),
+        "gfsb200_tree_set_solid": (i32, [vp, i32, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "gfsb200_tree_finalize": (i32, [vp, vp]),
         "gfsb200_tree_build_stencils": (i32, [vp]),
         "gfsb200_tree_get_view": (i32, [vp, C.POINTER(TreeView)]),
@@ -254,6 +257,13 @@ class Tree:
         _check(self._lib.gfsb200_tree_get_view(self.handle, C.byref(v)), "get_view")
         return TreeArrays(self, v)
 
+    def set_solid(self, cell: int, a: float, cm, s=None):
+        """mixed (solid-cut) cell of the finalized tree: fluid fraction, centre of mass and
+        (optionally) the 2*dim face fractions"""
+        v = (C.c_double * 3)(*[float(x) for x in list(cm) + [0.0] * (3 - len(cm))])
+        sv = None if s is None else (C.c_double * 6)(*[float(x) for x in list(s) + [1.0] * (6 - len(s))])
+        _check(self._lib.gfsb200_tree_set_solid(self.handle, int(cell), float(a), v, sv), "set_solid")
+
     def corner_interpolator(self, cell: int, k: int):
         cells = (C.c_int32 * 29)()
         w = (C.c_double * 29)()
@@ -286,6 +296,9 @@ class TreeArrays:
         self.la_slot = as_arr(v.la_slot, shape=(int(np.prod(self.la_n)),))
         self.n_vertices = v.n_vertices
         self.lattice_level = v.lattice_level
+        self.solid_a = as_arr(v.solid_a, shape=(n,)) if bool(v.solid_a) else None
+        self.solid_cm = as_arr(v.solid_cm, shape=(n, 3)) if bool(v.solid_cm) else None
+        self.solid_s = as_arr(v.solid_s, shape=(n, 2 * dim)) if bool(v.solid_s) else None
         if v.n_vertices and bool(v.vtx_off):
             self.vtx_off = as_arr(v.vtx_off, shape=(v.n_vertices + 1,))
             ne = int(self.vtx_off[-1])

@@ -78,6 +78,7 @@ struct gfsb200_ctx {
   bool have_tree;
   DevTree T;
   int32_t * d_child0, * d_neighbor, * d_la_slot, * d_vtx_off, * d_vtx_cell, * d_leaf_vtx, * d_parent;
+  double * d_solid_a, * d_solid_s;
   uint8_t * d_level, * d_info;
   double * d_vtx_w, * d_vtx_wuni;
   /* field */
@@ -147,6 +148,8 @@ static void free_tree (gfsb200_ctx * c)
   cudaFree (c->d_child0); cudaFree (c->d_neighbor); cudaFree (c->d_la_slot);
   cudaFree (c->d_vtx_off); cudaFree (c->d_vtx_cell); cudaFree (c->d_leaf_vtx); cudaFree (c->d_parent);
   c->d_parent = NULL;
+  cudaFree (c->d_solid_a); c->d_solid_a = NULL;
+  cudaFree (c->d_solid_s); c->d_solid_s = NULL;
   cudaFree (c->d_level); cudaFree (c->d_info); cudaFree (c->d_vtx_w); cudaFree (c->d_vtx_wuni);
   c->d_child0 = c->d_neighbor = c->d_la_slot = c->d_vtx_off = c->d_vtx_cell = c->d_leaf_vtx = NULL;
   c->d_level = c->d_info = NULL; c->d_vtx_w = c->d_vtx_wuni = NULL;
@@ -205,6 +208,7 @@ extern "C" int gfsb200_ctx_create (int device, gfsb200_ctx ** out)
   c->have_tree = c->have_field = c->own_field = false;
   c->d_child0 = c->d_neighbor = c->d_la_slot = c->d_vtx_off = c->d_vtx_cell = c->d_leaf_vtx = NULL;
   c->d_level = c->d_info = NULL; c->d_vtx_w = c->d_vtx_wuni = NULL; c->d_parent = NULL;
+  c->d_solid_a = c->d_solid_s = NULL;
   c->esc_count = NULL; c->esc_idx = NULL; c->esc_old = NULL; c->esc_cap = 0; c->esc_armed = false;
   c->mark_outside = false;
   c->forces_recorded = false;
@@ -290,6 +294,10 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
       (t->child0[i] < 0 ? CHILD_LEAF : t->child0[i]);
     int k = t->parent[i] < 0 ? 0 : i - t->child0[t->parent[i]];
     unsigned regular = (t->flags[i] & GFSB200_CELL_LEAF) ? CELL_REGULAR : 0;
+    if (t->solid_a && t->solid_a[i] != 1.)
+      regular = 0;                    /* a mixed cell may have closed faces (gfs_cell_face) */
+    else if (t->solid_cm && t->solid_cm[3*i] == t->solid_cm[3*i])
+      regular = 0;
     for (int d = 0; d < t->ndir && regular; d++) {
       int32_t nb = t->neighbor[(int64_t) i*t->ndir + d];
       if (nb < 0 || t->level[nb] != t->level[i] || !(t->flags[nb] & GFSB200_CELL_LEAF))
@@ -318,6 +326,8 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
   if ((r = dev_alloc_copy (&c->d_vtx_wuni, (const double *) wuni.data (), (size_t) t->n_vertices, c->stream))) return r;
   if ((r = dev_alloc_copy (&c->d_leaf_vtx, (const int32_t *) t->leaf_vtx, (size_t) n*nc, c->stream))) return r;
   if ((r = dev_alloc_copy (&c->d_parent, (const int32_t *) t->parent, (size_t) n, c->stream))) return r;
+  if (t->solid_a && (r = dev_alloc_copy (&c->d_solid_a, (const double *) t->solid_a, (size_t) n, c->stream))) return r;
+  if (t->solid_s && (r = dev_alloc_copy (&c->d_solid_s, (const double *) t->solid_s, (size_t) n*t->ndir, c->stream))) return r;
   CK (cudaStreamSynchronize (c->stream));   /* host staging vectors go out of scope */
 
   DevTree & T = c->T;
@@ -344,6 +354,8 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
   T.vtx_off = c->d_vtx_off; T.vtx_cell = c->d_vtx_cell; T.vtx_w = c->d_vtx_w; T.leaf_vtx = c->d_leaf_vtx;
   T.vtx_wuni = c->d_vtx_wuni;
   T.parent = c->d_parent;
+  T.solid_a = c->d_solid_a;            /* NULL when the tree has no mixed cell */
+  T.solid_s = c->d_solid_s;
   for (int rr = 0; rr < GFSB200_MAX_DEV_ROOTS; rr++)
     for (int d = 0; d < 6; d++)
       T.periodic[rr][d] = rr < t->n_roots ? (signed char) t->periodic[rr][d] : -1;
@@ -358,7 +370,7 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
      order), so that the cell pass can address them arithmetically instead of through the
      CSR tables.  Any deviation keeps the tables. */
   T.lattice_pattern = -1;
-  if (T.lattice_n1 > 0 && T.top_levels >= 2 && !getenv ("GFSB200_NO_LATTICE_PATTERN")) {
+  if (T.lattice_n1 > 0 && T.top_levels >= 2 && !t->solid_a && !getenv ("GFSB200_NO_LATTICE_PATTERN")) {
     const int dim = t->dim, nc = 1 << dim, n1 = T.lattice_n1, nn = n1 - 1;
     double wexp = NAN;                /* the common weight (2^-dim up to the rounding of the
 					 reference's sequential normalisation) */

@@ -67,7 +67,16 @@ __device__ __forceinline__ unsigned spread_bits2 (unsigned v)
   return v;
 }
 
-/* average_neighbor_value, src/fluid.c:64-93 (no solid fractions) */
+/* gfs_cell_face, src/fluid.c:42-52: a mixed cell has no neighbour through a closed face */
+template <int DIM>
+__device__ __forceinline__ int face_neighbor (const DevTree & T, int cell, int d)
+{
+  if (T.solid_s && !(T.solid_s[(int64_t) cell*2*DIM + d] > 0.))
+    return -1;
+  return T.neighbor[(int64_t) cell*2*DIM + d];
+}
+
+/* average_neighbor_value, src/fluid.c:64-93 */
 template <int DIM>
 __device__ double average_neighbor_value (const DevTree & T, const double * __restrict__ F,
 					  int cell, int nb, int d, double * x)
@@ -83,8 +92,10 @@ __device__ double average_neighbor_value (const DevTree & T, const double * __re
       continue;
     int c = c0 + k;
     if (T.child0[c] != CHILD_DESTROYED && F[c] != GFSB200_NODATA) {
-      a += 1.;
-      av += 1.*F[c];
+      /* GFS_IS_MIXED (child) ? solid->s[od] : 1. -- the table holds 1 for cells that are not mixed */
+      const double w = T.solid_s ? T.solid_s[(int64_t) c*2*DIM + od] : 1.;
+      a += w;
+      av += w*F[c];
     }
   }
   if (a > 0.) {
@@ -102,9 +113,8 @@ __device__ Grad2 interpolate_perp (const DevTree & T, const double * __restrict_
 				   int cell, int d1, int d2, double x, double y)
 {
   Grad2 p = { 1., 0. };
-  const int nd = 2*DIM;
   if (DIM == 3) {
-    int f1 = T.neighbor[(int64_t) cell*nd + d1];
+    int f1 = face_neighbor<DIM> (T, cell, d1);
     if (f1 >= 0) {
       double y1 = 1.;
       double p1 = average_neighbor_value<DIM> (T, F, cell, f1, d1, &y1);
@@ -115,7 +125,7 @@ __device__ Grad2 interpolate_perp (const DevTree & T, const double * __restrict_
       }
     }
   }
-  int f2 = T.neighbor[(int64_t) cell*nd + d2];
+  int f2 = face_neighbor<DIM> (T, cell, d2);
   if (f2 >= 0) {
     double x2 = 1.;
     double p2 = average_neighbor_value<DIM> (T, F, cell, f2, d2, &x2);
@@ -161,9 +171,9 @@ __device__ double neighbor_value (const DevTree & T, const double * __restrict__
 template <int DIM>
 __device__ double center_gradient (const DevTree & T, const double * __restrict__ F, int cell, int c)
 {
-  const int nd = 2*DIM, d = 2*c;
-  const int f1 = T.neighbor[(int64_t) cell*nd + (d ^ 1)];
-  const int f2 = T.neighbor[(int64_t) cell*nd + d];
+  const int d = 2*c;
+  const int f1 = face_neighbor<DIM> (T, cell, d ^ 1);
+  const int f2 = face_neighbor<DIM> (T, cell, d);
   const double v0 = F[cell];
   if (f1 >= 0) {
     double x1 = 1., v1;

@@ -34,6 +34,8 @@ struct DevTree {
   const uint8_t * level;       /* absolute level */
   const uint8_t * info;        /* flags (low 3 bits) | CELL_REGULAR | child id << 4 */
   const int32_t * parent;      /* [n_cells], -1 for roots */
+  const double * solid_a;      /* [n_cells] fluid fraction of mixed (solid-cut) cells, 1 elsewhere; NULL: none */
+  const double * solid_s;      /* [n_cells][2*dim] face fractions of mixed cells, 1 elsewhere; NULL: none */
   signed char periodic[GFSB200_MAX_DEV_ROOTS][6];   /* box root, side -> matching box root or -1 */
   /* stencils */
   int n_vertices;

@@ -94,6 +94,9 @@ static void free_final (gfsb200_tree * t)
   t->n_vertices = 0;
   t->lattice_level = -1;
   t->finalized = 0;
+  free (t->solid_a); t->solid_a = NULL;          /* indexed like the finalized tree */
+  free (t->solid_cm); t->solid_cm = NULL;
+  free (t->solid_s); t->solid_s = NULL;
 }
 
 void gfsb200_tree_free (gfsb200_tree * t)
@@ -101,7 +104,51 @@ void gfsb200_tree_free (gfsb200_tree * t)
   if (!t) return;
   free_final (t);
   free (t->parent); free (t->child0); free (t->level); free (t->flags); free (t->pos);
+  free (t->solid_a); free (t->solid_cm); free (t->solid_s);
   free (t);
+}
+
+/* GFS_IS_MIXED cells (src/fluid.h:93): the two members of their GfsSolidVector the
+ * particulate path reads -- the centre of mass enters the corner-interpolator weights
+ * (distance (), src/fluid.c:2983-3003), the fluid fraction gfs_cell_volume
+ * (src/domain.h:503-508), the face fractions gfs_cell_face and average_neighbor_value
+ * (src/fluid.c:42-52, 64-93), i.e. the gradients.  Indices are those of the finalized tree. */
+int gfsb200_tree_set_solid (gfsb200_tree * t, int cell, double a, const double cm[3], const double * s)
+{
+  if (!t || !t->finalized)
+    return gfsb200_fail (GFSB200_ERR_STATE, "set_solid: tree not finalized");
+  if (cell < 0 || cell >= t->n_cells || !cm || !(a > 0.) || !(a <= 1.))
+    return gfsb200_fail (GFSB200_ERR_ARG, "set_solid: bad argument");
+  if (!t->solid_a) {
+    t->solid_a = malloc ((size_t) t->n_cells*sizeof (double));
+    t->solid_cm = malloc ((size_t) t->n_cells*3*sizeof (double));
+    t->solid_s = malloc ((size_t) t->n_cells*t->ndir*sizeof (double));
+    if (!t->solid_a || !t->solid_cm || !t->solid_s) {
+      free (t->solid_a); free (t->solid_cm); free (t->solid_s);
+      t->solid_a = t->solid_cm = t->solid_s = NULL;
+      return gfsb200_fail (GFSB200_ERR_NOMEM, "set_solid: out of memory");
+    }
+    for (int32_t i = 0; i < t->n_cells; i++) {
+      t->solid_a[i] = 1.;
+      t->solid_cm[3*i] = t->solid_cm[3*i + 1] = t->solid_cm[3*i + 2] = NAN;
+      for (int d = 0; d < t->ndir; d++)
+	t->solid_s[(size_t) i*t->ndir + d] = 1.;
+    }
+  }
+  t->solid_a[cell] = a;
+  for (int d = 0; d < t->ndir; d++) {
+    if (s && !(s[d] >= 0. && s[d] <= 1.))
+      return gfsb200_fail (GFSB200_ERR_ARG, "set_solid: face fraction %g out of [0,1]", s[d]);
+    t->solid_s[(size_t) cell*t->ndir + d] = s ? s[d] : 1.;
+  }
+  for (int k = 0; k < 3; k++)
+    t->solid_cm[3*cell + k] = k < t->dim ? cm[k] : 0.;
+  /* any stencil table built before is stale */
+  free (t->vtx_off); free (t->vtx_cell); free (t->vtx_w); free (t->leaf_vtx);
+  t->vtx_off = NULL; t->vtx_cell = NULL; t->vtx_w = NULL; t->leaf_vtx = NULL;
+  t->n_vertices = 0;
+  t->lattice_level = -1;
+  return GFSB200_OK;
 }
 
 int gfsb200_tree_add_root (gfsb200_tree * t, const double pos[3], int level, int is_box)
@@ -674,5 +721,8 @@ int gfsb200_tree_get_view (const gfsb200_tree * t, gfsb200_tree_view * v)
   v->n_vertices = t->n_vertices;
   v->vtx_off = t->vtx_off; v->vtx_cell = t->vtx_cell; v->vtx_w = t->vtx_w; v->leaf_vtx = t->leaf_vtx;
   v->lattice_level = t->leaf_vtx ? t->lattice_level : -1;
+  v->solid_a = t->solid_a;
+  v->solid_cm = t->solid_cm;
+  v->solid_s = t->solid_s;
   return GFSB200_OK;
 }

@@ -42,6 +42,10 @@ struct gfsb200_tree {
   double * vtx_w;
   int32_t * leaf_vtx;
   int lattice_level;             /* >= 0: vertices are numbered row-major on the lattice of that level */
+  /* mixed (solid-cut) cells, GfsSolidVector of src/fluid.h:54-59: NULL when the tree has none */
+  double * solid_a;              /* [n] fluid fraction a, 1 for a cell that is not mixed */
+  double * solid_cm;             /* [n][3] centre of mass of the fluid part, NaN for a cell that is not mixed */
+  double * solid_s;              /* [n][ndir] fluid fraction of each face, 1 for a cell that is not mixed */
 };
 
 int gfsb200_fail (int code, const char * fmt, ...);

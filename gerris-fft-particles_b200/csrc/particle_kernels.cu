@@ -887,7 +887,9 @@ deposit_kernel (DevTree T, DevField fld, DevParticles P, DevStep S, double * __r
 					      Fx, Fy, Fz, rho);
 	if (!PROG && S.mutates_mass)       /* compute_forces_onfluid runs GfsForceAddedMass too */
 	  P.mass[i] = mass;
-	const double k = -inv_cellvol/rho;
+	/* the single-cell limit of diffuse_force (:2158-2175): gfs_cell_volume, i.e. times the
+	   fluid fraction in a mixed cell (the void fraction above uses ftt_cell_volume, :1931) */
+	const double k = -(T.solid_a ? inv_cellvol/T.solid_a[cell] : inv_cellvol)/rho;
 	ax = Fx*k; ay = Fy*k; az = Fz*k;
       }
     }
@@ -1200,7 +1202,10 @@ smoothed_deposit_kernel (DevTree T, DevField fld, DevParticles P, double rho_con
   double volume = 0., correction = 0.;
   traverse_kernel_support<DIM> (T, px, py, pz, rkernel,
     [&] (int cell, double cx, double cy, double cz, double half) {
-      const double h = 2.*half, cellvol = DIM == 3 ? h*h*h : h*h;     /* powers of two: exact */
+      const double h = 2.*half;
+      double cellvol = DIM == 3 ? h*h*h : h*h;                        /* powers of two: exact */
+      if (T.solid_a)                                                  /* gfs_cell_volume, src/domain.h:503-508 */
+	cellvol = __dmul_rn (cellvol, T.solid_a[cell]);
       volume = __dadd_rn (volume, cellvol);
       const double qx = (cx - px)*inv_rb, qy = (cy - py)*inv_rb;
       const double qz = DIM == 3 ? (fixz ? (cz - pz)*inv_rb : qz_const) : 0.;
@@ -1219,7 +1224,9 @@ smoothed_deposit_kernel (DevTree T, DevField fld, DevParticles P, double rho_con
   traverse_kernel_support<DIM> (T, px, py, pz, rkernel,
     [&] (int cell, double cx, double cy, double cz, double half) {
       const double inv_h = __longlong_as_double ((2045LL << 52) - __double_as_longlong (half));   /* 1/(2 half) */
-      const double inv_cellvol = DIM == 3 ? inv_h*inv_h*inv_h : inv_h*inv_h;
+      double inv_cellvol = DIM == 3 ? inv_h*inv_h*inv_h : inv_h*inv_h;
+      if (T.solid_a)
+	inv_cellvol = inv_cellvol/T.solid_a[cell];                    /* mixed cell: V_cell = h^dim a */
       const double ir = fld.alpha ? fld.alpha[cell] : inv_rho;       /* 1/rho = alpha */
       const double qx = (cx - px)*inv_rb, qy = (cy - py)*inv_rb;
       const double qz = DIM == 3 ? (fixz ? (cz - pz)*inv_rb : qz_const) : 0.;

@@ -197,7 +197,7 @@ static int do_path (const gfsb200_tree * t, int32_t cell, int slot, int32_t * n,
 }
 
 /* gfs_cell_corner_interpolator, src/fluid.c:3015-3069, for non-centred
- * variables on a tree without solid (mixed) cells */
+ * variables (U,V,W: src/variable.c:114); mixed cells as set by gfsb200_tree_set_solid */
 static void corner_interp (const gfsb200_tree * t, int32_t cell, const int * d, interp_t * inter)
 {
   int32_t n[8], c;
@@ -213,11 +213,31 @@ static void corner_interp (const gfsb200_tree * t, int32_t cell, const int * d, 
   double w = 0.;
   int boundaries = 0;
   const double diag = t->dim == 3 ? 0.866025403785 : 0.707106781185;  /* distance(), :2983-2992 */
+  /* ftt_corner_pos (cell, d), src/ftt.c:379-429: only needed next to mixed cells */
+  double corner[3] = { 0., 0., 0. };
+  if (t->solid_cm) {
+    const double size = ldexp (1., -t->level[cell]);
+    double rel[3] = { 0., 0., 0. };
+    for (int l = 0; l < t->dim; l++)
+      rel[d[l] >> 1] += d[l] & 1 ? -0.5 : 0.5;
+    for (int l = 0; l < t->dim; l++)
+      corner[l] = t->pos[3*cell + l] + size*rel[l];
+  }
   inter->n = 0;
   for (int i = 0; i < ncells; i++)
     if (n[i] >= 0) {
       double size = ldexp (1., -t->level[n[i]]);
-      double a = 1./(size*diag + 1e-12);
+      double dist = size*diag;
+      if (t->solid_cm && t->solid_cm[3*n[i]] == t->solid_cm[3*n[i]]) {
+	/* U,V,W are not "centered" variables: a mixed cell is weighted by the distance of
+	   the corner to the centre of mass of its fluid part (:2993-3002) */
+	const double * cm = t->solid_cm + 3*n[i];
+	dist = t->dim == 3 ?
+	  sqrt ((cm[0] - corner[0])*(cm[0] - corner[0]) + (cm[1] - corner[1])*(cm[1] - corner[1]) +
+		(cm[2] - corner[2])*(cm[2] - corner[2])) :
+	  sqrt ((cm[0] - corner[0])*(cm[0] - corner[0]) + (cm[1] - corner[1])*(cm[1] - corner[1]));
+      }
+      double a = 1./(dist + 1e-12);
       inter->c[inter->n] = n[i];
       inter->w[inter->n++] = a;
       w += a;
@@ -503,7 +523,7 @@ int gfsb200_tree_build_stencils (gfsb200_tree * t)
 
   {
     const int L = t->max_level - t->root_level;
-    if (t->n_box_roots == 1 && t->complete_level == t->max_level && L >= 1 &&
+    if (!t->solid_cm && t->n_box_roots == 1 && t->complete_level == t->max_level && L >= 1 &&
 	L <= (t->dim == 3 ? 10 : 15) && !getenv ("GFSB200_GENERAL_STENCILS")) {
       int r = lattice_stencils (t);
       if (r > 0) return GFSB200_OK;

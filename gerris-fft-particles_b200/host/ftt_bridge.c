@@ -20,6 +20,21 @@
 /* GFS_FLAG_BOUNDARY (src/fluid.h:63): ghost cells of a GfsBoundary tree */
 #define BRIDGE_FLAG_BOUNDARY (1u << (FTT_FLAG_USER + 1))
 
+/* GfsSolidVector, src/fluid.h:54-59, and where GfsStateVector (src/fluid.h:44-52) keeps the
+   pointer to it: right after f[FTT_NEIGHBORS] (two doubles per face) */
+struct bridge_solid {
+  double s[FTT_NEIGHBORS];
+  double a, fv;
+  FttCell * merged;
+  FttVector cm, ca, v;
+};
+
+static const struct bridge_solid * state_solid (const FttCell * c)
+{
+  return c->data ? *(const struct bridge_solid * const *)
+    ((const char *) c->data + FTT_NEIGHBORS*2*sizeof (double)) : NULL;
+}
+
 struct gfsb200_ftt_map {
   int32_t n_cells;
   FttCell ** cell;            /* flat index -> FttCell */
@@ -58,7 +73,7 @@ int gfsb200_ftt_flatten (int n_roots, void * const * roots_, const int * is_box,
       if ((is_box[r] != 0) == pass)
 	order[no++] = r;
 
-  size_t cap = 1024, n = 0;
+  size_t cap = 1024, n = 0, n_mixed = 0;
   FttCell ** cells = malloc (cap*sizeof (FttCell *));
   int rc = GFSB200_OK;
   for (int j = 0; j < n_roots && rc >= 0; j++) {
@@ -89,13 +104,8 @@ int gfsb200_ftt_flatten (int n_roots, void * const * roots_, const int * is_box,
     FttCell * c = cells[head];
     if (FTT_CELL_IS_DESTROYED (c))
       continue;
-    /* GfsStateVector.solid (src/fluid.h:44-52) sits right after f[FTT_NEIGHBORS]:
-       mixed cells need solid fractions the flat tree does not carry */
-    if (c->data && *(void * const *) ((const char *) c->data + FTT_NEIGHBORS*2*sizeof (double))) {
-      bridge_error = "flatten: mixed (solid) cells are not supported on the device path";
-      rc = GFSB200_ERR_UNSUPPORTED;
-      break;
-    }
+    if (state_solid (c))
+      n_mixed++;
     if (FTT_CELL_IS_LEAF (c))
       continue;
     struct _FttOct * oct = c->children;
@@ -125,6 +135,15 @@ int gfsb200_ftt_flatten (int n_roots, void * const * roots_, const int * is_box,
 	if ((size_t) perm[i] != i) { bridge_error = "flatten: finalize permuted cells"; rc = GFSB200_ERR_STATE; break; }
     free (perm);
   }
+  /* mixed (solid-cut) cells: fluid fraction and centre of mass go with the tree */
+  if (rc >= 0 && n_mixed)
+    for (size_t i = 0; i < n && rc >= 0; i++) {
+      const struct bridge_solid * sv = FTT_CELL_IS_DESTROYED (cells[i]) ? NULL : state_solid (cells[i]);
+      if (sv) {
+	const double cm[3] = { sv->cm.x, sv->cm.y, sv->cm.z };
+	rc = gfsb200_tree_set_solid (t, (int) i, sv->a, cm, sv->s);
+      }
+    }
   if (rc < 0) {
     if (!*bridge_error) bridge_error = gfsb200_last_error ();
     gfsb200_tree_free (t);

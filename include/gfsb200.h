@@ -110,6 +110,17 @@ int gfsb200_tree_add_boundary (gfsb200_tree * t, int box_root, int side);
  * gfsb200_particle_bc.  Call after add_boundary / link_roots. */
 int gfsb200_tree_set_periodic (gfsb200_tree * t, int box_root, int side, int matching_box_root);
 
+/* Mixed (solid-cut) cell of a FINALIZED tree: fluid fraction a in (0,1], centre of mass of the
+ * fluid part and fluid fraction s[2*dim] of each face (GfsSolidVector.a / .cm / .s,
+ * src/fluid.h:54-59; s = NULL: all faces open).  The centre of mass enters the
+ * corner-interpolator weights (distance (), src/fluid.c:2983-3003), the fraction the cell
+ * volume of the force deposits (gfs_cell_volume, src/domain.h:503-508), the face fractions the
+ * gradients behind the vorticity and the inertial force (a closed face has no neighbour:
+ * gfs_cell_face, src/fluid.c:42-52; finer neighbours are averaged with their face fractions:
+ * average_neighbor_value, :64-93).  Cells that are entirely solid are destroyed cells of the
+ * tree (split's destroyed_mask).  Call before build_stencils. */
+int gfsb200_tree_set_solid (gfsb200_tree * t, int cell, double a, const double cm[3], const double * s);
+
 /* Reorders to level order, builds neighbour tables, centres, locate array.
  * perm (may be NULL, else n_cells ints) receives old index -> new index. */
 int gfsb200_tree_finalize (gfsb200_tree * t, int32_t * perm);
@@ -144,6 +155,9 @@ typedef struct {
 					 order, src/fluid.c:2588-2606), -1 for non-leaves */
   int32_t lattice_level;              /* >= 0: all leaves at this level and vertex ids are
 					 row-major on its (2^L + 1)^dim lattice; else -1 */
+  const double * solid_a;             /* [n_cells] fluid fraction (1 = not mixed), or NULL: no mixed cell */
+  const double * solid_cm;            /* [n_cells][3] centre of mass (NaN = not mixed), or NULL */
+  const double * solid_s;             /* [n_cells][2*dim] face fractions (1 = not mixed), or NULL */
 } gfsb200_tree_view;
 
 int gfsb200_tree_get_view (const gfsb200_tree * t, gfsb200_tree_view * v);

@@ -73,6 +73,7 @@ def load(dim: int) -> C.CDLL:
         "ora_locate_array": (None, [vp, vp, vp, vp]),
         "ora_locate": (None, [vp, lng, vp, vp, vp, vp]),
         "ora_locate_one": (vp, [vp, dbl, dbl, dbl, i32]),
+        "ora_set_solid": (None, [u64, dbl, vp, vp]),
         "ora_cell_info": (None, [u64, vp, vp, vp, vp]),
         "ora_set_values": (None, [vp, i32, lng, vp, vp]), "ora_get_values": (None, [vp, i32, lng, vp, vp]),
         "ora_neighbor": (u64, [u64, i32]), "ora_count": (lng, [vp, i32]),
@@ -177,6 +178,14 @@ class Sim:
         out = np.zeros(len(x), dtype=np.uint64)
         self.L.ora_locate(self.h, len(x), _p(x), _p(y), _p(z), _p(out))
         return out
+
+    def set_solid(self, cell, a, cm, s=None):
+        """make `cell` (FttCell*) a mixed cell with fluid fraction a, centre of mass cm and face
+        fractions s (None: all 1); a <= 0: not mixed any more"""
+        v = np.zeros(3)
+        v[:len(cm)] = cm
+        sv = None if s is None else np.ascontiguousarray(list(s) + [1.0] * (6 - len(s)), dtype=np.float64)
+        self.L.ora_set_solid(int(cell), float(a), _p(v), _p(sv))
 
     def set_values(self, ivar, cells, vals):
         cells = np.ascontiguousarray(cells, dtype=np.uint64)

@@ -101,6 +101,7 @@ static void cell_init (FttCell * cell, OraSim * sim)
 static void cell_cleanup (FttCell * cell, gpointer data)
 {
   if (cell->data) {
+    g_free (GFS_STATE (cell)->solid);          /* ora_set_solid */
     g_free (cell->data);
     cell->data = NULL;
   }
@@ -471,6 +472,33 @@ void ora_locate (OraSim * sim, long n, const double * x, const double * y, const
     FttVector p = { x[i], y[i], z ? z[i] : 0., 0. };
     cell[i] = (uint64_t) (uintptr_t) domain_locate (sim, p, -1);
   }
+}
+
+/* Makes `cell` a mixed (solid-cut) cell: attaches a GfsSolidVector (src/fluid.h:54-59) with
+ * fluid fraction a, centre of mass cm and face fractions s[] (NULL: all 1), the members the
+ * particulate path reads (distance () src/fluid.c:2983-3003 through gfs_cell_cm;
+ * gfs_cell_volume; gfs_cell_face and average_neighbor_value in the gradients).  The reference
+ * computes them from a GTS surface (src/solid.c, GTS is absent here); the tests prescribe
+ * them.  a <= 0 removes the solid vector again. */
+void ora_set_solid (uint64_t cellp, double a, const double * cm, const double * s)
+{
+  FttCell * cell = (FttCell *) (uintptr_t) cellp;
+  FttDirection d;
+  g_assert (cell && cell->data);
+  if (a <= 0.) {
+    g_free (GFS_STATE (cell)->solid);
+    GFS_STATE (cell)->solid = NULL;
+    return;
+  }
+  if (!GFS_STATE (cell)->solid)
+    GFS_STATE (cell)->solid = g_malloc0 (sizeof (GfsSolidVector));
+  GFS_STATE (cell)->solid->a = a;
+  for (d = 0; d < FTT_NEIGHBORS; d++)
+    GFS_STATE (cell)->solid->s[d] = s ? s[d] : 1.;
+  GFS_STATE (cell)->solid->cm.x = cm[0];
+  GFS_STATE (cell)->solid->cm.y = cm[1];
+  GFS_STATE (cell)->solid->cm.z = FTT_DIMENSION > 2 ? cm[2] : 0.;
+  GFS_STATE (cell)->solid->ca = GFS_STATE (cell)->solid->cm;
 }
 
 /* single-point entry: the gfs_domain_locate that libgfsrefobj (the reference's

@@ -895,8 +895,15 @@ void gfs_clock_destroy (GfsClock * t)
   g_free (t);
 }
 
-/* fluid.c externals that only matter for mixed (solid) cells or statistics */
-void gfs_cell_cm (const FttCell * cell, FttVector * cm) { ftt_cell_pos (cell, cm); }
+/* fluid.c externals: mixed (solid) cells and statistics */
+/* src/solid.c:1264-1273 */
+void gfs_cell_cm (const FttCell * cell, FttVector * cm)
+{
+  if (GFS_IS_MIXED (cell))
+    *cm = GFS_STATE (cell)->solid->cm;
+  else
+    ftt_cell_pos (cell, cm);
+}
 void gts_range_init (GtsRange * r) { memset (r, 0, sizeof (GtsRange)); r->min = G_MAXDOUBLE; r->max = - G_MAXDOUBLE; }
 void gts_range_add_value (GtsRange * r, gdouble val)
 {

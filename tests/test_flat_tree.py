@@ -151,21 +151,62 @@ def test_error_paths():
         capi.Tree(4)
 
 
-def test_flatten_rejects_solid_cells():
-    """a mixed cell (GFS_STATE (cell)->solid != NULL) cannot be represented: the
-    bridge must refuse the tree instead of silently dropping the solid fractions"""
-    import ctypes
-    t, sim = build_pair(3, 2, 3, ())
+def make_mixed(sim, fmap, a, rng, frac=0.25):
+    """turns a random quarter of the box leaves (and a few ghost leaves) into mixed cells
+    with a prescribed fluid fraction and centre of mass; returns {flat index: (a, cm)}"""
+    leaves = a.box_leaves
+    pick = list(rng.choice(leaves, max(1, int(frac * len(leaves))), replace=False))
+    ghost = np.nonzero((a.child0 < 0) & ((a.flags & capi.CELL_BOUNDARY) != 0) &
+                       ((a.flags & capi.CELL_DESTROYED) == 0))[0]
+    pick += list(ghost[::7])
+    mixed = {}
+    for i in pick:
+        h = 2.0 ** -int(a.level[i])
+        frac_a = float(rng.uniform(0.05, 1.0))
+        cm = a.pos[i, :a.dim] + rng.uniform(-0.45, 0.45, a.dim) * h
+        fs = rng.choice([0.0, 0.3, 1.0], 2 * a.dim, p=[0.2, 0.4, 0.4])       # some faces closed
+        sim.set_solid(fmap.cells[i], frac_a, cm, fs)
+        mixed[int(i)] = (frac_a, cm, fs)
+    return mixed
+
+
+@pytest.mark.parametrize("dim,minl,maxl,sides", [(2, 2, 6, (0, 1, 2, 3)), (3, 2, 5, (0, 1, 2, 3, 4, 5)), (3, 4, 4, ())])
+def test_mixed_cells_through_the_bridge_and_in_the_stencils(dim, minl, maxl, sides):
+    """GFS_IS_MIXED cells: the bridge carries GfsSolidVector.a / .cm into the flat tree and
+    the corner interpolators weight such a cell by the distance from the corner to its
+    centre of mass (distance (), src/fluid.c:2983-3003) -- same cells, same order, same
+    weights to the last bit as gfs_cell_corner_interpolator on the reference tree,
+    T-junctions, ghost cells and the uniform (otherwise lattice) tree included"""
+    t, sim = build_pair(dim, minl, maxl, sides)
     roots, is_box = sim.roots()
-    t2, fmap = capi.flatten_ftt(3, roots, is_box)
-    leaf = int(fmap.cells[t2.view().box_leaves[5]])
-    data = ctypes.c_void_p.from_address(leaf + 8).value            # FttCell.data
-    solid_slot = ctypes.c_void_p.from_address(data + 6 * 16)        # GfsStateVector.solid
-    solid_slot.value = 0xdead0
-    with pytest.raises(capi.GfsB200Error, match="solid"):
-        capi.flatten_ftt(3, roots, is_box)
-    solid_slot.value = None
-    capi.flatten_ftt(3, roots, is_box)
+    t0, fmap0 = capi.flatten_ftt(dim, roots, is_box)
+    rng = np.random.default_rng(8)
+    mixed = make_mixed(sim, fmap0, t0.view(), rng)
+    t2, fmap = capi.flatten_ftt(dim, roots, is_box)
+    a = t2.view()
+    assert a.solid_a is not None and np.array_equal(fmap.cells, fmap0.cells)
+    for i, (fa, cm, fs) in mixed.items():
+        assert a.solid_a[i] == fa and np.array_equal(a.solid_cm[i, :dim], cm)
+        assert np.array_equal(a.solid_s[i], fs)
+    rest = np.setdiff1d(np.arange(a.n_cells), list(mixed))
+    assert np.all(a.solid_a[rest] == 1.0) and np.all(np.isnan(a.solid_cm[rest, 0])) and np.all(a.solid_s[rest] == 1.0)
+    t2.build_stencils()
+    a = t2.view()
+    assert a.lattice_level == -1 or minl == maxl          # weights differ: no single-weight shortcut needed
+    idx = helpers.PtrIndex(fmap.cells)
+    changed = 0
+    for i in a.box_leaves:
+        for k in range(2 ** dim):
+            cells, w = t2.corner_interpolator(int(i), k)
+            oc, ow = sim.corner_interpolator(fmap.cells[i], k)
+            assert list(idx(np.array(oc, dtype=np.uint64))) == cells and ow == w, (i, k)
+            changed += any(c in mixed for c in cells)
+            v = a.leaf_vtx[i, k]
+            sl = slice(a.vtx_off[v], a.vtx_off[v + 1])
+            assert sorted(zip(a.vtx_cell[sl], a.vtx_w[sl])) == sorted(zip(cells, w))
+    assert changed > 100
+    for i in mixed:                                        # leave the shared oracle tree clean
+        sim.set_solid(fmap.cells[i], 0.0, np.zeros(3))
 
 
 @pytest.mark.parametrize("dim,level,sides", [(3, 4, ()), (3, 3, (0, 1, 2, 3, 4, 5)), (2, 5, (0, 1, 2, 3)), (3, 4, (2, 5))])
