@@ -26,9 +26,9 @@
  *
  * and exports the same module symbols as modules/particulates.c:24-49.
  * A list that carries something the device does not implement (user force
- * classes, non-constant coefficient / density / viscosity functions), or a
- * domain with solid boundaries, is handed back to the reference's own event
- * untouched.
+ * classes, coefficient / density functions that are neither a constant nor a
+ * plain cell variable), or a simulation with moving solids, is handed back to
+ * the reference's own event untouched.
  */
 #include <stdlib.h>
 #include <string.h>
@@ -377,6 +377,23 @@ static GfsSourceDiffusion * viscosity_source (GfsVariable * v)
 
 /* fills *p; returns FALSE if the list needs something only the reference
  * CPU path implements */
+/* Embedded solids: the mixed cells travel with the tree (gfsb200_ftt_flatten carries each
+ * GfsSolidVector: centre of mass into the interpolation weights, face fractions into the
+ * gradients, fluid fraction into the deposits), which is re-flattened after an adapt only.
+ * Solids that MOVE (GfsSolidMoving, modules/moving.c) change those fractions every step
+ * without touching the mesh: such a simulation stays on the reference's own events. */
+static gboolean moving_solids (GfsSimulation * sim)
+{
+  GSList * i = sim->solids ? sim->solids->items : NULL;
+  for (; i; i = i->next) {
+    GtsObjectClass * k = GTS_OBJECT (i->data)->klass;
+    for (; k; k = k->parent_class)
+      if (!strcmp (k->info.name, "GfsSolidMoving"))
+	return TRUE;
+  }
+  return FALSE;
+}
+
 typedef struct {
   GfsVariable ** uold;                  /* -> B200State.uold */
   gboolean snapshot;
@@ -687,7 +704,7 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
   gdouble t[7];
   gint k;
 
-  if (sim->solids->items != NULL || !step_params (plist, sim, &par, &lv)) {
+  if (moving_solids (sim) || !step_params (plist, sim, &par, &lv)) {
     gfsb200_module_sync (plist);
     return (* reference_list_event) (event, sim);            /* not expressible on the device */
   }
@@ -779,7 +796,7 @@ static gboolean b200_particulate_field_event (GfsEvent * event, GfsSimulation * 
   B200State * s;
   gdouble * out;
 
-  if (sim->solids->items != NULL || !step_params (pfield->plist, sim, &par, &lv))
+  if (moving_solids (sim) || !step_params (pfield->plist, sim, &par, &lv))
     return (* reference_field_event) (event, sim);
   if (!(* GFS_EVENT_CLASS (gfs_variable_class ())->event) (event, sim))
     return FALSE;
@@ -822,7 +839,7 @@ static gboolean b200_source_particulate_event (GfsEvent * event, GfsSimulation *
   GSList * i;
   FttComponent c;
 
-  if (sim->solids->items != NULL || !step_params (sp->plist, sim, &par, &lv) ||
+  if (moving_solids (sim) || !step_params (sp->plist, sim, &par, &lv) ||
       gfsb200_kernel_fit (kernel_trampoline, sp->kernel_function, FTT_DIMENSION, &kernel) != GFSB200_OK)
     return (* reference_source_event) (event, sim);
   /* the timing gate of the parent class (:2180-2181) */

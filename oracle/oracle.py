@@ -330,7 +330,7 @@ def load_refobj(dim: int, module: bool = False) -> C.CDLL:
         "refobj_locate": (None, [vp, lng, vp, vp, vp, vp]),
         "refobj_locate_array": (None, [vp, vp, vp, vp]),
         "refobj_sim_time": (None, [vp, C.POINTER(dbl), C.POINTER(i32)]),
-        "refobj_sim_add_solid": (None, [vp]),
+        "refobj_sim_add_solid": (None, [vp, i32]),
         "refobj_list_new": (vp, [vp, lng] + [vp] * 8 + [C.POINTER(StepParams)]),
         "refobj_list_destroy": (None, [vp]),
         "refobj_list_size": (lng, [vp]),
@@ -398,9 +398,9 @@ class RefSim:
         self.R.refobj_locate_array(self.h, _p(mn), C.byref(h), _p(n))
         return mn[:self.dim], h.value, n[:self.dim]
 
-    def add_solid(self):
-        """an entry in sim->solids, as a GfsSolid declaration leaves"""
-        self.R.refobj_sim_add_solid(self.h)
+    def add_solid(self, moving=False):
+        """an entry in sim->solids, as a GfsSolid (or GfsSolidMoving) declaration leaves"""
+        self.R.refobj_sim_add_solid(self.h, int(moving))
 
     def time(self):
         t, i = C.c_double(), C.c_int()

@@ -1113,12 +1113,17 @@ REF_EXPORT void refobj_sim_destroy (RefSim * s)
   gts_object_destroy (GTS_OBJECT (s));
 }
 
-/* declares a GfsSolid in the simulation (an entry in sim->solids is all the
-   module looks at before handing the events back to the reference) */
-REF_EXPORT void refobj_sim_add_solid (RefSim * s)
+/* declares a solid in the simulation: a GfsSolid (moving == 0), or a GfsSolidMoving
+   (modules/moving.c), which the drop-in module hands back to the reference's events.
+   Only the class name and the entry in sim->solids matter to the particulate path. */
+SIMPLE_CLASS (ref_solid_class, GtsSListContaineeClass, "GfsSolid", GtsSListContainee, gts_slist_containee_class ())
+SIMPLE_CLASS (ref_solid_moving_class, GtsSListContaineeClass, "GfsSolidMoving", GtsSListContainee, ref_solid_class ())
+
+REF_EXPORT void refobj_sim_add_solid (RefSim * s, int moving)
 {
   gts_container_add (GTS_CONTAINER (s->sim.solids),
-		     GTS_CONTAINEE (gts_object_new (GTS_OBJECT_CLASS (gts_slist_containee_class ()))));
+		     GTS_CONTAINEE (gts_object_new (GTS_OBJECT_CLASS (moving ? ref_solid_moving_class () :
+									ref_solid_class ()))));
 }
 
 /* gfs_domain_locate (src/domain.c:2623-2638 over the GfsLocateArray of :43-145), the

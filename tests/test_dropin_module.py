@@ -339,3 +339,49 @@ def test_module_c1_full_config(monkeypatch):
             worst = max(worst, helpers.vec_rel_err(g, wv, keys))
     assert worst <= 1e-9, worst        # the documented drift bound after 1000 steps (drag only: no
                                        # cell-constant force, so no particle is excluded)
+
+
+@pytest.mark.parametrize("kind", ["c1", "ring3"])
+def test_module_with_embedded_solids(kind):
+    """a simulation with a (static) GfsSolid: the bridge carries the mixed cells'
+    GfsSolidVector into the flat tree, and list event, void-fraction field and smoothed
+    source through the module match the reference's own events on the same mixed tree"""
+    w, sim, ptrs = setup(kind)
+    a = w.arrays
+    rng = np.random.default_rng(6)
+    leaves = a.box_leaves
+    mixed = rng.choice(leaves, len(leaves) // 4, replace=False)
+    for i in mixed:
+        h = 2.0 ** -int(a.level[i])
+        sim.set_solid(ptrs[i], float(rng.uniform(0.05, 1.0)), a.pos[i, :a.dim] + rng.uniform(-0.45, 0.45, a.dim) * h,
+                      rng.choice([0.0, 0.3, 1.0], 2 * a.dim, p=[0.2, 0.4, 0.4]))
+    try:
+        parts = helpers.test_particles(w, 3000)
+        par = helpers.oracle_params(w)
+        live = (a.flags & capi.CELL_DESTROYED) == 0
+        box_leaf = live & (a.child0 < 0) & ((a.flags & capi.CELL_BOUNDARY) == 0)
+        res = {}
+        for module in (False, True):
+            rs = ora.RefSim(sim, module=module)
+            rs.configure(par)
+            rs.add_solid()
+            rl = ora.RefParticleList(rs, *[parts[k] for k in KEYS], par)
+            states = []
+            for step in range(3):
+                assert rl.event() == 1
+                states.append(rl.get())
+            for iv in range(4, 4 + w.dim):
+                sim.set_values(iv, ptrs[live], np.full(int(live.sum()), 3.0))
+            rl.source_event(4, 0.05, ora.Kernel(ora.KERNEL_GAUSSIAN, 1.0, 2e-4, 1, 0))
+            src = [sim.get_values(4 + c, ptrs[box_leaf]) for c in range(w.dim)]
+            res[module] = (states, src)
+            rs.close()
+        for step in range(3):
+            check(res[True][0][step], res[False][0][step], w.dim, 1e-12 if step == 0 else 1e-11, (kind, step))
+        for c in range(w.dim):
+            want, got = res[False][1][c], res[True][1][c]
+            assert np.abs(want).max() > 0
+            assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max(), c
+    finally:
+        for i in mixed:
+            sim.set_solid(ptrs[i], 0.0, np.zeros(3))

@@ -791,3 +791,127 @@ def test_periodic_wrap_and_drop(dim, ctx):
     assert wrapped_total > 5, "the test did not exercise wrapping"
     inside = ctx.locate(got["x"], got["y"], got["z"] if dim == 3 else None) >= 0
     assert inside.mean() > 0.95
+
+
+# ---------------------------------------------------------------------------
+# mixed (solid-cut) cells
+
+class _SolidWorld:
+    """a test world whose reference tree has a quarter of its leaves turned into mixed cells
+    (prescribed GfsSolidVector a / cm / s, some faces closed), flattened through the FttCell
+    bridge as the module does; the shared oracle tree is restored on exit"""
+
+    def __init__(self, kind, ctx, seed=5):
+        self.w, self.sim, self.ptrs, self.idx = setup(kind, ctx)
+        self.ctx, a = ctx, self.w.arrays
+        rng = np.random.default_rng(seed)
+        leaves = a.box_leaves
+        pick = list(rng.choice(leaves, max(1, len(leaves) // 4), replace=False))
+        ghost = np.nonzero((a.child0 < 0) & ((a.flags & capi.CELL_BOUNDARY) != 0) &
+                           ((a.flags & capi.CELL_DESTROYED) == 0))[0]
+        self.mixed = pick + list(ghost[::5])
+
+        def solid(i):
+            h = 2.0 ** -int(a.level[i])
+            return (float(rng.uniform(0.05, 1.0)), a.pos[i, :a.dim] + rng.uniform(-0.45, 0.45, a.dim) * h,
+                    rng.choice([0.0, 0.3, 1.0], 2 * a.dim, p=[0.2, 0.4, 0.4]))
+        self.solid = {int(i): solid(i) for i in self.mixed}
+
+    def __enter__(self):
+        w, sim, ptrs = self.w, self.sim, self.ptrs
+        for i, (fa, cm, fs) in self.solid.items():
+            sim.set_solid(ptrs[i], fa, cm, fs)
+        roots, is_box = sim.roots()
+        self.tree, fmap = capi.flatten_ftt(w.dim, roots, is_box)
+        assert np.array_equal(fmap.cells, ptrs)
+        self.tree.build_stencils()
+        self.arrays = self.tree.view()
+        assert self.arrays.solid_a is not None
+        self.ctx.upload_tree(self.tree)
+        self.ctx.upload_field(w.u, w.v, w.w)
+        return self
+
+    def __exit__(self, *exc):
+        for i in self.solid:
+            self.sim.set_solid(self.ptrs[i], 0.0, np.zeros(3))
+        self.ctx.upload_tree(self.w.tree)
+        self.ctx.upload_field(self.w.u, self.w.v, self.w.w)
+        return False
+
+
+@pytest.mark.parametrize("kind", ["c1", "uniform3", "ring3", "ring2", "chain3"])
+def test_mixed_cells_interpolation_and_vorticity(kind, ctx):
+    """GFS_IS_MIXED cells on the device: corner values / gfs_interpolate with the
+    centre-of-mass weights, vorticity with closed faces (gfs_cell_face) and face-fraction
+    averages over finer neighbours (average_neighbor_value) -- vorticity bit-exact"""
+    with _SolidWorld(kind, ctx) as sw:
+        w, sim, ptrs = sw.w, sw.sim, sw.ptrs
+        leaves = sw.arrays.box_leaves
+        vort = ctx.vorticity(leaves)
+        want = sim.vorticity(ptrs[leaves])
+        assert np.array_equal(vort, want), f"max diff {np.abs(vort - want).max():.3e}"
+        fields = [w.u, w.v] + ([w.w] if w.dim == 3 else [])
+        for comp, f in enumerate(fields):
+            got = ctx.corner_values(comp, leaves)
+            want = sim.corner_values(comp, ptrs[leaves])
+            tol = 4 * np.finfo(np.float64).eps * max(np.abs(f).max(), 1e-300)
+            assert np.abs(got - want).max() <= tol
+        rng = np.random.default_rng(1)
+        parts = _particles(w, 20000)
+        x, y, z = parts["x"], parts["y"], parts["z"]
+        u = ctx.interpolate(x, y, z)
+        inside = sim.locate(x, y, z) != 0
+        for comp, f in enumerate(fields):
+            want = sim.interpolate(comp, x, y, z)
+            tol = 8 * np.finfo(np.float64).eps * max(np.abs(f).max(), 1e-300)
+            assert np.abs(u[comp][inside] - want[inside]).max() <= tol
+    # and it matters: without the solids the reference gives another vorticity field
+    assert not np.array_equal(sim.vorticity(ptrs[leaves]), vort)
+
+
+@pytest.mark.parametrize("kind", ["c1", "ring3", "uniform3"])
+def test_mixed_cells_step_and_deposits(kind, ctx):
+    """the fused step and both force deposits on a tree with mixed cells, against the
+    reference arithmetic (gfs_cell_volume = h^dim a in the deposits)"""
+    with _SolidWorld(kind, ctx) as sw:
+        w, sim, ptrs, idx = sw.w, sw.sim, sw.ptrs, sw.idx
+        parts = _particles(w, 8000)
+        got = _run_step(ctx, w, parts)
+        cells, want = helpers.oracle_step(sim, ptrs, w, parts)
+        assert np.array_equal(got["cell"], cells)
+        _check_state(got, want, w.dim)
+        # single-cell force deposit
+        ctx.particles_upload(**parts)
+        ctx.deposit_volume()
+        ctx.deposit_force(w.step_params())
+        live = (w.arrays.flags & capi.CELL_DESTROYED) == 0
+        plist = ora.ParticleList(sim, *[parts[k] for k in ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")])
+        zero = np.zeros(int(live.sum()))
+        for iv in range(3, 3 + 1 + w.dim):
+            sim.set_values(iv, ptrs[live], zero)
+        plist.deposit_volume(3)
+        plist.deposit_force(helpers.oracle_params(w), 4)
+        for comp in range(1 + w.dim):
+            g = ctx.download_deposit(comp)[live]
+            wv = sim.get_values(3 + comp, ptrs[live])
+            assert np.abs(wv).max() > 0
+            assert np.abs(g - wv).max() <= 1e-12 * np.abs(wv).max(), comp
+        # kernel-smoothed deposit
+        small = _particles(w, 1500)
+        ctx.particles_upload(**small)
+        rk = 0.06 if w.dim == 2 else 0.04
+        ctx.deposit_force_smoothed(w.step_params(), rk, capi.KERNEL_GAUSSIAN, 1.0, 2e-4, 1, 0, record_norm=True)
+        corr, vol = ctx.download_kernel_norm()
+        plist = ora.ParticleList(sim, *[small[k] for k in ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")])
+        for iv in range(4, 4 + w.dim):
+            sim.set_values(iv, ptrs[live], zero)
+        wcorr, wvol = plist.deposit_force_smoothed(helpers.oracle_params(w), 4, rk,
+                                                   ora.Kernel(ora.KERNEL_GAUSSIAN, 1.0, 2e-4, 1, 0))
+        assert np.array_equal(vol, wvol)                    # same leaves, same h^dim a, same order
+        ok = np.isfinite(wcorr)
+        assert np.abs(corr[ok] - wcorr[ok]).max() <= 1e-13 * np.abs(wcorr[ok]).max()
+        for comp in range(w.dim):
+            g = ctx.download_deposit(1 + comp)[live]
+            wv = sim.get_values(4 + comp, ptrs[live])
+            assert np.abs(wv).max() > 0
+            assert np.abs(g - wv).max() <= 1e-12 * np.abs(wv).max(), comp

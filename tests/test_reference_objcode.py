@@ -353,8 +353,8 @@ def test_dropin_module_loads_and_hands_back_what_the_device_cannot_do():
     """libgfsrefmod = the reference objects + the drop-in GModule source
     (host/particulates_b200.c) linked as a Gerris installation would.  Its
     g_module_check_init() instantiates the 16 classes and re-points the three
-    hot-path events.  A simulation that declares solid boundaries is not
-    expressible on the device: the module must hand the event back to the
+    hot-path events.  A simulation with MOVING solids (fractions change every step
+    without an adapt) is not expressible on the device: the module must hand the event back to the
     reference's own method, untouched -- checked here without a GPU against the
     unmodified library."""
     w, sim, ptrs = setup("ring3")
@@ -365,7 +365,7 @@ def test_dropin_module_loads_and_hands_back_what_the_device_cannot_do():
         rs = ora.RefSim(sim, module=module)
         assert rs.R.refobj_module_name() == (b"particulates" if module else None)
         rs.configure(par)
-        rs.add_solid()
+        rs.add_solid(moving=True)
         rl = ora.RefParticleList(rs, *[parts[k] for k in KEYS], par)
         states.append([])
         for step in range(2):
