@@ -122,7 +122,7 @@ struct gfsb200_ctx {
   double * knorm;              /* [2][knorm_n] correction, volume of the last smoothed deposit */
   int64_t knorm_cap, knorm_n;
   int step_minb;               /* __launch_bounds__ min blocks/SM variant of the step kernel */
-  int step_mode;               /* 0: plain kernel; 2/3: TMA-staged persistent kernel, that many stages */
+  int step_mode;               /* gfsb200_launch_step's mode; < 0: chosen by tree type */
   /* timing */
   std::vector<cudaEvent_t> ev;
   size_t ev_used;
@@ -225,7 +225,7 @@ extern "C" int gfsb200_ctx_create (int device, gfsb200_ctx ** out)
   c->hp_chunk = 0; c->hp_h2d = c->hp_d2h = NULL;
   c->ev_used = 0; c->timing = true;
   c->step_minb = getenv ("GFSB200_STEP_MINB") ? atoi (getenv ("GFSB200_STEP_MINB")) : 3;
-  c->step_mode = getenv ("GFSB200_STEP_MODE") ? atoi (getenv ("GFSB200_STEP_MODE")) : 3;
+  c->step_mode = getenv ("GFSB200_STEP_MODE") ? atoi (getenv ("GFSB200_STEP_MODE")) : -1;
   if (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags (&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags (&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||

@@ -374,13 +374,22 @@ __host__ __device__ constexpr int prog_len (unsigned prog)
   return prog == 0 ? 0 : 1 + prog_len (prog >> 4);
 }
 
-template <int DIM, bool ONFLUID, bool LATTICE = false, unsigned PROG = 0>
+/* LATE: where the particle's velocity, mass and volume come from.  NoLate: they are the
+ * arguments.  The warp-pipelined step kernel passes LateShared instead: the values stay in
+ * the TMA-staged tile until the velocity gathers have been consumed, so that they occupy no
+ * registers while those gathers are in flight. */
+struct NoLate {
+  __device__ __forceinline__ void fetch (double, double &, double &, double &, double &, double &) const {}
+};
+
+template <int DIM, bool ONFLUID, bool LATTICE = false, unsigned PROG = 0, typename LATE = NoLate>
 __device__ __forceinline__ void total_force (const DevTree & T, const DevField & fld,
 					     const DevStep & S, const Located & L,
 					     double x, double y, double z,
 					     double vx, double vy, double vz,
 					     double & mass, double volume,
-					     double & Fx, double & Fy, double & Fz, double & rho_out)
+					     double & Fx, double & Fy, double & Fz, double & rho_out,
+					     const LATE late = LATE ())
 {
   const unsigned forces = PROG ? PROG : S.forces;
   const int n_forces = PROG ? prog_len (PROG) : S.n_forces;
@@ -412,8 +421,10 @@ __device__ __forceinline__ void total_force (const DevTree & T, const DevField &
   rho_out = rho;
   double rx = 0., ry = 0., rz = 0.;
   double u = 0., v = 0., w = 0.;
-  if (need_velocity) {
+  if (need_velocity)
     interpolate<DIM, LATTICE> (T, fld, L, x, y, z, u, v, w);
+  late.fetch (u, vx, vy, vz, mass, volume);
+  if (need_velocity) {
     rx = u - vx; ry = v - vy; rz = DIM == 3 ? w - vz : 0.;
   }
 #pragma unroll
@@ -738,6 +749,136 @@ step_kernel_pipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_tile
 	if (S.keep) S.keep[i] = 0;
       }
     }
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/* Warp-private variant of the TMA pipeline.  Each WARP owns STAGES tiles of 32 particles
+ * (8 bulk copies of 256 B per tile) with its own mbarriers: no CTA-wide barrier per tile,
+ * and the stage is released only at the END of the tile, so velocity, mass and volume are
+ * read from the staged tile when the force needs them (after the vertex gathers) and the
+ * position is re-read for the integration -- 16 registers fewer live across the gathers. */
+
+namespace pipe {
+
+/* shared-memory load that cannot be scheduled before `dep` is known */
+__device__ __forceinline__ double lds_after (const double * p, double dep)
+{
+  double v;
+  asm volatile ("ld.shared.f64 %0, [%1];   // after %2" : "=d"(v) : "r"(smem_u32 (p)), "d"(dep));
+  return v;
+}
+
+} // namespace pipe
+
+template <int DIM>
+struct LateShared {
+  const double * b;            /* this lane's slot in column 0 of the staged tile; columns 32 apart */
+  __device__ __forceinline__ void fetch (double dep, double & vx, double & vy, double & vz,
+					 double & mass, double & volume) const
+  {
+    constexpr int V0 = DIM == 3 ? 3 : 2;
+    vx = pipe::lds_after (b + 32*V0, dep);
+    vy = pipe::lds_after (b + 32*(V0 + 1), dep);
+    if (DIM == 3) vz = pipe::lds_after (b + 32*(V0 + 2), dep);
+    mass = pipe::lds_after (b + 32*(2*DIM), dep);
+    volume = pipe::lds_after (b + 32*(2*DIM + 1), dep);
+  }
+};
+
+template <int DIM, bool LATTICE, unsigned PROG, int STAGES, int MINB, int WPIPE_WARPS>
+__global__ void __launch_bounds__(32*WPIPE_WARPS, MINB)
+step_kernel_wpipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_tiles)
+{
+  constexpr int NC = DIM == 3 ? 8 : 6;
+  constexpr unsigned COL_BYTES = 32*sizeof (double);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double (* buf)[STAGES][NC][32] = reinterpret_cast<double (*)[STAGES][NC][32]> (smem_raw);
+  __shared__ uint64_t full[WPIPE_WARPS][STAGES];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  const double * col[NC];
+  if (DIM == 3) {
+    col[0] = P.x; col[1] = P.y; col[2] = P.z; col[3] = P.vx; col[4] = P.vy; col[5] = P.vz;
+    col[6] = P.mass; col[7] = P.volume;
+  }
+  else {
+    col[0] = P.x; col[1] = P.y; col[2] = P.vx; col[3] = P.vy; col[4] = P.mass; col[5] = P.volume;
+  }
+
+  const int first = blockIdx.x*WPIPE_WARPS + warp, stride = gridDim.x*WPIPE_WARPS;
+  uint64_t policy = 0;
+
+  auto issue = [&] (int s, int tile) {
+    pipe::mbar_expect_tx (&full[warp][s], NC*COL_BYTES);
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+      pipe::bulk_g2s (&buf[warp][s][c][0], col[c] + (int64_t) tile*32, COL_BYTES, &full[warp][s], policy);
+  };
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++)
+      pipe::mbar_init (&full[warp][s], 1);
+    pipe::fence_async_shared ();
+    policy = pipe::policy_evict_first ();
+#pragma unroll
+    for (int s = 0; s < STAGES; s++)
+      if (first + s*stride < n_tiles)
+	issue (s, first + s*stride);
+  }
+  __syncwarp ();
+
+  int s = 0;
+  unsigned parity = 0;
+  for (int tile = first; tile < n_tiles; tile += stride) {
+    pipe::mbar_wait (&full[warp][s], parity);
+    const double * b = &buf[warp][s][0][lane];
+    const int64_t i = (int64_t) tile*32 + lane;
+    if (i < P.n) {
+      double x = b[0], y = b[32], z = DIM == 3 ? b[64] : 0.;
+      const Located L = locate<DIM, LATTICE> (T, x, y, z);
+      if (L.cell >= 0) {
+	double Fx, Fy, Fz, rho;
+	double vx = 0., vy = 0., vz = 0., mass = 0., volume = 0.;
+	total_force<DIM, false, LATTICE, PROG, LateShared<DIM> > (T, fld, S, L, x, y, z, vx, vy, vz, mass, volume,
+								 Fx, Fy, Fz, rho, LateShared<DIM> { b });
+	if (!PROG && S.mutates_mass)
+	  P.mass[i] = mass;
+	/* position and velocity come back from the staged tile (total_force took them by value) */
+	x = pipe::lds_after (b, Fx); y = pipe::lds_after (b + 32, Fx);
+	vx = pipe::lds_after (b + 32*DIM, Fx); vy = pipe::lds_after (b + 32*(DIM + 1), Fx);
+	if (DIM == 3) {
+	  z = pipe::lds_after (b + 64, Fx); vz = pipe::lds_after (b + 32*(DIM + 2), Fx);
+	}
+	const double hdt = 0.5*S.dt, dtm = S.dt*__drcp_rn (mass);
+	x = fma (vx, hdt, x); vx = fma (Fx, dtm, vx); x = fma (vx, hdt, x);
+	y = fma (vy, hdt, y); vy = fma (Fy, dtm, vy); y = fma (vy, hdt, y);
+	if (DIM == 3) {
+	  z = fma (vz, hdt, z); vz = fma (Fz, dtm, vz); z = fma (vz, hdt, z);
+	}
+	if (S.track_escapes && !in_domain<DIM> (T, x, y, z))
+	  record_escape<DIM> (S, P, i);
+	__stcs (P.x + i, x); __stcs (P.y + i, y); __stcs (P.vx + i, vx); __stcs (P.vy + i, vy);
+	if (DIM == 3) {
+	  __stcs (P.z + i, z); __stcs (P.vz + i, vz);
+	}
+      }
+      else if (S.track_escapes) {
+	atomicAdd (S.esc_count + 3, 1);       /* outside the domain before the step */
+	if (S.keep) S.keep[i] = 0;
+      }
+    }
+    /* every lane has read what it needs: hand the stage back to the copy engine */
+    __syncwarp ();
+    if (lane == 0) {
+      const int next = tile + STAGES*stride;
+      if (next < n_tiles) {
+	pipe::fence_async_shared ();       /* generic-proxy reads before async-proxy writes */
+	issue (s, next);
+      }
+    }
+    if (++s == STAGES) { s = 0; parity ^= 1; }
   }
 }
 
@@ -1262,11 +1403,29 @@ static void launch_pipe (const DevTree * T, const DevField * F, const DevParticl
   step_kernel_pipe<DIM, LA, PR, ST, MB, TILE><<<grid, TILE, smem, st>>> (*T, *F, *P, *S, n_tiles);
 }
 
+template <int DIM, bool LA, unsigned PR, int ST, int MB, int WPIPE_WARPS>
+static void launch_wpipe (const DevTree * T, const DevField * F, const DevParticles * P,
+			  const DevStep * S, int n_sm, cudaStream_t st)
+{
+  const int n_tiles = (int) ((P->n + 31)/32);
+  const size_t smem = (size_t) WPIPE_WARPS*ST*(DIM == 3 ? 8 : 6)*32*sizeof (double);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute (step_kernel_wpipe<DIM, LA, PR, ST, MB, WPIPE_WARPS>,
+			  cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    configured = true;
+  }
+  int grid = n_sm*MB;
+  if (grid*WPIPE_WARPS > n_tiles) grid = (n_tiles + WPIPE_WARPS - 1)/WPIPE_WARPS;
+  step_kernel_wpipe<DIM, LA, PR, ST, MB, WPIPE_WARPS><<<grid, 32*WPIPE_WARPS, smem, st>>> (*T, *F, *P, *S, n_tiles);
+}
+
 extern "C" {
 
 /* mode: 0 plain kernel; 2: TMA-staged persistent kernel, 3 CTAs x 256 threads per SM;
- * 3 (default): the same with 6 CTAs x 128 threads -- shorter waits at the per-tile barrier
- * (64-thread tiles and a third stage measured within 1.5 % of it) */
+ * 3: the same with 6 CTAs x 128 threads -- shorter waits at the per-tile barrier
+ * (64-thread tiles and a third stage measured within 1.5 % of it); 7, 9: the warp-pipelined
+ * kernel (step_kernel_wpipe); < 0 (default): chosen by tree type */
 void gfsb200_launch_step (const DevTree * T, const DevField * F, const DevParticles * P,
 			  const DevStep * S, int rec, int minb, int mode, int n_sm, cudaStream_t st)
 {
@@ -1282,6 +1441,25 @@ void gfsb200_launch_step (const DevTree * T, const DevField * F, const DevPartic
     prog = S->forces;
   }
   if (rec || (S->cd_const == S->cd_const)) prog = 0;
+  /* default (mode < 0): the warp-pipelined kernel on 3D lattice trees (C2: 0.274 vs 0.284 ms),
+     the CTA-pipelined one elsewhere (C3: 0.279 vs 0.295 ms) -- profiles/README.md, round 1e */
+  if (mode < 0)
+    mode = lat && T->dim == 3 && prog != 0 ? 9 : 3;       /* runtime force lists spill at 72 registers */
+  if (!rec && mode >= 4 && P->n >= 1024) {
+    /* warp-private pipeline, 2 stages, 4 warps per CTA; 9: 7 CTAs/SM (72 registers, 28 warps);
+       7: 6 CTAs/SM (80 registers) */
+#define WP_ST(D, LA, PR) do { if (mode == 7) launch_wpipe<D, LA, PR, 2, 6, 4> (T, F, P, S, n_sm, st); \
+			      else launch_wpipe<D, LA, PR, 2, 7, 4> (T, F, P, S, n_sm, st); } while (0)
+#define WP_PR(D, LA) do { switch (prog) { \
+    case 0x1: WP_ST (D, LA, 0x1); break; case 0x21: WP_ST (D, LA, 0x21); break; \
+    case 0x321: WP_ST (D, LA, 0x321); break; case 0x31: WP_ST (D, LA, 0x31); break; \
+    case 0x3: WP_ST (D, LA, 0x3); break; default: WP_ST (D, LA, 0); } } while (0)
+    if (T->dim == 3) { if (lat) WP_PR (3, true); else WP_PR (3, false); }
+    else             { if (lat) WP_PR (2, true); else WP_PR (2, false); }
+#undef WP_PR
+#undef WP_ST
+    return;
+  }
   if (!rec && mode >= 2 && P->n >= 1024) {
 #define PIPE_ST(D, LA, PR) do { if (mode == 3) launch_pipe<D, LA, PR, 2, 6, 128> (T, F, P, S, n_sm, st); \
 				else launch_pipe<D, LA, PR, 2, 3, 256> (T, F, P, S, n_sm, st); } while (0)

@@ -563,17 +563,19 @@ def test_full_size_c2_properties(ctx):
     _check_state(sub_got, want, 3)
 
 
-@pytest.mark.parametrize("mode", ["0", "2", "3"])
+@pytest.mark.parametrize("mode", ["0", "2", "3", "7", "9"])
 @pytest.mark.parametrize("kind", ["c1", "uniform3", "ring3", "ring2", "chain2"])
 def test_step_fast_paths(kind, mode, monkeypatch):
     """The production launch (no cell/force recording): compile-time force
-    lists, lattice addressing on uniform trees, and the TMA-staged persistent
-    kernel (GFSB200_STEP_MODE 2/3 = stages) must all match the oracle."""
+    lists, lattice addressing on uniform trees, the TMA-staged persistent
+    kernel (GFSB200_STEP_MODE 2/3: CTA-wide stages) and the warp-pipelined one
+    (7/9: per-warp stages, particle fetched late from the staged tile) must all
+    match the oracle, whatever the default picks for the tree."""
     monkeypatch.setenv("GFSB200_STEP_MODE", mode)
     c = capi.Context(0)
     try:
         w, sim, ptrs, idx = setup(kind, c)
-        n = 20011                                   # not a multiple of the 256-particle tile
+        n = 20011                                   # not a multiple of the 256- or 32-particle tiles
         parts = _particles(w, n)
         c.particles_upload(**parts)
         for forces in (w.forces, (capi.FORCE_DRAG, capi.FORCE_BUOY), (capi.FORCE_LIFT,)):
