@@ -774,13 +774,14 @@ __device__ __forceinline__ double lds_after (const double * p, double dep)
 template <int DIM>
 struct LateShared {
   const double * b;            /* this lane's slot in column 0 of the staged tile; columns 32 apart */
+  double * keep;               /* the caller's vx, vy, vz (total_force takes them by value) */
   __device__ __forceinline__ void fetch (double dep, double & vx, double & vy, double & vz,
 					 double & mass, double & volume) const
   {
     constexpr int V0 = DIM == 3 ? 3 : 2;
-    vx = pipe::lds_after (b + 32*V0, dep);
-    vy = pipe::lds_after (b + 32*(V0 + 1), dep);
-    if (DIM == 3) vz = pipe::lds_after (b + 32*(V0 + 2), dep);
+    keep[0] = vx = pipe::lds_after (b + 32*V0, dep);
+    keep[1] = vy = pipe::lds_after (b + 32*(V0 + 1), dep);
+    if (DIM == 3) keep[2] = vz = pipe::lds_after (b + 32*(V0 + 2), dep);
     mass = pipe::lds_after (b + 32*(2*DIM), dep);
     volume = pipe::lds_after (b + 32*(2*DIM + 1), dep);
   }
@@ -841,16 +842,16 @@ step_kernel_wpipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_til
       if (L.cell >= 0) {
 	double Fx, Fy, Fz, rho;
 	double vx = 0., vy = 0., vz = 0., mass = 0., volume = 0.;
+	double vkeep[3];
 	total_force<DIM, false, LATTICE, PROG, LateShared<DIM> > (T, fld, S, L, x, y, z, vx, vy, vz, mass, volume,
-								 Fx, Fy, Fz, rho, LateShared<DIM> { b });
+									 Fx, Fy, Fz, rho, LateShared<DIM> { b, vkeep });
 	if (!PROG && S.mutates_mass)
 	  P.mass[i] = mass;
-	/* position and velocity come back from the staged tile (total_force took them by value) */
+	/* the position comes back from the staged tile, the velocity from the late fetch */
 	x = pipe::lds_after (b, Fx); y = pipe::lds_after (b + 32, Fx);
-	vx = pipe::lds_after (b + 32*DIM, Fx); vy = pipe::lds_after (b + 32*(DIM + 1), Fx);
-	if (DIM == 3) {
-	  z = pipe::lds_after (b + 64, Fx); vz = pipe::lds_after (b + 32*(DIM + 2), Fx);
-	}
+	if (DIM == 3) z = pipe::lds_after (b + 64, Fx);
+	vx = vkeep[0]; vy = vkeep[1];
+	if (DIM == 3) vz = vkeep[2];
 	const double hdt = 0.5*S.dt, dtm = S.dt*__drcp_rn (mass);
 	x = fma (vx, hdt, x); vx = fma (Fx, dtm, vx); x = fma (vx, hdt, x);
 	y = fma (vy, hdt, y); vy = fma (Fy, dtm, vy); y = fma (vy, hdt, y);
