@@ -599,8 +599,16 @@ lattice_cell_pass_kernel (DevTree T, DevField fld)
     for (int half = 0; half < 2; half++) {
       const int tz = tzq + 4*half;
       const int r0 = (tz + 1)*PLANE + (ty + 1)*REG + (tx + 1);      /* the leaf (bx*8 + tx, ...) */
-      /* ---- vertex (i,j,k) = the low corner of that leaf's +x+y+z neighbour: its 8 leaves are
-	 region cells r0 + {0,1} + {0,REG} + {0,PLANE} */
+      /* The 2 x 2 x 2 region cells r0 + {0,1} + {0,REG} + {0,PLANE} are read ONCE into registers:
+	 they are the 8 leaves of vertex (i,j,k) = the low corner of the leaf's +x+y+z neighbour, and
+	 also the leaf's own value and its three "+" neighbours for the gradients (the shared-memory
+	 data pipe is the busiest unit of this kernel: 103 -> 60 loads per warp). */
+      double c[3][8];
+#pragma unroll
+      for (int f = 0; f < 3; f++)
+#pragma unroll
+	for (int q = 0; q < 8; q++)
+	  c[f][q] = reg[f][r0 + (q & 1) + ((q >> 1) & 1)*REG + ((q >> 2) & 1)*PLANE];
       {
 	const int i = bx*BRICK + 1 + tx, j = by*BRICK + 1 + ty, k = bz*BRICK + 1 + tz;
 	if (i < nn && j < nn && k < nn) {
@@ -608,19 +616,22 @@ lattice_cell_pass_kernel (DevTree T, DevField fld)
 #pragma unroll
 	  for (int q = 0; q < 8; q++) {
 	    const int bits = (pattern >> (3*q)) & 7;
-	    const int r = r0 + (bits & 1) + ((bits >> 1) & 1)*REG + ((bits >> 2) & 1)*PLANE;
-	    s0 += wgt*reg[0][r]; s1 += wgt*reg[1][r]; s2 += wgt*reg[2][r];
+	    if (PATTERN >= 0) {                 /* compile-time order: straight from the registers */
+	      s0 += wgt*c[0][bits]; s1 += wgt*c[1][bits]; s2 += wgt*c[2][bits];
+	    }
+	    else {
+	      const int r = r0 + (bits & 1) + ((bits >> 1) & 1)*REG + ((bits >> 2) & 1)*PLANE;
+	      s0 += wgt*reg[0][r]; s1 += wgt*reg[1][r]; s2 += wgt*reg[2][r];
+	    }
 	  }
 	  /* GFS_NODATA is DBL_MAX: a stencil that touches one sums to >= w*DBL_MAX (or
 	     overflows); no velocity gets near that, so one magnitude test screens for the
 	     exact check */
 	  if (!(fabs (s0) < 1e300 && fabs (s1) < 1e300 && fabs (s2) < 1e300)) {
 	    bool bad = false;
-	    for (int q = 0; q < 8; q++) {
-	      const int bits = (pattern >> (3*q)) & 7;
-	      const int r = r0 + (bits & 1) + ((bits >> 1) & 1)*REG + ((bits >> 2) & 1)*PLANE;
-	      bad |= is_nodata (reg[0][r]) | is_nodata (reg[1][r]) | is_nodata (reg[2][r]);
-	    }
+#pragma unroll
+	    for (int q = 0; q < 8; q++)
+	      bad |= is_nodata (c[0][q]) | is_nodata (c[1][q]) | is_nodata (c[2][q]);
 	    if (bad) {
 	      s0 = s1 = s2 = GFSB200_NODATA;
 	      *fld.nodata_flag = 1;
@@ -633,28 +644,26 @@ lattice_cell_pass_kernel (DevTree T, DevField fld)
       }
       /* ---- the leaf itself.  gfs_center_gradient (src/fluid.c:434-475) with same-level leaf
 	 neighbours: centred where both exist (the x1 = x2 = 1 case), one-sided (v0 - v1)/1 or
-	 (v2 - v0)/1 at the hull where a neighbour is NULL, 0 where both are. */
+	 (v2 - v0)/1 at the hull where a neighbour is NULL, 0 where both are.  The "-" neighbours
+	 are read unconditionally (outside the lattice the region holds zeros) and the case is
+	 selected afterwards: the same operations on the same operands as the branches. */
       {
 	const int kx = bx*BRICK + tx, ky = by*BRICK + ty, kz = bz*BRICK + tz;
-	{
-	  const double size = T.top_h;
-	  auto grad = [&] (const double * F, int st, int kc) -> double {
-	    const double v0 = F[r0];
-	    if (kc > 0) {
-	      if (kc < nn - 1)
-		return ((F[r0 + st] - v0) + (v0 - F[r0 - st]))/2.;
-	      return (v0 - F[r0 - st])/1.;
-	    }
-	    return kc < nn - 1 ? (F[r0 + st] - v0)/1. : 0.;
-	  };
-	  /* neighbour in direction 2c is +axis c, 2c + 1 is -axis c (FttDirection) */
-	  const double wx = (grad (reg[2], REG, ky) - grad (reg[1], PLANE, kz))/size;
-	  const double wy = (grad (reg[0], PLANE, kz) - grad (reg[2], 1, kx))/size;
-	  const double wz = (grad (reg[1], 1, kx) - grad (reg[0], REG, ky))/size;
-	  double2 * o = reinterpret_cast<double2 *> (fld.vort + ((int64_t) (kz*nn + ky)*nn + kx)*4);
-	  o[0] = make_double2 (wx, wy);
-	  o[1] = make_double2 (wz, 0.);
-	}
+	/* size is a power of two: its inverse is an exponent flip and x/size == x*inv_size exactly */
+	const double inv_size = __longlong_as_double ((2046LL << 52) - __double_as_longlong (T.top_h));
+	auto grad = [&] (int f, int plus, int st, int kc) -> double {
+	  const double v0 = c[f][0];
+	  const double up = c[f][plus] - v0, dn = v0 - reg[f][r0 - st];
+	  const bool has_up = kc < nn - 1, has_dn = kc > 0;
+	  return has_up ? (has_dn ? (up + dn)/2. : up) : (has_dn ? dn : 0.);
+	};
+	/* neighbour in direction 2c is +axis c, 2c + 1 is -axis c (FttDirection); c[f][1|2|4] = +x|+y|+z */
+	const double wx = (grad (2, 2, REG, ky) - grad (1, 4, PLANE, kz))*inv_size;
+	const double wy = (grad (0, 4, PLANE, kz) - grad (2, 1, 1, kx))*inv_size;
+	const double wz = (grad (1, 1, 1, kx) - grad (0, 2, REG, ky))*inv_size;
+	double2 * o = reinterpret_cast<double2 *> (fld.vort + ((int64_t) (kz*nn + ky)*nn + kx)*4);
+	o[0] = make_double2 (wx, wy);
+	o[1] = make_double2 (wz, 0.);
       }
     }
     /* ---- vertices on the hull (a coordinate equal to 0 or nn): their stencils are the few
