@@ -476,7 +476,7 @@ def run_b200(args):
                        "timed_segments": n_segments,
                        "cell_pass_every_step": True, "particles_inside_at_end": inside_frac,
                        "l2": "per-step particle stream (%.0f MB) exceeds the 126 MB L2" % (n_local * bps / 1e6)},
-            "roofline": {"bound": "hbm", "kernel": "%s<%d,...> (TMA-staged fused locate+interpolate+force+integrate)" % ("step_kernel_wpipe" if world.dim == 3 and world.arrays.lattice_level >= 0 and not os.environ.get("GFSB200_STEP_MODE") else "step_kernel_pipe", world.dim),
+            "roofline": {"bound": "hbm", "kernel": "%s<%d,...> (TMA-staged fused locate+interpolate+force+integrate)" % ("step_kernel_wpipe" if not os.environ.get("GFSB200_STEP_MODE") else "step_kernel (GFSB200_STEP_MODE=%s)" % os.environ["GFSB200_STEP_MODE"], world.dim),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "frac_of_8TBs_spec": achieved / 8000.0,
                          "traffic": measured_traffic(args.config, n_local, world.dim), "peak_source": peak_src,

@@ -761,6 +761,16 @@ step_kernel_pipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_tile
 
 namespace pipe {
 
+/* elect.sync: true in exactly one lane of the (converged) warp.  ptxas knows that, so a bulk
+ * copy issued under it is a single UBLKCP; under `lane == 0` it wraps every copy in a loop over
+ * the active lanes (ELECT / R2UR / BRA.U.ANY: 90 of 593 instructions per tile). */
+__device__ __forceinline__ bool elect_one ()
+{
+  unsigned pred;
+  asm volatile ("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 /* shared-memory load that cannot be scheduled before `dep` is known */
 __device__ __forceinline__ double lds_after (const double * p, double dep)
 {
@@ -796,7 +806,12 @@ step_kernel_wpipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_til
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double (* buf)[STAGES][NC][32] = reinterpret_cast<double (*)[STAGES][NC][32]> (smem_raw);
   __shared__ uint64_t full[WPIPE_WARPS][STAGES];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  /* broadcast through a shuffle so that the compiler knows the warp index -- and with it the
+     tile number, the stage addresses and the operands of the bulk copies -- to be warp-uniform:
+     without it every UBLKCP sits in a lane-serialising loop (6 R2UR + ELECT + branch per copy,
+     90 of 593 instructions per tile) */
+  const int warp = __shfl_sync (0xffffffffu, (int) (threadIdx.x >> 5), 0);
 
   const double * col[NC];
   if (DIM == 3) {
@@ -808,7 +823,7 @@ step_kernel_wpipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_til
   }
 
   const int first = blockIdx.x*WPIPE_WARPS + warp, stride = gridDim.x*WPIPE_WARPS;
-  uint64_t policy = 0;
+  const uint64_t policy = pipe::policy_evict_first ();
 
   auto issue = [&] (int s, int tile) {
     pipe::mbar_expect_tx (&full[warp][s], NC*COL_BYTES);
@@ -817,12 +832,11 @@ step_kernel_wpipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_til
       pipe::bulk_g2s (&buf[warp][s][c][0], col[c] + (int64_t) tile*32, COL_BYTES, &full[warp][s], policy);
   };
 
-  if (lane == 0) {
+  if (pipe::elect_one ()) {
 #pragma unroll
     for (int s = 0; s < STAGES; s++)
       pipe::mbar_init (&full[warp][s], 1);
     pipe::fence_async_shared ();
-    policy = pipe::policy_evict_first ();
 #pragma unroll
     for (int s = 0; s < STAGES; s++)
       if (first + s*stride < n_tiles)
@@ -872,12 +886,10 @@ step_kernel_wpipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_til
     }
     /* every lane has read what it needs: hand the stage back to the copy engine */
     __syncwarp ();
-    if (lane == 0) {
-      const int next = tile + STAGES*stride;
-      if (next < n_tiles) {
-	pipe::fence_async_shared ();       /* generic-proxy reads before async-proxy writes */
-	issue (s, next);
-      }
+    const int next = tile + STAGES*stride;
+    if (next < n_tiles && pipe::elect_one ()) {
+      pipe::fence_async_shared ();         /* generic-proxy reads before async-proxy writes */
+      issue (s, next);
     }
     if (++s == STAGES) { s = 0; parity ^= 1; }
   }
@@ -1442,10 +1454,11 @@ void gfsb200_launch_step (const DevTree * T, const DevField * F, const DevPartic
     prog = S->forces;
   }
   if (rec || (S->cd_const == S->cd_const)) prog = 0;
-  /* default (mode < 0): the warp-pipelined kernel on 3D lattice trees (C2: 0.274 vs 0.284 ms),
-     the CTA-pipelined one elsewhere (C3: 0.279 vs 0.295 ms) -- profiles/README.md, round 1e */
+  /* default (mode < 0): the warp-pipelined kernel for the compile-time force lists (C2: 0.249 vs
+     0.285 ms, C3: 0.266 vs 0.280 ms -- profiles/README.md, round 1e); runtime force lists spill
+     at its 72 registers and keep the CTA-pipelined one */
   if (mode < 0)
-    mode = lat && T->dim == 3 && prog != 0 ? 9 : 3;       /* runtime force lists spill at 72 registers */
+    mode = prog != 0 ? 9 : 3;
   if (!rec && mode >= 4 && P->n >= 1024) {
     /* warp-private pipeline, 2 stages, 4 warps per CTA; 9: 7 CTAs/SM (72 registers, 28 warps);
        7: 6 CTAs/SM (80 registers) */
