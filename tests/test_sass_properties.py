@@ -1,0 +1,68 @@
+"""Static properties of the shipped sm_100a code that the measured numbers depend on
+(profiles/README.md, rounds 1e/1f).  CPU-only: reads the SASS of the in-tree library with
+cuobjdump; nothing is executed."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "gerris-fft-particles_b200", "lib", "libgfsb200.so")
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None or not os.path.exists(LIB),
+                                reason="needs cuobjdump and the built library")
+
+
+@pytest.fixture(scope="module")
+def sass():
+    out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
+    funcs, name = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            funcs[name] = []
+        elif name and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
+            funcs[name].append(line)
+    return funcs
+
+
+def _one(funcs, pattern):
+    hits = [k for k in funcs if re.search(pattern, k)]
+    assert len(hits) == 1, (pattern, hits)
+    return "\n".join(funcs[hits[0]])
+
+
+def test_library_is_sm_100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", LIB], capture_output=True, text=True, check=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+# the C2 / C3 production instances: 3D, lattice or not, drag+lift+buoyancy, 2 stages, 7 CTAs x 4 warps
+@pytest.mark.parametrize("lattice", [1, 0])
+def test_warp_pipelined_step_kernel(sass, lattice):
+    code = _one(sass, r"step_kernel_wpipeILi3ELb%dELj801ELi2ELi7ELi4E" % lattice)
+    # the particle stream comes in through the TMA engine onto mbarriers
+    assert code.count("UBLKCP") == 3 * 8            # prologue (2 stages) + refill, 8 columns each
+    assert "SYNCS.PHASECHK.TRANS64.TRYWAIT" in code and "SYNCS.ARRIVE.TRANS64" in code
+    # ... one UBLKCP per copy: no lane-serialising loop around it (round 1f)
+    assert "BRA.U.ANY" not in code
+    assert code.count("R2UR") <= 4
+    assert code.count("ELECT") <= 3
+    # no CTA-wide barrier in the loop, nothing in local memory (72 registers, no spills)
+    assert "BAR.SYNC" not in code
+    assert not re.search(r"\b(LDL|STL)\b", code)
+    # velocity, mass, volume and the position are fetched from the staged tile with LDS.64
+    assert len(re.findall(r"\bLDS\.64\b", code)) >= 11
+
+
+def test_cell_pass_shared_loads(sass):
+    code = _one(sass, r"lattice_cell_pass_kernelILi2206526E")
+    # 2 x (24 region cells + 6 "-" neighbours) 64-bit shared loads per thread (round 1e)
+    assert len(re.findall(r"\bLDS\.64\b", code)) <= 64
+    assert "LDGSTS" in code
+    # one 4-byte value parked across the compute phase for the hull part: nothing in the loop
+    assert len(re.findall(r"\b(LDL|STL)\b", code)) <= 4
