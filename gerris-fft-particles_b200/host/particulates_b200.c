@@ -103,7 +103,10 @@ static B200State * state_of (GfsParticleList * plist)
     s = g_malloc0 (sizeof (B200State));
     if (env) device = atoi (env);
 #ifdef HAVE_MPI
-    else device = GFS_DOMAIN (gfs_object_simulation (plist))->pid;   /* one rank per GPU */
+    else {                      /* one rank per GPU; pid is -1 in a serial run of an MPI build */
+      device = GFS_DOMAIN (gfs_object_simulation (plist))->pid;
+      if (device < 0) device = 0;
+    }
 #endif
     if (gfsb200_ctx_create (device, &s->ctx) != GFSB200_OK)
       g_error ("particulates (B200): %s", gfsb200_last_error ());   /* no CPU fallback */
