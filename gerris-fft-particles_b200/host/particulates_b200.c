@@ -723,10 +723,10 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
   t[1] = wall ();
   mirror_velocity (s, GFS_DOMAIN (sim));
   t[2] = wall ();
-  /* Host objects are authoritative between steps in this first binding
-     (FeedParticle, DropletToParticle, outputs and BCs all mutate them); a
-     resident mode that skips the two copies when nothing on the host touched
-     the list is the next step ("host object sync"). */
+  /* By default the host objects are authoritative between events (FeedParticle,
+     DropletToParticle, outputs and BCs all mutate them): gather + upload here, download +
+     scatter below.  In resident mode (GFSB200_RESIDENT=1) device_current skips the upload
+     when nothing on the host has touched the list since the last event. */
   carried = s->resident && s->host_stale && s->list_known;   /* what device_current is about to decide */
   n_up = device_current (s, plist);
   carried = carried && !s->uploaded;
