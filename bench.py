@@ -287,6 +287,69 @@ def workload_name(cfg):
 # --------------------------------------------------------------------------
 # B200 arm
 
+def device_cloud(torch, world, n_local, rank, device):
+    """The ring-config cloud (half uniform, half Gaussian around the core; v0 = analytic fluid
+    velocity) drawn ON THE DEVICE with torch's generator -- plumbing for the 200 M-particle C5
+    line, where drawing and shipping the cloud from the host would dominate the run.  Returns the
+    8 SoA columns as CUDA tensors."""
+    g = torch.Generator(device=device)
+    g.manual_seed(world.seed * 1000 + rank)
+    f64 = dict(dtype=torch.float64, device=device, generator=g)
+    n_uni = n_local // 2
+    n_g = n_local - n_uni
+    pos = []
+    theta = torch.rand(n_g, **f64) * (2.0 * np.pi)
+    for a in range(3):
+        uni = torch.rand(n_uni, **f64) * 0.9 - 0.45
+        off = torch.randn(n_g, **f64) * 0.08
+        if a == 0:
+            off += 0.25 * torch.cos(theta)
+        elif a == 1:
+            off += 0.25 * torch.sin(theta)
+        pos.append(torch.cat([uni, off]).clamp_(-0.49, 0.49))
+        del uni, off
+    del theta
+    m = world.meta
+    d = torch.rand(n_local, **f64) * (m["d_p"][1] - m["d_p"][0]) + m["d_p"][0]
+    vol = d ** 3 * (np.pi / 6.0)
+    mass = vol * m["rho_p"]
+    del d
+    # worlds.vortex_ring, restated for tensors
+    x, y, z = pos
+    R, gamma, a0 = 0.25, 1.0, 0.05
+    rho = torch.sqrt(x * x + y * y)
+    dr = rho - R
+    s2 = dr * dr + z * z
+    s2c = torch.clamp(s2, min=1e-300)
+    k = gamma / (2.0 * np.pi) * (1.0 - torch.exp(-s2 / (a0 * a0))) / s2c
+    ur, w = -k * z, k * dr
+    rs = torch.clamp(rho, min=1e-300)
+    vel = [ur * x / rs, ur * y / rs, w]
+    return pos + vel + [mass, vol]
+
+
+def fill_from_device(torch, ctx, cols, device):
+    """copy CUDA tensors into the context's SoA columns (device to device)"""
+    n = int(cols[0].numel())
+    ctx.particles_resize(n)
+    for ptr, src in zip(ctx.particles_device_ptrs(), cols):
+        dst = torch.as_tensor(_Alias(ptr, n), device=device)
+        dst.copy_(src)
+    torch.cuda.synchronize()
+
+
+class _Alias:
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+
+def stats_ms(ms):
+    a = np.asarray(ms, dtype=np.float64)
+    if a.size == 0:
+        return None
+    return {"min": float(a.min()), "median": float(np.median(a)), "max": float(a.max()), "n": int(a.size)}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -297,50 +360,87 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
     if world_size > 1:
+        # torch.distributed is rendezvous plumbing only (the NCCL id, the max over ranks of the
+        # timings): every data-path collective is issued by the C library on its own communicator
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=device)
+
+    def allmax(v):
+        if world_size == 1:
+            return float(v)
+        t = torch.tensor([v], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(v):
+        if world_size == 1:
+            return float(v)
+        t = torch.tensor([v], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
 
     pkg = entry.load_package()
     capi, worlds = pkg.capi, pkg.worlds
-    world = build_world(worlds, args.config, args.particles, args.level)
-    n_local = world.n_particles                       # weak scaling: fixed per-GPU batch
+    peak, peak_src = measured_peak()
     ctx = capi.Context(local_rank)
-    ctx.upload_tree(world.tree)
-    ctx.upload_field(world.u, world.v, world.w)
-    parts = worlds.make_particles(world, n_local * world_size, rank, world_size)
-    n_local = len(parts["x"])
-    ctx.particles_upload(**parts)
-    ctx.sort()
-    ctx.synchronize()
+    uid = [capi.comm_unique_id() if (rank == 0 and world_size > 1) else None]
+    if world_size > 1:
+        dist.broadcast_object_list(uid, src=0)
+    comm = capi.Comm.init_rank(ctx, uid[0], rank, world_size)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=device)
 
-    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
-    par = world.step_params()
-    reducer = None
-    if args.two_way and world_size > 1:
-        # the C-ABI's two deposit buffers, aliased (no copy) as tensors; the NCCL all-reduce of
-        # step n runs on a communication stream while step n+1 computes
-        reducer = pkg.multigpu.OverlappedDepositReduce(ctx, local_rank)
+    def order_particles():
+        """one GPU: sort by cell.  Several: every rank takes a contiguous slice of the GLOBAL cell
+        order -- its tables shrink to 1/N of the tree and its deposits to its own slice"""
+        if world_size == 1 and ordered[0]:
+            ctx.sort()                   # the one slice stays the whole tree: a plain re-sort
+        else:
+            comm.rebalance()
+            ordered[0] = True
 
-    def one_step(i):
-        ctx.refresh_field()
-        ctx.step(par)
-        if args.two_way:
-            if reducer is not None:
-                reducer.begin_step()
-            ctx.deposit_all(par)
-            if reducer is not None:
-                reducer.end_step()
-        if args.resort and (i + 1) % args.resort == 0:
-            ctx.sort()
+    ordered = [False]
 
     def barrier():
-        if reducer is not None:
-            reducer.drain()
         if world_size > 1:
             dist.barrier()
         torch.cuda.synchronize()
         ctx.synchronize()
+
+    def timed_steps(one_step, steps, tail=None):
+        """`steps` calls of one_step(i) between CUDA events on the context's stream, plus an event
+        after every step; returns (total ms, [ms per step])"""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record(stream)
+        for i in range(steps):
+            one_step(i)
+            if i == steps - 1 and tail is not None:
+                tail()
+            ev[i + 1].record(stream)
+        barrier()
+        per = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+        return ev[0].elapsed_time(ev[steps]), per
+
+    # ======================================================================
+    # headline: one-way, weak scaling (every rank holds the config's full batch)
+    world = build_world(worlds, args.config, args.particles, args.level)
+    n_share = world.n_particles
+    ctx.upload_tree(world.tree)
+    ctx.upload_field(world.u, world.v, world.w)
+    parts = worlds.make_particles(world, n_share * world_size, rank, world_size)
+    ctx.particles_upload(**parts)
+    order_particles()
+    ctx.synchronize()
+    n_local = ctx.count
+    total_particles = int(allsum(n_local))
+    par = world.step_params()
+
+    def one_step(i):
+        ctx.refresh_field()
+        ctx.step(par)
+        if args.resort and (i + 1) % args.resort == 0:
+            order_particles()
 
     # the sampler thread starts before the warm-up (NVML's first calls are slow); only the
     # samples taken while the timed region runs are kept
@@ -350,14 +450,23 @@ def run_b200(args):
     # The synthetic cloud sediments (rho_p/rho = 1000, g = -1): past ~150 steps particles start
     # leaving through the bottom wall and the kernel would early-out for them.  Long runs are
     # therefore timed in SEGMENTS of at most 100 steps, each started from the initial cloud
-    # (re-uploaded and re-sorted OUTSIDE the timed events); every segment must end with
+    # (re-uploaded and re-ordered OUTSIDE the timed events); every segment must end with
     # >= 99.9 % of its particles inside or the run aborts.
     SEG = 100
 
     def restore():
         ctx.particles_upload(**parts)
-        ctx.sort()
+        order_particles()
         barrier()
+
+    def check_inside(what):
+        before = ctx.count
+        removed = ctx.cull()
+        frac = 1.0 - removed / max(before, 1)
+        if frac < 0.999:
+            raise SystemExit(f"bench.py: only {frac:.4f} of the particles are still inside the domain "
+                             f"after {what} -- the workload is invalid")
+        return frac
 
     for i in range(min(args.warmup, SEG)):
         one_step(i)
@@ -367,53 +476,110 @@ def run_b200(args):
     ctx.timer_reset()
     t_region0 = time.perf_counter()
     launches0 = capi.kernel_launches()               # counted inside the library, per launch
-    ms, done, n_segments, inside_frac, sort_launches = 0.0, 0, 0, 1.0, 0
+    ms, done, n_segments, inside_frac, untimed_launches, per_step = 0.0, 0, 0, 1.0, 0, []
     while done < args.steps:
         m = min(SEG, args.steps - done)
         if done:
             skip = capi.kernel_launches()
             restore()
-            sort_launches += capi.kernel_launches() - skip      # untimed: not part of the claim
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for i in range(m):
-            one_step(done + i)
-        if reducer is not None:
-            reducer.join()          # the timed region ends when the last all-reduce has landed
-        e1.record(stream)
-        barrier()
-        ms += e0.elapsed_time(e1)
+            untimed_launches += capi.kernel_launches() - skip      # untimed: not part of the claim
+        seg_ms, per = timed_steps(lambda i: one_step(done + i), m)
+        ms += seg_ms
+        per_step += per
         done += m
         n_segments += 1
-        # validity: the timed kernel early-outs for particles outside the domain, so prove that
-        # (nearly) all of them were still inside when the segment ended
         skip = capi.kernel_launches()
-        removed = ctx.cull()
-        sort_launches += capi.kernel_launches() - skip
-        frac = 1.0 - removed / max(n_local, 1)
-        inside_frac = min(inside_frac, frac)
-        if frac < 0.999:
-            raise SystemExit(f"bench.py: only {frac:.4f} of the particles are still inside the domain "
-                             "after a timed segment -- the workload is invalid")
-    gpu_launches = capi.kernel_launches() - launches0 - sort_launches
+        inside_frac = min(inside_frac, check_inside("a timed segment"))
+        untimed_launches += capi.kernel_launches() - skip
+    gpu_launches = capi.kernel_launches() - launches0 - untimed_launches
     kernel_ms, kernel_launches = ctx.timer_read()
-    clocks = sampler.stop(t_region0, time.perf_counter()) if rank == 0 else None
+    t_region1 = time.perf_counter()
     n_sorts = (args.steps // args.resort) if args.resort else 0
-
-    if world_size > 1:
-        t = torch.tensor([ms], device=f"cuda:{local_rank}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    total_particles = n_local * world_size
+    ms = allmax(ms)
     value = total_particles * args.steps / (ms * 1e-3)
 
-    # ---- e2e: host buffers in, host buffers out, through the C-ABI -----------
+    # ======================================================================
+    # two-way: the same step with both deposits fused into the step kernel, and the sum of the
+    # deposited field over the ranks (gfsb200_deposit_allreduce) -- the path north_star names for
+    # multi-GPU.  Timed like the headline; the last exchange must have landed inside the region.
+    two_way = None
+    if not args.no_two_way:
+        restore()
+        par2 = world.step_params(fuse_deposit=True)
+
+        def two_way_step(i):
+            ctx.refresh_field()
+            ctx.step(par2)
+            comm.deposit_allreduce()
+
+        for i in range(3):
+            two_way_step(i)
+        comm.deposit_wait()
+        barrier()
+        ctx.timer_reset()
+        comm.exchange_stats()
+        k2 = min(args.steps, SEG)
+        t2_ms, t2_per = timed_steps(two_way_step, k2, tail=comm.deposit_wait)
+        t2_kernel_ms, _ = ctx.timer_read()
+        x_ms, x_n, x_bytes = comm.exchange_stats()
+        t2_ms = allmax(t2_ms)
+        # in-bench check of the exchanged field: volume conservation over ALL ranks and the same
+        # bytes on every rank
+        a = world.arrays
+        field = [ctx.download_deposit(c) for c in range(1 + world.dim)]
+        cons = float(np.sum(field[0] * a.h ** world.dim))
+        state = ctx.particles_download()
+        inside = ctx.locate(state["x"], state["y"], state["z"]) >= 0
+        vp = allsum(float(state["volume"][inside].sum()))
+        import hashlib
+        digest = hashlib.sha1(b"".join(np.ascontiguousarray(f).tobytes() for f in field)).hexdigest()
+        digests = [digest]
+        if world_size > 1:
+            digests = [None] * world_size
+            dist.all_gather_object(digests, digest)
+        check_inside("the two-way region")
+        b2 = 136 if world.dim == 3 else 96
+        ach2 = n_local * b2 / (t2_kernel_ms * 1e-3) / 1e9 if t2_kernel_ms > 0 else 0.0
+        whole2 = n_local * b2 / (t2_ms / k2 * 1e-3) / 1e9
+        two_way = {
+            "value": total_particles * k2 / (t2_ms * 1e-3), "unit": "particle-steps/s", "steps": k2,
+            "ms_per_step": t2_ms / k2, "step_ms": stats_ms(t2_per),
+            "what": "per step: cell pass + ONE fused kernel (locate, interpolate, forces, integrate, "
+                    "then void fraction and on-fluid force deposited at the new state) + "
+                    "gfsb200_deposit_allreduce; the last exchange lands inside the timed region",
+            "kernel": "step_kernel_wpipe<%d,...,DEP> (fused step + deposit)" % world.dim,
+            "kernel_ms": t2_kernel_ms,
+            "roofline": {"bound": "hbm", "algorithmic_bytes_per_particle_step": b2, "achieved": ach2,
+                         "peak": peak, "unit": "GB/s", "frac": ach2 / peak,
+                         "whole_step_achieved": whole2, "whole_step_frac": whole2 / peak},
+            "exchange": {"mode": ("owner slices: remote fp64 reductions over NVLink peer memory in the deposit "
+                                  "kernel + all-gather of the slices by the copy engines" if comm.peer_access
+                                  else "ncclAllReduce of the whole buffer"),
+                         "peer_access": bool(comm.peer_access), "device_ms": x_ms, "n": x_n,
+                         "bytes_sent_per_rank": int(x_bytes),
+                         "busbw_GBs": (x_bytes / (x_ms * 1e-3) / 1e9) if x_ms > 0 else None,
+                         "field_bytes": int((1 + world.dim) * a.n_cells * 8),
+                         "overlapped": "runs on a communication stream behind the deposit; the next "
+                                       "step's cell pass and step kernel do not wait for it"},
+            "check": {"sum_field_times_cell_volume": cons, "sum_particle_volume_all_ranks": vp,
+                      "rel_err": abs(cons - vp) / vp if vp else None,
+                      "conserved_1e-12": bool(vp and abs(cons - vp) <= 1e-12 * vp),
+                      "identical_on_all_ranks": len(set(digests)) == 1},
+        }
+        if two_way["check"]["rel_err"] is None or two_way["check"]["rel_err"] > 1e-9 or \
+                not two_way["check"]["identical_on_all_ranks"]:
+            raise SystemExit(f"bench.py: the exchanged deposit failed its check: {two_way['check']}")
+
+    # ======================================================================
+    # e2e: host buffers in, host buffers out, through the C-ABI
+    restore()
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     host = {k: torch.from_numpy(np.ascontiguousarray(parts[k])).pin_memory().numpy() for k in COLS if parts[k] is not None}
     fields = [torch.from_numpy(np.ascontiguousarray(f)).pin_memory().numpy()
               for f in (world.u, world.v, world.w) if f is not None]
+    n_host = len(host["x"])
     h2d = sum(a.nbytes for a in host.values()) + sum(a.nbytes for a in fields)
-    d2h = n_local * 8 * 2 * world.dim
+    d2h = n_host * 8 * 2 * world.dim
 
     def e2e_step():
         ctx.upload_field(*fields)                     # mirror U,V,W + cell pass
@@ -428,22 +594,21 @@ def run_b200(args):
     for _ in range(e2e_steps):
         e2e_step()
     barrier()
-    e2e_s = time.perf_counter() - t0
-    if world_size > 1:
-        t = torch.tensor([e2e_s], device=f"cuda:{local_rank}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = total_particles * e2e_steps / e2e_s
+    e2e_s = allmax(time.perf_counter() - t0)
+    e2e_value = allsum(n_host) * e2e_steps / e2e_s
 
     # ---- e2e, resident list: what a coupled run does on the steps where nothing on the host
-    # touches the particle objects -- the host solver's new U,V,W go up (pinned), the device runs
+    # touches the particle objects -- the host solver's new U,V,W go up ONCE (rank 0, pinned) and
+    # reach the other GPUs over NVLink (gfsb200_broadcast_field), the device runs
     # gfs_particle_list_event (cull + step + BCs) on the resident list, and only the event's
     # result (the number of particles removed) comes back
-    ctx.particles_upload(**parts)
-    ctx.sort()
+    restore()
 
     def resident_step():
-        ctx.upload_field(*fields)
+        if rank == 0:
+            comm.broadcast_field(0, *fields)
+        else:
+            comm.broadcast_field(0, *[None] * len(fields))
         return ctx.particle_list_event(par)
 
     resident_step()
@@ -453,15 +618,88 @@ def run_b200(args):
     for _ in range(res_steps):
         resident_step()
     barrier()
-    res_s = time.perf_counter() - t0
-    if world_size > 1:
-        t = torch.tensor([res_s], device=f"cuda:{local_rank}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        res_s = float(t.item())
+    res_s = allmax(time.perf_counter() - t0)
     res_value = total_particles * res_steps / res_s
+    field_bytes = int(sum(a.nbytes for a in fields))
+
+    # ======================================================================
+    # the other configs, short runs on the same context (C3: the non-lattice path -- child0
+    # descent + leaf_vtx loads; C5: STRONG scaling, 200 M particles over the N GPUs; 2D: the
+    # 80 B/particle-step roofline)
+    clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
+    configs = {}
+    if not args.no_configs:
+        def short_run(name, w, n_here, steps, fill, two=False):
+            ctx.upload_tree(w.tree)
+            ctx.upload_field(w.u, w.v, w.w)
+            fill()
+            order_particles()
+            p1 = w.step_params()
+
+            def st(i):
+                ctx.refresh_field()
+                ctx.step(p1)
+            for i in range(3):
+                st(i)
+            barrier()
+            ctx.timer_reset()
+            t_ms, per = timed_steps(st, steps)
+            k_ms, _ = ctx.timer_read()
+            frac_in = check_inside(name)
+            t_ms = allmax(t_ms)
+            n_tot = int(allsum(ctx.count))
+            bps1 = BYTES_PER_PARTICLE_STEP[w.dim]
+            out = {"workload": workload_name(name), "particles_total": n_tot, "particles_this_gpu": ctx.count,
+                   "cells": int(w.arrays.n_cells), "leaves": int(w.arrays.n_leaves),
+                   "levels": {int(k): int(v) for k, v in w.level_histogram().items()},
+                   "steps": steps, "ms_per_step": t_ms / steps, "step_ms": stats_ms(per),
+                   "value": n_tot * steps / (t_ms * 1e-3), "unit": "particle-steps/s",
+                   "step_kernel_ms": k_ms,
+                   "roofline_frac": ctx.count * bps1 / (k_ms * 1e-3) / 1e9 / peak if k_ms > 0 else None,
+                   "algorithmic_bytes_per_particle_step": bps1, "particles_inside_at_end": frac_in}
+            if two:
+                p2 = w.step_params(fuse_deposit=True)
+
+                def st2(i):
+                    ctx.refresh_field()
+                    ctx.step(p2)
+                    comm.deposit_allreduce()
+                for i in range(2):
+                    st2(i)
+                comm.deposit_wait()
+                barrier()
+                ctx.timer_reset()
+                comm.exchange_stats()
+                t_ms2, per2 = timed_steps(st2, steps, tail=comm.deposit_wait)
+                k_ms2, _ = ctx.timer_read()
+                x_ms2, _, x_b2 = comm.exchange_stats()
+                t_ms2 = allmax(t_ms2)
+                out["two_way"] = {"ms_per_step": t_ms2 / steps, "value": n_tot * steps / (t_ms2 * 1e-3),
+                                  "kernel_ms": k_ms2, "exchange_device_ms": x_ms2,
+                                  "bytes_sent_per_rank": int(x_b2),
+                                  "roofline_frac": ctx.count * 136 / (k_ms2 * 1e-3) / 1e9 / peak if k_ms2 > 0 else None}
+            return out
+
+        w3 = worlds.make_c3(n_particles=10_000_000)
+        if world_size == 1:
+            p3 = worlds.make_particles(w3)
+            configs["C3"] = short_run("C3", w3, len(p3["x"]), 20, lambda: ctx.particles_upload(**p3), two=True)
+            del p3
+        w5 = worlds.make_c5()
+        n5 = args.c5_particles // world_size
+        cols5 = device_cloud(torch, w5, n5, rank, device)
+        configs["C5"] = short_run("C5", w5, n5, 10, lambda: fill_from_device(torch, ctx, cols5, device), two=True)
+        configs["C5"]["scaling"] = "strong: %d particles in total, 1/N per GPU; cloud drawn on the device" % (n5 * world_size)
+        del cols5
+        torch.cuda.empty_cache()
+        if world_size == 1:
+            w2d = worlds.make_c1(level=10, n_particles=10_000_000)
+            p2d = worlds.make_particles(w2d)
+            configs["2D"] = short_run("C1", w2d, len(p2d["x"]), 20, lambda: ctx.particles_upload(**p2d))
+            configs["2D"]["workload"] = "2D lid-style level-10 quadtree (1024^2, four ghost layers), 10M particles, drag"
+            del p2d
 
     if rank == 0:
-        peak, peak_src = measured_peak()
         bps = BYTES_PER_PARTICLE_STEP[world.dim]
         achieved = n_local * bps / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
         line = {
@@ -469,9 +707,13 @@ def run_b200(args):
             "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
+            "step_ms": stats_ms(per_step),
             "config": {"workload": workload_name(args.config), "particles_per_gpu": n_local,
+                       "particles_total": total_particles,
                        "cells": int(world.arrays.n_cells), "leaves": int(world.arrays.n_leaves),
-                       "vertices": int(world.arrays.n_vertices), "two_way": bool(args.two_way),
+                       "vertices": int(world.arrays.n_vertices), "two_way": False,
+                       "sharding": ("one GPU: sorted by cell" if world_size == 1 else
+                                    "contiguous slices of the globally cell-sorted cloud (gfsb200_comm_rebalance)"),
                        "resort_every": args.resort, "sorts_in_timed_region": n_sorts,
                        "timed_segments": n_segments,
                        "cell_pass_every_step": True, "particles_inside_at_end": inside_frac,
@@ -481,26 +723,32 @@ def run_b200(args):
                          "frac_of_8TBs_spec": achieved / 8000.0,
                          "traffic": measured_traffic(args.config, n_local, world.dim), "peak_source": peak_src,
                          "algorithmic_bytes_per_particle_step": bps,
-                         "kernel_ms": kernel_ms, "kernel_launches": kernel_launches},
+                         "kernel_ms": kernel_ms, "kernel_launches": kernel_launches,
+                         "whole_step_frac": n_local * bps / (ms / args.steps * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "what": "per step: gfsb200_upload_field (U,V,W from pinned host memory, cell pass) + "
                             "gfsb200_step_host (8 particle columns H2D, fused step, 6 columns D2H, chunked "
                             "on three streams); wall clock"},
             "e2e_resident": {"value": res_value, "unit": "particle-steps/s",
-                             "h2d_bytes_per_step": int(sum(a.nbytes for a in fields)), "d2h_bytes_per_step": 8,
-                             "steps": res_steps,
-                             "what": "per step: gfsb200_upload_field (U,V,W from pinned host memory, cell pass) + "
+                             "h2d_bytes_per_step": field_bytes, "h2d_on": "rank 0 only",
+                             "nvlink_bytes_per_step_per_gpu": field_bytes if world_size > 1 else 0,
+                             "d2h_bytes_per_step": 8, "steps": res_steps,
+                             "what": "per step: gfsb200_broadcast_field (U,V,W from rank 0's pinned host memory "
+                                     "over PCIe once, ncclBroadcast over NVLink to the other GPUs, cell pass) + "
                                      "gfsb200_particle_list_event on the device-resident list (cull, fused step, "
                                      "particle BCs), returning the removed count; wall clock.  The full-sync "
                                      "`e2e` above is the headline; this is the same API with the list left on "
                                      "the device between steps"},
+            "two_way": two_way,
+            "configs": configs,
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world_size == 1:
             line["cpu_baseline"] = cpu_baseline(args, worlds)
         print(json.dumps(line), flush=True)
+    comm.close()
     ctx.close()
     if world_size > 1:
         dist.destroy_process_group()
@@ -538,7 +786,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2")
     ap.add_argument("--particles", type=int, default=0, help="particles per GPU (default: the config's)")
-    ap.add_argument("--two-way", action="store_true")
+    ap.add_argument("--no-two-way", action="store_true", help="skip the two-way block")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C3 / C5 / 2D lines")
+    ap.add_argument("--c5-particles", type=int, default=200_000_000, help="total particles of the C5 strong-scaling line")
     ap.add_argument("--level", type=int, default=0, help="experiment: override the C2 tree level")
     ap.add_argument("--resort", type=int, default=100,
                     help="re-sort particles by cell every R steps (0: never); particles cross a cell "

@@ -53,7 +53,7 @@ class StepParamsC(C.Structure):
         ("rho", C.c_double), ("mu", C.c_double), ("g", C.c_double * 3),
         ("cd_const", C.c_double), ("cl_const", C.c_double),
         ("record_cells", C.c_int32), ("record_forces", C.c_int32), ("cm_const", C.c_double),
-        ("track_escapes", C.c_int32),
+        ("track_escapes", C.c_int32), ("fuse_deposit", C.c_int32),
     ]
 
 
@@ -74,7 +74,7 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = os.path.join(LIB_DIR, "libgfsb200.so")
+    path = os.environ.get("GFSB200_LIB") or os.path.join(LIB_DIR, "libgfsb200.so")   # GFSB200_LIB: an A/B build
     if not os.path.exists(path):
         raise GfsB200Error(f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
     L = C.CDLL(path, mode=C.RTLD_GLOBAL)
@@ -142,6 +142,21 @@ def lib() -> C.CDLL:
         "gfsb200_deposit_select": (i32, [vp, i32]),
         "gfsb200_deposit_buffer": (i32, [vp, C.POINTER(vp), C.POINTER(i64)]),
         "gfsb200_download_deposit": (i32, [vp, i32, vp]),
+        "gfsb200_comm_unique_id": (i32, [vp]),
+        "gfsb200_comm_init_rank": (i32, [vp, vp, i32, i32, C.POINTER(vp)]),
+        "gfsb200_comm_init_all": (i32, [i32, C.POINTER(vp), C.POINTER(vp)]),
+        "gfsb200_comm_destroy": (None, [vp]),
+        "gfsb200_comm_rank": (i32, [vp]),
+        "gfsb200_comm_size": (i32, [vp]),
+        "gfsb200_comm_peer_access": (i32, [vp]),
+        "gfsb200_broadcast_field": (i32, [C.POINTER(vp), i32, i32, vp, vp, vp, vp, vp]),
+        "gfsb200_comm_rebalance": (i32, [C.POINTER(vp), i32]),
+        "gfsb200_comm_split": (i32, [vp, vp]),
+        "gfsb200_comm_splitters": (i32, [vp, C.c_int32, i32, vp]),
+        "gfsb200_deposit_allreduce": (i32, [C.POINTER(vp), i32]),
+        "gfsb200_deposit_wait": (i32, [vp]),
+        "gfsb200_comm_set_exchange": (i32, [vp, i32]),
+        "gfsb200_comm_exchange_stats": (i32, [vp, C.POINTER(dbl), C.POINTER(i64), C.POINTER(i64)]),
         "gfsb200_timer_reset": (i32, [vp]),
         "gfsb200_timer_read": (i32, [vp, C.POINTER(dbl), C.POINTER(i64)]),
         "gfsb200_kernel_launches": (i64, []),
@@ -322,7 +337,7 @@ class StepParams:
     def __init__(self, dt: float, forces: Sequence[int] = (), rho: float = 1.0, mu: float = 0.0,
                  g: Sequence[float] = (0.0, 0.0, 0.0), cd_const: float = float("nan"),
                  cl_const: float = float("nan"), record_cells: bool = False, record_forces: bool = False,
-                 cm_const: float = float("nan"), track_escapes: bool = False):
+                 cm_const: float = float("nan"), track_escapes: bool = False, fuse_deposit: bool = False):
         self.c = StepParamsC()
         lib().gfsb200_step_params_default(C.byref(self.c))
         self.c.dt = dt
@@ -335,6 +350,7 @@ class StepParams:
         self.c.cd_const, self.c.cl_const, self.c.cm_const = cd_const, cl_const, cm_const
         self.c.record_cells, self.c.record_forces = int(record_cells), int(record_forces)
         self.c.track_escapes = int(track_escapes)
+        self.c.fuse_deposit = int(fuse_deposit)
 
 
 class Context:
@@ -579,6 +595,105 @@ class Context:
         ms, n = C.c_double(), C.c_int64()
         _check(self._lib.gfsb200_timer_read(self.handle, C.byref(ms), C.byref(n)), "timer_read")
         return ms.value, n.value
+
+
+# ---------------------------------------------------------------------------
+# multi-GPU (gfsb200_comm*): one communicator per context
+
+EXCHANGE_AUTO, EXCHANGE_ALLREDUCE = 0, 1
+UNIQUE_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(UNIQUE_ID_BYTES)
+    _check(lib().gfsb200_comm_unique_id(buf), "comm_unique_id")
+    return buf.raw
+
+
+def comm_splitters(count: np.ndarray, nranks: int) -> np.ndarray:
+    """slice boundaries from global per-cell particle counts (host only, no device needed)"""
+    cnt = np.ascontiguousarray(count, dtype=np.uint32)
+    split = np.zeros(nranks + 1, dtype=np.int32)
+    _check(lib().gfsb200_comm_splitters(_ptr(cnt), len(cnt), nranks, _ptr(split)), "comm_splitters")
+    return split
+
+
+class Comm:
+    """The communicators of THIS process (one per local context): `Comm.init_rank` for one
+    process per GPU, `Comm.init_all` for one process driving several GPUs.  Every method is
+    a collective over all processes of the job."""
+
+    def __init__(self, handles, ctxs):
+        self._lib = lib()
+        self.handles = list(handles)
+        self.ctxs = list(ctxs)
+        self._arr = (C.c_void_p * len(self.handles))(*self.handles)
+
+    @classmethod
+    def init_rank(cls, ctx: "Context", unique_id: Optional[bytes], rank: int, nranks: int) -> "Comm":
+        h = C.c_void_p()
+        idbuf = C.create_string_buffer(unique_id, UNIQUE_ID_BYTES) if unique_id is not None else None
+        _check(lib().gfsb200_comm_init_rank(ctx.handle, idbuf, rank, nranks, C.byref(h)), "comm_init_rank")
+        return cls([h.value], [ctx])
+
+    @classmethod
+    def init_all(cls, ctxs) -> "Comm":
+        n = len(ctxs)
+        cs = (C.c_void_p * n)(*[c.handle for c in ctxs])
+        out = (C.c_void_p * n)()
+        _check(lib().gfsb200_comm_init_all(n, cs, out), "comm_init_all")
+        return cls([out[k] for k in range(n)], ctxs)
+
+    def close(self):
+        for h in self.handles:
+            self._lib.gfsb200_comm_destroy(h)
+        self.handles = []
+
+    @property
+    def n_local(self) -> int:
+        return len(self.handles)
+
+    @property
+    def size(self) -> int:
+        return self._lib.gfsb200_comm_size(self.handles[0])
+
+    @property
+    def rank(self) -> int:
+        return self._lib.gfsb200_comm_rank(self.handles[0])
+
+    @property
+    def peer_access(self) -> bool:
+        return bool(self._lib.gfsb200_comm_peer_access(self.handles[0]))
+
+    def set_exchange(self, mode: int):
+        for h in self.handles:
+            _check(self._lib.gfsb200_comm_set_exchange(h, mode), "comm_set_exchange")
+
+    def broadcast_field(self, root: int, u, v, w=None, alpha=None, mu=None):
+        arrs = [_f64(a) for a in (u, v, w, alpha, mu)]
+        _check(self._lib.gfsb200_broadcast_field(self._arr, self.n_local, root, *[_ptr(a) for a in arrs]),
+               "broadcast_field")
+
+    def rebalance(self):
+        _check(self._lib.gfsb200_comm_rebalance(self._arr, self.n_local), "comm_rebalance")
+
+    def split(self) -> np.ndarray:
+        s = np.zeros(self.size + 1, dtype=np.int32)
+        _check(self._lib.gfsb200_comm_split(self.handles[0], _ptr(s)), "comm_split")
+        return s
+
+    def deposit_allreduce(self):
+        _check(self._lib.gfsb200_deposit_allreduce(self._arr, self.n_local), "deposit_allreduce")
+
+    def deposit_wait(self):
+        for h in self.handles:
+            _check(self._lib.gfsb200_deposit_wait(h), "deposit_wait")
+
+    def exchange_stats(self, k: int = 0):
+        ms, n, b = C.c_double(), C.c_int64(), C.c_int64()
+        _check(self._lib.gfsb200_comm_exchange_stats(self.handles[k], C.byref(ms), C.byref(n), C.byref(b)),
+               "comm_exchange_stats")
+        return ms.value, n.value, b.value
 
 
 # ---------------------------------------------------------------------------

@@ -28,8 +28,8 @@ void gfsb200_launch_cell_pass (const DevTree *, const DevField *, int, cudaStrea
 			       cudaEvent_t, cudaEvent_t);
 void gfsb200_launch_vertex_values (const DevTree *, const DevField *, int, cudaStream_t);
 void gfsb200_launch_convective (const DevTree *, const DevField *, int, cudaStream_t);
-void gfsb200_launch_step (const DevTree *, const DevField *, const DevParticles *, const DevStep *,
-			  int, int, int, int, cudaStream_t);   /* (.., record, min blocks/SM, mode, SMs, stream) */
+int gfsb200_launch_step (const DevTree *, const DevField *, const DevParticles *, const DevStep *,
+			 int, int, int, int, cudaStream_t, const DevDeposit *);   /* (.., record, min blocks/SM, mode, SMs, stream, fused deposit) */
 void gfsb200_launch_advect (const DevTree *, const DevField *, const DevParticles *, double, int,
 			    cudaStream_t);
 void gfsb200_launch_locate (const DevTree *, int64_t, const double *, const double *,
@@ -40,7 +40,7 @@ void gfsb200_launch_interpolate (const DevTree *, const DevField *, int64_t, con
 void gfsb200_launch_corner_values (const DevTree *, const DevField *, int, int64_t, const int32_t *,
 				   double *, cudaStream_t);
 void gfsb200_launch_deposit (const DevTree *, const DevField *, const DevParticles *, const DevStep *,
-			     int, double *, double *, double *, double *, cudaStream_t);
+			     int, const DevDeposit *, int, const int32_t *, const uint8_t *, cudaStream_t);
 void gfsb200_launch_deposit_smoothed (const DevTree *, const DevField *, const DevParticles *,
 				      const DevStep *, double, const gfsb200_kernel *, double *, double *,
 				      double *, double *, cudaStream_t);
@@ -54,13 +54,14 @@ void gfsb200_launch_iota (int64_t, int32_t *, cudaStream_t);
 void gfsb200_launch_iota_u32 (int64_t, uint32_t *, uint32_t, cudaStream_t);
 void gfsb200_launch_sort_keys (int64_t, const int32_t *, uint32_t *, uint32_t, cudaStream_t);
 void gfsb200_launch_inside_flags (int64_t, const int32_t *, uint8_t *, cudaStream_t);
+void gfsb200_launch_outside_clear (int64_t, const int32_t *, uint8_t *, int *, cudaStream_t);
 cudaError_t gfsb200_cub_sort_pairs (void *, size_t *, const uint32_t *, uint32_t *, const int32_t *,
 				    int32_t *, int64_t, int, cudaStream_t);
 cudaError_t gfsb200_cub_select_flagged (void *, size_t *, const int32_t *, const uint8_t *,
 					int32_t *, int32_t *, int64_t, cudaStream_t);
 }
 
-#define NCOL 8     /* x y z vx vy vz mass volume */
+#include "ctx_internal.cuh"
 
 /* number of this library's own kernels launched so far in the process (CUB's sort / select
    kernels are not counted) */
@@ -68,70 +69,6 @@ extern "C" {
 long long gfsb200_launch_counter = 0;
 int64_t gfsb200_kernel_launches (void) { return gfsb200_launch_counter; }
 }
-
-struct gfsb200_ctx {
-  int device, n_sm;
-  cudaStream_t stream;
-  cudaStream_t aux_stream;     /* second stream of the cell pass */
-  cudaEvent_t ev_fork, ev_join;
-  /* tree */
-  bool have_tree;
-  DevTree T;
-  int32_t * d_child0, * d_neighbor, * d_la_slot, * d_vtx_off, * d_vtx_cell, * d_leaf_vtx, * d_parent;
-  double * d_solid_a, * d_solid_s;
-  uint8_t * d_level, * d_info;
-  double * d_vtx_w, * d_vtx_wuni;
-  /* field */
-  bool have_field, own_field;
-  DevField F;
-  double * d_field[5];         /* owned copies: u v w alpha mu */
-  double * d_prev[3];          /* Un Vn Wn (GfsForceInertial / GfsForceAddedMass) */
-  bool have_prev, acc_valid;
-  /* particles */
-  int64_t n, cap;
-  double * col[2][NCOL];       /* double-buffered SoA */
-  uint32_t * id[2];
-  int cur;
-  double * force[3];
-  int32_t * cell;
-  int64_t aux_cap;             /* capacity of force/cell/perm/key buffers */
-  int32_t * perm, * perm2;
-  uint32_t * key, * key2;
-  uint8_t * flag;
-  int32_t * d_count;
-  void * cub_tmp;
-  size_t cub_tmp_bytes;
-  double ** d_ptr_table;       /* [2][NCOL] device copy of col pointers */
-  /* escape tracking for gfs_particle_bc */
-  bool mark_outside;           /* the next tracked step flags (c->flag) the particles outside before it */
-  bool forces_recorded;        /* force[] holds what the last step (or on-fluid pass) recorded for the resident list */
-  int * esc_count;             /* [4]: escaped, wrapped, dropped, outside the domain before the step */
-  int32_t * esc_idx;
-  double * esc_old;
-  int esc_cap;
-  bool esc_armed;              /* the last step tracked escapes */
-  /* host-list pipeline (gfsb200_step_host) */
-  double * hp_col[3][NCOL];
-  int64_t hp_chunk;
-  cudaStream_t hp_h2d, hp_d2h;
-  cudaEvent_t hp_in[3], hp_done[3], hp_out[3];
-  /* deposit: two buffers so that the all-reduce of one step can overlap the next step */
-  double * deposit;            /* the selected one */
-  double * deposit_buf[2];
-  int64_t deposit_count;
-  double * knorm;              /* [2][knorm_n] correction, volume of the last smoothed deposit */
-  int64_t knorm_cap, knorm_n;
-  int step_minb;               /* __launch_bounds__ min blocks/SM variant of the step kernel */
-  int step_mode;               /* gfsb200_launch_step's mode; < 0: chosen by tree type */
-  /* timing */
-  std::vector<cudaEvent_t> ev;
-  size_t ev_used;
-  bool timing;
-};
-
-#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
-  return gfsb200_fail (GFSB200_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString (e_), __FILE__, __LINE__); \
-  } while (0)
 
 template <typename Tp>
 static int dev_alloc_copy (Tp ** dst, const Tp * src, size_t n, cudaStream_t st)
@@ -142,6 +79,34 @@ static int dev_alloc_copy (Tp ** dst, const Tp * src, size_t n, cudaStream_t st)
     CK (cudaMemcpyAsync (*dst, src, n*sizeof (Tp), cudaMemcpyHostToDevice, st));
   return GFSB200_OK;
 }
+
+/* Device scratch of the batched queries: ONE pooled allocation per context that only grows, carved
+ * up by a bump pointer -- an output event that fires every step pays no cudaMalloc / cudaFree (each
+ * of which synchronises the device). */
+struct Scratch {
+  gfsb200_ctx * c;
+  size_t used;
+  Scratch (gfsb200_ctx * ctx) : c (ctx), used (0) {}
+  static size_t pad (size_t b) { return (b + 255) & ~(size_t) 255; }
+  /* total: the sum of the padded sizes about to be taken */
+  int reserve (size_t total)
+  {
+    if (total <= c->scratch_bytes) return GFSB200_OK;
+    CK (cudaStreamSynchronize (c->stream));
+    cudaFree (c->scratch);
+    c->scratch = NULL; c->scratch_bytes = 0;
+    total += total/4;
+    CK (cudaMalloc ((void **) &c->scratch, total));
+    c->scratch_bytes = total;
+    return GFSB200_OK;
+  }
+  template <typename Tp> Tp * take (size_t n)
+  {
+    Tp * p = reinterpret_cast<Tp *> (reinterpret_cast<char *> (c->scratch) + used);
+    used += pad (n*sizeof (Tp));
+    return p;
+  }
+};
 
 static void free_tree (gfsb200_ctx * c)
 {
@@ -163,6 +128,7 @@ static void free_tree (gfsb200_ctx * c)
   cudaFree (c->deposit_buf[0]); cudaFree (c->deposit_buf[1]);
   cudaFree (c->knorm); c->knorm = NULL; c->knorm_cap = c->knorm_n = 0;
   c->deposit = c->deposit_buf[0] = c->deposit_buf[1] = NULL; c->deposit_count = 0;
+  c->dep_which = c->dep_result = 0;
   c->have_tree = c->have_field = false;
 }
 
@@ -221,6 +187,9 @@ extern "C" int gfsb200_ctx_create (int device, gfsb200_ctx ** out)
   c->cell = c->perm = c->perm2 = NULL; c->key = c->key2 = NULL; c->flag = NULL;
   c->d_count = NULL; c->cub_tmp = NULL; c->cub_tmp_bytes = 0; c->d_ptr_table = NULL;
   c->deposit = c->deposit_buf[0] = c->deposit_buf[1] = NULL; c->deposit_count = 0;
+  c->dep_which = c->dep_result = 0;
+  c->comm = NULL; c->tree_generation = 0;
+  c->scratch = NULL; c->scratch_bytes = 0;
   memset (c->hp_col, 0, sizeof c->hp_col);
   c->hp_chunk = 0; c->hp_h2d = c->hp_d2h = NULL;
   c->ev_used = 0; c->timing = true;
@@ -244,8 +213,10 @@ extern "C" void gfsb200_ctx_destroy (gfsb200_ctx * c)
   if (!c) return;
   cudaSetDevice (c->device);
   cudaStreamSynchronize (c->stream);
+  if (c->comm) gfsb200_comm_detach (c->comm);
   free_tree (c);
   free_particles (c);
+  cudaFree (c->scratch);
   for (int s = 0; s < 3; s++)
     for (int k = 0; k < NCOL; k++) cudaFree (c->hp_col[s][k]);
   if (c->hp_h2d) {
@@ -283,7 +254,9 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
     return gfsb200_fail (GFSB200_ERR_UNSUPPORTED, "upload_tree: more than %d root cells", GFSB200_MAX_DEV_ROOTS);
   CK (cudaSetDevice (c->device));
   CK (cudaStreamSynchronize (c->stream));
+  if (c->comm) gfsb200_comm_tree_changed (c->comm);   /* waits for its stream; ownership and peer pointers lapse */
   free_tree (c);
+  c->tree_generation++;
 
   const int32_t n = t->n_cells;
   const int nc = t->nchild;
@@ -502,19 +475,14 @@ extern "C" void gfsb200_host_free (void * p)
   if (p) cudaFreeHost (p);
 }
 
-extern "C" int gfsb200_upload_field (gfsb200_ctx * c, const double * u, const double * v,
-				     const double * w, const double * alpha, const double * mu)
+/* the owned device copies of U,V,W,alpha,mu: allocated for the components in `present', released
+ * for the others, and made the resident field */
+extern "C" int gfsb200_internal_field_buffers (gfsb200_ctx * c, const int present[5])
 {
-  if (!c || !c->have_tree) return gfsb200_fail (GFSB200_ERR_STATE, "upload_field: upload a tree first");
-  if (!u || !v || (c->T.dim == 3 && !w))
-    return gfsb200_fail (GFSB200_ERR_ARG, "upload_field: missing velocity component");
-  CK (cudaSetDevice (c->device));
-  const double * src[5] = { u, v, c->T.dim == 3 ? w : NULL, alpha, mu };
   const size_t bytes = (size_t) c->T.n_cells*sizeof (double);
   for (int i = 0; i < 5; i++) {
-    if (src[i]) {
+    if (present[i]) {
       if (!c->d_field[i]) CK (cudaMalloc ((void **) &c->d_field[i], bytes));
-      CK (cudaMemcpyAsync (c->d_field[i], src[i], bytes, cudaMemcpyHostToDevice, c->stream));
     }
     else if (c->d_field[i]) {
       CK (cudaStreamSynchronize (c->stream));
@@ -524,6 +492,24 @@ extern "C" int gfsb200_upload_field (gfsb200_ctx * c, const double * u, const do
   }
   c->F.u[0] = c->d_field[0]; c->F.u[1] = c->d_field[1]; c->F.u[2] = c->d_field[2];
   c->F.alpha = c->d_field[3]; c->F.mu = c->d_field[4];
+  return GFSB200_OK;
+}
+
+extern "C" int gfsb200_upload_field (gfsb200_ctx * c, const double * u, const double * v,
+				     const double * w, const double * alpha, const double * mu)
+{
+  if (!c || !c->have_tree) return gfsb200_fail (GFSB200_ERR_STATE, "upload_field: upload a tree first");
+  if (!u || !v || (c->T.dim == 3 && !w))
+    return gfsb200_fail (GFSB200_ERR_ARG, "upload_field: missing velocity component");
+  CK (cudaSetDevice (c->device));
+  const double * src[5] = { u, v, c->T.dim == 3 ? w : NULL, alpha, mu };
+  const int present[5] = { 1, 1, c->T.dim == 3, alpha != NULL, mu != NULL };
+  int r = gfsb200_internal_field_buffers (c, present);
+  if (r) return r;
+  const size_t bytes = (size_t) c->T.n_cells*sizeof (double);
+  for (int i = 0; i < 5; i++)
+    if (present[i])
+      CK (cudaMemcpyAsync (c->d_field[i], src[i], bytes, cudaMemcpyHostToDevice, c->stream));
   return gfsb200_refresh_field (c);
 }
 
@@ -546,15 +532,17 @@ extern "C" int gfsb200_download_corner_values (gfsb200_ctx * c, int comp, int64_
     return gfsb200_fail (GFSB200_ERR_ARG, "download_corner_values: bad argument");
   CK (cudaSetDevice (c->device));
   const int nc = 1 << c->T.dim;
-  int32_t * d_cells; double * d_out;
-  CK (cudaMalloc ((void **) &d_cells, (n ? n : 1)*sizeof (int32_t)));
-  CK (cudaMalloc ((void **) &d_out, (n ? n : 1)*nc*sizeof (double)));
+  if (n == 0) return GFSB200_OK;
+  Scratch sc (c);
+  int r = sc.reserve (Scratch::pad (n*sizeof (int32_t)) + Scratch::pad (n*nc*sizeof (double)));
+  if (r) return r;
+  int32_t * d_cells = sc.take<int32_t> (n);
+  double * d_out = sc.take<double> (n*nc);
   CK (cudaMemcpyAsync (d_cells, cells, n*sizeof (int32_t), cudaMemcpyHostToDevice, c->stream));
   gfsb200_launch_corner_values (&c->T, &c->F, comp, n, d_cells, d_out, c->stream);
   CK (cudaGetLastError ());
   CK (cudaMemcpyAsync (out, d_out, n*nc*sizeof (double), cudaMemcpyDeviceToHost, c->stream));
   CK (cudaStreamSynchronize (c->stream));
-  cudaFree (d_cells); cudaFree (d_out);
   return GFSB200_OK;
 }
 
@@ -609,43 +597,52 @@ static int ensure_aux (gfsb200_ctx * c, int64_t n)
   return GFSB200_OK;
 }
 
+/* capacity for n particles in both SoA buffers; the current contents (c->n particles) are kept */
+extern "C" int gfsb200_internal_reserve (gfsb200_ctx * c, int64_t n)
+{
+  if (n <= c->cap) return GFSB200_OK;
+  CK (cudaStreamSynchronize (c->stream));
+  int64_t keep = c->n;
+  /* columns are padded to a whole number of 256-particle tiles so that the
+     bulk copies of the staged step kernel never run past the allocation */
+  const int64_t alloc_n = (n + 255)/256*256;
+  double * ncol[2][NCOL]; uint32_t * nid[2];
+  for (int b = 0; b < 2; b++) {
+    for (int k = 0; k < NCOL; k++) {
+      CK (cudaMalloc ((void **) &ncol[b][k], alloc_n*sizeof (double)));
+      CK (cudaMemsetAsync (ncol[b][k], 0, alloc_n*sizeof (double), c->stream));
+    }
+    CK (cudaMalloc ((void **) &nid[b], alloc_n*sizeof (uint32_t)));
+  }
+  if (keep) {
+    for (int k = 0; k < NCOL; k++)
+      CK (cudaMemcpyAsync (ncol[0][k], c->col[c->cur][k], keep*sizeof (double), cudaMemcpyDeviceToDevice, c->stream));
+    CK (cudaMemcpyAsync (nid[0], c->id[c->cur], keep*sizeof (uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+    CK (cudaStreamSynchronize (c->stream));
+  }
+  for (int b = 0; b < 2; b++) {
+    for (int k = 0; k < NCOL; k++) { cudaFree (c->col[b][k]); c->col[b][k] = ncol[b][k]; }
+    cudaFree (c->id[b]); c->id[b] = nid[b];
+  }
+  c->cur = 0;
+  c->cap = n;
+  double * table[2*NCOL];
+  for (int b = 0; b < 2; b++) for (int k = 0; k < NCOL; k++) table[b*NCOL + k] = c->col[b][k];
+  CK (cudaMemcpyAsync (c->d_ptr_table, table, sizeof table, cudaMemcpyHostToDevice, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  return GFSB200_OK;
+}
+
+extern "C" int gfsb200_internal_ensure_aux (gfsb200_ctx * c, int64_t n) { return ensure_aux (c, n); }
+
 extern "C" int gfsb200_particles_resize (gfsb200_ctx * c, int64_t n)
 {
   if (!c || n < 0 || n > INT32_MAX)
     return gfsb200_fail (GFSB200_ERR_ARG, "particles_resize: bad count");
   CK (cudaSetDevice (c->device));
-  if (n > c->cap) {
-    CK (cudaStreamSynchronize (c->stream));
-    int64_t keep = c->n;
-    /* columns are padded to a whole number of 256-particle tiles so that the
-       bulk copies of the staged step kernel never run past the allocation */
-    const int64_t alloc_n = (n + 255)/256*256;
-    double * ncol[2][NCOL]; uint32_t * nid[2];
-    for (int b = 0; b < 2; b++) {
-      for (int k = 0; k < NCOL; k++) {
-	CK (cudaMalloc ((void **) &ncol[b][k], alloc_n*sizeof (double)));
-	CK (cudaMemsetAsync (ncol[b][k], 0, alloc_n*sizeof (double), c->stream));
-      }
-      CK (cudaMalloc ((void **) &nid[b], alloc_n*sizeof (uint32_t)));
-    }
-    if (keep) {
-      for (int k = 0; k < NCOL; k++)
-	CK (cudaMemcpyAsync (ncol[0][k], c->col[c->cur][k], keep*sizeof (double), cudaMemcpyDeviceToDevice, c->stream));
-      CK (cudaMemcpyAsync (nid[0], c->id[c->cur], keep*sizeof (uint32_t), cudaMemcpyDeviceToDevice, c->stream));
-      CK (cudaStreamSynchronize (c->stream));
-    }
-    for (int b = 0; b < 2; b++) {
-      for (int k = 0; k < NCOL; k++) { cudaFree (c->col[b][k]); c->col[b][k] = ncol[b][k]; }
-      cudaFree (c->id[b]); c->id[b] = nid[b];
-    }
-    c->cur = 0;
-    c->cap = n;
-    double * table[2*NCOL];
-    for (int b = 0; b < 2; b++) for (int k = 0; k < NCOL; k++) table[b*NCOL + k] = c->col[b][k];
-    CK (cudaMemcpyAsync (c->d_ptr_table, table, sizeof table, cudaMemcpyHostToDevice, c->stream));
-    CK (cudaStreamSynchronize (c->stream));
-  }
-  int r = ensure_aux (c, n > 0 ? n : 1);
+  int r = gfsb200_internal_reserve (c, n);
+  if (r) return r;
+  r = ensure_aux (c, n > 0 ? n : 1);
   if (r) return r;
   if (n > c->n)    /* new slots get ids continuing the sequence */
     gfsb200_launch_iota_u32 (n - c->n, c->id[c->cur] + c->n, (uint32_t) c->n + 1, c->stream);
@@ -807,6 +804,8 @@ static int timed_end (gfsb200_ctx * c)
   return GFSB200_OK;
 }
 
+static int deposit_target (gfsb200_ctx * c, int what, bool local_only, DevDeposit * D);
+
 extern "C" int gfsb200_step (gfsb200_ctx * c, const gfsb200_step_params * p)
 {
   if (!c || !c->have_field)
@@ -841,16 +840,29 @@ extern "C" int gfsb200_step (gfsb200_ctx * c, const gfsb200_step_params * p)
     c->esc_armed = true;
   }
   DevParticles P = particles_view (c);
+  DevDeposit D;
+  const bool fuse = p->fuse_deposit && S.n_forces > 0;
+  if (p->fuse_deposit && !fuse)
+    return gfsb200_fail (GFSB200_ERR_UNSUPPORTED, "step: fuse_deposit needs a force list (tracers deposit no force)");
+  if (fuse && (r = deposit_target (c, 3, false, &D))) return r;
   if ((r = timed_begin (c))) return r;
+  int fused = 0;
   if (S.n_forces == 0)
     gfsb200_launch_advect (&c->T, &c->F, &P, S.dt, p->record_cells, c->stream);
   else
-    gfsb200_launch_step (&c->T, &c->F, &P, &S, p->record_cells || p->record_forces, c->step_minb,
-			 c->step_mode, c->n_sm, c->stream);
+    fused = gfsb200_launch_step (&c->T, &c->F, &P, &S, p->record_cells || p->record_forces, c->step_minb,
+				 c->step_mode, c->n_sm, c->stream, fuse ? &D : NULL);
+  if (fuse && !fused) {
+    /* a kernel flavour without the fused tail (runtime force list, recorded forces): the same
+       result from the stand-alone pass over the new state */
+    gfsb200_launch_deposit (&c->T, &c->F, &P, &S, 3, &D, 0, NULL, NULL, c->stream);
+  }
   if ((r = timed_end (c))) return r;
   CK (cudaGetLastError ());
   if (S.n_forces > 0 && p->record_forces)
     c->forces_recorded = true;
+  c->last_step_fused = fuse;
+  if (fuse) { c->last_S = S; c->last_D = D; }
   return GFSB200_OK;
 }
 
@@ -904,6 +916,8 @@ extern "C" int gfsb200_step_host (gfsb200_ctx * c, const gfsb200_step_params * p
     return gfsb200_fail (GFSB200_ERR_UNSUPPORTED, "step_host: tracer lists go through gfsb200_step");
   if (n == 0) return GFSB200_OK;
   CK (cudaSetDevice (c->device));
+  if (p->fuse_deposit)
+    return gfsb200_fail (GFSB200_ERR_UNSUPPORTED, "step_host: fuse_deposit needs the resident list");
   if (S.mutates_mass)
     return gfsb200_fail (GFSB200_ERR_UNSUPPORTED, "step_host: GfsForceAddedMass rewrites mass; use the resident path");
   if ((r = prepare_inertial (c, &S))) return r;
@@ -932,7 +946,7 @@ extern "C" int gfsb200_step_host (gfsb200_ctx * c, const gfsb200_step_params * p
     P.x = c->hp_col[s][0]; P.y = c->hp_col[s][1]; P.z = c->hp_col[s][2];
     P.vx = c->hp_col[s][3]; P.vy = c->hp_col[s][4]; P.vz = c->hp_col[s][5];
     P.mass = c->hp_col[s][6]; P.volume = c->hp_col[s][7];
-    gfsb200_launch_step (&c->T, &c->F, &P, &S, 0, c->step_minb, c->step_mode, c->n_sm, c->stream);
+    gfsb200_launch_step (&c->T, &c->F, &P, &S, 0, c->step_minb, c->step_mode, c->n_sm, c->stream, NULL);
     CK (cudaGetLastError ());
     CK (cudaEventRecord (c->hp_done[s], c->stream));
     CK (cudaStreamWaitEvent (c->hp_d2h, c->hp_done[s], 0));
@@ -978,11 +992,11 @@ static int apply_permutation (gfsb200_ctx * c, int64_t n_new)
   return GFSB200_OK;
 }
 
-extern "C" int gfsb200_particles_sort (gfsb200_ctx * c)
+/* sort the resident particles by containing cell; the sorted keys (flat cell index, n_cells for a
+ * particle outside the domain) are left in c->key2 */
+extern "C" int gfsb200_internal_sort (gfsb200_ctx * c)
 {
-  if (!c || !c->have_tree) return gfsb200_fail (GFSB200_ERR_STATE, "particles_sort: no tree");
-  if (c->n <= 1) return GFSB200_OK;
-  CK (cudaSetDevice (c->device));
+  if (c->n <= 0) return GFSB200_OK;
   DevParticles P = particles_view (c);
   gfsb200_launch_locate (&c->T, P.n, P.x, P.y, P.z, c->cell, c->stream);
   gfsb200_launch_sort_keys (P.n, c->cell, c->key, (uint32_t) c->T.n_cells, c->stream);
@@ -996,6 +1010,14 @@ extern "C" int gfsb200_particles_sort (gfsb200_ctx * c)
   if (r) return r;
   CK (gfsb200_cub_sort_pairs (c->cub_tmp, &bytes, c->key, c->key2, c->perm, c->perm2, P.n, end_bit, c->stream));
   return apply_permutation (c, P.n);
+}
+
+extern "C" int gfsb200_particles_sort (gfsb200_ctx * c)
+{
+  if (!c || !c->have_tree) return gfsb200_fail (GFSB200_ERR_STATE, "particles_sort: no tree");
+  if (c->n <= 1) return GFSB200_OK;
+  CK (cudaSetDevice (c->device));
+  return gfsb200_internal_sort (c);
 }
 
 extern "C" int gfsb200_particles_cull (gfsb200_ctx * c, int64_t * n_removed)
@@ -1038,18 +1060,38 @@ static int particle_bc_impl (gfsb200_ctx * c, bool flags_ready, int outside, int
   CK (cudaMemcpyAsync (counts, c->esc_count, sizeof (int), cudaMemcpyDeviceToHost, c->stream));
   CK (cudaStreamSynchronize (c->stream));
   if (counts[0] == 0 && outside == 0) return GFSB200_OK;
-  if (counts[0] > c->esc_cap)
-    return gfsb200_fail (GFSB200_ERR_STATE, "particle_bc: %d particles left the domain in one step, more "
-			 "than the %d tracked (1/16 of the list)", counts[0], c->esc_cap);
+  /* More particles left in one step than the record holds (n/16 + 1024): the first esc_cap are
+     handled exactly; the others have lost their previous position (the step has overwritten it),
+     so the exit face cannot be found -- they are dropped, as a particle leaving through a
+     non-periodic side is (the pass below removes whatever is still outside). */
+  const bool overflow = counts[0] > c->esc_cap;
+  const int n_esc = overflow ? c->esc_cap : counts[0];
   DevParticles P = particles_view (c);
   if (!flags_ready)
     CK (cudaMemsetAsync (c->flag, 1, (size_t) P.n, c->stream));
-  if (counts[0] > 0) {
-    gfsb200_launch_particle_bc (&c->T, &P, counts[0], c->esc_idx, c->esc_old, c->flag, c->esc_count + 1,
+  if (n_esc > 0) {
+    gfsb200_launch_particle_bc (&c->T, &P, n_esc, c->esc_idx, c->esc_old, c->flag, c->esc_count + 1,
 				c->stream);
     CK (cudaGetLastError ());
+    if (c->last_step_fused) {
+      /* the fused step deposited nothing for a particle whose new position was outside; those
+	 that were wrapped back in deposit now, at the wrapped position */
+      gfsb200_launch_deposit (&c->T, &c->F, &P, &c->last_S, 3, &c->last_D, n_esc, c->esc_idx, c->flag, c->stream);
+      CK (cudaGetLastError ());
+    }
     CK (cudaMemcpyAsync (counts, c->esc_count, 3*sizeof (int), cudaMemcpyDeviceToHost, c->stream));
     CK (cudaStreamSynchronize (c->stream));
+  }
+  int lost = 0;
+  if (overflow) {
+    gfsb200_launch_locate (&c->T, P.n, P.x, P.y, P.z, c->cell, c->stream);
+    gfsb200_launch_outside_clear (P.n, c->cell, c->flag, c->esc_count + 1, c->stream);
+    CK (cudaGetLastError ());
+    int w = counts[1];
+    CK (cudaMemcpyAsync (&lost, c->esc_count + 1, sizeof (int), cudaMemcpyDeviceToHost, c->stream));
+    CK (cudaStreamSynchronize (c->stream));
+    lost -= w;                 /* esc_count[1] was reused as the counter of the clearing pass */
+    counts[2] += lost;
   }
   if (n_wrapped) *n_wrapped = counts[1];
   if (n_dropped) *n_dropped = counts[2];
@@ -1108,9 +1150,7 @@ extern "C" int gfsb200_escaped_download (gfsb200_ctx * c, int64_t cap, int32_t *
   int64_t n = 0;
   int r = gfsb200_escaped_count (c, &n);
   if (r) return r;
-  if (n > c->esc_cap)
-    return gfsb200_fail (GFSB200_ERR_STATE, "escaped_download: %lld particles left the domain in one step, "
-			 "more than the %d tracked (1/16 of the list)", (long long) n, c->esc_cap);
+  if (n > c->esc_cap) n = c->esc_cap;   /* the record holds n/16 + 1024 particles; *n_out tells the caller */
   if (n > cap) n = cap;
   if (n) {
     CK (cudaMemcpyAsync (idx, c->esc_idx, n*sizeof (int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -1172,17 +1212,18 @@ extern "C" int gfsb200_locate (gfsb200_ctx * c, int64_t n, const double * x, con
   CK (cudaSetDevice (c->device));
   double * d[3] = { NULL, NULL, NULL }; int32_t * dc = NULL;
   const double * src[3] = { x, y, z };
+  Scratch sc (c);
+  int r = sc.reserve (3*Scratch::pad (n*sizeof (double)) + Scratch::pad (n*sizeof (int32_t)));
+  if (r) return r;
   for (int a = 0; a < c->T.dim; a++) {
-    CK (cudaMalloc ((void **) &d[a], n*sizeof (double)));
+    d[a] = sc.take<double> (n);
     CK (cudaMemcpyAsync (d[a], src[a], n*sizeof (double), cudaMemcpyHostToDevice, c->stream));
   }
-  CK (cudaMalloc ((void **) &dc, n*sizeof (int32_t)));
+  dc = sc.take<int32_t> (n);
   gfsb200_launch_locate (&c->T, n, d[0], d[1], d[2], dc, c->stream);
   CK (cudaGetLastError ());
   CK (cudaMemcpyAsync (cell, dc, n*sizeof (int32_t), cudaMemcpyDeviceToHost, c->stream));
   CK (cudaStreamSynchronize (c->stream));
-  for (int a = 0; a < 3; a++) cudaFree (d[a]);
-  cudaFree (dc);
   return GFSB200_OK;
 }
 
@@ -1197,10 +1238,13 @@ extern "C" int gfsb200_interpolate (gfsb200_ctx * c, int64_t n, const double * x
   double * d[3] = { NULL, NULL, NULL }, * o[3] = { NULL, NULL, NULL };
   const double * src[3] = { x, y, z };
   double * dst[3] = { u, v, c->T.dim == 3 ? w : NULL };
+  Scratch sc (c);
+  int r = sc.reserve (6*Scratch::pad (n*sizeof (double)));
+  if (r) return r;
   for (int a = 0; a < c->T.dim; a++) {
-    CK (cudaMalloc ((void **) &d[a], n*sizeof (double)));
+    d[a] = sc.take<double> (n);
     CK (cudaMemcpyAsync (d[a], src[a], n*sizeof (double), cudaMemcpyHostToDevice, c->stream));
-    if (dst[a]) CK (cudaMalloc ((void **) &o[a], n*sizeof (double)));
+    if (dst[a]) o[a] = sc.take<double> (n);
   }
   gfsb200_launch_interpolate (&c->T, &c->F, n, d[0], d[1], d[2], o[0], o[1], o[2], c->stream);
   CK (cudaGetLastError ());
@@ -1208,7 +1252,6 @@ extern "C" int gfsb200_interpolate (gfsb200_ctx * c, int64_t n, const double * x
     if (dst[a])
       CK (cudaMemcpyAsync (dst[a], o[a], n*sizeof (double), cudaMemcpyDeviceToHost, c->stream));
   CK (cudaStreamSynchronize (c->stream));
-  for (int a = 0; a < 3; a++) { cudaFree (d[a]); cudaFree (o[a]); }
   return GFSB200_OK;
 }
 
@@ -1232,61 +1275,56 @@ extern "C" int gfsb200_output_location (gfsb200_ctx * c, int nvar, const double 
   int * flag = NULL;
   int32_t * dcell = NULL;
   std::vector<int32_t> hcell (n);
-  int rc = GFSB200_OK;
-#define OL(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
-    rc = gfsb200_fail (GFSB200_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString (e_), __FILE__, __LINE__); \
-    goto done; } } while (0)
-  {
-    const double * src[3] = { x, y, z };
-    for (int a = 0; a < dim; a++) {
-      OL (cudaMalloc ((void **) &d[a], n*sizeof (double)));
-      OL (cudaMemcpyAsync (d[a], src[a], n*sizeof (double), cudaMemcpyHostToDevice, c->stream));
-    }
-    OL (cudaMalloc ((void **) &dcell, n*sizeof (int32_t)));
-    gfsb200_launch_locate (&c->T, n, d[0], d[1], d[2], dcell, c->stream);
-    OL (cudaGetLastError ());
-    OL (cudaMemcpyAsync (hcell.data (), dcell, n*sizeof (int32_t), cudaMemcpyDeviceToHost, c->stream));
-    OL (cudaStreamSynchronize (c->stream));
-    if (cell) memcpy (cell, hcell.data (), n*sizeof (int32_t));
-    if (!interpolate) {
-      /* GFS_VALUE (cell, v) */
-      for (int k = 0; k < nvar; k++)
-	for (int64_t i = 0; i < n; i++)
-	  out[k][i] = hcell[i] >= 0 ? vars[k][hcell[i]] : GFSB200_NODATA;
-      goto done;
-    }
-    const int vs = dim == 3 ? 4 : 2;
-    for (int a = 0; a < dim; a++) {
-      OL (cudaMalloc ((void **) &f[a], nc*sizeof (double)));
-      OL (cudaMalloc ((void **) &o[a], n*sizeof (double)));
-    }
-    OL (cudaMalloc ((void **) &vtx, (size_t) (c->T.n_vertices ? c->T.n_vertices : 1)*vs*sizeof (double)));
-    OL (cudaMalloc ((void **) &flag, sizeof (int)));
-    for (int k0 = 0; k0 < nvar; k0 += dim) {
-      DevField tmp;
-      memset (&tmp, 0, sizeof tmp);
-      for (int a = 0; a < dim; a++) {
-	const int k = k0 + a < nvar ? k0 + a : k0;      /* pad a short batch with its first variable */
-	OL (cudaMemcpyAsync (f[a], vars[k], nc*sizeof (double), cudaMemcpyHostToDevice, c->stream));
-	tmp.u[a] = f[a];
-      }
-      tmp.vtx_val = vtx;
-      tmp.nodata_flag = flag;
-      OL (cudaMemsetAsync (flag, 0, sizeof (int), c->stream));
-      gfsb200_launch_vertex_values (&c->T, &tmp, c->n_sm, c->stream);
-      OL (cudaGetLastError ());
-      gfsb200_launch_interpolate (&c->T, &tmp, n, d[0], d[1], d[2], o[0], o[1], dim == 3 ? o[2] : NULL, c->stream);
-      OL (cudaGetLastError ());
-      for (int a = 0; a < dim && k0 + a < nvar; a++)
-	OL (cudaMemcpyAsync (out[k0 + a], o[a], n*sizeof (double), cudaMemcpyDeviceToHost, c->stream));
-      OL (cudaStreamSynchronize (c->stream));
-    }
+  const int vs = dim == 3 ? 4 : 2;
+  const size_t nv = (size_t) (c->T.n_vertices ? c->T.n_vertices : 1);
+  Scratch sc (c);
+  int rc = sc.reserve (6*Scratch::pad (n*sizeof (double)) + Scratch::pad (n*sizeof (int32_t)) +
+		       (interpolate ? 3*Scratch::pad (nc*sizeof (double)) + Scratch::pad (nv*vs*sizeof (double)) : 0) + 256);
+  if (rc) return rc;
+  const double * src[3] = { x, y, z };
+  for (int a = 0; a < dim; a++) {
+    d[a] = sc.take<double> (n);
+    CK (cudaMemcpyAsync (d[a], src[a], n*sizeof (double), cudaMemcpyHostToDevice, c->stream));
   }
-done:
-#undef OL
-  for (int a = 0; a < 3; a++) { cudaFree (d[a]); cudaFree (o[a]); cudaFree (f[a]); }
-  cudaFree (vtx); cudaFree (flag); cudaFree (dcell);
-  return rc;
+  dcell = sc.take<int32_t> (n);
+  gfsb200_launch_locate (&c->T, n, d[0], d[1], d[2], dcell, c->stream);
+  CK (cudaGetLastError ());
+  CK (cudaMemcpyAsync (hcell.data (), dcell, n*sizeof (int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  if (cell) memcpy (cell, hcell.data (), n*sizeof (int32_t));
+  if (!interpolate) {
+    /* GFS_VALUE (cell, v) */
+    for (int k = 0; k < nvar; k++)
+      for (int64_t i = 0; i < n; i++)
+	out[k][i] = hcell[i] >= 0 ? vars[k][hcell[i]] : GFSB200_NODATA;
+    return GFSB200_OK;
+  }
+  for (int a = 0; a < dim; a++) {
+    f[a] = sc.take<double> (nc);
+    o[a] = sc.take<double> (n);
+  }
+  vtx = sc.take<double> (nv*vs);
+  flag = sc.take<int> (1);
+  for (int k0 = 0; k0 < nvar; k0 += dim) {
+    DevField tmp;
+    memset (&tmp, 0, sizeof tmp);
+    for (int a = 0; a < dim; a++) {
+      const int k = k0 + a < nvar ? k0 + a : k0;      /* pad a short batch with its first variable */
+      CK (cudaMemcpyAsync (f[a], vars[k], nc*sizeof (double), cudaMemcpyHostToDevice, c->stream));
+      tmp.u[a] = f[a];
+    }
+    tmp.vtx_val = vtx;
+    tmp.nodata_flag = flag;
+    CK (cudaMemsetAsync (flag, 0, sizeof (int), c->stream));
+    gfsb200_launch_vertex_values (&c->T, &tmp, c->n_sm, c->stream);
+    CK (cudaGetLastError ());
+    gfsb200_launch_interpolate (&c->T, &tmp, n, d[0], d[1], dim == 3 ? d[2] : NULL, o[0], o[1], dim == 3 ? o[2] : NULL, c->stream);
+    CK (cudaGetLastError ());
+    for (int a = 0; a < dim && k0 + a < nvar; a++)
+      CK (cudaMemcpyAsync (out[k0 + a], o[a], n*sizeof (double), cudaMemcpyDeviceToHost, c->stream));
+    CK (cudaStreamSynchronize (c->stream));
+  }
+  return GFSB200_OK;
 }
 
 /* ------------------------------------------------------------------ */
@@ -1393,12 +1431,37 @@ extern "C" int gfsb200_checkpoint_load (gfsb200_ctx * c, const char * path)
     for (int k = 0; k < 3; k++)
       CK (cudaMemcpyAsync (c->force[k], col[8 + k].data (), n*sizeof (double), cudaMemcpyHostToDevice, c->stream));
     CK (cudaStreamSynchronize (c->stream));
+    c->forces_recorded = true;           /* a later sort or cull must carry the restored forces along */
   }
   return GFSB200_OK;
 }
 
 /* ------------------------------------------------------------------ */
 /* two-way coupling                                                     */
+
+/* The target of a deposit pass: the selected buffer, zeroed as the caller's mode requires.
+ * Without a communicator: the components in `what' (bit 0 void fraction, bit 1 forces) are zeroed
+ * here -- gfs_cell_reset on the leaves.  With one, comm.cu owns the policy (which buffer, which
+ * slice is this rank's, what has to be waited for): gfsb200_comm_prepare_deposit. */
+static int deposit_target (gfsb200_ctx * c, int what, bool local_only, DevDeposit * D)
+{
+  memset (D, 0, sizeof *D);
+  const size_t n = c->T.n_cells;
+  if (c->comm) {
+    int r = gfsb200_comm_prepare_deposit (c->comm, what, local_only, D);
+    if (r) return r;
+  }
+  else {
+    if (what & 1) CK (cudaMemsetAsync (c->deposit, 0, n*sizeof (double), c->stream));
+    if (what & 2) CK (cudaMemsetAsync (c->deposit + n, 0, (size_t) c->T.dim*n*sizeof (double), c->stream));
+    D->local = c->deposit;
+    D->own_lo = 0; D->own_hi = (int32_t) n;
+    D->peers = NULL;
+    c->dep_result = c->dep_which;
+  }
+  D->n_cells = (int64_t) n;
+  return GFSB200_OK;
+}
 
 /* what: bit 0 = void fraction (component 0), bit 1 = force (components 1..dim) */
 static int deposit (gfsb200_ctx * c, const gfsb200_step_params * p, int what)
@@ -1416,13 +1479,11 @@ static int deposit (gfsb200_ctx * c, const gfsb200_step_params * p, int what)
     int r = prepare_inertial (c, &S);
     if (r) return r;
   }
-  const size_t n = c->T.n_cells;
-  /* gfs_cell_reset on the leaves, then scatter */
-  if (what & 1) CK (cudaMemsetAsync (c->deposit, 0, n*sizeof (double), c->stream));
-  if (what & 2) CK (cudaMemsetAsync (c->deposit + n, 0, (size_t) c->T.dim*n*sizeof (double), c->stream));
+  DevDeposit D;
+  int r = deposit_target (c, what, false, &D);
+  if (r) return r;
   DevParticles P = particles_view (c);
-  gfsb200_launch_deposit (&c->T, &c->F, &P, &S, what, c->deposit, c->deposit + n, c->deposit + 2*n,
-			  c->T.dim == 3 ? c->deposit + 3*n : NULL, c->stream);
+  gfsb200_launch_deposit (&c->T, &c->F, &P, &S, what, &D, 0, NULL, NULL, c->stream);
   CK (cudaGetLastError ());
   return GFSB200_OK;
 }
@@ -1468,10 +1529,13 @@ extern "C" int gfsb200_deposit_force_smoothed (gfsb200_ctx * c, const gfsb200_st
     c->knorm_n = c->n;
   }
   const size_t n = c->T.n_cells;
-  CK (cudaMemsetAsync (c->deposit + n, 0, (size_t) c->T.dim*n*sizeof (double), c->stream));
+  /* the kernel support of a particle reaches cells of any rank's slice: with a communicator this
+     deposit is local and the exchange must be the all-reduce (GFSB200_EXCHANGE_ALLREDUCE) */
+  DevDeposit D;
+  if ((r = deposit_target (c, 2, true, &D))) return r;
   DevParticles P = particles_view (c);
-  gfsb200_launch_deposit_smoothed (&c->T, &c->F, &P, &S, rkernel, kernel, c->deposit + n, c->deposit + 2*n,
-				   c->T.dim == 3 ? c->deposit + 3*n : NULL,
+  gfsb200_launch_deposit_smoothed (&c->T, &c->F, &P, &S, rkernel, kernel, D.local + n, D.local + 2*n,
+				   c->T.dim == 3 ? D.local + 3*n : NULL,
 				   kernel->record_norm ? c->knorm : NULL, c->stream);
   CK (cudaGetLastError ());
   c->forces_recorded = true;           /* the on-fluid forces (compute_forces_onfluid) are left in force[] */
@@ -1500,13 +1564,15 @@ extern "C" int gfsb200_deposit_select (gfsb200_ctx * c, int which)
     CK (cudaMemsetAsync (c->deposit_buf[which], 0, (size_t) c->deposit_count*sizeof (double), c->stream));
   }
   c->deposit = c->deposit_buf[which];
+  c->dep_which = which;
+  if (!c->comm) c->dep_result = which;
   return GFSB200_OK;
 }
 
 extern "C" int gfsb200_deposit_buffer (gfsb200_ctx * c, double ** dev, int64_t * count)
 {
   if (!c || !c->have_tree) return gfsb200_fail (GFSB200_ERR_STATE, "deposit_buffer: no tree resident");
-  if (dev) *dev = c->deposit;
+  if (dev) *dev = c->comm ? c->deposit_buf[c->dep_result] : c->deposit;
   if (count) *count = c->deposit_count;
   return GFSB200_OK;
 }
@@ -1517,8 +1583,16 @@ extern "C" int gfsb200_download_deposit (gfsb200_ctx * c, int comp, double * out
   if (comp < 0 || comp > c->T.dim || !out) return gfsb200_fail (GFSB200_ERR_ARG, "download_deposit: bad argument");
   CK (cudaSetDevice (c->device));
   const size_t n = c->T.n_cells;
-  CK (cudaMemcpyAsync (out, c->deposit + comp*n, n*sizeof (double), cudaMemcpyDeviceToHost, c->stream));
+  const double * src = c->deposit;
+  if (c->comm) {
+    /* the buffer whose exchange was issued last, once every rank's share has landed */
+    int r = gfsb200_deposit_wait (c->comm);
+    if (r) return r;
+    src = c->deposit_buf[c->dep_result];
+  }
+  CK (cudaMemcpyAsync (out, src + comp*n, n*sizeof (double), cudaMemcpyDeviceToHost, c->stream));
   CK (cudaStreamSynchronize (c->stream));
+  if (c->comm) return gfsb200_comm_check (c->comm);
   return GFSB200_OK;
 }
 

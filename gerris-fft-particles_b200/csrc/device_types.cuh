@@ -100,6 +100,26 @@ struct DevStep {
   unsigned char * keep;        /* [n] or NULL: cleared for a particle that was outside the domain BEFORE the step */
 };
 
+/* Two-way coupling over several GPUs.  After gfsb200_comm_rebalance rank r holds the particles of
+ * the cells [split[r], split[r + 1]) of the flat tree and OWNS that slice of the deposit buffer: a
+ * deposit into a cell is an fp64 reduction on the owner's copy -- a plain L2 atomic for the own
+ * slice, a remote one over NVLink peer memory for the few particles that have drifted into another
+ * rank's cells since the last rebalance.  n = 0: no ownership, every deposit is local. */
+#define GFSB200_MAX_RANKS 16
+struct DevOwners {
+  int n, self;
+  int32_t split[GFSB200_MAX_RANKS + 1];
+  double * base[GFSB200_MAX_RANKS];   /* [1 + dim][n_cells] deposit buffer of every rank (base[self]: local) */
+};
+
+/* where a two-way pass accumulates: component k of cell c lives at owner(c)'s base + k*n_cells + c */
+struct DevDeposit {
+  double * local;              /* this rank's buffer, [1 + dim][n_cells] */
+  int64_t n_cells;
+  int32_t own_lo, own_hi;      /* cells [own_lo, own_hi) are this rank's: plain local atomics */
+  const DevOwners * peers;     /* device memory; NULL: one rank, everything is local */
+};
+
 /* compact every third (second) bit of a Morton key back into an integer */
 __host__ __device__ inline unsigned gfsb200_compact3 (unsigned v)
 {

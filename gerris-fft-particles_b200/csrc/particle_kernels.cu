@@ -254,6 +254,22 @@ __device__ __forceinline__ double lerp (double a, double b, double t)
   return fma (t, b - a, a);
 }
 
+/* One 32-byte row (three fp64 values + padding) of the vertex / vorticity / acceleration tables.
+ * Default: a 128-bit and a 64-bit read-only load.  -DGFSB200_ROW256: ONE 256-bit load (LDG.E.256,
+ * sm_100): the row is one 32-byte sector, and the L1 data pipe is charged per sector and request
+ * -- two requests to the same sector cost twice (profiles/README.md, round 2). */
+__device__ __forceinline__ void load_row (const double * __restrict__ row, double & a, double & b, double & c)
+{
+#ifdef GFSB200_ROW256
+  double pad;
+  asm ("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(pad) : "l"(row));
+#else
+  const double2 * p = reinterpret_cast<const double2 *> (row);
+  const double2 ab = __ldg (p);
+  a = ab.x; b = ab.y; c = __ldg (reinterpret_cast<const double *> (p + 1));
+#endif
+}
+
 /* Per-leaf NODATA fallback of gfs_cell_corner_value (src/fluid.c:3094-3097) */
 __device__ __forceinline__ double resolve (double v, const double * __restrict__ F, int cell)
 {
@@ -303,9 +319,7 @@ __device__ __forceinline__ void interpolate (const DevTree & T, const DevField &
       double fu[4], fv[4], fw[4];
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-	const double2 * p = reinterpret_cast<const double2 *> (fld.vtx_val + (int64_t) id[q[k]]*4);
-	const double2 a = __ldg (p);
-	fu[k] = a.x; fv[k] = a.y; fw[k] = __ldg (reinterpret_cast<const double *> (p + 1));
+	load_row (fld.vtx_val + (int64_t) id[q[k]]*4, fu[k], fv[k], fw[k]);
       }
       if (any_nodata) {
 #pragma unroll
@@ -407,9 +421,7 @@ __device__ __forceinline__ void total_force (const DevTree & T, const DevField &
   if (PROG && any_lift) {
     const int64_t slot = leaf_slot<DIM, LATTICE> (T, L);
     if (DIM == 3) {
-      const double2 * p = reinterpret_cast<const double2 *> (fld.vort + slot*4);
-      const double2 a = __ldg (p);
-      wx = a.x; wy = a.y; wz = __ldg (reinterpret_cast<const double *> (p + 1));
+      load_row (fld.vort + slot*4, wx, wy, wz);
     }
     else
       wz = __ldg (fld.vort + slot);
@@ -467,9 +479,7 @@ __device__ __forceinline__ void total_force (const DevTree & T, const DevField &
       if (!(PROG && any_lift)) {
 	const int64_t slot = leaf_slot<DIM, LATTICE> (T, L);
 	if (DIM == 3) {
-	  const double2 * p = reinterpret_cast<const double2 *> (fld.vort + slot*4);
-	  const double2 a = __ldg (p);
-	  wx = a.x; wy = a.y; wz = __ldg (reinterpret_cast<const double *> (p + 1));
+	  load_row (fld.vort + slot*4, wx, wy, wz);
 	}
 	else
 	  wz = __ldg (fld.vort + slot);
@@ -498,9 +508,7 @@ __device__ __forceinline__ void total_force (const DevTree & T, const DevField &
 	const int64_t slot = leaf_slot<DIM, LATTICE> (T, L);
 	double ax, ay, az = 0.;
 	if (DIM == 3) {
-	  const double2 * p = reinterpret_cast<const double2 *> (fld.acc + slot*4);
-	  const double2 a = __ldg (p);
-	  ax = a.x; ay = a.y; az = __ldg (reinterpret_cast<const double *> (p + 1));
+	  load_row (fld.acc + slot*4, ax, ay, az);
 	}
 	else {
 	  const double2 a = __ldg (reinterpret_cast<const double2 *> (fld.acc) + slot);
@@ -528,6 +536,111 @@ __device__ __forceinline__ void total_force (const DevTree & T, const DevField &
     Fx += fx; Fy += fy;
     if (DIM == 3) Fz += fz;
   }
+}
+
+/* ------------------------------------------------------------------ */
+/* deposition: one reduction per run of equal cells inside a warp       */
+
+/* the buffer that owns `cell': this rank's for its own slice [own_lo, own_hi) (and always on one
+ * rank), else the owner's copy in peer memory (NVLink) -- rare: only particles that drifted out of
+ * the rank's cells since the last gfsb200_comm_rebalance */
+__device__ __forceinline__ double * owner_base (const DevDeposit & D, int cell)
+{
+  if (D.peers == NULL || (cell >= D.own_lo && cell < D.own_hi))
+    return D.local;
+  int r = 0;
+  const int n = D.peers->n;
+  for (int k = 1; k < n; k++)
+    r += cell >= D.peers->split[k];
+  return D.peers->base[r];
+}
+
+/* fp64 reduction on global memory without a return value (RED.E.ADD.F64): explicit state space, so
+ * that no generic-address dispatch is generated, and explicit scope */
+__device__ __forceinline__ void red_add (double * p, double v, bool sys)
+{
+  if (sys)
+    asm volatile ("red.relaxed.sys.global.add.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
+  else
+    asm volatile ("red.relaxed.gpu.global.add.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
+}
+
+/* Adds (av, ax, ay, az) to components (0, 1, 2, 3) of dst[cell] with ONE reduction per component
+ * and per run of consecutive lanes that share the same cell (particles are kept sorted by cell, so
+ * runs are long): the run structure (heads by shuffle + ballot) is found once, each value is summed
+ * along its run by a shuffle tree, and the run's head issues the fp64 reductions (RED.ADD.F64: no
+ * return value, so a remote owner costs no round trip).  Lanes with cell < 0 contribute nothing.
+ * Must be called by all 32 lanes. */
+template <int DIM, bool VOL, bool FORCE>
+__device__ __forceinline__ void run_deposit (const DevDeposit & D, int cell, double av, double ax,
+					     double ay, double az)
+{
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int prev = __shfl_up_sync (full, cell, 1);
+  const bool head = lane == 0 || prev != cell;
+  const unsigned heads = __ballot_sync (full, head);
+  /* my run spans [my_head, run_end) */
+  const unsigned above = lane == 31 ? 0u : heads & (0xffffffffu << (lane + 1));
+  const int run_end = above ? __ffs (above) - 1 : 32;
+  /* as many rounds as the longest run of the warp needs (C2: ~5 particles per leaf -> 3 or 4
+     rounds instead of 5; every round is 8 SHFL on the L1 data pipe, the busiest unit of this kernel) */
+  const int longest = __reduce_max_sync (full, head ? run_end - lane : 0);
+#pragma unroll 1
+  for (int o = 1; o < longest; o <<= 1) {
+    const bool in = lane + o < run_end;
+    if (VOL) { const double t = __shfl_down_sync (full, av, o); if (in) av += t; }
+    if (FORCE) {
+      const double tx = __shfl_down_sync (full, ax, o), ty = __shfl_down_sync (full, ay, o);
+      if (in) { ax += tx; ay += ty; }
+      if (DIM == 3) { const double tz = __shfl_down_sync (full, az, o); if (in) az += tz; }
+    }
+  }
+  if (head && cell >= 0) {
+    double * dst = owner_base (D, cell) + cell;
+    /* with several ranks every slice also receives reductions from its peers' SMs: system scope */
+    const bool sys = D.peers != NULL;
+    if (VOL) red_add (dst, av, sys);
+    if (FORCE) {
+      red_add (dst + D.n_cells, ax, sys);
+      red_add (dst + 2*D.n_cells, ay, sys);
+      if (DIM == 3) red_add (dst + 3*D.n_cells, az, sys);
+    }
+  }
+}
+
+/* what one particle adds to its cell in a two-way pass:
+ *   VOL    GfsParticulateField with voidfraction_from_particles,
+ *          modules/particulatecommon.c:1929-1957:  v[cell] += V_p / V_cell
+ *   FORCE  GfsSourceParticulate in the single-cell limit, :2158-2228: forces
+ *          recomputed without GfsForceBuoy (compute_forces_onfluid :753-765),
+ *          then u_c[cell] -= F_c / rho / V_cell
+ * Returns the flat cell index (-1: outside, nothing to add). */
+template <int DIM, bool LATTICE, unsigned PROG, bool VOL, bool FORCE>
+__device__ __forceinline__ int deposit_terms (const DevTree & T, const DevField & fld, const DevStep & S,
+					      double x, double y, double z, double vx, double vy, double vz,
+					      double & mass, double volume,
+					      double & av, double & ax, double & ay, double & az)
+{
+  av = ax = ay = az = 0.;
+  const Located L = locate<DIM, LATTICE> (T, x, y, z);
+  const int cell = cell_index<DIM, LATTICE> (T, L);
+  if (cell < 0)
+    return -1;
+  /* 1/ftt_cell_volume: the cell size is a power of two, its inverse an exponent flip */
+  const double inv_h = __longlong_as_double ((2045LL << 52) - __double_as_longlong (L.half));   /* 1/(2 half) */
+  const double inv_cellvol = DIM == 3 ? inv_h*inv_h*inv_h : inv_h*inv_h;
+  if (VOL)
+    av = volume*inv_cellvol;
+  if (FORCE) {
+    double Fx, Fy, Fz, rho;
+    total_force<DIM, true, LATTICE, PROG> (T, fld, S, L, x, y, z, vx, vy, vz, mass, volume, Fx, Fy, Fz, rho);
+    /* the single-cell limit of diffuse_force (:2158-2175): gfs_cell_volume, i.e. times the
+       fluid fraction in a mixed cell (the void fraction above uses ftt_cell_volume, :1931) */
+    const double k = -(T.solid_a ? inv_cellvol/T.solid_a[cell] : inv_cellvol)/rho;
+    ax = Fx*k; ay = Fy*k; az = Fz*k;
+  }
+  return cell;
 }
 
 /* ------------------------------------------------------------------ */
@@ -797,9 +910,15 @@ struct LateShared {
   }
 };
 
-template <int DIM, bool LATTICE, unsigned PROG, int STAGES, int MINB, int WPIPE_WARPS>
+/* REC: also store the accumulated force (GfsParticulate.force) -- three more column stores.
+ * DEP: the two-way deposits of the same step, fused: after the integration the particle is
+ * located again at its NEW position, the on-fluid force is evaluated there (new velocity, same
+ * field) and void fraction + force are reduced into the deposit buffer -- what
+ * gfsb200_deposit_all does right after the step, without streaming the particles a second time
+ * (136 instead of 112 + 88 algorithmic bytes per particle-step). */
+template <int DIM, bool LATTICE, unsigned PROG, int STAGES, int MINB, int WPIPE_WARPS, bool REC, bool DEP>
 __global__ void __launch_bounds__(32*WPIPE_WARPS, MINB)
-step_kernel_wpipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_tiles)
+step_kernel_wpipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_tiles, DevDeposit D)
 {
   constexpr int NC = DIM == 3 ? 8 : 6;
   constexpr unsigned COL_BYTES = 32*sizeof (double);
@@ -850,17 +969,24 @@ step_kernel_wpipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_til
     pipe::mbar_wait (&full[warp][s], parity);
     const double * b = &buf[warp][s][0][lane];
     const int64_t i = (int64_t) tile*32 + lane;
+    int dcell = -1;
+    double av = 0., ax = 0., ay = 0., az = 0.;
     if (i < P.n) {
       double x = b[0], y = b[32], z = DIM == 3 ? b[64] : 0.;
       const Located L = locate<DIM, LATTICE> (T, x, y, z);
+      if (REC && P.cell)
+	P.cell[i] = cell_index<DIM, LATTICE> (T, L);
       if (L.cell >= 0) {
 	double Fx, Fy, Fz, rho;
 	double vx = 0., vy = 0., vz = 0., mass = 0., volume = 0.;
 	double vkeep[3];
 	total_force<DIM, false, LATTICE, PROG, LateShared<DIM> > (T, fld, S, L, x, y, z, vx, vy, vz, mass, volume,
-									 Fx, Fy, Fz, rho, LateShared<DIM> { b, vkeep });
+								 Fx, Fy, Fz, rho, LateShared<DIM> { b, vkeep });
 	if (!PROG && S.mutates_mass)
 	  P.mass[i] = mass;
+	if (REC) {
+	  __stcs (P.fx + i, Fx); __stcs (P.fy + i, Fy); __stcs (P.fz + i, Fz);
+	}
 	/* the position comes back from the staged tile, the velocity from the late fetch */
 	x = pipe::lds_after (b, Fx); y = pipe::lds_after (b + 32, Fx);
 	if (DIM == 3) z = pipe::lds_after (b + 64, Fx);
@@ -878,12 +1004,22 @@ step_kernel_wpipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_til
 	if (DIM == 3) {
 	  __stcs (P.z + i, z); __stcs (P.vz + i, vz);
 	}
+	if (DEP) {
+	  /* volume is re-read from the staged tile (total_force took it by value) */
+	  const double vol2 = pipe::lds_after (b + 32*(2*DIM + 1), vx);
+	  dcell = deposit_terms<DIM, LATTICE, PROG, true, true> (T, fld, S, x, y, z, vx, vy, vz, mass, vol2,
+								 av, ax, ay, az);
+	  if (!PROG && S.mutates_mass && dcell >= 0)
+	    P.mass[i] = mass;
+	}
       }
       else if (S.track_escapes) {
 	atomicAdd (S.esc_count + 3, 1);       /* outside the domain before the step */
 	if (S.keep) S.keep[i] = 0;
       }
     }
+    if (DEP)
+      run_deposit<DIM, true, true> (D, dcell, av, ax, ay, az);
     /* every lane has read what it needs: hand the stage back to the copy engine */
     __syncwarp ();
     const int next = tile + STAGES*stride;
@@ -977,85 +1113,35 @@ __global__ void corner_values_kernel (DevTree T, DevField fld, int comp, int64_t
 }
 
 /* ------------------------------------------------------------------ */
-/* deposition: one atomic per run of equal cells inside a warp          */
-
-/* Adds val to dst[cell] with one atomic per run of consecutive lanes that
- * share the same cell (particles are kept sorted by cell, so runs are long).
- * Lanes with cell < 0 contribute nothing. */
-__device__ __forceinline__ void run_atomic_add (double * __restrict__ dst, int cell, double val)
-{
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  /* run head = lowest lane of my run */
-  const int prev = __shfl_up_sync (full, cell, 1);
-  const bool head = lane == 0 || prev != cell;
-  const unsigned heads = __ballot_sync (full, head);
-  /* my run spans [my_head, next_head) */
-  const unsigned below = heads & (0xffffffffu >> (31 - lane));
-  const int my_head = 31 - __clz (below);
-  const unsigned above = lane == 31 ? 0u : heads & (0xffffffffu << (lane + 1));
-  const int run_end = above ? __ffs (above) - 1 : 32;
-  /* tree-sum inside the run: lane accumulates lane + o while inside run */
-  double s = val;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const double t = __shfl_down_sync (full, s, o);
-    if (lane + o < run_end)
-      s += t;
-  }
-  if (lane == my_head && cell >= 0)
-    atomicAdd (dst + cell, s);
-}
-
-/* One pass for both deposits of a two-way step:
- *   VOL    GfsParticulateField with voidfraction_from_particles,
- *          modules/particulatecommon.c:1929-1957:  v[cell] += V_p / V_cell
- *   FORCE  GfsSourceParticulate in the single-cell limit, :2158-2228: forces
- *          recomputed without GfsForceBuoy (compute_forces_onfluid :753-765),
- *          then u_c[cell] -= F_c / rho / V_cell
- * One locate, one interpolation set, same compile-time force programs and
- * lattice addressing as the step kernel; one atomic per run of equal cells. */
-template <int DIM, bool LATTICE, unsigned PROG, bool VOL, bool FORCE>
+/* One pass for both deposits of a two-way step (see deposit_terms): one locate, one
+ * interpolation set, same compile-time force programs and lattice addressing as the step kernel;
+ * one reduction per run of equal cells.  INDEXED: the pass runs over a list of particle indices
+ * (the particles gfs_particle_bc has just wrapped, after a fused step + deposit) instead of the
+ * whole list; keep[i] == 0 marks a particle that was dropped. */
+template <int DIM, bool LATTICE, unsigned PROG, bool VOL, bool FORCE, bool INDEXED>
 __global__ void __launch_bounds__(256, 3)
-deposit_kernel (DevTree T, DevField fld, DevParticles P, DevStep S, double * __restrict__ vol,
-		double * __restrict__ f0, double * __restrict__ f1, double * __restrict__ f2)
+deposit_kernel (DevTree T, DevField fld, DevParticles P, DevStep S, DevDeposit D,
+		int n_idx, const int32_t * __restrict__ idx, const uint8_t * __restrict__ keep)
 {
-  const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
+  int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
+  bool live = INDEXED ? i < n_idx : i < P.n;
+  if (INDEXED && live) {
+    i = idx[i];
+    live = keep[i] != 0;
+  }
   int cell = -1;
   double av = 0., ax = 0., ay = 0., az = 0.;
-  if (i < P.n) {
+  if (live) {
     const double x = __ldcs (P.x + i), y = __ldcs (P.y + i), z = DIM == 3 ? __ldcs (P.z + i) : 0.;
-    const Located L = locate<DIM, LATTICE> (T, x, y, z);
-    cell = cell_index<DIM, LATTICE> (T, L);
-    if (cell >= 0) {
-      const double volume = __ldcs (P.volume + i);
-      const double h = 2.*L.half;
-      const double inv_cellvol = 1./(DIM == 3 ? h*h*h : h*h);      /* 1/ftt_cell_volume: power of two, exact */
-      if (VOL)
-	av = volume*inv_cellvol;
-      if (FORCE) {
-	double Fx, Fy, Fz, rho;
-	double mass = __ldcs (P.mass + i);
-	total_force<DIM, true, LATTICE, PROG> (T, fld, S, L, x, y, z, __ldcs (P.vx + i), __ldcs (P.vy + i),
-					      DIM == 3 ? __ldcs (P.vz + i) : 0., mass, volume,
-					      Fx, Fy, Fz, rho);
-	if (!PROG && S.mutates_mass)       /* compute_forces_onfluid runs GfsForceAddedMass too */
-	  P.mass[i] = mass;
-	/* the single-cell limit of diffuse_force (:2158-2175): gfs_cell_volume, i.e. times the
-	   fluid fraction in a mixed cell (the void fraction above uses ftt_cell_volume, :1931) */
-	const double k = -(T.solid_a ? inv_cellvol/T.solid_a[cell] : inv_cellvol)/rho;
-	ax = Fx*k; ay = Fy*k; az = Fz*k;
-      }
-    }
+    double mass = FORCE ? __ldcs (P.mass + i) : 0.;
+    cell = deposit_terms<DIM, LATTICE, PROG, VOL, FORCE> (T, fld, S, x, y, z,
+							 FORCE ? __ldcs (P.vx + i) : 0., FORCE ? __ldcs (P.vy + i) : 0.,
+							 FORCE && DIM == 3 ? __ldcs (P.vz + i) : 0.,
+							 mass, __ldcs (P.volume + i), av, ax, ay, az);
+    if (FORCE && !PROG && S.mutates_mass && cell >= 0)       /* compute_forces_onfluid runs GfsForceAddedMass too */
+      P.mass[i] = mass;
   }
-  if (VOL)
-    run_atomic_add (vol, cell, av);
-  if (FORCE) {
-    run_atomic_add (f0, cell, ax);
-    run_atomic_add (f1, cell, ay);
-    if (DIM == 3)
-      run_atomic_add (f2, cell, az);
-  }
+  run_deposit<DIM, VOL, FORCE> (D, cell, av, ax, ay, az);
 }
 
 /* ------------------------------------------------------------------ */
@@ -1416,21 +1502,24 @@ static void launch_pipe (const DevTree * T, const DevField * F, const DevParticl
   step_kernel_pipe<DIM, LA, PR, ST, MB, TILE><<<grid, TILE, smem, st>>> (*T, *F, *P, *S, n_tiles);
 }
 
-template <int DIM, bool LA, unsigned PR, int ST, int MB, int WPIPE_WARPS>
+template <int DIM, bool LA, unsigned PR, int ST, int MB, int WPIPE_WARPS, bool REC, bool DEP>
 static void launch_wpipe (const DevTree * T, const DevField * F, const DevParticles * P,
-			  const DevStep * S, int n_sm, cudaStream_t st)
+			  const DevStep * S, int n_sm, cudaStream_t st, const DevDeposit * D)
 {
   const int n_tiles = (int) ((P->n + 31)/32);
   const size_t smem = (size_t) WPIPE_WARPS*ST*(DIM == 3 ? 8 : 6)*32*sizeof (double);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute (step_kernel_wpipe<DIM, LA, PR, ST, MB, WPIPE_WARPS>,
+    cudaFuncSetAttribute (step_kernel_wpipe<DIM, LA, PR, ST, MB, WPIPE_WARPS, REC, DEP>,
 			  cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     configured = true;
   }
   int grid = n_sm*MB;
   if (grid*WPIPE_WARPS > n_tiles) grid = (n_tiles + WPIPE_WARPS - 1)/WPIPE_WARPS;
-  step_kernel_wpipe<DIM, LA, PR, ST, MB, WPIPE_WARPS><<<grid, 32*WPIPE_WARPS, smem, st>>> (*T, *F, *P, *S, n_tiles);
+  DevDeposit none;
+  memset (&none, 0, sizeof none);
+  step_kernel_wpipe<DIM, LA, PR, ST, MB, WPIPE_WARPS, REC, DEP><<<grid, 32*WPIPE_WARPS, smem, st>>>
+    (*T, *F, *P, *S, n_tiles, DEP ? *D : none);
 }
 
 extern "C" {
@@ -1438,12 +1527,16 @@ extern "C" {
 /* mode: 0 plain kernel; 2: TMA-staged persistent kernel, 3 CTAs x 256 threads per SM;
  * 3: the same with 6 CTAs x 128 threads -- shorter waits at the per-tile barrier
  * (64-thread tiles and a third stage measured within 1.5 % of it); 7, 9: the warp-pipelined
- * kernel (step_kernel_wpipe); < 0 (default): chosen by tree type */
-void gfsb200_launch_step (const DevTree * T, const DevField * F, const DevParticles * P,
-			  const DevStep * S, int rec, int minb, int mode, int n_sm, cudaStream_t st)
+ * kernel (step_kernel_wpipe); < 0 (default): chosen by tree type.
+ * rec: also record cell and force per particle.  D != NULL: the caller wants the two-way deposits
+ * of this step fused into the kernel; returns 1 if the launched kernel did that (the warp-pipelined
+ * kernel with a compile-time force list), 0 if the caller has to run the deposit pass itself. */
+int gfsb200_launch_step (const DevTree * T, const DevField * F, const DevParticles * P,
+			 const DevStep * S, int rec, int minb, int mode, int n_sm, cudaStream_t st,
+			 const DevDeposit * D)
 {
   gfsb200_launch_counter += 1;
-  if (P->n <= 0) return;
+  if (P->n <= 0) return 0;
   const int th = 256;
   const unsigned g = grid_for (P->n, th);
   const bool lat = T->lattice_n1 > 0;
@@ -1453,27 +1546,37 @@ void gfsb200_launch_step (const DevTree * T, const DevField * F, const DevPartic
   case 0x1: case 0x21: case 0x321: case 0x31: case 0x3:
     prog = S->forces;
   }
-  if (rec || (S->cd_const == S->cd_const)) prog = 0;
+  if (S->cd_const == S->cd_const) prog = 0;
   /* default (mode < 0): the warp-pipelined kernel for the compile-time force lists (C2: 0.249 vs
      0.285 ms, C3: 0.266 vs 0.280 ms -- profiles/README.md, round 1e); runtime force lists spill
      at its 72 registers and keep the CTA-pipelined one */
   if (mode < 0)
     mode = prog != 0 ? 9 : 3;
-  if (!rec && mode >= 4 && P->n >= 1024) {
+  if (mode >= 4 && P->n >= 1024 && (prog != 0 || !rec)) {
     /* warp-private pipeline, 2 stages, 4 warps per CTA; 9: 7 CTAs/SM (72 registers, 28 warps);
-       7: 6 CTAs/SM (80 registers) */
-#define WP_ST(D, LA, PR) do { if (mode == 7) launch_wpipe<D, LA, PR, 2, 6, 4> (T, F, P, S, n_sm, st); \
-			      else launch_wpipe<D, LA, PR, 2, 7, 4> (T, F, P, S, n_sm, st); } while (0)
-#define WP_PR(D, LA) do { switch (prog) { \
-    case 0x1: WP_ST (D, LA, 0x1); break; case 0x21: WP_ST (D, LA, 0x21); break; \
-    case 0x321: WP_ST (D, LA, 0x321); break; case 0x31: WP_ST (D, LA, 0x31); break; \
-    case 0x3: WP_ST (D, LA, 0x3); break; default: WP_ST (D, LA, 0); } } while (0)
+       7: 6 CTAs/SM (80 registers).  The force-recording and the deposit-fusing flavours exist for
+       the compile-time force lists at 7 CTAs/SM only. */
+    const bool fuse = D != NULL && !rec && prog != 0 && mode != 7;
+#define WP_ST(D_, LA, PR) do { \
+      if (rec) launch_wpipe<D_, LA, PR, 2, 7, 4, true, false> (T, F, P, S, n_sm, st, NULL); \
+      else if (fuse) launch_wpipe<D_, LA, PR, 2, 7, 4, false, true> (T, F, P, S, n_sm, st, D); \
+      else if (mode == 7) launch_wpipe<D_, LA, PR, 2, 6, 4, false, false> (T, F, P, S, n_sm, st, NULL); \
+      else launch_wpipe<D_, LA, PR, 2, 7, 4, false, false> (T, F, P, S, n_sm, st, NULL); } while (0)
+#define WP_ST0(D_, LA) do { \
+      if (mode == 7) launch_wpipe<D_, LA, 0, 2, 6, 4, false, false> (T, F, P, S, n_sm, st, NULL); \
+      else launch_wpipe<D_, LA, 0, 2, 7, 4, false, false> (T, F, P, S, n_sm, st, NULL); } while (0)
+#define WP_PR(D_, LA) do { switch (prog) { \
+    case 0x1: WP_ST (D_, LA, 0x1); break; case 0x21: WP_ST (D_, LA, 0x21); break; \
+    case 0x321: WP_ST (D_, LA, 0x321); break; case 0x31: WP_ST (D_, LA, 0x31); break; \
+    case 0x3: WP_ST (D_, LA, 0x3); break; default: WP_ST0 (D_, LA); } } while (0)
     if (T->dim == 3) { if (lat) WP_PR (3, true); else WP_PR (3, false); }
     else             { if (lat) WP_PR (2, true); else WP_PR (2, false); }
 #undef WP_PR
+#undef WP_ST0
 #undef WP_ST
-    return;
+    return fuse ? 1 : 0;
   }
+  if (rec) prog = 0;
   if (!rec && mode >= 2 && P->n >= 1024) {
 #define PIPE_ST(D, LA, PR) do { if (mode == 3) launch_pipe<D, LA, PR, 2, 6, 128> (T, F, P, S, n_sm, st); \
 				else launch_pipe<D, LA, PR, 2, 3, 256> (T, F, P, S, n_sm, st); } while (0)
@@ -1485,7 +1588,7 @@ void gfsb200_launch_step (const DevTree * T, const DevField * F, const DevPartic
     else             { if (lat) PIPE_PR (2, true); else PIPE_PR (2, false); }
 #undef PIPE_PR
 #undef PIPE_ST
-    return;
+    return 0;
   }
 #define LAUNCH(D, R, LA, PR, MB) step_kernel<D, R, LA, PR, MB><<<g, th, 0, st>>> (*T, *F, *P, *S)
 #define PICK_MB(D, LA, PR) do { if (minb <= 3) LAUNCH (D, false, LA, PR, 3); else LAUNCH (D, false, LA, PR, 4); } while (0)
@@ -1500,6 +1603,7 @@ void gfsb200_launch_step (const DevTree * T, const DevField * F, const DevPartic
 #undef PICK_PR
 #undef PICK_MB
 #undef LAUNCH
+  return 0;
 }
 
 void gfsb200_launch_advect (const DevTree * T, const DevField * F, const DevParticles * P,
@@ -1552,14 +1656,16 @@ void gfsb200_launch_corner_values (const DevTree * T, const DevField * F, int co
     corner_values_kernel<2><<<grid_for (n*nc, 256), 256, 0, st>>> (*T, *F, comp, n, cells, out);
 }
 
-/* what: bit 0 = void fraction, bit 1 = force components */
+/* what: bit 0 = void fraction, bit 1 = force components.  idx != NULL: only the n_idx particles
+ * idx[k] with keep[idx[k]] != 0 */
 void gfsb200_launch_deposit (const DevTree * T, const DevField * F, const DevParticles * P,
-			     const DevStep * S, int what, double * vol, double * f0, double * f1,
-			     double * f2, cudaStream_t st)
+			     const DevStep * S, int what, const DevDeposit * D, int n_idx,
+			     const int32_t * idx, const uint8_t * keep, cudaStream_t st)
 {
   gfsb200_launch_counter += 1;
-  if (P->n <= 0 || !(what & 3)) return;
-  const unsigned g = grid_for (P->n, 256);
+  const int64_t n = idx ? n_idx : P->n;
+  if (n <= 0 || !(what & 3)) return;
+  const unsigned g = grid_for (n, 256);
   const bool lat = T->lattice_n1 > 0;
   unsigned prog = 0;
   if (what & 2)
@@ -1568,13 +1674,25 @@ void gfsb200_launch_deposit (const DevTree * T, const DevField * F, const DevPar
       prog = S->forces;
     }
   if (S->cd_const == S->cd_const) prog = 0;
-#define DEP(D, LA, PR, V, FO) deposit_kernel<D, LA, PR, V, FO><<<g, 256, 0, st>>> (*T, *F, *P, *S, vol, f0, f1, f2)
-#define DEP_W(D, LA, PR) do { if (what == 1) DEP (D, LA, 0, true, false); else if (what == 2) DEP (D, LA, PR, false, true); \
-			      else DEP (D, LA, PR, true, true); } while (0)
-#define DEP_PR(D, LA) do { switch (prog) { \
-    case 0x1: DEP_W (D, LA, 0x1); break; case 0x21: DEP_W (D, LA, 0x21); break; \
-    case 0x321: DEP_W (D, LA, 0x321); break; case 0x31: DEP_W (D, LA, 0x31); break; \
-    case 0x3: DEP_W (D, LA, 0x3); break; default: DEP_W (D, LA, 0); } } while (0)
+  if (idx) {
+    /* the rare fix-up pass after a fused step + deposit: runtime force list, both deposits */
+    if (T->dim == 3) {
+      if (lat) deposit_kernel<3, true, 0, true, true, true><<<g, 256, 0, st>>> (*T, *F, *P, *S, *D, n_idx, idx, keep);
+      else deposit_kernel<3, false, 0, true, true, true><<<g, 256, 0, st>>> (*T, *F, *P, *S, *D, n_idx, idx, keep);
+    }
+    else {
+      if (lat) deposit_kernel<2, true, 0, true, true, true><<<g, 256, 0, st>>> (*T, *F, *P, *S, *D, n_idx, idx, keep);
+      else deposit_kernel<2, false, 0, true, true, true><<<g, 256, 0, st>>> (*T, *F, *P, *S, *D, n_idx, idx, keep);
+    }
+    return;
+  }
+#define DEP(D_, LA, PR, V, FO) deposit_kernel<D_, LA, PR, V, FO, false><<<g, 256, 0, st>>> (*T, *F, *P, *S, *D, 0, NULL, NULL)
+#define DEP_W(D_, LA, PR) do { if (what == 1) DEP (D_, LA, 0, true, false); else if (what == 2) DEP (D_, LA, PR, false, true); \
+			      else DEP (D_, LA, PR, true, true); } while (0)
+#define DEP_PR(D_, LA) do { switch (prog) { \
+    case 0x1: DEP_W (D_, LA, 0x1); break; case 0x21: DEP_W (D_, LA, 0x21); break; \
+    case 0x321: DEP_W (D_, LA, 0x321); break; case 0x31: DEP_W (D_, LA, 0x31); break; \
+    case 0x3: DEP_W (D_, LA, 0x3); break; default: DEP_W (D_, LA, 0); } } while (0)
   if (T->dim == 3) { if (lat) DEP_PR (3, true); else DEP_PR (3, false); }
   else             { if (lat) DEP_PR (2, true); else DEP_PR (2, false); }
 #undef DEP_PR
@@ -1670,6 +1788,25 @@ void gfsb200_launch_inside_flags (int64_t n, const int32_t * cell, uint8_t * fla
 {
   gfsb200_launch_counter += 1;
   if (n > 0) inside_flag_kernel<<<grid_for (n, 256), 256, 0, st>>> (n, cell, flag);
+}
+
+/* keep[i] = 0 for every particle that is still flagged but lies outside the domain (cell < 0);
+ * *count is incremented once per particle cleared */
+__global__ void __launch_bounds__(256)
+outside_clear_kernel (int64_t n, const int32_t * __restrict__ cell, uint8_t * __restrict__ keep,
+		      int * __restrict__ count)
+{
+  const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n && cell[i] < 0 && keep[i]) {
+    keep[i] = 0;
+    atomicAdd (count, 1);
+  }
+}
+
+void gfsb200_launch_outside_clear (int64_t n, const int32_t * cell, uint8_t * keep, int * count, cudaStream_t st)
+{
+  gfsb200_launch_counter += 1;
+  if (n > 0) outside_clear_kernel<<<grid_for (n, 256), 256, 0, st>>> (n, cell, keep, count);
 }
 
 /* cub wrappers: pass tmp = NULL to query *tmp_bytes */

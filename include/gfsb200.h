@@ -241,6 +241,11 @@ typedef struct {
   double cm_const;                 /* constant GfsForceAddedMass coefficient function; NaN = 0.5 */
   int32_t track_escapes;           /* 1: remember which particles left the domain (with their
 				      previous position) for gfsb200_particle_bc */
+  int32_t fuse_deposit;            /* 1: the two-way deposits of the step in the same pass: after the
+				      integration each particle adds V_p/V_cell and its on-fluid force at
+				      its NEW state to the deposit buffer -- the result of calling
+				      gfsb200_deposit_all right after the step (the buffer is zeroed first),
+				      without streaming the particles twice */
 } gfsb200_step_params;
 
 void gfsb200_step_params_default (gfsb200_step_params * p);
@@ -389,6 +394,74 @@ int gfsb200_deposit_select (gfsb200_ctx * c, int which);
  * all-reduce (NCCL) issued by the caller on gfsb200_ctx_stream() */
 int gfsb200_deposit_buffer (gfsb200_ctx * c, double ** dev, int64_t * count);
 int gfsb200_download_deposit (gfsb200_ctx * c, int comp, double * out /* [n_cells] */);
+
+/* ---- multi-GPU --------------------------------------------------------- */
+/* Particles shard over the GPUs of one box; the flat tree and the field are replicated.  One
+ * communicator per context (= per GPU); a process may hold one rank (MPI / torchrun: one process per
+ * GPU) or all of them (a serial gerris3D driving every GPU of the box).  Every collective below takes
+ * the array of the CALLING PROCESS's communicators and must be called by every process of the job.
+ *
+ * Replaces, for a replicated field: the per-particle migration of gfs_particle_bc in a parallel
+ * run (mpi_send_particle / mpi_rcv_particle, modules/particulatecommon.c:3218-3244, over
+ * gfs_send_objects / gfs_receive_objects, src/domain.c:4464-4557) by gfsb200_comm_rebalance, and the
+ * scalar reductions of src/utils.h:36-42 (gfs_all_reduce) by a reduction of the whole deposited
+ * field.  NCCL is loaded at run time (libnccl.so.2) by the first call below: a single-GPU user never
+ * needs it. */
+typedef struct gfsb200_comm gfsb200_comm;
+#define GFSB200_UNIQUE_ID_BYTES 128
+/* rank 0 creates the id (ncclGetUniqueId); the host code hands it to every rank (MPI_Bcast, a file) */
+int gfsb200_comm_unique_id (void * id /* GFSB200_UNIQUE_ID_BYTES */);
+/* one process per GPU */
+int gfsb200_comm_init_rank (gfsb200_ctx * c, const void * id, int rank, int nranks, gfsb200_comm ** out);
+/* one process, n GPUs: rank r is ctxs[r] */
+int gfsb200_comm_init_all (int n, gfsb200_ctx * const * ctxs, gfsb200_comm ** out /* [n] */);
+void gfsb200_comm_destroy (gfsb200_comm * m);
+int gfsb200_comm_rank (const gfsb200_comm * m);
+int gfsb200_comm_size (const gfsb200_comm * m);
+/* 1 when every rank reaches every other rank's memory over NVLink peer access (same box) */
+int gfsb200_comm_peer_access (const gfsb200_comm * m);
+
+/* U,V,W (+alpha, mu) of rank `root' -- host arrays as for gfsb200_upload_field, read on the root's
+ * process only -- go up over PCIe ONCE and reach the other GPUs over NVLink (ncclBroadcast); every
+ * rank then rebuilds its vertex and vorticity tables. */
+int gfsb200_broadcast_field (gfsb200_comm * const * local, int n_local, int root,
+			     const double * u, const double * v, const double * w,
+			     const double * alpha, const double * mu);
+
+/* Global cell order: the resident particles of all ranks are redistributed (NCCL send/recv over
+ * NVLink) so that rank r holds, sorted by cell, the particles of the flat-tree cells
+ * [split[r], split[r + 1]) -- contiguous slices of the globally Morton-sorted cloud with equal
+ * particle counts up to one cell's population.  From then on a rank's deposits fall into its own
+ * slice of the field (except for the particles that drift across a slice boundary before the next
+ * rebalance), and gfsb200_deposit_allreduce shrinks from a reduction of the whole field to an
+ * all-gather of the slices.  Particle ids travel with the particles; recorded forces do not.
+ * Call it where a single GPU would call gfsb200_particles_sort. */
+int gfsb200_comm_rebalance (gfsb200_comm * const * local, int n_local);
+/* the slice boundaries of the last rebalance: split[0 .. size]; GFSB200_ERR_STATE before it */
+int gfsb200_comm_split (const gfsb200_comm * m, int32_t * split);
+/* host-only helper (exposed for tests): slice boundaries from the global per-cell particle counts */
+int gfsb200_comm_splitters (const uint32_t * count, int32_t n_cells, int nranks, int32_t * split);
+
+/* Sums the deposited field over the ranks: afterwards every rank holds sum_r deposit_r in the
+ * buffer gfsb200_download_deposit reads.  Asynchronous: the exchange runs on a communication stream
+ * behind the deposit; the next step may be issued at once (the library alternates the two deposit
+ * buffers) and gfsb200_download_deposit / gfsb200_deposit_wait order themselves after it.
+ *   - after gfsb200_comm_rebalance, on a box with peer access: the deposit kernels have already
+ *     reduced every contribution into its OWNER's slice (remote fp64 reductions through NVLink peer
+ *     memory for the drifters), so this is one cross-GPU barrier, the push of the own slice to every
+ *     peer (copy engines) and a completion flag -- (R-1)/R of the field per GPU instead of 2(R-1)/R;
+ *   - otherwise: ncclAllReduce of the whole buffer.
+ * With a communicator attached each deposit call must be followed by one allreduce before the next
+ * deposit of the same component. */
+int gfsb200_deposit_allreduce (gfsb200_comm * const * local, int n_local);
+/* orders the context's stream after the last exchange (own pushes AND the peers' pushes) */
+int gfsb200_deposit_wait (gfsb200_comm * m);
+#define GFSB200_EXCHANGE_AUTO 0       /* owner slices + all-gather when possible */
+#define GFSB200_EXCHANGE_ALLREDUCE 1  /* always ncclAllReduce the whole buffer (required for the smoothed deposit) */
+int gfsb200_comm_set_exchange (gfsb200_comm * m, int mode);
+/* device time (ms, CUDA events on the communication stream) of the exchanges since the last call,
+ * averaged, and the bytes one exchange sends from this rank */
+int gfsb200_comm_exchange_stats (gfsb200_comm * m, double * ms, int64_t * n, int64_t * bytes_sent);
 
 /* ---- timing ------------------------------------------------------------ */
 /* average device time (ms) of the fused step kernel over the launches since
