@@ -99,6 +99,7 @@ def lib() -> C.CDLL:
         "gfsb200_tree_build_stencils": (i32, [vp]),
         "gfsb200_tree_get_view": (i32, [vp, C.POINTER(TreeView)]),
         "gfsb200_tree_corner_interpolator": (i32, [vp, i32, i32, vp, vp]),
+        "gfsb200_device_count": (i32, []),
         "gfsb200_ctx_create": (i32, [i32, C.POINTER(vp)]),
         "gfsb200_ctx_destroy": (None, [vp]),
         "gfsb200_ctx_stream": (vp, [vp]),
@@ -106,6 +107,7 @@ def lib() -> C.CDLL:
         "gfsb200_upload_tree": (i32, [vp, vp]),
         "gfsb200_upload_field": (i32, [vp, vp, vp, vp, vp, vp]),
         "gfsb200_set_field_device": (i32, [vp, vp, vp, vp, vp, vp]),
+        "gfsb200_upload_field_part": (i32, [vp, i64, i64, vp, vp, vp, vp, vp]),
         "gfsb200_refresh_field": (i32, [vp]),
         "gfsb200_upload_field_prev": (i32, [vp, vp, vp, vp]),
         "gfsb200_download_corner_values": (i32, [vp, i32, i64, vp, vp]),
@@ -393,6 +395,13 @@ class Context:
             if a is not None and a.shape != (self.n_cells,):
                 raise GfsB200Error(f"field array of shape {a.shape}, expected ({self.n_cells},)")
         _check(self._lib.gfsb200_upload_field(self.handle, *[_ptr(a) for a in arrs]), "upload_field")
+
+    def upload_field_part(self, first: int, n: int, u, v, w=None, alpha=None, mu=None):
+        """copies cells [first, first + n) of the given (full-length, contiguous float64) arrays;
+        finish with refresh_field()"""
+        arrs = [u, v, w, alpha, mu]
+        _check(self._lib.gfsb200_upload_field_part(self.handle, first, n, *[_ptr(a) for a in arrs]),
+               "upload_field_part")
 
     def set_field_device(self, u: int, v: int, w: int = 0, alpha: int = 0, mu: int = 0):
         _check(self._lib.gfsb200_set_field_device(self.handle, u, v, w or None, alpha or None, mu or None),
@@ -720,6 +729,8 @@ def bridge(dim: int) -> C.CDLL:
         "gfsb200_ftt_map_cells": (C.POINTER(vp), [vp]),
         "gfsb200_ftt_gather": (i32, [vp, C.c_size_t, i32, C.c_double, vp]),
         "gfsb200_ftt_scatter": (i32, [vp, C.c_size_t, i32, i32, vp]),
+        "gfsb200_ftt_map_cache_data": (i32, [vp, C.c_uint]),
+        "gfsb200_ftt_gather_range": (i32, [vp, C.c_size_t, C.c_int32, C.c_int32, i32, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(B, name)
@@ -746,6 +757,10 @@ class FttMap:
                 self.handle = None
         except Exception:
             pass
+
+    def cache_data(self, generation: int = 0):
+        """record the data-block address of every cell: later gathers stream through it"""
+        _check(bridge(self.dim).gfsb200_ftt_map_cache_data(self.handle, generation), "ftt_map_cache_data")
 
     def gather(self, offset: int, var: int) -> np.ndarray:
         out = np.empty(len(self.cells))

@@ -148,6 +148,16 @@ static void free_particles (gfsb200_ctx * c)
   c->esc_count = NULL; c->esc_idx = NULL; c->esc_old = NULL; c->esc_cap = 0; c->esc_armed = false;
 }
 
+extern "C" int gfsb200_device_count (void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount (&n) != cudaSuccess) {
+    cudaGetLastError ();
+    return 0;
+  }
+  return n;
+}
+
 extern "C" int gfsb200_ctx_create (int device, gfsb200_ctx ** out)
 {
   if (!out)
@@ -262,6 +272,7 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
   const int nc = t->nchild;
   std::vector<int32_t> child0 (n);
   std::vector<uint8_t> info (n);
+  bool any_destroyed = false;
   for (int32_t i = 0; i < n; i++) {
     child0[i] = (t->flags[i] & GFSB200_CELL_DESTROYED) ? CHILD_DESTROYED :
       (t->child0[i] < 0 ? CHILD_LEAF : t->child0[i]);
@@ -277,6 +288,8 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
 	regular = 0;
     }
     info[i] = (uint8_t) ((t->flags[i] & 7) | regular | (k << 4));
+    if ((t->flags[i] & GFSB200_CELL_DESTROYED) && !(t->flags[i] & GFSB200_CELL_BOUNDARY))
+      any_destroyed = true;
   }
   std::vector<double> wuni (t->n_vertices ? t->n_vertices : 1);
   for (int32_t v = 0; v < t->n_vertices; v++) {
@@ -321,6 +334,7 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
   for (int a = 0; a < 3; a++) { T.la_min[a] = t->la_min[a]; T.la_n[a] = t->la_n[a]; }
   T.la_h = t->la_h;
   T.single_box = t->la_size == 1 && t->la_slot[0] == 0;
+  T.has_destroyed = any_destroyed;
   T.la_slot = c->d_la_slot;
   T.child0 = c->d_child0; T.neighbor = c->d_neighbor; T.level = c->d_level; T.info = c->d_info;
   T.n_vertices = t->n_vertices;
@@ -336,7 +350,7 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
   /* (a one-slot locate array means one GfsBox and no GfsBoundary root: hull cells have NULL
      neighbours, so "all neighbours are same-level leaves" == interior on such a tree) */
   if (t->lattice_level >= 0 && t->lattice_level - t->root_level == T.top_levels && T.single_box &&
-      t->n_roots == 1 && !getenv ("GFSB200_NO_LATTICE"))
+      t->n_roots == 1 && !any_destroyed && !getenv ("GFSB200_NO_LATTICE"))
     T.lattice_n1 = (1 << T.top_levels) + 1;
   /* Interior vertices of a lattice tree: check once, on the host, that every one of them
      carries the same stencil shape (the 2^dim leaves around it, equal weights, one common
@@ -511,6 +525,29 @@ extern "C" int gfsb200_upload_field (gfsb200_ctx * c, const double * u, const do
     if (present[i])
       CK (cudaMemcpyAsync (c->d_field[i], src[i], bytes, cudaMemcpyHostToDevice, c->stream));
   return gfsb200_refresh_field (c);
+}
+
+extern "C" int gfsb200_upload_field_part (gfsb200_ctx * c, int64_t first, int64_t n,
+					  const double * u, const double * v, const double * w,
+					  const double * alpha, const double * mu)
+{
+  if (!c || !c->have_tree) return gfsb200_fail (GFSB200_ERR_STATE, "upload_field_part: upload a tree first");
+  if (!u || !v || (c->T.dim == 3 && !w))
+    return gfsb200_fail (GFSB200_ERR_ARG, "upload_field_part: missing velocity component");
+  if (first < 0 || n < 0 || first + n > c->T.n_cells)
+    return gfsb200_fail (GFSB200_ERR_ARG, "upload_field_part: cells [%lld, %lld) out of range",
+			 (long long) first, (long long) (first + n));
+  CK (cudaSetDevice (c->device));
+  const double * src[5] = { u, v, c->T.dim == 3 ? w : NULL, alpha, mu };
+  const int present[5] = { 1, 1, c->T.dim == 3, alpha != NULL, mu != NULL };
+  int r = gfsb200_internal_field_buffers (c, present);
+  if (r) return r;
+  c->have_field = false;                 /* until gfsb200_refresh_field has rebuilt the tables */
+  for (int i = 0; i < 5; i++)
+    if (present[i] && n)
+      CK (cudaMemcpyAsync (c->d_field[i] + first, src[i] + first, (size_t) n*sizeof (double),
+			   cudaMemcpyHostToDevice, c->stream));
+  return GFSB200_OK;
 }
 
 extern "C" int gfsb200_set_field_device (gfsb200_ctx * c, const double * u, const double * v,

@@ -27,14 +27,16 @@
  * it and a process that already carries an NCCL (torch) shares that copy.
  *
  * Ordering of the owner-slice protocol (two deposit buffers, step n uses buffer n % 2):
- *   Z(n+1)  zero the OWN slice of the other buffer       } on the context's stream, in this order,
- *   D(n)    deposit: local + remote reductions into n%2  } issued by the deposit call of step n
+ *   D(n)    deposit: local + remote reductions into n%2  } on the context's stream, in this order;
+ *   Z(n+1)  zero the OWN slice of the other buffer       } Z is issued by gfsb200_deposit_allreduce
  *   X(n)    on the communication stream, after D(n): barrier B(n) -- every rank has finished D(n),
  *           so every remote reduction into my slice has landed (kernel completion drains them) --
  *           then the pushes of my slice, then the DONE flags.
- * A peer's D(n+1) reduces into my slice of buffer (n+1)%2 only after it has passed B(n), which
- * waits for my D(n), which follows my Z(n+1): the slice is zero before anything lands in it.  My
- * Z(n+2) (issued with D(n+1)) waits for my X(n): the slice is not cleared while it is being pushed.
+ * The context's stream orders D(n+1) after B(n) (an event recorded right behind the barrier kernel:
+ * the pushes are not waited for).  So a peer's D(n+1) reduces into my slice of buffer (n+1)%2 only
+ * after it has passed B(n), which waits for my arrival, which follows my Z(n+1): the slice is zero
+ * before anything lands in it.  My Z(n+2) waits for my X(n): the slice is not cleared while it is
+ * being pushed.
  */
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -99,7 +101,7 @@ Nccl * nccl_api ()
 /* ------------------------------------------------------------------ */
 /* flags in peer memory                                                 */
 
-enum { FLAG_ARRIVE = 0, FLAG_DONE = 1, FLAG_ERR = 2, FLAG_ROWS = 3 };
+enum { FLAG_ARRIVE = 0, FLAG_DONE = 1, FLAG_ERR = 2, FLAG_SRC = 3, FLAG_ROWS = 4 };
 #define FLAGS_BYTES (2u << 20)       /* its own allocation block (cudaIpc maps whole blocks) */
 #define SPIN_TIMEOUT_NS 20000000000ull
 
@@ -131,6 +133,8 @@ __global__ void comm_flags_kernel (PeerFlags peers, uint32_t * mine, int self, i
 {
   const int t = threadIdx.x;
   if (t >= n) return;
+  if (t == 0)                  /* the value the copy engine hands to the peers as DONE flag, later in the stream */
+    mine[FLAG_SRC*GFSB200_MAX_RANKS] = epoch;
   if (signal) {
     __threadfence_system ();
     st_release_sys (peers.p[t] + row*GFSB200_MAX_RANKS + self, epoch);
@@ -186,6 +190,8 @@ __global__ void lower_bound_kernel (int64_t n, const uint32_t * __restrict__ sor
 
 /* ------------------------------------------------------------------ */
 
+#define N_PUSH 4
+
 struct PeerInfo {
   uint64_t host;
   int32_t pid, device, rank, pad;
@@ -199,7 +205,11 @@ struct gfsb200_comm {
   ncclComm_t nccl;
   int exchange_mode;           /* GFSB200_EXCHANGE_* */
   cudaStream_t stream;         /* the communication stream */
+  cudaStream_t push[N_PUSH];   /* the pushes of one exchange fan out over these */
+  cudaEvent_t ev_fork, ev_join[N_PUSH];
   cudaEvent_t ev_dep, ev_x[2];
+  cudaEvent_t ev_barrier;      /* B(n) passed: every rank has cleared its slices for step n+1 */
+  bool barrier_pending;
   bool x_pending[2];           /* an exchange of buffer b has been issued and not yet waited for by the context's stream */
   int x_mode[2];
   uint32_t x_epoch[2];
@@ -443,7 +453,14 @@ static int comm_new (gfsb200_ctx * c, int rank, int nranks, ncclComm_t nc, gfsb2
   int lo = 0, hi = 0;
   CK (cudaDeviceGetStreamPriorityRange (&lo, &hi));
   CK (cudaStreamCreateWithPriority (&m->stream, cudaStreamNonBlocking, hi));
+  for (int j = 0; j < N_PUSH; j++) {
+    CK (cudaStreamCreateWithPriority (&m->push[j], cudaStreamNonBlocking, hi));
+    CK (cudaEventCreateWithFlags (&m->ev_join[j], cudaEventDisableTiming));
+  }
+  CK (cudaEventCreateWithFlags (&m->ev_fork, cudaEventDisableTiming));
   CK (cudaEventCreateWithFlags (&m->ev_dep, cudaEventDisableTiming));
+  CK (cudaEventCreateWithFlags (&m->ev_barrier, cudaEventDisableTiming));
+  m->barrier_pending = false;
   CK (cudaEventCreateWithFlags (&m->ev_x[0], cudaEventDisableTiming));
   CK (cudaEventCreateWithFlags (&m->ev_x[1], cudaEventDisableTiming));
   CK (cudaMalloc ((void **) &m->flags, FLAGS_BYTES));
@@ -535,7 +552,9 @@ extern "C" void gfsb200_comm_destroy (gfsb200_comm * m)
   if (dev >= 0) cudaSetDevice (dev);
   if (m->nccl && nccl_api ()) nccl_api ()->CommDestroy (m->nccl);
   cudaStreamDestroy (m->stream);
-  cudaEventDestroy (m->ev_dep); cudaEventDestroy (m->ev_x[0]); cudaEventDestroy (m->ev_x[1]);
+  for (int j = 0; j < N_PUSH; j++) { cudaStreamDestroy (m->push[j]); cudaEventDestroy (m->ev_join[j]); }
+  cudaEventDestroy (m->ev_fork);
+  cudaEventDestroy (m->ev_dep); cudaEventDestroy (m->ev_barrier); cudaEventDestroy (m->ev_x[0]); cudaEventDestroy (m->ev_x[1]);
   for (size_t i = 0; i < m->tev.size (); i++) cudaEventDestroy (m->tev[i]);
   cudaFree (m->flags); cudaFree (m->d_owners); cudaFree (m->d_small); cudaFree (m->d_info); cudaFree (m->d_hist);
   delete m;
@@ -563,6 +582,7 @@ extern "C" void gfsb200_comm_tree_changed (gfsb200_comm * m)
   close_peers (m);
   m->owner_valid = false;
   m->x_pending[0] = m->x_pending[1] = false;
+  m->barrier_pending = false;
   m->dep_mode = m->dep_done = 0;
   m->ahead_ok[0] = m->ahead_ok[1] = false;
 }
@@ -836,6 +856,7 @@ extern "C" int gfsb200_comm_rebalance (gfsb200_comm * const * local, int n_local
     CK (cudaStreamSynchronize (c->stream));
     m->ahead_ok[0] = m->ahead_ok[1] = true;
     m->x_pending[0] = m->x_pending[1] = false;
+    m->barrier_pending = false;
     m->owner_valid = true;
   }
   /* nobody deposits into a peer's slice before that peer has cleared it */
@@ -854,7 +875,7 @@ extern "C" int gfsb200_comm_rebalance (gfsb200_comm * const * local, int n_local
 extern "C" int gfsb200_comm_prepare_deposit (gfsb200_comm * m, int what, bool local_only, DevDeposit * D)
 {
   gfsb200_ctx * c = m->c;
-  const int t = c->dep_which, o = 1 - t;
+  const int t = c->dep_which;
   const size_t n = c->T.n_cells;
   if (!c->deposit_buf[1]) {
     CK (cudaMalloc ((void **) &c->deposit_buf[1], (size_t) c->deposit_count*sizeof (double)));
@@ -889,17 +910,13 @@ extern "C" int gfsb200_comm_prepare_deposit (gfsb200_comm * m, int what, bool lo
       return gfsb200_fail (GFSB200_ERR_STATE, "deposit: the rank's slice of the target buffer was not cleared ahead "
 			   "(whole-buffer deposits were mixed in): call gfsb200_comm_rebalance");
     const int32_t lo = m->split[m->rank], hi = m->split[m->rank + 1];
-    if (!m->dep_done) {
-      /* first deposit of the step: clear the own slice of the OTHER buffer for the next step, once
-	 its pushes have left (see the ordering note at the top of the file) */
-      if (m->x_pending[o]) {
-	CK (cudaStreamWaitEvent (c->stream, m->ev_x[o], 0));
-	/* (stays pending: gfsb200_deposit_wait still has to see the peers' DONE flags) */
-      }
-      if (hi > lo)
-	for (int k = 0; k <= c->T.dim; k++)
-	  CK (cudaMemsetAsync (c->deposit_buf[o] + k*n + lo, 0, (size_t) (hi - lo)*sizeof (double), c->stream));
-      m->ahead_ok[o] = true;
+    /* (the own slice of the OTHER buffer is cleared for the next step by gfsb200_deposit_allreduce,
+       behind this step's kernels: see the ordering note at the top of the file)
+       Nothing may be reduced into a peer's slice before that peer has cleared it: the deposit
+       kernel waits for B(n-1) -- the barrier only, not the pushes behind it. */
+    if (m->barrier_pending) {
+      CK (cudaStreamWaitEvent (c->stream, m->ev_barrier, 0));
+      m->barrier_pending = false;
     }
     D->own_lo = lo; D->own_hi = hi;
     D->peers = m->nranks > 1 ? m->d_owners + t : NULL;
@@ -947,9 +964,23 @@ extern "C" int gfsb200_deposit_allreduce (gfsb200_comm * const * local, int n_lo
     gfsb200_comm * m = local[k];
     gfsb200_ctx * c = m->c;
     CK (cudaSetDevice (c->device));
+    if (mode == MODE_OWNER) {
+      /* Z(n+1): clear my slice of the OTHER buffer for the next step -- on the context's stream,
+	 behind this step's kernels and before my arrival at B(n).  Its previous exchange has had a
+	 whole step to drain, so the wait below is normally already satisfied. */
+      const int o = 1 - c->dep_which;
+      const size_t n = c->T.n_cells;
+      const int32_t lo = m->split[m->rank], hi = m->split[m->rank + 1];
+      if (m->x_pending[o])
+	CK (cudaStreamWaitEvent (c->stream, m->ev_x[o], 0));     /* (stays pending for gfsb200_deposit_wait) */
+      if (hi > lo)
+	CK (cudaMemset2DAsync (c->deposit_buf[o] + lo, n*sizeof (double), 0, (size_t) (hi - lo)*sizeof (double),
+			       (size_t) c->T.dim + 1, c->stream));
+      m->ahead_ok[o] = true;
+    }
     CK (cudaEventRecord (m->ev_dep, c->stream));
     CK (cudaStreamWaitEvent (m->stream, m->ev_dep, 0));
-    if ((r = stat_begin (m))) return r;
+    if (!(mode == MODE_OWNER && R > 1) && (r = stat_begin (m))) return r;
     m->epoch++;
   }
   if (mode == MODE_LOCAL) {
@@ -978,17 +1009,34 @@ extern "C" int gfsb200_deposit_allreduce (gfsb200_comm * const * local, int n_lo
       gfsb200_launch_counter += 1;
       comm_flags_kernel<<<1, 32, 0, m->stream>>> (pf, m->flags, m->rank, R, FLAG_ARRIVE, m->epoch, 1, 1);
       CK (cudaGetLastError ());
-      /* my slice to every peer: copy engines over NVLink, no SM time */
-      if (hi > lo)
+      CK (cudaEventRecord (m->ev_barrier, m->stream));
+      m->barrier_pending = true;
+      if ((r = stat_begin (m))) return r;          /* the transfer is timed from here: the barrier is rank skew */
+      /* my slice to every peer: copy engines over NVLink, no SM time.  One contiguous copy per
+	 peer and component (a strided cudaMemcpy2DAsync between peers measured 100 GB/s against
+	 320+ for plain copies), spread over a few streams so that several engines and links work
+	 at once. */
+      if (hi > lo) {
+	CK (cudaEventRecord (m->ev_fork, m->stream));
+	for (int j = 0; j < N_PUSH; j++)
+	  CK (cudaStreamWaitEvent (m->push[j], m->ev_fork, 0));
+	int k2 = 0;
 	for (int d = 1; d < R; d++) {
 	  const int q = (m->rank + d) % R;
-	  for (int comp = 0; comp <= c->T.dim; comp++)
+	  for (int comp = 0; comp <= c->T.dim; comp++, k2++)
 	    CK (cudaMemcpyAsync (m->peer_dep[t][q] + comp*n + lo, c->deposit_buf[t] + comp*n + lo,
-				 (size_t) (hi - lo)*sizeof (double), cudaMemcpyDefault, m->stream));
+				 (size_t) (hi - lo)*sizeof (double), cudaMemcpyDefault, m->push[k2 % N_PUSH]));
 	}
-      gfsb200_launch_counter += 1;
-      comm_flags_kernel<<<1, 32, 0, m->stream>>> (pf, m->flags, m->rank, R, FLAG_DONE, m->epoch, 1, 0);
-      CK (cudaGetLastError ());
+	for (int j = 0; j < N_PUSH; j++) {
+	  CK (cudaEventRecord (m->ev_join[j], m->push[j]));
+	  CK (cudaStreamWaitEvent (m->stream, m->ev_join[j], 0));
+	}
+      }
+      /* DONE(n) to every rank, behind the pushes: 4-byte copies by the copy engine, not a kernel --
+	 a kernel would queue behind the next step's persistent step kernel, which fills every SM */
+      for (int q = 0; q < R; q++)
+	CK (cudaMemcpyAsync (m->peer_flags[q] + FLAG_DONE*GFSB200_MAX_RANKS + m->rank,
+			     m->flags + FLAG_SRC*GFSB200_MAX_RANKS, sizeof (uint32_t), cudaMemcpyDefault, m->stream));
       m->bytes_sent = (int64_t) (R - 1)*(c->T.dim + 1)*(hi - lo)*(int64_t) sizeof (double);
     }
   }

@@ -20,6 +20,8 @@ struct DevTree {
   int top_levels;              /* complete_level - root_level: levels resolved arithmetically */
   int top_start;               /* level_start of the complete level */
   int single_box;              /* locate array has exactly one slot holding box root 0 */
+  int has_destroyed;           /* some cell of a GfsBox tree is destroyed (entirely solid): the hull test does
+				  not decide whether a point is inside the domain */
   double root_size;            /* ftt_level_size (root_level) */
   double top_h, top_inv_h;     /* cell size at the complete level and its (exact) inverse */
   double la_inv_h;             /* 1/la_h; la_h = 2^-rootlevel, so x*la_inv_h == x/la_h bitwise */

@@ -207,6 +207,18 @@ __device__ __forceinline__ bool in_domain (const DevTree & T, double x, double y
 	   (DIM == 3 && (z > cz + half || z < cz - half)));
 }
 
+/* has the particle left the domain, i.e. is gfs_domain_locate (src/domain.c:2623-2638) NULL at p?
+ * The hull test decides unless the tree has destroyed (entirely solid) box cells: then only the
+ * full descent does (a particle that steps into a solid cell has left, modules/particulatecommon.c
+ * :3333-3335). */
+template <int DIM, bool LATTICE>
+__device__ __forceinline__ bool left_domain (const DevTree & T, double x, double y, double z)
+{
+  if (!LATTICE && T.has_destroyed)
+    return locate<DIM, LATTICE> (T, x, y, z).cell < 0;
+  return !in_domain<DIM> (T, x, y, z);
+}
+
 /* remember a particle that is about to leave the domain; its position before
  * the step is still in global memory at this point */
 template <int DIM>
@@ -686,7 +698,7 @@ step_kernel (DevTree T, DevField fld, DevParticles P, DevStep S)
   if (DIM == 3) {
     z = fma (vz, hdt, z); vz = fma (Fz, dtm, vz); z = fma (vz, hdt, z);
   }
-  if (S.track_escapes && !in_domain<DIM> (T, x, y, z))
+  if (S.track_escapes && left_domain<DIM, LATTICE> (T, x, y, z))
     record_escape<DIM> (S, P, i);
   __stcs (P.x + i, x); __stcs (P.y + i, y); __stcs (P.vx + i, vx); __stcs (P.vy + i, vy);
   if (DIM == 3) {
@@ -850,7 +862,7 @@ step_kernel_pipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_tile
 	if (DIM == 3) {
 	  z = fma (vz, hdt, z); vz = fma (Fz, dtm, vz); z = fma (vz, hdt, z);
 	}
-	if (S.track_escapes && !in_domain<DIM> (T, x, y, z))
+	if (S.track_escapes && left_domain<DIM, LATTICE> (T, x, y, z))
 	  record_escape<DIM> (S, P, i);
 	__stcs (P.x + i, x); __stcs (P.y + i, y); __stcs (P.vx + i, vx); __stcs (P.vy + i, vy);
 	if (DIM == 3) {
@@ -998,7 +1010,7 @@ step_kernel_wpipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_til
 	if (DIM == 3) {
 	  z = fma (vz, hdt, z); vz = fma (Fz, dtm, vz); z = fma (vz, hdt, z);
 	}
-	if (S.track_escapes && !in_domain<DIM> (T, x, y, z))
+	if (S.track_escapes && left_domain<DIM, LATTICE> (T, x, y, z))
 	  record_escape<DIM> (S, P, i);
 	__stcs (P.x + i, x); __stcs (P.y + i, y); __stcs (P.vx + i, vx); __stcs (P.vy + i, vy);
 	if (DIM == 3) {
@@ -1188,6 +1200,7 @@ particle_bc_kernel (DevTree T, DevParticles P, int n_esc, const int32_t * __rest
   const Located L = locate<DIM> (T, p0[0], p0[1], p0[2]);
   int d = -1;
   int cell = L.cell;
+  bool ghost = false;        /* the walk ended at a ghost cell of a GfsBoundary */
   if (cell >= 0) {
     double c[3] = { L.cx, L.cy, L.cz };
     double size = 2.*L.half;
@@ -1196,8 +1209,12 @@ particle_bc_kernel (DevTree T, DevParticles P, int n_esc, const int32_t * __rest
       if (d < 0)
 	break;
       const int nb = T.neighbor[(int64_t) cell*(2*DIM) + d];
-      if (nb < 0 || (T.info[nb] & GFSB200_CELL_BOUNDARY))
+      if (nb < 0)            /* the hull without a GfsBoundary, or a destroyed (solid) cell: dropped (:3259-3265) */
 	break;
+      if (T.info[nb] & GFSB200_CELL_BOUNDARY) {
+	ghost = true;
+	break;
+      }
       /* centre of the neighbour: same level, or one level coarser */
       const double dir = d & 1 ? -1. : 1.;
       if (T.level[nb] == T.level[cell])
@@ -1214,7 +1231,7 @@ particle_bc_kernel (DevTree T, DevParticles P, int n_esc, const int32_t * __rest
     }
   }
   int match = -1, root = -1;
-  if (cell >= 0 && d >= 0) {
+  if (cell >= 0 && d >= 0 && ghost) {
     root = cell;
     while (T.parent[root] >= 0)
       root = T.parent[root];

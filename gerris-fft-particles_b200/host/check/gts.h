@@ -105,6 +105,7 @@ GSList * g_slist_prepend (GSList * l, gpointer data);
 GSList * g_slist_append (GSList * l, gpointer data);
 GSList * g_slist_remove (GSList * l, gconstpointer data);
 void g_slist_free (GSList * l);
+GSList * g_slist_find (GSList * l, gconstpointer data);
 guint g_slist_length (GSList * l);
 typedef struct _GList GList;
 struct _GList { gpointer data; GList * next, * prev; };

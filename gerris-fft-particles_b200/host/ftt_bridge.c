@@ -38,6 +38,8 @@ static const struct bridge_solid * state_solid (const FttCell * c)
 struct gfsb200_ftt_map {
   int32_t n_cells;
   FttCell ** cell;            /* flat index -> FttCell */
+  char ** data;               /* flat index -> cell->data (NULL: destroyed cell, or no data), or NULL: not cached */
+  unsigned data_generation;
 };
 
 static const char * bridge_error = "";
@@ -47,6 +49,7 @@ void gfsb200_ftt_map_free (gfsb200_ftt_map * m)
 {
   if (!m) return;
   free (m->cell);
+  free (m->data);
   free (m);
 }
 
@@ -153,6 +156,8 @@ int gfsb200_ftt_flatten (int n_roots, void * const * roots_, const int * is_box,
   gfsb200_ftt_map * m = malloc (sizeof *m);
   m->n_cells = (int32_t) n;
   m->cell = cells;
+  m->data = NULL;
+  m->data_generation = 0;
   *tree_out = t;
   *map_out = m;
   return GFSB200_OK;
@@ -173,12 +178,41 @@ int gfsb200_ftt_gather (const gfsb200_ftt_map * m, size_t offset, int var, doubl
 int gfsb200_ftt_gather_many (const gfsb200_ftt_map * m, size_t offset, int nvar, const int * var,
 			     const double * nodata, double * const * out)
 {
-  if (!m || nvar < 0 || (nvar && (!var || !nodata || !out))) {
+  return gfsb200_ftt_gather_range (m, offset, 0, m ? m->n_cells : 0, nvar, var, nodata, out);
+}
+
+/* the same for the flat cells [first, last): out[k][i] is written for first <= i < last, so that
+   the caller can ship one slice to the device while the next one is being gathered */
+int gfsb200_ftt_gather_range (const gfsb200_ftt_map * m, size_t offset, int32_t first, int32_t last,
+			      int nvar, const int * var, const double * nodata, double * const * out)
+{
+  if (!m || nvar < 0 || (nvar && (!var || !nodata || !out)) || first < 0 || last > m->n_cells || first > last) {
     bridge_error = "gather: bad argument";
     return GFSB200_ERR_ARG;
   }
+  if (m->data) {
+    /* cached data pointers: a sequential read of the pointer array, the data blocks prefetched
+       a few cells ahead -- no FttCell / FttOct line is touched */
+    char * const * data = m->data;
+    const int32_t n = last;
 #pragma omp parallel for schedule(static)
-  for (int32_t i = 0; i < m->n_cells; i++) {
+    for (int32_t i = first; i < n; i++) {
+      if (i + 32 < n && data[i + 32])
+	__builtin_prefetch (data[i + 32] + offset, 0, 0);
+      const char * d = data[i];
+      if (!d)
+	for (int k = 0; k < nvar; k++)
+	  out[k][i] = nodata[k];
+      else {
+	const double * v = (const double *) (d + offset);
+	for (int k = 0; k < nvar; k++)
+	  out[k][i] = v[var[k]];
+      }
+    }
+    return GFSB200_OK;
+  }
+#pragma omp parallel for schedule(static)
+  for (int32_t i = first; i < last; i++) {
     FttCell * c = m->cell[i];
     if (FTT_CELL_IS_DESTROYED (c) || !c->data)
       for (int k = 0; k < nvar; k++)
@@ -192,9 +226,31 @@ int gfsb200_ftt_gather_many (const gfsb200_ftt_map * m, size_t offset, int nvar,
   return GFSB200_OK;
 }
 
+int gfsb200_ftt_map_cache_data (gfsb200_ftt_map * m, unsigned generation)
+{
+  if (!m) {
+    bridge_error = "cache_data: bad argument";
+    return GFSB200_ERR_ARG;
+  }
+  if (m->data && m->data_generation == generation)
+    return GFSB200_OK;
+  if (!m->data && !(m->data = malloc ((m->n_cells ? m->n_cells : 1)*sizeof (char *)))) {
+    bridge_error = "cache_data: out of memory";
+    return GFSB200_ERR_NOMEM;
+  }
+#pragma omp parallel for schedule(static)
+  for (int32_t i = 0; i < m->n_cells; i++) {
+    FttCell * c = m->cell[i];
+    m->data[i] = FTT_CELL_IS_DESTROYED (c) ? NULL : (char *) c->data;
+  }
+  m->data_generation = generation;
+  return GFSB200_OK;
+}
+
 int gfsb200_ftt_scatter (const gfsb200_ftt_map * m, size_t offset, int var, int leaves_only,
 			 const double * in)
 {
+#pragma omp parallel for schedule(static)
   for (int32_t i = 0; i < m->n_cells; i++) {
     FttCell * c = m->cell[i];
     /* leaves_only: the cells gfs_domain_cell_traverse (FTT_TRAVERSE_LEAFS) visits, i.e. the

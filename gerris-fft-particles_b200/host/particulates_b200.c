@@ -25,10 +25,19 @@
  *   GfsSourceParticulate.event source_particulate_event  modules/particulatecommon.c:2177-2228
  *
  * and exports the same module symbols as modules/particulates.c:24-49.
- * A list that carries something the device does not implement (user force
- * classes, coefficient / density functions that are neither a constant nor a
- * plain cell variable), or a simulation with moving solids, is handed back to
- * the reference's own event untouched.
+ *
+ * There is NO silent CPU fallback.  A list that carries something the device does not implement
+ * (user force classes, coefficient / density functions that are neither a constant nor a plain
+ * cell variable, a smoothing kernel outside the closed forms of gfsb200.h), a simulation with
+ * moving solids, or an MPI domain decomposition (the device path replicates the field and shards
+ * the particles over the GPUs of one box) stops the run with a g_error naming the object.  Setting
+ * GFSB200_ALLOW_REFERENCE_EVENT=1 opts in to the reference's own CPU event for exactly those
+ * objects, with one g_warning per object.
+ *
+ * Environment: GFSB200_DEVICE=<n> (device of a single-GPU run, default 0),
+ * GFSB200_RESIDENT=0 (write every particle back into its GfsParticulate after every event; by
+ * default the device copy is authoritative between events and the objects are refreshed when
+ * something on the host is about to look at them), GFSB200_MODULE_PROFILE=1.
  */
 #include <stdlib.h>
 #include <string.h>
@@ -47,8 +56,13 @@ typedef struct {
   gfsb200_ctx * ctx;
   gfsb200_tree * tree;
   gfsb200_ftt_map * map;
-  guint adapt_created, adapt_removed;   /* mesh-change signature, src/simulation.h:49-51 */
+  guint mesh_epoch;                     /* b200_mesh_epoch when the tree was flattened */
+  guint n_roots;                        /* box / boundary roots at that time ... */
+  gsize root_hash;                      /* ... and a hash of their addresses */
+  guint data_generation;                /* domain->allocated->len: the cell data blocks move when it grows */
   gboolean tree_valid;
+  gdouble * dep_out;                    /* page-locked staging of one deposited component */
+  gint32 dep_cap;
   gdouble * field[3];                   /* page-locked staging of U,V,W in flat order */
   gdouble * cellvar[2];                 /* page-locked staging of per-cell alpha / viscosity, when they are variables */
   gint32 field_cap;                     /* cells the five buffers above hold */
@@ -91,6 +105,25 @@ static gboolean (* reference_list_event) (GfsEvent *, GfsSimulation *) = NULL;
 static gboolean (* reference_field_event) (GfsEvent *, GfsSimulation *) = NULL;
 static gboolean (* reference_source_event) (GfsEvent *, GfsSimulation *) = NULL;
 
+/* No silent CPU fallback: an object the device path cannot express stops the run, unless the
+ * user has opted in to the reference's own CPU event for it (one warning per object). */
+static void reference_or_error (gpointer object, const gchar * name, const gchar * why)
+{
+  static GHashTable * warned = NULL;
+  const gchar * env = g_getenv ("GFSB200_ALLOW_REFERENCE_EVENT");
+  if (!env || atoi (env) == 0)
+    g_error ("particulates (B200): %s: %s cannot run on the device.  There is no silent CPU fallback; "
+	     "set GFSB200_ALLOW_REFERENCE_EVENT=1 to run the reference's own CPU event for this object",
+	     name ? name : "(unnamed)", why);
+  if (!warned)
+    warned = g_hash_table_new (NULL, NULL);
+  if (!g_hash_table_lookup (warned, object)) {
+    g_hash_table_insert (warned, object, object);
+    g_warning ("particulates (B200): %s: %s cannot run on the device: the reference's CPU event runs instead "
+	       "(GFSB200_ALLOW_REFERENCE_EVENT)", name ? name : "(unnamed)", why);
+  }
+}
+
 static B200State * state_of (GfsParticleList * plist)
 {
   B200State * s;
@@ -102,24 +135,11 @@ static B200State * state_of (GfsParticleList * plist)
     const gchar * env = g_getenv ("GFSB200_DEVICE");
     s = g_malloc0 (sizeof (B200State));
     if (env) device = atoi (env);
-#ifdef HAVE_MPI
-    else {                      /* one rank per GPU; pid is -1 in a serial run of an MPI build */
-      device = GFS_DOMAIN (gfs_object_simulation (plist))->pid;
-      if (device < 0) device = 0;
-    }
-#endif
     if (gfsb200_ctx_create (device, &s->ctx) != GFSB200_OK)
       g_error ("particulates (B200): %s", gfsb200_last_error ());   /* no CPU fallback */
     s->plist = plist;
-    s->resident = g_getenv ("GFSB200_RESIDENT") && atoi (g_getenv ("GFSB200_RESIDENT")) != 0;
-#ifdef HAVE_MPI
-    /* a parallel run exchanges particles inside gfs_particle_bc (:3218-3244, 3287-3316), which
-       must then run -- on up-to-date objects -- in every event on every rank */
-    if (GFS_DOMAIN (gfs_object_simulation (plist))->pid >= 0) {
-      s->resident = FALSE;
-      s->mpi = TRUE;
-    }
-#endif
+    /* the device copy is authoritative between events unless GFSB200_RESIDENT=0 */
+    s->resident = !(g_getenv ("GFSB200_RESIDENT") && atoi (g_getenv ("GFSB200_RESIDENT")) == 0);
     g_hash_table_insert (b200_states, plist, s);
   }
   return s;
@@ -235,6 +255,7 @@ static void b200_particle_list_destroy (GtsObject * o)
       gfsb200_host_free (s->field[c]);
     gfsb200_host_free (s->cellvar[0]);
     gfsb200_host_free (s->cellvar[1]);
+    gfsb200_host_free (s->dep_out);
     for (k = 0; k < 10; k++)
       gfsb200_host_free (s->col[k]);
     gfsb200_host_free (s->id);
@@ -255,6 +276,37 @@ static gpointer pinned (gsize bytes)
   return p;
 }
 
+/* Mesh identity.  sim->adapts_stats is not a signature: GfsOutputAdaptStats resets it after every
+ * output (src/output.c:688) and two adapts can produce the same counts.  Instead the module owns a
+ * hidden (unnamed, never written) GfsVariable per domain whose callbacks Gerris runs for EVERY cell
+ * it refines (coarse_fine, from gfs_cell_fine_init, src/domain.c:2979-3010) or destroys (cleanup,
+ * from gfs_cell_cleanup, src/fluid.c:1965-1985 -- coarsening, box migration, domain destruction):
+ * each bumps an epoch.  Boxes that ARRIVE (GfsEventBalance) are caught by the root signature. */
+static guint b200_mesh_epoch = 1;
+static GHashTable * b200_mesh_watch = NULL;    /* GfsDomain* -> its hidden GfsVariable */
+
+static void mesh_refined (FttCell * parent, GfsVariable * v) { b200_mesh_epoch++; }
+static void mesh_cell_destroyed (FttCell * cell, GfsVariable * v) { b200_mesh_epoch++; }
+static void mesh_none (FttCell * cell, GfsVariable * v) {}
+
+static void watch_mesh (GfsDomain * domain)
+{
+  GfsVariable * v;
+  if (!b200_mesh_watch)
+    b200_mesh_watch = g_hash_table_new (NULL, NULL);
+  v = g_hash_table_lookup (b200_mesh_watch, domain);
+  if (v && g_slist_find (domain->variables, v))
+    return;
+  v = gfs_domain_add_variable (domain, NULL, "B200 mesh watch");
+  if (v == NULL)
+    g_error ("particulates (B200): cannot add the mesh-watch variable");
+  v->coarse_fine = mesh_refined;
+  v->fine_coarse = mesh_none;
+  v->cleanup = (FttCellCleanupFunc) mesh_cell_destroyed;
+  g_hash_table_insert (b200_mesh_watch, domain, v);
+  b200_mesh_epoch++;                    /* whatever happened before the watch started is unknown */
+}
+
 typedef struct { GPtrArray * roots; GArray * is_box; } RootList;
 
 static void collect_roots (GfsBox * box, RootList * r)
@@ -273,18 +325,29 @@ static void collect_roots (GfsBox * box, RootList * r)
 static void refresh_tree (B200State * s, GfsSimulation * sim)
 {
   GfsDomain * domain = GFS_DOMAIN (sim);
-  if (s->tree_valid &&
-      s->adapt_created == sim->adapts_stats.created &&
-      s->adapt_removed == sim->adapts_stats.removed)
-    return;
   RootList r = { g_ptr_array_new (), g_array_new (FALSE, FALSE, sizeof (gint)) };
   FttComponent c;
+  gsize hash = 0;
+  guint k;
+  watch_mesh (domain);
   gts_container_foreach (GTS_CONTAINER (domain), (GtsFunc) collect_roots, &r);
+  for (k = 0; k < r.roots->len; k++)
+    hash = hash*31 + (gsize) r.roots->pdata[k];
+  if (s->tree_valid && s->mesh_epoch == b200_mesh_epoch && s->n_roots == r.roots->len && s->root_hash == hash) {
+    g_ptr_array_free (r.roots, TRUE);
+    g_array_free (r.is_box, TRUE);
+    return;
+  }
+  /* the flat tree's map points at FttCells of the old mesh: nothing may use it from here on */
+  s->tree_valid = FALSE;
   if (s->map) gfsb200_ftt_map_free (s->map);
   if (s->tree) gfsb200_tree_free (s->tree);
+  s->map = NULL; s->tree = NULL;
   if (gfsb200_ftt_flatten (r.roots->len, (void * const *) r.roots->pdata, (const int *) r.is_box->data,
 			   &s->tree, &s->map) != GFSB200_OK)
     g_error ("particulates (B200): %s", gfsb200_ftt_last_error ());
+  s->n_roots = r.roots->len;
+  s->root_hash = hash;
   g_ptr_array_free (r.roots, TRUE);
   g_array_free (r.is_box, TRUE);
   if (gfsb200_tree_build_stencils (s->tree) != GFSB200_OK ||
@@ -302,8 +365,7 @@ static void refresh_tree (B200State * s, GfsSimulation * sim)
     }
     s->field_cap = s->n_cells;
   }
-  s->adapt_created = sim->adapts_stats.created;
-  s->adapt_removed = sim->adapts_stats.removed;
+  s->mesh_epoch = b200_mesh_epoch;
   s->tree_valid = TRUE;
 }
 
@@ -328,10 +390,26 @@ static void mirror_velocity (B200State * s, GfsDomain * domain)
   if (s->mu_var) {
     var[n] = s->mu_var->i; nodata[n] = 0.; out[n++] = s->cellvar[1];
   }
-  gfsb200_ftt_gather_many (s->map, off, n, var, nodata, out);
-  if (gfsb200_upload_field (s->ctx, s->field[0], s->field[1], FTT_DIMENSION > 2 ? s->field[2] : NULL,
-			    s->alpha_var ? s->cellvar[0] : NULL, s->mu_var ? s->cellvar[1] : NULL) != GFSB200_OK)
-    g_error ("particulates (B200): %s", gfsb200_last_error ());
+  /* the data block of every cell is looked up once per flatten (and again when Gerris has moved
+     the blocks to make room for a new variable): the per-event gather never touches the tree */
+  if (gfsb200_ftt_map_cache_data (s->map, 1 + (domain->allocated ? domain->allocated->len : 0)) != GFSB200_OK)
+    g_error ("particulates (B200): %s", gfsb200_ftt_last_error ());
+  {
+    /* in slices: while the copy engine ships slice k (page-locked staging, asynchronous), the host
+       cores gather slice k + 1 out of the tree -- the upload hides behind the gather */
+    const gint32 slices = s->n_cells > (1 << 18) ? 8 : 1;
+    gint32 k;
+    for (k = 0; k < slices; k++) {
+      const gint32 first = (gint32) ((gint64) s->n_cells*k/slices), last = (gint32) ((gint64) s->n_cells*(k + 1)/slices);
+      gfsb200_ftt_gather_range (s->map, off, first, last, n, var, nodata, out);
+      if (gfsb200_upload_field_part (s->ctx, first, last - first, s->field[0], s->field[1],
+				     FTT_DIMENSION > 2 ? s->field[2] : NULL,
+				     s->alpha_var ? s->cellvar[0] : NULL, s->mu_var ? s->cellvar[1] : NULL) != GFSB200_OK)
+	g_error ("particulates (B200): %s", gfsb200_last_error ());
+    }
+    if (gfsb200_refresh_field (s->ctx) != GFSB200_OK)
+      g_error ("particulates (B200): %s", gfsb200_last_error ());
+  }
   if (s->uold) {                          /* Un,Vn,Wn of GfsForceInertial / GfsForceAddedMass */
     for (c = 0; c < FTT_DIMENSION; c++) {
       var[c] = s->uold[c]->i; nodata[c] = GFS_NODATA; out[c] = s->field[c];
@@ -413,8 +491,19 @@ static void adopt (B200State * s, const ListVars * lv)
 
 /* (reads the objects only: no device context is created for a list that ends up
    on the reference path) */
+static const gchar * step_params_why (GfsParticleList * plist, GfsSimulation * sim, gfsb200_step_params * p,
+				      ListVars * lv);
+
 static gboolean step_params (GfsParticleList * plist, GfsSimulation * sim, gfsb200_step_params * p,
-			     ListVars * lv)
+			     ListVars * lv, const gchar ** why)
+{
+  *why = step_params_why (plist, sim, p, lv);
+  return *why == NULL;
+}
+
+/* NULL if the list can run on the device, else what it carries that cannot */
+static const gchar * step_params_why (GfsParticleList * plist, GfsSimulation * sim, gfsb200_step_params * p,
+				      ListVars * lv)
 {
   GfsDomain * domain = GFS_DOMAIN (sim);
   GfsVariable ** u = gfs_domain_velocity (domain);
@@ -427,8 +516,10 @@ static gboolean step_params (GfsParticleList * plist, GfsSimulation * sim, gfsb2
   while (i) {
     GfsForceCoeff * coeff = GFS_IS_FORCE_COEFF (i->data) ? FORCE_COEFF (i->data) : NULL;
     gdouble k = coeff && coeff->coefficient ? gfs_function_get_constant_value (coeff->coefficient) : 0.;
-    if (p->n_forces == GFSB200_MAX_FORCES || k == G_MAXDOUBLE)
-      return FALSE;
+    if (p->n_forces == GFSB200_MAX_FORCES)
+      return "a force list longer than GFSB200_MAX_FORCES";
+    if (k == G_MAXDOUBLE)
+      return "a force coefficient GfsFunction that is not a constant (modules/particulatecommon.c:566-575)";
     if (GFS_IS_FORCE_DRAG (i->data)) {
       p->force[p->n_forces++] = GFSB200_FORCE_DRAG;
       if (coeff->coefficient) p->cd_const = k;
@@ -450,7 +541,7 @@ static gboolean step_params (GfsParticleList * plist, GfsSimulation * sim, gfsb2
     else if (GFS_IS_FORCE_BUOY (i->data))
       p->force[p->n_forces++] = GFSB200_FORCE_BUOY;
     else
-      return FALSE;                       /* user-defined force classes */
+      return "a user-defined force class";
     i = i->next;
   }
   /* fluid density 1/alpha (particulatecommon.c:534-535) */
@@ -460,7 +551,7 @@ static gboolean step_params (GfsParticleList * plist, GfsSimulation * sim, gfsb2
       /* alpha = <a cell variable>: mirrored per cell; any other expression stays on the host */
       GfsVariable * v = gfs_function_get_variable (sim->physical_params.alpha);
       if (v == NULL)
-	return FALSE;
+	return "PhysicalParams alpha given as an expression (neither a constant nor a plain variable)";
       lv->alpha_var = v;
     }
     else
@@ -486,13 +577,18 @@ static gboolean step_params (GfsParticleList * plist, GfsSimulation * sim, gfsb2
       if (GFS_IS_SOURCE (j->data)) {
 	gdouble g = gfs_function_get_constant_value (GFS_SOURCE (j->data)->intensity);
 	if (g == G_MAXDOUBLE)
-	  return FALSE;
+	  return "a GfsSource on the velocity whose intensity is not a constant";
 	p->g[c] += g;
       }
       j = j->next;
     }
   }
-  return TRUE;
+#ifdef HAVE_MPI
+  if (domain->pid >= 0)
+    return "an MPI domain decomposition (the device path replicates the field and shards the particles "
+      "over the GPUs of one box: run gerris serially)";
+#endif
+  return NULL;
 }
 
 /* ------------------------------------------------------------------ */
@@ -707,9 +803,13 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
   gdouble t[7];
   gint k;
 
-  if (moving_solids (sim) || !step_params (plist, sim, &par, &lv)) {
+  const gchar * why = NULL;
+  if (moving_solids (sim))
+    why = "a simulation with moving solids (GfsSolidMoving changes the cell fractions every step)";
+  if (why || !step_params (plist, sim, &par, &lv, &why)) {
+    reference_or_error (plist, "GfsParticleList", why);
     gfsb200_module_sync (plist);
-    return (* reference_list_event) (event, sim);            /* not expressible on the device */
+    return (* reference_list_event) (event, sim);            /* opted in: GFSB200_ALLOW_REFERENCE_EVENT */
   }
 
   /* the timing gate of gfs_event_list_event (src/event.c:2430-2439) */
@@ -752,9 +852,14 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
     gint64 outside = 0;
     if (gfsb200_step_counts (s->ctx, &escaped, &outside) != GFSB200_OK)
       g_error ("particulates (B200): %s", gfsb200_last_error ());
-    if (outside > 0)
-      g_error ("particulates (B200): %lld particles of a carried-over list are outside the domain",
-	       (long long) outside);
+    if (outside > 0) {
+      /* A carried-over list holds particles that are outside the domain (the escape count of the
+	 last event tests the box hull; a particle can also end up in a destroyed, i.e. solid,
+	 cell): the step has left them untouched; cull them now, as remove_particles_not_in_domain
+	 would have before the step, and let the objects follow */
+      if (gfsb200_particles_cull (s->ctx, &removed) != GFSB200_OK)
+	g_error ("particulates (B200): %s", gfsb200_last_error ());
+    }
     if (s->resident && escaped > 0)
       patch_pos_old (s, escaped);
   }
@@ -773,7 +878,7 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
   /* :993, host side as in the reference.  gfs_particle_bc spends one gfs_domain_locate per
      particle to find those that left the domain; the step kernel has already counted them,
      and when there are none the reference function has nothing to do. */
-  if (s->mpi || !par.track_escapes || escaped > 0)
+  if (!par.track_escapes || escaped > 0)
     gfs_particle_bc (plist);
   t[6] = wall ();
   if (s->warm) {                /* the first event pays for the flatten and the page-locked buffers */
@@ -790,6 +895,18 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
   return TRUE;
 }
 
+/* page-locked buffer for one component of the deposited field (kept: an event per step must not
+   allocate) */
+static gdouble * deposit_staging (B200State * s)
+{
+  if (s->n_cells > s->dep_cap) {
+    gfsb200_host_free (s->dep_out);
+    s->dep_out = pinned (sizeof (gdouble)*s->n_cells);
+    s->dep_cap = s->n_cells;
+  }
+  return s->dep_out;
+}
+
 static gboolean b200_particulate_field_event (GfsEvent * event, GfsSimulation * sim)
 {
   GfsVariable * v = GFS_VARIABLE (event);
@@ -799,8 +916,14 @@ static gboolean b200_particulate_field_event (GfsEvent * event, GfsSimulation * 
   B200State * s;
   gdouble * out;
 
-  if (moving_solids (sim) || !step_params (pfield->plist, sim, &par, &lv))
+  const gchar * why = NULL;
+  if (moving_solids (sim))
+    why = "a simulation with moving solids";
+  if (why || !step_params (pfield->plist, sim, &par, &lv, &why)) {
+    reference_or_error (event, "GfsParticulateField", why);
+    gfsb200_module_sync (pfield->plist);
     return (* reference_field_event) (event, sim);
+  }
   if (!(* GFS_EVENT_CLASS (gfs_variable_class ())->event) (event, sim))
     return FALSE;
   s = state_of (pfield->plist);
@@ -809,11 +932,11 @@ static gboolean b200_particulate_field_event (GfsEvent * event, GfsSimulation * 
   device_current (s, pfield->plist);
   if (gfsb200_deposit_volume (s->ctx) != GFSB200_OK)
     g_error ("particulates (B200): %s", gfsb200_last_error ());
-  out = g_malloc (sizeof (gdouble)*s->n_cells);
-  gfsb200_download_deposit (s->ctx, 0, out);
+  out = deposit_staging (s);
+  if (gfsb200_download_deposit (s->ctx, 0, out) != GFSB200_OK)
+    g_error ("particulates (B200): %s", gfsb200_last_error ());
   /* gfs_cell_reset on the leaves + the scatter of :1945-1953 */
   gfsb200_ftt_scatter (s->map, offsetof (GfsStateVector, place_holder), v->i, TRUE, out);
-  g_free (out);
   return TRUE;
 }
 
@@ -842,9 +965,18 @@ static gboolean b200_source_particulate_event (GfsEvent * event, GfsSimulation *
   GSList * i;
   FttComponent c;
 
-  if (moving_solids (sim) || !step_params (sp->plist, sim, &par, &lv) ||
+  const gchar * why = NULL;
+  if (moving_solids (sim))
+    why = "a simulation with moving solids";
+  if (!why && step_params (sp->plist, sim, &par, &lv, &why) &&
       gfsb200_kernel_fit (kernel_trampoline, sp->kernel_function, FTT_DIMENSION, &kernel) != GFSB200_OK)
+    why = "a smoothing kernel that is none of the closed forms the device evaluates (constant, Gaussian, "
+      "compact polynomial: include/gfsb200.h)";
+  if (why) {
+    reference_or_error (event, "GfsSourceParticulate", why);
+    gfsb200_module_sync (sp->plist);
     return (* reference_source_event) (event, sim);
+  }
   /* the timing gate of the parent class (:2180-2181) */
   if (!(* GFS_EVENT_CLASS (GTS_OBJECT_CLASS (gfs_source_particulate_class ())->parent_class)->event)
       (event, sim))
@@ -859,27 +991,32 @@ static gboolean b200_source_particulate_event (GfsEvent * event, GfsSimulation *
   if (gfsb200_deposit_force_smoothed (s->ctx, &par, sp->rkernel, &kernel) != GFSB200_OK)
     g_error ("particulates (B200): %s", gfsb200_last_error ());
   /* <plist>_Fx,_Fy,_Fz: gfs_cell_reset on the leaves + the scatter of diffuse_force */
-  out = g_malloc (sizeof (gdouble)*s->n_cells);
+  out = deposit_staging (s);
   for (c = 0; c < FTT_DIMENSION; c++) {
-    gfsb200_download_deposit (s->ctx, 1 + c, out);
+    if (gfsb200_download_deposit (s->ctx, 1 + c, out) != GFSB200_OK)
+      g_error ("particulates (B200): %s", gfsb200_last_error ());
     gfsb200_ftt_scatter (s->map, offsetof (GfsStateVector, place_holder), sp->u[c]->i, TRUE, out);
   }
-  g_free (out);
   /* the reference leaves the on-fluid force in particulate->force (:2195-2201); in resident
      mode with stale objects the device keeps it and the next sync_down delivers it */
   if (!state_of (sp->plist)->host_stale) {
+    gdouble * mass = g_malloc (sizeof (gdouble)*(n ? n : 1));
     for (c = 0; c < 3; c++)
       force[c] = g_malloc (sizeof (gdouble)*(n ? n : 1));
+    /* the on-fluid pass of a GfsForceAddedMass updates the particle mass too (compute_forces_onfluid
+       -> :391): it comes back with the forces, or the next upload would undo it */
     if (gfsb200_particles_download (s->ctx, NULL, NULL, NULL, NULL, NULL, NULL, force[0], force[1], force[2],
-  				  NULL, NULL, NULL, NULL) != GFSB200_OK)
+  				  mass, NULL, NULL, NULL) != GFSB200_OK)
       g_error ("particulates (B200): %s", gfsb200_last_error ());
     for (i = GFS_EVENT_LIST (sp->plist)->list->items; i && k < n; i = i->next, k++) {
       GfsParticulate * q = GFS_PARTICULATE (i->data);
       q->force.x = force[0][k]; q->force.y = force[1][k];
       q->force.z = FTT_DIMENSION > 2 ? force[2][k] : 0.;
+      q->mass = mass[k];
     }
     for (c = 0; c < 3; c++)
       g_free (force[c]);
+    g_free (mass);
   }
   return TRUE;
 }

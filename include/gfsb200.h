@@ -171,6 +171,8 @@ int gfsb200_tree_corner_interpolator (const gfsb200_tree * t, int cell, int k,
  * ------------------------------------------------------------------------ */
 typedef struct gfsb200_ctx gfsb200_ctx;
 
+/* number of CUDA devices the process sees (0: none, or no usable driver) */
+int gfsb200_device_count (void);
 int gfsb200_ctx_create (int device, gfsb200_ctx ** out);
 void gfsb200_ctx_destroy (gfsb200_ctx * c);
 /* the CUDA stream all of this context's work is issued on (cudaStream_t) */
@@ -190,6 +192,14 @@ int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t);
  * velocity table and the per-leaf vorticity table on the device. */
 int gfsb200_upload_field (gfsb200_ctx * c, const double * u, const double * v, const double * w,
 			  const double * alpha, const double * mu);
+/* The same mirror in slices: copies cells [first, first + n) of every array given (the arrays are
+ * indexed by flat cell, as above; the set of non-NULL arrays must be the same in every call of one
+ * update) and returns at once -- page-locked host arrays make the copy overlap whatever the host
+ * does next, e.g. gathering the next slice out of the FttCell tree.  The tables are NOT rebuilt:
+ * finish the update with gfsb200_refresh_field. */
+int gfsb200_upload_field_part (gfsb200_ctx * c, int64_t first, int64_t n,
+			       const double * u, const double * v, const double * w,
+			       const double * alpha, const double * mu);
 /* same, from device pointers */
 int gfsb200_set_field_device (gfsb200_ctx * c, const double * u, const double * v, const double * w,
 			      const double * alpha, const double * mu);

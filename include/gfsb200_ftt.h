@@ -43,6 +43,19 @@ int gfsb200_ftt_gather (const gfsb200_ftt_map * m, size_t offset, int var, doubl
  * out[k][i] = GFS_VALUEI (cell_i, var[k]), nodata[k] for destroyed cells */
 int gfsb200_ftt_gather_many (const gfsb200_ftt_map * m, size_t offset, int nvar, const int * var,
 			     const double * nodata, double * const * out);
+/* ... and for the flat cells [first, last) only: lets the caller ship one slice to the device
+ * (gfsb200_upload_field_part) while the next one is being gathered */
+int gfsb200_ftt_gather_range (const gfsb200_ftt_map * m, size_t offset, int32_t first, int32_t last,
+			      int nvar, const int * var, const double * nodata, double * const * out);
+/* The per-step gather is a pointer chase cell -> data (one cache miss per cell on top of the one
+ * for the cell itself).  gfsb200_ftt_map_cache_data records, once per flatten, where the data block
+ * of every cell lives; the gathers above then stream through that array with software prefetch and
+ * never touch the FttCell / FttOct structures.  Gerris moves the data blocks only when it grows
+ * them for a new variable (gfs_domain_alloc -> box_realloc, src/domain.c:3291-3305): the caller
+ * passes any value that changes when that happens (domain->allocated->len) as `generation', and the
+ * cache is rebuilt when it differs from the one it was built with. */
+int gfsb200_ftt_map_cache_data (gfsb200_ftt_map * m, unsigned generation);
+
 /* GFS_VALUEI (cell_i, var) = in[i]; leaves_only: only the leaves of the GfsBox trees, the
  * cells gfs_domain_cell_traverse (FTT_TRAVERSE_LEAFS) visits (ghost cells keep their value) */
 int gfsb200_ftt_scatter (const gfsb200_ftt_map * m, size_t offset, int var, int leaves_only,

@@ -16,6 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 FORCE_DRAG, FORCE_LIFT, FORCE_BUOY, FORCE_INERTIAL, FORCE_ADDEDMASS = 1, 2, 3, 4, 5
 KERNEL_CONSTANT, KERNEL_GAUSSIAN, KERNEL_COMPACT = 0, 1, 2
+KERNEL_ODD = 3            # a/(1 + b r^2): reference object code only (libgfsrefobj / libgfsrefmod)
 
 
 class Kernel(C.Structure):
@@ -331,6 +332,9 @@ def load_refobj(dim: int, module: bool = False) -> C.CDLL:
         "refobj_locate_array": (None, [vp, vp, vp, vp]),
         "refobj_sim_time": (None, [vp, C.POINTER(dbl), C.POINTER(i32)]),
         "refobj_sim_add_solid": (None, [vp, i32]),
+        "refobj_sim_refine": (i32, [vp, vp]),
+        "refobj_sim_coarsen": (i32, [vp, vp]),
+        "refobj_sim_destroy_cell": (i32, [vp, vp]),
         "refobj_list_new": (vp, [vp, lng] + [vp] * 8 + [C.POINTER(StepParams)]),
         "refobj_list_destroy": (None, [vp]),
         "refobj_list_size": (lng, [vp]),
@@ -402,6 +406,18 @@ class RefSim:
         """an entry in sim->solids, as a GfsSolid (or GfsSolidMoving) declaration leaves"""
         self.R.refobj_sim_add_solid(self.h, int(moving))
 
+    def refine(self, cell: int) -> bool:
+        """ftt_cell_refine_single + gfs_cell_fine_init on a leaf (FttCell*): what an adapt does"""
+        return bool(self.R.refobj_sim_refine(self.h, C.c_void_p(int(cell))))
+
+    def destroy_cell(self, cell: int) -> bool:
+        """ftt_cell_destroy: an entirely solid cell (what gfs_init_solid_fractions does)"""
+        return bool(self.R.refobj_sim_destroy_cell(self.h, C.c_void_p(int(cell))))
+
+    def coarsen(self, cell: int) -> bool:
+        """ftt_cell_coarsen + gfs_cell_cleanup of the children of a non-leaf cell"""
+        return bool(self.R.refobj_sim_coarsen(self.h, C.c_void_p(int(cell))))
+
     def time(self):
         t, i = C.c_double(), C.c_int()
         self.R.refobj_sim_time(self.h, C.byref(t), C.byref(i))
@@ -457,7 +473,11 @@ class RefParticleList:
         self.R.refobj_force(self.h, index, k, _p(f))
         return f
 
-    def get(self):
+    def get(self, sync=True):
+        """the state held by the GfsParticulate objects.  sync: call gfsb200_module_sync first, as
+        host code reading the objects of a device-resident list has to (a no-op in the reference)"""
+        if sync:
+            self.sync()
         n = len(self)
         out = {k: np.empty(n) for k in ("x", "y", "z", "vx", "vy", "vz", "fx", "fy", "fz", "mass")}
         ids = np.empty(n, dtype=np.uint32)

@@ -727,6 +727,25 @@ GfsVariableClass * gfs_variable_class (void)
   return klass;
 }
 
+/* gfs_variable_new, src/variable.c:140-181, for the harness: the cells of a RefSim carry a fixed
+ * number of value slots (the oracle allocated them), so a variable added at run time -- the
+ * drop-in module's unnamed mesh-watch variable, which never reads or writes its slot -- shares the
+ * last one instead of growing every cell (gfs_domain_alloc).  The callbacks start out unset: the
+ * harness' refinement copies the parent's values (refobj_sim_refine below). */
+GfsVariable * gfs_variable_new (GfsVariableClass * klass, GfsDomain * domain, const gchar * name,
+				const gchar * description)
+{
+  GfsVariable * v = GFS_VARIABLE (gts_object_new (GTS_OBJECT_CLASS (klass)));
+  GSList * last = domain->variables;
+  g_return_val_if_fail (last != NULL, NULL);
+  while (last->next) last = last->next;
+  gfs_object_simulation_set (v, domain);
+  v->i = GFS_VARIABLE (last->data)->i;
+  v->domain = domain;
+  v->name = name ? g_strdup (name) : NULL;
+  return v;
+}
+
 /* src/variable.c:183-191 */
 GfsVariable * gfs_variable_from_name (GSList * i, const gchar * name)
 {
@@ -1128,6 +1147,71 @@ REF_EXPORT void refobj_sim_add_solid (RefSim * s, int moving)
 
 /* gfs_domain_locate (src/domain.c:2623-2638 over the GfsLocateArray of :43-145), the
    reference's own object code, for n points */
+/* --- mesh adaptation, as gfs_simulation_adapt leaves it (src/adaptive.c) ----------------------
+ * refine: ftt_cell_refine_single (face 2:1 balance included) with the cell initialisation of
+ * gfs_cell_fine_init (src/domain.c:2979-3010) for the harness' fixed-size payload -- the children
+ * get the parent's values, then every variable's coarse_fine method runs;
+ * coarsen: ftt_cell_coarsen with gfs_cell_cleanup (src/fluid.c:1965-1985): every variable's
+ * cleanup method, then the payload is freed. */
+static void ref_cell_fine_init (FttCell * parent, RefSim * s)
+{
+  FttCellChildren child;
+  guint n;
+  GSList * i;
+  const size_t bytes = sizeof (GfsStateVector) + (s->nvar - 1)*sizeof (gdouble);
+  ftt_cell_children (parent, &child);
+  for (n = 0; n < FTT_CELLS; n++)
+    if (child.c[n]) {
+      child.c[n]->data = g_malloc0 (bytes);
+      memcpy (child.c[n]->data, parent->data, bytes);
+      GFS_STATE (child.c[n])->solid = NULL;
+    }
+  for (i = GFS_DOMAIN (s)->variables; i; i = i->next) {
+    GfsVariable * v = i->data;
+    if (v->coarse_fine)
+      (* v->coarse_fine) (parent, v);
+  }
+}
+
+static void ref_cell_cleanup (FttCell * cell, RefSim * s)
+{
+  GSList * i;
+  if (cell->data)
+    for (i = GFS_DOMAIN (s)->variables; i; i = i->next) {
+      GfsVariable * v = i->data;
+      if (v->cleanup)
+	(* v->cleanup) (cell, v);
+    }
+  g_free (cell->data);
+  cell->data = NULL;
+}
+
+static gboolean coarsen_always (FttCell * cell, gpointer data) { return TRUE; }
+
+REF_EXPORT int refobj_sim_refine (RefSim * s, FttCell * cell)
+{
+  if (!cell || !FTT_CELL_IS_LEAF (cell))
+    return 0;
+  ftt_cell_refine_single (cell, (FttCellInitFunc) ref_cell_fine_init, s);
+  return 1;
+}
+
+/* an entirely solid cell, as gfs_init_solid_fractions leaves it: destroyed (src/solid.c:833) */
+REF_EXPORT int refobj_sim_destroy_cell (RefSim * s, FttCell * cell)
+{
+  if (!cell || FTT_CELL_IS_ROOT (cell))
+    return 0;
+  ftt_cell_destroy (cell, (FttCellCleanupFunc) ref_cell_cleanup, s);
+  return 1;
+}
+
+REF_EXPORT int refobj_sim_coarsen (RefSim * s, FttCell * cell)
+{
+  if (!cell || FTT_CELL_IS_LEAF (cell))
+    return 0;
+  return ftt_cell_coarsen (cell, coarsen_always, NULL, (FttCellCleanupFunc) ref_cell_cleanup, s);
+}
+
 REF_EXPORT void refobj_locate (RefSim * s, long n, const double * x, const double * y, const double * z,
 			       void ** cell)
 {
@@ -1381,6 +1465,7 @@ static gdouble kernel_spatial (gdouble x, gdouble y, gdouble z, gpointer data)
     for (i = 0; i < k->p; i++) v *= t;
     return v;
   }
+  case 3: return k->a/(1. + k->b*r2);     /* none of the closed forms of gfsb200.h: stays on the host */
   }
   g_assert_not_reached ();
   return 0.;

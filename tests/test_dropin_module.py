@@ -63,12 +63,19 @@ def check(got, want, dim, rtol, what):
     assert np.abs(got["mass"][go] - want["mass"][wo]).max() <= 1e-14 * np.abs(want["mass"]).max(), what
 
 
+@pytest.mark.parametrize("resident", ["0", None])
 @pytest.mark.parametrize("kind", ["c1", "uniform3", "ring3", "ring2", "ring3b", "chain2", "chain3"])
-def test_module_particle_list_event(kind):
+def test_module_particle_list_event(kind, resident, monkeypatch):
     """GfsParticleList.event re-pointed by the module: flatten the live FttCell
     trees, mirror U,V,W, cull + fused step on the device, state written back into the
     GfsParticulate objects, gfs_particle_bc on the host -- against the reference's own
-    gfs_particle_list_event over 3 steps"""
+    gfs_particle_list_event over 3 steps.  resident "0": the objects are written back after every
+    event (GFSB200_RESIDENT=0); None: the default, the device copy is authoritative and the
+    harness reads the objects through gfsb200_module_sync"""
+    if resident is None:
+        monkeypatch.delenv("GFSB200_RESIDENT", raising=False)
+    else:
+        monkeypatch.setenv("GFSB200_RESIDENT", resident)
     w, sim, ptrs = setup(kind)
     parts = helpers.test_particles(w, 4000)
     parts["x"][::97] = 5.0                      # a few particles outside: culled by both
@@ -256,7 +263,7 @@ def run_resident(sim, parts, par, steps, record_at, periodic_mask=0):
     for step in range(1, steps + 1):
         assert rl.event() == 1
         if step == 1:
-            stale = rl.get()                      # NOT synced: what a careless reader would see
+            stale = rl.get(sync=False)            # NOT synced: what a careless reader would see
         if step in record_at:
             assert rl.sync()
             out[step] = rl.get()
@@ -266,10 +273,10 @@ def run_resident(sim, parts, par, steps, record_at, periodic_mask=0):
 
 @pytest.mark.parametrize("kind", ["uniform3", "ring2", "chain3"])
 def test_module_resident_mode(kind, monkeypatch, tmp_path):
-    """$GFSB200_RESIDENT=1: the device copy is authoritative between events (no object gather /
-    scatter per event); gfsb200_module_sync, the list's write method and the reference's own
-    reader classes refresh the objects on demand"""
-    monkeypatch.setenv("GFSB200_RESIDENT", "1")
+    """resident mode (the default since round 2; GFSB200_RESIDENT=0 turns it off): the device copy
+    is authoritative between events (no object gather / scatter per event); gfsb200_module_sync,
+    the list's write method and the reference's own reader classes refresh the objects on demand"""
+    monkeypatch.delenv("GFSB200_RESIDENT", raising=False)
     w, sim, ptrs = setup(kind)
     parts = helpers.test_particles(w, 3000)
     par = helpers.oracle_params(w)
@@ -385,3 +392,113 @@ def test_module_with_embedded_solids(kind):
     finally:
         for i in mixed:
             sim.set_solid(ptrs[i], 0.0, np.zeros(3))
+
+
+# ---------------------------------------------------------------------------
+# round 2: mesh identity, solid cells, the no-fallback policy
+
+@pytest.mark.parametrize("resident", ["0", None])
+def test_module_reflattens_after_every_adapt(resident, monkeypatch):
+    """the mesh changes between events -- cells refined (gfs_cell_fine_init) and
+    coarsened (gfs_cell_cleanup) as gfs_simulation_adapt does, twice with the SAME created /
+    removed counts, i.e. exactly the case sim->adapts_stats cannot tell apart -- and the module must
+    flatten the live tree again each time (its hidden variable's coarse_fine / cleanup methods see
+    every refined and destroyed cell).  A stale flat tree would interpolate with the old stencils
+    and its map would point at freed FttCells."""
+    if resident is None:
+        monkeypatch.delenv("GFSB200_RESIDENT", raising=False)
+    else:
+        monkeypatch.setenv("GFSB200_RESIDENT", resident)
+    w = helpers.test_world("ring3")
+    parts = helpers.test_particles(w, 3000)
+    par = helpers.oracle_params(w)
+    a = w.arrays
+    # coarse leaves of the box, away from the hull (their neighbours exist), in flat order
+    cand = [i for i in a.box_leaves if a.level[i] == 3 and np.all(np.abs(a.pos[i]) < 0.3)][:24]
+    assert len(cand) == 24
+    states = {}
+    for module in (False, True):
+        sim, ptrs = helpers.matched_oracle(w)          # one tree per run: the adapts are destructive
+        rs = ora.RefSim(sim, module=module)
+        rs.configure(par)
+        rl = ora.RefParticleList(rs, *[parts[k] for k in KEYS], par)
+        out = []
+        for step in range(6):
+            if step in (1, 2):                          # two adapts, 8 cells refined in each
+                for i in cand[8 * (step - 1):8 * step]:
+                    assert rs.refine(ptrs[i])
+            if step == 4:                               # and a coarsening
+                for i in cand[:4]:
+                    assert rs.coarsen(ptrs[i])
+            assert rl.event() == 1
+            out.append(rl.get())
+        rs.close()
+        states[module] = out
+    for step in range(6):
+        check(states[True][step], states[False][step], 3, 1e-12 if step == 0 else 1e-11, ("adapt", step))
+
+
+def test_module_particle_in_a_solid_cell_is_culled_not_fatal(monkeypatch):
+    """with entirely solid (destroyed) cells inside the box the hull test does
+    not decide whether a particle is still in the domain.  A particle that steps into a solid cell
+    must leave the list through gfs_particle_bc in the same event, as in the reference
+    (modules/particulatecommon.c:3333-3335) -- in resident mode too, where round 1 aborted."""
+    monkeypatch.delenv("GFSB200_RESIDENT", raising=False)
+    w = helpers.test_world("ring3")
+    a = w.arrays
+    # a coarse leaf well inside the box becomes entirely solid
+    nbr = a.neighbor.reshape(a.n_cells, 6)
+    dead = next(int(i) for i in a.box_leaves if a.level[i] == 3 and np.all(np.abs(a.pos[i]) < 0.32) and
+                nbr[i, 0] >= 0 and a.level[nbr[i, 0]] == 3 and a.child0[nbr[i, 0]] < 0)
+    parts = helpers.test_particles(w, 400)
+    # a handful of particles right next to the solid cell, moving into it
+    h = a.h[dead]
+    for j in range(10):
+        parts["x"][j] = a.pos[dead, 0] + 0.6 * h
+        parts["y"][j] = a.pos[dead, 1] + (j - 5) * 0.05 * h
+        parts["z"][j] = a.pos[dead, 2]
+        parts["vx"][j], parts["vy"][j], parts["vz"][j] = -0.5 * h / w.dt, 0.0, 0.0
+    par = helpers.oracle_params(w)
+    res = {}
+    for module in (False, True):
+        sim, ptrs = helpers.matched_oracle(w)
+        rs = ora.RefSim(sim, module=module)
+        rs.configure(par)
+        assert rs.destroy_cell(ptrs[dead])
+        rl = ora.RefParticleList(rs, *[parts[k] for k in KEYS], par)
+        out = []
+        for step in range(4):
+            assert rl.event() == 1
+            out.append(rl.get())
+        rs.close()
+        res[module] = out
+    assert len(res[False][0]["x"]) <= 390                     # the reference dropped them in event 1
+    for step in range(4):
+        assert len(res[True][step]["x"]) == len(res[False][step]["x"]), step
+        check(res[True][step], res[False][step], 3, 1e-11, ("solid cell", step))
+
+
+def test_module_unknown_kernel_needs_the_opt_in(monkeypatch):
+    """a smoothing kernel outside the closed forms: with GFSB200_ALLOW_REFERENCE_EVENT=1 the
+    reference's own event runs (one warning), and the result is the reference's, bit for bit"""
+    monkeypatch.setenv("GFSB200_ALLOW_REFERENCE_EVENT", "1")
+    w, sim, ptrs = setup("c1")
+    a = w.arrays
+    parts = helpers.test_particles(w, 300)
+    par = helpers.oracle_params(w)
+    live = (a.flags & capi.CELL_DESTROYED) == 0
+    k = ora.Kernel(ora.KERNEL_ODD, 1.0, 2e-4, 1, 0) if hasattr(ora, "KERNEL_ODD") else None
+    if k is None:
+        pytest.skip("the harness has no kernel outside the closed forms")
+    res = []
+    for module in (False, True):
+        for iv in range(4, 4 + w.dim):
+            sim.set_values(iv, ptrs[live], np.full(int(live.sum()), 3.0))
+        rs = ora.RefSim(sim, module=module)
+        rs.configure(par)
+        rl = ora.RefParticleList(rs, *[parts[q] for q in KEYS], par)
+        rl.source_event(4, 0.06, k)
+        res.append([sim.get_values(4 + c, ptrs[live]) for c in range(w.dim)])
+        rs.close()
+    for c in range(w.dim):
+        assert np.array_equal(res[0][c], res[1][c])

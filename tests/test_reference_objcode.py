@@ -349,14 +349,15 @@ def test_reference_object_code_reproduces_golden(path):
 
 
 @pytest.mark.skipif(not ora.refobj_available(3, module=True), reason="libgfsrefmod not built")
-def test_dropin_module_loads_and_hands_back_what_the_device_cannot_do():
+def test_dropin_module_loads_and_hands_back_what_the_device_cannot_do(monkeypatch):
     """libgfsrefmod = the reference objects + the drop-in GModule source
     (host/particulates_b200.c) linked as a Gerris installation would.  Its
     g_module_check_init() instantiates the 16 classes and re-points the three
     hot-path events.  A simulation with MOVING solids (fractions change every step
-    without an adapt) is not expressible on the device: the module must hand the event back to the
-    reference's own method, untouched -- checked here without a GPU against the
-    unmodified library."""
+    without an adapt) is not expressible on the device: with GFSB200_ALLOW_REFERENCE_EVENT=1 the
+    module hands the event back to the reference's own method, untouched -- checked here without a
+    GPU against the unmodified library (without the opt-in it stops the run: next test)."""
+    monkeypatch.setenv("GFSB200_ALLOW_REFERENCE_EVENT", "1")
     w, sim, ptrs = setup("ring3")
     parts = helpers.test_particles(w, 800)
     par = helpers.oracle_params(w)
@@ -374,6 +375,41 @@ def test_dropin_module_loads_and_hands_back_what_the_device_cannot_do():
         rs.close()
     for step in range(2):
         assert_same_state(states[0][step], states[1][step], 3, step)
+
+
+_NO_FALLBACK = r"""
+import sys
+sys.path.insert(0, %(tests)r)
+import helpers
+from helpers import ora
+KEYS = ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")
+w = helpers.test_world("ring3")
+sim, ptrs = helpers.matched_oracle(w)
+parts = helpers.test_particles(w, 50)
+par = helpers.oracle_params(w)
+rs = ora.RefSim(sim, module=True)
+rs.configure(par)
+rs.add_solid(moving=True)
+rl = ora.RefParticleList(rs, *[parts[k] for k in KEYS], par)
+print("before the event", flush=True)
+rl.event()
+print("the event returned", flush=True)
+"""
+
+
+@pytest.mark.skipif(not ora.refobj_available(3, module=True), reason="libgfsrefmod not built")
+def test_dropin_module_has_no_silent_cpu_fallback():
+    """the default: a list the device cannot run stops the simulation (g_error -> abort) with a
+    message naming the object and the reason; nothing runs on the CPU behind the user's back"""
+    import subprocess
+    import sys
+    env = {k: v for k, v in os.environ.items() if k != "GFSB200_ALLOW_REFERENCE_EVENT"}
+    r = subprocess.run([sys.executable, "-c", _NO_FALLBACK % {"tests": os.path.dirname(os.path.abspath(__file__))}],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert "before the event" in r.stdout and "the event returned" not in r.stdout
+    assert r.returncode != 0
+    assert "GfsParticleList" in r.stderr and "moving solids" in r.stderr
+    assert "no silent CPU fallback" in r.stderr and "GFSB200_ALLOW_REFERENCE_EVENT" in r.stderr
 
 
 @pytest.mark.parametrize("kind", ["c1", "uniform3", "ring3", "ring2", "ring3b", "chain2", "chain3", "periodic2",
