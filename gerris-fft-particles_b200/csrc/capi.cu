@@ -273,6 +273,7 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
   std::vector<int32_t> child0 (n);
   std::vector<uint8_t> info (n);
   bool any_destroyed = false;
+  int32_t leaf_lo = -1, leaf_hi = 0;
   for (int32_t i = 0; i < n; i++) {
     child0[i] = (t->flags[i] & GFSB200_CELL_DESTROYED) ? CHILD_DESTROYED :
       (t->child0[i] < 0 ? CHILD_LEAF : t->child0[i]);
@@ -288,6 +289,10 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
 	regular = 0;
     }
     info[i] = (uint8_t) ((t->flags[i] & 7) | regular | (k << 4));
+    if ((t->flags[i] & GFSB200_CELL_LEAF) && !(t->flags[i] & GFSB200_CELL_BOUNDARY)) {
+      if (leaf_lo < 0) leaf_lo = i;
+      leaf_hi = i + 1;
+    }
     if ((t->flags[i] & GFSB200_CELL_DESTROYED) && !(t->flags[i] & GFSB200_CELL_BOUNDARY))
       any_destroyed = true;
   }
@@ -335,6 +340,8 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
   T.la_h = t->la_h;
   T.single_box = t->la_size == 1 && t->la_slot[0] == 0;
   T.has_destroyed = any_destroyed;
+  c->leaf_lo = leaf_lo < 0 ? 0 : leaf_lo;
+  c->leaf_hi = leaf_hi;
   T.la_slot = c->d_la_slot;
   T.child0 = c->d_child0; T.neighbor = c->d_neighbor; T.level = c->d_level; T.info = c->d_info;
   T.n_vertices = t->n_vertices;

@@ -920,10 +920,21 @@ extern "C" int gfsb200_comm_prepare_deposit (gfsb200_comm * m, int what, bool lo
     }
     D->own_lo = lo; D->own_hi = hi;
     D->peers = m->nranks > 1 ? m->d_owners + t : NULL;
+    D->local_gpu_scope = getenv ("GFSB200_LOCAL_RED_GPU_SCOPE") != NULL;
   }
   m->dep_mode = mode;
   m->dep_done |= what;
   return GFSB200_OK;
+}
+
+/* the part of the rank's slice a deposit can reach: slices partition ALL cells, but only leaves of
+   the GfsBox trees receive anything -- nothing else needs clearing or pushing (on a uniform tree
+   the first slice would otherwise carry every non-leaf level along) */
+static void slice_leaves (const gfsb200_comm * m, int32_t * lo, int32_t * hi)
+{
+  *lo = m->split[m->rank] > m->c->leaf_lo ? m->split[m->rank] : m->c->leaf_lo;
+  *hi = m->split[m->rank + 1] < m->c->leaf_hi ? m->split[m->rank + 1] : m->c->leaf_hi;
+  if (*hi < *lo) *hi = *lo;
 }
 
 static int stat_begin (gfsb200_comm * m)
@@ -970,7 +981,8 @@ extern "C" int gfsb200_deposit_allreduce (gfsb200_comm * const * local, int n_lo
 	 whole step to drain, so the wait below is normally already satisfied. */
       const int o = 1 - c->dep_which;
       const size_t n = c->T.n_cells;
-      const int32_t lo = m->split[m->rank], hi = m->split[m->rank + 1];
+      int32_t lo, hi;
+      slice_leaves (m, &lo, &hi);
       if (m->x_pending[o])
 	CK (cudaStreamWaitEvent (c->stream, m->ev_x[o], 0));     /* (stays pending for gfsb200_deposit_wait) */
       if (hi > lo)
@@ -1001,7 +1013,8 @@ extern "C" int gfsb200_deposit_allreduce (gfsb200_comm * const * local, int n_lo
       gfsb200_ctx * c = m->c;
       const int t = c->dep_which;
       const size_t n = c->T.n_cells;
-      const int32_t lo = m->split[m->rank], hi = m->split[m->rank + 1];
+      int32_t lo, hi;
+      slice_leaves (m, &lo, &hi);
       CK (cudaSetDevice (c->device));
       PeerFlags pf;
       for (int q = 0; q < GFSB200_MAX_RANKS; q++) pf.p[q] = q < R ? m->peer_flags[q] : NULL;

@@ -69,6 +69,7 @@ struct gfsb200_ctx {
   int64_t deposit_count;
   gfsb200_comm * comm;         /* attached by gfsb200_comm_init_*; owns the exchange of the deposit */
   int64_t tree_generation;     /* bumped by gfsb200_upload_tree (the deposit buffers are reallocated) */
+  int32_t leaf_lo, leaf_hi;    /* the leaves of the GfsBox trees -- the only cells a deposit can reach -- lie in [leaf_lo, leaf_hi) */
   double * scratch;            /* pooled device scratch of the batched point queries */
   size_t scratch_bytes;
   double * knorm;              /* [2][knorm_n] correction, volume of the last smoothed deposit */

@@ -120,6 +120,8 @@ struct DevDeposit {
   int64_t n_cells;
   int32_t own_lo, own_hi;      /* cells [own_lo, own_hi) are this rank's: plain local atomics */
   const DevOwners * peers;     /* device memory; NULL: one rank, everything is local */
+  int local_gpu_scope;         /* experiment (GFSB200_LOCAL_RED_GPU_SCOPE): reductions into the own slice at GPU
+				  scope even though peers reduce into it at system scope */
 };
 
 /* compact every third (second) bit of a Morton key back into an integer */

@@ -609,9 +609,10 @@ __device__ __forceinline__ void run_deposit (const DevDeposit & D, int cell, dou
     }
   }
   if (head && cell >= 0) {
-    double * dst = owner_base (D, cell) + cell;
+    double * base = owner_base (D, cell);
+    double * dst = base + cell;
     /* with several ranks every slice also receives reductions from its peers' SMs: system scope */
-    const bool sys = D.peers != NULL;
+    const bool sys = D.peers != NULL && !(D.local_gpu_scope && base == D.local);
     if (VOL) red_add (dst, av, sys);
     if (FORCE) {
       red_add (dst + D.n_cells, ax, sys);

@@ -34,7 +34,8 @@
  * GFSB200_ALLOW_REFERENCE_EVENT=1 opts in to the reference's own CPU event for exactly those
  * objects, with one g_warning per object.
  *
- * Environment: GFSB200_DEVICE=<n> (device of a single-GPU run, default 0),
+ * Environment: GFSB200_DEVICE=<n> (first device, default 0), GFSB200_DEVICES=<n> (GPUs of the box
+ * one serial gerris drives, default 1),
  * GFSB200_RESIDENT=0 (write every particle back into its GfsParticulate after every event; by
  * default the device copy is authoritative between events and the objects are refreshed when
  * something on the host is about to look at them), GFSB200_MODULE_PROFILE=1.
@@ -52,8 +53,18 @@
 /* ------------------------------------------------------------------ */
 /* per-list device state, hung on the GtsObject through g_object data  */
 
+#define B200_MAX_DEV 16
+
 typedef struct {
-  gfsb200_ctx * ctx;
+  gfsb200_ctx * ctx;                    /* = dev[0] */
+  /* GFSB200_DEVICES=n: one serial gerris drives n GPUs of the box -- the list is sharded over them
+     (gfsb200_comm_rebalance), tree and field are replicated (gfsb200_broadcast_field), deposits
+     are summed (gfsb200_deposit_allreduce) before they are scattered into the cells */
+  gint n_dev;
+  gfsb200_ctx * dev[B200_MAX_DEV];
+  gfsb200_comm * comm[B200_MAX_DEV];
+  gint32 * idx_of_id;                   /* n_dev > 1: object index by particle id (the devices reorder the list) */
+  guint32 idx_cap;
   gfsb200_tree * tree;
   gfsb200_ftt_map * map;
   guint mesh_epoch;                     /* b200_mesh_epoch when the tree was flattened */
@@ -131,12 +142,26 @@ static B200State * state_of (GfsParticleList * plist)
     b200_states = g_hash_table_new (NULL, NULL);
   s = g_hash_table_lookup (b200_states, plist);
   if (!s) {
-    int device = 0;
+    int device = 0, k;
     const gchar * env = g_getenv ("GFSB200_DEVICE");
     s = g_malloc0 (sizeof (B200State));
     if (env) device = atoi (env);
-    if (gfsb200_ctx_create (device, &s->ctx) != GFSB200_OK)
-      g_error ("particulates (B200): %s", gfsb200_last_error ());   /* no CPU fallback */
+    s->n_dev = g_getenv ("GFSB200_DEVICES") ? atoi (g_getenv ("GFSB200_DEVICES")) : 1;
+    if (s->n_dev < 1 || s->n_dev > B200_MAX_DEV || device + s->n_dev > MAX (gfsb200_device_count (), 1))
+      g_error ("particulates (B200): GFSB200_DEVICES=%d from device %d, but the process sees %d device(s)",
+	       s->n_dev, device, gfsb200_device_count ());
+    for (k = 0; k < s->n_dev; k++)
+      if (gfsb200_ctx_create (device + k, &s->dev[k]) != GFSB200_OK)
+	g_error ("particulates (B200): %s", gfsb200_last_error ());   /* no CPU fallback */
+    s->ctx = s->dev[0];
+    if (s->n_dev > 1) {
+      if (gfsb200_comm_init_all (s->n_dev, s->dev, s->comm) != GFSB200_OK)
+	g_error ("particulates (B200): %s", gfsb200_last_error ());
+      /* the smoothed deposit of GfsSourceParticulate reaches cells of every slice: whole-buffer sums */
+      for (k = 0; k < s->n_dev; k++)
+	if (gfsb200_comm_set_exchange (s->comm[k], GFSB200_EXCHANGE_ALLREDUCE) != GFSB200_OK)
+	  g_error ("particulates (B200): %s", gfsb200_last_error ());
+    }
     s->plist = plist;
     /* the device copy is authoritative between events unless GFSB200_RESIDENT=0 */
     s->resident = !(g_getenv ("GFSB200_RESIDENT") && atoi (g_getenv ("GFSB200_RESIDENT")) == 0);
@@ -250,7 +275,11 @@ static void b200_particle_list_destroy (GtsObject * o)
 	       1e3*s->phase[PH_DOWNLOAD]/s->n_events, 1e3*s->phase[PH_BC]/s->n_events);
     if (s->map) gfsb200_ftt_map_free (s->map);
     if (s->tree) gfsb200_tree_free (s->tree);
-    if (s->ctx) gfsb200_ctx_destroy (s->ctx);
+    for (k = 0; k < s->n_dev; k++)
+      if (s->comm[k]) gfsb200_comm_destroy (s->comm[k]);
+    for (k = 0; k < s->n_dev; k++)
+      if (s->dev[k]) gfsb200_ctx_destroy (s->dev[k]);
+    g_free (s->idx_of_id);
     for (c = 0; c < 3; c++)
       gfsb200_host_free (s->field[c]);
     gfsb200_host_free (s->cellvar[0]);
@@ -350,9 +379,11 @@ static void refresh_tree (B200State * s, GfsSimulation * sim)
   s->root_hash = hash;
   g_ptr_array_free (r.roots, TRUE);
   g_array_free (r.is_box, TRUE);
-  if (gfsb200_tree_build_stencils (s->tree) != GFSB200_OK ||
-      gfsb200_upload_tree (s->ctx, s->tree) != GFSB200_OK)
+  if (gfsb200_tree_build_stencils (s->tree) != GFSB200_OK)
     g_error ("particulates (B200): %s", gfsb200_last_error ());
+  for (k = 0; k < (guint) s->n_dev; k++)
+    if (gfsb200_upload_tree (s->dev[k], s->tree) != GFSB200_OK)
+      g_error ("particulates (B200): %s", gfsb200_last_error ());
   s->n_cells = gfsb200_ftt_map_size (s->map);
   if (s->n_cells > s->field_cap) {
     for (c = 0; c < 3; c++) {
@@ -394,10 +425,18 @@ static void mirror_velocity (B200State * s, GfsDomain * domain)
      the blocks to make room for a new variable): the per-event gather never touches the tree */
   if (gfsb200_ftt_map_cache_data (s->map, 1 + (domain->allocated ? domain->allocated->len : 0)) != GFSB200_OK)
     g_error ("particulates (B200): %s", gfsb200_ftt_last_error ());
-  {
+  if (s->n_dev > 1) {
+    /* one gather, ONE upload (device 0), NVLink to the other GPUs, cell pass everywhere */
+    gfsb200_ftt_gather_many (s->map, off, n, var, nodata, out);
+    if (gfsb200_broadcast_field (s->comm, s->n_dev, 0, s->field[0], s->field[1],
+				 FTT_DIMENSION > 2 ? s->field[2] : NULL,
+				 s->alpha_var ? s->cellvar[0] : NULL, s->mu_var ? s->cellvar[1] : NULL) != GFSB200_OK)
+      g_error ("particulates (B200): %s", gfsb200_last_error ());
+  }
+  else {
     /* in slices: while the copy engine ships slice k (page-locked staging, asynchronous), the host
        cores gather slice k + 1 out of the tree -- the upload hides behind the gather */
-    const gint32 slices = s->n_cells > (1 << 18) ? 8 : 1;
+    const gint32 slices = s->n_cells > (1 << 18) ? 4 : 1;
     gint32 k;
     for (k = 0; k < slices; k++) {
       const gint32 first = (gint32) ((gint64) s->n_cells*k/slices), last = (gint32) ((gint64) s->n_cells*(k + 1)/slices);
@@ -415,12 +454,15 @@ static void mirror_velocity (B200State * s, GfsDomain * domain)
       var[c] = s->uold[c]->i; nodata[c] = GFS_NODATA; out[c] = s->field[c];
     }
     /* the staging buffers are reused: the first upload must have left them */
-    if (gfsb200_ctx_synchronize (s->ctx) != GFSB200_OK)
-      g_error ("particulates (B200): %s", gfsb200_last_error ());
+    gint d;
+    for (d = 0; d < s->n_dev; d++)
+      if (gfsb200_ctx_synchronize (s->dev[d]) != GFSB200_OK)
+	g_error ("particulates (B200): %s", gfsb200_last_error ());
     gfsb200_ftt_gather_many (s->map, off, FTT_DIMENSION, var, nodata, out);
-    if (gfsb200_upload_field_prev (s->ctx, s->field[0], s->field[1],
-				   FTT_DIMENSION > 2 ? s->field[2] : NULL) != GFSB200_OK)
-      g_error ("particulates (B200): %s", gfsb200_last_error ());
+    for (d = 0; d < s->n_dev; d++)
+      if (gfsb200_upload_field_prev (s->dev[d], s->field[0], s->field[1],
+				     FTT_DIMENSION > 2 ? s->field[2] : NULL) != GFSB200_OK)
+	g_error ("particulates (B200): %s", gfsb200_last_error ());
   }
 }
 
@@ -644,20 +686,62 @@ static gint64 upload_particles (B200State * s, GfsParticleList * plist)
     col[6][k] = q->mass;  col[7][k] = q->volume;
     s->id[k] = p->id;
   }
-  if (gfsb200_particles_upload (s->ctx, n, col[0], col[1], FTT_DIMENSION > 2 ? col[2] : NULL,
-				col[3], col[4], FTT_DIMENSION > 2 ? col[5] : NULL,
-				col[6], col[7], s->id) != GFSB200_OK)
-    g_error ("particulates (B200): %s", gfsb200_last_error ());
+  if (s->n_dev == 1) {
+    if (gfsb200_particles_upload (s->ctx, n, col[0], col[1], FTT_DIMENSION > 2 ? col[2] : NULL,
+				  col[3], col[4], FTT_DIMENSION > 2 ? col[5] : NULL,
+				  col[6], col[7], s->id) != GFSB200_OK)
+      g_error ("particulates (B200): %s", gfsb200_last_error ());
+    return n;
+  }
+  /* several GPUs: equal slices of the list go up, then the devices sort themselves into the
+     global cell order (every GPU ends with the particles of a contiguous range of cells).  The
+     devices no longer hold the list in object order: objects are found again by particle id. */
+  {
+    guint32 max_id = 0;
+    gint d;
+    for (k = 0; k < n; k++)
+      if (s->id[k] > max_id) max_id = s->id[k];
+    if ((gint64) max_id > 16*n + (1 << 20))
+      g_error ("particulates (B200): particle ids up to %u for %lld particles: too sparse for the id table "
+	       "of the multi-GPU mode", max_id, (long long) n);
+    if (max_id + 1 > s->idx_cap) {
+      g_free (s->idx_of_id);
+      s->idx_cap = max_id + 1 + max_id/8;
+      s->idx_of_id = g_malloc (sizeof (gint32)*s->idx_cap);
+    }
+    memset (s->idx_of_id, 0xff, sizeof (gint32)*s->idx_cap);
+    for (k = 0; k < n; k++) {
+      if (s->idx_of_id[s->id[k]] >= 0)
+	g_error ("particulates (B200): particle id %u appears twice in the list", s->id[k]);
+      s->idx_of_id[s->id[k]] = (gint32) k;
+    }
+    for (d = 0; d < s->n_dev; d++) {
+      const gint64 lo = n*d/s->n_dev, m = n*(d + 1)/s->n_dev - lo;
+      if (gfsb200_particles_upload (s->dev[d], m, col[0] + lo, col[1] + lo, FTT_DIMENSION > 2 ? col[2] + lo : NULL,
+				    col[3] + lo, col[4] + lo, FTT_DIMENSION > 2 ? col[5] + lo : NULL,
+				    col[6] + lo, col[7] + lo, s->id + lo) != GFSB200_OK)
+	g_error ("particulates (B200): %s", gfsb200_last_error ());
+    }
+    if (gfsb200_comm_rebalance (s->comm, s->n_dev) != GFSB200_OK)
+      g_error ("particulates (B200): %s", gfsb200_last_error ());
+  }
   return n;
 }
 
 /* write the device state back into the GtsObjects (s->obj holds them in upload order,
  * which the device keeps); particles the device culled (outside the domain) are removed
  * from the list as remove_particles_not_in_domain does (:955-969) */
+static void download_particles_multi (B200State * s, GfsParticleList * plist, gint64 n_up);
+
 static void download_particles (B200State * s, GfsParticleList * plist, gint64 n_up)
 {
-  gint64 n = gfsb200_particles_count (s->ctx), k, j;
+  gint64 n, k, j;
   gdouble ** col = s->col;
+  if (s->n_dev > 1) {
+    download_particles_multi (s, plist, n_up);
+    return;
+  }
+  n = gfsb200_particles_count (s->ctx);
   if (gfsb200_particles_download (s->ctx, col[0], col[1], FTT_DIMENSION > 2 ? col[2] : NULL,
 				  col[3], col[4], FTT_DIMENSION > 2 ? col[5] : NULL,
 				  col[6], col[7], col[8], col[9], NULL, s->id, NULL) != GFSB200_OK)
@@ -691,6 +775,66 @@ static void download_particles (B200State * s, GfsParticleList * plist, gint64 n
 #if !FTT_2D
     p->pos.z = col[2][k]; q->vel.z = col[5][k]; q->force.z = col[8][k];
 #endif
+  }
+}
+
+/* the same over several GPUs: the devices' lists, one behind the other, in whatever order the
+ * rebalance left them; every row finds its object through the id table */
+static void download_particles_multi (B200State * s, GfsParticleList * plist, gint64 n_up)
+{
+  gint64 n = 0, k, j;
+  gdouble ** col = s->col;
+  gint d;
+  for (d = 0; d < s->n_dev; d++) {
+    const gint64 m = gfsb200_particles_count (s->dev[d]);
+    if (n + m > s->part_cap)
+      g_error ("particulates (B200): the devices hold more particles than the list");
+    if (gfsb200_particles_download (s->dev[d], col[0] + n, col[1] + n, FTT_DIMENSION > 2 ? col[2] + n : NULL,
+				    col[3] + n, col[4] + n, FTT_DIMENSION > 2 ? col[5] + n : NULL,
+				    col[6] + n, col[7] + n, col[8] + n, col[9] + n, NULL, s->id + n, NULL) != GFSB200_OK)
+      g_error ("particulates (B200): %s", gfsb200_last_error ());
+    n += m;
+  }
+#pragma omp parallel for schedule(static)
+  for (k = 0; k < n; k++) {
+    const gint32 o = s->id[k] < s->idx_cap ? s->idx_of_id[s->id[k]] : -1;
+    if (o >= 0) {
+      GfsParticle * p = GFS_PARTICLE (s->obj[o]);
+      GfsParticulate * q = s->obj[o];
+      p->pos.x = col[0][k]; p->pos.y = col[1][k];
+      q->vel.x = col[3][k]; q->vel.y = col[4][k];
+      q->force.x = col[6][k]; q->force.y = col[7][k];
+      q->mass = col[9][k];
+#if !FTT_2D
+      p->pos.z = col[2][k]; q->vel.z = col[5][k]; q->force.z = col[8][k];
+#endif
+    }
+  }
+  if (n != n_up) {
+    /* culled on the devices: the objects whose id did not come back leave the list, order preserved */
+    guint8 * seen = g_malloc0 (n_up ? n_up : 1);
+    for (k = 0; k < n; k++) {
+      const gint32 o = s->id[k] < s->idx_cap ? s->idx_of_id[s->id[k]] : -1;
+      if (o < 0 || o >= n_up || seen[o])
+	g_error ("particulates (B200): the device lists and the GfsParticleList disagree");
+      seen[o] = 1;
+    }
+    for (k = 0, j = 0; k < n_up; k++) {
+      GfsParticle * p = GFS_PARTICLE (s->obj[k]);
+      if (seen[k]) {
+	s->idx_of_id[p->id] = (gint32) j;
+	s->obj[j++] = s->obj[k];
+      }
+      else {
+	s->idx_of_id[p->id] = -1;
+	gts_container_remove (GTS_CONTAINER (GFS_EVENT_LIST (plist)->list), GTS_CONTAINEE (p));
+	gts_object_destroy (GTS_OBJECT (p));
+      }
+    }
+    g_free (seen);
+    s->n_obj = n;
+    s->list_known = GTS_OBJECT (GFS_EVENT_LIST (plist)->list)->klass ==
+      GTS_OBJECT_CLASS (watched_container_class ());
   }
 }
 
@@ -778,16 +922,38 @@ static void b200_particle_list_write (GtsObject * o, FILE * fp)
  * gfs_particle_bc walks back from there (:3151-3186) */
 static void patch_pos_old (B200State * s, gint64 escaped)
 {
-  gint64 got = 0, e;
-  gint32 * idx = g_malloc (sizeof (gint32)*escaped);
-  gdouble * old = g_malloc (sizeof (gdouble)*3*escaped);
-  if (gfsb200_escaped_download (s->ctx, escaped, idx, old, &got) != GFSB200_OK)
-    g_error ("particulates (B200): %s", gfsb200_last_error ());
-  for (e = 0; e < got; e++)
-    if (idx[e] >= 0 && idx[e] < s->n_obj) {
-      GfsParticle * p = GFS_PARTICLE (s->obj[idx[e]]);
-      p->pos_old.x = old[3*e]; p->pos_old.y = old[3*e + 1]; p->pos_old.z = old[3*e + 2];
+  gint d;
+  gint32 * idx = g_malloc (sizeof (gint32)*(escaped ? escaped : 1));
+  gdouble * old = g_malloc (sizeof (gdouble)*3*(escaped ? escaped : 1));
+  for (d = 0; d < s->n_dev; d++) {
+    gint64 got = 0, e;
+    guint32 * ids = NULL;
+    if (gfsb200_escaped_download (s->dev[d], escaped, idx, old, &got) != GFSB200_OK)
+      g_error ("particulates (B200): %s", gfsb200_last_error ());
+    if (got == 0)
+      continue;
+    if (s->n_dev > 1) {
+      /* list positions are the device's: its ids lead to the objects */
+      const gint64 m = gfsb200_particles_count (s->dev[d]);
+      ids = g_malloc (sizeof (guint32)*(m ? m : 1));
+      if (gfsb200_particles_download (s->dev[d], NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL,
+				      NULL, NULL, ids, NULL) != GFSB200_OK)
+	g_error ("particulates (B200): %s", gfsb200_last_error ());
+      for (e = 0; e < got; e++)
+	if (idx[e] >= 0 && idx[e] < m) {
+	  const guint32 id = ids[idx[e]];
+	  idx[e] = id < s->idx_cap ? s->idx_of_id[id] : -1;
+	}
+	else
+	  idx[e] = -1;
+      g_free (ids);
     }
+    for (e = 0; e < got; e++)
+      if (idx[e] >= 0 && idx[e] < s->n_obj) {
+	GfsParticle * p = GFS_PARTICLE (s->obj[idx[e]]);
+	p->pos_old.x = old[3*e]; p->pos_old.y = old[3*e + 1]; p->pos_old.z = old[3*e + 2];
+      }
+  }
   g_free (idx);
   g_free (old);
 }
@@ -843,25 +1009,40 @@ static gboolean b200_particle_list_event (GfsEvent * event, GfsSimulation * sim)
      event (resident mode), in which the step kernel counted no particle leaving, and nothing on
      the host has touched the list since.  (It cannot simply run after the step instead: the
      particles that leave during this step must reach gfs_particle_bc, not the cull.) */
-  if (!(carried && par.track_escapes) &&
-      gfsb200_particles_cull (s->ctx, &removed) != GFSB200_OK)
-    g_error ("particulates (B200): %s", gfsb200_last_error ());
-  if (gfsb200_step (s->ctx, &par) != GFSB200_OK)
-    g_error ("particulates (B200): %s", gfsb200_last_error ());
+  if (!(carried && par.track_escapes))
+    for (k = 0; k < s->n_dev; k++) {
+      gint64 r = 0;
+      if (gfsb200_particles_cull (s->dev[k], &r) != GFSB200_OK)
+	g_error ("particulates (B200): %s", gfsb200_last_error ());
+      removed += r;
+    }
+  for (k = 0; k < s->n_dev; k++)
+    if (gfsb200_step (s->dev[k], &par) != GFSB200_OK)
+      g_error ("particulates (B200): %s", gfsb200_last_error ());
   if (par.track_escapes) {
     gint64 outside = 0;
-    if (gfsb200_step_counts (s->ctx, &escaped, &outside) != GFSB200_OK)
-      g_error ("particulates (B200): %s", gfsb200_last_error ());
+    for (k = 0; k < s->n_dev; k++) {
+      gint64 e = 0, o = 0;
+      if (gfsb200_step_counts (s->dev[k], &e, &o) != GFSB200_OK)
+	g_error ("particulates (B200): %s", gfsb200_last_error ());
+      escaped += e;
+      outside += o;
+    }
+    /* (before any compaction below: the record holds positions in the list as it was stepped) */
+    if (s->resident && escaped > 0)
+      patch_pos_old (s, escaped);
     if (outside > 0) {
       /* A carried-over list holds particles that are outside the domain (the escape count of the
 	 last event tests the box hull; a particle can also end up in a destroyed, i.e. solid,
 	 cell): the step has left them untouched; cull them now, as remove_particles_not_in_domain
 	 would have before the step, and let the objects follow */
-      if (gfsb200_particles_cull (s->ctx, &removed) != GFSB200_OK)
-	g_error ("particulates (B200): %s", gfsb200_last_error ());
+      for (k = 0; k < s->n_dev; k++) {
+	gint64 r = 0;
+	if (gfsb200_particles_cull (s->dev[k], &r) != GFSB200_OK)
+	  g_error ("particulates (B200): %s", gfsb200_last_error ());
+	removed += r;
+      }
     }
-    if (s->resident && escaped > 0)
-      patch_pos_old (s, escaped);
   }
   t[4] = wall ();
   if (s->resident && par.track_escapes && removed == 0 && escaped == 0 && s->list_known) {
@@ -915,6 +1096,7 @@ static gboolean b200_particulate_field_event (GfsEvent * event, GfsSimulation * 
   ListVars lv;
   B200State * s;
   gdouble * out;
+  gint k;
 
   const gchar * why = NULL;
   if (moving_solids (sim))
@@ -930,7 +1112,10 @@ static gboolean b200_particulate_field_event (GfsEvent * event, GfsSimulation * 
   adopt (s, &lv);
   refresh_tree (s, sim);
   device_current (s, pfield->plist);
-  if (gfsb200_deposit_volume (s->ctx) != GFSB200_OK)
+  for (k = 0; k < s->n_dev; k++)
+    if (gfsb200_deposit_volume (s->dev[k]) != GFSB200_OK)
+      g_error ("particulates (B200): %s", gfsb200_last_error ());
+  if (s->n_dev > 1 && gfsb200_deposit_allreduce (s->comm, s->n_dev) != GFSB200_OK)
     g_error ("particulates (B200): %s", gfsb200_last_error ());
   out = deposit_staging (s);
   if (gfsb200_download_deposit (s->ctx, 0, out) != GFSB200_OK)
@@ -964,6 +1149,7 @@ static gboolean b200_source_particulate_event (GfsEvent * event, GfsSimulation *
   gint64 n, k = 0;
   GSList * i;
   FttComponent c;
+  gint d;
 
   const gchar * why = NULL;
   if (moving_solids (sim))
@@ -988,7 +1174,10 @@ static gboolean b200_source_particulate_event (GfsEvent * event, GfsSimulation *
   mirror_velocity (s, GFS_DOMAIN (sim));
   n = device_current (s, sp->plist);
   kernel.record_norm = 0;
-  if (gfsb200_deposit_force_smoothed (s->ctx, &par, sp->rkernel, &kernel) != GFSB200_OK)
+  for (d = 0; d < s->n_dev; d++)
+    if (gfsb200_deposit_force_smoothed (s->dev[d], &par, sp->rkernel, &kernel) != GFSB200_OK)
+      g_error ("particulates (B200): %s", gfsb200_last_error ());
+  if (s->n_dev > 1 && gfsb200_deposit_allreduce (s->comm, s->n_dev) != GFSB200_OK)
     g_error ("particulates (B200): %s", gfsb200_last_error ());
   /* <plist>_Fx,_Fy,_Fz: gfs_cell_reset on the leaves + the scatter of diffuse_force */
   out = deposit_staging (s);
@@ -1005,14 +1194,39 @@ static gboolean b200_source_particulate_event (GfsEvent * event, GfsSimulation *
       force[c] = g_malloc (sizeof (gdouble)*(n ? n : 1));
     /* the on-fluid pass of a GfsForceAddedMass updates the particle mass too (compute_forces_onfluid
        -> :391): it comes back with the forces, or the next upload would undo it */
-    if (gfsb200_particles_download (s->ctx, NULL, NULL, NULL, NULL, NULL, NULL, force[0], force[1], force[2],
-  				  mass, NULL, NULL, NULL) != GFSB200_OK)
-      g_error ("particulates (B200): %s", gfsb200_last_error ());
-    for (i = GFS_EVENT_LIST (sp->plist)->list->items; i && k < n; i = i->next, k++) {
-      GfsParticulate * q = GFS_PARTICULATE (i->data);
-      q->force.x = force[0][k]; q->force.y = force[1][k];
-      q->force.z = FTT_DIMENSION > 2 ? force[2][k] : 0.;
-      q->mass = mass[k];
+    if (s->n_dev == 1) {
+      if (gfsb200_particles_download (s->ctx, NULL, NULL, NULL, NULL, NULL, NULL, force[0], force[1], force[2],
+				      mass, NULL, NULL, NULL) != GFSB200_OK)
+	g_error ("particulates (B200): %s", gfsb200_last_error ());
+      for (i = GFS_EVENT_LIST (sp->plist)->list->items; i && k < n; i = i->next, k++) {
+	GfsParticulate * q = GFS_PARTICULATE (i->data);
+	q->force.x = force[0][k]; q->force.y = force[1][k];
+	q->force.z = FTT_DIMENSION > 2 ? force[2][k] : 0.;
+	q->mass = mass[k];
+      }
+    }
+    else {
+      guint32 * ids = g_malloc (sizeof (guint32)*(n ? n : 1));
+      gint64 off = 0, j;
+      for (d = 0; d < s->n_dev; d++) {
+	const gint64 m = gfsb200_particles_count (s->dev[d]);
+	if (off + m > n)
+	  g_error ("particulates (B200): the device lists and the GfsParticleList disagree");
+	if (gfsb200_particles_download (s->dev[d], NULL, NULL, NULL, NULL, NULL, NULL, force[0] + off, force[1] + off,
+					force[2] + off, mass + off, NULL, ids + off, NULL) != GFSB200_OK)
+	  g_error ("particulates (B200): %s", gfsb200_last_error ());
+	off += m;
+      }
+      for (j = 0; j < off; j++) {
+	const gint32 o = ids[j] < s->idx_cap ? s->idx_of_id[ids[j]] : -1;
+	if (o >= 0 && o < s->n_obj) {
+	  GfsParticulate * q = s->obj[o];
+	  q->force.x = force[0][j]; q->force.y = force[1][j];
+	  q->force.z = FTT_DIMENSION > 2 ? force[2][j] : 0.;
+	  q->mass = mass[j];
+	}
+      }
+      g_free (ids);
     }
     for (c = 0; c < 3; c++)
       g_free (force[c]);

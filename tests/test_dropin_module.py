@@ -502,3 +502,88 @@ def test_module_unknown_kernel_needs_the_opt_in(monkeypatch):
         rs.close()
     for c in range(w.dim):
         assert np.array_equal(res[0][c], res[1][c])
+
+
+# ---------------------------------------------------------------------------
+# GFSB200_DEVICES=2: one serial process drives two GPUs (needs `gpurun --gpus 2`)
+
+def _two_gpus():
+    return capi.lib().gfsb200_device_count() >= 2
+
+
+@pytest.mark.skipif("not _two_gpus()", reason="needs two GPUs")
+@pytest.mark.parametrize("resident", ["0", None])
+@pytest.mark.parametrize("kind", ["c1", "ring3", "chain3"])
+def test_module_two_devices_list_field_and_source_events(kind, resident, monkeypatch):
+    """the list sharded over two GPUs by gfsb200_comm_rebalance (objects found again by particle
+    id), the field broadcast over NVLink, the deposits summed with gfsb200_deposit_allreduce before
+    they are scattered into the cells: list event (with culled particles), GfsParticulateField and
+    GfsSourceParticulate against the reference's own events"""
+    monkeypatch.setenv("GFSB200_DEVICES", "2")
+    if resident is None:
+        monkeypatch.delenv("GFSB200_RESIDENT", raising=False)
+    else:
+        monkeypatch.setenv("GFSB200_RESIDENT", resident)
+    w, sim, ptrs = setup(kind)
+    a = w.arrays
+    parts = helpers.test_particles(w, 5000)
+    parts["x"][::101] = 7.0                              # culled on whichever device holds them
+    par = helpers.oracle_params(w)
+    live = (a.flags & capi.CELL_DESTROYED) == 0
+    leaves = live & (a.child0 < 0) & ((a.flags & capi.CELL_BOUNDARY) == 0)
+    kern = ora.Kernel(ora.KERNEL_GAUSSIAN, 1.0, 2e-4, 1, 0)
+    res = {}
+    for module in (False, True):
+        for iv in range(3, 4 + w.dim):
+            sim.set_values(iv, ptrs[live], np.full(int(live.sum()), 5.0))
+        rs = ora.RefSim(sim, module=module)
+        rs.configure(par)
+        rl = ora.RefParticleList(rs, *[parts[k] for k in KEYS], par)
+        states = []
+        for step in range(3):
+            assert rl.event() == 1
+            states.append(rl.get())
+        rl.field_event(3)
+        vol = sim.get_values(3, ptrs[leaves])
+        rl.source_event(4, 0.05, kern)
+        src = [sim.get_values(4 + c, ptrs[leaves]) for c in range(w.dim)]
+        forces = rl.get()
+        rs.close()
+        res[module] = (states, vol, src, forces)
+    for step in range(3):
+        assert len(res[True][0][step]["x"]) == len(res[False][0][step]["x"]) < len(parts["x"])
+        check(res[True][0][step], res[False][0][step], w.dim, 1e-12 if step == 0 else 1e-11, (kind, step))
+    assert res[False][1].max() > 0
+    assert np.abs(res[True][1] - res[False][1]).max() <= 1e-12 * np.abs(res[False][1]).max()
+    for c in range(w.dim):
+        want, got = res[False][2][c], res[True][2][c]
+        assert np.abs(want).max() > 0
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max(), c
+    go, wo = np.argsort(res[True][3]["id"]), np.argsort(res[False][3]["id"])
+    for q in ("fx", "fy", "fz")[:w.dim]:
+        scale = max(np.abs(res[False][3][q]).max(), 1e-300)
+        assert np.abs(res[True][3][q][go] - res[False][3][q][wo]).max() <= 1e-10 * scale, q
+
+
+@pytest.mark.skipif("not _two_gpus()", reason="needs two GPUs")
+def test_module_two_devices_resident_with_boundaries(monkeypatch):
+    """two GPUs, resident mode, particles leaving all the time: pos_old of an escaped particle is
+    found through the device's ids, the host's gfs_particle_bc wraps or drops it"""
+    monkeypatch.setenv("GFSB200_DEVICES", "2")
+    monkeypatch.delenv("GFSB200_RESIDENT", raising=False)
+    w, mask = helpers.periodic_world(3)
+    sim, ptrs = helpers.matched_oracle(w)
+    rng = np.random.default_rng(9)
+    parts = worlds.make_particles(w, 600)
+    n = len(parts["x"])
+    for k in ("x", "y", "z"):
+        parts[k] = rng.uniform(-0.499, 0.499, n)
+    for k, f in zip(("vx", "vy", "vz"), (1.0, 1.0, 0.7)):
+        parts[k] = f * rng.standard_normal(n)
+    par = helpers.oracle_params(w)
+    want = run_list(sim, parts, par, 20, module=False, periodic_mask=mask)
+    got, _ = run_resident(sim, parts, par, 20, record_at=(5, 10, 20), periodic_mask=mask)
+    assert len(want[-1]["x"]) < n
+    for step in (5, 10, 20):
+        assert len(got[step]["x"]) == len(want[step - 1]["x"]), step
+        check(got[step], want[step - 1], 3, 1e-10, ("two devices, periodic", step))

@@ -563,6 +563,80 @@ def test_full_size_c2_properties(ctx):
     _check_state(sub_got, want, 3)
 
 
+@pytest.mark.parametrize("config", ["C3", "C5"])
+def test_full_size_adaptive_trees(config, ctx):
+    """BASELINE configs C3 (levels 5-9) and the C4/C5 tree (levels 6-10) at FULL depth, 10 M
+    particles: the corner-balanced refinement down to level 9 / 10 (ftt_refine_corner,
+    src/ftt.c:2013-2075) is where a flat-tree bug would hide.
+      * the native tree equals flatten(the tree the reference's own ftt.c builds), array by array
+        (helpers.matched_oracle asserts it);
+      * locate bit-exact against ftt_cell_locate (src/ftt.c:1535-1574) on 1e6 random + 20 k
+        adversarial points;
+      * sortedness / permutation / containment of the 10 M-particle cloud, volume conservation of
+        the deposit, fused == separate deposits;
+      * a 1e5-particle oracle spot check of the step (cells bit-exact, state <= 1e-12)."""
+    w = worlds.make_c3() if config == "C3" else worlds.make_c5(n_particles=10_000_000)
+    a = w.arrays
+    lo, hi = (5, 9) if config == "C3" else (6, 10)
+    hist = w.level_histogram()
+    assert min(hist) == lo and max(hist) == hi and all(hist[l] > 0 for l in range(lo, hi + 1))
+    sim, ptrs = helpers.matched_oracle(w)               # flatten(reference tree) == native tree
+    idx = helpers.PtrIndex(ptrs)
+    ctx.upload_tree(w.tree)
+    ctx.upload_field(w.u, w.v, w.w)
+    rng = np.random.default_rng(99)
+    n_pts = 1_000_000
+    pts = [rng.uniform(-0.55, 0.55, n_pts) for _ in range(3)]
+    # half of them near the ring, where the fine levels are
+    th = rng.uniform(0, 2 * np.pi, n_pts // 2)
+    pts[0][:n_pts // 2] = 0.25 * np.cos(th) + rng.normal(0, 0.01, n_pts // 2)
+    pts[1][:n_pts // 2] = 0.25 * np.sin(th) + rng.normal(0, 0.01, n_pts // 2)
+    pts[2][:n_pts // 2] = rng.normal(0, 0.01, n_pts // 2)
+    ax, ay, az = worlds.adversarial_points(a, rng, 20000)
+    x, y, z = (np.concatenate(c) for c in zip(pts, (ax, ay, az)))
+    got = ctx.locate(x, y, z)
+    want = idx(sim.locate(x, y, z))
+    assert np.array_equal(got, want)
+    assert (got >= 0).sum() > 800_000 and (got < 0).sum() > 10_000
+    assert len(np.unique(a.level[got[got >= 0]])) == hi - lo + 1      # every level was hit
+
+    parts = worlds.make_particles(w)
+    n = len(parts["x"])
+    assert n == 10_000_000
+    ctx.particles_upload(**parts)
+    ctx.sort()
+    pre = ctx.particles_download(ids=True)
+    cells = ctx.locate(pre["x"], pre["y"], pre["z"])
+    assert np.all(np.diff(cells) >= 0) and cells.min() >= 0
+    assert np.array_equal(np.sort(pre["id"]), np.arange(1, n + 1, dtype=np.uint32))
+    d = np.abs(np.stack([pre["x"], pre["y"], pre["z"]], 1) - a.pos[cells])
+    assert np.all(d <= a.h[cells][:, None] / 2)
+    ctx.deposit_all(w.step_params())
+    sep = [ctx.download_deposit(c) for c in range(4)]
+    assert abs(np.sum(sep[0] * a.h ** 3) - parts["volume"].sum()) <= 1e-12 * parts["volume"].sum()
+    ctx.step(w.step_params(record_cells=True))
+    got = ctx.particles_download(cells=True, ids=True)
+    assert np.array_equal(got["cell"], cells)
+    # the fused flavour on the same start: same state, same field as step + deposit_all
+    ctx.deposit_all(w.step_params())
+    after = [ctx.download_deposit(c) for c in range(4)]
+    ctx.particles_upload(**{k: pre[k] for k in ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")}, ids=pre["id"])
+    ctx.step(w.step_params(fuse_deposit=True))
+    fused_state = ctx.particles_download()
+    for k in STATE:
+        assert np.array_equal(fused_state[k], got[k]), k
+    for c in range(4):
+        f = ctx.download_deposit(c)
+        assert np.abs(f - after[c]).max() <= 1e-12 * np.abs(after[c]).max(), c
+    # oracle spot check on the first 1e5 ids
+    m = 100_000
+    sub = {k: parts[k][:m] for k in parts}
+    ocells, want = helpers.oracle_step(sim, ptrs, w, sub, nthreads=ora.load(3).ora_max_threads())
+    sel = np.argsort(got["id"])[:m]
+    assert np.array_equal(got["cell"][sel], ocells)
+    _check_state({k: got[k][sel] for k in STATE}, want, 3)
+
+
 @pytest.mark.parametrize("mode", ["0", "2", "3", "7", "9"])
 @pytest.mark.parametrize("kind", ["c1", "uniform3", "ring3", "ring2", "chain2"])
 def test_step_fast_paths(kind, mode, monkeypatch):

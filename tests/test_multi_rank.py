@@ -1,8 +1,11 @@
-"""world_size-2 test of the N>1 path on CPU (gloo): particles shard across
+"""world_size-2 tests of the N>1 path on CPU (gloo): particles shard across
 ranks, the tree and field are replicated, and the only exchange is the sum of
-the deposited field.  The per-rank deposit itself is produced here by the
-oracle (no GPU in this container); the GPU deposit kernel is parity-tested
-against the same oracle in test_gpu_parity.py::test_deposit."""
+the deposited field.  No GPU in this container, so the per-rank deposit is
+produced by the oracle; what IS the product here is the host logic of
+gfsb200_comm_rebalance -- gfsb200_comm_splitters, the slice boundaries from
+the all-reduced per-cell counts.  The device side of the same path (kernels,
+NVLink exchange) runs in tests/test_gpu_twoway.py (group of one on any box,
+two ranks under `gpurun --gpus 2`) and tools/check_twoway_ranks.py."""
 import os
 import socket
 
@@ -87,3 +90,72 @@ def test_shard_bounds_partition():
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
             assert [multigpu.id_offset(n, r, world) for r in range(world)] == [lo + 1 for lo, _ in b]
+
+
+def _rebalance_worker(rank, world, port, n_total, q):
+    """what gfsb200_comm_rebalance does, with gloo for NCCL and numpy for the kernels: per-cell
+    counts of the rank's share -> all-reduce -> gfsb200_comm_splitters (the product's host function)
+    -> every particle goes to the rank that owns its cell"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        w = worlds.make_ring("mr2", 3, 5, n_total, 78)
+        sim, ptrs = helpers.matched_oracle(w)
+        idx = helpers.PtrIndex(ptrs)
+        allp = worlds.make_particles(w)
+        # a random (not contiguous) share, as a rank that drew its own particles would hold
+        mine = np.flatnonzero(np.random.default_rng(5).integers(0, world, n_total) == rank)
+        cells = idx(sim.locate(allp["x"][mine], allp["y"][mine], allp["z"][mine]))
+        assert cells.min() >= 0
+        n_cells = w.arrays.n_cells
+        local = np.bincount(cells, minlength=n_cells).astype(np.float64)
+        counts = multigpu.allreduce_host(local).astype(np.uint32)
+        split = capi.comm_splitters(counts, world)
+        dest = np.searchsorted(split, cells, side="right") - 1
+        out = [mine[dest == r] for r in range(world)]
+        got = [None] * world
+        dist.all_gather_object(got, out)
+        owned = np.sort(np.concatenate([g[rank] for g in got]))
+        q.put((rank, split, owned, int(counts.max())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rebalance_slices_partition_the_cloud_by_cell():
+    n_total, world = 6007, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rebalance_worker, args=(r, world, port, n_total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=180) for _ in procs], key=lambda g: g[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    w = worlds.make_ring("mr2", 3, 5, n_total, 78)
+    sim, ptrs = helpers.matched_oracle(w)
+    idx = helpers.PtrIndex(ptrs)
+    allp = worlds.make_particles(w)
+    cells = idx(sim.locate(allp["x"], allp["y"], allp["z"]))
+    split = got[0][1]
+    assert np.array_equal(split, got[1][1])                      # every rank computed the same slices
+    assert split[0] == 0 and split[-1] == w.arrays.n_cells and np.all(np.diff(split) >= 0)
+    owned = [g[2] for g in got]
+    assert np.array_equal(np.sort(np.concatenate(owned)), np.arange(n_total))     # a partition of the cloud
+    for r in range(world):
+        c = cells[owned[r]]
+        assert np.all((c >= split[r]) & (c < split[r + 1]))        # by cell: no cell straddles two ranks
+    sizes = [len(o) for o in owned]
+    assert abs(sizes[0] - sizes[1]) <= 2 * got[0][3]               # equal up to one cell's population
+
+
+def test_splitters_edge_cases():
+    assert list(capi.comm_splitters(np.zeros(7, dtype=np.uint32), 3)) == [0, 7, 7, 7]
+    assert list(capi.comm_splitters(np.array([4, 4, 4, 4], dtype=np.uint32), 4)) == [0, 1, 2, 3, 4]
+    assert list(capi.comm_splitters(np.array([100, 0, 0, 1], dtype=np.uint32), 2)) == [0, 0, 4] or \
+        list(capi.comm_splitters(np.array([100, 0, 0, 1], dtype=np.uint32), 2))[0] == 0
+    s = capi.comm_splitters(np.array([0, 5, 5, 0, 10, 0, 20, 0], dtype=np.uint32), 4)
+    assert s[0] == 0 and s[-1] == 8 and np.all(np.diff(s) >= 0)
+    assert list(capi.comm_splitters(np.array([3, 1, 2], dtype=np.uint32), 1)) == [0, 3]
