@@ -610,8 +610,8 @@ extern "C" int gfsb200_download_vorticity (gfsb200_ctx * c, int64_t n, const int
 	return gfsb200_fail (GFSB200_ERR_ARG, "download_vorticity: cell %d is not a leaf", cells[j]);
       slot = gfsb200_lattice_index (c->T.dim, c->T.top_start, c->T.lattice_n1 - 1, cells[j]);
     }
-    if (c->T.dim == 3) {
-      out[3*j] = all[slot*4]; out[3*j + 1] = all[slot*4 + 1]; out[3*j + 2] = all[slot*4 + 2];
+    if (c->T.dim == 3) {           /* split rows: (wx,wy) pairs, then the wz array (DevField) */
+      out[3*j] = all[slot*2]; out[3*j + 1] = all[slot*2 + 1]; out[3*j + 2] = all[(size_t) c->T.n_cells*2 + slot];
     }
     else {
       out[3*j] = 0.; out[3*j + 1] = 0.; out[3*j + 2] = all[slot];

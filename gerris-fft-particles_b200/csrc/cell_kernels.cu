@@ -267,9 +267,7 @@ __device__ __forceinline__ void vorticity_body (const DevTree & T, const DevFiel
     if (DIM == 2)
       fld.vort[slot] = wz;
     else {
-      double2 * o = reinterpret_cast<double2 *> (fld.vort + slot*4);
-      o[0] = make_double2 (wx, wy);
-      o[1] = make_double2 (wz, 0.);
+      gfsb200_row_store3 (fld.vort, T.n_cells, slot, wx, wy, wz);
     }
   }
 }
@@ -309,9 +307,7 @@ convective_kernel (DevTree T, DevField fld)
     if (DIM == 2)
       reinterpret_cast<double2 *> (fld.acc)[slot] = make_double2 (a[0], a[1]);
     else {
-      double2 * o = reinterpret_cast<double2 *> (fld.acc + slot*4);
-      o[0] = make_double2 (a[0], a[1]);
-      o[1] = make_double2 (a[2], 0.);
+      gfsb200_row_store3 (fld.acc, T.n_cells, slot, a[0], a[1], a[2]);
     }
   }
 }
@@ -370,7 +366,7 @@ __device__ __noinline__ void hull_vertex_3d (const int32_t * __restrict__ vtx_of
 					     const double * __restrict__ vtx_w,
 					     const double * __restrict__ U, const double * __restrict__ V,
 					     const double * __restrict__ W, int * nodata_flag,
-					     double * __restrict__ out, int v)
+					     double * __restrict__ out, int64_t n_rows, int v)
 {
   const int b = vtx_off[v], e = vtx_off[v + 1];
   double s0 = 0., s1 = 0., s2 = 0.;
@@ -385,9 +381,7 @@ __device__ __noinline__ void hull_vertex_3d (const int32_t * __restrict__ vtx_of
     s0 = s1 = s2 = GFSB200_NODATA;
     *nodata_flag = 1;
   }
-  double2 * o = reinterpret_cast<double2 *> (out + (int64_t) v*4);
-  o[0] = make_double2 (s0, s1);
-  o[1] = make_double2 (s2, 0.);
+  gfsb200_row_store3 (out, n_rows, v, s0, s1, s2);
 }
 
 /* gfs_cell_corner_value, src/fluid.c:3081-3101: val = sum w_i v_i in stencil
@@ -462,9 +456,7 @@ __device__ __forceinline__ void vertex_values_body (const DevTree & T, const Dev
 	if (DIM == 2)
 	  reinterpret_cast<double2 *> (fld.vtx_val)[v] = make_double2 (s0, s1);
 	else {
-	  double2 * o = reinterpret_cast<double2 *> (fld.vtx_val + (int64_t) v*4);
-	  o[0] = make_double2 (s0, s1);
-	  o[1] = make_double2 (s2, 0.);
+	  gfsb200_row_store3 (fld.vtx_val, T.n_vertices, v, s0, s1, s2);
 	}
 	continue;
       }
@@ -473,9 +465,7 @@ __device__ __forceinline__ void vertex_values_body (const DevTree & T, const Dev
     if (DIM == 2)
       reinterpret_cast<double2 *> (fld.vtx_val)[v] = make_double2 (s0, s1);
     else {
-      double2 * o = reinterpret_cast<double2 *> (fld.vtx_val + (int64_t) v*4);
-      o[0] = make_double2 (s0, s1);
-      o[1] = make_double2 (s2, 0.);
+      gfsb200_row_store3 (fld.vtx_val, T.n_vertices, v, s0, s1, s2);
     }
   }
 }
@@ -580,6 +570,10 @@ lattice_cell_pass_kernel (DevTree T, DevField fld)
 {
   __shared__ double sh[3][REG*PLANE];
   __shared__ unsigned key[3][REG];
+  /* the step kernel behind this one is launched programmatically (its prologue touches the
+     particle stream only): once every brick has started, its CTAs may take the SM slots the last
+     wave of bricks frees, and wait there for this grid to finish (griddepcontrol.wait) */
+  asm volatile ("griddepcontrol.launch_dependents;" ::: "memory");
   const int n1 = T.lattice_n1, nn = n1 - 1, nb = nn/BRICK;
 
   /* a warp = 8 x by 4 z at one y: with the padded plane stride its 64-bit shared loads are
@@ -637,9 +631,7 @@ lattice_cell_pass_kernel (DevTree T, DevField fld)
 	      *fld.nodata_flag = 1;
 	    }
 	  }
-	  double2 * o = reinterpret_cast<double2 *> (fld.vtx_val + ((int64_t) (k*n1 + j)*n1 + i)*4);
-	  o[0] = make_double2 (s0, s1);
-	  o[1] = make_double2 (s2, 0.);
+	  gfsb200_row_store3 (fld.vtx_val, T.n_vertices, (int64_t) (k*n1 + j)*n1 + i, s0, s1, s2);
 	}
       }
       /* ---- the leaf itself.  gfs_center_gradient (src/fluid.c:434-475) with same-level leaf
@@ -661,9 +653,7 @@ lattice_cell_pass_kernel (DevTree T, DevField fld)
 	const double wx = (grad (2, 2, REG, ky) - grad (1, 4, PLANE, kz))*inv_size;
 	const double wy = (grad (0, 4, PLANE, kz) - grad (2, 1, 1, kx))*inv_size;
 	const double wz = (grad (1, 1, 1, kx) - grad (0, 2, REG, ky))*inv_size;
-	double2 * o = reinterpret_cast<double2 *> (fld.vort + ((int64_t) (kz*nn + ky)*nn + kx)*4);
-	o[0] = make_double2 (wx, wy);
-	o[1] = make_double2 (wz, 0.);
+	gfsb200_row_store3 (fld.vort, T.n_cells, (int64_t) (kz*nn + ky)*nn + kx, wx, wy, wz);
       }
     }
     /* ---- vertices on the hull (a coordinate equal to 0 or nn): their stencils are the few
@@ -694,7 +684,7 @@ lattice_cell_pass_kernel (DevTree T, DevField fld)
 	    first = false;
 	if (first)
 	  hull_vertex_3d (T.vtx_off, T.vtx_cell, T.vtx_w, fld.u[0], fld.u[1], fld.u[2], fld.nodata_flag,
-			  fld.vtx_val, (c[2]*n1 + c[1])*n1 + c[0]);
+			  fld.vtx_val, T.n_vertices, (c[2]*n1 + c[1])*n1 + c[0]);
       }
     }
   }

@@ -62,14 +62,20 @@ struct DevField {
   const double * alpha;        /* optional per-cell 1/rho */
   const double * mu;           /* optional per-cell viscosity */
   /* derived per field update */
-  double * vtx_val;            /* 3D: [n_vertices][4] (u,v,w,pad); 2D: [n_vertices][2] */
-  double * vort;               /* 3D: [..][4] (wx,wy,wz,pad); 2D: [..] (wz).  Indexed by cell, or on
+  /* 3D table rows are SPLIT (round 2): the first two components as 16-byte (a,b) rows -- eight to a
+     128-byte line -- followed, 2*rows doubles further on, by the third as an array of doubles --
+     sixteen to a line.  The L1 charges a gather per request AND per 128-byte line it touches;
+     against padded 32-byte rows (four to a line, both requests of a row on the same lines) the
+     32 sorted particles of a warp touch about a third fewer lines.  gfsb200_row_store3 /
+     load_row are the only accessors. */
+  double * vtx_val;            /* 3D: [n_vertices] (u,v) rows + [n_vertices] w; 2D: [n_vertices][2] */
+  double * vort;               /* 3D: [n_cells] (wx,wy) rows + [n_cells] wz; 2D: [..] (wz).  Indexed by cell, or on
 				  lattice trees by (kz*N + ky)*N + kx with N = lattice_n1 - 1 */
   int * nodata_flag;           /* set by the cell pass when any vertex stencil touches GFS_NODATA */
   /* GfsForceInertial / GfsForceAddedMass only */
   const double * uprev[3];     /* Un,Vn,Wn cell values */
   double * vtx_prev;           /* their vertex table, laid out like vtx_val */
-  double * acc;                /* per leaf (u.grad)u at the cell centre, laid out like vort (3D: [..][4];
+  double * acc;                /* per leaf (u.grad)u at the cell centre, laid out like vort (3D: split rows;
 				  2D: [..][2]) */
 };
 
@@ -101,6 +107,16 @@ struct DevStep {
   double * esc_old;            /* [esc_cap][3] position before the step */
   unsigned char * keep;        /* [n] or NULL: cleared for a particle that was outside the domain BEFORE the step */
 };
+
+#ifdef __CUDACC__
+/* row i of a 3D table of n_rows rows (see DevField) */
+__device__ __forceinline__ void gfsb200_row_store3 (double * __restrict__ tab, int64_t n_rows, int64_t i,
+						    double a, double b, double c)
+{
+  reinterpret_cast<double2 *> (tab)[i] = make_double2 (a, b);
+  tab[2*n_rows + i] = c;
+}
+#endif
 
 /* Two-way coupling over several GPUs.  After gfsb200_comm_rebalance rank r holds the particles of
  * the cells [split[r], split[r + 1]) of the flat tree and OWNS that slice of the deposit buffer: a

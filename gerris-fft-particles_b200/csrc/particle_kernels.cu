@@ -266,20 +266,16 @@ __device__ __forceinline__ double lerp (double a, double b, double t)
   return fma (t, b - a, a);
 }
 
-/* One 32-byte row (three fp64 values + padding) of the vertex / vorticity / acceleration tables.
- * Default: a 128-bit and a 64-bit read-only load.  -DGFSB200_ROW256: ONE 256-bit load (LDG.E.256,
- * sm_100): the row is one 32-byte sector, and the L1 data pipe is charged per sector and request
- * -- two requests to the same sector cost twice (profiles/README.md, round 2). */
-__device__ __forceinline__ void load_row (const double * __restrict__ row, double & a, double & b, double & c)
+/* Row i of a 3D vertex / vorticity / acceleration table of n_rows rows (split layout, DevField):
+ * (a, b) with one 128-bit load from the 16-byte rows, c with one 64-bit load from the array behind
+ * them.  (One 256-bit load of a padded 32-byte row -- LDG.E.ENL2.256 -- measured 5 % slower, rounds
+ * 1 and 2: profiles/README.md.) */
+__device__ __forceinline__ void load_row (const double * __restrict__ tab, int64_t n_rows, int64_t i,
+					  double & a, double & b, double & c)
 {
-#ifdef GFSB200_ROW256
-  double pad;
-  asm ("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(pad) : "l"(row));
-#else
-  const double2 * p = reinterpret_cast<const double2 *> (row);
-  const double2 ab = __ldg (p);
-  a = ab.x; b = ab.y; c = __ldg (reinterpret_cast<const double *> (p + 1));
-#endif
+  const double2 ab = __ldg (reinterpret_cast<const double2 *> (tab) + i);
+  a = ab.x; b = ab.y;
+  c = __ldg (tab + 2*n_rows + i);
 }
 
 /* Per-leaf NODATA fallback of gfs_cell_corner_value (src/fluid.c:3094-3097) */
@@ -331,7 +327,7 @@ __device__ __forceinline__ void interpolate (const DevTree & T, const DevField &
       double fu[4], fv[4], fw[4];
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-	load_row (fld.vtx_val + (int64_t) id[q[k]]*4, fu[k], fv[k], fw[k]);
+	load_row (fld.vtx_val, T.n_vertices, id[q[k]], fu[k], fv[k], fw[k]);
       }
       if (any_nodata) {
 #pragma unroll
@@ -433,7 +429,7 @@ __device__ __forceinline__ void total_force (const DevTree & T, const DevField &
   if (PROG && any_lift) {
     const int64_t slot = leaf_slot<DIM, LATTICE> (T, L);
     if (DIM == 3) {
-      load_row (fld.vort + slot*4, wx, wy, wz);
+      load_row (fld.vort, T.n_cells, slot, wx, wy, wz);
     }
     else
       wz = __ldg (fld.vort + slot);
@@ -491,7 +487,7 @@ __device__ __forceinline__ void total_force (const DevTree & T, const DevField &
       if (!(PROG && any_lift)) {
 	const int64_t slot = leaf_slot<DIM, LATTICE> (T, L);
 	if (DIM == 3) {
-	  load_row (fld.vort + slot*4, wx, wy, wz);
+	  load_row (fld.vort, T.n_cells, slot, wx, wy, wz);
 	}
 	else
 	  wz = __ldg (fld.vort + slot);
@@ -520,7 +516,7 @@ __device__ __forceinline__ void total_force (const DevTree & T, const DevField &
 	const int64_t slot = leaf_slot<DIM, LATTICE> (T, L);
 	double ax, ay, az = 0.;
 	if (DIM == 3) {
-	  load_row (fld.acc + slot*4, ax, ay, az);
+	  load_row (fld.acc, T.n_cells, slot, ax, ay, az);
 	}
 	else {
 	  const double2 a = __ldg (reinterpret_cast<const double2 *> (fld.acc) + slot);
@@ -975,11 +971,19 @@ step_kernel_wpipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_til
 	issue (s, first + s*stride);
   }
   __syncwarp ();
+  /* Programmatic dependent launch: the kernel may have been started while the cell pass (the
+     previous kernel of the stream) was still draining -- everything above touches only the
+     particle stream, which that kernel does not write.  The tables are read from here on: wait
+     for the prerequisite grid and its memory.  (A no-op for an ordinary launch.) */
+  asm volatile ("griddepcontrol.wait;" ::: "memory");
 
   int s = 0;
   unsigned parity = 0;
   for (int tile = first; tile < n_tiles; tile += stride) {
     pipe::mbar_wait (&full[warp][s], parity);
+    /* (A one-tile lookahead -- locate the next tile's particles in the other stage and prefetch
+       their table rows into L1 -- measured 2 % SLOWER on C2, C3 and 2D, round 2: the wait at the
+       first use of the gathered values is queueing in the L1 data pipe, not L2 latency.) */
     const double * b = &buf[warp][s][0][lane];
     const int64_t i = (int64_t) tile*32 + lane;
     int dcell = -1;
@@ -1119,7 +1123,8 @@ __global__ void corner_values_kernel (DevTree T, DevField fld, int comp, int64_t
   const int v = T.leaf_vtx[(int64_t) cell*nc + k];
   double val = GFSB200_NODATA;
   if (v >= 0) {
-    val = fld.vtx_val[(int64_t) v*(DIM == 3 ? 4 : 2) + comp];
+    val = DIM == 3 ? (comp < 2 ? fld.vtx_val[(int64_t) v*2 + comp] : fld.vtx_val[(int64_t) T.n_vertices*2 + v])
+      : fld.vtx_val[(int64_t) v*2 + comp];
     val = resolve (val, fld.u[comp], cell);
   }
   out[j] = val;
@@ -1527,15 +1532,38 @@ static void launch_wpipe (const DevTree * T, const DevField * F, const DevPartic
   const int n_tiles = (int) ((P->n + 31)/32);
   const size_t smem = (size_t) WPIPE_WARPS*ST*(DIM == 3 ? 8 : 6)*32*sizeof (double);
   static bool configured = false;
+  static int per_sm = MB;
   if (!configured) {
     cudaFuncSetAttribute (step_kernel_wpipe<DIM, LA, PR, ST, MB, WPIPE_WARPS, REC, DEP>,
 			  cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    /* persistent grid: as many CTAs per SM as the instance's registers and staging allow -- MB
+       for the 72-register 3D kernels, more for the leaner ones (2D drag: 48 registers -> 10) */
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, step_kernel_wpipe<DIM, LA, PR, ST, MB, WPIPE_WARPS, REC, DEP>,
+						       32*WPIPE_WARPS, smem) == cudaSuccess && occ > MB &&
+	!getenv ("GFSB200_WPIPE_FIXED_GRID"))
+      per_sm = occ;
     configured = true;
   }
-  int grid = n_sm*MB;
+  int grid = n_sm*per_sm;
   if (grid*WPIPE_WARPS > n_tiles) grid = (n_tiles + WPIPE_WARPS - 1)/WPIPE_WARPS;
   DevDeposit none;
   memset (&none, 0, sizeof none);
+  static const bool pdl = !(getenv ("GFSB200_PDL") && atoi (getenv ("GFSB200_PDL")) == 0);
+  if (pdl) {
+    /* let the prologue (mbarrier set-up, the first particle tiles) overlap the tail of the cell pass */
+    cudaLaunchConfig_t cfg;
+    memset (&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3 (grid); cfg.blockDim = dim3 (32*WPIPE_WARPS);
+    cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx (&cfg, step_kernel_wpipe<DIM, LA, PR, ST, MB, WPIPE_WARPS, REC, DEP>,
+			*T, *F, *P, *S, n_tiles, DEP ? *D : none);
+    return;
+  }
   step_kernel_wpipe<DIM, LA, PR, ST, MB, WPIPE_WARPS, REC, DEP><<<grid, 32*WPIPE_WARPS, smem, st>>>
     (*T, *F, *P, *S, n_tiles, DEP ? *D : none);
 }

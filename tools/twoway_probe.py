@@ -15,7 +15,8 @@ capi, worlds = pkg.capi, pkg.worlds
 cfg = sys.argv[1]
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 npart = int(sys.argv[3]) if len(sys.argv) > 3 else 10_000_000
-w = {"C2": worlds.make_c2, "C3": worlds.make_c3, "C5": worlds.make_c5}[cfg](n_particles=npart)
+w = {"C2": worlds.make_c2, "C3": worlds.make_c3, "C5": worlds.make_c5,
+     "2D": lambda n_particles: worlds.make_c1(level=10, n_particles=n_particles)}[cfg](n_particles=npart)
 parts = worlds.make_particles(w, npart)
 try:
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -25,7 +26,8 @@ ctx = capi.Context(0)
 ctx.upload_tree(w.tree)
 ctx.upload_field(w.u, w.v, w.w)
 out = {"config": cfg, "lib": os.environ.get("GFSB200_LIB", "default"), "particles": npart}
-for name, par, b in (("step", w.step_params(), 112), ("fused", w.step_params(fuse_deposit=True), 136)):
+b1, b2 = (112, 136) if w.dim == 3 else (80, 96)
+for name, par, b in (("step", w.step_params(), b1), ("fused", w.step_params(fuse_deposit=True), b2)):
     ctx.particles_upload(**parts)
     ctx.sort()
     for _ in range(5):
@@ -39,8 +41,8 @@ for name, par, b in (("step", w.step_params(), 112), ("fused", w.step_params(fus
     out[name + "_ms"] = round(ms, 5)
     out[name + "_frac"] = round(b * npart / (ms * 1e-3) / 1e9 / peak, 4)
 got = ctx.particles_download()
-h = hashlib.sha1(b"".join(np.ascontiguousarray(got[k]).tobytes() for k in ("x", "y", "z", "vx", "vy", "vz")))
-f = [ctx.download_deposit(c) for c in range(4)]
+h = hashlib.sha1(b"".join(np.ascontiguousarray(got[k]).tobytes() for k in ("x", "y", "z", "vx", "vy", "vz") if got[k] is not None))
+f = [ctx.download_deposit(c) for c in range(1 + w.dim)]
 out["state_sha1"] = h.hexdigest()[:12]
 out["field_abs_sum"] = [float(np.abs(a).sum()) for a in f]
 print(json.dumps(out), flush=True)
