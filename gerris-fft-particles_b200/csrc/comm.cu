@@ -27,8 +27,8 @@
  * it and a process that already carries an NCCL (torch) shares that copy.
  *
  * Ordering of the owner-slice protocol (two deposit buffers, step n uses buffer n % 2):
- *   D(n)    deposit: local + remote reductions into n%2  } on the context's stream, in this order;
- *   Z(n+1)  zero the OWN slice of the other buffer       } Z is issued by gfsb200_deposit_allreduce
+ *   D(n)    deposit: local + remote reductions into n%2 (the context's stream)
+ *   Z(n+1)  zero the OWN slice of the other buffer: first thing on the communication stream after D(n)
  *   X(n)    on the communication stream, after D(n): barrier B(n) -- every rank has finished D(n),
  *           so every remote reduction into my slice has landed (kernel completion drains them) --
  *           then the pushes of my slice, then the DONE flags.
@@ -975,23 +975,26 @@ extern "C" int gfsb200_deposit_allreduce (gfsb200_comm * const * local, int n_lo
     gfsb200_comm * m = local[k];
     gfsb200_ctx * c = m->c;
     CK (cudaSetDevice (c->device));
+    CK (cudaEventRecord (m->ev_dep, c->stream));
+    CK (cudaStreamWaitEvent (m->stream, m->ev_dep, 0));
     if (mode == MODE_OWNER) {
-      /* Z(n+1): clear my slice of the OTHER buffer for the next step -- on the context's stream,
-	 behind this step's kernels and before my arrival at B(n).  Its previous exchange has had a
-	 whole step to drain, so the wait below is normally already satisfied. */
+      /* Z(n+1): clear my slice of the OTHER buffer for the next step -- on the communication
+	 stream, behind this step's kernels and the previous exchange of that buffer (same stream),
+	 before my arrival at B(n).  The context's stream goes straight on to the next step's cell
+	 pass; its next deposit kernel waits for ev_barrier (gfsb200_comm_prepare_deposit). */
       const int o = 1 - c->dep_which;
       const size_t n = c->T.n_cells;
       int32_t lo, hi;
       slice_leaves (m, &lo, &hi);
-      if (m->x_pending[o])
-	CK (cudaStreamWaitEvent (c->stream, m->ev_x[o], 0));     /* (stays pending for gfsb200_deposit_wait) */
       if (hi > lo)
 	CK (cudaMemset2DAsync (c->deposit_buf[o] + lo, n*sizeof (double), 0, (size_t) (hi - lo)*sizeof (double),
-			       (size_t) c->T.dim + 1, c->stream));
+			       (size_t) c->T.dim + 1, m->stream));
       m->ahead_ok[o] = true;
+      if (R == 1) {
+	CK (cudaEventRecord (m->ev_barrier, m->stream));
+	m->barrier_pending = true;
+      }
     }
-    CK (cudaEventRecord (m->ev_dep, c->stream));
-    CK (cudaStreamWaitEvent (m->stream, m->ev_dep, 0));
     if (!(mode == MODE_OWNER && R > 1) && (r = stat_begin (m))) return r;
     m->epoch++;
   }
