@@ -356,8 +356,17 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
   T.lattice_n1 = 0;
   /* (a one-slot locate array means one GfsBox and no GfsBoundary root: hull cells have NULL
      neighbours, so "all neighbours are same-level leaves" == interior on such a tree) */
+  /* The lattice flavour of locate () lets the locate-array slot test stand for the root test of
+     ftt_cell_locate as well: that needs the slot to BE the box -- same lower corner, same size --
+     with corners that are exact in fp64 (they are for dyadic boxes; anything else keeps the
+     general path). */
+  bool slot_is_box = T.la_h == T.root_size;
+  for (int a = 0; a < t->dim; a++) {
+    const double c = T.root_pos[0][a], half = 0.5*T.root_size, lo = c - half, hi = c + half;
+    slot_is_box = slot_is_box && T.la_min[a] == lo && lo + half == c && hi - half == c && lo + T.root_size == hi;
+  }
   if (t->lattice_level >= 0 && t->lattice_level - t->root_level == T.top_levels && T.single_box &&
-      t->n_roots == 1 && !any_destroyed && !getenv ("GFSB200_NO_LATTICE"))
+      t->n_roots == 1 && !any_destroyed && slot_is_box && !getenv ("GFSB200_NO_LATTICE"))
     T.lattice_n1 = (1 << T.top_levels) + 1;
   /* Interior vertices of a lattice tree: check once, on the host, that every one of them
      carries the same stencil shape (the 2^dim leaves around it, equal weights, one common

@@ -79,6 +79,46 @@ __device__ __forceinline__ Located locate (const DevTree & T, double x, double y
   L.cx = L.cy = L.cz = 0.; L.half = 0.;
   L.kx = L.ky = L.kz = 0;
 
+  if (LATTICE) {
+    /* One GfsBox, one locate-array slot, every leaf at the complete level (checked at upload,
+       lattice_n1 > 0, together with la_min == root centre - root_size/2 and la_h == root_size,
+       both exact).  The slot test floor ((p - min)/la_h) == 0, i.e. 0 <= (p - min)*la_inv_h < 1,
+       then implies the inclusive root test of ftt_cell_locate (p - min >= 0 and fl (p - min) < h
+       => min <= p < min + h), so that test is not repeated; and (p - min)*top_inv_h is the same
+       product scaled by the exact factor n = 2^levels, so ONE product per axis serves the slot
+       test (0 <= s < n) and the column candidate (trunc (s) <= n - 1, no clamp).  The candidate
+       is repaired by the two exact threshold comparisons of column (), and the centre comes
+       from the repaired column kept in floating point: same values as the general path below,
+       bit for bit, without its root_pos loads, second set of int -> double conversions and
+       6 + 6 comparisons. */
+    const int n = 1 << T.top_levels;
+    const double h = T.top_h, inv_h = T.top_inv_h, nd = (double) n;
+    const double lox = T.la_min[0], loy = T.la_min[1], loz = DIM == 3 ? T.la_min[2] : 0.;
+    const double sx = (x - lox)*inv_h, sy = (y - loy)*inv_h, sz = DIM == 3 ? (z - loz)*inv_h : 0.;
+    if (!(sx >= 0. && sx < nd && sy >= 0. && sy < nd && sz >= 0. && sz < nd))
+      return L;
+    int k[3];
+    double c[3];
+    const double p[3] = { x, y, z }, lo[3] = { lox, loy, loz }, sc[3] = { sx, sy, sz };
+#pragma unroll
+    for (int a = 0; a < DIM; a++) {
+      const int kc = __double2int_rz (sc[a]);
+      double kd = (double) kc;
+      const double tk = fma (kd, h, lo[a]);            /* lower threshold of column kc, exact */
+      const bool up = (p[a] > tk + h) & (kc < n - 1);
+      const bool down = (!(p[a] > tk)) & (kc > 0);
+      if (up) kd += 1.;
+      if (down) kd -= 1.;
+      k[a] = kc + (up ? 1 : 0) - (down ? 1 : 0);
+      c[a] = lo[a] + (kd + 0.5)*h;
+    }
+    L.kx = k[0]; L.ky = k[1]; L.kz = DIM == 3 ? k[2] : 0;
+    L.cx = c[0]; L.cy = c[1]; L.cz = DIM == 3 ? c[2] : 0.;
+    L.half = 0.5*h;
+    L.cell = 0;             /* the Morton index is only materialised when asked for (cell_index ()) */
+    return L;
+  }
+
   /* GfsLocateArray, src/domain.c:43-80: i_c = floor ((p_c - min_c)/h); h is a
      power of two, so the division is a multiplication by its exact inverse.
      NaN coordinates fail every comparison below and end up outside, as in the
@@ -214,7 +254,13 @@ __device__ __forceinline__ bool in_domain (const DevTree & T, double x, double y
 template <int DIM, bool LATTICE>
 __device__ __forceinline__ bool left_domain (const DevTree & T, double x, double y, double z)
 {
-  if (!LATTICE && T.has_destroyed)
+  if (LATTICE) {
+    /* the locate-array slot test decides (see locate ()) */
+    const double tx = (x - T.la_min[0])*T.la_inv_h, ty = (y - T.la_min[1])*T.la_inv_h;
+    const double tz = DIM == 3 ? (z - T.la_min[2])*T.la_inv_h : 0.;
+    return !(tx >= 0. && tx < 1. && ty >= 0. && ty < 1. && tz >= 0. && tz < 1.);
+  }
+  if (T.has_destroyed)
     return locate<DIM, LATTICE> (T, x, y, z).cell < 0;
   return !in_domain<DIM> (T, x, y, z);
 }
@@ -254,8 +300,8 @@ __device__ __forceinline__ int64_t leaf_slot (const DevTree & T, const Located &
 {
   if (!LATTICE)
     return L.cell;
-  const int n = T.lattice_n1 - 1;
-  return DIM == 3 ? ((int64_t) L.kz*n + L.ky)*n + L.kx : (int64_t) L.ky*n + L.kx;
+  const int n = T.lattice_n1 - 1;         /* n <= 2^10 (3D) / 2^15 (2D): the slot fits 32 bits */
+  return DIM == 3 ? (L.kz*n + L.ky)*n + L.kx : L.ky*n + L.kx;
 }
 
 /* ------------------------------------------------------------------ */
@@ -901,21 +947,31 @@ __device__ __forceinline__ double lds_after (const double * p, double dep)
   return v;
 }
 
+/* the same from a shared-window address computed once per tile, column COL of the staged tile */
+template <int COL>
+__device__ __forceinline__ double lds_col_after (uint32_t lane_addr, double dep)
+{
+  double v;
+  asm volatile ("ld.shared.f64 %0, [%1+%2];   // after %3" : "=d"(v) : "r"(lane_addr), "n"(COL*32*8), "d"(dep));
+  return v;
+}
+
 } // namespace pipe
 
 template <int DIM>
 struct LateShared {
-  const double * b;            /* this lane's slot in column 0 of the staged tile; columns 32 apart */
+  uint32_t b;                  /* shared-window address of this lane's slot in column 0 of the staged
+				  tile; columns 32 doubles apart */
   double * keep;               /* the caller's vx, vy, vz (total_force takes them by value) */
   __device__ __forceinline__ void fetch (double dep, double & vx, double & vy, double & vz,
 					 double & mass, double & volume) const
   {
     constexpr int V0 = DIM == 3 ? 3 : 2;
-    keep[0] = vx = pipe::lds_after (b + 32*V0, dep);
-    keep[1] = vy = pipe::lds_after (b + 32*(V0 + 1), dep);
-    if (DIM == 3) keep[2] = vz = pipe::lds_after (b + 32*(V0 + 2), dep);
-    mass = pipe::lds_after (b + 32*(2*DIM), dep);
-    volume = pipe::lds_after (b + 32*(2*DIM + 1), dep);
+    keep[0] = vx = pipe::lds_col_after<V0> (b, dep);
+    keep[1] = vy = pipe::lds_col_after<V0 + 1> (b, dep);
+    if (DIM == 3) keep[2] = vz = pipe::lds_col_after<V0 + 2> (b, dep);
+    mass = pipe::lds_col_after<2*DIM> (b, dep);
+    volume = pipe::lds_col_after<2*DIM + 1> (b, dep);
   }
 };
 
@@ -985,6 +1041,7 @@ step_kernel_wpipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_til
        their table rows into L1 -- measured 2 % SLOWER on C2, C3 and 2D, round 2: the wait at the
        first use of the gathered values is queueing in the L1 data pipe, not L2 latency.) */
     const double * b = &buf[warp][s][0][lane];
+    const uint32_t sb = pipe::smem_u32 (b);
     const int64_t i = (int64_t) tile*32 + lane;
     int dcell = -1;
     double av = 0., ax = 0., ay = 0., az = 0.;
@@ -998,15 +1055,15 @@ step_kernel_wpipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_til
 	double vx = 0., vy = 0., vz = 0., mass = 0., volume = 0.;
 	double vkeep[3];
 	total_force<DIM, false, LATTICE, PROG, LateShared<DIM> > (T, fld, S, L, x, y, z, vx, vy, vz, mass, volume,
-								 Fx, Fy, Fz, rho, LateShared<DIM> { b, vkeep });
+								 Fx, Fy, Fz, rho, LateShared<DIM> { sb, vkeep });
 	if (!PROG && S.mutates_mass)
 	  P.mass[i] = mass;
 	if (REC) {
 	  __stcs (P.fx + i, Fx); __stcs (P.fy + i, Fy); __stcs (P.fz + i, Fz);
 	}
 	/* the position comes back from the staged tile, the velocity from the late fetch */
-	x = pipe::lds_after (b, Fx); y = pipe::lds_after (b + 32, Fx);
-	if (DIM == 3) z = pipe::lds_after (b + 64, Fx);
+	x = pipe::lds_col_after<0> (sb, Fx); y = pipe::lds_col_after<1> (sb, Fx);
+	if (DIM == 3) z = pipe::lds_col_after<2> (sb, Fx);
 	vx = vkeep[0]; vy = vkeep[1];
 	if (DIM == 3) vz = vkeep[2];
 	const double hdt = 0.5*S.dt, dtm = S.dt*__drcp_rn (mass);
@@ -1023,7 +1080,7 @@ step_kernel_wpipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_til
 	}
 	if (DEP) {
 	  /* volume is re-read from the staged tile (total_force took it by value) */
-	  const double vol2 = pipe::lds_after (b + 32*(2*DIM + 1), vx);
+	  const double vol2 = pipe::lds_col_after<2*DIM + 1> (sb, vx);
 	  dcell = deposit_terms<DIM, LATTICE, PROG, true, true> (T, fld, S, x, y, z, vx, vy, vz, mass, vol2,
 								 av, ax, ay, az);
 	  if (!PROG && S.mutates_mass && dcell >= 0)
