@@ -317,7 +317,9 @@ template <int DIM>
 __device__ __forceinline__ void vertex_from_tables (const DevTree & T, const DevField & fld, int v,
 						     double & s0, double & s1, double & s2)
 {
-  bool nodata = false;
+  /* per VARIABLE, as gfs_cell_corner_value is called per variable: a NODATA value of V in the
+     stencil does not touch the corner value of U */
+  bool nd0 = false, nd1 = false, nd2 = false;
   s0 = s1 = s2 = 0.;
   const int b = T.vtx_off[v], e = T.vtx_off[v + 1];
   /* most stencils carry one weight repeated (equal-size cells around the
@@ -346,14 +348,16 @@ __device__ __forceinline__ void vertex_from_tables (const DevTree & T, const Dev
 #pragma unroll
     for (int j = 0; j < NB; j++) {
 	/* GFS_NODATA = DBL_MAX: compare the high word on the integer pipe */
-	nodata |= is_nodata (a0[j]) | is_nodata (a1[j]) | (DIM == 3 && is_nodata (a2[j]));
+	nd0 |= is_nodata (a0[j]); nd1 |= is_nodata (a1[j]); nd2 |= DIM == 3 && is_nodata (a2[j]);
 	s0 += w[j]*a0[j];
 	s1 += w[j]*a1[j];
 	if (DIM == 3) s2 += w[j]*a2[j];
     }
   }
-  if (nodata) {
-    s0 = s1 = s2 = GFSB200_NODATA;
+  if (nd0 | nd1 | nd2) {
+    if (nd0) s0 = GFSB200_NODATA;
+    if (nd1) s1 = GFSB200_NODATA;
+    if (nd2) s2 = GFSB200_NODATA;
     *fld.nodata_flag = 1;
   }
 }
@@ -370,15 +374,17 @@ __device__ __noinline__ void hull_vertex_3d (const int32_t * __restrict__ vtx_of
 {
   const int b = vtx_off[v], e = vtx_off[v + 1];
   double s0 = 0., s1 = 0., s2 = 0.;
-  bool nodata = false;
+  bool nd0 = false, nd1 = false, nd2 = false;
   for (int i = b; i < e; i++) {
     const int c = vtx_cell[i];
     const double w = vtx_w[i], a0 = U[c], a1 = V[c], a2 = W[c];
-    nodata |= is_nodata (a0) | is_nodata (a1) | is_nodata (a2);
+    nd0 |= is_nodata (a0); nd1 |= is_nodata (a1); nd2 |= is_nodata (a2);
     s0 += w*a0; s1 += w*a1; s2 += w*a2;
   }
-  if (nodata) {
-    s0 = s1 = s2 = GFSB200_NODATA;
+  if (nd0 | nd1 | nd2) {
+    if (nd0) s0 = GFSB200_NODATA;
+    if (nd1) s1 = GFSB200_NODATA;
+    if (nd2) s2 = GFSB200_NODATA;
     *nodata_flag = 1;
   }
   gfsb200_row_store3 (out, n_rows, v, s0, s1, s2);
@@ -414,7 +420,7 @@ __device__ __forceinline__ void vertex_values_body (const DevTree & T, const Dev
       v = (k*n1 + j)*n1 + i;
     }
     double s0 = 0., s1 = 0., s2 = 0.;
-    bool nodata = false;
+    bool nd0 = false, nd1 = false, nd2 = false;
     if (n1 > 0 && T.lattice_pattern >= 0) {
       const int i = v % n1, j = (v/n1) % n1, k = DIM == 3 ? v/(n1*n1) : 1;
       const int nn = n1 - 1;
@@ -444,13 +450,15 @@ __device__ __forceinline__ void vertex_values_body (const DevTree & T, const Dev
 	}
 #pragma unroll
 	for (int q = 0; q < NB; q++) {
-	  nodata |= is_nodata (a0[q]) | is_nodata (a1[q]) | (DIM == 3 && is_nodata (a2[q]));
+	  nd0 |= is_nodata (a0[q]); nd1 |= is_nodata (a1[q]); nd2 |= DIM == 3 && is_nodata (a2[q]);
 	  s0 += w*a0[q];
 	  s1 += w*a1[q];
 	  if (DIM == 3) s2 += w*a2[q];
 	}
-	if (nodata) {
-	  s0 = s1 = s2 = GFSB200_NODATA;
+	if (nd0 | nd1 | nd2) {
+	  if (nd0) s0 = GFSB200_NODATA;
+	  if (nd1) s1 = GFSB200_NODATA;
+	  if (nd2) s2 = GFSB200_NODATA;
 	  *fld.nodata_flag = 1;
 	}
 	if (DIM == 2)
@@ -622,12 +630,15 @@ lattice_cell_pass_kernel (DevTree T, DevField fld)
 	     overflows); no velocity gets near that, so one magnitude test screens for the
 	     exact check */
 	  if (!(fabs (s0) < 1e300 && fabs (s1) < 1e300 && fabs (s2) < 1e300)) {
-	    bool bad = false;
+	    bool bad0 = false, bad1 = false, bad2 = false;     /* per variable (gfs_cell_corner_value) */
 #pragma unroll
-	    for (int q = 0; q < 8; q++)
-	      bad |= is_nodata (c[0][q]) | is_nodata (c[1][q]) | is_nodata (c[2][q]);
-	    if (bad) {
-	      s0 = s1 = s2 = GFSB200_NODATA;
+	    for (int q = 0; q < 8; q++) {
+	      bad0 |= is_nodata (c[0][q]); bad1 |= is_nodata (c[1][q]); bad2 |= is_nodata (c[2][q]);
+	    }
+	    if (bad0 | bad1 | bad2) {
+	      if (bad0) s0 = GFSB200_NODATA;
+	      if (bad1) s1 = GFSB200_NODATA;
+	      if (bad2) s2 = GFSB200_NODATA;
 	      *fld.nodata_flag = 1;
 	    }
 	  }

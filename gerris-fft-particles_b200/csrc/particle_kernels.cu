@@ -330,6 +330,44 @@ __device__ __forceinline__ double resolve (double v, const double * __restrict__
   return __double2hiint (v) == 0x7fefffff && __double2loint (v) == (int) 0xffffffff ? F[cell] : v;
 }
 
+/* The trilinear form of gfs_interpolate_from_corners (src/fluid.c:2666-2681) from the eight vertex
+ * rows id[0..7] of a 3D leaf, written as nested linear interpolations.
+ * Corners: 0(-,-,+) 1(+,-,+) 2(+,+,+) 3(-,+,+) 4(-,-,-) 5(+,-,-) 6(+,+,-) 7(-,+,-), evaluated one
+ * z-plane at a time (back: 4 5 7 6, front: 0 1 3 2) so that only 12 corner values are live at once.
+ * ND: some vertex of the field carries GFS_NODATA -- resolve every value against the leaf's own. */
+template <bool ND>
+__device__ __forceinline__ void trilinear_rows (const double * __restrict__ vtx_val, int64_t n_vertices,
+						const int (& id)[8], double tx, double ty, double tz,
+						const double * __restrict__ U, const double * __restrict__ V,
+						const double * __restrict__ W, int cell,
+						double & u, double & v, double & w)
+{
+  double pu[2], pv[2], pw[2];
+#pragma unroll
+  for (int plane = 0; plane < 2; plane++) {
+    const int q[4] = { plane ? 0 : 4, plane ? 1 : 5, plane ? 3 : 7, plane ? 2 : 6 };
+    double fu[4], fv[4], fw[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      load_row (vtx_val, n_vertices, id[q[k]], fu[k], fv[k], fw[k]);
+    }
+    if (ND) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+	fu[k] = resolve (fu[k], U, cell);
+	fv[k] = resolve (fv[k], V, cell);
+	fw[k] = resolve (fw[k], W, cell);
+      }
+    }
+    pu[plane] = lerp (lerp (fu[0], fu[1], tx), lerp (fu[2], fu[3], tx), ty);
+    pv[plane] = lerp (lerp (fv[0], fv[1], tx), lerp (fv[2], fv[3], tx), ty);
+    pw[plane] = lerp (lerp (fw[0], fw[1], tx), lerp (fw[2], fw[3], tx), ty);
+  }
+  u = lerp (pu[0], pu[1], tz);
+  v = lerp (pv[0], pv[1], tz);
+  w = lerp (pw[0], pw[1], tz);
+}
+
 /* gfs_interpolate (src/fluid.c:2697-2710) of U,V,W at p inside leaf L.
  * 3D: trilinear in the 8 corner values (gfs_interpolate_from_corners,
  * :2666-2681, written as nested linear interpolations);
@@ -362,34 +400,13 @@ __device__ __forceinline__ void interpolate (const DevTree & T, const DevField &
     const double tx = fma (x - L.cx, 0.5*inv, 0.5);
     const double ty = fma (y - L.cy, 0.5*inv, 0.5);
     const double tz = fma (z - L.cz, 0.5*inv, 0.5);
-    /* corners: 0(-,-,+) 1(+,-,+) 2(+,+,+) 3(-,+,+) 4(-,-,-) 5(+,-,-) 6(+,+,-) 7(-,+,-).
-       Evaluated one z-plane at a time (back: 4 5 7 6, front: 0 1 3 2) so that
-       only 12 corner values are live at once. */
-    const int cell = any_nodata ? cell_index<DIM, LATTICE> (T, L) : 0;
-    double pu[2], pv[2], pw[2];
-#pragma unroll
-    for (int plane = 0; plane < 2; plane++) {
-      const int q[4] = { plane ? 0 : 4, plane ? 1 : 5, plane ? 3 : 7, plane ? 2 : 6 };
-      double fu[4], fv[4], fw[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-	load_row (fld.vtx_val, T.n_vertices, id[q[k]], fu[k], fv[k], fw[k]);
-      }
-      if (any_nodata) {
-#pragma unroll
-	for (int k = 0; k < 4; k++) {
-	  fu[k] = resolve (fu[k], fld.u[0], cell);
-	  fv[k] = resolve (fv[k], fld.u[1], cell);
-	  fw[k] = resolve (fw[k], fld.u[2], cell);
-	}
-      }
-      pu[plane] = lerp (lerp (fu[0], fu[1], tx), lerp (fu[2], fu[3], tx), ty);
-      pv[plane] = lerp (lerp (fv[0], fv[1], tx), lerp (fv[2], fv[3], tx), ty);
-      pw[plane] = lerp (lerp (fw[0], fw[1], tx), lerp (fw[2], fw[3], tx), ty);
-    }
-    u = lerp (pu[0], pu[1], tz);
-    v = lerp (pv[0], pv[1], tz);
-    w = lerp (pw[0], pw[1], tz);
+    /* two copies of the form: fields with GFS_NODATA vertices are rare, and sharing one copy kept
+       six registers of cell-value addresses alive across the gathers of every particle */
+    if (any_nodata)
+      trilinear_rows<true> (fld.vtx_val, T.n_vertices, id, tx, ty, tz, fld.u[0], fld.u[1], fld.u[2],
+			    cell_index<DIM, LATTICE> (T, L), u, v, w);
+    else
+      trilinear_rows<false> (fld.vtx_val, T.n_vertices, id, tx, ty, tz, NULL, NULL, NULL, 0, u, v, w);
   }
   else {
     int4 id;

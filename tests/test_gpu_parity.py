@@ -107,6 +107,54 @@ def test_interpolate(kind, ctx):
         assert np.abs(got[comp][inside] - want[inside]).max() <= 1e-14 * scale
 
 
+@pytest.mark.parametrize("kind", ["uniform3", "ring3"])
+def test_interpolate_with_nodata_cells(kind, ctx):
+    """A field with GFS_NODATA cells: every vertex whose stencil touches one falls back to the
+    calling leaf's own value (gfs_cell_corner_value, src/fluid.c:3094-3097) -- the out-of-line
+    flavour of the trilinear form (trilinear_rows_nodata); a point inside a NODATA cell returns
+    NODATA (gfs_interpolate :2704-2705).  Uniform (lattice) and adaptive tree, against the oracle;
+    then one fused step of particles kept out of the NODATA cells, against the oracle."""
+    import copy
+    w = copy.copy(_world(kind))
+    rng = np.random.default_rng(17)
+    leaves = w.arrays.box_leaves
+    bad = rng.choice(leaves, max(8, len(leaves) // 200), replace=False)
+    w.u, w.v, w.w = w.u.copy(), w.v.copy(), w.w.copy()
+    w.u[bad[::3]] = capi.NODATA
+    w.v[bad[1::3]] = capi.NODATA
+    w.w[bad[2::3]] = capi.NODATA
+    sim, ptrs = helpers.matched_oracle(w)
+    ctx.upload_tree(w.tree)
+    ctx.upload_field(w.u, w.v, w.w)
+    n = 50_000
+    cols = [rng.uniform(-0.5, 0.5, n) for _ in range(3)]
+    got = ctx.interpolate(*cols)
+    touched = 0
+    for comp, f in enumerate((w.u, w.v, w.w)):
+        want = sim.interpolate(comp, *cols)
+        data = want != capi.NODATA
+        assert np.array_equal(got[comp] == capi.NODATA, ~data)
+        touched += int((~data).sum())
+        scale = np.abs(f[f != capi.NODATA]).max()
+        assert np.abs(got[comp][data] - want[data]).max() <= 1e-14 * scale
+    assert touched > 0
+    # the fused step (lattice kernel on uniform3) with the fallback active
+    parts = _particles(w, 20_000)
+    cells = ctx.locate(parts["x"], parts["y"], parts["z"])
+    # (a NODATA neighbour poisons the centred differences behind the lift force -- in the reference
+    # too: keep the particles whose leaf has a finite vorticity)
+    uc = np.unique(cells)
+    vort = np.asarray(ctx.vorticity(uc)).reshape(len(uc), -1)
+    poisoned = uc[~np.all(np.abs(vort) < 1e100, axis=1)]
+    keep = ~np.isin(cells, bad) & ~np.isin(cells, poisoned)
+    assert keep.sum() > 1000
+    parts = {k: v[keep] for k, v in parts.items()}
+    got = _run_step(ctx, w, parts)
+    ocells, want = helpers.oracle_step(sim, ptrs, w, parts)
+    assert np.array_equal(got["cell"], ocells)
+    _check_state(got, want, 3)
+
+
 def _run_step(ctx, w, parts, **kw):
     ctx.particles_upload(**parts)
     ctx.step(w.step_params(record_cells=True, record_forces=True, **kw))
