@@ -801,6 +801,7 @@ static int make_step (const gfsb200_step_params * p, DevStep * S)
   }
   S->rho = p->rho; S->mu = p->mu;
   S->inv_mu = p->mu != 0. ? 1./p->mu : 0.;
+  S->inv_rho = 1./p->rho;
   for (int a = 0; a < 3; a++) S->g[a] = p->g[a];
   S->cd_const = p->cd_const; S->cl_const = p->cl_const;
   S->cm_const = p->cm_const;

@@ -95,6 +95,7 @@ struct DevStep {
   int need_velocity;           /* any drag/lift in the list */
   double rho, mu;
   double inv_mu;               /* 1/mu for a constant viscosity (0 when mu == 0) */
+  double inv_rho;              /* 1/rho, correctly rounded on the host */
   double g[3];
   double cd_const, cl_const;   /* NaN = built-in law */
   double cm_const;             /* GfsForceAddedMass coefficient, NaN = 0.5 */
