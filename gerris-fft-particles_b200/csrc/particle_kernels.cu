@@ -1024,7 +1024,13 @@ struct LateShared {
  * field) and void fraction + force are reduced into the deposit buffer -- what
  * gfsb200_deposit_all does right after the step, without streaming the particles a second time
  * (136 instead of 112 + 88 algorithmic bytes per particle-step). */
-template <int DIM, bool LATTICE, unsigned PROG, int STAGES, int MINB, int WPIPE_WARPS, bool REC, bool DEP>
+/* STREAM: the particle stream is marked as such -- evict-first bulk loads, streaming stores -- so that
+ * it leaves the tables their L2 lines.  That pays when the tables fit the L2 (the adaptive configs:
+ * C5 with 200 M particles loses 6 % without it) and in the fused step + deposit kernel, whose second
+ * evaluation re-reads them; on a big uniform tree (C2: 102 MB of tables against 126 MB of L2) the plain
+ * step kernel is 1.5 % faster with ordinary loads and stores (profiles/README.md, round 2). */
+template <int DIM, bool LATTICE, unsigned PROG, int STAGES, int MINB, int WPIPE_WARPS, bool REC, bool DEP,
+	  bool STREAM = true>
 __global__ void __launch_bounds__(32*WPIPE_WARPS, MINB)
 step_kernel_wpipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_tiles, DevDeposit D)
 {
@@ -1051,7 +1057,7 @@ step_kernel_wpipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_til
 
   const int first = blockIdx.x*WPIPE_WARPS + warp, stride = gridDim.x*WPIPE_WARPS;
   uint64_t policy;
-  if (DEP)
+  if (STREAM)
     policy = pipe::policy_evict_first ();
   else
     asm volatile ("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(policy));
@@ -1123,11 +1129,7 @@ step_kernel_wpipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_til
 	}
 	if (S.track_escapes && left_domain<DIM, LATTICE> (T, x, y, z))
 	  record_escape<DIM> (S, P, i);
-	/* Cache policy of the particle stream, measured (profiles/README.md, round 2): the plain step
-	   kernel is 1.5 % faster with ordinary stores and no evict-first hint on the bulk loads (C2
-	   0.2319 -> 0.2288 ms, 2D 0.1858 -> 0.1825), the fused step + deposit kernel 1 % faster with
-	   streaming stores and evict-first loads (its second evaluation re-reads the tables) */
-	if (DEP) {
+	if (STREAM) {
 	  __stcs (P.x + i, x); __stcs (P.y + i, y); __stcs (P.vx + i, vx); __stcs (P.vy + i, vy);
 	  if (DIM == 3) {
 	    __stcs (P.z + i, z); __stcs (P.vz + i, vz);
@@ -1641,7 +1643,7 @@ static void launch_pipe (const DevTree * T, const DevField * F, const DevParticl
   step_kernel_pipe<DIM, LA, PR, ST, MB, TILE><<<grid, TILE, smem, st>>> (*T, *F, *P, *S, n_tiles);
 }
 
-template <int DIM, bool LA, unsigned PR, int ST, int MB, int WPIPE_WARPS, bool REC, bool DEP>
+template <int DIM, bool LA, unsigned PR, int ST, int MB, int WPIPE_WARPS, bool REC, bool DEP, bool STREAM = true>
 static void launch_wpipe (const DevTree * T, const DevField * F, const DevParticles * P,
 			  const DevStep * S, int n_sm, cudaStream_t st, const DevDeposit * D)
 {
@@ -1650,12 +1652,12 @@ static void launch_wpipe (const DevTree * T, const DevField * F, const DevPartic
   static bool configured = false;
   static int per_sm = MB;
   if (!configured) {
-    cudaFuncSetAttribute (step_kernel_wpipe<DIM, LA, PR, ST, MB, WPIPE_WARPS, REC, DEP>,
+    cudaFuncSetAttribute (step_kernel_wpipe<DIM, LA, PR, ST, MB, WPIPE_WARPS, REC, DEP, STREAM>,
 			  cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     /* persistent grid: as many CTAs per SM as the instance's registers and staging allow -- MB
        for the 72-register 3D kernels, more for the leaner ones (2D drag: 48 registers -> 10) */
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, step_kernel_wpipe<DIM, LA, PR, ST, MB, WPIPE_WARPS, REC, DEP>,
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, step_kernel_wpipe<DIM, LA, PR, ST, MB, WPIPE_WARPS, REC, DEP, STREAM>,
 						       32*WPIPE_WARPS, smem) == cudaSuccess && occ > MB &&
 	!getenv ("GFSB200_WPIPE_FIXED_GRID"))
       per_sm = occ;
@@ -1676,11 +1678,11 @@ static void launch_wpipe (const DevTree * T, const DevField * F, const DevPartic
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx (&cfg, step_kernel_wpipe<DIM, LA, PR, ST, MB, WPIPE_WARPS, REC, DEP>,
+    cudaLaunchKernelEx (&cfg, step_kernel_wpipe<DIM, LA, PR, ST, MB, WPIPE_WARPS, REC, DEP, STREAM>,
 			*T, *F, *P, *S, n_tiles, DEP ? *D : none);
     return;
   }
-  step_kernel_wpipe<DIM, LA, PR, ST, MB, WPIPE_WARPS, REC, DEP><<<grid, 32*WPIPE_WARPS, smem, st>>>
+  step_kernel_wpipe<DIM, LA, PR, ST, MB, WPIPE_WARPS, REC, DEP, STREAM><<<grid, 32*WPIPE_WARPS, smem, st>>>
     (*T, *F, *P, *S, n_tiles, DEP ? *D : none);
 }
 
@@ -1719,10 +1721,14 @@ int gfsb200_launch_step (const DevTree * T, const DevField * F, const DevParticl
        7: 6 CTAs/SM (80 registers).  The force-recording and the deposit-fusing flavours exist for
        the compile-time force lists at 7 CTAs/SM only. */
     const bool fuse = D != NULL && !rec && prog != 0 && mode != 7;
+    /* vertex + vorticity tables against the L2 (see STREAM); lattice trees: 48 B per vertex and leaf in 3D */
+    const bool big_tables = lat && (double) T->n_vertices*(T->dim == 3 ? 48. : 24.) > 20e6 &&
+      !getenv ("GFSB200_STREAM_HINT");
 #define WP_ST(D_, LA, PR) do { \
       if (rec) launch_wpipe<D_, LA, PR, 2, 7, 4, true, false> (T, F, P, S, n_sm, st, NULL); \
       else if (fuse) launch_wpipe<D_, LA, PR, 2, 7, 4, false, true> (T, F, P, S, n_sm, st, D); \
       else if (mode == 7) launch_wpipe<D_, LA, PR, 2, 6, 4, false, false> (T, F, P, S, n_sm, st, NULL); \
+      else if (LA && big_tables) launch_wpipe<D_, LA, PR, 2, 7, 4, false, false, !LA> (T, F, P, S, n_sm, st, NULL); \
       else launch_wpipe<D_, LA, PR, 2, 7, 4, false, false> (T, F, P, S, n_sm, st, NULL); } while (0)
 #define WP_ST0(D_, LA) do { \
       if (mode == 7) launch_wpipe<D_, LA, 0, 2, 6, 4, false, false> (T, F, P, S, n_sm, st, NULL); \
