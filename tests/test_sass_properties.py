@@ -44,7 +44,9 @@ def test_library_is_sm_100a_only():
 # the C2 / C3 production instances: 3D, lattice or not, drag+lift+buoyancy, 2 stages, 7 CTAs x 4 warps
 @pytest.mark.parametrize("lattice", [1, 0])
 def test_warp_pipelined_step_kernel(sass, lattice):
-    code = _one(sass, r"step_kernel_wpipeILi3ELb%dELj801ELi2ELi7ELi4ELb0ELb0E" % lattice)
+    # (last flag, round 2: the stream policy -- ordinary loads / stores on the big uniform tree,
+    # evict-first + streaming stores on the adaptive ones)
+    code = _one(sass, r"step_kernel_wpipeILi3ELb%dELj801ELi2ELi7ELi4ELb0ELb0ELb%dE" % (lattice, 1 - lattice))
     # the particle stream comes in through the TMA engine onto mbarriers
     assert code.count("UBLKCP") == 3 * 8            # prologue (2 stages) + refill, 8 columns each
     assert "SYNCS.PHASECHK.TRANS64.TRYWAIT" in code and "SYNCS.ARRIVE.TRANS64" in code
@@ -63,7 +65,7 @@ def test_warp_pipelined_step_kernel(sass, lattice):
 def test_fused_step_deposit_kernel(sass, lattice):
     """the two-way flavour of the same kernel (round 2): same TMA pipeline, no spills, and the
     deposits leave as fp64 reductions without a return value (a remote owner costs no round trip)"""
-    code = _one(sass, r"step_kernel_wpipeILi3ELb%dELj801ELi2ELi7ELi4ELb0ELb1E" % lattice)
+    code = _one(sass, r"step_kernel_wpipeILi3ELb%dELj801ELi2ELi7ELi4ELb0ELb1ELb1E" % lattice)
     assert code.count("UBLKCP") == 3 * 8
     assert "BAR.SYNC" not in code
     assert not re.search(r"\b(LDL|STL)\b", code)
@@ -77,7 +79,7 @@ def test_fused_step_deposit_kernel(sass, lattice):
 def test_force_recording_step_kernel(sass):
     """the flavour the GModule uses (GfsParticulate.force is part of the object): three more
     column stores on the same pipeline"""
-    code = _one(sass, r"step_kernel_wpipeILi3ELb1ELj801ELi2ELi7ELi4ELb1ELb0E")
+    code = _one(sass, r"step_kernel_wpipeILi3ELb1ELj801ELi2ELi7ELi4ELb1ELb0ELb1E")
     assert code.count("UBLKCP") == 3 * 8
     assert not re.search(r"\b(LDL|STL)\b", code)
     # six state columns (ordinary stores since round 2: measured faster in the kernels without the
