@@ -512,7 +512,11 @@ extern "C" int gfsb200_internal_field_buffers (gfsb200_ctx * c, const int presen
   const size_t bytes = (size_t) c->T.n_cells*sizeof (double);
   for (int i = 0; i < 5; i++) {
     if (present[i]) {
-      if (!c->d_field[i]) CK (cudaMalloc ((void **) &c->d_field[i], bytes));
+      /* (+ 16: the bulk staging of lattice_cell_pass_kernel reads one cell past the last leaf) */
+      if (!c->d_field[i]) {
+	CK (cudaMalloc ((void **) &c->d_field[i], bytes + 16));
+	CK (cudaMemsetAsync (c->d_field[i] + c->T.n_cells, 0, 16, c->stream));
+      }
     }
     else if (c->d_field[i]) {
       CK (cudaStreamSynchronize (c->stream));

@@ -534,11 +534,10 @@ __device__ __forceinline__ void cp_async8 (double * smem_dst, const double * gme
 }
 
 /* issue the asynchronous copies of one brick's region into buffer `buf` */
-__device__ __forceinline__ void stage_brick (const DevTree & T, const DevField & fld, int brick,
+__device__ __forceinline__ void stage_brick (const DevTree & T, const DevField & fld, int bx, int by, int bz,
 					      double (* buf)[REG*PLANE], unsigned (* key)[REG])
 {
-  const int nn = T.lattice_n1 - 1, nb = nn/BRICK;
-  const int bx = brick % nb, by = (brick/nb) % nb, bz = brick/(nb*nb);
+  const int nn = T.lattice_n1 - 1;
   /* Morton key of region cell (x,y,z) = key[0][x] | key[1][y] | key[2][z]; 0xffffffff marks a
      coordinate outside the lattice */
   if (threadIdx.x < 3*REG) {
@@ -569,20 +568,121 @@ __device__ __forceinline__ void stage_brick (const DevTree & T, const DevField &
   asm volatile ("cp.async.commit_group;" ::: "memory");
 }
 
+/* BULK staging (round 2).  The 512 leaves of a brick are CONSECUTIVE cells of the flat tree (Morton
+ * order), so they need no gather: one bulk copy per component (cp.async.bulk, 4 KB, issued by one
+ * thread, landing on an mbarrier) brings them into a staging array, and the CTA moves them from there
+ * into the (x,y,z)-indexed region -- 2 x 3 LDS/STS per thread, conflict-free on the load side --
+ * while only the 488 halo cells still come as 8-byte LDGSTS gathers.  The gathers were the largest
+ * single item on the L1 data pipe, the busiest unit of this kernel (72 %): 94 LDGSTS per brick, 20
+ * sectors each.  The flat index of a brick's first leaf is odd (level_start = 1 + 8 + ... is), so the
+ * copy starts one cell early to be 16-byte aligned and takes one cell more at the end; the field
+ * arrays are allocated with that one cell of slack. */
+#define STG_CELLS (BRICK*BRICK*BRICK + 2)
+
+__device__ __forceinline__ void stage_brick_bulk (const DevTree & T, const DevField & fld, int bx, int by, int bz,
+						   double (* buf)[REG*PLANE], unsigned (* key)[REG],
+						   double (* stg)[STG_CELLS], uint64_t * bar)
+{
+  const int nn = T.lattice_n1 - 1;
+  const unsigned bar_a = (unsigned) __cvta_generic_to_shared (bar);
+  if (threadIdx.x < 3*REG) {
+    const int axis = threadIdx.x/REG, l = threadIdx.x % REG;
+    const int g = (axis == 0 ? bx : axis == 1 ? by : bz)*BRICK - 1 + l;
+    unsigned k = 0xffffffffu;
+    if ((unsigned) g < (unsigned) nn)
+      k = axis == 0 ? spread_bits3 (g) : spread_bits3 (~g & (nn - 1)) << axis;
+    key[axis][l] = k;
+  }
+  if (threadIdx.x == 0) {
+    asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_a) : "memory");
+    asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads ();
+  /* first leaf of the brick: the key with the three low bits of every coordinate cleared (y and z enter
+     the key inverted: the brick's cells are the 512 keys above it) */
+  const int first = T.top_start + (int) ((key[0][1] | key[1][1] | key[2][1]) & ~511u);
+  const int off = first & 1;
+  if (threadIdx.x == 0) {
+    const unsigned bytes = (unsigned) ((BRICK*BRICK*BRICK + 2*off)*sizeof (double));
+    asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_a), "r"(3*bytes) : "memory");
+#pragma unroll
+    for (int f = 0; f < 3; f++)
+      asm volatile ("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		    :: "r"((unsigned) __cvta_generic_to_shared (&stg[f][0])), "l"(fld.u[f] + (first - off)),
+		       "r"(bytes), "r"(bar_a) : "memory");
+  }
+  /* the halo: planes lz = 0 and 9 (100 cells each), then the ring of 36 cells around each of the 8
+     planes between them */
+  const double * __restrict__ U = fld.u[0], * __restrict__ V = fld.u[1], * __restrict__ W = fld.u[2];
+  constexpr int N_HALO = REG*REG*REG - BRICK*BRICK*BRICK;
+#pragma unroll
+  for (int it = 0; it < (N_HALO + 255)/256; it++) {
+    const int hcell = threadIdx.x + 256*it;
+    if (hcell < N_HALO) {
+      int lx, ly, lz;
+      if (hcell < 2*REG*REG) {
+	lz = hcell < REG*REG ? 0 : REG - 1;
+	const int q = hcell < REG*REG ? hcell : hcell - REG*REG;
+	ly = q/REG; lx = q - ly*REG;
+      }
+      else {
+	const int h2 = hcell - 2*REG*REG, ring = 4*REG - 4;
+	lz = 1 + h2/ring;
+	const int q = h2 - (lz - 1)*ring;
+	if (q < REG) { ly = 0; lx = q; }
+	else if (q < 2*REG) { ly = REG - 1; lx = q - REG; }
+	else { ly = 1 + ((q - 2*REG) >> 1); lx = (q & 1) ? REG - 1 : 0; }
+      }
+      const unsigned kx = key[0][lx], ky = key[1][ly], kz = key[2][lz];
+      const int o = lz*PLANE + ly*REG + lx;
+      if (kx != 0xffffffffu && ky != 0xffffffffu && kz != 0xffffffffu) {
+	const int c = T.top_start + (int) (kx | ky | kz);
+	cp_async8 (&buf[0][o], U + c); cp_async8 (&buf[1][o], V + c); cp_async8 (&buf[2][o], W + c);
+      }
+      else
+	buf[0][o] = buf[1][o] = buf[2][o] = 0.;
+    }
+  }
+  asm volatile ("cp.async.commit_group;" ::: "memory");
+  /* the bulk copies have landed (phase 0 of the barrier) */
+  asm volatile ("{\n\t.reg .pred p;\n\t"
+		"WAIT_%=:\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+		"@p bra DONE_%=;\n\t"
+		"bra WAIT_%=;\n\t"
+		"DONE_%=:\n\t}" :: "r"(bar_a) : "memory");
+  /* staging (Morton order within the brick: x bits direct, y and z bits inverted) -> region */
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    const int m = threadIdx.x + 256*half;
+    const int lx = (m & 1) | ((m >> 2) & 2) | ((m >> 4) & 4);
+    const int ly = 7 - (((m >> 1) & 1) | ((m >> 3) & 2) | ((m >> 5) & 4));
+    const int lz = 7 - (((m >> 2) & 1) | ((m >> 4) & 2) | ((m >> 6) & 4));
+    const int o = (lz + 1)*PLANE + (ly + 1)*REG + lx + 1;
+#pragma unroll
+    for (int f = 0; f < 3; f++)
+      buf[f][o] = stg[f][off + m];
+  }
+}
+
 /* One CTA per brick, 4 CTAs per SM (64 registers: the 24 shared loads of a vertex are in flight
  * together).  A persistent variant with two region buffers (the next brick's copies in flight
  * during the compute phase) measured 1.6x SLOWER; dropped. */
-template <int PATTERN>
+template <int PATTERN, bool BULK = false>
 __global__ void __launch_bounds__(256, 4)
 lattice_cell_pass_kernel (DevTree T, DevField fld)
 {
   __shared__ double sh[3][REG*PLANE];
   __shared__ unsigned key[3][REG];
+  __shared__ __align__(16) double stg[BULK ? 3 : 1][BULK ? STG_CELLS : 2];
+  __shared__ uint64_t stg_bar;
   /* the step kernel behind this one is launched programmatically (its prologue touches the
      particle stream only): once every brick has started, its CTAs may take the SM slots the last
      wave of bricks frees, and wait there for this grid to finish (griddepcontrol.wait) */
   asm volatile ("griddepcontrol.launch_dependents;" ::: "memory");
-  const int n1 = T.lattice_n1, nn = n1 - 1, nb = nn/BRICK;
+  /* one CTA per brick, the grid is (nb, nb, nb): no division to find the brick's coordinates */
+  const int n1 = T.lattice_n1, nn = n1 - 1, nb = gridDim.x;
+  const int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
 
   /* a warp = 8 x by 4 z at one y: with the padded plane stride its 64-bit shared loads are
      conflict-free, and its 32-byte table rows form four 256-byte runs */
@@ -590,13 +690,16 @@ lattice_cell_pass_kernel (DevTree T, DevField fld)
   const double wgt = T.lattice_w;
   const int pattern = PATTERN >= 0 ? PATTERN : T.lattice_pattern;
 
-  const int brick = blockIdx.x;
-  stage_brick (T, fld, brick, sh, key);
+  if (BULK)
+    stage_brick_bulk (T, fld, bx, by, bz, sh, key, reinterpret_cast<double (*)[STG_CELLS]> (&stg[0][0]), &stg_bar);
+  else
+    stage_brick (T, fld, bx, by, bz, sh, key);
   asm volatile ("cp.async.wait_group 0;" ::: "memory");
   __syncthreads ();
   {
     const double (* reg)[REG*PLANE] = sh;
-    const int bx = brick % nb, by = (brick/nb) % nb, bz = brick/(nb*nb);
+    /* a brick off the hull: every leaf has all six neighbours (no case selection in the gradients) */
+    const bool inner = bx > 0 && bx < nb - 1 && by > 0 && by < nb - 1 && bz > 0 && bz < nb - 1;
 #pragma unroll
     for (int half = 0; half < 2; half++) {
       const int tz = tzq + 4*half;
@@ -642,7 +745,7 @@ lattice_cell_pass_kernel (DevTree T, DevField fld)
 	      *fld.nodata_flag = 1;
 	    }
 	  }
-	  gfsb200_row_store3 (fld.vtx_val, T.n_vertices, (int64_t) (k*n1 + j)*n1 + i, s0, s1, s2);
+	  gfsb200_row_store3 (fld.vtx_val, T.n_vertices, (k*n1 + j)*n1 + i, s0, s1, s2);
 	}
       }
       /* ---- the leaf itself.  gfs_center_gradient (src/fluid.c:434-475) with same-level leaf
@@ -660,11 +763,24 @@ lattice_cell_pass_kernel (DevTree T, DevField fld)
 	  const bool has_up = kc < nn - 1, has_dn = kc > 0;
 	  return has_up ? (has_dn ? (up + dn)/2. : up) : (has_dn ? dn : 0.);
 	};
+	auto grad_inner = [&] (int f, int plus, int st) -> double {
+	  const double v0 = c[f][0];
+	  const double up = c[f][plus] - v0, dn = v0 - reg[f][r0 - st];
+	  return (up + dn)/2.;
+	};
 	/* neighbour in direction 2c is +axis c, 2c + 1 is -axis c (FttDirection); c[f][1|2|4] = +x|+y|+z */
-	const double wx = (grad (2, 2, REG, ky) - grad (1, 4, PLANE, kz))*inv_size;
-	const double wy = (grad (0, 4, PLANE, kz) - grad (2, 1, 1, kx))*inv_size;
-	const double wz = (grad (1, 1, 1, kx) - grad (0, 2, REG, ky))*inv_size;
-	gfsb200_row_store3 (fld.vort, T.n_cells, (int64_t) (kz*nn + ky)*nn + kx, wx, wy, wz);
+	double wx, wy, wz;
+	if (inner) {
+	  wx = (grad_inner (2, 2, REG) - grad_inner (1, 4, PLANE))*inv_size;
+	  wy = (grad_inner (0, 4, PLANE) - grad_inner (2, 1, 1))*inv_size;
+	  wz = (grad_inner (1, 1, 1) - grad_inner (0, 2, REG))*inv_size;
+	}
+	else {
+	  wx = (grad (2, 2, REG, ky) - grad (1, 4, PLANE, kz))*inv_size;
+	  wy = (grad (0, 4, PLANE, kz) - grad (2, 1, 1, kx))*inv_size;
+	  wz = (grad (1, 1, 1, kx) - grad (0, 2, REG, ky))*inv_size;
+	}
+	gfsb200_row_store3 (fld.vort, T.n_cells, (kz*nn + ky)*nn + kx, wx, wy, wz);
       }
     }
     /* ---- vertices on the hull (a coordinate equal to 0 or nn): their stencils are the few
@@ -760,10 +876,13 @@ extern "C" void gfsb200_launch_cell_pass (const DevTree * T, const DevField * fl
   if (T->dim == 3 && T->lattice_bricks) {
     const int nb = (T->lattice_n1 - 1)/BRICK;
     gfsb200_launch_counter += 1;
-    if (T->lattice_pattern == REFERENCE_PATTERN)
-      lattice_cell_pass_kernel<REFERENCE_PATTERN><<<nb*nb*nb, 256, 0, stream>>> (*T, *fld);
+    static const bool bulk = !(getenv ("GFSB200_CELLPASS_BULK") && atoi (getenv ("GFSB200_CELLPASS_BULK")) == 0);
+    if (T->lattice_pattern == REFERENCE_PATTERN) {
+      if (bulk) lattice_cell_pass_kernel<REFERENCE_PATTERN, true><<<dim3 (nb, nb, nb), 256, 0, stream>>> (*T, *fld);
+      else lattice_cell_pass_kernel<REFERENCE_PATTERN><<<dim3 (nb, nb, nb), 256, 0, stream>>> (*T, *fld);
+    }
     else
-      lattice_cell_pass_kernel<-1><<<nb*nb*nb, 256, 0, stream>>> (*T, *fld);
+      lattice_cell_pass_kernel<-1><<<dim3 (nb, nb, nb), 256, 0, stream>>> (*T, *fld);
     return;
   }
   if (T->n_cells <= SMALL_TREE_CELLS) {
