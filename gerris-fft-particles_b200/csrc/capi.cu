@@ -439,6 +439,7 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
   CK (cudaMalloc ((void **) &c->F.vort, (size_t) n*ws*sizeof (double)));
   CK (cudaMemsetAsync (c->F.vort, 0, (size_t) n*ws*sizeof (double), c->stream));
   CK (cudaMalloc ((void **) &c->F.nodata_flag, sizeof (int)));
+  CK (cudaMemsetAsync (c->F.nodata_flag, 0xff, sizeof (int), c->stream));  /* -1: no epoch (they start at 1) */
   c->deposit_count = (int64_t) (1 + t->dim)*n;
   CK (cudaMalloc ((void **) &c->deposit_buf[0], (size_t) c->deposit_count*sizeof (double)));
   CK (cudaMemsetAsync (c->deposit_buf[0], 0, (size_t) c->deposit_count*sizeof (double), c->stream));
@@ -453,7 +454,8 @@ extern "C" int gfsb200_refresh_field (gfsb200_ctx * c)
   if (!c || !c->have_tree || !c->F.u[0])
     return gfsb200_fail (GFSB200_ERR_STATE, "refresh_field: no tree/field resident");
   CK (cudaSetDevice (c->device));
-  CK (cudaMemsetAsync (c->F.nodata_flag, 0, sizeof (int), c->stream));
+  /* a new epoch instead of clearing the flag (DevField.nodata_epoch) */
+  c->F.nodata_epoch = c->F.nodata_epoch >= 0x7ffffff0 ? 1 : c->F.nodata_epoch + 1;
   gfsb200_launch_cell_pass (&c->T, &c->F, c->n_sm, c->stream, c->aux_stream, c->ev_fork, c->ev_join);
   CK (cudaGetLastError ());
   c->have_field = true;
@@ -1373,6 +1375,7 @@ extern "C" int gfsb200_output_location (gfsb200_ctx * c, int nvar, const double 
     }
     tmp.vtx_val = vtx;
     tmp.nodata_flag = flag;
+    tmp.nodata_epoch = 1;
     CK (cudaMemsetAsync (flag, 0, sizeof (int), c->stream));
     gfsb200_launch_vertex_values (&c->T, &tmp, c->n_sm, c->stream);
     CK (cudaGetLastError ());

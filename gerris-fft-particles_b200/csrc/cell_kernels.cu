@@ -358,7 +358,7 @@ __device__ __forceinline__ void vertex_from_tables (const DevTree & T, const Dev
     if (nd0) s0 = GFSB200_NODATA;
     if (nd1) s1 = GFSB200_NODATA;
     if (nd2) s2 = GFSB200_NODATA;
-    *fld.nodata_flag = 1;
+    *fld.nodata_flag = fld.nodata_epoch;
   }
 }
 
@@ -369,7 +369,7 @@ __device__ __noinline__ void hull_vertex_3d (const int32_t * __restrict__ vtx_of
 					     const int32_t * __restrict__ vtx_cell,
 					     const double * __restrict__ vtx_w,
 					     const double * __restrict__ U, const double * __restrict__ V,
-					     const double * __restrict__ W, int * nodata_flag,
+					     const double * __restrict__ W, int * nodata_flag, int nodata_epoch,
 					     double * __restrict__ out, int64_t n_rows, int v)
 {
   const int b = vtx_off[v], e = vtx_off[v + 1];
@@ -385,7 +385,7 @@ __device__ __noinline__ void hull_vertex_3d (const int32_t * __restrict__ vtx_of
     if (nd0) s0 = GFSB200_NODATA;
     if (nd1) s1 = GFSB200_NODATA;
     if (nd2) s2 = GFSB200_NODATA;
-    *nodata_flag = 1;
+    *nodata_flag = nodata_epoch;
   }
   gfsb200_row_store3 (out, n_rows, v, s0, s1, s2);
 }
@@ -459,7 +459,7 @@ __device__ __forceinline__ void vertex_values_body (const DevTree & T, const Dev
 	  if (nd0) s0 = GFSB200_NODATA;
 	  if (nd1) s1 = GFSB200_NODATA;
 	  if (nd2) s2 = GFSB200_NODATA;
-	  *fld.nodata_flag = 1;
+	  *fld.nodata_flag = fld.nodata_epoch;
 	}
 	if (DIM == 2)
 	  reinterpret_cast<double2 *> (fld.vtx_val)[v] = make_double2 (s0, s1);
@@ -742,7 +742,7 @@ lattice_cell_pass_kernel (DevTree T, DevField fld)
 	      if (bad0) s0 = GFSB200_NODATA;
 	      if (bad1) s1 = GFSB200_NODATA;
 	      if (bad2) s2 = GFSB200_NODATA;
-	      *fld.nodata_flag = 1;
+	      *fld.nodata_flag = fld.nodata_epoch;
 	    }
 	  }
 	  gfsb200_row_store3 (fld.vtx_val, T.n_vertices, (k*n1 + j)*n1 + i, s0, s1, s2);
@@ -810,7 +810,7 @@ lattice_cell_pass_kernel (DevTree T, DevField fld)
 	  if (g < f && c[g >> 1] == ((g & 1) ? nn : 0))
 	    first = false;
 	if (first)
-	  hull_vertex_3d (T.vtx_off, T.vtx_cell, T.vtx_w, fld.u[0], fld.u[1], fld.u[2], fld.nodata_flag,
+	  hull_vertex_3d (T.vtx_off, T.vtx_cell, T.vtx_w, fld.u[0], fld.u[1], fld.u[2], fld.nodata_flag, fld.nodata_epoch,
 			  fld.vtx_val, T.n_vertices, (c[2]*n1 + c[1])*n1 + c[0]);
       }
     }

@@ -71,7 +71,9 @@ struct DevField {
   double * vtx_val;            /* 3D: [n_vertices] (u,v) rows + [n_vertices] w; 2D: [n_vertices][2] */
   double * vort;               /* 3D: [n_cells] (wx,wy) rows + [n_cells] wz; 2D: [..] (wz).  Indexed by cell, or on
 				  lattice trees by (kz*N + ky)*N + kx with N = lattice_n1 - 1 */
-  int * nodata_flag;           /* set by the cell pass when any vertex stencil touches GFS_NODATA */
+  int * nodata_flag;           /* the cell pass writes nodata_epoch here when a vertex stencil touches GFS_NODATA */
+  int nodata_epoch;            /* number of this field update: the flag is never cleared, a reader compares it
+				  with the epoch (one stream operation less per step than a memset) */
   /* GfsForceInertial / GfsForceAddedMass only */
   const double * uprev[3];     /* Un,Vn,Wn cell values */
   double * vtx_prev;           /* their vertex table, laid out like vtx_val */

@@ -398,7 +398,7 @@ __device__ __forceinline__ void interpolate (const DevTree & T, const DevField &
   /* half is a power of two: its inverse is an exponent flip, no division */
   const double inv = __longlong_as_double ((2046LL << 52) - __double_as_longlong (L.half));
   /* one uniform load decides whether any vertex needs the NODATA fallback */
-  const bool any_nodata = __ldg (fld.nodata_flag) != 0;
+  const bool any_nodata = __ldg (fld.nodata_flag) == fld.nodata_epoch;
   if (DIM == 3) {
     int id[8];
     if (LATTICE) {
