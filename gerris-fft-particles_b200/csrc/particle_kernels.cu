@@ -849,6 +849,13 @@ __device__ __forceinline__ void bulk_g2s (void * dst, const void * src, unsigned
 		:: "r"(smem_u32 (dst)), "l"(src), "r"(bytes), "r"(smem_u32 (bar)), "l"(policy) : "memory");
 }
 
+/* the same without a cache hint */
+__device__ __forceinline__ void bulk_g2s_plain (void * dst, const void * src, unsigned bytes, uint64_t * bar)
+{
+  asm volatile ("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		:: "r"(smem_u32 (dst)), "l"(src), "r"(bytes), "r"(smem_u32 (bar)) : "memory");
+}
+
 __device__ __forceinline__ void fence_async_shared ()
 {
   asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1056,17 +1063,17 @@ step_kernel_wpipe (DevTree T, DevField fld, DevParticles P, DevStep S, int n_til
   }
 
   const int first = blockIdx.x*WPIPE_WARPS + warp, stride = gridDim.x*WPIPE_WARPS;
-  uint64_t policy;
-  if (STREAM)
-    policy = pipe::policy_evict_first ();
-  else
-    asm volatile ("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(policy));
+  const uint64_t policy = STREAM ? pipe::policy_evict_first () : 0;
 
   auto issue = [&] (int s, int tile) {
     pipe::mbar_expect_tx (&full[warp][s], NC*COL_BYTES);
 #pragma unroll
-    for (int c = 0; c < NC; c++)
-      pipe::bulk_g2s (&buf[warp][s][c][0], col[c] + (int64_t) tile*32, COL_BYTES, &full[warp][s], policy);
+    for (int c = 0; c < NC; c++) {
+      if (STREAM)
+	pipe::bulk_g2s (&buf[warp][s][c][0], col[c] + (int64_t) tile*32, COL_BYTES, &full[warp][s], policy);
+      else
+	pipe::bulk_g2s_plain (&buf[warp][s][c][0], col[c] + (int64_t) tile*32, COL_BYTES, &full[warp][s]);
+    }
   };
 
   if (pipe::elect_one ()) {
