@@ -23,7 +23,12 @@ the sum of the segment times over the number of steps.
 Prints ONE JSON line (rank 0).  `value` is whole-job particle-steps/s with
 inputs resident in HBM; `e2e` is the same metric through the host-buffer
 C-ABI call (H2D of the particle arrays and the field, D2H of the new state
-inside the timed region); `roofline` describes the fused step kernel;
+inside the timed region); `roofline` describes the fused step kernel -- its
+launch duration is measured live, with CUDA events on the kernel's stream inside
+the library, around every 4th launch of the timed region (--kernel-timer-every;
+the events are stream operations between the cell pass and the step kernel and
+cost 1.5 % of a step when every launch carries them; `kernel_launches` is the
+number of launches averaged over);
 `cpu_baseline` is the reference's own object code (oracle/_ref/libgfsrefobj:
 modules/particulatecommon.c, src/event.c, src/particle.c, src/fluid.c, src/ftt.c
 compiled unmodified) running gfs_event_do on a GfsParticleList on one host core
@@ -385,6 +390,11 @@ def run_b200(args):
     capi, worlds = pkg.capi, pkg.worlds
     peak, peak_src = measured_peak()
     ctx = capi.Context(local_rank)
+    # The kernel-time events of the library are stream operations BETWEEN the cell pass and the step
+    # kernel: around every launch they cost 1.5 % of a C2 step (0.2885 vs 0.2835 ms).  They are
+    # recorded around every 4th launch of the timed region (--kernel-timer-every 1: all of them);
+    # roofline.kernel_launches says how many launches the average is over.
+    ctx.timer_sampling(args.kernel_timer_every)
     uid = [capi.comm_unique_id() if (rank == 0 and world_size > 1) else None]
     if world_size > 1:
         dist.broadcast_object_list(uid, src=0)
@@ -724,6 +734,10 @@ def run_b200(args):
                          "traffic": measured_traffic(args.config, n_local, world.dim), "peak_source": peak_src,
                          "algorithmic_bytes_per_particle_step": bps,
                          "kernel_ms": kernel_ms, "kernel_launches": kernel_launches,
+                         "kernel_timing": "CUDA events inside the library around every %s launch of the timed "
+                                          "region (%d of its %d step-kernel launches)" % (
+                                              "" if args.kernel_timer_every == 1 else "%dth" % args.kernel_timer_every,
+                                              kernel_launches, args.steps),
                          "whole_step_frac": n_local * bps / (ms / args.steps * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
@@ -795,6 +809,8 @@ def main():
                          "every ~15 steps at most in these configs and the step kernel slows by ~1 %% "
                          "over 100 steps without a re-sort, while one re-sort costs ~0.6 ms")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--kernel-timer-every", type=int, default=4,
+                    help="CUDA events around every n-th step-kernel launch (1: every launch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -161,6 +161,7 @@ def lib() -> C.CDLL:
         "gfsb200_comm_exchange_stats": (i32, [vp, C.POINTER(dbl), C.POINTER(i64), C.POINTER(i64)]),
         "gfsb200_timer_reset": (i32, [vp]),
         "gfsb200_timer_read": (i32, [vp, C.POINTER(dbl), C.POINTER(i64)]),
+        "gfsb200_timer_sampling": (i32, [vp, i32]),
         "gfsb200_kernel_launches": (i64, []),
     }
     for name, (res, args) in sig.items():
@@ -599,6 +600,10 @@ class Context:
 
     def timer_reset(self):
         _check(self._lib.gfsb200_timer_reset(self.handle), "timer_reset")
+
+    def timer_sampling(self, every: int):
+        """CUDA events around every `every`-th step-kernel launch only (1: all, 0: none)"""
+        _check(self._lib.gfsb200_timer_sampling(self.handle, int(every)), "timer_sampling")
 
     def timer_read(self):
         ms, n = C.c_double(), C.c_int64()

@@ -80,6 +80,8 @@ struct gfsb200_ctx {
   std::vector<cudaEvent_t> ev;
   size_t ev_used;
   bool timing;
+  int timer_every;             /* gfsb200_timer_sampling: events around every n-th launch (1: all, 0: none) */
+  long timer_calls;
 };
 
 /* comm.cu: the exchange of the deposited field between the GPUs of one box */

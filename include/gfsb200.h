@@ -478,6 +478,11 @@ int gfsb200_comm_exchange_stats (gfsb200_comm * m, double * ms, int64_t * n, int
  * the last reset, measured with CUDA events on the context's stream */
 int gfsb200_timer_reset (gfsb200_ctx * c);
 int gfsb200_timer_read (gfsb200_ctx * c, double * step_kernel_ms, int64_t * launches);
+/* time every `every`-th launch only (1, the default: all of them; 0: none).  The two events of a timed
+ * launch are stream operations between the cell pass and the step kernel -- they also keep the step
+ * kernel's programmatic launch from overlapping the cell pass -- and cost 1.5 % of a C2 step
+ * (profiles/README.md, round 2); a sample of the launches gives the same average. */
+int gfsb200_timer_sampling (gfsb200_ctx * c, int every);
 /* how many of this library's own CUDA kernels have been launched by the process so far (the
  * library kernels inside cub::DeviceRadixSort / DeviceSelect are not counted) */
 int64_t gfsb200_kernel_launches (void);
