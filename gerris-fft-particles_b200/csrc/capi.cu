@@ -365,6 +365,7 @@ extern "C" int gfsb200_upload_tree (gfsb200_ctx * c, const gfsb200_tree * t)
     const double c = T.root_pos[0][a], half = 0.5*T.root_size, lo = c - half, hi = c + half;
     slot_is_box = slot_is_box && T.la_min[a] == lo && lo + half == c && hi - half == c && lo + T.root_size == hi;
   }
+  T.slot_is_box = T.single_box && t->n_roots == 1 && slot_is_box;
   if (t->lattice_level >= 0 && t->lattice_level - t->root_level == T.top_levels && T.single_box &&
       t->n_roots == 1 && !any_destroyed && slot_is_box && !getenv ("GFSB200_NO_LATTICE"))
     T.lattice_n1 = (1 << T.top_levels) + 1;

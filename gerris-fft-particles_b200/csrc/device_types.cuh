@@ -20,6 +20,8 @@ struct DevTree {
   int top_levels;              /* complete_level - root_level: levels resolved arithmetically */
   int top_start;               /* level_start of the complete level */
   int single_box;              /* locate array has exactly one slot holding box root 0 */
+  int slot_is_box;             /* ... and that slot IS the box: same lower corner, same size, corners exact in fp64
+				  (host-checked) -- the slot test then implies the root test of ftt_cell_locate */
   int has_destroyed;           /* some cell of a GfsBox tree is destroyed (entirely solid): the hull test does
 				  not decide whether a point is inside the domain */
   double root_size;            /* ftt_level_size (root_level) */

@@ -172,8 +172,11 @@ __device__ __forceinline__ Located locate (const DevTree & T, double x, double y
   /* ftt_cell_locate, src/ftt.c:1535-1574: inclusive root test ... */
   double cx = T.root_pos[root][0], cy = T.root_pos[root][1], cz = DIM == 3 ? T.root_pos[root][2] : 0.;
   double half = 0.5*T.root_size;
-  if (x > cx + half || x < cx - half || y > cy + half || y < cy - half ||
-      (DIM == 3 && (z > cz + half || z < cz - half)))
+  /* (one box whose locate-array slot is the box itself: the slot test above has decided, see the
+     lattice path) */
+  if (!T.slot_is_box &&
+      (x > cx + half || x < cx - half || y > cy + half || y < cy - half ||
+       (DIM == 3 && (z > cz + half || z < cz - half))))
     return L;
 
   int cell = root;
