@@ -559,6 +559,25 @@ def test_lattice_cell_pass_equals_table_driven_kernels(level, ctx, monkeypatch):
             assert np.array_equal(corner_f[c].view(np.uint64), corner_t[c].view(np.uint64)), c
 
 
+def test_kernel_timer_sampling(ctx):
+    """gfsb200_timer_sampling: the library's kernel-time events around every n-th launch only
+    (1: all, 0: none); a reset starts a new sample with a timed launch."""
+    w, sim, ptrs, idx = setup("uniform3", ctx)
+    ctx.particles_upload(**_particles(w, 5000))
+    par = w.step_params()
+    try:
+        for every, want in ((1, 8), (4, 2), (3, 3), (0, 0)):
+            ctx.timer_sampling(every)
+            ctx.timer_reset()
+            for _ in range(8):
+                ctx.step(par)
+            ms, n = ctx.timer_read()
+            assert n == want, (every, n)
+            assert (ms > 0) == (want > 0)
+    finally:
+        ctx.timer_sampling(1)
+
+
 def test_empty_and_single_particle(ctx):
     w, sim, ptrs, idx = setup("uniform3", ctx)
     empty = {k: np.zeros(0) for k in ("x", "y", "z", "vx", "vy", "vz", "mass", "volume")}
