@@ -155,6 +155,8 @@ def lib() -> C.CDLL:
         "gfsb200_comm_rebalance": (i32, [C.POINTER(vp), i32]),
         "gfsb200_comm_split": (i32, [vp, vp]),
         "gfsb200_comm_splitters": (i32, [vp, C.c_int32, i32, vp]),
+        "gfsb200_comm_owner_table": (i32, [vp, vp]),
+        "gfsb200_comm_owner_slices": (i32, [vp, C.c_int32, C.c_int32, i32, vp, i32, vp]),
         "gfsb200_deposit_allreduce": (i32, [C.POINTER(vp), i32]),
         "gfsb200_deposit_wait": (i32, [vp]),
         "gfsb200_comm_set_exchange": (i32, [vp, i32]),
@@ -632,6 +634,18 @@ def comm_splitters(count: np.ndarray, nranks: int) -> np.ndarray:
     return split
 
 
+def comm_owner_slices(child0: np.ndarray, n_roots: int, dim: int, count: np.ndarray, nranks: int) -> np.ndarray:
+    """owner of every leaf (255: not a leaf) from the tree and the global per-cell particle counts: equal
+    shares along the depth-first leaf order (host only, no device needed)"""
+    c0 = np.ascontiguousarray(child0, dtype=np.int32)
+    cnt = np.ascontiguousarray(count, dtype=np.uint32)
+    assert len(c0) == len(cnt)
+    owner = np.zeros(len(c0), dtype=np.uint8)
+    _check(lib().gfsb200_comm_owner_slices(_ptr(c0), len(c0), n_roots, dim, _ptr(cnt), nranks, _ptr(owner)),
+           "comm_owner_slices")
+    return owner
+
+
 class Comm:
     """The communicators of THIS process (one per local context): `Comm.init_rank` for one
     process per GPU, `Comm.init_all` for one process driving several GPUs.  Every method is
@@ -695,6 +709,12 @@ class Comm:
         s = np.zeros(self.size + 1, dtype=np.int32)
         _check(self._lib.gfsb200_comm_split(self.handles[0], _ptr(s)), "comm_split")
         return s
+
+    def owner_table(self, n_cells: int) -> np.ndarray:
+        """the rank that owns every cell after the last rebalance (255: not a leaf)"""
+        o = np.full(n_cells, 255, dtype=np.uint8)
+        _check(self._lib.gfsb200_comm_owner_table(self.handles[0], _ptr(o)), "comm_owner_table")
+        return o
 
     def deposit_allreduce(self):
         _check(self._lib.gfsb200_deposit_allreduce(self._arr, self.n_local), "deposit_allreduce")

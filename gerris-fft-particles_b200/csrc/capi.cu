@@ -53,6 +53,7 @@ void gfsb200_launch_particle_bc (const DevTree *, const DevParticles *, int, con
 void gfsb200_launch_iota (int64_t, int32_t *, cudaStream_t);
 void gfsb200_launch_iota_u32 (int64_t, uint32_t *, uint32_t, cudaStream_t);
 void gfsb200_launch_sort_keys (int64_t, const int32_t *, uint32_t *, uint32_t, cudaStream_t);
+void gfsb200_launch_owner_keys (int64_t, const uint32_t *, uint32_t, const uint8_t *, uint32_t *, uint32_t, cudaStream_t);
 void gfsb200_launch_inside_flags (int64_t, const int32_t *, uint8_t *, cudaStream_t);
 void gfsb200_launch_outside_clear (int64_t, const int32_t *, uint8_t *, int *, cudaStream_t);
 cudaError_t gfsb200_cub_sort_pairs (void *, size_t *, const uint32_t *, uint32_t *, const int32_t *,
@@ -1075,6 +1076,27 @@ extern "C" int gfsb200_internal_sort (gfsb200_ctx * c)
   if (r) return r;
   CK (gfsb200_cub_sort_pairs (c->cub_tmp, &bytes, c->key, c->key2, c->perm, c->perm2, P.n, end_bit, c->stream));
   return apply_permutation (c, P.n);
+}
+
+/* Right after gfsb200_internal_sort: a STABLE re-sort of the cell-sorted list by the rank that owns each
+ * particle's cell (owner_of, device memory; particles outside the domain last), so that every rank's
+ * share is one contiguous stretch, still sorted by cell inside.  The sorted owner keys (nranks for the
+ * particles outside) are left in c->key2. */
+extern "C" int gfsb200_internal_sort_by_owner (gfsb200_ctx * c, const uint8_t * owner_of, int nranks)
+{
+  if (c->n <= 0) return GFSB200_OK;
+  const int64_t n = c->n;
+  gfsb200_launch_owner_keys (n, c->key2, (uint32_t) c->T.n_cells, owner_of, c->key, (uint32_t) nranks, c->stream);
+  gfsb200_launch_iota (n, c->perm, c->stream);
+  CK (cudaGetLastError ());
+  int end_bit = 1;
+  while (end_bit < 32 && (1u << end_bit) <= (uint32_t) nranks) end_bit++;
+  size_t bytes = 0;
+  CK (gfsb200_cub_sort_pairs (NULL, &bytes, c->key, c->key2, c->perm, c->perm2, n, end_bit, c->stream));
+  int r = ensure_cub_tmp (c, bytes);
+  if (r) return r;
+  CK (gfsb200_cub_sort_pairs (c->cub_tmp, &bytes, c->key, c->key2, c->perm, c->perm2, n, end_bit, c->stream));
+  return apply_permutation (c, n);
 }
 
 extern "C" int gfsb200_particles_sort (gfsb200_ctx * c)

@@ -228,6 +228,10 @@ struct gfsb200_comm {
   /* ownership */
   bool owner_valid;
   int32_t split[GFSB200_MAX_RANKS + 1];
+  bool by_owner;               /* adaptive trees: the slices are ranges of the depth-first leaf order (owner table) */
+  uint8_t * d_owner_of; int64_t owner_cap;
+  std::vector<uint8_t> owner_of;             /* host copy */
+  std::vector<int32_t> range_lo, range_hi;   /* the cell ranges that hold this rank's leaves (one per level at most) */
   uint32_t epoch;
   /* scratch */
   uint32_t * d_hist; int64_t hist_cap;
@@ -446,6 +450,7 @@ static int comm_new (gfsb200_ctx * c, int rank, int nranks, ncclComm_t nc, gfsb2
   m->owner_valid = false;
   m->epoch = 0;
   m->d_hist = NULL; m->hist_cap = 0;
+  m->by_owner = false; m->d_owner_of = NULL; m->owner_cap = 0;
   m->tev_used = 0; m->bytes_sent = 0;
   memset (m->peer_flags, 0, sizeof m->peer_flags);
   memset (m->peer_dep, 0, sizeof m->peer_dep);
@@ -557,6 +562,7 @@ extern "C" void gfsb200_comm_destroy (gfsb200_comm * m)
   cudaEventDestroy (m->ev_dep); cudaEventDestroy (m->ev_barrier); cudaEventDestroy (m->ev_x[0]); cudaEventDestroy (m->ev_x[1]);
   for (size_t i = 0; i < m->tev.size (); i++) cudaEventDestroy (m->tev[i]);
   cudaFree (m->flags); cudaFree (m->d_owners); cudaFree (m->d_small); cudaFree (m->d_info); cudaFree (m->d_hist);
+  cudaFree (m->d_owner_of);
   delete m;
 }
 
@@ -581,6 +587,7 @@ extern "C" void gfsb200_comm_tree_changed (gfsb200_comm * m)
   cudaStreamSynchronize (m->stream);
   close_peers (m);
   m->owner_valid = false;
+  m->by_owner = false;
   m->x_pending[0] = m->x_pending[1] = false;
   m->barrier_pending = false;
   m->dep_mode = m->dep_done = 0;
@@ -664,10 +671,71 @@ extern "C" int gfsb200_comm_splitters (const uint32_t * count, int32_t n_cells, 
   return GFSB200_OK;
 }
 
+/* Slices of the DEPTH-FIRST leaf order (adaptive trees).  The flat tree is level-ordered: a particle that
+ * crosses from a leaf into a neighbour of another level lands far away in the cell index, i.e. -- with
+ * slices of that index -- in another rank's slice (6 % of the C5 cloud after 20 steps).  In depth-first
+ * order neighbouring leaves of any level stay close.  child0[c]: first child of cell c (children are
+ * consecutive), < 0 for a leaf; the roots are cells 0 .. n_roots - 1; count[c]: particles in cell c.
+ * owner[c] = rank of leaf c, 255 for a cell that is not a leaf.  Equal shares as gfsb200_comm_splitters
+ * cuts them, along the depth-first order.  Within one level the owners are non-decreasing in the cell
+ * index (the level's cells are Morton-ordered), so a rank's leaves of one level sit in one range of cells
+ * that holds no other rank's leaf. */
+extern "C" int gfsb200_comm_owner_slices (const int32_t * child0, int32_t n_cells, int32_t n_roots, int dim,
+					  const uint32_t * count, int nranks, uint8_t * owner)
+{
+  if (!child0 || !count || !owner || n_cells < 0 || n_roots < 0 || n_roots > n_cells || nranks < 1 || nranks > 254 ||
+      (dim != 2 && dim != 3))
+    return gfsb200_fail (GFSB200_ERR_ARG, "comm_owner_slices: bad argument");
+  const int nc = 1 << dim;
+  std::vector<int32_t> leaves, stack;
+  leaves.reserve ((size_t) n_cells);
+  for (int32_t r = 0; r < n_roots; r++) {
+    stack.push_back (r);
+    while (!stack.empty ()) {
+      const int32_t c = stack.back ();
+      stack.pop_back ();
+      const int32_t c0 = child0[c];
+      if (c0 < 0) { leaves.push_back (c); continue; }
+      if (c0 + nc > n_cells)
+	return gfsb200_fail (GFSB200_ERR_ARG, "comm_owner_slices: child index out of range");
+      for (int k = nc - 1; k >= 0; k--) stack.push_back (c0 + k);
+    }
+  }
+  std::vector<uint32_t> cp (leaves.size ());
+  for (size_t i = 0; i < leaves.size (); i++) cp[i] = count[leaves[i]];
+  int32_t split[256];
+  int r = gfsb200_comm_splitters (cp.data (), (int32_t) leaves.size (), nranks, split);
+  if (r) return r;
+  memset (owner, 255, (size_t) n_cells);
+  int q = 0;
+  for (size_t i = 0; i < leaves.size (); i++) {
+    while (q + 1 < nranks && (int32_t) i >= split[q + 1]) q++;
+    owner[leaves[i]] = (uint8_t) q;
+  }
+  return GFSB200_OK;
+}
+
+/* owner of every cell after the last gfsb200_comm_rebalance (255: not a leaf / no owner) */
+extern "C" int gfsb200_comm_owner_table (const gfsb200_comm * m, uint8_t * owner)
+{
+  if (!m || !owner) return gfsb200_fail (GFSB200_ERR_ARG, "comm_owner_table: bad argument");
+  if (!m->owner_valid) return gfsb200_fail (GFSB200_ERR_STATE, "comm_owner_table: no rebalance since the tree was uploaded");
+  const int32_t n = m->c->T.n_cells;
+  if (m->by_owner)
+    memcpy (owner, m->owner_of.data (), (size_t) n);
+  else
+    for (int q = 0; q < m->nranks; q++)
+      for (int32_t c = m->split[q]; c < m->split[q + 1]; c++) owner[c] = (uint8_t) q;
+  return GFSB200_OK;
+}
+
 extern "C" int gfsb200_comm_split (const gfsb200_comm * m, int32_t * split)
 {
   if (!m || !split) return gfsb200_fail (GFSB200_ERR_ARG, "comm_split: bad argument");
   if (!m->owner_valid) return gfsb200_fail (GFSB200_ERR_STATE, "comm_split: no rebalance since the tree was uploaded");
+  if (m->by_owner)
+    return gfsb200_fail (GFSB200_ERR_STATE, "comm_split: on this (adaptive) tree the slices are ranges of the "
+			 "depth-first leaf order, not of the cell index: gfsb200_comm_owner_table");
   memcpy (split, m->split, (m->nranks + 1)*sizeof (int32_t));
   return GFSB200_OK;
 }
@@ -721,6 +789,31 @@ extern "C" int gfsb200_comm_rebalance (gfsb200_comm * const * local, int n_local
   }
   int32_t split[GFSB200_MAX_RANKS + 1];
   if ((r = gfsb200_comm_splitters (hist.data (), n_cells, R, split))) return r;
+  /* adaptive trees, several ranks: slices of the depth-first leaf order instead (gfsb200_comm_owner_slices) */
+  const bool by_owner = R > 1 && local[0]->c->T.lattice_n1 <= 0 && !getenv ("GFSB200_SLICES_BY_CELL");
+  std::vector<uint8_t> owner_of;
+  if (by_owner) {
+    gfsb200_ctx * c = local[0]->c;
+    std::vector<int32_t> child0 ((size_t) n_cells);
+    CK (cudaSetDevice (c->device));
+    CK (cudaMemcpyAsync (child0.data (), c->T.child0, (size_t) n_cells*sizeof (int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK (cudaStreamSynchronize (c->stream));
+    owner_of.resize ((size_t) n_cells);
+    if ((r = gfsb200_comm_owner_slices (child0.data (), n_cells, c->T.n_roots, c->T.dim, hist.data (), R, owner_of.data ())))
+      return r;
+    for (int k = 0; k < n_local; k++) {
+      gfsb200_comm * m = local[k];
+      CK (cudaSetDevice (m->c->device));
+      if (m->owner_cap < (int64_t) n_cells) {
+	cudaFree (m->d_owner_of); m->d_owner_of = NULL; m->owner_cap = 0;
+	CK (cudaMalloc ((void **) &m->d_owner_of, (size_t) n_cells));
+	m->owner_cap = n_cells;
+      }
+      CK (cudaMemcpyAsync (m->d_owner_of, owner_of.data (), (size_t) n_cells, cudaMemcpyHostToDevice, m->c->stream));
+      /* every rank's share becomes one contiguous stretch of the list (still cell-sorted inside) */
+      if ((r = gfsb200_internal_sort_by_owner (m->c, m->d_owner_of, R))) return r;
+    }
+  }
 
   /* 2. where the slices begin in every rank's sorted list; who sends how much to whom
      (one rank: the sorted list already is the one slice) */
@@ -731,7 +824,8 @@ extern "C" int gfsb200_comm_rebalance (gfsb200_comm * const * local, int n_local
     gfsb200_ctx * c = m->c;
     CK (cudaSetDevice (c->device));
     uint32_t bound[GFSB200_MAX_RANKS + 2];
-    for (int q = 0; q <= R; q++) bound[q] = (uint32_t) split[q];     /* bound[R] = n_cells: the particles outside */
+    for (int q = 0; q <= R; q++)       /* bound[R]: where the particles outside the domain begin */
+      bound[q] = by_owner ? (uint32_t) q : (uint32_t) split[q];
     uint32_t * d_bound = (uint32_t *) m->d_small;
     int32_t * d_pos = m->d_small + GFSB200_MAX_RANKS + 2;
     CK (cudaMemcpyAsync (d_bound, bound, (R + 1)*sizeof (uint32_t), cudaMemcpyHostToDevice, c->stream));
@@ -843,6 +937,21 @@ extern "C" int gfsb200_comm_rebalance (gfsb200_comm * const * local, int n_local
     gfsb200_ctx * c = m->c;
     CK (cudaSetDevice (c->device));
     memcpy (m->split, split, sizeof split);
+    m->by_owner = by_owner;
+    m->range_lo.clear (); m->range_hi.clear ();
+    if (by_owner) {
+      /* the ranges of cells that hold this rank's leaves: runs of the cell index without another rank's
+	 leaf in them (cells that are no leaves, 255, receive no deposit and may ride along), clipped to
+	 the leaves of the GfsBox trees */
+      m->owner_of = owner_of;
+      int32_t run_lo = -1, last = -1;
+      for (int32_t cell = c->leaf_lo; cell < c->leaf_hi; cell++) {
+	const uint8_t o = owner_of[(size_t) cell];
+	if (o == (uint8_t) m->rank) { if (run_lo < 0) run_lo = cell; last = cell; }
+	else if (o != 255 && run_lo >= 0) { m->range_lo.push_back (run_lo); m->range_hi.push_back (last + 1); run_lo = -1; }
+      }
+      if (run_lo >= 0) { m->range_lo.push_back (run_lo); m->range_hi.push_back (last + 1); }
+    }
     DevOwners own[2];
     memset (own, 0, sizeof own);
     for (int b = 0; b < 2; b++) {
@@ -920,6 +1029,10 @@ extern "C" int gfsb200_comm_prepare_deposit (gfsb200_comm * m, int what, bool lo
     }
     D->own_lo = lo; D->own_hi = hi;
     D->peers = m->nranks > 1 ? m->d_owners + t : NULL;
+    if (m->by_owner && m->nranks > 1) {
+      D->owner_of = m->d_owner_of;
+      D->self = m->rank;
+    }
     D->local_gpu_scope = getenv ("GFSB200_LOCAL_RED_GPU_SCOPE") != NULL;
   }
   m->dep_mode = mode;
@@ -935,6 +1048,17 @@ static void slice_leaves (const gfsb200_comm * m, int32_t * lo, int32_t * hi)
   *lo = m->split[m->rank] > m->c->leaf_lo ? m->split[m->rank] : m->c->leaf_lo;
   *hi = m->split[m->rank + 1] < m->c->leaf_hi ? m->split[m->rank + 1] : m->c->leaf_hi;
   if (*hi < *lo) *hi = *lo;
+}
+
+/* the same as a list of ranges: one (slice_leaves) when the slices are ranges of the cell index, the
+   per-level runs of the owner table on adaptive trees */
+static void slice_ranges (const gfsb200_comm * m, std::vector<int32_t> & lo, std::vector<int32_t> & hi)
+{
+  lo.clear (); hi.clear ();
+  if (m->by_owner) { lo = m->range_lo; hi = m->range_hi; return; }
+  int32_t a, b;
+  slice_leaves (m, &a, &b);
+  if (b > a) { lo.push_back (a); hi.push_back (b); }
 }
 
 static int stat_begin (gfsb200_comm * m)
@@ -984,10 +1108,10 @@ extern "C" int gfsb200_deposit_allreduce (gfsb200_comm * const * local, int n_lo
 	 pass; its next deposit kernel waits for ev_barrier (gfsb200_comm_prepare_deposit). */
       const int o = 1 - c->dep_which;
       const size_t n = c->T.n_cells;
-      int32_t lo, hi;
-      slice_leaves (m, &lo, &hi);
-      if (hi > lo)
-	CK (cudaMemset2DAsync (c->deposit_buf[o] + lo, n*sizeof (double), 0, (size_t) (hi - lo)*sizeof (double),
+      std::vector<int32_t> lo, hi;
+      slice_ranges (m, lo, hi);
+      for (size_t g = 0; g < lo.size (); g++)
+	CK (cudaMemset2DAsync (c->deposit_buf[o] + lo[g], n*sizeof (double), 0, (size_t) (hi[g] - lo[g])*sizeof (double),
 			       (size_t) c->T.dim + 1, m->stream));
       m->ahead_ok[o] = true;
       if (R == 1) {
@@ -1016,8 +1140,8 @@ extern "C" int gfsb200_deposit_allreduce (gfsb200_comm * const * local, int n_lo
       gfsb200_ctx * c = m->c;
       const int t = c->dep_which;
       const size_t n = c->T.n_cells;
-      int32_t lo, hi;
-      slice_leaves (m, &lo, &hi);
+      std::vector<int32_t> lo, hi;
+      slice_ranges (m, lo, hi);
       CK (cudaSetDevice (c->device));
       PeerFlags pf;
       for (int q = 0; q < GFSB200_MAX_RANKS; q++) pf.p[q] = q < R ? m->peer_flags[q] : NULL;
@@ -1032,16 +1156,19 @@ extern "C" int gfsb200_deposit_allreduce (gfsb200_comm * const * local, int n_lo
 	 peer and component (a strided cudaMemcpy2DAsync between peers measured 100 GB/s against
 	 320+ for plain copies), spread over a few streams so that several engines and links work
 	 at once. */
-      if (hi > lo) {
+      int64_t slice_cells = 0;
+      for (size_t g = 0; g < lo.size (); g++) slice_cells += hi[g] - lo[g];
+      if (slice_cells > 0) {
 	CK (cudaEventRecord (m->ev_fork, m->stream));
 	for (int j = 0; j < N_PUSH; j++)
 	  CK (cudaStreamWaitEvent (m->push[j], m->ev_fork, 0));
 	int k2 = 0;
 	for (int d = 1; d < R; d++) {
 	  const int q = (m->rank + d) % R;
-	  for (int comp = 0; comp <= c->T.dim; comp++, k2++)
-	    CK (cudaMemcpyAsync (m->peer_dep[t][q] + comp*n + lo, c->deposit_buf[t] + comp*n + lo,
-				 (size_t) (hi - lo)*sizeof (double), cudaMemcpyDefault, m->push[k2 % N_PUSH]));
+	  for (int comp = 0; comp <= c->T.dim; comp++)
+	    for (size_t g = 0; g < lo.size (); g++, k2++)
+	      CK (cudaMemcpyAsync (m->peer_dep[t][q] + comp*n + lo[g], c->deposit_buf[t] + comp*n + lo[g],
+				   (size_t) (hi[g] - lo[g])*sizeof (double), cudaMemcpyDefault, m->push[k2 % N_PUSH]));
 	}
 	for (int j = 0; j < N_PUSH; j++) {
 	  CK (cudaEventRecord (m->ev_join[j], m->push[j]));
@@ -1053,7 +1180,7 @@ extern "C" int gfsb200_deposit_allreduce (gfsb200_comm * const * local, int n_lo
       for (int q = 0; q < R; q++)
 	CK (cudaMemcpyAsync (m->peer_flags[q] + FLAG_DONE*GFSB200_MAX_RANKS + m->rank,
 			     m->flags + FLAG_SRC*GFSB200_MAX_RANKS, sizeof (uint32_t), cudaMemcpyDefault, m->stream));
-      m->bytes_sent = (int64_t) (R - 1)*(c->T.dim + 1)*(hi - lo)*(int64_t) sizeof (double);
+      m->bytes_sent = (int64_t) (R - 1)*(c->T.dim + 1)*slice_cells*(int64_t) sizeof (double);
     }
   }
   for (int k = 0; k < n_local; k++) {

@@ -92,6 +92,7 @@ void gfsb200_comm_detach (gfsb200_comm * m);
 int gfsb200_comm_check (gfsb200_comm * m);
 /* capi.cu internals comm.cu builds on */
 int gfsb200_internal_sort (gfsb200_ctx * c);                 /* sort by cell; sorted keys left in c->key2 */
+int gfsb200_internal_sort_by_owner (gfsb200_ctx * c, const uint8_t * owner_of, int nranks);
 int gfsb200_internal_reserve (gfsb200_ctx * c, int64_t n);   /* capacity for n particles, contents kept */
 int gfsb200_internal_ensure_aux (gfsb200_ctx * c, int64_t n);
 int gfsb200_internal_field_buffers (gfsb200_ctx * c, const int present[5]);

@@ -140,6 +140,9 @@ struct DevDeposit {
   double * local;              /* this rank's buffer, [1 + dim][n_cells] */
   int64_t n_cells;
   int32_t own_lo, own_hi;      /* cells [own_lo, own_hi) are this rank's: plain local atomics */
+  const uint8_t * owner_of;    /* [n_cells] or NULL: the owning rank of every leaf when the slices are ranges of the
+				  depth-first leaf order (adaptive trees) instead of ranges of the cell index */
+  int self;                    /* this rank (owner_of) */
   const DevOwners * peers;     /* device memory; NULL: one rank, everything is local */
   int local_gpu_scope;         /* experiment (GFSB200_LOCAL_RED_GPU_SCOPE): reductions into the own slice at GPU
 				  scope even though peers reduce into it at system scope */

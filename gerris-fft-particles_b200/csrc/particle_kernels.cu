@@ -642,7 +642,15 @@ __device__ __forceinline__ void total_force (const DevTree & T, const DevField &
  * the rank's cells since the last gfsb200_comm_rebalance */
 __device__ __forceinline__ double * owner_base (const DevDeposit & D, int cell)
 {
-  if (D.peers == NULL || (cell >= D.own_lo && cell < D.own_hi))
+  if (D.peers == NULL)
+    return D.local;
+  if (D.owner_of) {
+    /* adaptive trees: slices of the depth-first leaf order, looked up per cell (one byte; only the
+       head of a run of equal cells gets here) */
+    const int r = D.owner_of[cell];
+    return r == D.self ? D.local : D.peers->base[r];
+  }
+  if (cell >= D.own_lo && cell < D.own_hi)
     return D.local;
   int r = 0;
   const int n = D.peers->n;
@@ -1428,6 +1436,19 @@ __global__ void sort_keys_kernel (int64_t n, const int32_t * __restrict__ cell,
   if (i < n) key[i] = cell[i] < 0 ? outside_key : (uint32_t) cell[i];
 }
 
+/* key[i] = owner of the cell particle i sits in (sorted cell keys of the last sort; a key >= n_cells:
+ * outside the domain -> `outside_key') */
+__global__ void owner_keys_kernel (int64_t n, const uint32_t * __restrict__ cell_key, uint32_t n_cells,
+				   const uint8_t * __restrict__ owner_of, uint32_t * __restrict__ key,
+				   uint32_t outside_key)
+{
+  const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n) {
+    const uint32_t c = cell_key[i];
+    key[i] = c < n_cells ? (uint32_t) owner_of[c] : outside_key;
+  }
+}
+
 __global__ void inside_flag_kernel (int64_t n, const int32_t * __restrict__ cell,
 				    uint8_t * __restrict__ flag)
 {
@@ -1960,6 +1981,13 @@ void gfsb200_launch_sort_keys (int64_t n, const int32_t * cell, uint32_t * key,
 {
   gfsb200_launch_counter += 1;
   if (n > 0) sort_keys_kernel<<<grid_for (n, 256), 256, 0, st>>> (n, cell, key, outside_key);
+}
+
+void gfsb200_launch_owner_keys (int64_t n, const uint32_t * cell_key, uint32_t n_cells, const uint8_t * owner_of,
+				uint32_t * key, uint32_t outside_key, cudaStream_t st)
+{
+  gfsb200_launch_counter += 1;
+  if (n > 0) owner_keys_kernel<<<grid_for (n, 256), 256, 0, st>>> (n, cell_key, n_cells, owner_of, key, outside_key);
 }
 
 void gfsb200_launch_inside_flags (int64_t n, const int32_t * cell, uint8_t * flag, cudaStream_t st)

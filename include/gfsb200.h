@@ -447,10 +447,19 @@ int gfsb200_broadcast_field (gfsb200_comm * const * local, int n_local, int root
  * all-gather of the slices.  Particle ids travel with the particles; recorded forces do not.
  * Call it where a single GPU would call gfsb200_particles_sort. */
 int gfsb200_comm_rebalance (gfsb200_comm * const * local, int n_local);
-/* the slice boundaries of the last rebalance: split[0 .. size]; GFSB200_ERR_STATE before it */
+/* the slice boundaries of the last rebalance: split[0 .. size]; GFSB200_ERR_STATE before it, and on
+ * adaptive trees with several ranks, where the slices are ranges of the DEPTH-FIRST leaf order (a
+ * particle that crosses into a leaf of another level stays near its rank's slice; in the level-ordered
+ * cell index it would land in another rank's) -- there the owner of a leaf is looked up: */
 int gfsb200_comm_split (const gfsb200_comm * m, int32_t * split);
-/* host-only helper (exposed for tests): slice boundaries from the global per-cell particle counts */
+/* owner[c], c < n_cells: the rank that owns cell c after the last rebalance (255: not a leaf) */
+int gfsb200_comm_owner_table (const gfsb200_comm * m, uint8_t * owner);
+/* host-only helpers (exposed for tests): slice boundaries from the global per-cell particle counts;
+ * owners of the leaves from the tree (child0[c]: first of the 2^dim consecutive children of cell c, < 0
+ * for a leaf; roots: cells 0 .. n_roots - 1) and the counts, equal shares along the depth-first order */
 int gfsb200_comm_splitters (const uint32_t * count, int32_t n_cells, int nranks, int32_t * split);
+int gfsb200_comm_owner_slices (const int32_t * child0, int32_t n_cells, int32_t n_roots, int dim,
+			       const uint32_t * count, int nranks, uint8_t * owner);
 
 /* Sums the deposited field over the ranks: afterwards every rank holds sum_r deposit_r in the
  * buffer gfsb200_download_deposit reads.  Asynchronous: the exchange runs on a communication stream

@@ -159,3 +159,37 @@ def test_splitters_edge_cases():
     s = capi.comm_splitters(np.array([0, 5, 5, 0, 10, 0, 20, 0], dtype=np.uint32), 4)
     assert s[0] == 0 and s[-1] == 8 and np.all(np.diff(s) >= 0)
     assert list(capi.comm_splitters(np.array([3, 1, 2], dtype=np.uint32), 1)) == [0, 3]
+
+
+def test_owner_slices_follow_the_depth_first_leaf_order():
+    """gfsb200_comm_owner_slices (the product's host function behind gfsb200_comm_rebalance on adaptive
+    trees): the owners are non-decreasing along the depth-first leaf order, the shares are equal up to
+    one leaf's population, every leaf has an owner and no other cell has, and inside one level a rank's
+    leaves form ONE range of the (level-ordered) cell index that holds no other rank's leaf -- what the
+    exchange pushes and clears."""
+    w = worlds.make_ring("owners", 3, 6, 1000, 99)
+    a = w.arrays
+    rng = np.random.default_rng(3)
+    leaves = np.flatnonzero(a.child0 < 0)
+    count = np.zeros(a.n_cells, dtype=np.uint32)
+    count[a.box_leaves] = rng.integers(0, 40, len(a.box_leaves))
+    n_roots = int(np.sum(a.level == a.level.min()))
+    for ranks in (2, 3, 8):
+        owner = capi.comm_owner_slices(a.child0, n_roots, 3, count, ranks)
+        assert np.all(owner[leaves] < ranks) and np.all(np.delete(owner, leaves) == 255)
+        # depth-first order by hand
+        order, stack = [], list(range(n_roots))[::-1]
+        while stack:
+            c = stack.pop()
+            if a.child0[c] < 0:
+                order.append(c)
+            else:
+                stack.extend(range(a.child0[c] + 7, a.child0[c] - 1, -1))
+        order = np.array(order)
+        assert len(order) == len(leaves)
+        assert np.all(np.diff(owner[order].astype(int)) >= 0)
+        share = np.array([count[order][owner[order] == q].sum() for q in range(ranks)])
+        assert share.sum() == count.sum() and share.max() - share.min() <= 2 * 40
+        for lv in np.unique(a.level[leaves]):
+            cells = leaves[a.level[leaves] == lv]                 # ascending cell index
+            assert np.all(np.diff(owner[cells].astype(int)) >= 0), lv

@@ -68,11 +68,11 @@ def main():
 
     ctx.particles_upload(**mine, ids=ids)
     comm.rebalance()
-    split = comm.split()
+    owner = comm.owner_table(w.arrays.n_cells)
     got = ctx.particles_download(ids=True)
     c = ctx.locate(got["x"], got["y"], got["z"])
     assert np.all(np.diff(c) >= 0), "not sorted by cell"
-    assert np.all((c >= split[rank]) & (c < split[rank + 1])), "a particle outside the rank's slice"
+    assert np.all(owner[c] == rank), "a particle outside the rank's slice"
     counts = [None] * size
     dist.all_gather_object(counts, int(ctx.count))
     assert sum(counts) == n_total
@@ -114,7 +114,7 @@ def main():
             assert abs(vol - vp) <= 1e-12 * vp, (vol, vp)
             now = ctx.particles_download()
             cc = ctx.locate(now["x"], now["y"], now["z"])
-            drifted += int(np.sum((cc >= 0) & ((cc < split[rank]) | (cc >= split[rank + 1]))))
+            drifted += int(np.sum((cc >= 0) & (owner[np.maximum(cc, 0)] != rank)))
     total_drift = [None] * size
     dist.all_gather_object(total_drift, drifted)
     if comm.size > 1:
@@ -134,10 +134,10 @@ def main():
 
     # a second rebalance (the drifters go home) and one more exchange
     comm.rebalance()
-    split = comm.split()
+    owner = comm.owner_table(w.arrays.n_cells)
     now = ctx.particles_download()
     cc = ctx.locate(now["x"], now["y"], now["z"])
-    assert np.all((cc >= split[rank]) & (cc < split[rank + 1]))
+    assert np.all(owner[cc] == rank)
     ref.step(par); ref.deposit_all(par)
     ctx.step(par_f); comm.deposit_allreduce()
     for k in range(4):
@@ -146,7 +146,8 @@ def main():
     ms, n, sent = comm.exchange_stats()
     dist.barrier()
     if rank == 0:
-        print(f"two-rank exchange ok: {size} ranks, peer access {comm.peer_access}, slices {list(split)}, "
+        share = [int(np.sum(owner == q)) for q in range(size)]
+        print(f"two-rank exchange ok: {size} ranks, peer access {comm.peer_access}, leaves per rank {share}, "
               f"{sum(total_drift)} drifter observations, exchange {ms:.3f} ms over {n} calls, {sent} bytes sent per rank",
               flush=True)
     comm.close()

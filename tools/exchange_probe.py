@@ -56,9 +56,9 @@ ms, cnt, sent = comm.exchange_stats()
 kms, _ = ctx.timer_read()
 now = ctx.particles_download()
 cc = ctx.locate(now["x"], now["y"], now["z"])
-sp = comm.split()
+owner = comm.owner_table(w.arrays.n_cells)
 out["fused_kernel_ms"] = kms
-out["drifters_fraction"] = float(np.mean((cc >= 0) & ((cc < sp[rank]) | (cc >= sp[rank + 1]))))
+out["drifters_fraction"] = float(np.mean((cc >= 0) & (owner[np.maximum(cc, 0)] != rank)))
 out["overlapped"] = {"transfer_ms": ms, "GBs": sent / (ms * 1e-3) / 1e9 if ms > 0 else None, "wall_ms_per_step": wall * 1e3}
 res = [None] * size
 dist.all_gather_object(res, out)
