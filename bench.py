@@ -104,12 +104,13 @@ class ClockSampler:
         nv, h = self._nv, self._h
         while not self._stop.is_set():
             try:
+                t0 = time.perf_counter()
                 sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 try:
                     why = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
                     why = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.rows.append((float(sm), int(why), time.perf_counter()))
+                self.rows.append((float(sm), int(why), t0, time.perf_counter()))
             except Exception:
                 pass
             time.sleep(self.period)
@@ -120,18 +121,30 @@ class ClockSampler:
             self._thread.start()
 
     def stop(self, t_begin=None, t_end=None):
-        """statistics over the samples taken inside [t_begin, t_end] (host clock)"""
+        """statistics over the samples whose NVML queries overlap [t_begin, t_end] (host clock).  The
+        headline region is a few milliseconds and one query can take that long on a busy GPU: when no
+        query overlaps it the window is widened (50 ms on either side -- the warm-up steps before and the
+        two-way region after run the same kernels --, then the whole run) and `window` says so."""
         self._stop.set()
         if self._thread:
             self._thread.join()
+        window = "all samples"
         if t_begin is not None:
-            self.rows = [r for r in self.rows if t_begin <= r[2] <= t_end]
+            window = "timed region"
+            rows = [r for r in self.rows if r[3] >= t_begin and r[2] <= t_end]
+            if not rows:
+                window = "timed region +- 50 ms"
+                rows = [r for r in self.rows if r[3] >= t_begin - 0.05 and r[2] <= t_end + 0.05]
+            if not rows:
+                window = "whole run (no NVML query overlapped the timed region)"
+                rows = list(self.rows)
+            self.rows = rows
         names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                  0x4: "sw_power_cap"}
         sm = [r[0] for r in self.rows]
         reasons = sorted({n for r in self.rows for bit, n in names.items() if r[1] & bit})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_sm,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def build_world(worlds, name, n_particles, level=0):
