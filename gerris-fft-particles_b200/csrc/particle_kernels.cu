@@ -1000,15 +1000,8 @@ __device__ __forceinline__ bool elect_one ()
   return pred != 0;
 }
 
-/* shared-memory load that cannot be scheduled before `dep` is known */
-__device__ __forceinline__ double lds_after (const double * p, double dep)
-{
-  double v;
-  asm volatile ("ld.shared.f64 %0, [%1];   // after %2" : "=d"(v) : "r"(smem_u32 (p)), "d"(dep));
-  return v;
-}
-
-/* the same from a shared-window address computed once per tile, column COL of the staged tile */
+/* shared-memory load that cannot be scheduled before `dep` is known: column COL of the staged tile,
+ * from the shared-window address of the lane's slot in column 0 (computed once per tile) */
 template <int COL>
 __device__ __forceinline__ double lds_col_after (uint32_t lane_addr, double dep)
 {
