@@ -652,7 +652,38 @@ def run_b200(args):
     clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
     configs = {}
     if not args.no_configs:
-        def short_run(name, w, n_here, steps, fill, two=False):
+        def balance_by_cost(w, step_fn, rounds=2):
+            """N > 1, adaptive tree: equal numbers of particles are not equal work (a particle in a deep
+            leaf costs more than one in a shallow leaf).  Every rank times its kernel over a few steps,
+            the shares of the next gfsb200_comm_rebalance are made inversely proportional to the measured
+            time per particle, twice -- outside the timed region, like the re-sort."""
+            if world_size == 1:
+                return None
+            share = np.full(world_size, 1.0 / world_size)
+            for _ in range(rounds):
+                ctx.timer_sampling(1)
+                ctx.timer_reset()
+                for i in range(4):
+                    step_fn(i)
+                if comm_pending[0]:
+                    comm.deposit_wait()
+                barrier()
+                k_ms, _ = ctx.timer_read()
+                ctx.timer_sampling(args.kernel_timer_every)
+                t = torch.zeros(world_size, device=device, dtype=torch.float64)
+                t[rank] = k_ms
+                dist.all_reduce(t)
+                t = t.cpu().numpy()
+                share = share * (t.mean() / t)
+                share /= share.sum()
+                comm.set_shares(share)
+                comm.rebalance()
+                barrier()
+            return [float(x) for x in share]
+
+        comm_pending = [False]
+
+        def short_run(name, w, n_here, steps, fill, two=False, balance=False):
             ctx.upload_tree(w.tree)
             ctx.upload_field(w.u, w.v, w.w)
             fill()
@@ -665,6 +696,7 @@ def run_b200(args):
             for i in range(3):
                 st(i)
             barrier()
+            shares = balance_by_cost(w, st) if balance else None
             ctx.timer_reset()
             t_ms, per = timed_steps(st, steps)
             k_ms, _ = ctx.timer_read()
@@ -691,6 +723,10 @@ def run_b200(args):
                     st2(i)
                 comm.deposit_wait()
                 barrier()
+                if balance:
+                    comm_pending[0] = True
+                    shares2 = balance_by_cost(w, st2)
+                    comm_pending[0] = False
                 ctx.timer_reset()
                 comm.exchange_stats()
                 t_ms2, per2 = timed_steps(st2, steps, tail=comm.deposit_wait)
@@ -701,6 +737,13 @@ def run_b200(args):
                                   "kernel_ms": k_ms2, "exchange_device_ms": x_ms2,
                                   "bytes_sent_per_rank": int(x_b2),
                                   "roofline_frac": ctx.count * 136 / (k_ms2 * 1e-3) / 1e9 / peak if k_ms2 > 0 else None}
+                if balance and shares2:
+                    out["two_way"]["shares"] = shares2
+            if balance and shares:
+                out["shares"] = shares
+                out["sharding"] = ("slices of the depth-first leaf order; shares inversely proportional to the "
+                                   "measured kernel time per particle (gfsb200_comm_set_shares), set outside the timed region")
+                comm.set_shares(None)
             return out
 
         w3 = worlds.make_c3(n_particles=10_000_000)
@@ -711,7 +754,8 @@ def run_b200(args):
         w5 = worlds.make_c5()
         n5 = args.c5_particles // world_size
         cols5 = device_cloud(torch, w5, n5, rank, device)
-        configs["C5"] = short_run("C5", w5, n5, 10, lambda: fill_from_device(torch, ctx, cols5, device), two=True)
+        configs["C5"] = short_run("C5", w5, n5, 10, lambda: fill_from_device(torch, ctx, cols5, device), two=True,
+                                  balance=world_size > 1)
         configs["C5"]["scaling"] = "strong: %d particles in total, 1/N per GPU; cloud drawn on the device" % (n5 * world_size)
         del cols5
         torch.cuda.empty_cache()

@@ -156,6 +156,7 @@ def lib() -> C.CDLL:
         "gfsb200_comm_split": (i32, [vp, vp]),
         "gfsb200_comm_splitters": (i32, [vp, C.c_int32, i32, vp]),
         "gfsb200_comm_owner_table": (i32, [vp, vp]),
+        "gfsb200_comm_set_shares": (i32, [vp, i32, vp]),
         "gfsb200_comm_owner_slices": (i32, [vp, C.c_int32, C.c_int32, i32, vp, i32, vp]),
         "gfsb200_deposit_allreduce": (i32, [C.POINTER(vp), i32]),
         "gfsb200_deposit_wait": (i32, [vp]),
@@ -709,6 +710,13 @@ class Comm:
         s = np.zeros(self.size + 1, dtype=np.int32)
         _check(self._lib.gfsb200_comm_split(self.handles[0], _ptr(s)), "comm_split")
         return s
+
+    def set_shares(self, share=None):
+        """target shares of the particles for the next rebalance (one positive number per rank of the
+        job; None: equal shares)"""
+        s = None if share is None else np.ascontiguousarray(share, dtype=np.float64)
+        assert s is None or len(s) == self.size
+        _check(self._lib.gfsb200_comm_set_shares(self._arr, self.n_local, _ptr(s)), "comm_set_shares")
 
     def owner_table(self, n_cells: int) -> np.ndarray:
         """the rank that owns every cell after the last rebalance (255: not a leaf)"""

@@ -228,6 +228,8 @@ struct gfsb200_comm {
   /* ownership */
   bool owner_valid;
   int32_t split[GFSB200_MAX_RANKS + 1];
+  double share_cum[GFSB200_MAX_RANKS + 1];   /* gfsb200_comm_set_shares: cumulative target shares (share_cum[R] = 1) */
+  bool shares_set;
   bool by_owner;               /* adaptive trees: the slices are ranges of the depth-first leaf order (owner table) */
   uint8_t * d_owner_of; int64_t owner_cap;
   std::vector<uint8_t> owner_of;             /* host copy */
@@ -451,6 +453,7 @@ static int comm_new (gfsb200_ctx * c, int rank, int nranks, ncclComm_t nc, gfsb2
   m->epoch = 0;
   m->d_hist = NULL; m->hist_cap = 0;
   m->by_owner = false; m->d_owner_of = NULL; m->owner_cap = 0;
+  m->shares_set = false;
   m->tev_used = 0; m->bytes_sent = 0;
   memset (m->peer_flags, 0, sizeof m->peer_flags);
   memset (m->peer_dep, 0, sizeof m->peer_dep);
@@ -680,8 +683,18 @@ extern "C" int gfsb200_comm_splitters (const uint32_t * count, int32_t n_cells, 
  * cuts them, along the depth-first order.  Within one level the owners are non-decreasing in the cell
  * index (the level's cells are Morton-ordered), so a rank's leaves of one level sit in one range of cells
  * that holds no other rank's leaf. */
+static int owner_slices (const int32_t * child0, int32_t n_cells, int32_t n_roots, int dim,
+			 const uint32_t * count, int nranks, const double * cum, uint8_t * owner);
+static void splitters_by_share (const uint32_t * count, int32_t n_cells, int nranks, const double * cum, int32_t * split);
+
 extern "C" int gfsb200_comm_owner_slices (const int32_t * child0, int32_t n_cells, int32_t n_roots, int dim,
 					  const uint32_t * count, int nranks, uint8_t * owner)
+{
+  return owner_slices (child0, n_cells, n_roots, dim, count, nranks, NULL, owner);
+}
+
+static int owner_slices (const int32_t * child0, int32_t n_cells, int32_t n_roots, int dim,
+			 const uint32_t * count, int nranks, const double * cum, uint8_t * owner)
 {
   if (!child0 || !count || !owner || n_cells < 0 || n_roots < 0 || n_roots > n_cells || nranks < 1 || nranks > 254 ||
       (dim != 2 && dim != 3))
@@ -704,8 +717,12 @@ extern "C" int gfsb200_comm_owner_slices (const int32_t * child0, int32_t n_cell
   std::vector<uint32_t> cp (leaves.size ());
   for (size_t i = 0; i < leaves.size (); i++) cp[i] = count[leaves[i]];
   int32_t split[256];
-  int r = gfsb200_comm_splitters (cp.data (), (int32_t) leaves.size (), nranks, split);
-  if (r) return r;
+  if (cum)
+    splitters_by_share (cp.data (), (int32_t) leaves.size (), nranks, cum, split);
+  else {
+    int r = gfsb200_comm_splitters (cp.data (), (int32_t) leaves.size (), nranks, split);
+    if (r) return r;
+  }
   memset (owner, 255, (size_t) n_cells);
   int q = 0;
   for (size_t i = 0; i < leaves.size (); i++) {
@@ -726,6 +743,51 @@ extern "C" int gfsb200_comm_owner_table (const gfsb200_comm * m, uint8_t * owner
   else
     for (int q = 0; q < m->nranks; q++)
       for (int32_t c = m->split[q]; c < m->split[q + 1]; c++) owner[c] = (uint8_t) q;
+  return GFSB200_OK;
+}
+
+/* the same with unequal target shares: slice r starts where the running count reaches cum[r]*total
+ * (cum[0] = 0 <= cum[1] <= ... <= cum[nranks] = 1) */
+static void splitters_by_share (const uint32_t * count, int32_t n_cells, int nranks, const double * cum, int32_t * split)
+{
+  int64_t total = 0;
+  for (int32_t i = 0; i < n_cells; i++) total += count[i];
+  split[0] = 0;
+  int64_t run = 0;
+  int32_t cell = 0;
+  for (int r = 1; r < nranks; r++) {
+    const int64_t target = (int64_t) ((double) total*cum[r]);
+    while (cell < n_cells && run + count[cell] <= target) run += count[cell++];
+    split[r] = cell;
+  }
+  split[nranks] = n_cells;
+}
+
+/* Target shares of the particles for the NEXT gfsb200_comm_rebalance (share[r] > 0, any scale; NULL:
+ * equal shares again).  Equal numbers of particles are not equal work on an adaptive tree -- a particle
+ * in a deep leaf costs the kernels more than one in a shallow leaf --: a caller that has timed its ranks
+ * hands each one a share inversely proportional to its measured time per particle. */
+extern "C" int gfsb200_comm_set_shares (gfsb200_comm * const * local, int n_local, const double * share)
+{
+  int r = check_local (local, n_local, "comm_set_shares");
+  if (r) return r;
+  const int R = local[0]->nranks;
+  double cum[GFSB200_MAX_RANKS + 1];
+  cum[0] = 0.;
+  if (share) {
+    double sum = 0.;
+    for (int q = 0; q < R; q++) {
+      if (!(share[q] > 0.)) return gfsb200_fail (GFSB200_ERR_ARG, "comm_set_shares: share[%d] is not positive", q);
+      sum += share[q];
+    }
+    double run = 0.;
+    for (int q = 0; q < R; q++) { run += share[q]; cum[q + 1] = run/sum; }
+    cum[R] = 1.;
+  }
+  for (int k = 0; k < n_local; k++) {
+    local[k]->shares_set = share != NULL;
+    if (share) memcpy (local[k]->share_cum, cum, sizeof cum);
+  }
   return GFSB200_OK;
 }
 
@@ -788,7 +850,10 @@ extern "C" int gfsb200_comm_rebalance (gfsb200_comm * const * local, int n_local
     CK (cudaStreamSynchronize (c->stream));
   }
   int32_t split[GFSB200_MAX_RANKS + 1];
-  if ((r = gfsb200_comm_splitters (hist.data (), n_cells, R, split))) return r;
+  const double * cum = local[0]->shares_set ? local[0]->share_cum : NULL;
+  if (cum)
+    splitters_by_share (hist.data (), n_cells, R, cum, split);
+  else if ((r = gfsb200_comm_splitters (hist.data (), n_cells, R, split))) return r;
   /* adaptive trees, several ranks: slices of the depth-first leaf order instead (gfsb200_comm_owner_slices) */
   const bool by_owner = R > 1 && local[0]->c->T.lattice_n1 <= 0 && !getenv ("GFSB200_SLICES_BY_CELL");
   std::vector<uint8_t> owner_of;
@@ -799,7 +864,7 @@ extern "C" int gfsb200_comm_rebalance (gfsb200_comm * const * local, int n_local
     CK (cudaMemcpyAsync (child0.data (), c->T.child0, (size_t) n_cells*sizeof (int32_t), cudaMemcpyDeviceToHost, c->stream));
     CK (cudaStreamSynchronize (c->stream));
     owner_of.resize ((size_t) n_cells);
-    if ((r = gfsb200_comm_owner_slices (child0.data (), n_cells, c->T.n_roots, c->T.dim, hist.data (), R, owner_of.data ())))
+    if ((r = owner_slices (child0.data (), n_cells, c->T.n_roots, c->T.dim, hist.data (), R, cum, owner_of.data ())))
       return r;
     for (int k = 0; k < n_local; k++) {
       gfsb200_comm * m = local[k];

@@ -447,6 +447,11 @@ int gfsb200_broadcast_field (gfsb200_comm * const * local, int n_local, int root
  * all-gather of the slices.  Particle ids travel with the particles; recorded forces do not.
  * Call it where a single GPU would call gfsb200_particles_sort. */
 int gfsb200_comm_rebalance (gfsb200_comm * const * local, int n_local);
+/* Target shares of the particles for the next rebalance: share[r] > 0 for every rank of the job, any
+ * scale (NULL: equal shares, the default).  Equal counts are not equal work on an adaptive tree; a caller
+ * that has timed its ranks (gfsb200_timer_read) hands each one a share inversely proportional to its
+ * measured time per particle. */
+int gfsb200_comm_set_shares (gfsb200_comm * const * local, int n_local, const double * share);
 /* the slice boundaries of the last rebalance: split[0 .. size]; GFSB200_ERR_STATE before it, and on
  * adaptive trees with several ranks, where the slices are ranges of the DEPTH-FIRST leaf order (a
  * particle that crosses into a leaf of another level stays near its rank's slice; in the level-ordered
