@@ -143,6 +143,24 @@ def main():
     for k in range(4):
         a, b = ctx.download_deposit(k), ref.download_deposit(k)
         assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max(), k
+    # unequal target shares (a caller that has timed its ranks): the counts follow them
+    want = np.linspace(1.0, 2.0, size)
+    comm.set_shares(want)
+    comm.rebalance()
+    counts = [None] * size
+    dist.all_gather_object(counts, int(ctx.count))
+    frac = np.array(counts, dtype=float) / sum(counts)
+    assert np.abs(frac - want / want.sum()).max() <= 0.02, (frac, want / want.sum())
+    owner = comm.owner_table(w.arrays.n_cells)
+    now = ctx.particles_download()
+    cc = ctx.locate(now["x"], now["y"], now["z"])
+    assert np.all(owner[cc] == rank)
+    ref.step(par); ref.deposit_all(par)
+    ctx.step(par_f); comm.deposit_allreduce()
+    for k in range(4):
+        a, b = ctx.download_deposit(k), ref.download_deposit(k)
+        assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max(), k
+    comm.set_shares(None)
     ms, n, sent = comm.exchange_stats()
     dist.barrier()
     if rank == 0:
