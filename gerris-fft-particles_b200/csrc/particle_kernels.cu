@@ -648,7 +648,7 @@ __device__ __forceinline__ double * owner_base (const DevDeposit & D, int cell)
     /* adaptive trees: slices of the depth-first leaf order, looked up per cell (one byte; only the
        head of a run of equal cells gets here) */
     const int r = D.owner_of[cell];
-    return r == D.self ? D.local : D.peers->base[r];
+    return r == D.self || r >= D.peers->n ? D.local : D.peers->base[r];     /* (255: not a leaf -- never reached) */
   }
   if (cell >= D.own_lo && cell < D.own_hi)
     return D.local;
